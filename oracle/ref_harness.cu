@@ -1,0 +1,274 @@
+// ref_harness -- drives the UNMODIFIED reference (tiny-cuda-nn, compiled from /root/reference by
+// oracle/Makefile into oracle/_ref/) through its own public C++ API.
+//
+// TEST / MEASUREMENT INFRASTRUCTURE ONLY. Nothing under tiny-cuda-nn_b200/ links or calls this.
+// Two jobs:
+//   dump   write golden vectors (inputs, initial params, encoded features, outputs, losses,
+//          gradients, post-step params) for tests/golden/ -- see tests/golden/make_golden.sh
+//   bench  time trainer->training_step / network->inference with CUDA events for the
+//          `bench.py --impl reference` arm (jit on / jit off / CutlassMLP via the JSON config)
+//   probe  print the per-level grid scale / resolution as evaluated on the device with the
+//          reference's build flags next to the host evaluation (SURVEY.md §7 "hard parts")
+//
+// API used: tcnn::create_from_config (config.h:53), Trainer::training_step / loss (trainer.h:254,372),
+// NetworkWithInputEncoding::inference / encoding() (object.h:214, network_with_input_encoding.h:169),
+// generate_random_uniform (random.h:69).
+#include <tiny-cuda-nn/common_device.h>
+#include <tiny-cuda-nn/config.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+using namespace tcnn;
+using precision_t = network_precision_t;
+
+static json load_json(const std::string& path) {
+	std::ifstream f{path};
+	if (!f) {
+		throw std::runtime_error{"cannot open " + path};
+	}
+	return json::parse(f, nullptr, true, true);
+}
+
+template <typename T>
+static void write_bin(const std::string& path, const T* dev, size_t n) {
+	std::vector<T> h(n);
+	CUDA_CHECK_THROW(cudaMemcpy(h.data(), dev, n * sizeof(T), cudaMemcpyDeviceToHost));
+	std::ofstream f{path, std::ios::binary};
+	f.write((const char*)h.data(), n * sizeof(T));
+}
+
+template <typename T>
+static void write_host_bin(const std::string& path, const std::vector<T>& h) {
+	std::ofstream f{path, std::ios::binary};
+	f.write((const char*)h.data(), h.size() * sizeof(T));
+}
+
+// Closed-form smooth target field in [0,1]^n_out, evaluated on the host in fp32. The same expression
+// is restated in tiny-cuda-nn_b200 (bench / tests) so that both arms train on identical data.
+static void make_targets(const std::vector<float>& x, uint32_t n_in, uint32_t n_out, uint32_t B, std::vector<float>& y) {
+	y.resize((size_t)n_out * B);
+	for (uint32_t i = 0; i < B; ++i) {
+		for (uint32_t c = 0; c < n_out; ++c) {
+			float phase = 0.0f;
+			for (uint32_t d = 0; d < n_in; ++d) {
+				phase += x[(size_t)i * n_in + d] * (float)(c + 1 + d) / (float)(1u << d);
+			}
+			y[(size_t)i * n_out + c] = 0.5f + 0.5f * sinf(6.2831853f * phase);
+		}
+	}
+}
+
+__global__ void probe_scales(uint32_t n_levels, float log2_per_level_scale, uint32_t base_resolution, float* scales, uint32_t* resolutions) {
+	const uint32_t l = threadIdx.x;
+	if (l >= n_levels) return;
+	const float s = grid_scale(l, log2_per_level_scale, base_resolution);
+	scales[l] = s;
+	resolutions[l] = grid_resolution(s);
+}
+
+static int cmd_probe(int argc, char** argv) {
+	const float per_level_scale = argc > 2 ? (float)atof(argv[2]) : 1.5f;
+	const uint32_t base = argc > 3 ? atoi(argv[3]) : 16;
+	const uint32_t L = argc > 4 ? atoi(argv[4]) : 16;
+	GPUMemory<float> s(L);
+	GPUMemory<uint32_t> r(L);
+	const float l2 = std::log2(per_level_scale);
+	probe_scales<<<1, 128>>>(L, l2, base, s.data(), r.data());
+	std::vector<float> hs(L);
+	std::vector<uint32_t> hr(L);
+	s.copy_to_host(hs);
+	r.copy_to_host(hr);
+	printf("{\"per_level_scale\": %.9g, \"base\": %u, \"levels\": [", per_level_scale, base);
+	for (uint32_t l = 0; l < L; ++l) {
+		const float host = grid_scale(l, l2, base);
+		uint32_t db, hb;
+		memcpy(&db, &hs[l], 4);
+		memcpy(&hb, &host, 4);
+		printf("%s{\"level\": %u, \"dev_scale\": %.9g, \"dev_bits\": %u, \"dev_res\": %u, \"host_scale\": %.9g, \"host_bits\": %u, \"host_res\": %u}", l ? ", " : "", l, hs[l], db, hr[l], host, hb, grid_resolution(host));
+	}
+	printf("]}\n");
+	return 0;
+}
+
+struct Setup {
+	json config;
+	uint32_t n_in, n_out, B;
+	TrainableModel model;
+	GPUMatrix<float> x, y;
+	std::vector<float> hx, hy;
+};
+
+static void make_setup(Setup& s, const std::string& config_path, uint32_t n_in, uint32_t n_out, uint32_t B, bool jit, uint32_t input_seed = 1337) {
+	s.config = load_json(config_path);
+	s.n_in = n_in;
+	s.n_out = n_out;
+	s.B = B;
+	s.model = create_from_config(n_in, n_out, s.config);
+	s.model.network->set_jit_fusion(jit && tcnn::supports_jit_fusion());
+	s.x = GPUMatrix<float>(n_in, B);
+	s.y = GPUMatrix<float>(n_out, B);
+	default_rng_t rng{input_seed};
+	generate_random_uniform<float>(nullptr, rng, (size_t)B * n_in, s.x.data());
+	s.hx.resize((size_t)B * n_in);
+	CUDA_CHECK_THROW(cudaMemcpy(s.hx.data(), s.x.data(), s.hx.size() * sizeof(float), cudaMemcpyDeviceToHost));
+	make_targets(s.hx, n_in, n_out, B, s.hy);
+	CUDA_CHECK_THROW(cudaMemcpy(s.y.data(), s.hy.data(), s.hy.size() * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+// dump <config.json> <n_in> <n_out> <B> <n_steps> <outdir> <jit 0|1>
+static int cmd_dump(int argc, char** argv) {
+	if (argc < 9) {
+		fprintf(stderr, "usage: dump config n_in n_out B n_steps outdir jit\n");
+		return 2;
+	}
+	const std::string outdir = argv[7];
+	mkdir(outdir.c_str(), 0755);
+	Setup s;
+	make_setup(s, argv[2], atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[8]) != 0);
+	const uint32_t n_steps = atoi(argv[6]);
+	auto& trainer = s.model.trainer;
+	auto& network = s.model.network;
+	const size_t n_params = trainer->n_params();
+	const uint32_t B = s.B;
+
+	write_host_bin(outdir + "/x.f32", s.hx);
+	write_host_bin(outdir + "/y.f32", s.hy);
+	write_bin(outdir + "/params_init.f32", trainer->params_full_precision(), n_params);
+
+	// Encoded features exactly as the MLP consumes them (padded width, preferred layout = SoA for grids).
+	auto enc = network->encoding();
+	GPUMatrixDynamic<precision_t> encoded{enc->padded_output_width(), B, nullptr, enc->preferred_output_layout()};
+	enc->inference_mixed_precision(nullptr, s.x, encoded, true);
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	write_bin(outdir + "/encoded.f16", (const uint16_t*)encoded.data(), (size_t)enc->padded_output_width() * B);
+
+	// fp32 inference output (n_out x B column-major == [B][n_out]).
+	GPUMatrix<float> pred(s.n_out, B);
+	network->inference(nullptr, s.x, pred);
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	write_bin(outdir + "/inference.f32", pred.data(), (size_t)s.n_out * B);
+
+	// One fwd+bwd without optimizer: padded fp16 output, loss values, fp16 gradients.
+	std::vector<float> losses;
+	{
+		auto ctx = trainer->training_step(nullptr, s.x, s.y, nullptr, /*run_optimizer=*/false);
+		CUDA_CHECK_THROW(cudaDeviceSynchronize());
+		if (ctx->output.data()) {
+			write_bin(outdir + "/output.f16", (const uint16_t*)ctx->output.data(), (size_t)network->padded_output_width() * B);
+		}
+		write_bin(outdir + "/loss_values.f32", ctx->L.data(), ctx->L.n_elements());
+		write_bin(outdir + "/grads_step0.f16", (const uint16_t*)trainer->param_gradients(), n_params);
+		losses.push_back(trainer->loss(nullptr, *ctx));
+	}
+
+	// n_steps full training steps on the same batch.
+	for (uint32_t i = 0; i < n_steps; ++i) {
+		auto ctx = trainer->training_step(nullptr, s.x, s.y);
+		losses.push_back(trainer->loss(nullptr, *ctx));
+		if (i == 0) {
+			CUDA_CHECK_THROW(cudaDeviceSynchronize());
+			write_bin(outdir + "/params_step1.f32", trainer->params_full_precision(), n_params);
+		}
+	}
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	write_bin(outdir + "/params_final.f32", trainer->params_full_precision(), n_params);
+	write_bin(outdir + "/params_final.f16", (const uint16_t*)trainer->params(), n_params);
+	network->inference(nullptr, s.x, pred);
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	write_bin(outdir + "/inference_final.f32", pred.data(), (size_t)s.n_out * B);
+
+	json meta;
+	meta["config"] = s.config;
+	meta["n_in"] = s.n_in;
+	meta["n_out"] = s.n_out;
+	meta["batch"] = B;
+	meta["n_steps"] = n_steps;
+	meta["n_params"] = n_params;
+	meta["n_encoding_params"] = enc->n_params();
+	meta["encoded_width"] = enc->padded_output_width();
+	meta["encoded_layout"] = enc->preferred_output_layout() == SoA ? "SoA" : "AoS";
+	meta["padded_output_width"] = network->padded_output_width();
+	meta["jit_fusion"] = network->jit_fusion();
+	meta["loss_n_elements"] = losses.empty() ? 0 : 1;
+	meta["losses"] = losses;
+	meta["hyperparams"] = network->hyperparams();
+	std::ofstream f{outdir + "/meta.json"};
+	f << meta.dump(1) << std::endl;
+	printf("dumped %s: n_params=%zu losses[0]=%g losses[last]=%g jit=%d\n", outdir.c_str(), n_params, losses.front(), losses.back(), (int)network->jit_fusion());
+	return 0;
+}
+
+// bench <config.json> <n_in> <n_out> <B> <steps> <warmup> <jit 0|1> [inference 0|1]
+static int cmd_bench(int argc, char** argv) {
+	if (argc < 9) {
+		fprintf(stderr, "usage: bench config n_in n_out B steps warmup jit [inference]\n");
+		return 2;
+	}
+	Setup s;
+	make_setup(s, argv[2], atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[8]) != 0);
+	const uint32_t steps = atoi(argv[6]), warmup = atoi(argv[7]);
+	const bool inference = argc > 9 && atoi(argv[9]) != 0;
+	auto& trainer = s.model.trainer;
+	auto& network = s.model.network;
+	cudaStream_t stream;
+	CUDA_CHECK_THROW(cudaStreamCreate(&stream));
+	GPUMatrix<float> pred(s.n_out, s.B);
+
+	auto one = [&]() {
+		if (inference) {
+			network->inference(stream, s.x, pred);
+		} else {
+			trainer->training_step(stream, s.x, s.y);
+		}
+	};
+	for (uint32_t i = 0; i < warmup; ++i) one();
+	CUDA_CHECK_THROW(cudaStreamSynchronize(stream));
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	auto w0 = std::chrono::steady_clock::now();
+	cudaEventRecord(e0, stream);
+	for (uint32_t i = 0; i < steps; ++i) one();
+	cudaEventRecord(e1, stream);
+	CUDA_CHECK_THROW(cudaStreamSynchronize(stream));
+	auto w1 = std::chrono::steady_clock::now();
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e0, e1);
+	const double wall_ms = std::chrono::duration<double, std::milli>(w1 - w0).count();
+	float final_loss = -1.0f;
+	if (!inference) {
+		auto ctx = trainer->training_step(stream, s.x, s.y);
+		final_loss = trainer->loss(stream, *ctx);
+	}
+	printf("{\"impl\": \"reference\", \"mode\": \"%s\", \"jit_fusion\": %s, \"network\": \"%s\", \"batch\": %u, \"steps\": %u, \"warmup\": %u, \"ms_per_step\": %.6f, \"wall_ms_per_step\": %.6f, \"samples_per_s\": %.6e, \"n_params\": %zu, \"final_loss\": %.6g}\n",
+		inference ? "inference" : "training_step", network->jit_fusion() ? "true" : "false",
+		s.config.value("network", json::object()).value("otype", "MLP").c_str(),
+		s.B, steps, warmup, ms / steps, wall_ms / steps, (double)s.B * steps / (ms * 1e-3), trainer->n_params(), final_loss);
+	return 0;
+}
+
+int main(int argc, char** argv) {
+	try {
+		if (argc < 2) {
+			fprintf(stderr, "usage: %s dump|bench|probe ...\n", argv[0]);
+			return 2;
+		}
+		const std::string cmd = argv[1];
+		if (cmd == "dump") return cmd_dump(argc, argv);
+		if (cmd == "bench") return cmd_bench(argc, argv);
+		if (cmd == "probe") return cmd_probe(argc, argv);
+		fprintf(stderr, "unknown command %s\n", cmd.c_str());
+		return 2;
+	} catch (const std::exception& e) {
+		fprintf(stderr, "ref_harness: uncaught exception: %s\n", e.what());
+		return 1;
+	}
+}
