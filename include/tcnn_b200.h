@@ -1,0 +1,118 @@
+/* tcnn_b200.h -- C ABI of the Blackwell-native HashGrid + FullyFusedMLP hot path.
+ *
+ * This is the drop-in boundary: plain C, opaque handles, raw device/host pointers, no torch / C++ types.
+ * Each entry point names the reference interface (file:line relative to tiny-cuda-nn's tree) it replaces.
+ * The reference's own boundary is C++ in two tiers; this ABI carries both:
+ *   - "trainer tier"  == tcnn::create_from_config / Trainer / NetworkWithInputEncoding  (config.h:46-63,
+ *                        trainer.h:51-532, network_with_input_encoding.h:42-150)
+ *   - "module tier"   == tcnn::cpp::Module, the type-erased API the PyTorch extension binds (cpp_api.h:48-125)
+ * the headers under include/tiny-cuda-nn/ (header-only C++ shim over this ABI) restores the reference's C++ names on top.
+ *
+ * Conventions (identical to the reference):
+ *   - inputs are fp32, sample-contiguous: [batch][n_input_dims] == column-major n_input_dims x batch (gpu_matrix.h:226-228)
+ *   - batch sizes must be multiples of 256 (common.h:246, object.h:169)
+ *   - parameters are one flat buffer [MLP weights | grid table] (network_with_input_encoding.h:115-130), the trainer
+ *     owns [fp32 master | fp16 params | fp16 gradients] (trainer.h:489-503)
+ *   - all work is stream-ordered on the caller's stream; nothing synchronises except tcnnb_loss and *_host calls
+ *   - errors: every call returns 0 on success, non-zero on failure; tcnnb_last_error() returns the message the
+ *     reference would have thrown as std::runtime_error (common_host.h:71-110). There is NO CPU fallback.
+ */
+#ifndef TCNN_B200_H
+#define TCNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tcnnb_model tcnnb_model;   /* TrainableModel{loss, optimizer, network, trainer}  (config.h:46-51) */
+typedef void* tcnnb_stream;               /* cudaStream_t */
+
+/* ---- library-level (cpp_api.h:59-86) ---- */
+const char* tcnnb_last_error(void);
+uint32_t tcnnb_batch_size_granularity(void);             /* cpp_api.h:61  -> 256 */
+float tcnnb_default_loss_scale(void);                    /* cpp_api.h:67 / common.h:243 -> 128 for fp16 */
+int tcnnb_cuda_device(void);                             /* cpp_api.h:63 */
+int tcnnb_set_cuda_device(int device);                   /* cpp_api.h:64 */
+uint32_t tcnnb_abi_version(void);
+
+/* ---- construction: tcnn::create_from_config(n_input_dims, n_output_dims, json) + Trainer(..., seed) ----
+ * config.h:53-63, trainer.h:51-87. `config_json` is the same JSON document the reference parses
+ * ({"loss":{}, "optimizer":{}, "encoding":{}, "network":{}}, keys and defaults per src/encoding.cu, src/network.cu,
+ * src/loss.cu, src/optimizer.cu). Parameters are initialised exactly like the reference (same pcg32 streams).
+ * Unsupported otypes fail loudly. */
+int tcnnb_create_from_config(uint32_t n_input_dims, uint32_t n_output_dims, const char* config_json, uint32_t seed, tcnnb_model** out);
+void tcnnb_destroy(tcnnb_model* model);
+
+/* ---- introspection (network_with_input_encoding.h:132-150, trainer.h:385-407,477-482) ---- */
+uint64_t tcnnb_n_params(const tcnnb_model* m);                 /* trainer->n_params() */
+uint64_t tcnnb_n_mlp_params(const tcnnb_model* m);             /* network part; grid params follow */
+uint32_t tcnnb_n_input_dims(const tcnnb_model* m);
+uint32_t tcnnb_n_output_dims(const tcnnb_model* m);            /* network->output_width() */
+uint32_t tcnnb_padded_output_width(const tcnnb_model* m);      /* network->padded_output_width() */
+uint32_t tcnnb_encoded_width(const tcnnb_model* m);            /* encoding->padded_output_width() */
+float* tcnnb_params_full_precision(tcnnb_model* m);            /* trainer->params_full_precision(): device fp32 [n_params] */
+void* tcnnb_params(tcnnb_model* m);                            /* trainer->params(): device fp16 [n_params] */
+void* tcnnb_param_gradients(tcnnb_model* m);                   /* trainer->param_gradients(): device fp16 [n_params] */
+/* Level table of the grid encoding: offsets in entries (n_levels+1), per-level scale and resolution (grid.h:692-737). */
+int tcnnb_grid_levels(const tcnnb_model* m, uint32_t* n_levels, uint32_t* offsets, float* scales, uint32_t* resolutions);
+/* JSON with the resolved hyper-parameters (object.h hyperparams()); pointer valid until the next call on this model. */
+const char* tcnnb_hyperparams(tcnnb_model* m);
+
+/* ---- trainer->set_params_full_precision / set_params (trainer.h:409-440) ---- */
+int tcnnb_set_params_full_precision(tcnnb_model* m, const float* params, uint64_t n, int device_ptr);
+
+/* ---- trainer->training_step(stream, input, target, ..., run_optimizer) (trainer.h:254-357) ----
+ * input_dev [batch][n_in] fp32, target_dev [batch][n_out] fp32, both device pointers.
+ * Runs fwd + loss + bwd (+ Adam when run_optimizer != 0). The loss of this step is fetched with tcnnb_loss. */
+int tcnnb_training_step(tcnnb_model* m, tcnnb_stream stream, uint32_t batch_size, const float* input_dev, const float* target_dev, int run_optimizer);
+/* Data-parallel variant: this rank's shard of a global batch; the loss is normalised over global_batch_size
+ * (loss n_total, relative_l2.h:62) so that gradient sums over ranks equal the single-GPU gradients. */
+int tcnnb_training_step_shard(tcnnb_model* m, tcnnb_stream stream, uint32_t shard_batch_size, uint32_t global_batch_size, const float* input_dev, const float* target_dev, int run_optimizer);
+/* trainer->optimizer_step(stream, loss_scale) (trainer.h:155-157): Adam on the current gradient buffers. */
+int tcnnb_optimizer_step(tcnnb_model* m, tcnnb_stream stream);
+/* Device pointer + element count of the fp32 accumulator that holds the MLP weight gradients between the backward
+ * pass and the optimizer (for the data-parallel all-reduce); the grid gradients are tcnnb_param_gradients(). */
+float* tcnnb_mlp_gradient_accumulator(tcnnb_model* m);
+/* trainer->loss(stream, ctx) (trainer.h:372-378, reduce_sum.h:132-146): sum of the loss values of the last step;
+ * synchronises the stream. */
+int tcnnb_loss(tcnnb_model* m, tcnnb_stream stream, float* loss_out);
+
+/* ---- network->inference(stream, input, output) (object.h:214-282): fp32 [batch][n_out] ---- */
+int tcnnb_inference(tcnnb_model* m, tcnnb_stream stream, uint32_t batch_size, const float* input_dev, float* output_dev);
+
+/* ---- host-buffer entry points (what a foreign-language binding calls with its own arrays) ----
+ * Copies inputs host->device (pinned staging inside the model), runs the step, copies the loss / outputs back and
+ * synchronises. */
+int tcnnb_training_step_host(tcnnb_model* m, uint32_t batch_size, const float* input_host, const float* target_host, float* loss_out);
+int tcnnb_inference_host(tcnnb_model* m, uint32_t batch_size, const float* input_host, float* output_host);
+
+/* ---- trainer->serialize / deserialize (trainer.h:442-482): fp16 params (+ optional Adam state) as raw bytes ---- */
+uint64_t tcnnb_serialize_size(const tcnnb_model* m, int with_optimizer);
+int tcnnb_serialize(tcnnb_model* m, void* dst_host, uint64_t size, int with_optimizer);
+int tcnnb_deserialize(tcnnb_model* m, const void* src_host, uint64_t size);
+
+/* ---- test / profiling taps: per-sample intermediates of the fused kernel (null = off). Not part of the drop-in surface. */
+typedef struct {
+	void* encoded;        /* fp16 [batch][64] */
+	void* hidden;         /* fp16 [n_hidden][batch][64] */
+	void* output;         /* fp16 [batch][16] */
+	void* dL_doutput;     /* fp16 [batch][16] */
+	void* grad_hidden;    /* fp16 [n_hidden][batch][64] */
+	void* dL_dencoded;    /* fp16 [batch][64] */
+	float* loss_values;   /* fp32 [batch][n_out] */
+} tcnnb_debug_taps;
+int tcnnb_set_debug_taps(tcnnb_model* m, const tcnnb_debug_taps* taps);
+/* Per-kernel device timing for the roofline report: when enabled, CUDA events bracket the fused fwd+bwd kernel and the
+ * optimizer kernel of every training step on the caller's stream; tcnnb_read_profile synchronises and returns the sums. */
+int tcnnb_set_profiling(tcnnb_model* m, int enable);
+int tcnnb_read_profile(tcnnb_model* m, float* fused_ms_total, float* optimizer_ms_total, uint32_t* n_steps);
+/* Number of kernels this library launched since load (bench.py's gpu_launches). */
+uint64_t tcnnb_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

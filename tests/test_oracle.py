@@ -1,0 +1,171 @@
+"""CPU tests of the oracle (the restatement of the reference) against the reference's own known answers and against
+size-independent properties. No GPU needed."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+
+HEADLINE = {
+    "loss": {"otype": "RelativeL2"},
+    "optimizer": {"otype": "Adam", "learning_rate": 1e-2, "beta1": 0.9, "beta2": 0.99, "epsilon": 1e-15, "l2_reg": 1e-6},
+    "encoding": {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 19, "base_resolution": 16, "per_level_scale": 1.5},
+    "network": {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None", "n_neurons": 64, "n_hidden_layers": 2},
+}
+SMALL = {**HEADLINE, "encoding": {**HEADLINE["encoding"], "log2_hashmap_size": 12}}
+
+
+def test_pcg32_known_answers(oracle):
+    # PCG reference demo vectors (pcg32_srandom(42, 54)): the published first outputs of PCG-XSH-RR 64/32.
+    rng = ob.Pcg32()
+    oracle.orc_pcg32_seed(ctypes.byref(rng), ctypes.c_uint64(42), ctypes.c_uint64(54))
+    got = [oracle.orc_pcg32_next_uint(ctypes.byref(rng)) for _ in range(6)]
+    assert got == [0xA15C02B7, 0x7B47F409, 0xBA1D3330, 0x83D2F293, 0xBFA4784B, 0xCBED606E]
+
+
+def test_pcg32_advance_matches_stepping(oracle):
+    a, b = ob.default_rng(1337), ob.default_rng(1337)
+    for _ in range(1000):
+        oracle.orc_pcg32_next_uint(ctypes.byref(a))
+    oracle.orc_pcg32_advance(ctypes.byref(b), ctypes.c_int64(1000))
+    assert (a.state, a.inc) == (b.state, b.inc)
+
+
+def test_generate_random_uniform_layout(oracle):
+    # random.h:40-69: element idx = i + n_threads*j is the j-th draw of thread i which jumped ahead 4*i draws.
+    n = 1000
+    rng = ob.default_rng(7)
+    out = ob.generate_random_uniform(rng, n)
+    n_threads = ((n + 3) // 4 + 127) // 128 * 128
+    seq = ob.default_rng(7)
+    draws = np.array([oracle.orc_pcg32_next_float(ctypes.byref(seq)) for _ in range(4 * n_threads)], np.float32)
+    for idx in (0, 1, 127, 128, 511, 512, 999):
+        i, j = idx % n_threads, idx // n_threads
+        assert out[idx] == draws[4 * i + j]
+    assert ((out >= 0) & (out < 1)).all()
+    # the generator state advanced by exactly n
+    ref = ob.default_rng(7)
+    oracle.orc_pcg32_advance(ctypes.byref(ref), ctypes.c_int64(n))
+    assert rng.state == ref.state
+
+
+def test_grid_sizing_known_answer(oracle):
+    # tests/test_grid.cu:37-71 of the reference: base 32, T=2^16, F=2, L=20, scale 1.5, 3-D.
+    g = ob.Grid(3, 20, 2, 16, 32, 1.5, ob.GRID_HASH, ob.INTERP_LINEAR, 0)
+    assert oracle.orc_grid_setup(ctypes.byref(g)) == 0
+    assert g.padded_width == 48 and 20 * 2 == 40  # padded_output_width == 40 at alignment 1; 48 at the MLP's alignment 16
+    assert g.offsets[0] == 0 and g.offsets[1] == 32768 and g.offsets[2] == 98304
+    assert g.offsets[2] - g.offsets[1] == 65536 and g.offsets[3] - g.offsets[2] == 65536
+    assert g.n_params == 2555904
+
+
+def test_headline_sizing(oracle):
+    m = ob.OracleModel.__new__(ob.OracleModel)
+    g = ob.Grid(3, 16, 2, 19, 16, 1.5, ob.GRID_HASH, ob.INTERP_LINEAR, 0)
+    oracle.orc_grid_setup(ctypes.byref(g))
+    assert list(g.resolutions[:16]) == [16, 24, 36, 54, 81, 122, 183, 274, 411, 616, 923, 1384, 2076, 3114, 4671, 7007]
+    sizes = [g.offsets[i + 1] - g.offsets[i] for i in range(16)]
+    assert sizes[:4] == [4096, 13824, 46656, 157464] and all(s == 524288 for s in sizes[4:])
+    assert g.n_params == 13026992
+    g2 = ob.Grid(3, 16, 2, 19, 16, 2.0, ob.GRID_HASH, ob.INTERP_LINEAR, 0)
+    oracle.orc_grid_setup(ctypes.byref(g2))
+    assert g2.n_params == 14229504
+
+
+def test_xavier_init_statistics():
+    m = ob.OracleModel(3, 3, SMALL)
+    assert m.n_mlp == 64 * 32 + 64 * 64 + 16 * 64 == 7168
+    w0 = m.params_fp32[: 64 * 32]
+    w1 = m.params_fp32[64 * 32 : 64 * 32 + 64 * 64]
+    w2 = m.params_fp32[64 * 32 + 64 * 64 : 7168]
+    for w, s in ((w0, 0.25), (w1, np.sqrt(6 / 128)), (w2, np.sqrt(6 / 80))):
+        assert np.abs(w).max() <= s and np.abs(w).max() > 0.95 * s
+    grid = m.params_fp32[7168:]
+    assert np.abs(grid).max() <= 1e-4 and abs(grid.mean()) < 2e-6
+
+
+def test_hash_index_properties():
+    # coherent_prime_hash multiplies x by 1: for even cell x, hash(x+1,y,z) == hash(x,y,z) ^ 1 -- checked through
+    # the oracle's index output on a hashed level; and dense levels index x + y*res + z*res^2 (mod size).
+    m = ob.OracleModel(3, 3, SMALL)
+    rng = ob.default_rng(3)
+    x = ob.generate_random_uniform(rng, 256 * 3).reshape(256, 3)
+    _, idx = m.encode(x, want_indices=True)
+    g = m.grid
+    for level in (0, 5, 15):
+        scale = g.scales[level]
+        res = int(np.ceil(scale)) + 1
+        size = g.offsets[level + 1] - g.offsets[level]
+        p = (np.float32(scale) * x + np.float32(0.5)).astype(np.float32)
+        cell = np.floor(p).astype(np.int64)
+        if level == 0:
+            want = (cell[:, 0] + cell[:, 1] * res + cell[:, 2] * res * res) % size
+        else:
+            want = ((cell[:, 0] * 1) ^ ((cell[:, 1] * 2654435761) & 0xFFFFFFFF) ^ ((cell[:, 2] * 805459861) & 0xFFFFFFFF)) % size
+            even = cell[:, 0] % 2 == 0
+            assert ((idx[even, level, 0] ^ 1) == idx[even, level, 1]).all()
+        assert (idx[:, level, 0] == want).all()
+
+
+def test_encoding_is_linear_in_table():
+    # Size-independent property: with a table that is constant per level, the N-linear blend returns that constant
+    # (weights sum to 1) up to fp16 rounding of the 8 partial sums.
+    m = ob.OracleModel(3, 3, SMALL)
+    p = m.params_fp32.copy()
+    off = m.n_mlp
+    for level in range(16):
+        a, b = m.grid.offsets[level] * 2, m.grid.offsets[level + 1] * 2
+        p[off + a : off + b] = 0.001 * (level + 1)
+    m.set_params_full_precision(p)
+    rng = ob.default_rng(11)
+    x = ob.generate_random_uniform(rng, 512 * 3).reshape(512, 3)
+    enc = ob.half_bits_to_float(m.encode(x))
+    for level in range(16):
+        assert np.allclose(enc[2 * level], 0.001 * (level + 1), rtol=4e-3)
+
+
+def test_training_reduces_loss_and_accum_modes_agree():
+    rng = ob.default_rng(1337)
+    x = ob.generate_random_uniform(rng, 512 * 3).reshape(512, 3)
+    y = ob.make_targets(x, 3)
+    losses = {}
+    for mode in (ob.ACCUM_FP32, ob.ACCUM_FP16_K16):
+        m = ob.OracleModel(3, 3, SMALL, accum_mode=mode)
+        ls = [m.training_step(x, y) for _ in range(12)]
+        assert ls[-1] < 0.7 * ls[0]
+        losses[mode] = ls
+    assert abs(losses[0][0] - losses[1][0]) < 1e-2 * losses[0][0]
+
+
+def test_adam_skips_zero_gradient_grid_params():
+    m = ob.OracleModel(3, 3, SMALL)
+    rng = ob.default_rng(5)
+    x = ob.generate_random_uniform(rng, 256 * 3).reshape(256, 3)
+    y = ob.make_targets(x, 3)
+    before = m.params_fp32.copy()
+    m.training_step(x, y)
+    g = ob.half_bits_to_float(m.grads_fp16)[m.n_mlp :]
+    untouched = g == 0
+    assert untouched.any() and (~untouched).any()
+    assert np.array_equal(before[m.n_mlp :][untouched], m.params_fp32[m.n_mlp :][untouched])  # adam.h:79-82
+    assert (m.steps[m.n_mlp :][untouched] == 0).all() and (m.steps[m.n_mlp :][~untouched] == 1).all()
+    assert (m.steps[: m.n_mlp] == 1).all()  # matrix params always step (l2_reg)
+
+
+def test_loss_gradient_matches_finite_difference():
+    # relative_l2.h:64-75: grad = loss_scale * d(value)/d(pred) with the denominator treated as constant.
+    B, stride, dims = 256, 16, 3
+    rs = np.random.RandomState(0)
+    pred = rs.uniform(-1, 1, (B, stride)).astype(np.float16)
+    tgt = rs.uniform(0, 1, (B, dims)).astype(np.float32)
+    lib = ob.load()
+    values = np.zeros((B, stride), np.float32)
+    grads = np.zeros((B, stride), np.uint16)
+    lib.orc_loss(ob.LOSS_RELATIVE_L2, B, stride, dims, ctypes.c_float(128.0), ob._p(pred.view(np.uint16)), ob._p(tgt), ob._p(values), ob._p(grads))
+    g = ob.half_bits_to_float(grads)
+    p32 = pred.astype(np.float32)[:, :dims]
+    expect = 128.0 * 2 * (p32 - tgt) / (p32 * p32 + 0.01) / (B * dims)
+    assert np.allclose(g[:, :dims], expect, rtol=2e-3, atol=1e-7)
+    assert (g[:, dims:] == 0).all() and (values[:, dims:] == 0).all()
+    assert np.allclose(values[:, :dims], (p32 - tgt) ** 2 / (p32 * p32 + 0.01) / (B * dims), rtol=1e-5)

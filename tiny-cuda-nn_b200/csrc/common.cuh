@@ -1,0 +1,43 @@
+// common.cuh -- shared device/host declarations for the tcnn_b200 kernels.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tcnnb {
+
+constexpr uint32_t MAX_LEVELS = 32;            // levels handled by the by-value kernel argument (L*F <= 64 on the fused path)
+constexpr uint32_t BATCH_GRANULARITY = 256;    // common.h:246 BATCH_SIZE_GRANULARITY
+constexpr uint32_t TILE_M = 128;               // samples per MMA tile = TMEM lanes
+
+// Same numeric values as the reference enums (common.h:133-164).
+enum Activation : uint32_t { ACT_RELU = 0, ACT_LEAKY_RELU = 1, ACT_SILU = 2, ACT_EXPONENTIAL = 3, ACT_SINE = 4, ACT_SIGMOID = 5, ACT_SQUAREPLUS = 6, ACT_SOFTPLUS = 7, ACT_TANH = 8, ACT_NONE = 9 };
+enum GridType : uint32_t { GRID_HASH = 0, GRID_DENSE = 1, GRID_TILED = 2 };
+enum InterpolationType : uint32_t { INTERP_NEAREST = 0, INTERP_LINEAR = 1, INTERP_SMOOTHSTEP = 2 };
+enum LossType : uint32_t { LOSS_L2 = 0, LOSS_RELATIVE_L2 = 1 };
+
+// One resolution level of the multiresolution grid, precomputed on the host from the reference's sizing rule
+// (grid.h:692-737) with the per-level scale evaluated ON THE DEVICE by eval_level_scales() so that it carries the
+// same bits as the reference's in-kernel grid_scale() (common_device.h:886-891, fast-math ex2.approx + fma).
+struct LevelInfo {
+	uint32_t offset;      // first entry of this level in the table (entries, not params)
+	uint32_t size;        // number of entries ("hashmap_size", grid.h:92)
+	float scale;          // grid_scale(level)
+	uint32_t resolution;  // grid_resolution(scale)
+	uint32_t use_hash;    // grid_type == Hash && size < dense stride (common_device.h:880)
+	uint32_t pow2_mask;   // size - 1 if size is a power of two, else 0 (index % size == index & mask)
+};
+
+struct GridMeta {
+	uint32_t n_levels;
+	uint32_t n_features;    // n_levels * F
+	uint32_t padded_width;  // multiple of 16
+	uint32_t interpolation;
+	LevelInfo levels[MAX_LEVELS];
+};
+
+struct Pcg32 {
+	uint64_t state, inc;
+};
+
+}  // namespace tcnnb

@@ -1,0 +1,504 @@
+// fused_step.cu -- the hot path in ONE kernel: HashGrid gather + trilinear blend -> FullyFusedMLP forward (tcgen05)
+// -> loss -> MLP backward (tcgen05: dgrad and wgrad) -> hash-grid gradient scatter (f16x2 reductions).
+//
+// Replaces, for one training step, the reference's kernel_grid (grid.h:49), kernel_mlp_fused (fully_fused_mlp.cu:500),
+// relative_l2_loss / l2_loss (losses/*.h:40), kernel_mlp_fused_backward (fully_fused_mlp.cu:151), the three CUTLASS
+// split-K weight-gradient GEMMs and the dL/d(encoded) GEMM (fully_fused_mlp.cu:784-836) and kernel_grid_backward
+// (grid.h:215). No activation ever leaves the SM: the only HBM/L2 traffic is positions, targets, the fp16 tables
+// (gather), their fp16 gradient tables (red.f16x2) and 7 K fp32 weight-gradient partial sums per CTA.
+//
+// Structure (one CTA = 128 threads = one 128-sample tile at a time, 2 CTAs co-resident per SM):
+//   thread t <-> sample t of the tile <-> row t of every smem operand tile <-> TMEM lane t.
+//   Operand tiles are [128 rows][64 fp16] in the canonical SWIZZLE_128B layout; the SAME bytes are consumed as a
+//   K-major A operand by the forward/dgrad MMAs (M = samples, K = neurons) and as an MN-major operand by the wgrad
+//   MMAs (M/N = neurons, K = samples), so no transposes are ever materialised.
+//   Weights are staged once per CTA: W_l [out][in] row-major is the K-major B operand of the forward MMA and, read
+//   MN-major, the B operand of the dgrad MMA (W_l^T).
+//   Accumulators live in TMEM: ACC (64 columns, reused by every layer) + one 64x64 fp32 wgrad accumulator per weight
+//   matrix that persists across all tiles of the CTA and is flushed once with red.global.add.f32.
+#include "common.cuh"
+#include "fused_step.h"
+#include "grid_device.cuh"
+#include "ptx.cuh"
+
+namespace tcnnb {
+
+using namespace ptx;
+
+namespace {
+
+constexpr uint32_t TILE_BYTES = TILE_M * 128;  // [128][64] fp16
+constexpr uint32_t WIDTH = 64;
+
+// Byte offset of 16-byte chunk `c` (0..7) of row `r` inside a SWIZZLE_128B tile.
+__device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) {
+	return r * 128u + ((c ^ (r & 7u)) << 4);
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+	asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+	asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+	__half2 h = __floats2half2_rn(lo, hi);
+	return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ uint32_t relu_pack(uint32_t lo_bits, uint32_t hi_bits) {
+	// fp32 accumulator -> fp16 (rn) -> ReLU in fp16, as warp_activation<__half> does (common_device.h:115-121).
+	__half2 h = __floats2half2_rn(__uint_as_float(lo_bits), __uint_as_float(hi_bits));
+	h = __hmax2(h, __float2half2_rn(0.0f));
+	return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// gradient (fp32 acc -> fp16) * (forward > 0), warp_activation_backward ReLU (common_device.h:363-368).
+__device__ __forceinline__ uint32_t relu_bwd_pack(uint32_t lo_bits, uint32_t hi_bits, uint32_t fwd_bits) {
+	__half2 g = __floats2half2_rn(__uint_as_float(lo_bits), __uint_as_float(hi_bits));
+	const __half2 f = *reinterpret_cast<const __half2*>(&fwd_bits);
+	const __half2 mask = __hgt2(f, __float2half2_rn(0.0f));  // 1.0 / 0.0
+	g = __hmul2(g, mask);
+	return *reinterpret_cast<uint32_t*>(&g);
+}
+
+struct Smem {
+	// dynamic shared memory, 1024-byte aligned:
+	//   [ enc | h_0 .. h_{NH-1} | gA | gB(=dy) | W_0 | W_1 .. W_{NH-1} | W_out ] then barriers
+	uint32_t enc, h0, gA, gB, w0, w_out, bar, tmem_slot;
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------------
+template <uint32_t D, uint32_t F, bool TRAIN>
+__global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParams p) {
+	extern __shared__ __align__(1024) uint8_t smem_raw[];
+	const uint32_t tid = threadIdx.x;
+	const uint32_t warp = tid >> 5;
+	const uint32_t NH = p.n_hidden_layers;
+	const uint32_t in_w = p.grid.padded_width;
+
+	// ---- shared memory carve-up (all tile bases 1024-aligned)
+	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+	Smem s;
+	s.enc = smem_base;
+	s.h0 = s.enc + TILE_BYTES;
+	s.gA = s.h0 + NH * TILE_BYTES;
+	s.gB = s.gA + (TRAIN ? TILE_BYTES : 0);
+	s.w0 = s.gB + TILE_BYTES;
+	s.w_out = s.w0 + NH * (WIDTH * 128);
+	s.bar = s.w_out + 16 * 128;
+	s.tmem_slot = s.bar + 8;
+
+	// ---- one-time setup: barrier, TMEM, weights
+	const uint32_t tmem_cols = TRAIN ? (NH + 2) * 64 <= 256 ? 256u : 512u : 64u;
+	if (tid == 0) {
+		mbar_init(s.bar, 1);
+		fence_mbar_init();
+	}
+	if (warp == 0) {
+		tmem_alloc(s.tmem_slot, tmem_cols);
+		tmem_relinquish();
+	}
+
+	// Stage the fp16 weights: W_l rows are 128-byte tile rows (K-major, SWIZZLE_128B); unused columns are zeroed.
+	{
+		const __half* __restrict__ w = p.params;  // MLP weights come first in the parameter buffer
+		// first layer: [64][in_w]
+		for (uint32_t i = tid; i < WIDTH * 8; i += 128) {
+			const uint32_t r = i >> 3, c = i & 7;
+			uint4 v = make_uint4(0, 0, 0, 0);
+			if (c * 8 < in_w) v = __ldg(reinterpret_cast<const uint4*>(w + r * in_w + c * 8));
+			st_shared_v4(s.w0 + sw128(r, c), v.x, v.y, v.z, v.w);
+		}
+		w += WIDTH * in_w;
+		for (uint32_t l = 1; l < NH; ++l) {
+			for (uint32_t i = tid; i < WIDTH * 8; i += 128) {
+				const uint32_t r = i >> 3, c = i & 7;
+				const uint4 v = __ldg(reinterpret_cast<const uint4*>(w + r * WIDTH + c * 8));
+				st_shared_v4(s.w0 + l * (WIDTH * 128) + sw128(r, c), v.x, v.y, v.z, v.w);
+			}
+			w += WIDTH * WIDTH;
+		}
+		for (uint32_t i = tid; i < 16 * 8; i += 128) {
+			const uint32_t r = i >> 3, c = i & 7;
+			const uint4 v = __ldg(reinterpret_cast<const uint4*>(w + r * WIDTH + c * 8));
+			st_shared_v4(s.w_out + sw128(r, c), v.x, v.y, v.z, v.w);
+		}
+	}
+
+	fence_proxy_async_smem();
+	tc_fence_before_sync();
+	__syncthreads();
+	tc_fence_after_sync();
+
+	uint32_t tmem_base;
+	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(s.tmem_slot));
+	const uint32_t tmem_acc = tmem_base;                          // 64 columns
+	const uint32_t lane_field = (warp * 32u) << 16;               // this warp's TMEM lane quadrant
+	uint32_t phase = 0;
+
+	// Instruction descriptors.
+	constexpr uint32_t IDESC_FWD_N64 = umma_idesc_f16(128, 64, 0, 0);   // A K-major, B K-major
+	constexpr uint32_t IDESC_FWD_N16 = umma_idesc_f16(128, 16, 0, 0);
+	constexpr uint32_t IDESC_DGRAD = umma_idesc_f16(128, 64, 0, 1);     // A K-major, B MN-major (W^T)
+	constexpr uint32_t IDESC_WGRAD = umma_idesc_f16(64, 64, 1, 1);      // A, B MN-major (K = samples)
+
+	// K-major operand, k-step j: +32 bytes. MN-major operand, k-step j (16 rows): +2048 bytes.
+	auto kmaj = [](uint32_t tile, uint32_t j) { return umma_desc_sw128(tile + j * 32u, 16u, 1024u); };
+	auto mnmaj = [](uint32_t tile, uint32_t j) { return umma_desc_sw128(tile + j * 2048u, TILE_BYTES, 1024u); };
+
+	// All threads: make this thread's smem tile writes / TMEM reads visible, then rendezvous.
+	auto stage_sync = [&]() {
+		tmem_ld_wait();
+		tc_fence_before_sync();
+		fence_proxy_async_smem();
+		__syncthreads();
+	};
+	auto wait_mma = [&]() {
+		mbar_wait(s.bar, phase);
+		phase ^= 1u;
+		tc_fence_after_sync();
+	};
+
+	float loss_acc = 0.0f;
+	bool dw_started = false;
+
+	const uint32_t n_tiles = p.batch_size / TILE_M;
+	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		const uint32_t sample = tile * TILE_M + tid;
+
+		// ================================================================ gather + N-linear blend -> enc tile
+		float x[D];
+#pragma unroll
+		for (uint32_t d = 0; d < D; ++d) x[d] = __ldg(p.positions + (size_t)sample * D + d);
+
+		{
+			static_assert(F == 2, "fused path: F == 2");
+			constexpr uint32_t LEVELS_PER_CHUNK = 8 / F;  // one 16-byte chunk = 8 features
+			const __half* __restrict__ table = p.params + p.n_mlp_params;
+			const uint32_t n_chunks = in_w / 8;
+			for (uint32_t chunk = 0; chunk < 8; ++chunk) {
+				uint32_t packed[4] = {0, 0, 0, 0};
+				if (chunk < n_chunks) {
+#pragma unroll
+					for (uint32_t k = 0; k < LEVELS_PER_CHUNK; ++k) {
+						const uint32_t level = chunk * LEVELS_PER_CHUNK + k;
+						if (level < p.grid.n_levels) {  // warp-uniform; levels beyond n_levels are zero padding (grid.h:759-766)
+							const LevelInfo lv = p.grid.levels[level];
+							CellPos<D> cp;
+							pos_fract<D>(x, lv.scale, p.grid.interpolation, cp);
+							const uint32_t* __restrict__ lt = reinterpret_cast<const uint32_t*>(table + (size_t)lv.offset * F);
+							uint32_t vals[1u << D];
+							float wts[1u << D];
+#pragma unroll
+							for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+								uint32_t c[D];
+								wts[idx] = corner<D>(cp, idx, c);
+								vals[idx] = __ldg(lt + corner_index<D>(lv, c));
+							}
+							__half2 result = __float2half2_rn(0.0f);
+#pragma unroll
+							for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+								// fma((T)weight, grid_val, result) with T = __half -> __hfma2 (grid.h:162, vec.h:372-378)
+								result = __hfma2(__float2half2_rn(wts[idx]), *reinterpret_cast<const __half2*>(&vals[idx]), result);
+							}
+							packed[k] = *reinterpret_cast<uint32_t*>(&result);
+						}
+					}
+				}
+				st_shared_v4(s.enc + sw128(tid, chunk), packed[0], packed[1], packed[2], packed[3]);
+				if (p.dbg_enc) *reinterpret_cast<uint4*>(p.dbg_enc + (size_t)sample * 64 + chunk * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+			}
+		}
+
+		// ================================================================ forward hidden layers
+		for (uint32_t l = 0; l < NH; ++l) {
+			stage_sync();
+			if (tid == 0) {
+				tc_fence_after_sync();
+				const uint32_t a_tile = l == 0 ? s.enc : s.h0 + (l - 1) * TILE_BYTES;
+				const uint32_t b_tile = s.w0 + l * (WIDTH * 128);
+				const uint32_t ksteps = l == 0 ? in_w / 16 : WIDTH / 16;
+				for (uint32_t j = 0; j < ksteps; ++j) umma_f16_ss(tmem_acc, kmaj(a_tile, j), kmaj(b_tile, j), IDESC_FWD_N64, j > 0);
+				umma_commit(s.bar);
+			}
+			wait_mma();
+			const uint32_t h_tile = s.h0 + l * TILE_BYTES;
+#pragma unroll
+			for (uint32_t half = 0; half < 2; ++half) {
+				uint32_t r[32];
+				tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
+				tmem_ld_wait();
+#pragma unroll
+				for (uint32_t c = 0; c < 4; ++c) {
+					const uint32_t v0 = relu_pack(r[c * 8 + 0], r[c * 8 + 1]), v1 = relu_pack(r[c * 8 + 2], r[c * 8 + 3]);
+					const uint32_t v2 = relu_pack(r[c * 8 + 4], r[c * 8 + 5]), v3 = relu_pack(r[c * 8 + 6], r[c * 8 + 7]);
+					st_shared_v4(h_tile + sw128(tid, half * 4 + c), v0, v1, v2, v3);
+					if (p.dbg_hidden) *reinterpret_cast<uint4*>(p.dbg_hidden + ((size_t)l * p.batch_size + sample) * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
+				}
+			}
+		}
+
+		// ================================================================ output layer (N = 16) + loss
+		stage_sync();
+		if (tid == 0) {
+			tc_fence_after_sync();
+			const uint32_t a_tile = s.h0 + (NH - 1) * TILE_BYTES;
+			for (uint32_t j = 0; j < WIDTH / 16; ++j) umma_f16_ss(tmem_acc, kmaj(a_tile, j), kmaj(s.w_out, j), IDESC_FWD_N16, j > 0);
+			umma_commit(s.bar);
+		}
+		wait_mma();
+		{
+			uint32_t r[16];
+			tmem_ld_32x32b_x16(tmem_acc + lane_field, r);
+			tmem_ld_wait();
+			// The reference's network output is fp16 (fully_fused_mlp.cu:421-476); everything downstream reads that rounding.
+			__half y16[16];
+#pragma unroll
+			for (uint32_t j = 0; j < 16; ++j) y16[j] = __float2half_rn(__uint_as_float(r[j]));
+			if (p.out_fp16) {
+				uint4* dst = reinterpret_cast<uint4*>(p.out_fp16 + (size_t)sample * 16);
+				dst[0] = *reinterpret_cast<uint4*>(&y16[0]);
+				dst[1] = *reinterpret_cast<uint4*>(&y16[8]);
+			}
+			if (p.out_fp32) {
+				for (uint32_t j = 0; j < p.n_out; ++j) p.out_fp32[(size_t)sample * p.n_out + j] = __half2float(y16[j]);
+			}
+			if (TRAIN) {
+				// relative_l2_loss / l2_loss (losses/relative_l2.h:56-75, l2.h:56-74); pad lanes give 0.
+				__half dy[16];
+				const float n_total = (float)(p.loss_batch_size * p.n_out);
+#pragma unroll
+				for (uint32_t j = 0; j < 16; ++j) {
+					float g = 0.0f;
+					if (j < p.n_out) {
+						const float pred = __half2float(y16[j]);
+						const float diff = pred - __ldg(p.targets + (size_t)sample * p.n_out + j);
+						float value, grad;
+						if (p.loss_type == LOSS_RELATIVE_L2) {
+							const float psq = pred * pred + 0.01f;
+							value = diff * diff / psq / n_total;
+							grad = 2.0f * diff / psq;
+						} else {
+							value = diff * diff / n_total;
+							grad = 2.0f * diff;
+						}
+						g = p.loss_scale * grad / n_total;
+						loss_acc += value;
+						if (p.loss_values) p.loss_values[(size_t)sample * p.n_out + j] = value;
+					}
+					dy[j] = __float2half_rn(g);
+				}
+				const uint4 lo = *reinterpret_cast<uint4*>(&dy[0]), hi = *reinterpret_cast<uint4*>(&dy[8]);
+				st_shared_v4(s.gB + sw128(tid, 0), lo.x, lo.y, lo.z, lo.w);
+				st_shared_v4(s.gB + sw128(tid, 1), hi.x, hi.y, hi.z, hi.w);
+				if (p.dbg_dy) {
+					uint4* dst = reinterpret_cast<uint4*>(p.dbg_dy + (size_t)sample * 16);
+					dst[0] = lo;
+					dst[1] = hi;
+				}
+			}
+		}
+
+		if (TRAIN) {
+			// ============================================================ backward through the output layer
+			// g_{NH-1} = (dy . W_out) * act'(h_{NH-1});  dW_out^T += h_{NH-1}^T . dy   (fully_fused_mlp.cu:192-240, :784-787)
+			uint32_t g_cur = s.gA, g_other = s.gB;
+			stage_sync();
+			if (tid == 0) {
+				tc_fence_after_sync();
+				const uint32_t h_last = s.h0 + (NH - 1) * TILE_BYTES;
+				umma_f16_ss(tmem_acc, kmaj(s.gB, 0), mnmaj(s.w_out, 0), IDESC_DGRAD, 0);
+				const uint32_t dw = tmem_base + 64u * (1 + NH);
+				for (uint32_t j = 0; j < TILE_M / 16; ++j) umma_f16_ss(dw, mnmaj(h_last, j), mnmaj(s.gB, j), IDESC_WGRAD, dw_started || j > 0);
+				umma_commit(s.bar);
+			}
+			wait_mma();
+			{
+				const uint32_t h_tile = s.h0 + (NH - 1) * TILE_BYTES;
+#pragma unroll
+				for (uint32_t half = 0; half < 2; ++half) {
+					uint32_t r[32];
+					tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
+					tmem_ld_wait();
+#pragma unroll
+					for (uint32_t c = 0; c < 4; ++c) {
+						uint32_t f0, f1, f2, f3;
+						ld_shared_v4(h_tile + sw128(tid, half * 4 + c), f0, f1, f2, f3);
+						const uint32_t v0 = relu_bwd_pack(r[c * 8 + 0], r[c * 8 + 1], f0), v1 = relu_bwd_pack(r[c * 8 + 2], r[c * 8 + 3], f1);
+						const uint32_t v2 = relu_bwd_pack(r[c * 8 + 4], r[c * 8 + 5], f2), v3 = relu_bwd_pack(r[c * 8 + 6], r[c * 8 + 7], f3);
+						st_shared_v4(g_cur + sw128(tid, half * 4 + c), v0, v1, v2, v3);
+						if (p.dbg_grad_hidden) *reinterpret_cast<uint4*>(p.dbg_grad_hidden + ((size_t)(NH - 1) * p.batch_size + sample) * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
+					}
+				}
+			}
+
+			// ============================================================ backward through hidden matmuls l = NH-1 .. 1
+			// g_{l-1} = (g_l . W_l) * act'(h_{l-1});  dW_l += g_l^T . h_{l-1}   (fully_fused_mlp.cu:248-250, :815-830)
+			for (uint32_t l = NH - 1; l >= 1; --l) {
+				stage_sync();
+				if (tid == 0) {
+					tc_fence_after_sync();
+					const uint32_t w_tile = s.w0 + l * (WIDTH * 128);
+					const uint32_t h_prev = s.h0 + (l - 1) * TILE_BYTES;
+					for (uint32_t j = 0; j < WIDTH / 16; ++j) umma_f16_ss(tmem_acc, kmaj(g_cur, j), mnmaj(w_tile, j), IDESC_DGRAD, j > 0);
+					const uint32_t dw = tmem_base + 64u * (1 + l);
+					for (uint32_t j = 0; j < TILE_M / 16; ++j) umma_f16_ss(dw, mnmaj(g_cur, j), mnmaj(h_prev, j), IDESC_WGRAD, dw_started || j > 0);
+					umma_commit(s.bar);
+				}
+				wait_mma();
+				const uint32_t h_tile = s.h0 + (l - 1) * TILE_BYTES;
+#pragma unroll
+				for (uint32_t half = 0; half < 2; ++half) {
+					uint32_t r[32];
+					tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
+					tmem_ld_wait();
+#pragma unroll
+					for (uint32_t c = 0; c < 4; ++c) {
+						uint32_t f0, f1, f2, f3;
+						ld_shared_v4(h_tile + sw128(tid, half * 4 + c), f0, f1, f2, f3);
+						const uint32_t v0 = relu_bwd_pack(r[c * 8 + 0], r[c * 8 + 1], f0), v1 = relu_bwd_pack(r[c * 8 + 2], r[c * 8 + 3], f1);
+						const uint32_t v2 = relu_bwd_pack(r[c * 8 + 4], r[c * 8 + 5], f2), v3 = relu_bwd_pack(r[c * 8 + 6], r[c * 8 + 7], f3);
+						st_shared_v4(g_other + sw128(tid, half * 4 + c), v0, v1, v2, v3);
+						if (p.dbg_grad_hidden) *reinterpret_cast<uint4*>(p.dbg_grad_hidden + ((size_t)(l - 1) * p.batch_size + sample) * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
+					}
+				}
+				const uint32_t t = g_cur;
+				g_cur = g_other;
+				g_other = t;
+			}
+
+			// ============================================================ first layer: dL/d(encoded) and dW_0
+			// d_enc = g_0 . W_0 (fully_fused_mlp.cu:833-836);  dW_0 += g_0^T . enc (:827-830)
+			stage_sync();
+			if (tid == 0) {
+				tc_fence_after_sync();
+				for (uint32_t j = 0; j < WIDTH / 16; ++j) umma_f16_ss(tmem_acc, kmaj(g_cur, j), mnmaj(s.w0, j), IDESC_DGRAD, j > 0);
+				const uint32_t dw = tmem_base + 64u;
+				for (uint32_t j = 0; j < TILE_M / 16; ++j) umma_f16_ss(dw, mnmaj(g_cur, j), mnmaj(s.enc, j), IDESC_WGRAD, dw_started || j > 0);
+				umma_commit(s.bar);
+			}
+			dw_started = true;
+			wait_mma();
+
+			// ============================================================ hash-grid gradient scatter (grid.h:215-320)
+			{
+				// dL/d(encoded) is an fp16 matrix in the reference (output of fc_multiply, fully_fused_mlp.cu:835): round the
+				// fp32 accumulator once, park this sample's row in its own (now idle) row of the enc tile.
+#pragma unroll
+				for (uint32_t half = 0; half < 2; ++half) {
+					uint32_t r[32];
+					tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
+					tmem_ld_wait();
+#pragma unroll
+					for (uint32_t c = 0; c < 4; ++c) {
+						const uint32_t v0 = pack_half2(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1]));
+						const uint32_t v1 = pack_half2(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3]));
+						const uint32_t v2 = pack_half2(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5]));
+						const uint32_t v3 = pack_half2(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7]));
+						st_shared_v4(s.enc + sw128(tid, half * 4 + c), v0, v1, v2, v3);
+						if (p.dbg_denc) *reinterpret_cast<uint4*>(p.dbg_denc + (size_t)sample * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
+					}
+				}
+				__half* __restrict__ grad_table = p.grads + p.n_mlp_params;
+#pragma unroll 2
+				for (uint32_t level = 0; level < p.grid.n_levels; ++level) {
+					const LevelInfo lv = p.grid.levels[level];
+					CellPos<D> cp;
+					pos_fract<D>(x, lv.scale, p.grid.interpolation, cp);
+					uint32_t gbits;
+					const uint32_t feat = level * F;  // 2 features = one 32-bit word
+					asm volatile("ld.shared.b32 %0, [%1];" : "=r"(gbits) : "r"(s.enc + sw128(tid, feat >> 3) + (feat & 7u) * 2u));
+					const __half2 grad = *reinterpret_cast<const __half2*>(&gbits);
+					__half2* __restrict__ lt = reinterpret_cast<__half2*>(grad_table + (size_t)lv.offset * F);
+#pragma unroll
+					for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+						uint32_t c[D];
+						const float w = corner<D>(cp, idx, c);
+						// (GRAD_T)weight * grad -> __hmul2, then atomic f16x2 add (grid.h:252-255, vec.h:328-336)
+						red_add_f16x2(lt + corner_index<D>(lv, c), __hmul2(__float2half2_rn(w), grad));
+					}
+				}
+			}
+		}
+	}
+
+	// ================================================================ flush weight gradients, loss, teardown
+	if (TRAIN) {
+		tmem_ld_wait();
+		tc_fence_before_sync();
+		__syncthreads();
+		tc_fence_after_sync();
+		if (dw_started) {
+			// M = 64 accumulators: row m lives in TMEM lane (m % 16) + 32 * (m / 16) -> lanes 0..15 of each warp.
+			const uint32_t lane = tid & 31u;
+			const uint32_t m = warp * 16 + lane;
+			for (uint32_t l = 0; l <= NH; ++l) {
+				const uint32_t dw = tmem_base + 64u * (1 + l) + lane_field;
+#pragma unroll
+				for (uint32_t half = 0; half < 2; ++half) {
+					uint32_t r[32];
+					tmem_ld_32x32b_x32(dw + half * 32, r);
+					tmem_ld_wait();
+					if (lane < 16) {
+						if (l == 0) {
+							// dW_0[out = m][in = n], n < in_w
+							float* dst = p.dw_accum + m * in_w;
+#pragma unroll
+							for (uint32_t k = 0; k < 32; ++k) {
+								const uint32_t n = half * 32 + k;
+								if (n < in_w) red_add_f32(dst + n, __uint_as_float(r[k]));
+							}
+						} else if (l < NH) {
+							float* dst = p.dw_accum + WIDTH * in_w + (l - 1) * WIDTH * WIDTH + m * WIDTH + half * 32;
+#pragma unroll
+							for (uint32_t k = 0; k < 32; ++k) red_add_f32(dst + k, __uint_as_float(r[k]));
+						} else if (half == 0) {
+							// accumulator holds dW_out^T[in = m][out = n], n < 16
+							float* dst = p.dw_accum + WIDTH * in_w + (NH - 1) * WIDTH * WIDTH;
+#pragma unroll
+							for (uint32_t n = 0; n < 16; ++n) red_add_f32(dst + n * WIDTH + m, __uint_as_float(r[n]));
+						}
+					}
+				}
+			}
+		}
+		// loss: warp reduce, one atomic per warp
+#pragma unroll
+		for (uint32_t o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xFFFFFFFFu, loss_acc, o);
+		if ((tid & 31u) == 0 && p.loss_sum) atomicAdd(p.loss_sum, loss_acc);
+	}
+
+	tmem_ld_wait();
+	tc_fence_before_sync();
+	__syncthreads();
+	if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+size_t fused_step_smem_bytes(uint32_t n_hidden_layers, bool train) {
+	const size_t tiles = 1 + n_hidden_layers + (train ? 2 : 1);
+	return tiles * TILE_BYTES + n_hidden_layers * (WIDTH * 128) + 16 * 128 + 64 + 1024 /* alignment slack */;
+}
+
+template <uint32_t D, bool TRAIN>
+static cudaError_t launch_impl(const FusedStepParams& p, uint32_t n_ctas, cudaStream_t stream) {
+	auto kernel = fused_step_kernel<D, 2, TRAIN>;
+	const size_t smem = fused_step_smem_bytes(p.n_hidden_layers, TRAIN);
+	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (err != cudaSuccess) return err;
+	kernel<<<n_ctas, 128, smem, stream>>>(p);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_fused_step(const FusedStepParams& p, uint32_t n_pos_dims, bool train, uint32_t n_ctas, cudaStream_t stream) {
+	if (n_pos_dims == 3) return train ? launch_impl<3, true>(p, n_ctas, stream) : launch_impl<3, false>(p, n_ctas, stream);
+	if (n_pos_dims == 2) return train ? launch_impl<2, true>(p, n_ctas, stream) : launch_impl<2, false>(p, n_ctas, stream);
+	return cudaErrorInvalidValue;
+}
+
+}  // namespace tcnnb

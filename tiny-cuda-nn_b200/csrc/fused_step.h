@@ -1,0 +1,39 @@
+// fused_step.h -- launch interface of the fused HashGrid + FullyFusedMLP kernel (fused_step.cu).
+#pragma once
+#include "common.cuh"
+
+namespace tcnnb {
+
+struct FusedStepParams {
+	// model
+	GridMeta grid;
+	uint32_t n_hidden_layers;      // 1..6, hidden width 64, ReLU
+	uint32_t n_out;                // logical outputs (<= 16)
+	uint32_t n_mlp_params;         // grid params start here in the parameter / gradient buffers
+	uint32_t loss_type;            // LossType
+	float loss_scale;              // 128 for fp16 params (common.h:243)
+	// batch
+	uint32_t batch_size;           // samples processed by this launch (multiple of 256)
+	uint32_t loss_batch_size;      // samples the loss is normalised over (== batch_size unless the batch is sharded over GPUs)
+	const float* positions;        // [batch][D] fp32
+	const float* targets;          // [batch][n_out] fp32 (training only)
+	// parameters: [MLP weights | grid table] fp16, and the matching fp16 gradient buffer (grid part accumulated with red.f16x2)
+	const __half* params;
+	__half* grads;
+	float* dw_accum;               // fp32 [n_mlp_params] weight-gradient accumulator (red.add.f32), must be zero on entry
+	float* loss_sum;               // fp32 scalar accumulator (may be null)
+	float* loss_values;            // [batch][n_out] fp32 (may be null)
+	__half* out_fp16;              // [batch][16] padded network output (may be null)
+	float* out_fp32;               // [batch][n_out] (may be null)
+	// debug taps (tests only; null in production): per-sample rows of every intermediate
+	__half* dbg_enc;               // [batch][64]
+	__half* dbg_hidden;            // [n_hidden][batch][64]
+	__half* dbg_dy;                // [batch][16]
+	__half* dbg_grad_hidden;       // [n_hidden][batch][64]
+	__half* dbg_denc;              // [batch][64]
+};
+
+size_t fused_step_smem_bytes(uint32_t n_hidden_layers, bool train);
+cudaError_t launch_fused_step(const FusedStepParams& p, uint32_t n_pos_dims, bool train, uint32_t n_ctas, cudaStream_t stream);
+
+}  // namespace tcnnb

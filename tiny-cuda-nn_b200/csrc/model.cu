@@ -1,0 +1,896 @@
+// model.cu -- host side of the hot path and the C ABI declared in include/tcnn_b200.h.
+//
+// Mirrors, for the HashGrid + FullyFusedMLP path only, what the reference spreads over
+//   config.h:53-63              create_from_config
+//   src/encoding.cu:132-150     create_encoding ("otype" dispatch, case-insensitive)  + grid.h:1726-1851 (grid JSON keys)
+//   src/network.cu:51-141       select_network / create_network
+//   src/loss.cu:82-90           create_loss
+//   src/optimizer.cu:50-80      create_optimizer + optimizers/adam.h:221-303 (Adam JSON keys)
+//   trainer.h:51-87,254-378     Trainer ctor / initialize_params / training_step / loss
+//   network_with_input_encoding.h:115-150  parameter layout [MLP | grid]
+// There is deliberately no fallback: unsupported configurations raise the error the caller sees via tcnnb_last_error().
+#include "../../include/tcnn_b200.h"
+
+#include "common.cuh"
+#include "fused_step.h"
+#include "json_mini.h"
+#include "misc_kernels.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace tcnnb {
+
+static std::atomic<uint64_t> g_kernel_launches{0};
+static thread_local std::string g_last_error;
+
+#define TCNNB_CUDA_CHECK(x)                                                                                             \
+	do {                                                                                                                  \
+		cudaError_t _e = (x);                                                                                               \
+		if (_e != cudaSuccess) throw std::runtime_error(std::string(#x " failed: ") + cudaGetErrorString(_e));              \
+	} while (0)
+
+static std::string to_lower(std::string s) {
+	std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+	return s;
+}
+static bool ieq(const std::string& a, const std::string& b) { return to_lower(a) == to_lower(b); }
+
+static uint32_t next_multiple(uint32_t v, uint32_t d) { return ((v + d - 1) / d) * d; }
+static uint32_t powi(uint32_t base, uint32_t e) { uint32_t r = 1; for (uint32_t i = 0; i < e; ++i) r *= base; return r; }
+
+// ---- host pcg32 (same published algorithm as the device copy in misc_kernels.cu; pcg32.h:53-69,103-112,145-166)
+struct HostPcg32 {
+	uint64_t state, inc;
+	static constexpr uint64_t MULT = 0x5851f42d4c957f2dULL;
+	HostPcg32(uint64_t initstate, uint64_t initseq = 1) {
+		state = 0;
+		inc = (initseq << 1u) | 1u;
+		next_uint();
+		state += initstate;
+		next_uint();
+	}
+	uint32_t next_uint() {
+		const uint64_t old = state;
+		state = old * MULT + inc;
+		const uint32_t xorshifted = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+		const uint32_t rot = (uint32_t)(old >> 59u);
+		return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31));
+	}
+	float next_float() {
+		const uint32_t u = (next_uint() >> 9) | 0x3f800000u;
+		float f;
+		std::memcpy(&f, &u, 4);
+		return f - 1.0f;
+	}
+	void advance(uint64_t delta) {
+		uint64_t cur_mult = MULT, cur_plus = inc, acc_mult = 1u, acc_plus = 0u;
+		while (delta > 0) {
+			if (delta & 1) {
+				acc_mult *= cur_mult;
+				acc_plus = acc_plus * cur_mult + cur_plus;
+			}
+			cur_plus = (cur_mult + 1) * cur_plus;
+			cur_mult *= cur_mult;
+			delta /= 2;
+		}
+		state = acc_mult * state + acc_plus;
+	}
+	Pcg32 device() const { return Pcg32{state, inc}; }
+};
+
+template <typename T>
+struct DeviceBuffer {
+	T* ptr = nullptr;
+	size_t n = 0;
+	DeviceBuffer() {}
+	DeviceBuffer(const DeviceBuffer&) = delete;
+	DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+	~DeviceBuffer() { release(); }
+	void release() {
+		if (ptr) cudaFree(ptr);
+		ptr = nullptr;
+		n = 0;
+	}
+	void resize(size_t count) {
+		if (count == n) return;
+		release();
+		if (count) TCNNB_CUDA_CHECK(cudaMalloc(&ptr, count * sizeof(T)));
+		n = count;
+	}
+	void zero(cudaStream_t stream = nullptr) {
+		if (n) TCNNB_CUDA_CHECK(cudaMemsetAsync(ptr, 0, n * sizeof(T), stream));
+	}
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+struct GridConfig {
+	uint32_t n_pos_dims = 3;
+	uint32_t n_levels = 16;
+	uint32_t n_features_per_level = 2;
+	uint32_t log2_hashmap_size = 19;
+	uint32_t base_resolution = 16;
+	float per_level_scale = 2.0f;
+	uint32_t grid_type = GRID_HASH;
+	uint32_t interpolation = INTERP_LINEAR;
+	bool stochastic_interpolation = false;
+	bool fixed_point_pos = false;
+	std::string otype = "HashGrid";
+	// derived
+	std::vector<uint32_t> offsets;      // n_levels + 1, in entries
+	std::vector<uint32_t> resolutions;  // from the host evaluation (sizing, grid.h:701)
+	std::vector<float> scales;          // device evaluation (lookup)
+	uint32_t n_params = 0;
+	uint32_t padded_width = 0;
+};
+
+struct MlpConfig {
+	std::string otype = "FullyFusedMLP";
+	uint32_t in_width = 0;
+	uint32_t width = 128;
+	uint32_t n_hidden_layers = 5;
+	uint32_t out_width = 0;
+	uint32_t padded_out_width = 0;
+	uint32_t activation = ACT_RELU;
+	uint32_t output_activation = ACT_NONE;
+	uint32_t n_params = 0;
+};
+
+static uint32_t parse_activation(const std::string& name) {
+	// src/common_host.cu:70-94
+	static const std::pair<const char*, uint32_t> table[] = {
+		{"None", ACT_NONE}, {"ReLU", ACT_RELU}, {"LeakyReLU", ACT_LEAKY_RELU}, {"SiLU", ACT_SILU}, {"Exponential", ACT_EXPONENTIAL},
+		{"Sigmoid", ACT_SIGMOID}, {"Sine", ACT_SINE}, {"Squareplus", ACT_SQUAREPLUS}, {"Softplus", ACT_SOFTPLUS}, {"Tanh", ACT_TANH},
+	};
+	for (auto& kv : table) if (ieq(name, kv.first)) return kv.second;
+	throw std::runtime_error("Invalid activation name: " + name);
+}
+
+static const char* activation_name(uint32_t a) {
+	switch (a) {
+		case ACT_NONE: return "None";
+		case ACT_RELU: return "ReLU";
+		case ACT_LEAKY_RELU: return "LeakyReLU";
+		case ACT_SILU: return "SiLU";
+		case ACT_EXPONENTIAL: return "Exponential";
+		case ACT_SIGMOID: return "Sigmoid";
+		case ACT_SINE: return "Sine";
+		case ACT_SQUAREPLUS: return "Squareplus";
+		case ACT_SOFTPLUS: return "Softplus";
+		case ACT_TANH: return "Tanh";
+	}
+	return "?";
+}
+
+// grid.h:1726-1851
+static GridConfig parse_grid(uint32_t n_dims_to_encode, const json::Value& e) {
+	GridConfig g;
+	g.otype = e.value("otype", "OneBlob");  // src/encoding.cu:133 default
+	const std::string lower = to_lower(g.otype);
+	if (!(lower == "grid" || lower == "hashgrid" || lower == "tiledgrid" || lower == "densegrid")) {
+		static const char* known[] = {"composite", "empty", "frequency", "identity", "oneblob", "sphericalharmonics", "trianglewave", "oneblobfrequency", "nrc"};
+		for (auto k : known) {
+			if (lower == k) throw std::runtime_error("Encoding '" + g.otype + "' is outside the tcnn_b200 hot path (only Grid/HashGrid/DenseGrid/TiledGrid are built)");
+		}
+		throw std::runtime_error("Encoding '" + g.otype + "' not found");
+	}
+	const std::string hash = e.value("hash", "CoherentPrime");
+	if (!ieq(hash, "CoherentPrime")) {
+		static const char* other[] = {"Prime", "ReversedPrime", "Rng", "BaseConvert"};
+		for (auto k : other) if (ieq(hash, k)) throw std::runtime_error(std::string("GridEncoding: compiled without ") + k + " hash support.");
+		throw std::runtime_error("Invalid hash type: " + hash);
+	}
+	g.n_features_per_level = (uint32_t)e.value("n_features_per_level", 2.0);
+	if (!(g.n_features_per_level == 1 || g.n_features_per_level == 2 || g.n_features_per_level == 4 || g.n_features_per_level == 8)) {
+		throw std::runtime_error("GridEncoding: n_features_per_level must be 1, 2, 4, or 8.");
+	}
+	g.log2_hashmap_size = (uint32_t)e.value("log2_hashmap_size", 19.0);
+	const std::string default_type = lower == "tiledgrid" ? "Tiled" : (lower == "densegrid" ? "Dense" : "Hash");
+	uint32_t n_features;
+	if (e.contains("n_features") || e.contains("n_grid_features")) {
+		n_features = (uint32_t)(e.contains("n_features") ? e.value("n_features", 0.0) : e.value("n_grid_features", 0.0));
+		if (e.contains("n_levels")) {
+			throw std::runtime_error("GridEncoding: may not specify n_features and n_levels simultaneously (one determines the other)");
+		}
+	} else {
+		n_features = g.n_features_per_level * (uint32_t)e.value("n_levels", 16.0);
+	}
+	if (n_features % g.n_features_per_level != 0) {
+		throw std::runtime_error("GridEncoding: n_features=" + std::to_string(n_features) + " must be a multiple of N_FEATURES_PER_LEVEL=" + std::to_string(g.n_features_per_level));
+	}
+	g.n_levels = n_features / g.n_features_per_level;
+	const std::string type = e.value("type", default_type);
+	if (ieq(type, "Hash")) g.grid_type = GRID_HASH;
+	else if (ieq(type, "Dense")) g.grid_type = GRID_DENSE;
+	else if (ieq(type, "Tiled") || ieq(type, "Tile")) g.grid_type = GRID_TILED;
+	else throw std::runtime_error("Invalid grid type: " + type);
+	g.base_resolution = (uint32_t)e.value("base_resolution", 16.0);
+	g.fixed_point_pos = e.value("fixed_point_pos", false);
+	const float default_scale = g.grid_type == GRID_DENSE ? std::exp(std::log(256.0f / (float)g.base_resolution) / (g.n_levels - 1)) : 2.0f;
+	g.per_level_scale = (float)e.value("per_level_scale", (double)default_scale);
+	g.stochastic_interpolation = e.value("stochastic_interpolation", false);
+	const std::string interp = e.value("interpolation", "Linear");
+	if (ieq(interp, "Nearest")) g.interpolation = INTERP_NEAREST;
+	else if (ieq(interp, "Linear")) g.interpolation = INTERP_LINEAR;
+	else if (ieq(interp, "Smoothstep")) g.interpolation = INTERP_SMOOTHSTEP;
+	else throw std::runtime_error("Invalid interpolation type: " + interp);
+	if (n_dims_to_encode < 2 || n_dims_to_encode > 4) throw std::runtime_error("GridEncoding: number of input dims must be 2 or 3.");
+	g.n_pos_dims = n_dims_to_encode;
+	if (g.n_levels > 128) throw std::runtime_error("GridEncoding: m_n_levels=" + std::to_string(g.n_levels) + " must be at most MAX_N_LEVELS=128");
+
+	// Level sizing, grid.h:692-737 (host evaluation of grid_scale / grid_resolution).
+	const float log2_scale = std::log2(g.per_level_scale);
+	uint32_t offset = 0;
+	g.offsets.resize(g.n_levels + 1);
+	g.resolutions.resize(g.n_levels);
+	for (uint32_t i = 0; i < g.n_levels; ++i) {
+		const float scale = exp2f(i * log2_scale) * g.base_resolution - 1.0f;
+		const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
+		g.resolutions[i] = resolution;
+		const uint32_t max_params = std::numeric_limits<uint32_t>::max() / 2;
+		uint32_t params_in_level = std::pow((float)resolution, (float)g.n_pos_dims) > (float)max_params ? max_params : powi(resolution, g.n_pos_dims);
+		params_in_level = next_multiple(params_in_level, 8u);
+		if (g.grid_type == GRID_TILED) params_in_level = std::min(params_in_level, powi(g.base_resolution, g.n_pos_dims));
+		else if (g.grid_type == GRID_HASH) params_in_level = std::min(params_in_level, 1u << g.log2_hashmap_size);
+		g.offsets[i] = offset;
+		offset += params_in_level;
+	}
+	g.offsets[g.n_levels] = offset;
+	g.n_params = offset * g.n_features_per_level;
+	return g;
+}
+
+struct Model {
+	uint32_t n_in = 0, n_out = 0;
+	GridConfig grid;
+	MlpConfig mlp;
+	uint32_t loss_type = LOSS_RELATIVE_L2;
+	std::string loss_name = "RelativeL2";
+	AdamParams adam;
+	uint32_t adam_step_count = 0;
+	float loss_scale = 128.0f;  // default_loss_scale<__half>() (common.h:243)
+	int device = 0;
+	int n_sms = 148;
+
+	size_t n_params = 0;
+	// trainer.h:489-503: one allocation [fp32 master | fp16 params | fp16 gradients]
+	DeviceBuffer<char> params_buffer;
+	float* params_fp32 = nullptr;
+	__half* params_fp16 = nullptr;
+	__half* grads_fp16 = nullptr;
+	DeviceBuffer<float> first_moments, second_moments;
+	DeviceBuffer<uint32_t> param_steps;
+	DeviceBuffer<float> dw_accum;   // fp32 MLP weight-gradient accumulator
+	DeviceBuffer<float> scalars;    // [0] = loss sum
+	DeviceBuffer<float> level_scales_dev;
+	bool mlp_grads_in_accum = false;
+
+	// host staging for the *_host entry points
+	float* pinned = nullptr;
+	size_t pinned_floats = 0;
+	DeviceBuffer<float> stage_in, stage_target, stage_out;
+	cudaStream_t own_stream = nullptr;
+
+	tcnnb_debug_taps taps{};
+	std::string hyperparams_json;
+
+	// optional per-kernel timing (bench.py roofline): events around the fused kernel and the Adam kernel of every step
+	bool profiling = false;
+	std::vector<cudaEvent_t> prof_events;  // triples: before fused, after fused, after adam
+
+	~Model() {
+		if (pinned) cudaFreeHost(pinned);
+		if (own_stream) cudaStreamDestroy(own_stream);
+		for (auto e : prof_events) cudaEventDestroy(e);
+	}
+
+	cudaEvent_t prof_mark(cudaStream_t stream) {
+		cudaEvent_t e = nullptr;
+		if (profiling && prof_events.size() < 3 * 8192) {
+			if (cudaEventCreate(&e) == cudaSuccess) {
+				cudaEventRecord(e, stream);
+				prof_events.push_back(e);
+			}
+		}
+		return e;
+	}
+
+	GridMeta grid_meta() const {
+		GridMeta m{};
+		m.n_levels = grid.n_levels;
+		m.n_features = grid.n_levels * grid.n_features_per_level;
+		m.padded_width = grid.padded_width;
+		m.interpolation = grid.interpolation;
+		static const uint32_t MAX_BASES[] = {0x0, 0xFFFFFFFF, 0xFFFF, 0x659, 0xFF, 0x54, 0x28, 0x17, 0xF, 0xB, 0x9};
+		for (uint32_t l = 0; l < grid.n_levels; ++l) {
+			LevelInfo& lv = m.levels[l];
+			lv.offset = grid.offsets[l];
+			lv.size = grid.offsets[l + 1] - grid.offsets[l];
+			lv.scale = grid.scales[l];
+			lv.resolution = (uint32_t)ceilf(lv.scale) + 1;  // grid_resolution(scale) as the kernels evaluate it (grid.h:98)
+			// grid_index (common_device.h:847-884)
+			uint32_t stride = 1;
+			bool dense_ok = lv.resolution <= MAX_BASES[grid.n_pos_dims];
+			if (dense_ok) {
+				for (uint32_t d = 0; d < grid.n_pos_dims; ++d) stride *= lv.resolution;
+			} else {
+				stride = 0xFFFFFFFFu;
+			}
+			if (grid.grid_type == GRID_HASH && lv.size < stride) lv.use_hash = 1;
+			else lv.use_hash = dense_ok ? 0 : 2;
+			lv.pow2_mask = (lv.size & (lv.size - 1)) == 0 ? lv.size - 1 : 0;
+		}
+		return m;
+	}
+};
+
+static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Value& cfg, uint32_t seed) {
+	TCNNB_CUDA_CHECK(cudaGetDevice(&m.device));
+	cudaDeviceProp prop;
+	TCNNB_CUDA_CHECK(cudaGetDeviceProperties(&prop, m.device));
+	if (prop.major != 10) {
+		throw std::runtime_error("tcnn_b200 requires an sm_100-class GPU (B200); found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor));
+	}
+	m.n_sms = prop.multiProcessorCount;
+	m.n_in = n_in;
+	m.n_out = n_out;
+
+	// ---- loss (src/loss.cu:82-90)
+	const json::Value& loss = cfg.sub("loss");
+	m.loss_name = loss.value("otype", "RelativeL2");
+	if (ieq(m.loss_name, "RelativeL2")) m.loss_type = LOSS_RELATIVE_L2;
+	else if (ieq(m.loss_name, "L2")) m.loss_type = LOSS_L2;
+	else {
+		static const char* known[] = {"RelativeL2Luminance", "L1", "RelativeL1", "Mape", "Smape", "CrossEntropy", "Variance"};
+		for (auto k : known) if (ieq(m.loss_name, k)) throw std::runtime_error("Loss '" + m.loss_name + "' is outside the tcnn_b200 hot path (L2 and RelativeL2 are built)");
+		throw std::runtime_error("Loss '" + m.loss_name + "' not found");
+	}
+
+	// ---- optimizer (src/optimizer.cu:50-80, adam.h:221-303)
+	const json::Value& opt = cfg.sub("optimizer");
+	const std::string opt_name = opt.value("otype", "Adam");
+	if (!ieq(opt_name, "Adam")) {
+		throw std::runtime_error("Optimizer '" + opt_name + "' is outside the tcnn_b200 hot path (Adam is built)");
+	}
+	AdamParams& a = m.adam;
+	a.beta1 = (float)opt.value("beta1", (double)a.beta1);
+	a.beta2 = (float)opt.value("beta2", (double)a.beta2);
+	a.epsilon = (float)opt.value("epsilon", (double)a.epsilon);
+	a.learning_rate = (float)opt.value("learning_rate", (double)a.learning_rate);
+	a.l2_reg = (float)opt.value("l2_reg", (double)a.l2_reg);
+	a.adabound = opt.value("adabound", false);
+	a.relative_decay = (float)opt.value("relative_decay", (double)a.relative_decay);
+	a.absolute_decay = (float)opt.value("absolute_decay", (double)a.absolute_decay);
+	a.clipping_magnitude = (float)opt.value("clipping_magnitude", (double)a.clipping_magnitude);
+	a.gradient_clipping_magnitude = (float)opt.value("gradient_clipping_magnitude", (double)a.gradient_clipping_magnitude);
+	a.non_matrix_learning_rate_factor = (float)opt.value("non_matrix_learning_rate_factor", (double)a.non_matrix_learning_rate_factor);
+	a.non_matrix_l2_reg = (float)opt.value("non_matrix_l2_reg", (double)a.non_matrix_l2_reg);
+	a.optimize_matrix_params = opt.value("optimize_matrix_params", true);
+	a.optimize_non_matrix_params = opt.value("optimize_non_matrix_params", true);
+	a.skip_zero_grad_non_matrix_params = opt.value("skip_zero_grad_non_matrix_params", true);
+
+	// ---- network (src/network.cu:51-141) and encoding alignment (network_with_input_encoding.h:47)
+	const json::Value& net = cfg.sub("network");
+	MlpConfig& mlp = m.mlp;
+	mlp.otype = net.value("otype", "MLP");
+	const bool fully_fused = ieq(mlp.otype, "FullyFusedMLP") || ieq(mlp.otype, "MegakernelMLP");
+	const bool cutlass = ieq(mlp.otype, "MLP") || ieq(mlp.otype, "CutlassMLP");
+	if (!fully_fused && !cutlass) throw std::runtime_error("Invalid network type: " + mlp.otype);
+	mlp.width = (uint32_t)net.value("n_neurons", 128.0);
+	mlp.n_hidden_layers = (uint32_t)net.value("n_hidden_layers", 5.0);
+	mlp.activation = parse_activation(net.value("activation", "ReLU"));
+	mlp.output_activation = parse_activation(net.value("output_activation", "None"));
+	if (fully_fused && !(mlp.width == 16 || mlp.width == 32 || mlp.width == 64 || mlp.width == 128)) {
+		throw std::runtime_error("FullyFusedMLP only supports 16, 32, 64, and 128 neurons, but got " + std::to_string(mlp.width) + ". Use CutlassMLP instead if this is a requirement.");
+	}
+	if (mlp.n_hidden_layers < 1) throw std::runtime_error("FullyFusedMLP requires at least 1 hidden layer (3 layers in total).");
+
+	m.grid = parse_grid(n_in, cfg.sub("encoding"));
+	const uint32_t alignment = 16;  // FullyFusedMLP / CutlassMLP REQUIRED_ALIGNMENT (src/network.cu:79-98)
+	m.grid.padded_width = next_multiple(m.grid.n_levels * m.grid.n_features_per_level, alignment);
+
+	mlp.in_width = m.grid.padded_width;
+	mlp.out_width = n_out;
+	mlp.padded_out_width = next_multiple(n_out, 16u);
+	mlp.n_params = mlp.width * mlp.in_width + (mlp.n_hidden_layers - 1) * mlp.width * mlp.width + mlp.padded_out_width * mlp.width;
+
+	// ---- what the sm_100a kernels of this round cover; everything else fails loudly (no fallback by design)
+	if (mlp.width != 64) throw std::runtime_error("tcnn_b200: the tcgen05 fused path currently covers n_neurons == 64 (got " + std::to_string(mlp.width) + ")");
+	if (mlp.n_hidden_layers > 6) throw std::runtime_error("tcnn_b200: the fused path keeps all hidden activations on chip and covers n_hidden_layers <= 6");
+	if (mlp.activation != ACT_RELU) throw std::runtime_error(std::string("tcnn_b200: fused path covers activation == ReLU (got ") + activation_name(mlp.activation) + ")");
+	if (mlp.output_activation != ACT_NONE) throw std::runtime_error(std::string("tcnn_b200: fused path covers output_activation == None (got ") + activation_name(mlp.output_activation) + ")");
+	if (mlp.padded_out_width != 16) throw std::runtime_error("tcnn_b200: fused path covers n_output_dims <= 16");
+	if (m.grid.n_features_per_level != 2) throw std::runtime_error("tcnn_b200: fused path covers n_features_per_level == 2");
+	if (m.grid.n_pos_dims != 2 && m.grid.n_pos_dims != 3) throw std::runtime_error("tcnn_b200: fused path covers 2-D and 3-D inputs");
+	if (m.grid.padded_width > 64 || m.grid.n_levels > MAX_LEVELS) throw std::runtime_error("tcnn_b200: fused path covers encodings up to 64 features");
+	if (m.grid.interpolation == INTERP_NEAREST) throw std::runtime_error("tcnn_b200: fused path covers Linear and Smoothstep interpolation");
+	if (m.grid.stochastic_interpolation) throw std::runtime_error("tcnn_b200: stochastic_interpolation is not built");
+
+	// ---- per-level scales, evaluated on the device like the reference's kernels (common_device.h:886-891)
+	m.grid.scales.resize(m.grid.n_levels);
+	m.level_scales_dev.resize(128);
+	TCNNB_CUDA_CHECK(launch_level_scales(nullptr, m.grid.n_levels, std::log2(m.grid.per_level_scale), m.grid.base_resolution, m.level_scales_dev.ptr));
+	++g_kernel_launches;
+	TCNNB_CUDA_CHECK(cudaMemcpy(m.grid.scales.data(), m.level_scales_dev.ptr, sizeof(float) * m.grid.n_levels, cudaMemcpyDeviceToHost));
+
+	// ---- parameter buffers (trainer.h:69-87,489-503)
+	m.n_params = (size_t)mlp.n_params + m.grid.n_params;
+	m.params_buffer.resize(m.n_params * (sizeof(float) + 2 * sizeof(__half)));
+	m.params_buffer.zero();
+	m.params_fp32 = (float*)m.params_buffer.ptr;
+	m.params_fp16 = (__half*)(m.params_buffer.ptr + sizeof(float) * m.n_params);
+	m.grads_fp16 = (__half*)(m.params_buffer.ptr + sizeof(float) * m.n_params + sizeof(__half) * m.n_params);
+	m.first_moments.resize(m.n_params);
+	m.first_moments.zero();
+	m.second_moments.resize(m.n_params);
+	m.second_moments.zero();
+	m.param_steps.resize(m.n_params);
+	m.param_steps.zero();
+	m.dw_accum.resize(mlp.n_params);
+	m.dw_accum.zero();
+	m.scalars.resize(4);
+	m.scalars.zero();
+
+	// ---- initialisation: std::seed_seq{seed} -> pcg32{seeds[0]} (trainer.h:51-58)
+	std::seed_seq seq{seed};
+	std::vector<uint32_t> seeds(2);
+	seq.generate(seeds.begin(), seeds.end());
+	HostPcg32 rng{seeds.front()};
+	// MLP: xavier uniform on the host, sequential draws (fully_fused_mlp.cu:868-892, gpu_matrix.h:292-306)
+	{
+		std::vector<float> w(mlp.n_params);
+		std::vector<std::pair<uint32_t, uint32_t>> mats;
+		mats.emplace_back(mlp.width, mlp.in_width);
+		for (uint32_t i = 0; i + 1 < mlp.n_hidden_layers; ++i) mats.emplace_back(mlp.width, mlp.width);
+		mats.emplace_back(mlp.padded_out_width, mlp.width);
+		size_t pos = 0;
+		for (auto& rc : mats) {
+			const float scale = 1.0f * std::sqrt(6.0f / (float)(rc.second + rc.first));
+			for (size_t i = 0; i < (size_t)rc.first * rc.second; ++i) w[pos++] = rng.next_float() * 2.0f * scale - scale;
+		}
+		TCNNB_CUDA_CHECK(cudaMemcpy(m.params_fp32, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+	}
+	// grid: U(-1e-4, 1e-4) generated on the device with the jump-ahead pattern (grid.h:1076-1079, random.h:56-69)
+	TCNNB_CUDA_CHECK(launch_random_uniform(nullptr, rng.device(), m.grid.n_params, m.params_fp32 + mlp.n_params, -1e-4f, 1e-4f));
+	++g_kernel_launches;
+	rng.advance(m.grid.n_params);
+	// fp32 -> fp16 (trainer.h:409-421)
+	TCNNB_CUDA_CHECK(launch_cast_params(nullptr, m.n_params, m.params_fp32, m.params_fp16));
+	++g_kernel_launches;
+	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
+	TCNNB_CUDA_CHECK(cudaStreamCreateWithFlags(&m.own_stream, cudaStreamNonBlocking));
+}
+
+static void check_batch(uint32_t batch) {
+	if (batch == 0 || batch % BATCH_GRANULARITY != 0) {
+		// object.h:169: CHECK_THROW(input.n() % BATCH_SIZE_GRANULARITY == 0)
+		throw std::runtime_error("batch size " + std::to_string(batch) + " must be a non-zero multiple of " + std::to_string(BATCH_GRANULARITY));
+	}
+}
+
+static FusedStepParams make_params(Model& m, uint32_t batch, uint32_t loss_batch, const float* x, const float* y) {
+	FusedStepParams p{};
+	p.grid = m.grid_meta();
+	p.n_hidden_layers = m.mlp.n_hidden_layers;
+	p.n_out = m.n_out;
+	p.n_mlp_params = m.mlp.n_params;
+	p.loss_type = m.loss_type;
+	p.loss_scale = m.loss_scale;
+	p.batch_size = batch;
+	p.loss_batch_size = loss_batch;
+	p.positions = x;
+	p.targets = y;
+	p.params = m.params_fp16;
+	p.grads = m.grads_fp16;
+	p.dw_accum = m.dw_accum.ptr;
+	p.loss_sum = m.scalars.ptr;
+	p.loss_values = m.taps.loss_values;
+	p.out_fp16 = (__half*)m.taps.output;
+	p.dbg_enc = (__half*)m.taps.encoded;
+	p.dbg_hidden = (__half*)m.taps.hidden;
+	p.dbg_dy = (__half*)m.taps.dL_doutput;
+	p.dbg_grad_hidden = (__half*)m.taps.grad_hidden;
+	p.dbg_denc = (__half*)m.taps.dL_dencoded;
+	return p;
+}
+
+static uint32_t fused_grid_size(const Model& m, uint32_t batch) {
+	const uint32_t tiles = batch / TILE_M;
+	const uint32_t resident = 2u * (uint32_t)m.n_sms;  // __launch_bounds__(128, 2): two CTAs per SM, one wave
+	return std::min(tiles, resident);
+}
+
+static void optimizer_step(Model& m, cudaStream_t stream) {
+	++m.adam_step_count;
+	AdamParams a = m.adam;
+	a.lower_lr_bound = 0;
+	a.upper_lr_bound = std::numeric_limits<float>::max();
+	if (a.adabound) {  // adam.h:165-168
+		a.lower_lr_bound = 0.1f - 0.1f / ((1 - a.beta2) * (float)m.adam_step_count + 1);
+		a.upper_lr_bound = 0.1f + 0.1f / ((1 - a.beta2) * (float)m.adam_step_count);
+	}
+	TCNNB_CUDA_CHECK(launch_adam_step(stream, a, (uint32_t)m.n_params, m.mlp.n_params, m.loss_scale, m.params_fp32, m.params_fp16, m.grads_fp16,
+	                                  m.mlp_grads_in_accum ? m.dw_accum.ptr : nullptr, m.first_moments.ptr, m.second_moments.ptr, m.param_steps.ptr));
+	++g_kernel_launches;
+	m.mlp_grads_in_accum = false;
+}
+
+static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_t loss_batch, const float* x, const float* y, bool run_optimizer) {
+	check_batch(batch);
+	// GradientMode::Overwrite: zero the grid gradient table (grid.h:865-867) and the loss accumulator.
+	TCNNB_CUDA_CHECK(cudaMemsetAsync(m.grads_fp16 + m.mlp.n_params, 0, sizeof(__half) * m.grid.n_params, stream));
+	TCNNB_CUDA_CHECK(cudaMemsetAsync(m.scalars.ptr, 0, sizeof(float), stream));
+	if (m.mlp_grads_in_accum) {
+		// a previous step left un-consumed weight gradients (run_optimizer == false twice in a row): Overwrite semantics
+		TCNNB_CUDA_CHECK(cudaMemsetAsync(m.dw_accum.ptr, 0, sizeof(float) * m.mlp.n_params, stream));
+	}
+	FusedStepParams p = make_params(m, batch, loss_batch, x, y);
+	m.prof_mark(stream);
+	TCNNB_CUDA_CHECK(launch_fused_step(p, m.grid.n_pos_dims, true, fused_grid_size(m, batch), stream));
+	++g_kernel_launches;
+	m.prof_mark(stream);
+	m.mlp_grads_in_accum = true;
+	if (run_optimizer) {
+		optimizer_step(m, stream);
+	}
+	m.prof_mark(stream);
+}
+
+static void finalize_mlp_grads(Model& m, cudaStream_t stream) {
+	if (m.mlp_grads_in_accum) {
+		TCNNB_CUDA_CHECK(launch_mlp_grad_finalize(stream, m.mlp.n_params, m.dw_accum.ptr, m.grads_fp16));
+		++g_kernel_launches;
+		m.mlp_grads_in_accum = false;
+	}
+}
+
+static void inference(Model& m, cudaStream_t stream, uint32_t batch, const float* x, float* out) {
+	check_batch(batch);
+	FusedStepParams p = make_params(m, batch, batch, x, nullptr);
+	p.out_fp32 = out;
+	p.loss_sum = nullptr;
+	TCNNB_CUDA_CHECK(launch_fused_step(p, m.grid.n_pos_dims, false, std::min(batch / TILE_M, 4u * (uint32_t)m.n_sms), stream));
+	++g_kernel_launches;
+}
+
+static void ensure_staging(Model& m, uint32_t batch) {
+	const size_t need = (size_t)batch * (m.n_in + m.n_out) + 16;
+	if (m.pinned_floats < need) {
+		if (m.pinned) cudaFreeHost(m.pinned);
+		m.pinned = nullptr;
+		TCNNB_CUDA_CHECK(cudaMallocHost(&m.pinned, need * sizeof(float)));
+		m.pinned_floats = need;
+	}
+	m.stage_in.resize(std::max(m.stage_in.n, (size_t)batch * m.n_in));
+	m.stage_target.resize(std::max(m.stage_target.n, (size_t)batch * m.n_out));
+	m.stage_out.resize(std::max(m.stage_out.n, (size_t)batch * m.n_out));
+}
+
+static std::string make_hyperparams(const Model& m) {
+	json::Value root = json::Value::object();
+	json::Value& enc = root["encoding"];
+	enc["otype"] = json::Value::string("Grid");
+	enc["type"] = json::Value::string(m.grid.grid_type == GRID_HASH ? "Hash" : (m.grid.grid_type == GRID_DENSE ? "Dense" : "Tiled"));
+	enc["n_levels"] = json::Value::number(m.grid.n_levels);
+	enc["n_features_per_level"] = json::Value::number(m.grid.n_features_per_level);
+	enc["base_resolution"] = json::Value::number(m.grid.base_resolution);
+	enc["log2_hashmap_size"] = json::Value::number(m.grid.log2_hashmap_size);
+	enc["per_level_scale"] = json::Value::number(m.grid.per_level_scale);
+	enc["interpolation"] = json::Value::string(m.grid.interpolation == INTERP_LINEAR ? "Linear" : (m.grid.interpolation == INTERP_SMOOTHSTEP ? "Smoothstep" : "Nearest"));
+	enc["hash"] = json::Value::string("CoherentPrime");
+	json::Value& net = root["network"];
+	net["otype"] = json::Value::string("FullyFusedMLP");
+	net["activation"] = json::Value::string(activation_name(m.mlp.activation));
+	net["output_activation"] = json::Value::string(activation_name(m.mlp.output_activation));
+	net["n_neurons"] = json::Value::number(m.mlp.width);
+	net["n_hidden_layers"] = json::Value::number(m.mlp.n_hidden_layers);
+	json::Value& loss = root["loss"];
+	loss["otype"] = json::Value::string(m.loss_type == LOSS_L2 ? "L2" : "RelativeL2");
+	json::Value& opt = root["optimizer"];
+	opt["otype"] = json::Value::string("Adam");
+	opt["learning_rate"] = json::Value::number(m.adam.learning_rate);
+	opt["beta1"] = json::Value::number(m.adam.beta1);
+	opt["beta2"] = json::Value::number(m.adam.beta2);
+	opt["epsilon"] = json::Value::number(m.adam.epsilon);
+	opt["l2_reg"] = json::Value::number(m.adam.l2_reg);
+	root["n_params"] = json::Value::number((double)m.n_params);
+	root["n_mlp_params"] = json::Value::number(m.mlp.n_params);
+	root["encoded_width"] = json::Value::number(m.grid.padded_width);
+	return json::dump(root);
+}
+
+}  // namespace tcnnb
+
+// ==================================================================================================================
+// C ABI
+// ==================================================================================================================
+using namespace tcnnb;
+
+struct tcnnb_model {
+	Model impl;
+};
+
+#define TCNNB_API_BEGIN try {
+#define TCNNB_API_END                         \
+	return 0;                                   \
+	}                                           \
+	catch (const std::exception& e) {           \
+		g_last_error = e.what();                  \
+		return 1;                                 \
+	}                                           \
+	catch (...) {                               \
+		g_last_error = "unknown exception";       \
+		return 1;                                 \
+	}
+
+extern "C" {
+
+const char* tcnnb_last_error(void) { return g_last_error.c_str(); }
+uint32_t tcnnb_batch_size_granularity(void) { return BATCH_GRANULARITY; }
+float tcnnb_default_loss_scale(void) { return 128.0f; }
+uint32_t tcnnb_abi_version(void) { return 1; }
+uint64_t tcnnb_kernel_launch_count(void) { return g_kernel_launches.load(); }
+
+int tcnnb_cuda_device(void) {
+	int d = -1;
+	if (cudaGetDevice(&d) != cudaSuccess) return -1;
+	return d;
+}
+
+int tcnnb_set_cuda_device(int device) {
+	TCNNB_API_BEGIN
+	TCNNB_CUDA_CHECK(cudaSetDevice(device));
+	TCNNB_API_END
+}
+
+int tcnnb_create_from_config(uint32_t n_input_dims, uint32_t n_output_dims, const char* config_json, uint32_t seed, tcnnb_model** out) {
+	TCNNB_API_BEGIN
+	if (!out) throw std::runtime_error("tcnnb_create_from_config: out is null");
+	*out = nullptr;
+	const json::Value cfg = json::parse(config_json ? config_json : "{}");
+	std::unique_ptr<tcnnb_model> m{new tcnnb_model{}};
+	build_model(m->impl, n_input_dims, n_output_dims, cfg, seed);
+	*out = m.release();
+	TCNNB_API_END
+}
+
+void tcnnb_destroy(tcnnb_model* model) { delete model; }
+
+uint64_t tcnnb_n_params(const tcnnb_model* m) { return m->impl.n_params; }
+uint64_t tcnnb_n_mlp_params(const tcnnb_model* m) { return m->impl.mlp.n_params; }
+uint32_t tcnnb_n_input_dims(const tcnnb_model* m) { return m->impl.n_in; }
+uint32_t tcnnb_n_output_dims(const tcnnb_model* m) { return m->impl.n_out; }
+uint32_t tcnnb_padded_output_width(const tcnnb_model* m) { return m->impl.mlp.padded_out_width; }
+uint32_t tcnnb_encoded_width(const tcnnb_model* m) { return m->impl.grid.padded_width; }
+float* tcnnb_params_full_precision(tcnnb_model* m) { return m->impl.params_fp32; }
+void* tcnnb_params(tcnnb_model* m) { return m->impl.params_fp16; }
+float* tcnnb_mlp_gradient_accumulator(tcnnb_model* m) { return m->impl.dw_accum.ptr; }
+
+void* tcnnb_param_gradients(tcnnb_model* m) {
+	// The MLP part is materialised as fp16 on demand (the fused kernel accumulates it in fp32).
+	try {
+		finalize_mlp_grads(m->impl, nullptr);
+		cudaStreamSynchronize(nullptr);
+	} catch (const std::exception& e) {
+		g_last_error = e.what();
+		return nullptr;
+	}
+	return m->impl.grads_fp16;
+}
+
+int tcnnb_grid_levels(const tcnnb_model* m, uint32_t* n_levels, uint32_t* offsets, float* scales, uint32_t* resolutions) {
+	TCNNB_API_BEGIN
+	const GridConfig& g = m->impl.grid;
+	if (n_levels) *n_levels = g.n_levels;
+	for (uint32_t l = 0; l < g.n_levels; ++l) {
+		if (offsets) offsets[l] = g.offsets[l];
+		if (scales) scales[l] = g.scales[l];
+		if (resolutions) resolutions[l] = (uint32_t)ceilf(g.scales[l]) + 1;
+	}
+	if (offsets) offsets[g.n_levels] = g.offsets[g.n_levels];
+	TCNNB_API_END
+}
+
+const char* tcnnb_hyperparams(tcnnb_model* m) {
+	m->impl.hyperparams_json = make_hyperparams(m->impl);
+	return m->impl.hyperparams_json.c_str();
+}
+
+int tcnnb_set_params_full_precision(tcnnb_model* m, const float* params, uint64_t n, int device_ptr) {
+	TCNNB_API_BEGIN
+	Model& mm = m->impl;
+	if (n != mm.n_params) throw std::runtime_error("Can't set fp params because buffer has the wrong size.");  // trainer.h:410-412
+	TCNNB_CUDA_CHECK(cudaMemcpy(mm.params_fp32, params, sizeof(float) * n, device_ptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+	TCNNB_CUDA_CHECK(launch_cast_params(nullptr, mm.n_params, mm.params_fp32, mm.params_fp16));
+	++g_kernel_launches;
+	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
+	TCNNB_API_END
+}
+
+int tcnnb_training_step(tcnnb_model* m, tcnnb_stream stream, uint32_t batch_size, const float* input_dev, const float* target_dev, int run_optimizer) {
+	TCNNB_API_BEGIN
+	training_step(m->impl, (cudaStream_t)stream, batch_size, batch_size, input_dev, target_dev, run_optimizer != 0);
+	TCNNB_API_END
+}
+
+int tcnnb_training_step_shard(tcnnb_model* m, tcnnb_stream stream, uint32_t shard_batch_size, uint32_t global_batch_size, const float* input_dev, const float* target_dev, int run_optimizer) {
+	TCNNB_API_BEGIN
+	training_step(m->impl, (cudaStream_t)stream, shard_batch_size, global_batch_size, input_dev, target_dev, run_optimizer != 0);
+	TCNNB_API_END
+}
+
+int tcnnb_optimizer_step(tcnnb_model* m, tcnnb_stream stream) {
+	TCNNB_API_BEGIN
+	optimizer_step(m->impl, (cudaStream_t)stream);
+	TCNNB_API_END
+}
+
+int tcnnb_loss(tcnnb_model* m, tcnnb_stream stream, float* loss_out) {
+	TCNNB_API_BEGIN
+	float v = 0;
+	TCNNB_CUDA_CHECK(cudaMemcpyAsync(&v, m->impl.scalars.ptr, sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+	TCNNB_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+	if (loss_out) *loss_out = v;
+	TCNNB_API_END
+}
+
+int tcnnb_inference(tcnnb_model* m, tcnnb_stream stream, uint32_t batch_size, const float* input_dev, float* output_dev) {
+	TCNNB_API_BEGIN
+	inference(m->impl, (cudaStream_t)stream, batch_size, input_dev, output_dev);
+	TCNNB_API_END
+}
+
+int tcnnb_training_step_host(tcnnb_model* m, uint32_t batch_size, const float* input_host, const float* target_host, float* loss_out) {
+	TCNNB_API_BEGIN
+	Model& mm = m->impl;
+	check_batch(batch_size);
+	ensure_staging(mm, batch_size);
+	cudaStream_t s = mm.own_stream;
+	const size_t n_x = (size_t)batch_size * mm.n_in, n_y = (size_t)batch_size * mm.n_out;
+	// Stage through pinned memory unless the caller's buffers are already page-locked.
+	cudaPointerAttributes attr{};
+	const bool x_pinned = cudaPointerGetAttributes(&attr, input_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+	const bool y_pinned = cudaPointerGetAttributes(&attr, target_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	const float* sx = input_host;
+	const float* sy = target_host;
+	if (!x_pinned) { std::memcpy(mm.pinned, input_host, n_x * sizeof(float)); sx = mm.pinned; }
+	if (!y_pinned) { std::memcpy(mm.pinned + n_x, target_host, n_y * sizeof(float)); sy = mm.pinned + n_x; }
+	TCNNB_CUDA_CHECK(cudaMemcpyAsync(mm.stage_in.ptr, sx, n_x * sizeof(float), cudaMemcpyHostToDevice, s));
+	TCNNB_CUDA_CHECK(cudaMemcpyAsync(mm.stage_target.ptr, sy, n_y * sizeof(float), cudaMemcpyHostToDevice, s));
+	training_step(mm, s, batch_size, batch_size, mm.stage_in.ptr, mm.stage_target.ptr, true);
+	float* loss_pinned = mm.pinned + mm.pinned_floats - 1;
+	TCNNB_CUDA_CHECK(cudaMemcpyAsync(loss_pinned, mm.scalars.ptr, sizeof(float), cudaMemcpyDeviceToHost, s));
+	TCNNB_CUDA_CHECK(cudaStreamSynchronize(s));
+	if (loss_out) *loss_out = *loss_pinned;
+	TCNNB_API_END
+}
+
+int tcnnb_inference_host(tcnnb_model* m, uint32_t batch_size, const float* input_host, float* output_host) {
+	TCNNB_API_BEGIN
+	Model& mm = m->impl;
+	check_batch(batch_size);
+	ensure_staging(mm, batch_size);
+	cudaStream_t s = mm.own_stream;
+	const size_t n_x = (size_t)batch_size * mm.n_in, n_y = (size_t)batch_size * mm.n_out;
+	std::memcpy(mm.pinned, input_host, n_x * sizeof(float));
+	TCNNB_CUDA_CHECK(cudaMemcpyAsync(mm.stage_in.ptr, mm.pinned, n_x * sizeof(float), cudaMemcpyHostToDevice, s));
+	inference(mm, s, batch_size, mm.stage_in.ptr, mm.stage_out.ptr);
+	TCNNB_CUDA_CHECK(cudaMemcpyAsync(mm.pinned + n_x, mm.stage_out.ptr, n_y * sizeof(float), cudaMemcpyDeviceToHost, s));
+	TCNNB_CUDA_CHECK(cudaStreamSynchronize(s));
+	std::memcpy(output_host, mm.pinned + n_x, n_y * sizeof(float));
+	TCNNB_API_END
+}
+
+// Snapshot layout: [u64 n_params][u32 with_optimizer][u32 adam_step][fp16 params][fp32 m][fp32 v][u32 steps]
+uint64_t tcnnb_serialize_size(const tcnnb_model* m, int with_optimizer) {
+	const uint64_t n = m->impl.n_params;
+	return 16 + n * 2 + (with_optimizer ? n * 12 : 0);
+}
+
+int tcnnb_serialize(tcnnb_model* m, void* dst_host, uint64_t size, int with_optimizer) {
+	TCNNB_API_BEGIN
+	Model& mm = m->impl;
+	if (size < tcnnb_serialize_size(m, with_optimizer)) throw std::runtime_error("tcnnb_serialize: destination too small");
+	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
+	char* p = (char*)dst_host;
+	const uint64_t n = mm.n_params;
+	const uint32_t wo = with_optimizer ? 1 : 0, st = mm.adam_step_count;
+	std::memcpy(p, &n, 8);
+	std::memcpy(p + 8, &wo, 4);
+	std::memcpy(p + 12, &st, 4);
+	p += 16;
+	TCNNB_CUDA_CHECK(cudaMemcpy(p, mm.params_fp16, n * 2, cudaMemcpyDeviceToHost));
+	p += n * 2;
+	if (with_optimizer) {
+		TCNNB_CUDA_CHECK(cudaMemcpy(p, mm.first_moments.ptr, n * 4, cudaMemcpyDeviceToHost));
+		p += n * 4;
+		TCNNB_CUDA_CHECK(cudaMemcpy(p, mm.second_moments.ptr, n * 4, cudaMemcpyDeviceToHost));
+		p += n * 4;
+		TCNNB_CUDA_CHECK(cudaMemcpy(p, mm.param_steps.ptr, n * 4, cudaMemcpyDeviceToHost));
+	}
+	TCNNB_API_END
+}
+
+namespace tcnnb {
+__global__ void half_to_float_kernel(uint64_t n, const __half* __restrict__ in, float* __restrict__ out) {
+	const uint64_t i = threadIdx.x + (uint64_t)blockIdx.x * blockDim.x;
+	if (i < n) out[i] = (float)in[i];
+}
+}  // namespace tcnnb
+
+int tcnnb_deserialize(tcnnb_model* m, const void* src_host, uint64_t size) {
+	TCNNB_API_BEGIN
+	Model& mm = m->impl;
+	if (size < 16) throw std::runtime_error("tcnnb_deserialize: truncated snapshot");
+	const char* p = (const char*)src_host;
+	uint64_t n;
+	uint32_t wo, st;
+	std::memcpy(&n, p, 8);
+	std::memcpy(&wo, p + 8, 4);
+	std::memcpy(&st, p + 12, 4);
+	if (n != mm.n_params) throw std::runtime_error("Can't set params because buffer has the wrong size.");  // trainer.h:424-426
+	if (size < 16 + n * 2 + (wo ? n * 12 : 0)) throw std::runtime_error("tcnnb_deserialize: truncated snapshot");
+	p += 16;
+	// set_params (trainer.h:423-440): fp16 params are authoritative, fp32 master = (float)fp16
+	TCNNB_CUDA_CHECK(cudaMemcpy(mm.params_fp16, p, n * 2, cudaMemcpyHostToDevice));
+	half_to_float_kernel<<<(uint32_t)((n + 255) / 256), 256>>>(n, mm.params_fp16, mm.params_fp32);
+	++g_kernel_launches;
+	p += n * 2;
+	if (wo) {
+		TCNNB_CUDA_CHECK(cudaMemcpy(mm.first_moments.ptr, p, n * 4, cudaMemcpyHostToDevice));
+		p += n * 4;
+		TCNNB_CUDA_CHECK(cudaMemcpy(mm.second_moments.ptr, p, n * 4, cudaMemcpyHostToDevice));
+		p += n * 4;
+		TCNNB_CUDA_CHECK(cudaMemcpy(mm.param_steps.ptr, p, n * 4, cudaMemcpyHostToDevice));
+		mm.adam_step_count = st;
+	}
+	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
+	TCNNB_API_END
+}
+
+int tcnnb_set_profiling(tcnnb_model* m, int enable) {
+	TCNNB_API_BEGIN
+	Model& mm = m->impl;
+	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
+	for (auto e : mm.prof_events) cudaEventDestroy(e);
+	mm.prof_events.clear();
+	mm.profiling = enable != 0;
+	TCNNB_API_END
+}
+
+int tcnnb_read_profile(tcnnb_model* m, float* fused_ms_total, float* optimizer_ms_total, uint32_t* n_steps) {
+	TCNNB_API_BEGIN
+	Model& mm = m->impl;
+	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
+	float fused = 0, opt = 0;
+	const size_t n = mm.prof_events.size() / 3;
+	for (size_t i = 0; i < n; ++i) {
+		float a = 0, b = 0;
+		TCNNB_CUDA_CHECK(cudaEventElapsedTime(&a, mm.prof_events[3 * i], mm.prof_events[3 * i + 1]));
+		TCNNB_CUDA_CHECK(cudaEventElapsedTime(&b, mm.prof_events[3 * i + 1], mm.prof_events[3 * i + 2]));
+		fused += a;
+		opt += b;
+	}
+	if (fused_ms_total) *fused_ms_total = fused;
+	if (optimizer_ms_total) *optimizer_ms_total = opt;
+	if (n_steps) *n_steps = (uint32_t)n;
+	TCNNB_API_END
+}
+
+int tcnnb_set_debug_taps(tcnnb_model* m, const tcnnb_debug_taps* taps) {
+	TCNNB_API_BEGIN
+	if (taps) m->impl.taps = *taps;
+	else m->impl.taps = tcnnb_debug_taps{};
+	TCNNB_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// ptx.cuh -- thin inline-PTX wrappers for the sm_100a features the kernels use:
+// mbarrier, tcgen05 (alloc / mma / commit / ld / fences), async-proxy fences, f16x2 reductions.
+// Everything here is sm_100a-only by design (no fallback paths).
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace tcnnb {
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+	return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---------------------------------------------------------------- mbarrier
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+
+__device__ __forceinline__ void fence_mbar_init() {
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_LOOP:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra WAIT_DONE;\n"
+		"bra WAIT_LOOP;\n"
+		"WAIT_DONE:\n"
+		"}\n" ::"r"(bar), "r"(parity)
+		: "memory");
+}
+
+// ---------------------------------------------------------------- proxies / fences
+// Make generic-proxy shared-memory writes visible to the async proxy (tcgen05.mma operand reads).
+__device__ __forceinline__ void fence_proxy_async_smem() {
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before_sync() {
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+
+__device__ __forceinline__ void tc_fence_after_sync() {
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// ---------------------------------------------------------------- TMEM allocation (one full warp calls these)
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t n_cols) {
+	asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(n_cols) : "memory");
+}
+
+__device__ __forceinline__ void tmem_relinquish() {
+	asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t n_cols) {
+	asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(n_cols) : "memory");
+}
+
+// ---------------------------------------------------------------- UMMA descriptors
+// Shared-memory matrix descriptor, SWIZZLE_128B canonical layouts (tile rows are 128 bytes = 64 fp16):
+//   bits [ 0,14) start address >> 4        bits [16,30) leading byte offset >> 4
+//   bits [32,46) stride byte offset >> 4   bits [46,48) version = 1 (sm_100)
+//   bits [61,64) layout type: 2 = SWIZZLE_128B
+// K-major operand  ([rows = M/N][64 K-elements]):  SBO = 1024 B (next group of 8 rows), LBO unused (1).
+// MN-major operand ([rows = K][64 MN-elements]):   SBO = 1024 B (next group of 8 K-rows), LBO = stride between
+//   64-element blocks along MN (only read when the MN extent exceeds 64).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+	uint64_t d = 0;
+	d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+	d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+	d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+	d |= (uint64_t)1 << 46;
+	d |= (uint64_t)2 << 61;
+	return d;
+}
+
+// Instruction descriptor for kind::f16 with fp16 A/B and fp32 accumulation.
+//   [4,6) c_format = 1 (f32); [7,10) a_format = 0 (f16); [10,13) b_format = 0 (f16);
+//   [15] a_major (0 = K, 1 = MN); [16] b_major; [17,23) N >> 3; [24,29) M >> 4.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
+	return (1u << 4) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem], issued by ONE thread.
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"setp.ne.b32 p, %4, 0;\n"
+		"tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+		"}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+		: "memory");
+}
+
+// Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// ---------------------------------------------------------------- TMEM -> registers
+// 32x32b: lane i of the warp reads TMEM lane (base_lane + i); .x32 = 32 consecutive 32-bit columns.
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+	asm volatile(
+		"tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+		"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+		"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+		: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+		  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+		  "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+		  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+		: "r"(taddr)
+		: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+	asm volatile(
+		"tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+		"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+		: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+		  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+		: "r"(taddr)
+		: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_wait() {
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------- global reductions
+// red.global.add.noftz.f16x2: the same instruction the reference's atomic_add_gmem(__half2) lowers to (vec.h:328-336).
+__device__ __forceinline__ void red_add_f16x2(__half2* addr, __half2 v) {
+	asm volatile("red.relaxed.gpu.global.add.noftz.f16x2 [%0], %1;" ::"l"(addr), "r"(*reinterpret_cast<uint32_t*>(&v)) : "memory");
+}
+
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+	asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
+}  // namespace ptx
+}  // namespace tcnnb

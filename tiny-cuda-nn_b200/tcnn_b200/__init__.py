@@ -1,0 +1,296 @@
+"""tcnn_b200 -- thin ctypes binding over the C ABI in include/tcnn_b200.h (libtcnn_b200.so).
+
+This mirrors, in Python, the names a user of the reference touches on this path:
+`create_from_config(n_input_dims, n_output_dims, config)` -> TrainableModel with `.trainer.training_step(...)`,
+`.trainer.loss()`, `.network.inference(...)` (config.h:46-63, trainer.h:254-378, object.h:214).
+It is plumbing for tests and bench.py: torch is used only for device memory and streams. There is no CPU
+fallback -- if the CUDA library is missing or the device is not a B200, construction raises.
+"""
+import ctypes
+import json
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(os.path.dirname(_HERE), "libtcnn_b200.so")
+_lib = None
+
+
+class TcnnError(RuntimeError):
+    pass
+
+
+class DebugTaps(ctypes.Structure):
+    _fields_ = [
+        ("encoded", ctypes.c_void_p),
+        ("hidden", ctypes.c_void_p),
+        ("output", ctypes.c_void_p),
+        ("dL_doutput", ctypes.c_void_p),
+        ("grad_hidden", ctypes.c_void_p),
+        ("dL_dencoded", ctypes.c_void_p),
+        ("loss_values", ctypes.c_void_p),
+    ]
+
+
+# (name, restype, argtypes) of every symbol include/tcnn_b200.h declares; tests check the .so exports all of them.
+_u32, _u64, _f32p, _vp, _int = ctypes.c_uint32, ctypes.c_uint64, ctypes.POINTER(ctypes.c_float), ctypes.c_void_p, ctypes.c_int
+ABI = [
+    ("tcnnb_last_error", ctypes.c_char_p, []),
+    ("tcnnb_batch_size_granularity", _u32, []),
+    ("tcnnb_default_loss_scale", ctypes.c_float, []),
+    ("tcnnb_cuda_device", _int, []),
+    ("tcnnb_set_cuda_device", _int, [_int]),
+    ("tcnnb_abi_version", _u32, []),
+    ("tcnnb_create_from_config", _int, [_u32, _u32, ctypes.c_char_p, _u32, ctypes.POINTER(_vp)]),
+    ("tcnnb_destroy", None, [_vp]),
+    ("tcnnb_n_params", _u64, [_vp]),
+    ("tcnnb_n_mlp_params", _u64, [_vp]),
+    ("tcnnb_n_input_dims", _u32, [_vp]),
+    ("tcnnb_n_output_dims", _u32, [_vp]),
+    ("tcnnb_padded_output_width", _u32, [_vp]),
+    ("tcnnb_encoded_width", _u32, [_vp]),
+    ("tcnnb_params_full_precision", _vp, [_vp]),
+    ("tcnnb_params", _vp, [_vp]),
+    ("tcnnb_param_gradients", _vp, [_vp]),
+    ("tcnnb_grid_levels", _int, [_vp, ctypes.POINTER(_u32), ctypes.POINTER(_u32), _f32p, ctypes.POINTER(_u32)]),
+    ("tcnnb_hyperparams", ctypes.c_char_p, [_vp]),
+    ("tcnnb_set_params_full_precision", _int, [_vp, _vp, _u64, _int]),
+    ("tcnnb_training_step", _int, [_vp, _vp, _u32, _vp, _vp, _int]),
+    ("tcnnb_training_step_shard", _int, [_vp, _vp, _u32, _u32, _vp, _vp, _int]),
+    ("tcnnb_optimizer_step", _int, [_vp, _vp]),
+    ("tcnnb_mlp_gradient_accumulator", _vp, [_vp]),
+    ("tcnnb_loss", _int, [_vp, _vp, _f32p]),
+    ("tcnnb_inference", _int, [_vp, _vp, _u32, _vp, _vp]),
+    ("tcnnb_training_step_host", _int, [_vp, _u32, _vp, _vp, _f32p]),
+    ("tcnnb_inference_host", _int, [_vp, _u32, _vp, _vp]),
+    ("tcnnb_serialize_size", _u64, [_vp, _int]),
+    ("tcnnb_serialize", _int, [_vp, _vp, _u64, _int]),
+    ("tcnnb_deserialize", _int, [_vp, _vp, _u64]),
+    ("tcnnb_set_debug_taps", _int, [_vp, ctypes.POINTER(DebugTaps)]),
+    ("tcnnb_set_profiling", _int, [_vp, _int]),
+    ("tcnnb_read_profile", _int, [_vp, _f32p, _f32p, ctypes.POINTER(_u32)]),
+    ("tcnnb_kernel_launch_count", _u64, []),
+]
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Load libtcnn_b200.so (fails loudly if it has not been built: `python __graft_entry__.py build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise TcnnError(f"{_LIB_PATH} is missing: build the CUDA extension first (python __graft_entry__.py build). There is no CPU fallback.")
+    import torch  # noqa: F401  -- makes libcudart.so.12 resident before our library resolves it
+
+    lib = ctypes.CDLL(_LIB_PATH)
+    for name, restype, argtypes in ABI:
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise TcnnError(load().tcnnb_last_error().decode())
+
+
+def _stream_handle(stream):
+    if stream is None:
+        import torch
+
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if isinstance(stream, int):
+        return ctypes.c_void_p(stream)
+    return ctypes.c_void_p(stream.cuda_stream)
+
+
+class _Network:
+    """NetworkWithInputEncoding surface: inference / n_params / padded_output_width."""
+
+    def __init__(self, model):
+        self._m = model
+
+    def n_params(self):
+        return self._m.n_params
+
+    def padded_output_width(self):
+        return load().tcnnb_padded_output_width(self._m._h)
+
+    def inference(self, inputs, outputs=None, stream=None):
+        """network->inference(stream, input, output): inputs [B, n_in] fp32 cuda -> [B, n_out] fp32 (object.h:214)."""
+        import torch
+
+        m = self._m
+        assert inputs.is_cuda and inputs.dtype == torch.float32 and inputs.is_contiguous()
+        B = inputs.shape[0]
+        if outputs is None:
+            outputs = torch.empty(B, m.n_output_dims, dtype=torch.float32, device=inputs.device)
+        _check(load().tcnnb_inference(m._h, _stream_handle(stream), B, inputs.data_ptr(), outputs.data_ptr()))
+        return outputs
+
+
+class _Trainer:
+    """Trainer surface: training_step / loss / params / param_gradients / serialize (trainer.h)."""
+
+    def __init__(self, model):
+        self._m = model
+
+    def training_step(self, inputs, targets, run_optimizer=True, stream=None):
+        import torch
+
+        m = self._m
+        assert inputs.is_cuda and targets.is_cuda and inputs.dtype == torch.float32 and targets.dtype == torch.float32
+        assert inputs.is_contiguous() and targets.is_contiguous()
+        _check(load().tcnnb_training_step(m._h, _stream_handle(stream), inputs.shape[0], inputs.data_ptr(), targets.data_ptr(), int(run_optimizer)))
+        return self
+
+    def training_step_shard(self, inputs, targets, global_batch_size, run_optimizer=False, stream=None):
+        m = self._m
+        _check(load().tcnnb_training_step_shard(m._h, _stream_handle(stream), inputs.shape[0], global_batch_size, inputs.data_ptr(), targets.data_ptr(), int(run_optimizer)))
+        return self
+
+    def optimizer_step(self, stream=None):
+        _check(load().tcnnb_optimizer_step(self._m._h, _stream_handle(stream)))
+
+    def loss(self, ctx=None, stream=None):
+        out = ctypes.c_float(0)
+        _check(load().tcnnb_loss(self._m._h, _stream_handle(stream), ctypes.byref(out)))
+        return out.value
+
+    def n_params(self):
+        return self._m.n_params
+
+    def _view(self, ptr, n, dtype):
+        import torch
+
+        class _Ext:
+            pass
+
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        typestr = {torch.float32: "<f4", torch.float16: "<f2", torch.int32: "<i4"}[dtype]
+        holder = _Ext()
+        holder.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2, "strides": (itemsize,)}
+        return torch.as_tensor(holder, device="cuda")
+
+    def params_full_precision(self):
+        import torch
+
+        return self._view(load().tcnnb_params_full_precision(self._m._h), self._m.n_params, torch.float32)
+
+    def params(self):
+        import torch
+
+        return self._view(load().tcnnb_params(self._m._h), self._m.n_params, torch.float16)
+
+    def param_gradients(self):
+        import torch
+
+        ptr = load().tcnnb_param_gradients(self._m._h)
+        if not ptr:
+            raise TcnnError(load().tcnnb_last_error().decode())
+        return self._view(ptr, self._m.n_params, torch.float16)
+
+    def mlp_gradient_accumulator(self):
+        import torch
+
+        return self._view(load().tcnnb_mlp_gradient_accumulator(self._m._h), self._m.n_mlp_params, torch.float32)
+
+    def set_params_full_precision(self, params):
+        import torch
+
+        if params.is_cuda:
+            _check(load().tcnnb_set_params_full_precision(self._m._h, params.data_ptr(), params.numel(), 1))
+        else:
+            p = params.contiguous().to(torch.float32)
+            _check(load().tcnnb_set_params_full_precision(self._m._h, p.data_ptr(), p.numel(), 0))
+
+    def serialize(self, with_optimizer=False):
+        n = load().tcnnb_serialize_size(self._m._h, int(with_optimizer))
+        buf = (ctypes.c_char * n)()
+        _check(load().tcnnb_serialize(self._m._h, buf, n, int(with_optimizer)))
+        return bytes(buf)
+
+    def deserialize(self, blob):
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        _check(load().tcnnb_deserialize(self._m._h, buf, len(blob)))
+
+
+class TrainableModel:
+    """Result of create_from_config (config.h:46-51): .network and .trainer share one parameter set."""
+
+    def __init__(self, n_input_dims, n_output_dims, config, seed=1337):
+        lib = load()
+        handle = ctypes.c_void_p()
+        text = config if isinstance(config, str) else json.dumps(config)
+        rc = lib.tcnnb_create_from_config(n_input_dims, n_output_dims, text.encode(), seed, ctypes.byref(handle))
+        _check(rc)
+        self._h = handle
+        self.n_input_dims = n_input_dims
+        self.n_output_dims = n_output_dims
+        self.n_params = lib.tcnnb_n_params(handle)
+        self.n_mlp_params = lib.tcnnb_n_mlp_params(handle)
+        self.encoded_width = lib.tcnnb_encoded_width(handle)
+        self.network = _Network(self)
+        self.trainer = _Trainer(self)
+
+    def hyperparams(self):
+        return json.loads(load().tcnnb_hyperparams(self._h).decode())
+
+    def grid_levels(self):
+        lib = load()
+        n = ctypes.c_uint32(0)
+        offsets = (ctypes.c_uint32 * 129)()
+        scales = (ctypes.c_float * 128)()
+        res = (ctypes.c_uint32 * 128)()
+        _check(lib.tcnnb_grid_levels(self._h, ctypes.byref(n), offsets, scales, res))
+        L = n.value
+        return {"n_levels": L, "offsets": list(offsets[: L + 1]), "scales": list(scales[:L]), "resolutions": list(res[:L])}
+
+    def set_debug_taps(self, **tensors):
+        taps = DebugTaps()
+        for k, t in tensors.items():
+            setattr(taps, k, t.data_ptr() if t is not None else None)
+        _check(load().tcnnb_set_debug_taps(self._h, ctypes.byref(taps)))
+
+    def set_profiling(self, enable):
+        _check(load().tcnnb_set_profiling(self._h, int(enable)))
+
+    def read_profile(self):
+        f, o, n = ctypes.c_float(0), ctypes.c_float(0), ctypes.c_uint32(0)
+        _check(load().tcnnb_read_profile(self._h, ctypes.byref(f), ctypes.byref(o), ctypes.byref(n)))
+        return {"fused_ms_total": f.value, "optimizer_ms_total": o.value, "n_steps": n.value}
+
+    def training_step_host(self, inputs_np, targets_np):
+        """C-ABI call with HOST buffers (numpy fp32, C-contiguous): H2D + step + D2H of the loss inside."""
+        out = ctypes.c_float(0)
+        _check(load().tcnnb_training_step_host(self._h, inputs_np.shape[0], inputs_np.ctypes.data, targets_np.ctypes.data, ctypes.byref(out)))
+        return out.value
+
+    def inference_host(self, inputs_np, outputs_np):
+        _check(load().tcnnb_inference_host(self._h, inputs_np.shape[0], inputs_np.ctypes.data, outputs_np.ctypes.data))
+        return outputs_np
+
+    def close(self):
+        if self._h:
+            load().tcnnb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def create_from_config(n_input_dims, n_output_dims, config, seed=1337):
+    """tcnn::create_from_config (config.h:53-63) + Trainer(..., seed = 1337) (trainer.h:51)."""
+    return TrainableModel(n_input_dims, n_output_dims, config, seed)
+
+
+def kernel_launch_count():
+    return load().tcnnb_kernel_launch_count()
