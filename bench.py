@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py -- training_step throughput of the HashGrid + FullyFusedMLP hot path (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one trainer->training_step (fused fwd+loss+bwd kernel + Adam) over one batch of 2^18 synthetic
+uniform-[0,1)^3 positions with closed-form targets. Prints ONE JSON line (rank 0). See DESIGN.md "Measurement".
+Own arm: N ranks (one per GPU, torchrun), batch sharded over ranks (global batch = N * 2^18 -> weak scaling), gradients
+all-reduced over NCCL before the (replicated) Adam step.
+Reference arm (--impl reference): the UNMODIFIED reference compiled into oracle/_ref/ref_harness (its sm_100 build, run
+on the GPU through its own C++ API; all three modes are timed and the fastest FullyFusedMLP mode is the line's value),
+plus the CPU oracle port on the host cores as cpu_baseline. The reference has no CPU implementation of this path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tiny-cuda-nn_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+BATCH = 1 << 18
+N_IN, N_OUT = 3, 3
+CONFIG_PATH = os.path.join(ROOT, "tests", "golden", "configs", "headline.json")
+METRIC = "training_step samples/sec, HashGrid+FullyFusedMLP(64,2) batch=2^18"
+WORKLOAD = "HashGrid(L=16,F=2,T=2^19,base=16,scale=1.5)+FullyFusedMLP(64x2,ReLU)->3, RelativeL2, Adam, batch=2^18/GPU, uniform [0,1)^3"
+# algorithmic bytes of the fused kernel per sample (12 in + 12 target + 512 gather + 512 scatter)
+FUSED_BYTES_PER_SAMPLE = 1048
+ADAM_BYTES_PER_PARAM = 36
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.samples = []
+        self.reasons = set()
+        self.stop = threading.Event()
+        self.index = index
+        self.thread = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().splitlines()
+                if out:
+                    f = [v.strip() for v in out[0].split(",")]
+                    self.samples.append((float(f[0]), float(f[1])))
+                    for n, v in zip(names, f[3:7]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(n)
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=5)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(self.reasons), "samples": 0}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons), "samples": len(sm)}
+
+
+def cpu_baseline(sample_batch=16384, steps=1):
+    """The oracle port timed on the host cores over a bounded sample of the same workload (full-size tables)."""
+    import numpy as np
+
+    import oracle_binding as ob
+
+    cfg = json.load(open(CONFIG_PATH))
+    m = ob.OracleModel(N_IN, N_OUT, cfg)
+    rng = ob.default_rng(1337)
+    x = ob.generate_random_uniform(rng, sample_batch * N_IN).reshape(sample_batch, N_IN)
+    y = ob.make_targets(x, N_OUT)
+    m.training_step(x, y)  # warm-up (page in 13 M parameters)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m.training_step(x, y)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": sample_batch / dt, "unit": "samples/s", "cores": ob.load().orc_num_threads(), "kind": "port",
+            "sample": f"{steps} training step(s) of {sample_batch} samples on the full 13.03M-parameter model (oracle/oracle_cpu.cpp, OpenMP)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    line = {"metric": METRIC, "unit": "samples/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "l2": "per-step working set (tables+optimizer state ~770 MB) exceeds the 126 MB L2; no explicit flush"}}
+    modes = {}
+    if os.path.exists(harness):
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        env = dict(os.environ)
+        for name, cfg, jit in (("fully_fused", "headline.json", 0), ("fully_fused_jit", "headline.json", 1), ("cutlass", "headline_cutlass.json", 0)):
+            cmd = [harness, "bench", os.path.join(ROOT, "tests", "golden", "configs", cfg), str(N_IN), str(N_OUT), str(BATCH), str(args.steps), str(args.warmup), str(jit)]
+            try:
+                with ClockSampler() as cs:
+                    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+                js = [l for l in out.stdout.splitlines() if l.startswith("{")]
+                if js:
+                    modes[name] = json.loads(js[-1])
+                    modes[name]["clocks"] = cs.summary()
+                else:
+                    modes[name] = {"error": (out.stderr or out.stdout)[-400:]}
+            except Exception as e:  # noqa: BLE001
+                modes[name] = {"error": repr(e)}
+    ok = {k: v for k, v in modes.items() if "samples_per_s" in v and k != "cutlass"}
+    cb = cpu_baseline()
+    if ok:
+        best = max(ok, key=lambda k: ok[k]["samples_per_s"])
+        line.update(value=ok[best]["samples_per_s"], ms_per_step=ok[best]["ms_per_step"], reference_mode=best, clocks=ok[best].get("clocks"))
+        line["reference_modes"] = modes
+        line["cpu_baseline"] = {"value": ok[best]["samples_per_s"], "unit": "samples/s", "cores": 0, "kind": "reference",
+                                "sample": f"the reference's own sm_100 build on the GPU ({best}); it has no CPU path. CPU oracle port: {cb['value']:.3e} samples/s on {cb['cores']} threads"}
+        line["cpu_oracle_port"] = cb
+    else:
+        # reference binary absent: the oracle port on the host cores is the only reference arm available
+        line.update(value=cb["value"], ms_per_step=1e3 * BATCH / cb["value"], reference_mode="cpu_oracle_port", reference_modes=modes)
+        line["cpu_baseline"] = cb
+    line["e2e"] = {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    line["gpu_launches"] = 0
+    print(json.dumps(line))
+
+
+def run_own(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import oracle_binding as ob  # input generator + cpu_baseline only
+    import tcnn_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cfg = json.load(open(CONFIG_PATH))
+    model = tcnn_b200.create_from_config(N_IN, N_OUT, cfg)
+    trainer = model.trainer
+    global_batch = BATCH * world
+
+    # A pool of distinct batches (each rank draws its own stream) so consecutive steps do not re-read identical inputs.
+    pool = 4
+    rng = ob.default_rng(1337 + rank)
+    xs, ys, xh, yh = [], [], [], []
+    for _ in range(pool):
+        x = ob.generate_random_uniform(rng, BATCH * N_IN).reshape(BATCH, N_IN)
+        y = ob.make_targets(x, N_OUT)
+        xh.append(torch.from_numpy(x).pin_memory())
+        yh.append(torch.from_numpy(y).pin_memory())
+        xs.append(xh[-1].cuda())
+        ys.append(yh[-1].cuda())
+    grid_grads = trainer.param_gradients()[model.n_mlp_params:]
+    mlp_acc = trainer.mlp_gradient_accumulator()
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        if world == 1:
+            trainer.training_step(xs[i % pool], ys[i % pool])
+        else:
+            trainer.training_step_shard(xs[i % pool], ys[i % pool], global_batch, run_optimizer=False)
+            dist.all_reduce(grid_grads)
+            dist.all_reduce(mlp_acc)
+            trainer.optimizer_step()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    sync_all()
+    launches0 = tcnn_b200.kernel_launch_count()
+    model.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as cs:
+        sync_all()
+        e0.record(stream)
+        for i in range(args.steps):
+            step(i)
+        e1.record(stream)
+        sync_all()
+    ms = e0.elapsed_time(e1)
+    prof = model.read_profile()
+    model.set_profiling(False)
+    launches = tcnn_b200.kernel_launch_count() - launches0
+    final_loss = trainer.loss()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # ---- end-to-end through the C ABI with HOST buffers: H2D of positions+targets and D2H of the loss every step
+    e2e_steps = max(3, min(args.steps, 20))
+    xn = [t.numpy() for t in xh]
+    yn = [t.numpy() for t in yh]
+    model.training_step_host(xn[0], yn[0])
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        model.training_step_host(xn[i % pool], yn[i % pool])
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+
+    if rank == 0:
+        peak, peak_kind = measured_peaks()
+        n_prof = max(1, prof["n_steps"])
+        fused_ms = prof["fused_ms_total"] / n_prof
+        adam_ms = prof["optimizer_ms_total"] / n_prof
+        achieved = FUSED_BYTES_PER_SAMPLE * BATCH / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else 0.0
+        ms_per_step = ms / args.steps
+        line = {
+            "metric": METRIC, "value": global_batch * args.steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": global_batch, "parallelism": f"dp{world}",
+                       "l2": "per-step working set (tables+optimizer state ~770 MB) exceeds the 126 MB L2; 4 rotating input batches; no explicit flush"},
+            "clocks": cs.summary(),
+            "e2e": {"value": global_batch * e2e_steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": BATCH * (N_IN + N_OUT) * 4, "d2h_bytes_per_step": 4,
+                    "steps": e2e_steps, "api": "tcnnb_training_step_host (C ABI, host buffers)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "fused_step_kernel<3,2,true>", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "kernel_ms": fused_ms, "optimizer_kernel_ms": adam_ms,
+                         "optimizer_achieved_gbs": ADAM_BYTES_PER_PARAM * model.n_params / (adam_ms * 1e-3) / 1e9 if adam_ms > 0 else None,
+                         "step_share": fused_ms / ms_per_step if ms_per_step > 0 else None},
+            "final_loss": final_loss,
+        }
+        try:
+            line["cpu_baseline"] = cpu_baseline() if world == 1 else None
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"error": repr(e)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 		fence_mbar_init();
 	}
 	if (warp == 0) {
+		__syncwarp();
 		tmem_alloc(s.tmem_slot, tmem_cols);
 		tmem_relinquish();
 	}
@@ -226,6 +227,7 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 				for (uint32_t j = 0; j < ksteps; ++j) umma_f16_ss(tmem_acc, kmaj(a_tile, j), kmaj(b_tile, j), IDESC_FWD_N64, j > 0);
 				umma_commit(s.bar);
 			}
+			__syncwarp();
 			wait_mma();
 			const uint32_t h_tile = s.h0 + l * TILE_BYTES;
 #pragma unroll
@@ -251,6 +253,7 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 			for (uint32_t j = 0; j < WIDTH / 16; ++j) umma_f16_ss(tmem_acc, kmaj(a_tile, j), kmaj(s.w_out, j), IDESC_FWD_N16, j > 0);
 			umma_commit(s.bar);
 		}
+		__syncwarp();
 		wait_mma();
 		{
 			uint32_t r[16];
@@ -317,6 +320,7 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 				for (uint32_t j = 0; j < TILE_M / 16; ++j) umma_f16_ss(dw, mnmaj(h_last, j), mnmaj(s.gB, j), IDESC_WGRAD, dw_started || j > 0);
 				umma_commit(s.bar);
 			}
+			__syncwarp();
 			wait_mma();
 			{
 				const uint32_t h_tile = s.h0 + (NH - 1) * TILE_BYTES;
@@ -350,6 +354,7 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 					for (uint32_t j = 0; j < TILE_M / 16; ++j) umma_f16_ss(dw, mnmaj(g_cur, j), mnmaj(h_prev, j), IDESC_WGRAD, dw_started || j > 0);
 					umma_commit(s.bar);
 				}
+				__syncwarp();
 				wait_mma();
 				const uint32_t h_tile = s.h0 + (l - 1) * TILE_BYTES;
 #pragma unroll
@@ -382,6 +387,7 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 				for (uint32_t j = 0; j < TILE_M / 16; ++j) umma_f16_ss(dw, mnmaj(g_cur, j), mnmaj(s.enc, j), IDESC_WGRAD, dw_started || j > 0);
 				umma_commit(s.bar);
 			}
+			__syncwarp();
 			dw_started = true;
 			wait_mma();
 
