@@ -231,15 +231,21 @@ def test_full_size_properties(torch_cuda):
     assert err < 2e-2, err
 
     p_before = model.trainer.params_full_precision().clone()
-    losses = []
-    for _ in range(5):
+    model.trainer.training_step(xd, yd)
+    losses = [model.trainer.loss()]
+    p_after = model.trainer.params_full_precision().clone()
+    g_step = model.trainer.param_gradients().float()
+    # adam.h:79-82: grid entries whose gradient of THIS step is exactly zero are skipped; every other one moved by ~lr
+    zero = g_step[7168:] == 0
+    assert zero.any() and (~zero).any()
+    assert torch.equal(p_before[7168:][zero], p_after[7168:][zero])
+    moved = (p_before[7168:][~zero] != p_after[7168:][~zero]).float().mean().item()
+    assert moved > 0.999
+    for _ in range(4):
         model.trainer.training_step(xd, yd)
         losses.append(model.trainer.loss())
     assert losses[-1] < losses[0]
-    p_after = model.trainer.params_full_precision()
-    grid_untouched = (g_full[7168:] == 0)
-    assert torch.equal(p_before[7168:][grid_untouched], p_after[7168:][grid_untouched])
-    assert torch.isfinite(p_after).all()
+    assert torch.isfinite(model.trainer.params_full_precision()).all()
 
     l_host = model.training_step_host(x, y)
     assert np.isfinite(l_host) and l_host < losses[0]
@@ -279,3 +285,73 @@ def test_errors_fail_loudly(torch_cuda):
     bad["network"]["n_neurons"] = 48
     with pytest.raises(tcnn_b200.TcnnError, match="only supports 16, 32, 64, and 128"):
         tcnn_b200.create_from_config(3, 3, bad)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Against the reference itself: tests/golden/*.npz were dumped by the UNMODIFIED reference (sm_100 build) on a B200.
+# ------------------------------------------------------------------------------------------------------------------
+from golden_util import CASES as GOLDEN_CASES, load_case, load_config  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_against_reference_golden_vectors(torch_cuda, name):
+    torch = torch_cuda
+    import tcnn_b200
+
+    _, n_in, n_out, B, _ = GOLDEN_CASES[name]
+    g = load_case(name)
+    cfg = load_config(name)
+    model = tcnn_b200.create_from_config(n_in, n_out, cfg)
+    x, y = g["x_f32"].reshape(B, n_in), g["y_f32"].reshape(B, n_out)
+    xd, yd = torch.from_numpy(x.copy()).cuda(), torch.from_numpy(y.copy()).cuda()
+
+    # initial parameters: bit-exact with the reference's Trainer (same pcg32 streams, same fp32 expressions)
+    p0 = model.trainer.params_full_precision().cpu().numpy()
+    assert np.array_equal(p0.view(np.uint32), g["params_init_f32"].view(np.uint32))
+
+    enc_tap = torch.zeros(B, 64, dtype=torch.float16, device="cuda")
+    out_tap = torch.zeros(B, 16, dtype=torch.float16, device="cuda")
+    lv_tap = torch.zeros(B, n_out, dtype=torch.float32, device="cuda")
+    model.set_debug_taps(encoded=enc_tap, output=out_tap, loss_values=lv_tap)
+
+    inf = model.network.inference(xd).cpu().numpy()
+    assert rae(inf, g["inference_f32"].reshape(B, n_out), 99.0) < 1e-2  # tests/test_common.h:177
+
+    model.trainer.training_step(xd, yd, run_optimizer=False)
+    loss0 = model.trainer.loss()
+    torch.cuda.synchronize()
+    # encoded features == the reference's kernel_grid output, bit for bit (hash indices, cell selection, fp16 blend)
+    W = g["meta"]["encoded_width"]
+    assert np.array_equal(f16(enc_tap)[:, :W].T, g["encoded_f16"].reshape(W, B))
+    a = ob.half_bits_to_float(f16(out_tap))[:, :n_out]
+    b = ob.half_bits_to_float(g["output_f16"].reshape(B, 16))[:, :n_out]
+    assert rae(a, b, 99.0) < 1e-2
+    assert np.abs(a - b).max() <= 4 * 2.0 ** -24 + 4e-3 * np.abs(b).max()
+    assert abs(loss0 - g["meta"]["losses"][0]) <= 1e-3 * g["meta"]["losses"][0]
+    assert rae(lv_tap.cpu().numpy(), g["loss_values_f32"].reshape(B, 16)[:, :n_out], 99.0) < 1e-2
+
+    # parameter gradients: tests/test_common.h:218 (mean RAE < 1.2e-2 on the best 99.9 %)
+    grads = ob.half_bits_to_float(f16(model.trainer.param_gradients()))
+    ref = ob.half_bits_to_float(g["grads_step0_f16"])
+    n_mlp = model.n_mlp_params
+    assert rae(grads[:n_mlp], ref[:n_mlp], 99.9) < 1.2e-2
+    assert rae(grads[n_mlp:], ref[n_mlp:], 99.9) < 1.2e-2
+    assert ((grads[n_mlp:] != 0) != (ref[n_mlp:] != 0)).mean() < 2e-3
+
+    # Adam: one step, then the whole 10-step trajectory
+    lr = cfg["optimizer"]["learning_rate"]
+    model.trainer.training_step(xd, yd)
+    losses = [loss0, model.trainer.loss()]
+    p1 = model.trainer.params_full_precision().cpu().numpy()
+    d = np.abs(p1 - g["params_step1_f32"])
+    assert np.percentile(d, 99) < 2e-2 * lr and d.mean() < 1e-2 * lr
+    assert ((p1 != p0) != (g["params_step1_f32"] != g["params_init_f32"])).mean() < 2e-3
+    for _ in range(g["meta"]["n_steps"] - 1):
+        model.trainer.training_step(xd, yd)
+        losses.append(model.trainer.loss())
+    for mine, theirs in zip(losses, g["meta"]["losses"]):
+        assert abs(mine - theirs) <= 3e-2 * abs(theirs), (losses, g["meta"]["losses"])
+    out = model.network.inference(xd).cpu().numpy()
+    assert rae(out, g["inference_final_f32"].reshape(B, n_out), 99.0) < 5e-2
+    pf = ob.half_bits_to_float(f16(model.trainer.params()))
+    assert np.abs(pf - ob.half_bits_to_float(g["params_final_f16"])).mean() < 0.05 * lr * g["meta"]["n_steps"]
