@@ -334,7 +334,11 @@ def test_against_reference_golden_vectors(torch_cuda, name):
     grads = ob.half_bits_to_float(f16(model.trainer.param_gradients()))
     ref = ob.half_bits_to_float(g["grads_step0_f16"])
     n_mlp = model.n_mlp_params
-    assert rae(grads[:n_mlp], ref[:n_mlp], 99.9) < 1.2e-2
+    # The MLP weight gradients are where the accumulator model matters: the reference accumulates 512..2^18 products in
+    # fp16 (CUTLASS split-K, cutlass_matmul.h:67), this kernel in fp32 (tcgen05). The reference's own two implementations
+    # (offline vs JIT) differ by 1.17e-2 on this vector, the fp32-accumulating oracle sits 1.23e-2 / 1.34e-2 from them and
+    # the fp16-accumulating oracle 7e-4 from the offline kernels (tests/test_oracle_golden.py): bar = 2e-2 for the MLP part.
+    assert rae(grads[:n_mlp], ref[:n_mlp], 99.9) < 2e-2
     assert rae(grads[n_mlp:], ref[n_mlp:], 99.9) < 1.2e-2
     assert ((grads[n_mlp:] != 0) != (ref[n_mlp:] != 0)).mean() < 2e-3
 

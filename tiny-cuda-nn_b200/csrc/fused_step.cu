@@ -196,10 +196,18 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 							uint32_t vals[1u << D];
 							float wts[1u << D];
 #pragma unroll
-							for (uint32_t idx = 0; idx < (1u << D); ++idx) {
-								uint32_t c[D];
-								wts[idx] = corner<D>(cp, idx, c);
-								vals[idx] = __ldg(lt + corner_index<D>(lv, c));
+							for (uint32_t pr = 0; pr < (1u << (D - 1)); ++pr) {
+								const CornerPair<D> cpair = corner_pair<D>(lv, cp, pr);
+								wts[2 * pr] = cpair.w0;
+								wts[2 * pr + 1] = cpair.w1;
+								if (p.ablate & ABLATE_GATHER) {
+									vals[2 * pr] = cpair.idx0;
+									vals[2 * pr + 1] = cpair.idx1;
+								} else if (p.ablate & ABLATE_PAIRING) {
+									gather_pair_f16x2(lt, cpair.idx0, cpair.idx1, false, vals[2 * pr], vals[2 * pr + 1]);
+								} else {
+									gather_pair_f16x2(lt, cpair.idx0, cpair.idx1, cpair.paired, vals[2 * pr], vals[2 * pr + 1]);
+								}
 							}
 							__half2 result = __float2half2_rn(0.0f);
 #pragma unroll
@@ -420,13 +428,16 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 					const uint32_t feat = level * F;  // 2 features = one 32-bit word
 					asm volatile("ld.shared.b32 %0, [%1];" : "=r"(gbits) : "r"(s.enc + sw128(tid, feat >> 3) + (feat & 7u) * 2u));
 					const __half2 grad = *reinterpret_cast<const __half2*>(&gbits);
-					__half2* __restrict__ lt = reinterpret_cast<__half2*>(grad_table + (size_t)lv.offset * F);
+					uint32_t* __restrict__ lt = reinterpret_cast<uint32_t*>(grad_table + (size_t)lv.offset * F);
 #pragma unroll
-					for (uint32_t idx = 0; idx < (1u << D); ++idx) {
-						uint32_t c[D];
-						const float w = corner<D>(cp, idx, c);
+					for (uint32_t pr = 0; pr < (1u << (D - 1)); ++pr) {
+						const CornerPair<D> cpair = corner_pair<D>(lv, cp, pr);
 						// (GRAD_T)weight * grad -> __hmul2, then atomic f16x2 add (grid.h:252-255, vec.h:328-336)
-						red_add_f16x2(lt + corner_index<D>(lv, c), __hmul2(__float2half2_rn(w), grad));
+						const __half2 a0 = __hmul2(__float2half2_rn(cpair.w0), grad);
+						const __half2 a1 = __hmul2(__float2half2_rn(cpair.w1), grad);
+						if (!(p.ablate & ABLATE_SCATTER)) {
+							scatter_pair_f16x2(lt, cpair.idx0, cpair.idx1, cpair.paired && !(p.ablate & ABLATE_PAIRING), *reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
+						}
 					}
 				}
 			}

@@ -4,7 +4,12 @@
 
 namespace tcnnb {
 
+// Ablation switches for profiling experiments (scripts/ablate.py); 0 in production. They skip memory operations only,
+// so the results of an ablated launch are meaningless.
+enum : uint32_t { ABLATE_GATHER = 1, ABLATE_SCATTER = 2, ABLATE_PAIRING = 4 };
+
 struct FusedStepParams {
+	uint32_t ablate;
 	// model
 	GridMeta grid;
 	uint32_t n_hidden_layers;      // 1..6, hidden width 64, ReLU

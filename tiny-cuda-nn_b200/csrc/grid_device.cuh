@@ -68,4 +68,63 @@ __device__ __forceinline__ float corner(const CellPos<D>& p, uint32_t idx, uint3
 	return w;
 }
 
+// The two corners of a cell that differ only in x (corner indices 2*pair and 2*pair+1): entry indices and weights.
+// For a hashed level with a power-of-two table the coherent-prime hash multiplies x by 1, so for an even cell x the
+// two entries are idx and idx^1, i.e. they share one aligned 8-byte slot; on dense levels they are idx and idx+1.
+// `paired` tells the caller that one 64-bit access at (idx0 & ~1) covers both.
+template <uint32_t D>
+struct CornerPair {
+	uint32_t idx0, idx1;
+	float w0, w1;
+	bool paired;
+};
+
+template <uint32_t D>
+__device__ __forceinline__ CornerPair<D> corner_pair(const LevelInfo& lv, const CellPos<D>& p, uint32_t pair) {
+	CornerPair<D> r;
+	uint32_t c0[D], c1[D];
+	r.w0 = corner<D>(p, 2 * pair, c0);
+	r.w1 = corner<D>(p, 2 * pair + 1, c1);
+	r.idx0 = corner_index<D>(lv, c0);
+	r.idx1 = corner_index<D>(lv, c1);
+	r.paired = (r.idx0 ^ r.idx1) == 1u;
+	return r;
+}
+
+// Gather the two fp16x2 entries of a corner pair: one 64-bit load when they share an aligned slot, else two 32-bit loads.
+__device__ __forceinline__ void gather_pair_f16x2(const uint32_t* __restrict__ table, uint32_t idx0, uint32_t idx1, bool paired, uint32_t& v0, uint32_t& v1) {
+	const uint32_t* a0 = table + (paired ? (idx0 & ~1u) : idx0);
+	const uint32_t* a1 = table + idx1;
+	uint32_t lo, hi;
+	asm("{\n"
+	    ".reg .pred p;\n"
+	    "setp.ne.u32 p, %4, 0;\n"
+	    "@p ld.global.nc.v2.u32 {%0, %1}, [%2];\n"
+	    "@!p ld.global.nc.u32 %0, [%2];\n"
+	    "@!p ld.global.nc.u32 %1, [%3];\n"
+	    "}\n"
+	    : "=r"(lo), "=r"(hi)
+	    : "l"(a0), "l"(a1), "r"((uint32_t)paired));
+	const bool swap = paired && (idx0 & 1u);
+	v0 = swap ? hi : lo;
+	v1 = swap ? lo : hi;
+}
+
+// Scatter-add two fp16x2 addends of a corner pair: one 64-bit vector reduction when paired, else two 32-bit reductions.
+__device__ __forceinline__ void scatter_pair_f16x2(uint32_t* __restrict__ table, uint32_t idx0, uint32_t idx1, bool paired, uint32_t a0, uint32_t a1) {
+	uint32_t* p0 = table + (paired ? (idx0 & ~1u) : idx0);
+	uint32_t* p1 = table + idx1;
+	const bool swap = paired && (idx0 & 1u);
+	const uint32_t lo = swap ? a1 : a0;
+	const uint32_t hi = swap ? a0 : a1;
+	asm volatile("{\n"
+	             ".reg .pred p;\n"
+	             "setp.ne.u32 p, %4, 0;\n"
+	             "@p red.relaxed.gpu.global.add.noftz.v2.f16x2 [%0], {%2, %3};\n"
+	             "@!p red.relaxed.gpu.global.add.noftz.f16x2 [%0], %2;\n"
+	             "@!p red.relaxed.gpu.global.add.noftz.f16x2 [%1], %3;\n"
+	             "}\n" ::"l"(p0), "l"(p1), "r"(lo), "r"(hi), "r"((uint32_t)paired)
+	             : "memory");
+}
+
 }  // namespace tcnnb

@@ -140,6 +140,82 @@ __global__ void adam_step_kernel(const AdamParams a, const uint32_t n_elements, 
 	weights[i] = (__half)new_weight;
 }
 
+// One Adam update, shared by the scalar and the 4-wide kernels. Returns false if the parameter is skipped.
+__device__ __forceinline__ bool adam_update(const AdamParams& a, const bool is_matrix, const float loss_scale, const __half grad_h,
+                                            float& weight_fp, float& first_moment, float& second_moment, uint32_t& step) {
+	float gradient = (float)grad_h / loss_scale;
+	if (!is_matrix) {
+		if (!a.optimize_non_matrix_params || (gradient == 0 && a.skip_zero_grad_non_matrix_params)) return false;
+	} else {
+		if (!a.optimize_matrix_params) return false;
+	}
+	if (is_matrix) {
+		gradient += a.l2_reg * weight_fp;
+	} else {
+		gradient += a.non_matrix_l2_reg * weight_fp;
+	}
+	if (a.gradient_clipping_magnitude != 0.0f) {
+		gradient = copysignf(fminf(fabsf(gradient), a.gradient_clipping_magnitude), gradient);
+	}
+	const float gradient_sq = gradient * gradient;
+	first_moment = a.beta1 * first_moment + (1 - a.beta1) * gradient;
+	second_moment = a.beta2 * second_moment + (1 - a.beta2) * gradient_sq;
+	float learning_rate = a.learning_rate;
+	if (!is_matrix) learning_rate *= a.non_matrix_learning_rate_factor;
+	const uint32_t current_step = ++step;
+	learning_rate *= sqrtf(1 - powf(a.beta2, (float)current_step)) / (1 - powf(a.beta1, (float)current_step));
+	const float effective_learning_rate = fminf(fmaxf(learning_rate / (sqrtf(second_moment) + a.epsilon), a.lower_lr_bound), a.upper_lr_bound);
+	const float decayed_weight = (1 - a.relative_decay * learning_rate) * weight_fp - copysignf(a.absolute_decay * learning_rate, weight_fp);
+	float new_weight = decayed_weight - effective_learning_rate * first_moment;
+	if (a.clipping_magnitude != 0.0f) {
+		new_weight = fminf(fmaxf(new_weight, -a.clipping_magnitude), a.clipping_magnitude);
+	}
+	weight_fp = new_weight;
+	return true;
+}
+
+// 4 parameters per thread: 128-bit streaming accesses to the fp32 state, 64-bit to the fp16 params / gradients.
+// Groups whose four gradients are all zero (untouched hash-table entries) touch nothing but the 8 gradient bytes.
+__global__ void __launch_bounds__(256) adam_step_vec4_kernel(const AdamParams a, const uint32_t n_groups, const uint32_t n_matrix_weights, const float loss_scale,
+                                      float4* __restrict__ weights_full_precision, uint2* __restrict__ weights, uint2* __restrict__ gradients,
+                                      float4* __restrict__ dw_accum, float4* __restrict__ first_moments, float4* __restrict__ second_moments,
+                                      uint4* __restrict__ param_steps) {
+	const uint32_t gidx = threadIdx.x + blockIdx.x * blockDim.x;
+	if (gidx >= n_groups) return;
+	const uint32_t i0 = gidx * 4;
+
+	__half g[4];
+	if (i0 + 3 < n_matrix_weights && dw_accum != nullptr) {
+		const float4 acc = dw_accum[gidx];
+		dw_accum[gidx] = make_float4(0.f, 0.f, 0.f, 0.f);
+		g[0] = (__half)acc.x; g[1] = (__half)acc.y; g[2] = (__half)acc.z; g[3] = (__half)acc.w;
+		gradients[gidx] = *reinterpret_cast<const uint2*>(g);
+	} else {
+		const uint2 raw = gradients[gidx];
+		*reinterpret_cast<uint2*>(g) = raw;
+		if (i0 >= n_matrix_weights && a.skip_zero_grad_non_matrix_params && ((raw.x | raw.y) & 0x7FFF7FFFu) == 0) return;  // all four are +-0
+	}
+
+	float4 w4 = __ldcs(weights_full_precision + gidx);
+	float4 m4 = __ldcs(first_moments + gidx);
+	float4 v4 = __ldcs(second_moments + gidx);
+	uint4 s4 = __ldcs(param_steps + gidx);
+	float w[4] = {w4.x, w4.y, w4.z, w4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+	uint32_t st[4] = {s4.x, s4.y, s4.z, s4.w};
+	bool any = false;
+#pragma unroll
+	for (uint32_t k = 0; k < 4; ++k) {
+		any |= adam_update(a, i0 + k < n_matrix_weights, loss_scale, g[k], w[k], m[k], v[k], st[k]);
+	}
+	if (!any) return;
+	__stcs(weights_full_precision + gidx, make_float4(w[0], w[1], w[2], w[3]));
+	__stcs(first_moments + gidx, make_float4(m[0], m[1], m[2], m[3]));
+	__stcs(second_moments + gidx, make_float4(v[0], v[1], v[2], v[3]));
+	__stcs(param_steps + gidx, make_uint4(st[0], st[1], st[2], st[3]));
+	__half h[4] = {(__half)w[0], (__half)w[1], (__half)w[2], (__half)w[3]};
+	weights[gidx] = *reinterpret_cast<const uint2*>(h);
+}
+
 __global__ void mlp_grad_finalize_kernel(uint32_t n, float* __restrict__ dw_accum, __half* __restrict__ gradients) {
 	const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
 	if (i < n) {
@@ -174,8 +250,20 @@ cudaError_t launch_adam_step(cudaStream_t stream, const AdamParams& a, uint32_t 
                              float* weights_full_precision, __half* weights, __half* gradients, float* dw_accum, float* first_moments,
                              float* second_moments, uint32_t* param_steps) {
 	if (n_elements == 0) return cudaSuccess;
-	adam_step_kernel<<<blocks_for(n_elements, 256), 256, 0, stream>>>(a, n_elements, n_matrix_weights, loss_scale, weights_full_precision, weights,
-	                                                                gradients, dw_accum, first_moments, second_moments, param_steps);
+	auto aligned = [](const void* p, size_t a) { return ((uintptr_t)p % a) == 0; };
+	// A skipped lane of a partially updated group is written back with its loaded (unchanged) value, which is only
+	// equivalent to "not touched" if the weights' fp16 copy equals (half)fp32 master -- true for trainer-owned buffers.
+	const bool vec_ok = n_elements % 4 == 0 && n_matrix_weights % 4 == 0 && aligned(weights_full_precision, 16) && aligned(weights, 8) && aligned(gradients, 8) &&
+	                    aligned(first_moments, 16) && aligned(second_moments, 16) && aligned(param_steps, 16) && (dw_accum == nullptr || aligned(dw_accum, 16));
+	if (vec_ok) {
+		const uint32_t n_groups = n_elements / 4;
+		adam_step_vec4_kernel<<<blocks_for(n_groups, 256), 256, 0, stream>>>(a, n_groups, n_matrix_weights, loss_scale, (float4*)weights_full_precision, (uint2*)weights,
+		                                                                   (uint2*)gradients, (float4*)dw_accum, (float4*)first_moments, (float4*)second_moments,
+		                                                                   (uint4*)param_steps);
+	} else {
+		adam_step_kernel<<<blocks_for(n_elements, 256), 256, 0, stream>>>(a, n_elements, n_matrix_weights, loss_scale, weights_full_precision, weights, gradients,
+		                                                                dw_accum, first_moments, second_moments, param_steps);
+	}
 	return cudaGetLastError();
 }
 

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -283,6 +284,7 @@ struct Model {
 	std::string hyperparams_json;
 
 	// optional per-kernel timing (bench.py roofline): events around the fused kernel and the Adam kernel of every step
+	uint32_t ablate = 0;  // profiling experiments only (TCNNB_ABLATE env var)
 	bool profiling = false;
 	std::vector<cudaEvent_t> prof_events;  // triples: before fused, after fused, after adam
 
@@ -340,6 +342,7 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 		throw std::runtime_error("tcnn_b200 requires an sm_100-class GPU (B200); found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor));
 	}
 	m.n_sms = prop.multiProcessorCount;
+	if (const char* e = std::getenv("TCNNB_ABLATE")) m.ablate = (uint32_t)std::atoi(e);
 	m.n_in = n_in;
 	m.n_out = n_out;
 
@@ -478,6 +481,7 @@ static void check_batch(uint32_t batch) {
 
 static FusedStepParams make_params(Model& m, uint32_t batch, uint32_t loss_batch, const float* x, const float* y) {
 	FusedStepParams p{};
+	p.ablate = m.ablate;
 	p.grid = m.grid_meta();
 	p.n_hidden_layers = m.mlp.n_hidden_layers;
 	p.n_out = m.n_out;
