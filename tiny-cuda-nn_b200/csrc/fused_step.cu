@@ -7,8 +7,9 @@
 // (grid.h:215). No activation ever leaves the SM: the only HBM/L2 traffic is positions, targets, the fp16 tables
 // (gather), their fp16 gradient tables (red.f16x2) and 7 K fp32 weight-gradient partial sums per CTA.
 //
-// Structure (one CTA = 128 threads = one 128-sample tile at a time, 2 CTAs co-resident per SM):
-//   thread t <-> sample t of the tile <-> row t of every smem operand tile <-> TMEM lane t.
+// Structure (one CTA = 256 threads = one 128-sample tile at a time, 2 CTAs co-resident per SM = 16 warps):
+//   two threads per sample: thread t (t < 128) and thread t + 128 share row t of every smem operand tile and TMEM lane t;
+//   they split the resolution levels (gather / scatter) and the accumulator columns (epilogues) between them.
 //   Operand tiles are [128 rows][64 fp16] in the canonical SWIZZLE_128B layout; the SAME bytes are consumed as a
 //   K-major A operand by the forward/dgrad MMAs (M = samples, K = neurons) and as an MN-major operand by the wgrad
 //   MMAs (M/N = neurons, K = samples), so no transposes are ever materialised.
@@ -74,10 +75,12 @@ struct Smem {
 
 // ------------------------------------------------------------------------------------------------------------------
 template <uint32_t D, uint32_t F, bool TRAIN>
-__global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParams p) {
+__global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParams p) {
 	extern __shared__ __align__(1024) uint8_t smem_raw[];
 	const uint32_t tid = threadIdx.x;
 	const uint32_t warp = tid >> 5;
+	const uint32_t row = tid & 127u;   // sample within the tile == smem tile row == TMEM lane
+	const uint32_t hsel = tid >> 7;    // which half of the levels / accumulator columns this thread owns (warp-uniform)
 	const uint32_t NH = p.n_hidden_layers;
 	const uint32_t in_w = p.grid.padded_width;
 
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 	{
 		const __half* __restrict__ w = p.params;  // MLP weights come first in the parameter buffer
 		// first layer: [64][in_w]
-		for (uint32_t i = tid; i < WIDTH * 8; i += 128) {
+		for (uint32_t i = tid; i < WIDTH * 8; i += 256) {
 			const uint32_t r = i >> 3, c = i & 7;
 			uint4 v = make_uint4(0, 0, 0, 0);
 			if (c * 8 < in_w) v = __ldg(reinterpret_cast<const uint4*>(w + r * in_w + c * 8));
@@ -117,14 +120,14 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 		}
 		w += WIDTH * in_w;
 		for (uint32_t l = 1; l < NH; ++l) {
-			for (uint32_t i = tid; i < WIDTH * 8; i += 128) {
+			for (uint32_t i = tid; i < WIDTH * 8; i += 256) {
 				const uint32_t r = i >> 3, c = i & 7;
 				const uint4 v = __ldg(reinterpret_cast<const uint4*>(w + r * WIDTH + c * 8));
 				st_shared_v4(s.w0 + l * (WIDTH * 128) + sw128(r, c), v.x, v.y, v.z, v.w);
 			}
 			w += WIDTH * WIDTH;
 		}
-		for (uint32_t i = tid; i < 16 * 8; i += 128) {
+		for (uint32_t i = tid; i < 16 * 8; i += 256) {
 			const uint32_t r = i >> 3, c = i & 7;
 			const uint4 v = __ldg(reinterpret_cast<const uint4*>(w + r * WIDTH + c * 8));
 			st_shared_v4(s.w_out + sw128(r, c), v.x, v.y, v.z, v.w);
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 	uint32_t tmem_base;
 	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(s.tmem_slot));
 	const uint32_t tmem_acc = tmem_base;                          // 64 columns
-	const uint32_t lane_field = (warp * 32u) << 16;               // this warp's TMEM lane quadrant
+	const uint32_t lane_field = ((warp & 3u) * 32u) << 16;        // this warp's TMEM lane quadrant
 	uint32_t phase = 0;
 
 	// Instruction descriptors.
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 
 	const uint32_t n_tiles = p.batch_size / TILE_M;
 	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-		const uint32_t sample = tile * TILE_M + tid;
+		const uint32_t sample = tile * TILE_M + row;
 
 		// ================================================================ gather + N-linear blend -> enc tile
 		float x[D];
@@ -181,10 +184,12 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 			static_assert(F == 2, "fused path: F == 2");
 			constexpr uint32_t LEVELS_PER_CHUNK = 8 / F;  // one 16-byte chunk = 8 features
 			const __half* __restrict__ table = p.params + p.n_mlp_params;
-			const uint32_t n_chunks = in_w / 8;
-			for (uint32_t chunk = 0; chunk < 8; ++chunk) {
+			const uint32_t n_chunks = in_w / 8;  // even: in_w is a multiple of 16
+			// level-bearing chunks [0, n_chunks) and zero chunks [n_chunks, 8) are both split evenly between the two threads
+			for (uint32_t cc = 0; cc < 4; ++cc) {
+				const uint32_t chunk = cc < n_chunks / 2 ? hsel * (n_chunks / 2) + cc : n_chunks + hsel * ((8 - n_chunks) / 2) + (cc - n_chunks / 2);
 				uint32_t packed[4] = {0, 0, 0, 0};
-				if (chunk < n_chunks) {
+				if (cc < n_chunks / 2) {
 #pragma unroll
 					for (uint32_t k = 0; k < LEVELS_PER_CHUNK; ++k) {
 						const uint32_t level = chunk * LEVELS_PER_CHUNK + k;
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 						}
 					}
 				}
-				st_shared_v4(s.enc + sw128(tid, chunk), packed[0], packed[1], packed[2], packed[3]);
+				st_shared_v4(s.enc + sw128(row, chunk), packed[0], packed[1], packed[2], packed[3]);
 				if (p.dbg_enc) *reinterpret_cast<uint4*>(p.dbg_enc + (size_t)sample * 64 + chunk * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
 			}
 		}
@@ -238,8 +243,8 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 			__syncwarp();
 			wait_mma();
 			const uint32_t h_tile = s.h0 + l * TILE_BYTES;
-#pragma unroll
-			for (uint32_t half = 0; half < 2; ++half) {
+			{
+				const uint32_t half = hsel;  // this thread's 32 accumulator columns
 				uint32_t r[32];
 				tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
 				tmem_ld_wait();
@@ -247,7 +252,7 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 				for (uint32_t c = 0; c < 4; ++c) {
 					const uint32_t v0 = relu_pack(r[c * 8 + 0], r[c * 8 + 1]), v1 = relu_pack(r[c * 8 + 2], r[c * 8 + 3]);
 					const uint32_t v2 = relu_pack(r[c * 8 + 4], r[c * 8 + 5]), v3 = relu_pack(r[c * 8 + 6], r[c * 8 + 7]);
-					st_shared_v4(h_tile + sw128(tid, half * 4 + c), v0, v1, v2, v3);
+					st_shared_v4(h_tile + sw128(row, half * 4 + c), v0, v1, v2, v3);
 					if (p.dbg_hidden) *reinterpret_cast<uint4*>(p.dbg_hidden + ((size_t)l * p.batch_size + sample) * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
 				}
 			}
@@ -263,7 +268,7 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 		}
 		__syncwarp();
 		wait_mma();
-		{
+		if (hsel == 0) {
 			uint32_t r[16];
 			tmem_ld_32x32b_x16(tmem_acc + lane_field, r);
 			tmem_ld_wait();
@@ -305,8 +310,8 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 					dy[j] = __float2half_rn(g);
 				}
 				const uint4 lo = *reinterpret_cast<uint4*>(&dy[0]), hi = *reinterpret_cast<uint4*>(&dy[8]);
-				st_shared_v4(s.gB + sw128(tid, 0), lo.x, lo.y, lo.z, lo.w);
-				st_shared_v4(s.gB + sw128(tid, 1), hi.x, hi.y, hi.z, hi.w);
+				st_shared_v4(s.gB + sw128(row, 0), lo.x, lo.y, lo.z, lo.w);
+				st_shared_v4(s.gB + sw128(row, 1), hi.x, hi.y, hi.z, hi.w);
 				if (p.dbg_dy) {
 					uint4* dst = reinterpret_cast<uint4*>(p.dbg_dy + (size_t)sample * 16);
 					dst[0] = lo;
@@ -332,18 +337,18 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 			wait_mma();
 			{
 				const uint32_t h_tile = s.h0 + (NH - 1) * TILE_BYTES;
-#pragma unroll
-				for (uint32_t half = 0; half < 2; ++half) {
+				{
+					const uint32_t half = hsel;
 					uint32_t r[32];
 					tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
 					tmem_ld_wait();
 #pragma unroll
 					for (uint32_t c = 0; c < 4; ++c) {
 						uint32_t f0, f1, f2, f3;
-						ld_shared_v4(h_tile + sw128(tid, half * 4 + c), f0, f1, f2, f3);
+						ld_shared_v4(h_tile + sw128(row, half * 4 + c), f0, f1, f2, f3);
 						const uint32_t v0 = relu_bwd_pack(r[c * 8 + 0], r[c * 8 + 1], f0), v1 = relu_bwd_pack(r[c * 8 + 2], r[c * 8 + 3], f1);
 						const uint32_t v2 = relu_bwd_pack(r[c * 8 + 4], r[c * 8 + 5], f2), v3 = relu_bwd_pack(r[c * 8 + 6], r[c * 8 + 7], f3);
-						st_shared_v4(g_cur + sw128(tid, half * 4 + c), v0, v1, v2, v3);
+						st_shared_v4(g_cur + sw128(row, half * 4 + c), v0, v1, v2, v3);
 						if (p.dbg_grad_hidden) *reinterpret_cast<uint4*>(p.dbg_grad_hidden + ((size_t)(NH - 1) * p.batch_size + sample) * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
 					}
 				}
@@ -365,18 +370,18 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 				__syncwarp();
 				wait_mma();
 				const uint32_t h_tile = s.h0 + (l - 1) * TILE_BYTES;
-#pragma unroll
-				for (uint32_t half = 0; half < 2; ++half) {
+				{
+					const uint32_t half = hsel;
 					uint32_t r[32];
 					tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
 					tmem_ld_wait();
 #pragma unroll
 					for (uint32_t c = 0; c < 4; ++c) {
 						uint32_t f0, f1, f2, f3;
-						ld_shared_v4(h_tile + sw128(tid, half * 4 + c), f0, f1, f2, f3);
+						ld_shared_v4(h_tile + sw128(row, half * 4 + c), f0, f1, f2, f3);
 						const uint32_t v0 = relu_bwd_pack(r[c * 8 + 0], r[c * 8 + 1], f0), v1 = relu_bwd_pack(r[c * 8 + 2], r[c * 8 + 3], f1);
 						const uint32_t v2 = relu_bwd_pack(r[c * 8 + 4], r[c * 8 + 5], f2), v3 = relu_bwd_pack(r[c * 8 + 6], r[c * 8 + 7], f3);
-						st_shared_v4(g_other + sw128(tid, half * 4 + c), v0, v1, v2, v3);
+						st_shared_v4(g_other + sw128(row, half * 4 + c), v0, v1, v2, v3);
 						if (p.dbg_grad_hidden) *reinterpret_cast<uint4*>(p.dbg_grad_hidden + ((size_t)(l - 1) * p.batch_size + sample) * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
 					}
 				}
@@ -402,11 +407,15 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 			// ============================================================ hash-grid gradient scatter (grid.h:215-320)
 			{
 				// dL/d(encoded) is an fp16 matrix in the reference (output of fc_multiply, fully_fused_mlp.cu:835): round the
-				// fp32 accumulator once, park this sample's row in its own (now idle) row of the enc tile.
-#pragma unroll
-				for (uint32_t half = 0; half < 2; ++half) {
+				// fp32 accumulator once. Each of the two threads of a sample reads the in_w/2 columns of ITS levels and parks them
+				// in its private half (4 chunks) of the sample's now idle enc-tile row.
+				constexpr uint32_t LEVELS_PER_CHUNK = 8 / F;
+				const uint32_t n_chunks = in_w / 8;
+				const uint32_t level_begin = hsel * (n_chunks / 2) * LEVELS_PER_CHUNK;
+				const uint32_t level_end = min(p.grid.n_levels, level_begin + (n_chunks / 2) * LEVELS_PER_CHUNK);
+				{
 					uint32_t r[32];
-					tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
+					tmem_ld_32x32b_x32(tmem_acc + lane_field + hsel * (in_w / 2), r);
 					tmem_ld_wait();
 #pragma unroll
 					for (uint32_t c = 0; c < 4; ++c) {
@@ -414,19 +423,19 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 						const uint32_t v1 = pack_half2(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3]));
 						const uint32_t v2 = pack_half2(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5]));
 						const uint32_t v3 = pack_half2(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7]));
-						st_shared_v4(s.enc + sw128(tid, half * 4 + c), v0, v1, v2, v3);
-						if (p.dbg_denc) *reinterpret_cast<uint4*>(p.dbg_denc + (size_t)sample * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
+						st_shared_v4(s.enc + sw128(row, hsel * 4 + c), v0, v1, v2, v3);
+						if (p.dbg_denc && c < n_chunks / 2) *reinterpret_cast<uint4*>(p.dbg_denc + (size_t)sample * 64 + (hsel * (n_chunks / 2) + c) * 8) = make_uint4(v0, v1, v2, v3);
 					}
 				}
 				__half* __restrict__ grad_table = p.grads + p.n_mlp_params;
 #pragma unroll 2
-				for (uint32_t level = 0; level < p.grid.n_levels; ++level) {
+				for (uint32_t level = level_begin; level < level_end; ++level) {
 					const LevelInfo lv = p.grid.levels[level];
 					CellPos<D> cp;
 					pos_fract<D>(x, lv.scale, p.grid.interpolation, cp);
 					uint32_t gbits;
-					const uint32_t feat = level * F;  // 2 features = one 32-bit word
-					asm volatile("ld.shared.b32 %0, [%1];" : "=r"(gbits) : "r"(s.enc + sw128(tid, feat >> 3) + (feat & 7u) * 2u));
+					const uint32_t feat = (level - level_begin) * F;  // 2 features = one 32-bit word of this thread's half row
+					asm volatile("ld.shared.b32 %0, [%1];" : "=r"(gbits) : "r"(s.enc + sw128(row, hsel * 4 + (feat >> 3)) + (feat & 7u) * 2u));
 					const __half2 grad = *reinterpret_cast<const __half2*>(&gbits);
 					uint32_t* __restrict__ lt = reinterpret_cast<uint32_t*>(grad_table + (size_t)lv.offset * F);
 #pragma unroll
@@ -451,35 +460,34 @@ __global__ void __launch_bounds__(128, 2) fused_step_kernel(const FusedStepParam
 		__syncthreads();
 		tc_fence_after_sync();
 		if (dw_started) {
-			// M = 64 accumulators: row m lives in TMEM lane (m % 16) + 32 * (m / 16) -> lanes 0..15 of each warp.
+			// M = 64 accumulators: row m lives in TMEM lane (m % 16) + 32 * (m / 16) -> lanes 0..15 of each lane quadrant.
+			// Warp w reads quadrant w & 3 and column half w >> 2.
 			const uint32_t lane = tid & 31u;
-			const uint32_t m = warp * 16 + lane;
+			const uint32_t m = (warp & 3u) * 16 + lane;
+			const uint32_t half = hsel;
 			for (uint32_t l = 0; l <= NH; ++l) {
 				const uint32_t dw = tmem_base + 64u * (1 + l) + lane_field;
+				uint32_t r[32];
+				tmem_ld_32x32b_x32(dw + half * 32, r);
+				tmem_ld_wait();
+				if (lane < 16) {
+					if (l == 0) {
+						// dW_0[out = m][in = n], n < in_w
+						float* dst = p.dw_accum + m * in_w;
 #pragma unroll
-				for (uint32_t half = 0; half < 2; ++half) {
-					uint32_t r[32];
-					tmem_ld_32x32b_x32(dw + half * 32, r);
-					tmem_ld_wait();
-					if (lane < 16) {
-						if (l == 0) {
-							// dW_0[out = m][in = n], n < in_w
-							float* dst = p.dw_accum + m * in_w;
-#pragma unroll
-							for (uint32_t k = 0; k < 32; ++k) {
-								const uint32_t n = half * 32 + k;
-								if (n < in_w) red_add_f32(dst + n, __uint_as_float(r[k]));
-							}
-						} else if (l < NH) {
-							float* dst = p.dw_accum + WIDTH * in_w + (l - 1) * WIDTH * WIDTH + m * WIDTH + half * 32;
-#pragma unroll
-							for (uint32_t k = 0; k < 32; ++k) red_add_f32(dst + k, __uint_as_float(r[k]));
-						} else if (half == 0) {
-							// accumulator holds dW_out^T[in = m][out = n], n < 16
-							float* dst = p.dw_accum + WIDTH * in_w + (NH - 1) * WIDTH * WIDTH;
-#pragma unroll
-							for (uint32_t n = 0; n < 16; ++n) red_add_f32(dst + n * WIDTH + m, __uint_as_float(r[n]));
+						for (uint32_t k = 0; k < 32; k += 4) {
+							const uint32_t n = half * 32 + k;
+							if (n < in_w) red_add_v4_f32(dst + n, __uint_as_float(r[k]), __uint_as_float(r[k + 1]), __uint_as_float(r[k + 2]), __uint_as_float(r[k + 3]));
 						}
+					} else if (l < NH) {
+						float* dst = p.dw_accum + WIDTH * in_w + (l - 1) * WIDTH * WIDTH + m * WIDTH + half * 32;
+#pragma unroll
+						for (uint32_t k = 0; k < 32; k += 4) red_add_v4_f32(dst + k, __uint_as_float(r[k]), __uint_as_float(r[k + 1]), __uint_as_float(r[k + 2]), __uint_as_float(r[k + 3]));
+					} else if (half == 0) {
+						// accumulator holds dW_out^T[in = m][out = n], n < 16
+						float* dst = p.dw_accum + WIDTH * in_w + (NH - 1) * WIDTH * WIDTH;
+#pragma unroll
+						for (uint32_t n = 0; n < 16; ++n) red_add_f32(dst + n * WIDTH + m, __uint_as_float(r[n]));
 					}
 				}
 			}
@@ -508,7 +516,7 @@ static cudaError_t launch_impl(const FusedStepParams& p, uint32_t n_ctas, cudaSt
 	const size_t smem = fused_step_smem_bytes(p.n_hidden_layers, TRAIN);
 	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (err != cudaSuccess) return err;
-	kernel<<<n_ctas, 128, smem, stream>>>(p);
+	kernel<<<n_ctas, 256, smem, stream>>>(p);
 	return cudaGetLastError();
 }
 

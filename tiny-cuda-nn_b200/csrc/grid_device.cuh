@@ -31,6 +31,20 @@ __device__ __forceinline__ void pos_fract(const float (&x)[D], float scale, uint
 	}
 }
 
+// index % size without a division wherever the level allows it (warp-uniform choice).
+__device__ __forceinline__ uint32_t level_mod(const LevelInfo& lv, uint32_t index) {
+	if (lv.pow2_mask) return index & lv.pow2_mask;
+	if (lv.small_mod) {
+		// in-range positions give index < 2 * size; positions outside [0,1) (wrap-around indexing) take the slow exact path
+		if (index >= lv.size) {
+			index -= lv.size;
+			if (index >= lv.size) index %= lv.size;
+		}
+		return index;
+	}
+	return index % lv.size;
+}
+
 // Entry index of one corner inside its level.
 template <uint32_t D>
 __device__ __forceinline__ uint32_t corner_index(const LevelInfo& lv, const uint32_t (&c)[D]) {
@@ -48,7 +62,7 @@ __device__ __forceinline__ uint32_t corner_index(const LevelInfo& lv, const uint
 			stride *= lv.resolution;
 		}
 	}
-	return lv.pow2_mask ? (index & lv.pow2_mask) : (index % lv.size);
+	return level_mod(lv, index);
 }
 
 // Corner `idx` of the cell: coordinates and fp32 interpolation weight, multiplied in dimension order like the reference.
@@ -85,8 +99,26 @@ __device__ __forceinline__ CornerPair<D> corner_pair(const LevelInfo& lv, const 
 	uint32_t c0[D], c1[D];
 	r.w0 = corner<D>(p, 2 * pair, c0);
 	r.w1 = corner<D>(p, 2 * pair + 1, c1);
-	r.idx0 = corner_index<D>(lv, c0);
-	r.idx1 = corner_index<D>(lv, c1);
+	// Both corners share every coordinate but x: hash / stride contribution of dims 1.. is computed once.
+	if (lv.use_hash == LEVEL_HASH) {
+		uint32_t rest = 0;
+		if (D > 1) rest ^= c0[1] * 2654435761u;
+		if (D > 2) rest ^= c0[2] * 805459861u;
+		if (D > 3) rest ^= c0[3] * 3674653429u;
+		r.idx0 = level_mod(lv, c0[0] ^ rest);
+		r.idx1 = level_mod(lv, c1[0] ^ rest);
+	} else if (lv.use_hash == LEVEL_DENSE) {
+		uint32_t rest = 0, stride = lv.resolution;
+#pragma unroll
+		for (uint32_t d = 1; d < D; ++d) {
+			rest += c0[d] * stride;
+			stride *= lv.resolution;
+		}
+		r.idx0 = level_mod(lv, c0[0] + rest);
+		r.idx1 = level_mod(lv, c1[0] + rest);
+	} else {
+		r.idx0 = r.idx1 = 0;
+	}
 	r.paired = (r.idx0 ^ r.idx1) == 1u;
 	return r;
 }

@@ -184,22 +184,26 @@ __global__ void __launch_bounds__(256) adam_step_vec4_kernel(const AdamParams a,
 	if (gidx >= n_groups) return;
 	const uint32_t i0 = gidx * 4;
 
+	// Issue every load of this group up front (independent 128-bit streams); the zero-gradient early-out below only
+	// saves the write-back -- untouched groups are ~2 % of a step, memory-level parallelism matters more.
+	const bool from_accum = i0 + 3 < n_matrix_weights && dw_accum != nullptr;
+	const uint2 raw = from_accum ? make_uint2(0, 0) : gradients[gidx];
+	const float4 w4 = __ldcs(weights_full_precision + gidx);
+	const float4 m4 = __ldcs(first_moments + gidx);
+	const float4 v4 = __ldcs(second_moments + gidx);
+	const uint4 s4 = __ldcs(param_steps + gidx);
+
 	__half g[4];
-	if (i0 + 3 < n_matrix_weights && dw_accum != nullptr) {
+	if (from_accum) {
 		const float4 acc = dw_accum[gidx];
 		dw_accum[gidx] = make_float4(0.f, 0.f, 0.f, 0.f);
 		g[0] = (__half)acc.x; g[1] = (__half)acc.y; g[2] = (__half)acc.z; g[3] = (__half)acc.w;
 		gradients[gidx] = *reinterpret_cast<const uint2*>(g);
 	} else {
-		const uint2 raw = gradients[gidx];
 		*reinterpret_cast<uint2*>(g) = raw;
 		if (i0 >= n_matrix_weights && a.skip_zero_grad_non_matrix_params && ((raw.x | raw.y) & 0x7FFF7FFFu) == 0) return;  // all four are +-0
 	}
 
-	float4 w4 = __ldcs(weights_full_precision + gidx);
-	float4 m4 = __ldcs(first_moments + gidx);
-	float4 v4 = __ldcs(second_moments + gidx);
-	uint4 s4 = __ldcs(param_steps + gidx);
 	float w[4] = {w4.x, w4.y, w4.z, w4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
 	uint32_t st[4] = {s4.x, s4.y, s4.z, s4.w};
 	bool any = false;

@@ -329,6 +329,8 @@ struct Model {
 			if (grid.grid_type == GRID_HASH && lv.size < stride) lv.use_hash = 1;
 			else lv.use_hash = dense_ok ? 0 : 2;
 			lv.pow2_mask = (lv.size & (lv.size - 1)) == 0 ? lv.size - 1 : 0;
+			// dense index <= res * (res^D - 1) / (res - 1) < 2 * res^D: a conditional subtract is an exact modulo when size >= res^D
+			lv.small_mod = (lv.use_hash == 0 && stride != 0xFFFFFFFFu && lv.size >= stride && lv.resolution >= 2) ? 1 : 0;
 		}
 		return m;
 	}

@@ -141,5 +141,10 @@ __device__ __forceinline__ void red_add_f32(float* addr, float v) {
 	asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 
+// 16-byte vector reduction (sm_90+): four fp32 adds in one L2 operation; address must be 16-byte aligned.
+__device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
+	asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 }  // namespace ptx
 }  // namespace tcnnb
