@@ -180,52 +180,49 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 #pragma unroll
 		for (uint32_t d = 0; d < D; ++d) x[d] = __ldg(p.positions + (size_t)sample * D + d);
 
+		static_assert(F == 2, "fused path: F == 2");
+		constexpr uint32_t LEVELS_PER_CHUNK = 8 / F;  // one 16-byte chunk = 8 features
+		const uint32_t n_chunks = in_w / 8;             // even: in_w is a multiple of 16
+		// This thread's levels: the level-bearing chunks are split evenly between the two threads of a sample.
+		const uint32_t level_begin = hsel * (n_chunks / 2) * LEVELS_PER_CHUNK;
+		const uint32_t level_end = min(p.grid.n_levels, level_begin + (n_chunks / 2) * LEVELS_PER_CHUNK);
 		{
-			static_assert(F == 2, "fused path: F == 2");
-			constexpr uint32_t LEVELS_PER_CHUNK = 8 / F;  // one 16-byte chunk = 8 features
+			// Zero this thread's 4 chunks of the row first (padding features are zero, grid.h:759-766), then drop each level's
+			// fp16x2 result into place. The loop is deliberately NOT unrolled: the L1 wavefront pipe, not load latency, bounds the
+			// gather, and the unrolled body overflowed the instruction caches (profiles/r01_*).
+			const uint32_t my_chunk0 = hsel * (n_chunks / 2);
+#pragma unroll
+			for (uint32_t c = 0; c < 4; ++c) {
+				const uint32_t chunk = c < n_chunks / 2 ? my_chunk0 + c : n_chunks + hsel * ((8 - n_chunks) / 2) + (c - n_chunks / 2);
+				st_shared_v4(s.enc + sw128(row, chunk), 0, 0, 0, 0);
+			}
 			const __half* __restrict__ table = p.params + p.n_mlp_params;
-			const uint32_t n_chunks = in_w / 8;  // even: in_w is a multiple of 16
-			// level-bearing chunks [0, n_chunks) and zero chunks [n_chunks, 8) are both split evenly between the two threads
-			for (uint32_t cc = 0; cc < 4; ++cc) {
-				const uint32_t chunk = cc < n_chunks / 2 ? hsel * (n_chunks / 2) + cc : n_chunks + hsel * ((8 - n_chunks) / 2) + (cc - n_chunks / 2);
-				uint32_t packed[4] = {0, 0, 0, 0};
-				if (cc < n_chunks / 2) {
+#pragma unroll 1
+			for (uint32_t level = level_begin; level < level_end; ++level) {
+				const LevelInfo lv = p.grid.levels[level];
+				LevelCorners<D> lc;
+				level_corners<D>(lv, x, p.grid.interpolation, lc);
+				const uint32_t* __restrict__ lt = reinterpret_cast<const uint32_t*>(table + (size_t)lv.offset * F);
+				uint32_t vals[1u << D];
 #pragma unroll
-					for (uint32_t k = 0; k < LEVELS_PER_CHUNK; ++k) {
-						const uint32_t level = chunk * LEVELS_PER_CHUNK + k;
-						if (level < p.grid.n_levels) {  // warp-uniform; levels beyond n_levels are zero padding (grid.h:759-766)
-							const LevelInfo lv = p.grid.levels[level];
-							CellPos<D> cp;
-							pos_fract<D>(x, lv.scale, p.grid.interpolation, cp);
-							const uint32_t* __restrict__ lt = reinterpret_cast<const uint32_t*>(table + (size_t)lv.offset * F);
-							uint32_t vals[1u << D];
-							float wts[1u << D];
-#pragma unroll
-							for (uint32_t pr = 0; pr < (1u << (D - 1)); ++pr) {
-								const CornerPair<D> cpair = corner_pair<D>(lv, cp, pr);
-								wts[2 * pr] = cpair.w0;
-								wts[2 * pr + 1] = cpair.w1;
-								if (p.ablate & ABLATE_GATHER) {
-									vals[2 * pr] = cpair.idx0;
-									vals[2 * pr + 1] = cpair.idx1;
-								} else if (p.ablate & ABLATE_PAIRING) {
-									gather_pair_f16x2(lt, cpair.idx0, cpair.idx1, false, vals[2 * pr], vals[2 * pr + 1]);
-								} else {
-									gather_pair_f16x2(lt, cpair.idx0, cpair.idx1, cpair.paired, vals[2 * pr], vals[2 * pr + 1]);
-								}
-							}
-							__half2 result = __float2half2_rn(0.0f);
-#pragma unroll
-							for (uint32_t idx = 0; idx < (1u << D); ++idx) {
-								// fma((T)weight, grid_val, result) with T = __half -> __hfma2 (grid.h:162, vec.h:372-378)
-								result = __hfma2(__float2half2_rn(wts[idx]), *reinterpret_cast<const __half2*>(&vals[idx]), result);
-							}
-							packed[k] = *reinterpret_cast<uint32_t*>(&result);
-						}
+				for (uint32_t pr = 0; pr < (1u << (D - 1)); ++pr) {
+					const bool paired = (lc.paired >> pr) & 1u;
+					if (p.ablate & ABLATE_GATHER) {
+						vals[2 * pr] = lc.idx[2 * pr];
+						vals[2 * pr + 1] = lc.idx[2 * pr + 1];
+					} else {
+						gather_pair_f16x2(lt, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(p.ablate & ABLATE_PAIRING), vals[2 * pr], vals[2 * pr + 1]);
 					}
 				}
-				st_shared_v4(s.enc + sw128(row, chunk), packed[0], packed[1], packed[2], packed[3]);
-				if (p.dbg_enc) *reinterpret_cast<uint4*>(p.dbg_enc + (size_t)sample * 64 + chunk * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+				__half2 result = __float2half2_rn(0.0f);
+#pragma unroll
+				for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+					// fma((T)weight, grid_val, result) with T = __half -> __hfma2 (grid.h:162, vec.h:372-378)
+					result = __hfma2(__float2half2_rn(lc.w[idx]), *reinterpret_cast<const __half2*>(&vals[idx]), result);
+				}
+				const uint32_t feat = level * F;
+				asm volatile("st.shared.b32 [%0], %1;" ::"r"(s.enc + sw128(row, feat >> 3) + (feat & 7u) * 2u), "r"(*reinterpret_cast<uint32_t*>(&result)) : "memory");
+				if (p.dbg_enc) *reinterpret_cast<uint32_t*>(p.dbg_enc + (size_t)sample * 64 + feat) = *reinterpret_cast<uint32_t*>(&result);
 			}
 		}
 
@@ -409,10 +406,6 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 				// dL/d(encoded) is an fp16 matrix in the reference (output of fc_multiply, fully_fused_mlp.cu:835): round the
 				// fp32 accumulator once. Each of the two threads of a sample reads the in_w/2 columns of ITS levels and parks them
 				// in its private half (4 chunks) of the sample's now idle enc-tile row.
-				constexpr uint32_t LEVELS_PER_CHUNK = 8 / F;
-				const uint32_t n_chunks = in_w / 8;
-				const uint32_t level_begin = hsel * (n_chunks / 2) * LEVELS_PER_CHUNK;
-				const uint32_t level_end = min(p.grid.n_levels, level_begin + (n_chunks / 2) * LEVELS_PER_CHUNK);
 				{
 					uint32_t r[32];
 					tmem_ld_32x32b_x32(tmem_acc + lane_field + hsel * (in_w / 2), r);
@@ -428,11 +421,11 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 					}
 				}
 				__half* __restrict__ grad_table = p.grads + p.n_mlp_params;
-#pragma unroll 2
+#pragma unroll 1
 				for (uint32_t level = level_begin; level < level_end; ++level) {
 					const LevelInfo lv = p.grid.levels[level];
-					CellPos<D> cp;
-					pos_fract<D>(x, lv.scale, p.grid.interpolation, cp);
+					LevelCorners<D> lc;
+					level_corners<D>(lv, x, p.grid.interpolation, lc);
 					uint32_t gbits;
 					const uint32_t feat = (level - level_begin) * F;  // 2 features = one 32-bit word of this thread's half row
 					asm volatile("ld.shared.b32 %0, [%1];" : "=r"(gbits) : "r"(s.enc + sw128(row, hsel * 4 + (feat >> 3)) + (feat & 7u) * 2u));
@@ -440,12 +433,12 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 					uint32_t* __restrict__ lt = reinterpret_cast<uint32_t*>(grad_table + (size_t)lv.offset * F);
 #pragma unroll
 					for (uint32_t pr = 0; pr < (1u << (D - 1)); ++pr) {
-						const CornerPair<D> cpair = corner_pair<D>(lv, cp, pr);
 						// (GRAD_T)weight * grad -> __hmul2, then atomic f16x2 add (grid.h:252-255, vec.h:328-336)
-						const __half2 a0 = __hmul2(__float2half2_rn(cpair.w0), grad);
-						const __half2 a1 = __hmul2(__float2half2_rn(cpair.w1), grad);
+						const __half2 a0 = __hmul2(__float2half2_rn(lc.w[2 * pr]), grad);
+						const __half2 a1 = __hmul2(__float2half2_rn(lc.w[2 * pr + 1]), grad);
+						const bool paired = (lc.paired >> pr) & 1u;
 						if (!(p.ablate & ABLATE_SCATTER)) {
-							scatter_pair_f16x2(lt, cpair.idx0, cpair.idx1, cpair.paired && !(p.ablate & ABLATE_PAIRING), *reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
+							scatter_pair_f16x2(lt, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(p.ablate & ABLATE_PAIRING), *reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
 						}
 					}
 				}

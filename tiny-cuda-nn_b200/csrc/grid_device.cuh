@@ -35,11 +35,9 @@ __device__ __forceinline__ void pos_fract(const float (&x)[D], float scale, uint
 __device__ __forceinline__ uint32_t level_mod(const LevelInfo& lv, uint32_t index) {
 	if (lv.pow2_mask) return index & lv.pow2_mask;
 	if (lv.small_mod) {
-		// in-range positions give index < 2 * size; positions outside [0,1) (wrap-around indexing) take the slow exact path
-		if (index >= lv.size) {
-			index -= lv.size;
-			if (index >= lv.size) index %= lv.size;
-		}
+		// in-range positions give index < 2 * size; positions outside [0,1) (wrap-around indexing) take the exact slow path
+		index -= index >= lv.size ? lv.size : 0u;
+		if (index >= lv.size) index %= lv.size;
 		return index;
 	}
 	return index % lv.size;
@@ -121,6 +119,79 @@ __device__ __forceinline__ CornerPair<D> corner_pair(const LevelInfo& lv, const 
 	}
 	r.paired = (r.idx0 ^ r.idx1) == 1u;
 	return r;
+}
+
+// All 2^D corners of one cell at one level: interpolation weights in the reference's multiplication order
+// (weight = 1 * t_x * t_y * t_z, grid.h:146-157), entry indices, and which x-pairs (corners 2k, 2k+1) share an aligned
+// 8-byte slot. Contributions of the non-x dimensions to the hash / dense stride are computed once per value, not per corner.
+template <uint32_t D>
+struct LevelCorners {
+	float w[1u << D];
+	uint32_t idx[1u << D];
+	uint32_t paired;  // bit k: pair k is covered by one 64-bit access at (idx[2k] & ~1)
+};
+
+template <uint32_t D>
+__device__ __forceinline__ void level_corners(const LevelInfo& lv, const float (&x)[D], uint32_t interpolation, LevelCorners<D>& out) {
+	CellPos<D> cp;
+	pos_fract<D>(x, lv.scale, interpolation, cp);
+	// weights: w[i] for corner bits (b0 = x, b1 = y, ...), built dimension by dimension -> ((t_x * t_y) * t_z)
+	out.w[0] = 1.0f - cp.frac[0];
+	out.w[1] = cp.frac[0];
+#pragma unroll
+	for (uint32_t d = 1; d < D; ++d) {
+		const float hi = cp.frac[d], lo = 1.0f - cp.frac[d];
+#pragma unroll
+		for (uint32_t i = 0; i < (1u << d); ++i) {
+			out.w[i + (1u << d)] = out.w[i] * hi;
+			out.w[i] = out.w[i] * lo;
+		}
+	}
+	// indices
+	uint32_t rest[1u << (D - 1)];
+	rest[0] = 0;
+	if (lv.use_hash == LEVEL_HASH) {
+		constexpr uint32_t primes[4] = {1u, 2654435761u, 805459861u, 3674653429u};
+#pragma unroll
+		for (uint32_t d = 1; d < D; ++d) {
+			const uint32_t h0 = cp.cell[d] * primes[d], h1 = h0 + primes[d];
+#pragma unroll
+			for (uint32_t i = 0; i < (1u << (d - 1)); ++i) {
+				rest[i + (1u << (d - 1))] = rest[i] ^ h1;
+				rest[i] = rest[i] ^ h0;
+			}
+		}
+#pragma unroll
+		for (uint32_t k = 0; k < (1u << (D - 1)); ++k) {
+			out.idx[2 * k] = level_mod(lv, cp.cell[0] ^ rest[k]);
+			out.idx[2 * k + 1] = level_mod(lv, (cp.cell[0] + 1u) ^ rest[k]);
+		}
+	} else if (lv.use_hash == LEVEL_DENSE) {
+		uint32_t stride = lv.resolution;
+#pragma unroll
+		for (uint32_t d = 1; d < D; ++d) {
+			const uint32_t s0 = cp.cell[d] * stride, s1 = s0 + stride;
+#pragma unroll
+			for (uint32_t i = 0; i < (1u << (d - 1)); ++i) {
+				rest[i + (1u << (d - 1))] = rest[i] + s1;
+				rest[i] = rest[i] + s0;
+			}
+			stride *= lv.resolution;
+		}
+#pragma unroll
+		for (uint32_t k = 0; k < (1u << (D - 1)); ++k) {
+			out.idx[2 * k] = level_mod(lv, cp.cell[0] + rest[k]);
+			out.idx[2 * k + 1] = level_mod(lv, cp.cell[0] + 1u + rest[k]);
+		}
+	} else {
+#pragma unroll
+		for (uint32_t i = 0; i < (1u << D); ++i) out.idx[i] = 0;
+	}
+	out.paired = 0;
+#pragma unroll
+	for (uint32_t k = 0; k < (1u << (D - 1)); ++k) {
+		if ((out.idx[2 * k] ^ out.idx[2 * k + 1]) == 1u) out.paired |= 1u << k;
+	}
 }
 
 // Gather the two fp16x2 entries of a corner pair: one 64-bit load when they share an aligned slot, else two 32-bit loads.
