@@ -67,8 +67,8 @@ __device__ __forceinline__ uint32_t relu_bwd_pack(uint32_t lo_bits, uint32_t hi_
 
 struct Smem {
 	// dynamic shared memory, 1024-byte aligned:
-	//   [ enc | h_0 .. h_{NH-1} | gA | gB(=dy) | W_0 | W_1 .. W_{NH-1} | W_out ] then barriers
-	uint32_t enc, h0, gA, gB, w0, w_out, bar, tmem_slot;
+	//   [ enc_0 | enc_1 | h_0 .. h_{NH-1} | dy | (park) | W_0 .. W_{NH-1} | W_out ] then barriers
+	uint32_t enc, h0, dy, park, w0, w_out, bar, tmem_slot;
 };
 
 }  // namespace
@@ -76,6 +76,7 @@ struct Smem {
 // ------------------------------------------------------------------------------------------------------------------
 template <uint32_t D, uint32_t F, bool TRAIN>
 __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParams p) {
+	static_assert(F == 2, "fused path: F == 2");
 	extern __shared__ __align__(1024) uint8_t smem_raw[];
 	const uint32_t tid = threadIdx.x;
 	const uint32_t warp = tid >> 5;
@@ -85,16 +86,20 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 	const uint32_t in_w = p.grid.padded_width;
 
 	// ---- shared memory carve-up (all tile bases 1024-aligned)
+	//   [ enc_0 | enc_1 | h_0 .. h_{NH-1} | dy (+ parked dL/d(enc)) | (park tile if in_w > 48) | W_0 .. W_{NH-1} | W_out ] barriers
+	// The backward activations g_l overwrite h_l in place, so there are no separate gradient tiles.
 	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 	Smem s;
-	s.enc = smem_base;
-	s.h0 = s.enc + TILE_BYTES;
-	s.gA = s.h0 + NH * TILE_BYTES;
-	s.gB = s.gA + (TRAIN ? TILE_BYTES : 0);
-	s.w0 = s.gB + TILE_BYTES;
+	s.enc = smem_base;                                  // two buffers: tile t and tile t+1
+	s.h0 = s.enc + 2 * TILE_BYTES;
+	s.dy = s.h0 + NH * TILE_BYTES;
+	const bool park_in_dy = in_w <= 48;               // 96 spare bytes per dy row hold 2 x 12 levels of parked gradients
+	s.park = park_in_dy ? s.dy : s.dy + TILE_BYTES;
+	s.w0 = s.dy + (TRAIN ? (park_in_dy ? 1 : 2) : 0) * TILE_BYTES;
 	s.w_out = s.w0 + NH * (WIDTH * 128);
 	s.bar = s.w_out + 16 * 128;
 	s.tmem_slot = s.bar + 8;
+	const uint32_t park_f0 = park_in_dy ? 16 + hsel * 24 : hsel * 32;  // first fp16 column of this thread's parking slots
 
 	// ---- one-time setup: barrier, TMEM, weights
 	const uint32_t tmem_cols = TRAIN ? (NH + 2) * 64 <= 256 ? 256u : 512u : 64u;
@@ -111,8 +116,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 	// Stage the fp16 weights: W_l rows are 128-byte tile rows (K-major, SWIZZLE_128B); unused columns are zeroed.
 	{
 		const __half* __restrict__ w = p.params;  // MLP weights come first in the parameter buffer
-		// first layer: [64][in_w]
-		for (uint32_t i = tid; i < WIDTH * 8; i += 256) {
+		for (uint32_t i = tid; i < WIDTH * 8; i += 256) {  // first layer: [64][in_w]
 			const uint32_t r = i >> 3, c = i & 7;
 			uint4 v = make_uint4(0, 0, 0, 0);
 			if (c * 8 < in_w) v = __ldg(reinterpret_cast<const uint4*>(w + r * in_w + c * 8));
@@ -168,282 +172,282 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 		tc_fence_after_sync();
 	};
 
-	float loss_acc = 0.0f;
-	bool dw_started = false;
+	// ---- this thread's share of the resolution levels: the level-bearing 16-byte chunks of a row are split evenly
+	constexpr uint32_t LEVELS_PER_CHUNK = 8 / F;
+	const uint32_t n_chunks = in_w / 8;  // even: in_w is a multiple of 16
+	const uint32_t level_begin = hsel * (n_chunks / 2) * LEVELS_PER_CHUNK;
+	const uint32_t level_end = min(p.grid.n_levels, level_begin + (n_chunks / 2) * LEVELS_PER_CHUNK);
+	const uint32_t n_my_levels = level_end > level_begin ? level_end - level_begin : 0;
+	const __half* __restrict__ table = p.params + p.n_mlp_params;
 
-	const uint32_t n_tiles = p.batch_size / TILE_M;
-	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-		const uint32_t sample = tile * TILE_M + row;
-
-		// ================================================================ gather + N-linear blend -> enc tile
-		float x[D];
-#pragma unroll
-		for (uint32_t d = 0; d < D; ++d) x[d] = __ldg(p.positions + (size_t)sample * D + d);
-
-		static_assert(F == 2, "fused path: F == 2");
-		constexpr uint32_t LEVELS_PER_CHUNK = 8 / F;  // one 16-byte chunk = 8 features
-		const uint32_t n_chunks = in_w / 8;             // even: in_w is a multiple of 16
-		// This thread's levels: the level-bearing chunks are split evenly between the two threads of a sample.
-		const uint32_t level_begin = hsel * (n_chunks / 2) * LEVELS_PER_CHUNK;
-		const uint32_t level_end = min(p.grid.n_levels, level_begin + (n_chunks / 2) * LEVELS_PER_CHUNK);
-		{
-			// Zero this thread's 4 chunks of the row first (padding features are zero, grid.h:759-766), then drop each level's
-			// fp16x2 result into place. The loop is deliberately NOT unrolled: the L1 wavefront pipe, not load latency, bounds the
-			// gather, and the unrolled body overflowed the instruction caches (profiles/r01_*).
-			const uint32_t my_chunk0 = hsel * (n_chunks / 2);
+	// Gather + N-linear blend of part `part` of `parts` of this thread's levels for the sample at `x` into tile `enc_tile`.
+	// Loops are deliberately not unrolled: memory-system throughput, not load latency, bounds the gather, and an unrolled
+	// body overflows the instruction caches (profiles/).
+	auto gather_part = [&](const float (&x)[D], uint32_t enc_tile, uint32_t sample, uint32_t part, uint32_t parts) {
+		if (part == 0) {
+			// zero this thread's 4 chunks of the row first (padding features are zero, grid.h:759-766)
 #pragma unroll
 			for (uint32_t c = 0; c < 4; ++c) {
-				const uint32_t chunk = c < n_chunks / 2 ? my_chunk0 + c : n_chunks + hsel * ((8 - n_chunks) / 2) + (c - n_chunks / 2);
-				st_shared_v4(s.enc + sw128(row, chunk), 0, 0, 0, 0);
-			}
-			const __half* __restrict__ table = p.params + p.n_mlp_params;
-#pragma unroll 1
-			for (uint32_t level = level_begin; level < level_end; ++level) {
-				const LevelInfo lv = p.grid.levels[level];
-				LevelCorners<D> lc;
-				level_corners<D>(lv, x, p.grid.interpolation, lc);
-				const uint32_t* __restrict__ lt = reinterpret_cast<const uint32_t*>(table + (size_t)lv.offset * F);
-				uint32_t vals[1u << D];
-#pragma unroll
-				for (uint32_t pr = 0; pr < (1u << (D - 1)); ++pr) {
-					const bool paired = (lc.paired >> pr) & 1u;
-					if (p.ablate & ABLATE_GATHER) {
-						vals[2 * pr] = lc.idx[2 * pr];
-						vals[2 * pr + 1] = lc.idx[2 * pr + 1];
-					} else {
-						gather_pair_f16x2(lt, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(p.ablate & ABLATE_PAIRING), vals[2 * pr], vals[2 * pr + 1]);
-					}
-				}
-				__half2 result = __float2half2_rn(0.0f);
-#pragma unroll
-				for (uint32_t idx = 0; idx < (1u << D); ++idx) {
-					// fma((T)weight, grid_val, result) with T = __half -> __hfma2 (grid.h:162, vec.h:372-378)
-					result = __hfma2(__float2half2_rn(lc.w[idx]), *reinterpret_cast<const __half2*>(&vals[idx]), result);
-				}
-				const uint32_t feat = level * F;
-				asm volatile("st.shared.b32 [%0], %1;" ::"r"(s.enc + sw128(row, feat >> 3) + (feat & 7u) * 2u), "r"(*reinterpret_cast<uint32_t*>(&result)) : "memory");
-				if (p.dbg_enc) *reinterpret_cast<uint32_t*>(p.dbg_enc + (size_t)sample * 64 + feat) = *reinterpret_cast<uint32_t*>(&result);
+				const uint32_t chunk = c < n_chunks / 2 ? hsel * (n_chunks / 2) + c : n_chunks + hsel * ((8 - n_chunks) / 2) + (c - n_chunks / 2);
+				st_shared_v4(enc_tile + sw128(row, chunk), 0, 0, 0, 0);
 			}
 		}
+		const uint32_t lb = level_begin + (n_my_levels * part) / parts, le = level_begin + (n_my_levels * (part + 1)) / parts;
+#pragma unroll 1
+		for (uint32_t level = lb; level < le; ++level) {
+			const LevelInfo lv = p.grid.levels[level];
+			LevelCorners<D> lc;
+			level_corners<D>(lv, x, p.grid.interpolation, lc);
+			const uint32_t* __restrict__ lt = reinterpret_cast<const uint32_t*>(table + (size_t)lv.offset * F);
+			uint32_t vals[1u << D];
+#pragma unroll
+			for (uint32_t pr = 0; pr < (1u << (D - 1)); ++pr) {
+				const bool paired = (lc.paired >> pr) & 1u;
+				if (p.ablate & ABLATE_GATHER) {
+					vals[2 * pr] = lc.idx[2 * pr];
+					vals[2 * pr + 1] = lc.idx[2 * pr + 1];
+				} else {
+					gather_pair_f16x2(lt, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(p.ablate & ABLATE_PAIRING), vals[2 * pr], vals[2 * pr + 1]);
+				}
+			}
+			__half2 result = __float2half2_rn(0.0f);
+#pragma unroll
+			for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+				// fma((T)weight, grid_val, result) with T = __half -> __hfma2 (grid.h:162, vec.h:372-378)
+				result = __hfma2(__float2half2_rn(lc.w[idx]), *reinterpret_cast<const __half2*>(&vals[idx]), result);
+			}
+			const uint32_t feat = level * F;
+			asm volatile("st.shared.b32 [%0], %1;" ::"r"(enc_tile + sw128(row, feat >> 3) + (feat & 7u) * 2u), "r"(*reinterpret_cast<uint32_t*>(&result)) : "memory");
+			if (p.dbg_enc) *reinterpret_cast<uint32_t*>(p.dbg_enc + (size_t)sample * 64 + feat) = *reinterpret_cast<uint32_t*>(&result);
+		}
+	};
 
-		// ================================================================ forward hidden layers
-		for (uint32_t l = 0; l < NH; ++l) {
+	// Scatter part `part` of `parts` of this thread's levels: the parked fp16 dL/d(enc) of the sample at `x`.
+	auto scatter_part = [&](const float (&x)[D], uint32_t part, uint32_t parts) {
+		__half* __restrict__ grad_table = p.grads + p.n_mlp_params;
+		const uint32_t lb = level_begin + (n_my_levels * part) / parts, le = level_begin + (n_my_levels * (part + 1)) / parts;
+#pragma unroll 1
+		for (uint32_t level = lb; level < le; ++level) {
+			const LevelInfo lv = p.grid.levels[level];
+			LevelCorners<D> lc;
+			level_corners<D>(lv, x, p.grid.interpolation, lc);
+			uint32_t gbits;
+			const uint32_t feat = park_f0 + (level - level_begin) * F;  // 2 features = one 32-bit word
+			asm volatile("ld.shared.b32 %0, [%1];" : "=r"(gbits) : "r"(s.park + sw128(row, feat >> 3) + (feat & 7u) * 2u));
+			const __half2 grad = *reinterpret_cast<const __half2*>(&gbits);
+			uint32_t* __restrict__ lt = reinterpret_cast<uint32_t*>(grad_table + (size_t)lv.offset * F);
+#pragma unroll
+			for (uint32_t pr = 0; pr < (1u << (D - 1)); ++pr) {
+				// (GRAD_T)weight * grad -> __hmul2, then atomic f16x2 add (grid.h:252-255, vec.h:328-336)
+				const __half2 a0 = __hmul2(__float2half2_rn(lc.w[2 * pr]), grad);
+				const __half2 a1 = __hmul2(__float2half2_rn(lc.w[2 * pr + 1]), grad);
+				const bool paired = (lc.paired >> pr) & 1u;
+				if (!(p.ablate & ABLATE_SCATTER)) {
+					scatter_pair_f16x2(lt, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(p.ablate & ABLATE_PAIRING), *reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
+				}
+			}
+		}
+	};
+
+	auto load_x = [&](uint32_t tile, float (&x)[D]) {
+#pragma unroll
+		for (uint32_t d = 0; d < D; ++d) x[d] = __ldg(p.positions + ((size_t)tile * TILE_M + row) * D + d);
+	};
+
+	// ---- software pipeline over this CTA's tiles: while the tensor core works on tile t (2*NH + 2 MMA batches, each followed
+	// by an mbarrier wait), the wait slots are filled with the gather of tile t+1 (slots 0,1) and the scatter of tile t-1
+	// (slots 2..). The gather / scatter of a tile therefore never sit on the critical path of its own MLP chain.
+	constexpr uint32_t GATHER_PARTS = 2;
+	const uint32_t n_slots = 2 * NH + 2;
+	const uint32_t scatter_parts = TRAIN ? min(4u, n_slots - GATHER_PARTS) : 0u;
+
+	float loss_acc = 0.0f;
+	bool dw_started = false;
+	bool have_prev = false;
+	float x_prev[D], x_cur[D], x_next[D];
+#pragma unroll
+	for (uint32_t d = 0; d < D; ++d) x_prev[d] = x_cur[d] = x_next[d] = 0.0f;
+
+	const uint32_t n_tiles = p.batch_size / TILE_M;
+	uint32_t tile = blockIdx.x;
+	if (tile < n_tiles) {
+		load_x(tile, x_cur);
+		for (uint32_t part = 0; part < GATHER_PARTS; ++part) gather_part(x_cur, s.enc, tile * TILE_M + row, part, GATHER_PARTS);
+	}
+	uint32_t buf = 0;
+	for (; tile < n_tiles; tile += gridDim.x, buf ^= 1u) {
+		const uint32_t sample = tile * TILE_M + row;
+		const uint32_t enc_cur = s.enc + buf * TILE_BYTES, enc_nxt = s.enc + (buf ^ 1u) * TILE_BYTES;
+		const uint32_t next_tile = tile + gridDim.x;
+		const bool have_next = next_tile < n_tiles;
+		if (have_next) load_x(next_tile, x_next);
+		// One tile = n_batches MMA batches. Batch b: stage_sync -> one thread issues the MMAs -> every thread fills the wait
+		// slot with memory work of the neighbouring tiles -> wait for the tensor core -> epilogue of batch b.
+		//   b <  NH          forward hidden layer b
+		//   b == NH          output layer + loss
+		//   NH < b <= 2NH    backward through layer l = 2NH + 1 - b (l = NH is the output layer): dgrad + wgrad
+		//   b == 2NH + 1     first layer: dL/d(encoded) + dW_0
+		const uint32_t n_batches = TRAIN ? 2 * NH + 2 : NH + 1;
+#pragma unroll 1
+		for (uint32_t b = 0; b < n_batches; ++b) {
 			stage_sync();
 			if (tid == 0) {
 				tc_fence_after_sync();
-				const uint32_t a_tile = l == 0 ? s.enc : s.h0 + (l - 1) * TILE_BYTES;
-				const uint32_t b_tile = s.w0 + l * (WIDTH * 128);
-				const uint32_t ksteps = l == 0 ? in_w / 16 : WIDTH / 16;
-				for (uint32_t j = 0; j < ksteps; ++j) umma_f16_ss(tmem_acc, kmaj(a_tile, j), kmaj(b_tile, j), IDESC_FWD_N64, j > 0);
+				if (b < NH) {
+					const uint32_t a_tile = b == 0 ? enc_cur : s.h0 + (b - 1) * TILE_BYTES;
+					const uint32_t b_tile = s.w0 + b * (WIDTH * 128);
+					const uint32_t ksteps = b == 0 ? in_w / 16 : WIDTH / 16;
+					for (uint32_t j = 0; j < ksteps; ++j) umma_f16_ss(tmem_acc, kmaj(a_tile, j), kmaj(b_tile, j), IDESC_FWD_N64, j > 0);
+				} else if (b == NH) {
+					const uint32_t a_tile = s.h0 + (NH - 1) * TILE_BYTES;
+					for (uint32_t j = 0; j < WIDTH / 16; ++j) umma_f16_ss(tmem_acc, kmaj(a_tile, j), kmaj(s.w_out, j), IDESC_FWD_N16, j > 0);
+				} else if (b <= 2 * NH) {
+					// g_{NH-1} = (dy . W_out) * act'(h_{NH-1});  dW_out^T += h_{NH-1}^T . dy   (fully_fused_mlp.cu:192-240, :784-787)
+					// g_{l-1}  = (g_l . W_l)   * act'(h_{l-1});   dW_l     += g_l^T . h_{l-1}   (fully_fused_mlp.cu:248-250, :815-830)
+					const uint32_t l = 2 * NH + 1 - b;
+					const uint32_t h_prev = s.h0 + (l - 1) * TILE_BYTES;
+					if (l == NH) {
+						umma_f16_ss(tmem_acc, kmaj(s.dy, 0), mnmaj(s.w_out, 0), IDESC_DGRAD, 0);
+						const uint32_t dw = tmem_base + 64u * (1 + NH);
+						for (uint32_t j = 0; j < TILE_M / 16; ++j) umma_f16_ss(dw, mnmaj(h_prev, j), mnmaj(s.dy, j), IDESC_WGRAD, dw_started || j > 0);
+					} else {
+						const uint32_t g_tile = s.h0 + l * TILE_BYTES;  // g_l lives in h_l's tile
+						const uint32_t w_tile = s.w0 + l * (WIDTH * 128);
+						for (uint32_t j = 0; j < WIDTH / 16; ++j) umma_f16_ss(tmem_acc, kmaj(g_tile, j), mnmaj(w_tile, j), IDESC_DGRAD, j > 0);
+						const uint32_t dw = tmem_base + 64u * (1 + l);
+						for (uint32_t j = 0; j < TILE_M / 16; ++j) umma_f16_ss(dw, mnmaj(g_tile, j), mnmaj(h_prev, j), IDESC_WGRAD, dw_started || j > 0);
+					}
+				} else {
+					// d_enc = g_0 . W_0 (fully_fused_mlp.cu:833-836);  dW_0 += g_0^T . enc (:827-830)
+					const uint32_t g_tile = s.h0;
+					for (uint32_t j = 0; j < WIDTH / 16; ++j) umma_f16_ss(tmem_acc, kmaj(g_tile, j), mnmaj(s.w0, j), IDESC_DGRAD, j > 0);
+					const uint32_t dw = tmem_base + 64u;
+					for (uint32_t j = 0; j < TILE_M / 16; ++j) umma_f16_ss(dw, mnmaj(g_tile, j), mnmaj(enc_cur, j), IDESC_WGRAD, dw_started || j > 0);
+				}
 				umma_commit(s.bar);
 			}
 			__syncwarp();
+
+			// ---- wait slot: gather of tile t+1 (slots 0, 1), scatter of tile t-1 (following slots)
+			if (b < GATHER_PARTS) {
+				if (have_next) gather_part(x_next, enc_nxt, next_tile * TILE_M + row, b, GATHER_PARTS);
+			} else if (TRAIN && have_prev && b < GATHER_PARTS + scatter_parts) {
+				scatter_part(x_prev, b - GATHER_PARTS, scatter_parts);
+			}
 			wait_mma();
-			const uint32_t h_tile = s.h0 + l * TILE_BYTES;
-			{
-				const uint32_t half = hsel;  // this thread's 32 accumulator columns
+
+			// ---- epilogue of batch b
+			if (b < NH) {
+				const uint32_t h_tile = s.h0 + b * TILE_BYTES;
 				uint32_t r[32];
-				tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
+				tmem_ld_32x32b_x32(tmem_acc + lane_field + hsel * 32, r);  // this thread's 32 accumulator columns
 				tmem_ld_wait();
 #pragma unroll
 				for (uint32_t c = 0; c < 4; ++c) {
 					const uint32_t v0 = relu_pack(r[c * 8 + 0], r[c * 8 + 1]), v1 = relu_pack(r[c * 8 + 2], r[c * 8 + 3]);
 					const uint32_t v2 = relu_pack(r[c * 8 + 4], r[c * 8 + 5]), v3 = relu_pack(r[c * 8 + 6], r[c * 8 + 7]);
-					st_shared_v4(h_tile + sw128(row, half * 4 + c), v0, v1, v2, v3);
-					if (p.dbg_hidden) *reinterpret_cast<uint4*>(p.dbg_hidden + ((size_t)l * p.batch_size + sample) * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
+					st_shared_v4(h_tile + sw128(row, hsel * 4 + c), v0, v1, v2, v3);
+					if (p.dbg_hidden) *reinterpret_cast<uint4*>(p.dbg_hidden + ((size_t)b * p.batch_size + sample) * 64 + (hsel * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
 				}
-			}
-		}
-
-		// ================================================================ output layer (N = 16) + loss
-		stage_sync();
-		if (tid == 0) {
-			tc_fence_after_sync();
-			const uint32_t a_tile = s.h0 + (NH - 1) * TILE_BYTES;
-			for (uint32_t j = 0; j < WIDTH / 16; ++j) umma_f16_ss(tmem_acc, kmaj(a_tile, j), kmaj(s.w_out, j), IDESC_FWD_N16, j > 0);
-			umma_commit(s.bar);
-		}
-		__syncwarp();
-		wait_mma();
-		if (hsel == 0) {
-			uint32_t r[16];
-			tmem_ld_32x32b_x16(tmem_acc + lane_field, r);
-			tmem_ld_wait();
-			// The reference's network output is fp16 (fully_fused_mlp.cu:421-476); everything downstream reads that rounding.
-			__half y16[16];
-#pragma unroll
-			for (uint32_t j = 0; j < 16; ++j) y16[j] = __float2half_rn(__uint_as_float(r[j]));
-			if (p.out_fp16) {
-				uint4* dst = reinterpret_cast<uint4*>(p.out_fp16 + (size_t)sample * 16);
-				dst[0] = *reinterpret_cast<uint4*>(&y16[0]);
-				dst[1] = *reinterpret_cast<uint4*>(&y16[8]);
-			}
-			if (p.out_fp32) {
-				for (uint32_t j = 0; j < p.n_out; ++j) p.out_fp32[(size_t)sample * p.n_out + j] = __half2float(y16[j]);
-			}
-			if (TRAIN) {
-				// relative_l2_loss / l2_loss (losses/relative_l2.h:56-75, l2.h:56-74); pad lanes give 0.
-				__half dy[16];
-				const float n_total = (float)(p.loss_batch_size * p.n_out);
-#pragma unroll
-				for (uint32_t j = 0; j < 16; ++j) {
-					float g = 0.0f;
-					if (j < p.n_out) {
-						const float pred = __half2float(y16[j]);
-						const float diff = pred - __ldg(p.targets + (size_t)sample * p.n_out + j);
-						float value, grad;
-						if (p.loss_type == LOSS_RELATIVE_L2) {
-							const float psq = pred * pred + 0.01f;
-							value = diff * diff / psq / n_total;
-							grad = 2.0f * diff / psq;
-						} else {
-							value = diff * diff / n_total;
-							grad = 2.0f * diff;
-						}
-						g = p.loss_scale * grad / n_total;
-						loss_acc += value;
-						if (p.loss_values) p.loss_values[(size_t)sample * p.n_out + j] = value;
-					}
-					dy[j] = __float2half_rn(g);
-				}
-				const uint4 lo = *reinterpret_cast<uint4*>(&dy[0]), hi = *reinterpret_cast<uint4*>(&dy[8]);
-				st_shared_v4(s.gB + sw128(row, 0), lo.x, lo.y, lo.z, lo.w);
-				st_shared_v4(s.gB + sw128(row, 1), hi.x, hi.y, hi.z, hi.w);
-				if (p.dbg_dy) {
-					uint4* dst = reinterpret_cast<uint4*>(p.dbg_dy + (size_t)sample * 16);
-					dst[0] = lo;
-					dst[1] = hi;
-				}
-			}
-		}
-
-		if (TRAIN) {
-			// ============================================================ backward through the output layer
-			// g_{NH-1} = (dy . W_out) * act'(h_{NH-1});  dW_out^T += h_{NH-1}^T . dy   (fully_fused_mlp.cu:192-240, :784-787)
-			uint32_t g_cur = s.gA, g_other = s.gB;
-			stage_sync();
-			if (tid == 0) {
-				tc_fence_after_sync();
-				const uint32_t h_last = s.h0 + (NH - 1) * TILE_BYTES;
-				umma_f16_ss(tmem_acc, kmaj(s.gB, 0), mnmaj(s.w_out, 0), IDESC_DGRAD, 0);
-				const uint32_t dw = tmem_base + 64u * (1 + NH);
-				for (uint32_t j = 0; j < TILE_M / 16; ++j) umma_f16_ss(dw, mnmaj(h_last, j), mnmaj(s.gB, j), IDESC_WGRAD, dw_started || j > 0);
-				umma_commit(s.bar);
-			}
-			__syncwarp();
-			wait_mma();
-			{
-				const uint32_t h_tile = s.h0 + (NH - 1) * TILE_BYTES;
-				{
-					const uint32_t half = hsel;
-					uint32_t r[32];
-					tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
+			} else if (b == NH) {
+				if (hsel == 0) {
+					uint32_t r[16];
+					tmem_ld_32x32b_x16(tmem_acc + lane_field, r);
 					tmem_ld_wait();
+					// The reference's network output is fp16 (fully_fused_mlp.cu:421-476); everything downstream reads that rounding.
+					__half y16[16];
 #pragma unroll
-					for (uint32_t c = 0; c < 4; ++c) {
-						uint32_t f0, f1, f2, f3;
-						ld_shared_v4(h_tile + sw128(row, half * 4 + c), f0, f1, f2, f3);
-						const uint32_t v0 = relu_bwd_pack(r[c * 8 + 0], r[c * 8 + 1], f0), v1 = relu_bwd_pack(r[c * 8 + 2], r[c * 8 + 3], f1);
-						const uint32_t v2 = relu_bwd_pack(r[c * 8 + 4], r[c * 8 + 5], f2), v3 = relu_bwd_pack(r[c * 8 + 6], r[c * 8 + 7], f3);
-						st_shared_v4(g_cur + sw128(row, half * 4 + c), v0, v1, v2, v3);
-						if (p.dbg_grad_hidden) *reinterpret_cast<uint4*>(p.dbg_grad_hidden + ((size_t)(NH - 1) * p.batch_size + sample) * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
+					for (uint32_t j = 0; j < 16; ++j) y16[j] = __float2half_rn(__uint_as_float(r[j]));
+					if (p.out_fp16) {
+						uint4* dst = reinterpret_cast<uint4*>(p.out_fp16 + (size_t)sample * 16);
+						dst[0] = *reinterpret_cast<uint4*>(&y16[0]);
+						dst[1] = *reinterpret_cast<uint4*>(&y16[8]);
+					}
+					if (p.out_fp32) {
+						for (uint32_t j = 0; j < p.n_out; ++j) p.out_fp32[(size_t)sample * p.n_out + j] = __half2float(y16[j]);
+					}
+					if (TRAIN) {
+						// relative_l2_loss / l2_loss (losses/relative_l2.h:56-75, l2.h:56-74); pad lanes give 0.
+						__half dy[16];
+						const float n_total = (float)(p.loss_batch_size * p.n_out);
+#pragma unroll
+						for (uint32_t j = 0; j < 16; ++j) {
+							float g = 0.0f;
+							if (j < p.n_out) {
+								const float pred = __half2float(y16[j]);
+								const float diff = pred - __ldg(p.targets + (size_t)sample * p.n_out + j);
+								float value, grad;
+								if (p.loss_type == LOSS_RELATIVE_L2) {
+									const float psq = pred * pred + 0.01f;
+									value = diff * diff / psq / n_total;
+									grad = 2.0f * diff / psq;
+								} else {
+									value = diff * diff / n_total;
+									grad = 2.0f * diff;
+								}
+								g = p.loss_scale * grad / n_total;
+								loss_acc += value;
+								if (p.loss_values) p.loss_values[(size_t)sample * p.n_out + j] = value;
+							}
+							dy[j] = __float2half_rn(g);
+						}
+						const uint4 lo = *reinterpret_cast<uint4*>(&dy[0]), hi = *reinterpret_cast<uint4*>(&dy[8]);
+						st_shared_v4(s.dy + sw128(row, 0), lo.x, lo.y, lo.z, lo.w);
+						st_shared_v4(s.dy + sw128(row, 1), hi.x, hi.y, hi.z, hi.w);
+						if (p.dbg_dy) {
+							uint4* dst = reinterpret_cast<uint4*>(p.dbg_dy + (size_t)sample * 16);
+							dst[0] = lo;
+							dst[1] = hi;
+						}
 					}
 				}
-			}
-
-			// ============================================================ backward through hidden matmuls l = NH-1 .. 1
-			// g_{l-1} = (g_l . W_l) * act'(h_{l-1});  dW_l += g_l^T . h_{l-1}   (fully_fused_mlp.cu:248-250, :815-830)
-			for (uint32_t l = NH - 1; l >= 1; --l) {
-				stage_sync();
-				if (tid == 0) {
-					tc_fence_after_sync();
-					const uint32_t w_tile = s.w0 + l * (WIDTH * 128);
-					const uint32_t h_prev = s.h0 + (l - 1) * TILE_BYTES;
-					for (uint32_t j = 0; j < WIDTH / 16; ++j) umma_f16_ss(tmem_acc, kmaj(g_cur, j), mnmaj(w_tile, j), IDESC_DGRAD, j > 0);
-					const uint32_t dw = tmem_base + 64u * (1 + l);
-					for (uint32_t j = 0; j < TILE_M / 16; ++j) umma_f16_ss(dw, mnmaj(g_cur, j), mnmaj(h_prev, j), IDESC_WGRAD, dw_started || j > 0);
-					umma_commit(s.bar);
-				}
-				__syncwarp();
-				wait_mma();
+			} else if (b <= 2 * NH) {
+				// g overwrites h IN PLACE: every thread rewrites only chunks of its own row that it has just read, and all MMAs
+				// that read this tile (forward A operand, wgrad B operand of the batch just completed) are finished.
+				const uint32_t l = 2 * NH + 1 - b;
 				const uint32_t h_tile = s.h0 + (l - 1) * TILE_BYTES;
-				{
-					const uint32_t half = hsel;
-					uint32_t r[32];
-					tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
-					tmem_ld_wait();
+				uint32_t r[32];
+				tmem_ld_32x32b_x32(tmem_acc + lane_field + hsel * 32, r);
+				tmem_ld_wait();
 #pragma unroll
-					for (uint32_t c = 0; c < 4; ++c) {
-						uint32_t f0, f1, f2, f3;
-						ld_shared_v4(h_tile + sw128(row, half * 4 + c), f0, f1, f2, f3);
-						const uint32_t v0 = relu_bwd_pack(r[c * 8 + 0], r[c * 8 + 1], f0), v1 = relu_bwd_pack(r[c * 8 + 2], r[c * 8 + 3], f1);
-						const uint32_t v2 = relu_bwd_pack(r[c * 8 + 4], r[c * 8 + 5], f2), v3 = relu_bwd_pack(r[c * 8 + 6], r[c * 8 + 7], f3);
-						st_shared_v4(g_other + sw128(row, half * 4 + c), v0, v1, v2, v3);
-						if (p.dbg_grad_hidden) *reinterpret_cast<uint4*>(p.dbg_grad_hidden + ((size_t)(l - 1) * p.batch_size + sample) * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
-					}
+				for (uint32_t c = 0; c < 4; ++c) {
+					uint32_t f0, f1, f2, f3;
+					ld_shared_v4(h_tile + sw128(row, hsel * 4 + c), f0, f1, f2, f3);
+					const uint32_t v0 = relu_bwd_pack(r[c * 8 + 0], r[c * 8 + 1], f0), v1 = relu_bwd_pack(r[c * 8 + 2], r[c * 8 + 3], f1);
+					const uint32_t v2 = relu_bwd_pack(r[c * 8 + 4], r[c * 8 + 5], f2), v3 = relu_bwd_pack(r[c * 8 + 6], r[c * 8 + 7], f3);
+					st_shared_v4(h_tile + sw128(row, hsel * 4 + c), v0, v1, v2, v3);
+					if (p.dbg_grad_hidden) *reinterpret_cast<uint4*>(p.dbg_grad_hidden + ((size_t)(l - 1) * p.batch_size + sample) * 64 + (hsel * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
 				}
-				const uint32_t t = g_cur;
-				g_cur = g_other;
-				g_other = t;
-			}
-
-			// ============================================================ first layer: dL/d(encoded) and dW_0
-			// d_enc = g_0 . W_0 (fully_fused_mlp.cu:833-836);  dW_0 += g_0^T . enc (:827-830)
-			stage_sync();
-			if (tid == 0) {
-				tc_fence_after_sync();
-				for (uint32_t j = 0; j < WIDTH / 16; ++j) umma_f16_ss(tmem_acc, kmaj(g_cur, j), mnmaj(s.w0, j), IDESC_DGRAD, j > 0);
-				const uint32_t dw = tmem_base + 64u;
-				for (uint32_t j = 0; j < TILE_M / 16; ++j) umma_f16_ss(dw, mnmaj(g_cur, j), mnmaj(s.enc, j), IDESC_WGRAD, dw_started || j > 0);
-				umma_commit(s.bar);
-			}
-			__syncwarp();
-			dw_started = true;
-			wait_mma();
-
-			// ============================================================ hash-grid gradient scatter (grid.h:215-320)
-			{
-				// dL/d(encoded) is an fp16 matrix in the reference (output of fc_multiply, fully_fused_mlp.cu:835): round the
-				// fp32 accumulator once. Each of the two threads of a sample reads the in_w/2 columns of ITS levels and parks them
-				// in its private half (4 chunks) of the sample's now idle enc-tile row.
-				{
-					uint32_t r[32];
-					tmem_ld_32x32b_x32(tmem_acc + lane_field + hsel * (in_w / 2), r);
-					tmem_ld_wait();
+			} else {
+				// dL/d(encoded) is an fp16 matrix in the reference (output of fc_multiply, fully_fused_mlp.cu:835): round the fp32
+				// accumulator once and park this thread's levels; they are scattered during the NEXT tile's wait slots.
+				dw_started = true;
+				uint32_t r[32];
+				tmem_ld_32x32b_x32(tmem_acc + lane_field + hsel * (in_w / 2), r);
+				tmem_ld_wait();
 #pragma unroll
-					for (uint32_t c = 0; c < 4; ++c) {
-						const uint32_t v0 = pack_half2(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1]));
-						const uint32_t v1 = pack_half2(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3]));
-						const uint32_t v2 = pack_half2(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5]));
-						const uint32_t v3 = pack_half2(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7]));
-						st_shared_v4(s.enc + sw128(row, hsel * 4 + c), v0, v1, v2, v3);
-						if (p.dbg_denc && c < n_chunks / 2) *reinterpret_cast<uint4*>(p.dbg_denc + (size_t)sample * 64 + (hsel * (n_chunks / 2) + c) * 8) = make_uint4(v0, v1, v2, v3);
-					}
-				}
-				__half* __restrict__ grad_table = p.grads + p.n_mlp_params;
-#pragma unroll 1
-				for (uint32_t level = level_begin; level < level_end; ++level) {
-					const LevelInfo lv = p.grid.levels[level];
-					LevelCorners<D> lc;
-					level_corners<D>(lv, x, p.grid.interpolation, lc);
-					uint32_t gbits;
-					const uint32_t feat = (level - level_begin) * F;  // 2 features = one 32-bit word of this thread's half row
-					asm volatile("ld.shared.b32 %0, [%1];" : "=r"(gbits) : "r"(s.enc + sw128(row, hsel * 4 + (feat >> 3)) + (feat & 7u) * 2u));
-					const __half2 grad = *reinterpret_cast<const __half2*>(&gbits);
-					uint32_t* __restrict__ lt = reinterpret_cast<uint32_t*>(grad_table + (size_t)lv.offset * F);
-#pragma unroll
-					for (uint32_t pr = 0; pr < (1u << (D - 1)); ++pr) {
-						// (GRAD_T)weight * grad -> __hmul2, then atomic f16x2 add (grid.h:252-255, vec.h:328-336)
-						const __half2 a0 = __hmul2(__float2half2_rn(lc.w[2 * pr]), grad);
-						const __half2 a1 = __hmul2(__float2half2_rn(lc.w[2 * pr + 1]), grad);
-						const bool paired = (lc.paired >> pr) & 1u;
-						if (!(p.ablate & ABLATE_SCATTER)) {
-							scatter_pair_f16x2(lt, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(p.ablate & ABLATE_PAIRING), *reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
-						}
+				for (uint32_t k = 0; k < 16; ++k) {
+					if (k < n_my_levels) {
+						const uint32_t v = pack_half2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]));
+						const uint32_t feat = park_f0 + k * F;
+						asm volatile("st.shared.b32 [%0], %1;" ::"r"(s.park + sw128(row, feat >> 3) + (feat & 7u) * 2u), "r"(v) : "memory");
+						if (p.dbg_denc) *reinterpret_cast<uint32_t*>(p.dbg_denc + (size_t)sample * 64 + (level_begin + k) * F) = v;
 					}
 				}
 			}
 		}
+		if (TRAIN) {
+#pragma unroll
+			for (uint32_t d = 0; d < D; ++d) x_prev[d] = x_cur[d];
+			have_prev = true;
+		}
+#pragma unroll
+		for (uint32_t d = 0; d < D; ++d) x_cur[d] = x_next[d];
+	}
+
+	// ---- drain: scatter of the last tile
+	if (TRAIN && have_prev) {
+		for (uint32_t part = 0; part < scatter_parts; ++part) scatter_part(x_prev, part, scatter_parts);
 	}
 
 	// ================================================================ flush weight gradients, loss, teardown
@@ -498,15 +502,15 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-size_t fused_step_smem_bytes(uint32_t n_hidden_layers, bool train) {
-	const size_t tiles = 1 + n_hidden_layers + (train ? 2 : 1);
+size_t fused_step_smem_bytes(uint32_t n_hidden_layers, uint32_t in_w, bool train) {
+	const size_t tiles = 2 + n_hidden_layers + (train ? (in_w <= 48 ? 1 : 2) : 0);
 	return tiles * TILE_BYTES + n_hidden_layers * (WIDTH * 128) + 16 * 128 + 64 + 1024 /* alignment slack */;
 }
 
 template <uint32_t D, bool TRAIN>
 static cudaError_t launch_impl(const FusedStepParams& p, uint32_t n_ctas, cudaStream_t stream) {
 	auto kernel = fused_step_kernel<D, 2, TRAIN>;
-	const size_t smem = fused_step_smem_bytes(p.n_hidden_layers, TRAIN);
+	const size_t smem = fused_step_smem_bytes(p.n_hidden_layers, p.grid.padded_width, TRAIN);
 	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (err != cudaSuccess) return err;
 	kernel<<<n_ctas, 256, smem, stream>>>(p);

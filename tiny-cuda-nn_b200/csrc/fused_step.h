@@ -38,7 +38,7 @@ struct FusedStepParams {
 	__half* dbg_denc;              // [batch][64]
 };
 
-size_t fused_step_smem_bytes(uint32_t n_hidden_layers, bool train);
+size_t fused_step_smem_bytes(uint32_t n_hidden_layers, uint32_t in_w, bool train);
 cudaError_t launch_fused_step(const FusedStepParams& p, uint32_t n_pos_dims, bool train, uint32_t n_ctas, cudaStream_t stream);
 
 }  // namespace tcnnb
