@@ -238,6 +238,7 @@ def run_own(args):
         n_prof = max(1, prof["n_steps"])
         fused_ms = prof["fused_ms_total"] / n_prof
         adam_ms = prof["optimizer_ms_total"] / n_prof
+        binning_ms = prof["binning_ms_total"] / n_prof
         achieved = FUSED_BYTES_PER_SAMPLE * BATCH / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else 0.0
         ms_per_step = ms / args.steps
         line = {
@@ -251,7 +252,7 @@ def run_own(args):
                     "steps": e2e_steps, "api": "tcnnb_training_step_host (C ABI, host buffers)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "fused_step_kernel<3,2,true>", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel_ms": fused_ms, "optimizer_kernel_ms": adam_ms,
+                         "frac": achieved / peak, "traffic": None, "kernel_ms": fused_ms, "optimizer_kernel_ms": adam_ms, "binning_kernels_ms": binning_ms,
                          "optimizer_achieved_gbs": ADAM_BYTES_PER_PARAM * model.n_params / (adam_ms * 1e-3) / 1e9 if adam_ms > 0 else None,
                          "step_share": fused_ms / ms_per_step if ms_per_step > 0 else None},
             "final_loss": final_loss,

@@ -105,10 +105,10 @@ typedef struct {
 	float* loss_values;   /* fp32 [batch][n_out] */
 } tcnnb_debug_taps;
 int tcnnb_set_debug_taps(tcnnb_model* m, const tcnnb_debug_taps* taps);
-/* Per-kernel device timing for the roofline report: when enabled, CUDA events bracket the fused fwd+bwd kernel and the
- * optimizer kernel of every training step on the caller's stream; tcnnb_read_profile synchronises and returns the sums. */
+/* Per-kernel device timing for the roofline report: when enabled, CUDA events bracket the binning kernels, the fused fwd+bwd kernel
+ * and the optimizer kernel of every training step on the caller's stream; tcnnb_read_profile synchronises and returns the sums. */
 int tcnnb_set_profiling(tcnnb_model* m, int enable);
-int tcnnb_read_profile(tcnnb_model* m, float* fused_ms_total, float* optimizer_ms_total, uint32_t* n_steps);
+int tcnnb_read_profile(tcnnb_model* m, float* fused_ms_total, float* optimizer_ms_total, float* binning_ms_total, uint32_t* n_steps);
 /* Number of kernels this library launched since load (bench.py's gpu_launches). */
 uint64_t tcnnb_kernel_launch_count(void);
 

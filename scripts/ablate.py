@@ -24,4 +24,4 @@ N = 50
 for i in range(N):
     model.trainer.training_step(xs[i % 4], ys[i % 4])
 p = model.read_profile()
-print(json.dumps({"ablate": int(os.environ.get("TCNNB_ABLATE", "0")), "fused_ms": p["fused_ms_total"] / p["n_steps"], "adam_ms": p["optimizer_ms_total"] / p["n_steps"]}))
+print(json.dumps({"ablate": int(os.environ.get("TCNNB_ABLATE", "0")), "fused_ms": p["fused_ms_total"] / p["n_steps"], "binning_ms": p["binning_ms_total"] / p["n_steps"], "adam_ms": p["optimizer_ms_total"] / p["n_steps"]}))

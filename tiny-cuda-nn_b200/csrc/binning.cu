@@ -1,0 +1,132 @@
+// binning.cu -- per-step spatial binning of the batch (counting sort by the (y, z) column of each sample).
+//
+// Why: the multiresolution gather / scatter is bound by the number of distinct 32-byte sectors the memory system has to
+// serve. Both the dense index (x + y*res + z*res^2, common_device.h:866-871) and the coherent-prime hash (x*1 ^ y*p1 ^ z*p2,
+// common_device.h:787-791) are CONTIGUOUS IN X for a fixed (y, z) cell. If the 32 samples of a warp share a (y, z) column, their
+// corner entries on the coarse and middle levels fall into a handful of 128-byte lines (and repeat across warps, so they hit
+// in L1) instead of 32 different ones. Gradients and the loss are sums over samples, so processing the batch in a different
+// order changes nothing but the (already unordered) accumulation order; per-sample outputs are written through `perm`.
+//
+// The reference has no counterpart (it consumes the batch in the caller's order); this is a B200-specific scheduling step.
+#include "binning.h"
+
+namespace tcnnb {
+
+namespace {
+
+__device__ __forceinline__ uint32_t part1by1(uint32_t v) {  // spread the low 8 bits: abcdefgh -> 0a0b0c0d0e0f0g0h
+	v &= 0xFFu;
+	v = (v | (v << 4)) & 0x0F0Fu;
+	v = (v | (v << 2)) & 0x3333u;
+	v = (v | (v << 1)) & 0x5555u;
+	return v;
+}
+
+template <uint32_t D>
+__device__ __forceinline__ uint32_t bin_key(const float* __restrict__ pos, uint32_t i, uint32_t log2_r) {
+	const uint32_t R = 1u << log2_r;
+	if (D == 2) {
+		const float y = pos[(size_t)i * 2 + 1];
+		return min(R - 1u, (uint32_t)max(0, (int)(y * (float)R)));
+	}
+	const float y = pos[(size_t)i * D + 1], z = pos[(size_t)i * D + 2];
+	const uint32_t yc = min(R - 1u, (uint32_t)max(0, (int)(y * (float)R)));
+	const uint32_t zc = min(R - 1u, (uint32_t)max(0, (int)(z * (float)R)));
+	// Morton order of the columns keeps consecutive bins (= consecutive tiles) spatially adjacent
+	return part1by1(yc) | (part1by1(zc) << 1);
+}
+
+template <uint32_t D>
+__global__ void bin_count_kernel(uint32_t n, const float* __restrict__ pos, uint32_t log2_r, uint32_t* __restrict__ keys, uint32_t* __restrict__ hist) {
+	const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
+	if (i >= n) return;
+	const uint32_t k = bin_key<D>(pos, i, log2_r);
+	keys[i] = k;
+	atomicAdd(hist + k, 1u);
+}
+
+// Exclusive scan of `n_bins` counters by one block of 1024 threads; hist[b] becomes the first output slot of bin b.
+__global__ void bin_scan_kernel(uint32_t n_bins, uint32_t* __restrict__ hist) {
+	__shared__ uint32_t warp_sums[32];
+	__shared__ uint32_t carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (uint32_t base = 0; base < n_bins; base += 1024) {
+		const uint32_t i = base + threadIdx.x;
+		const uint32_t v = i < n_bins ? hist[i] : 0u;
+		uint32_t incl = v;
+#pragma unroll
+		for (uint32_t o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+			if ((threadIdx.x & 31u) >= o) incl += t;
+		}
+		if ((threadIdx.x & 31u) == 31u) warp_sums[threadIdx.x >> 5] = incl;
+		__syncthreads();
+		if (threadIdx.x < 32) {
+			uint32_t w = warp_sums[threadIdx.x];
+#pragma unroll
+			for (uint32_t o = 1; o < 32; o <<= 1) {
+				const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, w, o);
+				if (threadIdx.x >= o) w += t;
+			}
+			warp_sums[threadIdx.x] = w;
+		}
+		__syncthreads();
+		const uint32_t warp_prefix = (threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0u;
+		const uint32_t c = carry;
+		if (i < n_bins) hist[i] = c + warp_prefix + incl - v;
+		__syncthreads();
+		if (threadIdx.x == 1023) carry = c + warp_prefix + incl;
+		__syncthreads();
+	}
+}
+
+template <uint32_t D>
+__global__ void bin_scatter_kernel(uint32_t n, uint32_t n_out, const float* __restrict__ pos, const float* __restrict__ tgt, const uint32_t* __restrict__ keys,
+                                   uint32_t* __restrict__ cursor, float* __restrict__ pos_sorted, float* __restrict__ tgt_sorted, uint32_t* __restrict__ perm) {
+	const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
+	if (i >= n) return;
+	const uint32_t dst = atomicAdd(cursor + keys[i], 1u);
+#pragma unroll
+	for (uint32_t d = 0; d < D; ++d) pos_sorted[(size_t)dst * D + d] = pos[(size_t)i * D + d];
+	if (tgt) {
+		for (uint32_t j = 0; j < n_out; ++j) tgt_sorted[(size_t)dst * n_out + j] = tgt[(size_t)i * n_out + j];
+	}
+	perm[dst] = i;
+}
+
+}  // namespace
+
+uint32_t binning_log2_resolution(uint32_t n_samples, uint32_t n_pos_dims) {
+	// aim at ~16 samples per bin: n_bins = n / 16 = R^(D-1)
+	uint32_t log2_bins = 0;
+	while ((1ull << (log2_bins + 1)) * 16ull <= n_samples) ++log2_bins;
+	uint32_t log2_r = n_pos_dims == 2 ? log2_bins : log2_bins / 2;
+	if (n_pos_dims != 2 && log2_r > 8) log2_r = 8;  // part1by1 interleaves 8 bits per axis
+	if (log2_r > 16) log2_r = 16;
+	return log2_r;
+}
+
+uint32_t binning_n_bins(uint32_t log2_r, uint32_t n_pos_dims) { return n_pos_dims == 2 ? (1u << log2_r) : (1u << (2 * log2_r)); }
+
+cudaError_t launch_binning(cudaStream_t stream, uint32_t n_pos_dims, uint32_t n, uint32_t n_out, const float* pos, const float* tgt, uint32_t log2_r, uint32_t* keys,
+                           uint32_t* hist, float* pos_sorted, float* tgt_sorted, uint32_t* perm) {
+	const uint32_t n_bins = binning_n_bins(log2_r, n_pos_dims);
+	cudaError_t err = cudaMemsetAsync(hist, 0, sizeof(uint32_t) * n_bins, stream);
+	if (err != cudaSuccess) return err;
+	const uint32_t blocks = (n + 255) / 256;
+	if (n_pos_dims == 2) {
+		bin_count_kernel<2><<<blocks, 256, 0, stream>>>(n, pos, log2_r, keys, hist);
+		bin_scan_kernel<<<1, 1024, 0, stream>>>(n_bins, hist);
+		bin_scatter_kernel<2><<<blocks, 256, 0, stream>>>(n, n_out, pos, tgt, keys, hist, pos_sorted, tgt_sorted, perm);
+	} else if (n_pos_dims == 3) {
+		bin_count_kernel<3><<<blocks, 256, 0, stream>>>(n, pos, log2_r, keys, hist);
+		bin_scan_kernel<<<1, 1024, 0, stream>>>(n_bins, hist);
+		bin_scatter_kernel<3><<<blocks, 256, 0, stream>>>(n, n_out, pos, tgt, keys, hist, pos_sorted, tgt_sorted, perm);
+	} else {
+		return cudaErrorInvalidValue;
+	}
+	return cudaGetLastError();
+}
+
+}  // namespace tcnnb

@@ -272,11 +272,12 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 	uint32_t tile = blockIdx.x;
 	if (tile < n_tiles) {
 		load_x(tile, x_cur);
-		for (uint32_t part = 0; part < GATHER_PARTS; ++part) gather_part(x_cur, s.enc, tile * TILE_M + row, part, GATHER_PARTS);
+		for (uint32_t part = 0; part < GATHER_PARTS; ++part) gather_part(x_cur, s.enc, p.dbg_enc && p.perm ? __ldg(p.perm + tile * TILE_M + row) : tile * TILE_M + row, part, GATHER_PARTS);
 	}
 	uint32_t buf = 0;
 	for (; tile < n_tiles; tile += gridDim.x, buf ^= 1u) {
-		const uint32_t sample = tile * TILE_M + row;
+		const uint32_t sample = tile * TILE_M + row;                       // row of the (possibly binned) input arrays
+		const uint32_t osample = p.perm ? __ldg(p.perm + sample) : sample;  // caller's sample index, for per-sample outputs
 		const uint32_t enc_cur = s.enc + buf * TILE_BYTES, enc_nxt = s.enc + (buf ^ 1u) * TILE_BYTES;
 		const uint32_t next_tile = tile + gridDim.x;
 		const bool have_next = next_tile < n_tiles;
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 
 			// ---- wait slot: gather of tile t+1 (slots 0, 1), scatter of tile t-1 (following slots)
 			if (b < GATHER_PARTS) {
-				if (have_next) gather_part(x_next, enc_nxt, next_tile * TILE_M + row, b, GATHER_PARTS);
+				if (have_next) gather_part(x_next, enc_nxt, p.dbg_enc && p.perm ? __ldg(p.perm + next_tile * TILE_M + row) : next_tile * TILE_M + row, b, GATHER_PARTS);
 			} else if (TRAIN && have_prev && b < GATHER_PARTS + scatter_parts) {
 				scatter_part(x_prev, b - GATHER_PARTS, scatter_parts);
 			}
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 					const uint32_t v0 = relu_pack(r[c * 8 + 0], r[c * 8 + 1]), v1 = relu_pack(r[c * 8 + 2], r[c * 8 + 3]);
 					const uint32_t v2 = relu_pack(r[c * 8 + 4], r[c * 8 + 5]), v3 = relu_pack(r[c * 8 + 6], r[c * 8 + 7]);
 					st_shared_v4(h_tile + sw128(row, hsel * 4 + c), v0, v1, v2, v3);
-					if (p.dbg_hidden) *reinterpret_cast<uint4*>(p.dbg_hidden + ((size_t)b * p.batch_size + sample) * 64 + (hsel * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
+					if (p.dbg_hidden) *reinterpret_cast<uint4*>(p.dbg_hidden + ((size_t)b * p.batch_size + osample) * 64 + (hsel * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
 				}
 			} else if (b == NH) {
 				if (hsel == 0) {
@@ -359,12 +360,12 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 #pragma unroll
 					for (uint32_t j = 0; j < 16; ++j) y16[j] = __float2half_rn(__uint_as_float(r[j]));
 					if (p.out_fp16) {
-						uint4* dst = reinterpret_cast<uint4*>(p.out_fp16 + (size_t)sample * 16);
+						uint4* dst = reinterpret_cast<uint4*>(p.out_fp16 + (size_t)osample * 16);
 						dst[0] = *reinterpret_cast<uint4*>(&y16[0]);
 						dst[1] = *reinterpret_cast<uint4*>(&y16[8]);
 					}
 					if (p.out_fp32) {
-						for (uint32_t j = 0; j < p.n_out; ++j) p.out_fp32[(size_t)sample * p.n_out + j] = __half2float(y16[j]);
+						for (uint32_t j = 0; j < p.n_out; ++j) p.out_fp32[(size_t)osample * p.n_out + j] = __half2float(y16[j]);
 					}
 					if (TRAIN) {
 						// relative_l2_loss / l2_loss (losses/relative_l2.h:56-75, l2.h:56-74); pad lanes give 0.
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 								}
 								g = p.loss_scale * grad / n_total;
 								loss_acc += value;
-								if (p.loss_values) p.loss_values[(size_t)sample * p.n_out + j] = value;
+								if (p.loss_values) p.loss_values[(size_t)osample * p.n_out + j] = value;
 							}
 							dy[j] = __float2half_rn(g);
 						}
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 						st_shared_v4(s.dy + sw128(row, 0), lo.x, lo.y, lo.z, lo.w);
 						st_shared_v4(s.dy + sw128(row, 1), hi.x, hi.y, hi.z, hi.w);
 						if (p.dbg_dy) {
-							uint4* dst = reinterpret_cast<uint4*>(p.dbg_dy + (size_t)sample * 16);
+							uint4* dst = reinterpret_cast<uint4*>(p.dbg_dy + (size_t)osample * 16);
 							dst[0] = lo;
 							dst[1] = hi;
 						}
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 					const uint32_t v0 = relu_bwd_pack(r[c * 8 + 0], r[c * 8 + 1], f0), v1 = relu_bwd_pack(r[c * 8 + 2], r[c * 8 + 3], f1);
 					const uint32_t v2 = relu_bwd_pack(r[c * 8 + 4], r[c * 8 + 5], f2), v3 = relu_bwd_pack(r[c * 8 + 6], r[c * 8 + 7], f3);
 					st_shared_v4(h_tile + sw128(row, hsel * 4 + c), v0, v1, v2, v3);
-					if (p.dbg_grad_hidden) *reinterpret_cast<uint4*>(p.dbg_grad_hidden + ((size_t)(l - 1) * p.batch_size + sample) * 64 + (hsel * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
+					if (p.dbg_grad_hidden) *reinterpret_cast<uint4*>(p.dbg_grad_hidden + ((size_t)(l - 1) * p.batch_size + osample) * 64 + (hsel * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
 				}
 			} else {
 				// dL/d(encoded) is an fp16 matrix in the reference (output of fc_multiply, fully_fused_mlp.cu:835): round the fp32
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 						const uint32_t v = pack_half2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]));
 						const uint32_t feat = park_f0 + k * F;
 						asm volatile("st.shared.b32 [%0], %1;" ::"r"(s.park + sw128(row, feat >> 3) + (feat & 7u) * 2u), "r"(v) : "memory");
-						if (p.dbg_denc) *reinterpret_cast<uint32_t*>(p.dbg_denc + (size_t)sample * 64 + (level_begin + k) * F) = v;
+						if (p.dbg_denc) *reinterpret_cast<uint32_t*>(p.dbg_denc + (size_t)osample * 64 + (level_begin + k) * F) = v;
 					}
 				}
 			}

@@ -11,6 +11,7 @@
 // There is deliberately no fallback: unsupported configurations raise the error the caller sees via tcnnb_last_error().
 #include "../../include/tcnn_b200.h"
 
+#include "binning.h"
 #include "common.cuh"
 #include "fused_step.h"
 #include "json_mini.h"
@@ -274,6 +275,11 @@ struct Model {
 	DeviceBuffer<float> level_scales_dev;
 	bool mlp_grads_in_accum = false;
 
+	// spatial binning scratch (binning.cu): sorted copies of the batch + permutation
+	bool binning = true;  // TCNNB_BINNING=0 disables
+	DeviceBuffer<float> bin_pos, bin_tgt;
+	DeviceBuffer<uint32_t> bin_keys, bin_hist, bin_perm;
+
 	// host staging for the *_host entry points
 	float* pinned = nullptr;
 	size_t pinned_floats = 0;
@@ -286,7 +292,7 @@ struct Model {
 	// optional per-kernel timing (bench.py roofline): events around the fused kernel and the Adam kernel of every step
 	uint32_t ablate = 0;  // profiling experiments only (TCNNB_ABLATE env var)
 	bool profiling = false;
-	std::vector<cudaEvent_t> prof_events;  // triples: before fused, after fused, after adam
+	std::vector<cudaEvent_t> prof_events;  // quadruples: step start, after binning, after fused kernel, after Adam
 
 	~Model() {
 		if (pinned) cudaFreeHost(pinned);
@@ -296,7 +302,7 @@ struct Model {
 
 	cudaEvent_t prof_mark(cudaStream_t stream) {
 		cudaEvent_t e = nullptr;
-		if (profiling && prof_events.size() < 3 * 8192) {
+		if (profiling && prof_events.size() < 4 * 8192) {
 			if (cudaEventCreate(&e) == cudaSuccess) {
 				cudaEventRecord(e, stream);
 				prof_events.push_back(e);
@@ -345,6 +351,7 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 	}
 	m.n_sms = prop.multiProcessorCount;
 	if (const char* e = std::getenv("TCNNB_ABLATE")) m.ablate = (uint32_t)std::atoi(e);
+	if (const char* e = std::getenv("TCNNB_BINNING")) m.binning = std::atoi(e) != 0;
 	m.n_in = n_in;
 	m.n_out = n_out;
 
@@ -539,6 +546,21 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
 		TCNNB_CUDA_CHECK(cudaMemsetAsync(m.dw_accum.ptr, 0, sizeof(float) * m.mlp.n_params, stream));
 	}
 	FusedStepParams p = make_params(m, batch, loss_batch, x, y);
+	m.prof_mark(stream);
+	// Process the batch in (y, z)-column order: same sums, far fewer distinct memory sectors on the coarse levels (binning.cu).
+	if (m.binning && batch >= 16384) {
+		const uint32_t log2_r = binning_log2_resolution(batch, m.grid.n_pos_dims);
+		m.bin_pos.resize(std::max(m.bin_pos.n, (size_t)batch * m.n_in));
+		m.bin_tgt.resize(std::max(m.bin_tgt.n, (size_t)batch * m.n_out));
+		m.bin_keys.resize(std::max(m.bin_keys.n, (size_t)batch));
+		m.bin_perm.resize(std::max(m.bin_perm.n, (size_t)batch));
+		m.bin_hist.resize(std::max(m.bin_hist.n, (size_t)binning_n_bins(log2_r, m.grid.n_pos_dims)));
+		TCNNB_CUDA_CHECK(launch_binning(stream, m.grid.n_pos_dims, batch, m.n_out, x, y, log2_r, m.bin_keys.ptr, m.bin_hist.ptr, m.bin_pos.ptr, m.bin_tgt.ptr, m.bin_perm.ptr));
+		g_kernel_launches += 3;
+		p.positions = m.bin_pos.ptr;
+		p.targets = m.bin_tgt.ptr;
+		p.perm = m.bin_perm.ptr;
+	}
 	m.prof_mark(stream);
 	TCNNB_CUDA_CHECK(launch_fused_step(p, m.grid.n_pos_dims, true, fused_grid_size(m, batch), stream));
 	++g_kernel_launches;
@@ -873,19 +895,22 @@ int tcnnb_set_profiling(tcnnb_model* m, int enable) {
 	TCNNB_API_END
 }
 
-int tcnnb_read_profile(tcnnb_model* m, float* fused_ms_total, float* optimizer_ms_total, uint32_t* n_steps) {
+int tcnnb_read_profile(tcnnb_model* m, float* fused_ms_total, float* optimizer_ms_total, float* binning_ms_total, uint32_t* n_steps) {
 	TCNNB_API_BEGIN
 	Model& mm = m->impl;
 	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
-	float fused = 0, opt = 0;
-	const size_t n = mm.prof_events.size() / 3;
+	float fused = 0, opt = 0, bin = 0;
+	const size_t n = mm.prof_events.size() / 4;
 	for (size_t i = 0; i < n; ++i) {
-		float a = 0, b = 0;
-		TCNNB_CUDA_CHECK(cudaEventElapsedTime(&a, mm.prof_events[3 * i], mm.prof_events[3 * i + 1]));
-		TCNNB_CUDA_CHECK(cudaEventElapsedTime(&b, mm.prof_events[3 * i + 1], mm.prof_events[3 * i + 2]));
+		float a = 0, b = 0, c = 0;
+		TCNNB_CUDA_CHECK(cudaEventElapsedTime(&c, mm.prof_events[4 * i], mm.prof_events[4 * i + 1]));
+		TCNNB_CUDA_CHECK(cudaEventElapsedTime(&a, mm.prof_events[4 * i + 1], mm.prof_events[4 * i + 2]));
+		TCNNB_CUDA_CHECK(cudaEventElapsedTime(&b, mm.prof_events[4 * i + 2], mm.prof_events[4 * i + 3]));
 		fused += a;
 		opt += b;
+		bin += c;
 	}
+	if (binning_ms_total) *binning_ms_total = bin;
 	if (fused_ms_total) *fused_ms_total = fused;
 	if (optimizer_ms_total) *optimizer_ms_total = opt;
 	if (n_steps) *n_steps = (uint32_t)n;

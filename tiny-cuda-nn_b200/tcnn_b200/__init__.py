@@ -67,7 +67,7 @@ ABI = [
     ("tcnnb_deserialize", _int, [_vp, _vp, _u64]),
     ("tcnnb_set_debug_taps", _int, [_vp, ctypes.POINTER(DebugTaps)]),
     ("tcnnb_set_profiling", _int, [_vp, _int]),
-    ("tcnnb_read_profile", _int, [_vp, _f32p, _f32p, ctypes.POINTER(_u32)]),
+    ("tcnnb_read_profile", _int, [_vp, _f32p, _f32p, _f32p, ctypes.POINTER(_u32)]),
     ("tcnnb_kernel_launch_count", _u64, []),
 ]
 
@@ -261,9 +261,9 @@ class TrainableModel:
         _check(load().tcnnb_set_profiling(self._h, int(enable)))
 
     def read_profile(self):
-        f, o, n = ctypes.c_float(0), ctypes.c_float(0), ctypes.c_uint32(0)
-        _check(load().tcnnb_read_profile(self._h, ctypes.byref(f), ctypes.byref(o), ctypes.byref(n)))
-        return {"fused_ms_total": f.value, "optimizer_ms_total": o.value, "n_steps": n.value}
+        f, o, b, n = ctypes.c_float(0), ctypes.c_float(0), ctypes.c_float(0), ctypes.c_uint32(0)
+        _check(load().tcnnb_read_profile(self._h, ctypes.byref(f), ctypes.byref(o), ctypes.byref(b), ctypes.byref(n)))
+        return {"fused_ms_total": f.value, "optimizer_ms_total": o.value, "binning_ms_total": b.value, "n_steps": n.value}
 
     def training_step_host(self, inputs_np, targets_np):
         """C-ABI call with HOST buffers (numpy fp32, C-contiguous): H2D + step + D2H of the loss inside."""
