@@ -147,9 +147,30 @@ __device__ __forceinline__ void level_corners(const LevelInfo& lv, const float (
 			out.w[i] = out.w[i] * lo;
 		}
 	}
-	// indices
+	// indices: two straight-line paths selected by a warp-uniform test (all lanes of a warp work on the same level)
 	uint32_t rest[1u << (D - 1)];
 	rest[0] = 0;
+	if (lv.use_hash == LEVEL_HASH && lv.pow2_mask != 0) {
+		// hashed level, power-of-two table: index = (x ^ y*p1 ^ z*p2) & mask; the x-pair shares an aligned slot iff x is even
+		constexpr uint32_t primes[4] = {1u, 2654435761u, 805459861u, 3674653429u};
+#pragma unroll
+		for (uint32_t d = 1; d < D; ++d) {
+			const uint32_t h0 = cp.cell[d] * primes[d], h1 = h0 + primes[d];
+#pragma unroll
+			for (uint32_t i = 0; i < (1u << (d - 1)); ++i) {
+				rest[i + (1u << (d - 1))] = rest[i] ^ h1;
+				rest[i] = rest[i] ^ h0;
+			}
+		}
+		const uint32_t x0 = cp.cell[0], x1 = cp.cell[0] + 1u;
+#pragma unroll
+		for (uint32_t k = 0; k < (1u << (D - 1)); ++k) {
+			out.idx[2 * k] = (x0 ^ rest[k]) & lv.pow2_mask;
+			out.idx[2 * k + 1] = (x1 ^ rest[k]) & lv.pow2_mask;
+		}
+		out.paired = (x0 & 1u) ? 0u : (1u << (1u << (D - 1))) - 1u;
+		return;
+	}
 	if (lv.use_hash == LEVEL_HASH) {
 		constexpr uint32_t primes[4] = {1u, 2654435761u, 805459861u, 3674653429u};
 #pragma unroll
@@ -163,8 +184,8 @@ __device__ __forceinline__ void level_corners(const LevelInfo& lv, const float (
 		}
 #pragma unroll
 		for (uint32_t k = 0; k < (1u << (D - 1)); ++k) {
-			out.idx[2 * k] = level_mod(lv, cp.cell[0] ^ rest[k]);
-			out.idx[2 * k + 1] = level_mod(lv, (cp.cell[0] + 1u) ^ rest[k]);
+			out.idx[2 * k] = (cp.cell[0] ^ rest[k]) % lv.size;
+			out.idx[2 * k + 1] = ((cp.cell[0] + 1u) ^ rest[k]) % lv.size;
 		}
 	} else if (lv.use_hash == LEVEL_DENSE) {
 		uint32_t stride = lv.resolution;
@@ -178,10 +199,20 @@ __device__ __forceinline__ void level_corners(const LevelInfo& lv, const float (
 			}
 			stride *= lv.resolution;
 		}
+		bool slow = false;
 #pragma unroll
 		for (uint32_t k = 0; k < (1u << (D - 1)); ++k) {
-			out.idx[2 * k] = level_mod(lv, cp.cell[0] + rest[k]);
-			out.idx[2 * k + 1] = level_mod(lv, cp.cell[0] + 1u + rest[k]);
+			// in-range positions give index < 2 * size on a level that holds its full dense grid (small_mod)
+			uint32_t i0 = cp.cell[0] + rest[k], i1 = i0 + 1u;
+			i0 -= i0 >= lv.size ? lv.size : 0u;
+			i1 -= i1 >= lv.size ? lv.size : 0u;
+			slow |= i0 >= lv.size || i1 >= lv.size;
+			out.idx[2 * k] = i0;
+			out.idx[2 * k + 1] = i1;
+		}
+		if (slow || !lv.small_mod) {  // tiled grids, or positions outside [0,1): exact modulo (wrap-around indexing)
+#pragma unroll
+			for (uint32_t k = 0; k < (1u << D); ++k) out.idx[k] %= lv.size;
 		}
 	} else {
 #pragma unroll
