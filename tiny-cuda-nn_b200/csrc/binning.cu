@@ -41,52 +41,54 @@ __global__ void bin_count_kernel(uint32_t n, const float* __restrict__ pos, uint
 	const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
 	if (i >= n) return;
 	const uint32_t k = bin_key<D>(pos, i, log2_r);
-	keys[i] = k;
-	atomicAdd(hist + k, 1u);
+	// the value returned by the counting atomic is this sample's rank inside its bin: the scatter pass needs no atomics
+	const uint32_t rank = atomicAdd(hist + k, 1u);
+	reinterpret_cast<uint2*>(keys)[i] = make_uint2(k, rank);
 }
 
-// Exclusive scan of `n_bins` counters by one block of 1024 threads; hist[b] becomes the first output slot of bin b.
-__global__ void bin_scan_kernel(uint32_t n_bins, uint32_t* __restrict__ hist) {
+// Exclusive scan of `n_bins` counters by one block of 1024 threads: cursor[b] = first output slot of bin b.
+// Each thread owns a contiguous run of bins (local serial prefix), the 1024 run totals are scanned with shuffles.
+// The counters are re-armed to zero for the next step, so no memset is needed per step.
+__global__ void __launch_bounds__(1024) bin_scan_kernel(uint32_t n_bins, uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor) {
 	__shared__ uint32_t warp_sums[32];
-	__shared__ uint32_t carry;
-	if (threadIdx.x == 0) carry = 0;
+	const uint32_t per = (n_bins + 1023u) / 1024u;
+	const uint32_t begin = threadIdx.x * per, end = min(n_bins, begin + per);
+	uint32_t total = 0;
+	for (uint32_t i = begin; i < end; ++i) total += hist[i];
+	uint32_t incl = total;
+#pragma unroll
+	for (uint32_t o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+		if ((threadIdx.x & 31u) >= o) incl += t;
+	}
+	if ((threadIdx.x & 31u) == 31u) warp_sums[threadIdx.x >> 5] = incl;
 	__syncthreads();
-	for (uint32_t base = 0; base < n_bins; base += 1024) {
-		const uint32_t i = base + threadIdx.x;
-		const uint32_t v = i < n_bins ? hist[i] : 0u;
-		uint32_t incl = v;
+	if (threadIdx.x < 32) {
+		uint32_t w = warp_sums[threadIdx.x];
 #pragma unroll
 		for (uint32_t o = 1; o < 32; o <<= 1) {
-			const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-			if ((threadIdx.x & 31u) >= o) incl += t;
+			const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, w, o);
+			if (threadIdx.x >= o) w += t;
 		}
-		if ((threadIdx.x & 31u) == 31u) warp_sums[threadIdx.x >> 5] = incl;
-		__syncthreads();
-		if (threadIdx.x < 32) {
-			uint32_t w = warp_sums[threadIdx.x];
-#pragma unroll
-			for (uint32_t o = 1; o < 32; o <<= 1) {
-				const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, w, o);
-				if (threadIdx.x >= o) w += t;
-			}
-			warp_sums[threadIdx.x] = w;
-		}
-		__syncthreads();
-		const uint32_t warp_prefix = (threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0u;
-		const uint32_t c = carry;
-		if (i < n_bins) hist[i] = c + warp_prefix + incl - v;
-		__syncthreads();
-		if (threadIdx.x == 1023) carry = c + warp_prefix + incl;
-		__syncthreads();
+		warp_sums[threadIdx.x] = w;
+	}
+	__syncthreads();
+	uint32_t run = ((threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0u) + incl - total;
+	for (uint32_t i = begin; i < end; ++i) {
+		const uint32_t c = hist[i];
+		cursor[i] = run;
+		hist[i] = 0;
+		run += c;
 	}
 }
 
 template <uint32_t D>
 __global__ void bin_scatter_kernel(uint32_t n, uint32_t n_out, const float* __restrict__ pos, const float* __restrict__ tgt, const uint32_t* __restrict__ keys,
-                                   uint32_t* __restrict__ cursor, float* __restrict__ pos_sorted, float* __restrict__ tgt_sorted, uint32_t* __restrict__ perm) {
+                                   const uint32_t* __restrict__ cursor, float* __restrict__ pos_sorted, float* __restrict__ tgt_sorted, uint32_t* __restrict__ perm) {
 	const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
 	if (i >= n) return;
-	const uint32_t dst = atomicAdd(cursor + keys[i], 1u);
+	const uint2 kr = reinterpret_cast<const uint2*>(keys)[i];
+	const uint32_t dst = __ldg(cursor + kr.x) + kr.y;
 #pragma unroll
 	for (uint32_t d = 0; d < D; ++d) pos_sorted[(size_t)dst * D + d] = pos[(size_t)i * D + d];
 	if (tgt) {
@@ -112,17 +114,16 @@ uint32_t binning_n_bins(uint32_t log2_r, uint32_t n_pos_dims) { return n_pos_dim
 cudaError_t launch_binning(cudaStream_t stream, uint32_t n_pos_dims, uint32_t n, uint32_t n_out, const float* pos, const float* tgt, uint32_t log2_r, uint32_t* keys,
                            uint32_t* hist, float* pos_sorted, float* tgt_sorted, uint32_t* perm) {
 	const uint32_t n_bins = binning_n_bins(log2_r, n_pos_dims);
-	cudaError_t err = cudaMemsetAsync(hist, 0, sizeof(uint32_t) * n_bins, stream);
-	if (err != cudaSuccess) return err;
+	uint32_t* cursor = hist + n_bins;  // hist: [n_bins counters (zero between calls) | n_bins cursors]
 	const uint32_t blocks = (n + 255) / 256;
 	if (n_pos_dims == 2) {
 		bin_count_kernel<2><<<blocks, 256, 0, stream>>>(n, pos, log2_r, keys, hist);
-		bin_scan_kernel<<<1, 1024, 0, stream>>>(n_bins, hist);
-		bin_scatter_kernel<2><<<blocks, 256, 0, stream>>>(n, n_out, pos, tgt, keys, hist, pos_sorted, tgt_sorted, perm);
+		bin_scan_kernel<<<1, 1024, 0, stream>>>(n_bins, hist, cursor);
+		bin_scatter_kernel<2><<<blocks, 256, 0, stream>>>(n, n_out, pos, tgt, keys, cursor, pos_sorted, tgt_sorted, perm);
 	} else if (n_pos_dims == 3) {
 		bin_count_kernel<3><<<blocks, 256, 0, stream>>>(n, pos, log2_r, keys, hist);
-		bin_scan_kernel<<<1, 1024, 0, stream>>>(n_bins, hist);
-		bin_scatter_kernel<3><<<blocks, 256, 0, stream>>>(n, n_out, pos, tgt, keys, hist, pos_sorted, tgt_sorted, perm);
+		bin_scan_kernel<<<1, 1024, 0, stream>>>(n_bins, hist, cursor);
+		bin_scatter_kernel<3><<<blocks, 256, 0, stream>>>(n, n_out, pos, tgt, keys, cursor, pos_sorted, tgt_sorted, perm);
 	} else {
 		return cudaErrorInvalidValue;
 	}

@@ -68,7 +68,7 @@ __device__ __forceinline__ uint32_t relu_bwd_pack(uint32_t lo_bits, uint32_t hi_
 struct Smem {
 	// dynamic shared memory, 1024-byte aligned:
 	//   [ enc_0 | enc_1 | h_0 .. h_{NH-1} | dy | (park) | W_0 .. W_{NH-1} | W_out ] then barriers
-	uint32_t enc, h0, dy, park, w0, w_out, bar, tmem_slot;
+	uint32_t enc, h0, dy, park, w0, w_out, bar, tmem_slot, levels;
 };
 
 }  // namespace
@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 	s.w_out = s.w0 + NH * (WIDTH * 128);
 	s.bar = s.w_out + 16 * 128;
 	s.tmem_slot = s.bar + 8;
+	s.levels = s.bar + 16;  // LevelInfo[MAX_LEVELS] copy: dynamic indexing of kernel parameters costs a constant-cache round trip per level
 	const uint32_t park_f0 = park_in_dy ? 16 + hsel * 24 : hsel * 32;  // first fp16 column of this thread's parking slots
 
 	// ---- one-time setup: barrier, TMEM, weights
@@ -111,6 +112,11 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 		__syncwarp();
 		tmem_alloc(s.tmem_slot, tmem_cols);
 		tmem_relinquish();
+	}
+
+	for (uint32_t i = tid; i < p.grid.n_levels * (uint32_t)(sizeof(LevelInfo) / 4); i += 256) {
+		const uint32_t v = reinterpret_cast<const uint32_t*>(p.grid.levels)[i];
+		asm volatile("st.shared.b32 [%0], %1;" ::"r"(s.levels + i * 4), "r"(v) : "memory");
 	}
 
 	// Stage the fp16 weights: W_l rows are 128-byte tile rows (K-major, SWIZZLE_128B); unused columns are zeroed.
@@ -180,6 +186,16 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 	const uint32_t n_my_levels = level_end > level_begin ? level_end - level_begin : 0;
 	const __half* __restrict__ table = p.params + p.n_mlp_params;
 
+	auto load_level = [&](uint32_t level) {
+		LevelInfo lv;
+		uint32_t* w = reinterpret_cast<uint32_t*>(&lv);
+		const uint32_t base = s.levels + level * (uint32_t)sizeof(LevelInfo);
+		static_assert(sizeof(LevelInfo) == 32, "LevelInfo layout");
+		asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(base));
+		asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(base + 16));
+		return lv;
+	};
+
 	// Gather + N-linear blend of part `part` of `parts` of this thread's levels for the sample at `x` into tile `enc_tile`.
 	// Loops are deliberately not unrolled: memory-system throughput, not load latency, bounds the gather, and an unrolled
 	// body overflows the instruction caches (profiles/).
@@ -193,32 +209,56 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 			}
 		}
 		const uint32_t lb = level_begin + (n_my_levels * part) / parts, le = level_begin + (n_my_levels * (part + 1)) / parts;
-#pragma unroll 1
-		for (uint32_t level = lb; level < le; ++level) {
-			const LevelInfo lv = p.grid.levels[level];
+		// Two levels in flight: the loads of level l+1 are issued before the values of level l are consumed, so the
+		// (long, loaded-L2) latency of one level hides behind the index arithmetic and the loads of the next.
+		struct InFlight {
+			uint32_t vals[1u << D];
+			uint32_t w16[1u << D];  // (half)weight duplicated into both halves
+		};
+		auto issue = [&](uint32_t level, InFlight& f) {
+			const LevelInfo lv = load_level(level);
 			LevelCorners<D> lc;
 			level_corners<D>(lv, x, p.grid.interpolation, lc);
 			const uint32_t* __restrict__ lt = reinterpret_cast<const uint32_t*>(table + (size_t)lv.offset * F);
-			uint32_t vals[1u << D];
 #pragma unroll
 			for (uint32_t pr = 0; pr < (1u << (D - 1)); ++pr) {
 				const bool paired = (lc.paired >> pr) & 1u;
 				if (p.ablate & ABLATE_GATHER) {
-					vals[2 * pr] = lc.idx[2 * pr];
-					vals[2 * pr + 1] = lc.idx[2 * pr + 1];
+					f.vals[2 * pr] = lc.idx[2 * pr];
+					f.vals[2 * pr + 1] = lc.idx[2 * pr + 1];
 				} else {
-					gather_pair_f16x2(lt, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(p.ablate & ABLATE_PAIRING), vals[2 * pr], vals[2 * pr + 1]);
+					gather_pair_f16x2(lt, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(p.ablate & ABLATE_PAIRING), f.vals[2 * pr], f.vals[2 * pr + 1]);
 				}
 			}
+#pragma unroll
+			for (uint32_t i = 0; i < (1u << D); ++i) {
+				const __half2 h = __float2half2_rn(lc.w[i]);
+				f.w16[i] = *reinterpret_cast<const uint32_t*>(&h);
+			}
+		};
+		auto consume = [&](uint32_t level, const InFlight& f) {
 			__half2 result = __float2half2_rn(0.0f);
 #pragma unroll
 			for (uint32_t idx = 0; idx < (1u << D); ++idx) {
 				// fma((T)weight, grid_val, result) with T = __half -> __hfma2 (grid.h:162, vec.h:372-378)
-				result = __hfma2(__float2half2_rn(lc.w[idx]), *reinterpret_cast<const __half2*>(&vals[idx]), result);
+				result = __hfma2(*reinterpret_cast<const __half2*>(&f.w16[idx]), *reinterpret_cast<const __half2*>(&f.vals[idx]), result);
 			}
 			const uint32_t feat = level * F;
 			asm volatile("st.shared.b32 [%0], %1;" ::"r"(enc_tile + sw128(row, feat >> 3) + (feat & 7u) * 2u), "r"(*reinterpret_cast<uint32_t*>(&result)) : "memory");
 			if (p.dbg_enc) *reinterpret_cast<uint32_t*>(p.dbg_enc + (size_t)sample * 64 + feat) = *reinterpret_cast<uint32_t*>(&result);
+		};
+		if (lb < le) {
+			InFlight a, b;
+			issue(lb, a);
+#pragma unroll 1
+			for (uint32_t level = lb; level < le; level += 2) {
+				if (level + 1 < le) issue(level + 1, b);
+				consume(level, a);
+				if (level + 1 < le) {
+					if (level + 2 < le) issue(level + 2, a);
+					consume(level + 1, b);
+				}
+			}
 		}
 	};
 
@@ -228,7 +268,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 		const uint32_t lb = level_begin + (n_my_levels * part) / parts, le = level_begin + (n_my_levels * (part + 1)) / parts;
 #pragma unroll 1
 		for (uint32_t level = lb; level < le; ++level) {
-			const LevelInfo lv = p.grid.levels[level];
+			const LevelInfo lv = load_level(level);
 			LevelCorners<D> lc;
 			level_corners<D>(lv, x, p.grid.interpolation, lc);
 			uint32_t gbits;
@@ -505,7 +545,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 // ------------------------------------------------------------------------------------------------------------------
 size_t fused_step_smem_bytes(uint32_t n_hidden_layers, uint32_t in_w, bool train) {
 	const size_t tiles = 2 + n_hidden_layers + (train ? (in_w <= 48 ? 1 : 2) : 0);
-	return tiles * TILE_BYTES + n_hidden_layers * (WIDTH * 128) + 16 * 128 + 64 + 1024 /* alignment slack */;
+	return tiles * TILE_BYTES + n_hidden_layers * (WIDTH * 128) + 16 * 128 + 16 + MAX_LEVELS * sizeof(LevelInfo) + 1024 /* alignment slack */;
 }
 
 template <uint32_t D, bool TRAIN>

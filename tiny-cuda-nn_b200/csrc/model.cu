@@ -552,9 +552,15 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
 		const uint32_t log2_r = binning_log2_resolution(batch, m.grid.n_pos_dims);
 		m.bin_pos.resize(std::max(m.bin_pos.n, (size_t)batch * m.n_in));
 		m.bin_tgt.resize(std::max(m.bin_tgt.n, (size_t)batch * m.n_out));
-		m.bin_keys.resize(std::max(m.bin_keys.n, (size_t)batch));
+		m.bin_keys.resize(std::max(m.bin_keys.n, 2 * (size_t)batch));
 		m.bin_perm.resize(std::max(m.bin_perm.n, (size_t)batch));
-		m.bin_hist.resize(std::max(m.bin_hist.n, (size_t)binning_n_bins(log2_r, m.grid.n_pos_dims)));
+		{
+			const size_t need = 2 * (size_t)binning_n_bins(log2_r, m.grid.n_pos_dims);
+			if (m.bin_hist.n != need) {  // layout depends on n_bins: (re)allocate and zero the counters once
+				m.bin_hist.resize(need);
+				m.bin_hist.zero(stream);
+			}
+		}
 		TCNNB_CUDA_CHECK(launch_binning(stream, m.grid.n_pos_dims, batch, m.n_out, x, y, log2_r, m.bin_keys.ptr, m.bin_hist.ptr, m.bin_pos.ptr, m.bin_tgt.ptr, m.bin_perm.ptr));
 		g_kernel_launches += 3;
 		p.positions = m.bin_pos.ptr;
