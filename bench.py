@@ -176,18 +176,13 @@ def run_own(args):
         yh.append(torch.from_numpy(y).pin_memory())
         xs.append(xh[-1].cuda())
         ys.append(yh[-1].cuda())
-    grid_grads = trainer.param_gradients()[model.n_mlp_params:]
-    mlp_acc = trainer.mlp_gradient_accumulator()
+    from tcnn_b200.dp import DataParallelTrainer
+
+    dp = DataParallelTrainer(trainer)  # world == 1: plain training_step; else shard step + 2 all-reduces + replicated Adam
     stream = torch.cuda.current_stream()
 
     def step(i):
-        if world == 1:
-            trainer.training_step(xs[i % pool], ys[i % pool])
-        else:
-            trainer.training_step_shard(xs[i % pool], ys[i % pool], global_batch, run_optimizer=False)
-            dist.all_reduce(grid_grads)
-            dist.all_reduce(mlp_acc)
-            trainer.optimizer_step()
+        dp.training_step(xs[i % pool], ys[i % pool])
 
     def sync_all():
         if world > 1:

@@ -540,9 +540,19 @@ void orc_mlp_backward(const orc_mlp_t* m, uint32_t B, int accum_mode, const uint
 // ---------------------------------------------------------------------------------------------
 // Loss
 // ---------------------------------------------------------------------------------------------
+static void loss_impl(int loss_type, uint32_t B, uint32_t stride, uint32_t dims, float loss_scale, uint32_t n_total, const uint16_t* prediction, const float* target, float* values, uint16_t* grads);
+
 void orc_loss(int loss_type, uint32_t B, uint32_t stride, uint32_t dims, float loss_scale, const uint16_t* prediction, const float* target, float* values, uint16_t* grads) {
+	loss_impl(loss_type, B, stride, dims, loss_scale, B * stride / stride * dims, prediction, target, values, grads);
+}
+
+// n_total is the normalisation count (relative_l2.h:62); a data-parallel shard passes the GLOBAL batch * dims.
+void orc_loss_n(int loss_type, uint32_t B, uint32_t stride, uint32_t dims, float loss_scale, uint32_t n_total, const uint16_t* prediction, const float* target, float* values, uint16_t* grads) {
+	loss_impl(loss_type, B, stride, dims, loss_scale, n_total, prediction, target, values, grads);
+}
+
+static void loss_impl(int loss_type, uint32_t B, uint32_t stride, uint32_t dims, float loss_scale, uint32_t n_total, const uint16_t* prediction, const float* target, float* values, uint16_t* grads) {
 	const uint32_t n_elements = B * stride;
-	const uint32_t n_total = n_elements / stride * dims;
 #pragma omp parallel for schedule(static)
 	for (int64_t ii = 0; ii < (int64_t)n_elements; ++ii) {
 		const uint32_t i = (uint32_t)ii;
@@ -616,6 +626,13 @@ void orc_adam_step(const orc_adam_t* a, uint64_t n, uint64_t n_matrix, float los
 // Whole step (trainer.h:254-357, non-JIT order of operations §3.2)
 // ---------------------------------------------------------------------------------------------
 double orc_training_step(const orc_model_t* model, uint32_t B, const float* positions, const float* targets, float* params_fp32, uint16_t* params_fp16, uint16_t* grads_fp16, float* m1, float* m2, uint32_t* steps, int run_optimizer, float* loss_values) {
+	return orc_training_step_shard(model, B, B, positions, targets, params_fp32, params_fp16, grads_fp16, nullptr, m1, m2, steps, run_optimizer, loss_values);
+}
+
+// One rank's shard of a global batch (new: the reference has no multi-GPU path). The loss is normalised over the global
+// batch so that summing the shards' gradients reproduces the single-process gradients. If grad_sums is non-null it
+// receives the exact (double) gradient sums of this shard: ranks add those and round once, like the device's fp32 path.
+double orc_training_step_shard(const orc_model_t* model, uint32_t B, uint32_t B_global, const float* positions, const float* targets, float* params_fp32, uint16_t* params_fp16, uint16_t* grads_fp16, double* grad_sums, float* m1, float* m2, uint32_t* steps, int run_optimizer, float* loss_values) {
 	const orc_grid_t* g = model->grid;
 	const orc_mlp_t* m = model->mlp;
 	const size_t n_mlp = m->n_params, n_grid = g->n_params, n = n_mlp + n_grid;
@@ -627,7 +644,7 @@ double orc_training_step(const orc_model_t* model, uint32_t B, const float* posi
 
 	std::vector<float> L((size_t)B * OUT);
 	std::vector<uint16_t> dL_dy((size_t)B * OUT);
-	orc_loss(model->loss_type, B, OUT, m->out_width, model->loss_scale, out.data(), targets, L.data(), dL_dy.data());
+	orc_loss_n(model->loss_type, B, OUT, m->out_width, model->loss_scale, B_global * m->out_width, out.data(), targets, L.data(), dL_dy.data());
 	double loss_sum = 0;
 	for (size_t i = 0; i < L.size(); ++i) loss_sum += L[i];
 	if (loss_values) {
@@ -641,6 +658,10 @@ double orc_training_step(const orc_model_t* model, uint32_t B, const float* posi
 	orc_grid_backward(g, B, positions, d_enc.data(), dG.data());
 	for (size_t i = 0; i < n_mlp; ++i) grads_fp16[i] = d2h(dW[i]);
 	for (size_t i = 0; i < n_grid; ++i) grads_fp16[n_mlp + i] = d2h(dG[i]);
+	if (grad_sums) {
+		for (size_t i = 0; i < n_mlp; ++i) grad_sums[i] = dW[i];
+		for (size_t i = 0; i < n_grid; ++i) grad_sums[n_mlp + i] = dG[i];
+	}
 
 	if (run_optimizer) {
 		orc_adam_step(model->adam, n, n_mlp, model->loss_scale, params_fp32, params_fp16, grads_fp16, m1, m2, steps);

@@ -108,6 +108,9 @@ void orc_mlp_backward(const orc_mlp_t* m, uint32_t B, int accum_mode, const uint
 void orc_loss(int loss_type, uint32_t B, uint32_t stride, uint32_t dims, float loss_scale, const uint16_t* prediction,
               const float* target, float* values, uint16_t* grads);
 
+void orc_loss_n(int loss_type, uint32_t B, uint32_t stride, uint32_t dims, float loss_scale, uint32_t n_total, const uint16_t* prediction,
+                const float* target, float* values, uint16_t* grads);
+
 /* ---- Adam (optimizers/adam.h:48-129) ---- gradients as fp16 bits (what the reference's buffer holds). */
 void orc_adam_step(const orc_adam_t* a, uint64_t n, uint64_t n_matrix, float loss_scale, float* weights_fp32,
                    uint16_t* weights_fp16, const uint16_t* grads_fp16, float* m1, float* m2, uint32_t* steps);
@@ -125,6 +128,10 @@ typedef struct {
 double orc_training_step(const orc_model_t* model, uint32_t B, const float* positions, const float* targets,
                          float* params_fp32, uint16_t* params_fp16, uint16_t* grads_fp16, float* m1, float* m2,
                          uint32_t* steps, int run_optimizer, float* loss_values /* [B][out_width] or NULL */);
+/* Data-parallel shard of a global batch (loss normalised over B_global); grad_sums (optional) = exact double sums. */
+double orc_training_step_shard(const orc_model_t* model, uint32_t B, uint32_t B_global, const float* positions, const float* targets,
+                               float* params_fp32, uint16_t* params_fp16, uint16_t* grads_fp16, double* grad_sums, float* m1, float* m2,
+                               uint32_t* steps, int run_optimizer, float* loss_values);
 /* network->inference (object.h:214-282): fp32 [B][out_width]. */
 void orc_inference(const orc_model_t* model, uint32_t B, const float* positions, const uint16_t* params_fp16, float* out);
 

@@ -212,3 +212,37 @@ def make_targets(x, n_out):
 
 def half_bits_to_float(a):
     return a.view(np.float16).astype(np.float32)
+
+
+class OracleShardTrainer:
+    """Stand-in for the CUDA trainer with the interface tcnn_b200.dp.DataParallelTrainer drives, backed by the CPU oracle.
+    Lets the data-parallel host logic (sharding, global loss normalisation, gradient all-reduce, replicated Adam) be
+    tested with gloo on CPU. Gradient buffers are fp64 exact sums (the device all-reduces fp16 / fp32 partial sums)."""
+
+    def __init__(self, n_in, n_out, config, seed=1337):
+        import torch
+
+        self.m = OracleModel(n_in, n_out, config, seed=seed)
+        self.grad_sums = torch.zeros(self.m.n_params, dtype=torch.float64)
+        self._loss = 0.0
+        load().orc_training_step_shard.restype = ctypes.c_double
+
+    def training_step_shard(self, x, y, global_batch, run_optimizer=False):
+        m = self.m
+        xs, ys = np.ascontiguousarray(x.numpy()), np.ascontiguousarray(y.numpy())
+        self._loss = m.lib.orc_training_step_shard(ctypes.byref(m.desc), xs.shape[0], int(global_batch), _p(xs), _p(ys), _p(m.params_fp32), _p(m.params_fp16),
+                                                   _p(m.grads_fp16), ctypes.c_void_p(self.grad_sums.data_ptr()), _p(m.m1), _p(m.m2), _p(m.steps), 0, None)
+        if run_optimizer:
+            self.optimizer_step()
+
+    def gradient_buffers(self):
+        return [self.grad_sums]
+
+    def optimizer_step(self):
+        m = self.m
+        m.grads_fp16[:] = self.grad_sums.numpy().astype(np.float16).view(np.uint16)
+        m.lib.orc_adam_step(ctypes.byref(m.adam), ctypes.c_uint64(m.n_params), ctypes.c_uint64(m.n_mlp), ctypes.c_float(128.0), _p(m.params_fp32), _p(m.params_fp16),
+                            _p(m.grads_fp16), _p(m.m1), _p(m.m2), _p(m.steps))
+
+    def loss(self):
+        return self._loss

@@ -47,54 +47,66 @@ __global__ void bin_count_kernel(uint32_t n, const float* __restrict__ pos, uint
 }
 
 // Exclusive scan of `n_bins` counters by one block of 1024 threads: cursor[b] = first output slot of bin b.
-// Each thread owns a contiguous run of bins (local serial prefix), the 1024 run totals are scanned with shuffles.
+// The counters are staged through shared memory with coalesced accesses (all loads of a thread are independent), each
+// thread scans a contiguous run of the staged copy, and the 1024 run totals are combined with shuffles.
 // The counters are re-armed to zero for the next step, so no memset is needed per step.
+constexpr uint32_t SCAN_CHUNK = 16384;  // bins staged per pass (64 KB of shared memory)
+
 __global__ void __launch_bounds__(1024) bin_scan_kernel(uint32_t n_bins, uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor) {
+	extern __shared__ uint32_t staged[];
 	__shared__ uint32_t warp_sums[32];
-	const uint32_t per = (n_bins + 1023u) / 1024u;
-	const uint32_t begin = threadIdx.x * per, end = min(n_bins, begin + per);
-	uint32_t total = 0;
-	for (uint32_t i = begin; i < end; ++i) total += hist[i];
-	uint32_t incl = total;
-#pragma unroll
-	for (uint32_t o = 1; o < 32; o <<= 1) {
-		const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-		if ((threadIdx.x & 31u) >= o) incl += t;
-	}
-	if ((threadIdx.x & 31u) == 31u) warp_sums[threadIdx.x >> 5] = incl;
-	__syncthreads();
-	if (threadIdx.x < 32) {
-		uint32_t w = warp_sums[threadIdx.x];
+	__shared__ uint32_t carry;
+	if (threadIdx.x == 0) carry = 0;
+	for (uint32_t base = 0; base < n_bins; base += SCAN_CHUNK) {
+		const uint32_t n = min(SCAN_CHUNK, n_bins - base);
+		for (uint32_t i = threadIdx.x; i < n; i += 1024) {
+			staged[i] = hist[base + i];
+			hist[base + i] = 0;
+		}
+		__syncthreads();
+		const uint32_t per = (n + 1023u) / 1024u;
+		const uint32_t begin = min(n, threadIdx.x * per), end = min(n, begin + per);
+		uint32_t total = 0;
+		for (uint32_t i = begin; i < end; ++i) total += staged[i];
+		uint32_t incl = total;
 #pragma unroll
 		for (uint32_t o = 1; o < 32; o <<= 1) {
-			const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, w, o);
-			if (threadIdx.x >= o) w += t;
+			const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+			if ((threadIdx.x & 31u) >= o) incl += t;
 		}
-		warp_sums[threadIdx.x] = w;
-	}
-	__syncthreads();
-	uint32_t run = ((threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0u) + incl - total;
-	for (uint32_t i = begin; i < end; ++i) {
-		const uint32_t c = hist[i];
-		cursor[i] = run;
-		hist[i] = 0;
-		run += c;
+		if ((threadIdx.x & 31u) == 31u) warp_sums[threadIdx.x >> 5] = incl;
+		__syncthreads();
+		if (threadIdx.x < 32) {
+			uint32_t w = warp_sums[threadIdx.x];
+#pragma unroll
+			for (uint32_t o = 1; o < 32; o <<= 1) {
+				const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, w, o);
+				if (threadIdx.x >= o) w += t;
+			}
+			warp_sums[threadIdx.x] = w;
+		}
+		__syncthreads();
+		const uint32_t c = carry;
+		uint32_t run = c + ((threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0u) + incl - total;
+		for (uint32_t i = begin; i < end; ++i) {
+			const uint32_t v = staged[i];
+			staged[i] = run;
+			run += v;
+		}
+		__syncthreads();
+		for (uint32_t i = threadIdx.x; i < n; i += 1024) cursor[base + i] = staged[i];
+		if (threadIdx.x == 1023) carry = c + warp_sums[31];
+		__syncthreads();
 	}
 }
 
-template <uint32_t D>
-__global__ void bin_scatter_kernel(uint32_t n, uint32_t n_out, const float* __restrict__ pos, const float* __restrict__ tgt, const uint32_t* __restrict__ keys,
-                                   const uint32_t* __restrict__ cursor, float* __restrict__ pos_sorted, float* __restrict__ tgt_sorted, uint32_t* __restrict__ perm) {
+// perm[first slot of the sample's bin + its rank inside the bin] = sample. Only the permutation is materialised: the fused
+// kernel fetches positions / targets through it (one extra 12-byte read per sample, against ~100 table sectors per sample).
+__global__ void bin_scatter_kernel(uint32_t n, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm) {
 	const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
 	if (i >= n) return;
 	const uint2 kr = reinterpret_cast<const uint2*>(keys)[i];
-	const uint32_t dst = __ldg(cursor + kr.x) + kr.y;
-#pragma unroll
-	for (uint32_t d = 0; d < D; ++d) pos_sorted[(size_t)dst * D + d] = pos[(size_t)i * D + d];
-	if (tgt) {
-		for (uint32_t j = 0; j < n_out; ++j) tgt_sorted[(size_t)dst * n_out + j] = tgt[(size_t)i * n_out + j];
-	}
-	perm[dst] = i;
+	perm[__ldg(cursor + kr.x) + kr.y] = i;
 }
 
 }  // namespace
@@ -111,22 +123,25 @@ uint32_t binning_log2_resolution(uint32_t n_samples, uint32_t n_pos_dims) {
 
 uint32_t binning_n_bins(uint32_t log2_r, uint32_t n_pos_dims) { return n_pos_dims == 2 ? (1u << log2_r) : (1u << (2 * log2_r)); }
 
-cudaError_t launch_binning(cudaStream_t stream, uint32_t n_pos_dims, uint32_t n, uint32_t n_out, const float* pos, const float* tgt, uint32_t log2_r, uint32_t* keys,
-                           uint32_t* hist, float* pos_sorted, float* tgt_sorted, uint32_t* perm) {
+cudaError_t launch_binning(cudaStream_t stream, uint32_t n_pos_dims, uint32_t n, const float* pos, uint32_t log2_r, uint32_t* keys, uint32_t* hist, uint32_t* perm) {
 	const uint32_t n_bins = binning_n_bins(log2_r, n_pos_dims);
 	uint32_t* cursor = hist + n_bins;  // hist: [n_bins counters (zero between calls) | n_bins cursors]
 	const uint32_t blocks = (n + 255) / 256;
+	static bool attr_set = false;
+	if (!attr_set) {
+		cudaError_t err = cudaFuncSetAttribute(bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SCAN_CHUNK * sizeof(uint32_t)));
+		if (err != cudaSuccess) return err;
+		attr_set = true;
+	}
 	if (n_pos_dims == 2) {
 		bin_count_kernel<2><<<blocks, 256, 0, stream>>>(n, pos, log2_r, keys, hist);
-		bin_scan_kernel<<<1, 1024, 0, stream>>>(n_bins, hist, cursor);
-		bin_scatter_kernel<2><<<blocks, 256, 0, stream>>>(n, n_out, pos, tgt, keys, cursor, pos_sorted, tgt_sorted, perm);
 	} else if (n_pos_dims == 3) {
 		bin_count_kernel<3><<<blocks, 256, 0, stream>>>(n, pos, log2_r, keys, hist);
-		bin_scan_kernel<<<1, 1024, 0, stream>>>(n_bins, hist, cursor);
-		bin_scatter_kernel<3><<<blocks, 256, 0, stream>>>(n, n_out, pos, tgt, keys, cursor, pos_sorted, tgt_sorted, perm);
 	} else {
 		return cudaErrorInvalidValue;
 	}
+	bin_scan_kernel<<<1, 1024, SCAN_CHUNK * sizeof(uint32_t), stream>>>(n_bins, hist, cursor);
+	bin_scatter_kernel<<<blocks, 256, 0, stream>>>(n, keys, cursor, perm);
 	return cudaGetLastError();
 }
 

@@ -8,10 +8,9 @@ namespace tcnnb {
 uint32_t binning_log2_resolution(uint32_t n_samples, uint32_t n_pos_dims);
 uint32_t binning_n_bins(uint32_t log2_r, uint32_t n_pos_dims);
 
-// pos [n][D], tgt [n][n_out] (may be null) -> pos_sorted, tgt_sorted, perm[sorted index] = original index.
-// keys: scratch [2 * n] (bin, rank-in-bin per sample); hist: scratch [2 * n_bins], whose first n_bins words must be ZERO on entry (they are left zero on
-// exit, so one memset at allocation time suffices). 3 launches on `stream`.
-cudaError_t launch_binning(cudaStream_t stream, uint32_t n_pos_dims, uint32_t n, uint32_t n_out, const float* pos, const float* tgt, uint32_t log2_r, uint32_t* keys,
-                           uint32_t* hist, float* pos_sorted, float* tgt_sorted, uint32_t* perm);
+// pos [n][D] -> perm[binned index] = original sample index.
+// keys: scratch [2 * n] (bin, rank-in-bin per sample); hist: scratch [2 * n_bins], whose first n_bins words must be ZERO on
+// entry (they are left zero on exit, so one memset at allocation time suffices). 3 launches on `stream`.
+cudaError_t launch_binning(cudaStream_t stream, uint32_t n_pos_dims, uint32_t n, const float* pos, uint32_t log2_r, uint32_t* keys, uint32_t* hist, uint32_t* perm);
 
 }  // namespace tcnnb

@@ -248,16 +248,13 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 			if (p.dbg_enc) *reinterpret_cast<uint32_t*>(p.dbg_enc + (size_t)sample * 64 + feat) = *reinterpret_cast<uint32_t*>(&result);
 		};
 		if (lb < le) {
-			InFlight a, b;
-			issue(lb, a);
+			InFlight cur, nxt;
+			issue(lb, cur);
 #pragma unroll 1
-			for (uint32_t level = lb; level < le; level += 2) {
-				if (level + 1 < le) issue(level + 1, b);
-				consume(level, a);
-				if (level + 1 < le) {
-					if (level + 2 < le) issue(level + 2, a);
-					consume(level + 1, b);
-				}
+			for (uint32_t level = lb; level < le; ++level) {
+				if (level + 1 < le) issue(level + 1, nxt);
+				consume(level, cur);
+				cur = nxt;
 			}
 		}
 	};
@@ -289,9 +286,12 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 		}
 	};
 
-	auto load_x = [&](uint32_t tile, float (&x)[D]) {
+	// Tile row -> caller's sample index (identity unless the batch was spatially binned) and its position.
+	auto load_x = [&](uint32_t tile, float (&x)[D], uint32_t& osample) {
+		osample = tile * TILE_M + row;
+		if (p.perm) osample = __ldg(p.perm + osample);
 #pragma unroll
-		for (uint32_t d = 0; d < D; ++d) x[d] = __ldg(p.positions + ((size_t)tile * TILE_M + row) * D + d);
+		for (uint32_t d = 0; d < D; ++d) x[d] = __ldg(p.positions + (size_t)osample * D + d);
 	};
 
 	// ---- software pipeline over this CTA's tiles: while the tensor core works on tile t (2*NH + 2 MMA batches, each followed
@@ -305,23 +305,23 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 	bool dw_started = false;
 	bool have_prev = false;
 	float x_prev[D], x_cur[D], x_next[D];
+	uint32_t os_cur = 0, os_next = 0;  // caller's sample index of this thread's row in the current / next tile
 #pragma unroll
 	for (uint32_t d = 0; d < D; ++d) x_prev[d] = x_cur[d] = x_next[d] = 0.0f;
 
 	const uint32_t n_tiles = p.batch_size / TILE_M;
 	uint32_t tile = blockIdx.x;
 	if (tile < n_tiles) {
-		load_x(tile, x_cur);
-		for (uint32_t part = 0; part < GATHER_PARTS; ++part) gather_part(x_cur, s.enc, p.dbg_enc && p.perm ? __ldg(p.perm + tile * TILE_M + row) : tile * TILE_M + row, part, GATHER_PARTS);
+		load_x(tile, x_cur, os_cur);
+		for (uint32_t part = 0; part < GATHER_PARTS; ++part) gather_part(x_cur, s.enc, os_cur, part, GATHER_PARTS);
 	}
 	uint32_t buf = 0;
 	for (; tile < n_tiles; tile += gridDim.x, buf ^= 1u) {
-		const uint32_t sample = tile * TILE_M + row;                       // row of the (possibly binned) input arrays
-		const uint32_t osample = p.perm ? __ldg(p.perm + sample) : sample;  // caller's sample index, for per-sample outputs
+		const uint32_t osample = os_cur;  // caller's sample index: targets and per-sample outputs
 		const uint32_t enc_cur = s.enc + buf * TILE_BYTES, enc_nxt = s.enc + (buf ^ 1u) * TILE_BYTES;
 		const uint32_t next_tile = tile + gridDim.x;
 		const bool have_next = next_tile < n_tiles;
-		if (have_next) load_x(next_tile, x_next);
+		if (have_next) load_x(next_tile, x_next, os_next);
 		// One tile = n_batches MMA batches. Batch b: stage_sync -> one thread issues the MMAs -> every thread fills the wait
 		// slot with memory work of the neighbouring tiles -> wait for the tensor core -> epilogue of batch b.
 		//   b <  NH          forward hidden layer b
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 
 			// ---- wait slot: gather of tile t+1 (slots 0, 1), scatter of tile t-1 (following slots)
 			if (b < GATHER_PARTS) {
-				if (have_next) gather_part(x_next, enc_nxt, p.dbg_enc && p.perm ? __ldg(p.perm + next_tile * TILE_M + row) : next_tile * TILE_M + row, b, GATHER_PARTS);
+				if (have_next) gather_part(x_next, enc_nxt, os_next, b, GATHER_PARTS);
 			} else if (TRAIN && have_prev && b < GATHER_PARTS + scatter_parts) {
 				scatter_part(x_prev, b - GATHER_PARTS, scatter_parts);
 			}
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 							float g = 0.0f;
 							if (j < p.n_out) {
 								const float pred = __half2float(y16[j]);
-								const float diff = pred - __ldg(p.targets + (size_t)sample * p.n_out + j);
+								const float diff = pred - __ldg(p.targets + (size_t)osample * p.n_out + j);
 								float value, grad;
 								if (p.loss_type == LOSS_RELATIVE_L2) {
 									const float psq = pred * pred + 0.01f;
@@ -484,6 +484,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 		}
 #pragma unroll
 		for (uint32_t d = 0; d < D; ++d) x_cur[d] = x_next[d];
+		os_cur = os_next;
 	}
 
 	// ---- drain: scatter of the last tile

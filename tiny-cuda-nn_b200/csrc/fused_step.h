@@ -22,7 +22,7 @@ struct FusedStepParams {
 	uint32_t loss_batch_size;      // samples the loss is normalised over (== batch_size unless the batch is sharded over GPUs)
 	const float* positions;        // [batch][D] fp32
 	const float* targets;          // [batch][n_out] fp32 (training only)
-	const uint32_t* perm;          // optional: positions/targets are a spatially binned copy; row i is original sample perm[i]
+	const uint32_t* perm;          // optional spatial binning: tile row i processes the caller's sample perm[i] (positions/targets/outputs)
 	// parameters: [MLP weights | grid table] fp16, and the matching fp16 gradient buffer (grid part accumulated with red.f16x2)
 	const __half* params;
 	__half* grads;

@@ -277,7 +277,6 @@ struct Model {
 
 	// spatial binning scratch (binning.cu): sorted copies of the batch + permutation
 	bool binning = true;  // TCNNB_BINNING=0 disables
-	DeviceBuffer<float> bin_pos, bin_tgt;
 	DeviceBuffer<uint32_t> bin_keys, bin_hist, bin_perm;
 
 	// host staging for the *_host entry points
@@ -550,8 +549,6 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
 	// Process the batch in (y, z)-column order: same sums, far fewer distinct memory sectors on the coarse levels (binning.cu).
 	if (m.binning && batch >= 16384) {
 		const uint32_t log2_r = binning_log2_resolution(batch, m.grid.n_pos_dims);
-		m.bin_pos.resize(std::max(m.bin_pos.n, (size_t)batch * m.n_in));
-		m.bin_tgt.resize(std::max(m.bin_tgt.n, (size_t)batch * m.n_out));
 		m.bin_keys.resize(std::max(m.bin_keys.n, 2 * (size_t)batch));
 		m.bin_perm.resize(std::max(m.bin_perm.n, (size_t)batch));
 		{
@@ -561,10 +558,8 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
 				m.bin_hist.zero(stream);
 			}
 		}
-		TCNNB_CUDA_CHECK(launch_binning(stream, m.grid.n_pos_dims, batch, m.n_out, x, y, log2_r, m.bin_keys.ptr, m.bin_hist.ptr, m.bin_pos.ptr, m.bin_tgt.ptr, m.bin_perm.ptr));
+		TCNNB_CUDA_CHECK(launch_binning(stream, m.grid.n_pos_dims, batch, x, log2_r, m.bin_keys.ptr, m.bin_hist.ptr, m.bin_perm.ptr));
 		g_kernel_launches += 3;
-		p.positions = m.bin_pos.ptr;
-		p.targets = m.bin_tgt.ptr;
 		p.perm = m.bin_perm.ptr;
 	}
 	m.prof_mark(stream);

@@ -200,6 +200,18 @@ class _Trainer:
 
         return self._view(load().tcnnb_mlp_gradient_accumulator(self._m._h), self._m.n_mlp_params, torch.float32)
 
+    def gradient_buffers(self):
+        """The two buffers a data-parallel all-reduce must sum: fp16 grid-gradient table, fp32 MLP weight-gradient accumulator."""
+        if not hasattr(self, "_grad_bufs"):
+            import torch
+
+            ptr = load().tcnnb_param_gradients(self._m._h)
+            self._grad_bufs = [self._view(ptr + 2 * self._m.n_mlp_params, self._m.n_params - self._m.n_mlp_params, torch.float16), self.mlp_gradient_accumulator()]
+        return self._grad_bufs
+
+    def device(self):
+        return "cuda"
+
     def set_params_full_precision(self, params):
         import torch
 
