@@ -59,9 +59,22 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(uint32_t n_bins, uint32_
 	if (threadIdx.x == 0) carry = 0;
 	for (uint32_t base = 0; base < n_bins; base += SCAN_CHUNK) {
 		const uint32_t n = min(SCAN_CHUNK, n_bins - base);
-		for (uint32_t i = threadIdx.x; i < n; i += 1024) {
-			staged[i] = hist[base + i];
-			hist[base + i] = 0;
+		{
+			// all 16 loads of a thread in flight at once (a rolled loop would pay one memory latency per iteration)
+			uint32_t v[SCAN_CHUNK / 1024];
+#pragma unroll
+			for (uint32_t j = 0; j < SCAN_CHUNK / 1024; ++j) {
+				const uint32_t i = threadIdx.x + j * 1024;
+				v[j] = i < n ? hist[base + i] : 0u;
+			}
+#pragma unroll
+			for (uint32_t j = 0; j < SCAN_CHUNK / 1024; ++j) {
+				const uint32_t i = threadIdx.x + j * 1024;
+				if (i < n) {
+					staged[i] = v[j];
+					hist[base + i] = 0;
+				}
+			}
 		}
 		__syncthreads();
 		const uint32_t per = (n + 1023u) / 1024u;
