@@ -76,6 +76,8 @@ int tcnnb_optimizer_step(tcnnb_model* m, tcnnb_stream stream);
 /* Device pointer + element count of the fp32 accumulator that holds the MLP weight gradients between the backward
  * pass and the optimizer (for the data-parallel all-reduce); the grid gradients are tcnnb_param_gradients(). */
 float* tcnnb_mlp_gradient_accumulator(tcnnb_model* m);
+/* Device pointer to the fp16 gradient table of the grid encoding (n_params - n_mlp_params elements); no side effects. */
+void* tcnnb_grid_gradients(tcnnb_model* m);
 /* trainer->loss(stream, ctx) (trainer.h:372-378, reduce_sum.h:132-146): sum of the loss values of the last step;
  * synchronises the stream. */
 int tcnnb_loss(tcnnb_model* m, tcnnb_stream stream, float* loss_out);

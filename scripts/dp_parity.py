@@ -1,0 +1,67 @@
+"""2-GPU check (run under gpurun --gpus 2 as a plain python script that spawns 2 ranks): data-parallel step == single-GPU step."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tiny-cuda-nn_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+CFG = json.load(open(os.path.join(ROOT, "tests", "golden", "configs", "hash3d_small.json")))
+B = 32768
+
+
+def worker(rank, world, out):
+    import oracle_binding as ob
+    import tcnn_b200
+    from tcnn_b200.dp import DataParallelTrainer
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    rng = ob.default_rng(1337)
+    x = ob.generate_random_uniform(rng, B * 3).reshape(B, 3)
+    y = ob.make_targets(x, 3)
+    model = tcnn_b200.create_from_config(3, 3, CFG)
+    dp = DataParallelTrainer(model.trainer)
+    lo, hi = dp.shard(B)
+    xd, yd = torch.from_numpy(x[lo:hi]).cuda(), torch.from_numpy(y[lo:hi]).cuda()
+    losses = []
+    for _ in range(5):
+        dp.training_step(xd, yd)
+        losses.append(dp.loss())
+    torch.cuda.synchronize()
+    np.savez(os.path.join(out, f"dp{rank}.npz"), p=model.trainer.params_full_precision().cpu().numpy(), losses=np.array(losses))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    mp.spawn(worker, args=(2, out), nprocs=2, join=True)
+    import oracle_binding as ob
+    import tcnn_b200
+
+    torch.cuda.set_device(0)
+    rng = ob.default_rng(1337)
+    x = ob.generate_random_uniform(rng, B * 3).reshape(B, 3)
+    y = ob.make_targets(x, 3)
+    model = tcnn_b200.create_from_config(3, 3, CFG)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    losses = []
+    for _ in range(5):
+        model.trainer.training_step(xd, yd)
+        losses.append(model.trainer.loss())
+    p1 = model.trainer.params_full_precision().cpu().numpy()
+    r0, r1 = np.load(os.path.join(out, "dp0.npz")), np.load(os.path.join(out, "dp1.npz"))
+    print("replicas identical:", np.array_equal(r0["p"], r1["p"]))
+    print("losses dp:", r0["losses"].tolist())
+    print("losses 1gpu:", losses)
+    print("max |param diff| dp vs 1gpu:", float(np.abs(r0["p"] - p1).max()), "mean:", float(np.abs(r0["p"] - p1).mean()))
+    assert np.array_equal(r0["p"], r1["p"])
+    assert np.allclose(r0["losses"], losses, rtol=2e-2)
+    print("DP PARITY OK")

@@ -1,0 +1,56 @@
+// fused_common.cuh -- device helpers shared by the fused-step kernels (fused_step.cu, fused_ws.cu).
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace tcnnb {
+namespace fused {
+
+using namespace ptx;
+
+constexpr uint32_t TILE_BYTES = TILE_M * 128;  // [128][64] fp16
+constexpr uint32_t WIDTH = 64;
+
+// Byte offset of 16-byte chunk `c` (0..7) of row `r` inside a SWIZZLE_128B tile.
+__device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) {
+	return r * 128u + ((c ^ (r & 7u)) << 4);
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+	asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+	asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+	__half2 h = __floats2half2_rn(lo, hi);
+	return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ uint32_t relu_pack(uint32_t lo_bits, uint32_t hi_bits) {
+	// fp32 accumulator -> fp16 (rn) -> ReLU in fp16, as warp_activation<__half> does (common_device.h:115-121).
+	__half2 h = __floats2half2_rn(__uint_as_float(lo_bits), __uint_as_float(hi_bits));
+	h = __hmax2(h, __float2half2_rn(0.0f));
+	return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// gradient (fp32 acc -> fp16) * (forward > 0), warp_activation_backward ReLU (common_device.h:363-368).
+__device__ __forceinline__ uint32_t relu_bwd_pack(uint32_t lo_bits, uint32_t hi_bits, uint32_t fwd_bits) {
+	__half2 g = __floats2half2_rn(__uint_as_float(lo_bits), __uint_as_float(hi_bits));
+	const __half2 f = *reinterpret_cast<const __half2*>(&fwd_bits);
+	const __half2 mask = __hgt2(f, __float2half2_rn(0.0f));  // 1.0 / 0.0
+	g = __hmul2(g, mask);
+	return *reinterpret_cast<uint32_t*>(&g);
+}
+
+struct SmemSync {
+	// dynamic shared memory, 1024-byte aligned:
+	//   [ enc_0 | enc_1 | h_0 .. h_{NH-1} | dy | (park) | W_0 .. W_{NH-1} | W_out ] then barriers
+	uint32_t enc, h0, dy, park, w0, w_out, bar, tmem_slot, levels;
+};
+
+
+}  // namespace fused
+}  // namespace tcnnb

@@ -42,4 +42,8 @@ struct FusedStepParams {
 size_t fused_step_smem_bytes(uint32_t n_hidden_layers, uint32_t in_w, bool train);
 cudaError_t launch_fused_step(const FusedStepParams& p, uint32_t n_pos_dims, bool train, uint32_t n_ctas, cudaStream_t stream);
 
+// Warp-specialised variant (fused_ws.cu): one 640-thread CTA per SM.
+size_t fused_ws_smem_bytes(uint32_t n_hidden_layers, bool train);
+cudaError_t launch_fused_ws(const FusedStepParams& p, uint32_t n_pos_dims, bool train, uint32_t n_ctas, cudaStream_t stream);
+
 }  // namespace tcnnb

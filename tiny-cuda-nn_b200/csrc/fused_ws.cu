@@ -1,0 +1,498 @@
+// fused_ws.cu -- warp-specialised variant of the fused training / inference step (same math as fused_step.cu).
+//
+// Why a second structure: in the bulk-synchronous kernel every MMA batch ends in a CTA-wide barrier, so the long and
+// uneven latencies of the table gathers / gradient reductions that fill the wait slots end up on the critical path of the
+// MLP chain (profiles/: 12 % barrier stalls, 45 % long-scoreboard). Here the two kinds of work never wait for each other
+// inside a tile:
+//
+//   warps 0..3   "MLP group" (128 threads, thread t <-> tile row t <-> TMEM lane t): issues the tcgen05 MMAs and runs the
+//                epilogues of one 128-sample tile at a time, tile after tile.
+//   warps 4..19  "memory group": two sub-groups of 8 warps (256 threads = two threads per sample). Sub-group g owns the
+//                tiles k = g, g+2, ... of this CTA: it gathers + blends tile k into enc[g], then scatters the parked
+//                dL/d(enc) of its previous tile k-2, continuously, while the MLP group works on tile k-1.
+//
+// Hand-offs are mbarriers only:  enc_full[g]  (memory -> MLP: encoded tile ready)
+//                                enc_free[g]  (tcgen05.commit -> memory: last MMA that reads enc[g] has finished)
+//                                park_full[g] (MLP -> memory: dL/d(enc) of the tile parked)
+//                                park_free[g] (memory -> MLP: parked gradients consumed)
+// One persistent CTA per SM (640 threads), grid = #SMs.
+#include "common.cuh"
+#include "fused_common.cuh"
+#include "fused_step.h"
+#include "grid_device.cuh"
+#include "ptx.cuh"
+
+namespace tcnnb {
+
+using namespace ptx;
+using namespace fused;
+
+namespace {
+
+constexpr uint32_t WS_MLP_THREADS = 128;
+constexpr uint32_t WS_SUB_THREADS = 256;
+constexpr uint32_t WS_THREADS = WS_MLP_THREADS + 2 * WS_SUB_THREADS;  // 640
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads) {
+	asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+
+}  // namespace
+
+template <uint32_t D, uint32_t F, bool TRAIN>
+__global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStepParams p) {
+	static_assert(F == 2, "fused path: F == 2");
+	extern __shared__ __align__(1024) uint8_t smem_raw[];
+	const uint32_t tid = threadIdx.x;
+	const uint32_t warp = tid >> 5;
+	const uint32_t NH = p.n_hidden_layers;
+	const uint32_t in_w = p.grid.padded_width;
+
+	// ---- shared memory: [ enc_0 | enc_1 | h_0 .. h_{NH-1} | dy | park_0 | park_1 | W_0 .. W_{NH-1} | W_out ] barriers, level table
+	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+	const uint32_t s_enc = smem_base;
+	const uint32_t s_h0 = s_enc + 2 * TILE_BYTES;
+	const uint32_t s_dy = s_h0 + NH * TILE_BYTES;
+	const uint32_t s_park = s_dy + (TRAIN ? TILE_BYTES : 0);
+	const uint32_t s_w0 = s_park + (TRAIN ? 2 * TILE_BYTES : 0);
+	const uint32_t s_wout = s_w0 + NH * (WIDTH * 128);
+	const uint32_t s_bars = s_wout + 16 * 128;  // 9 mbarriers
+	const uint32_t bar_mma = s_bars;
+	const uint32_t bar_enc_full = s_bars + 8;    // [2]
+	const uint32_t bar_enc_free = s_bars + 24;   // [2]
+	const uint32_t bar_park_full = s_bars + 40;  // [2]
+	const uint32_t bar_park_free = s_bars + 56;  // [2]
+	const uint32_t s_tmem_slot = s_bars + 72;
+	const uint32_t s_levels = s_bars + 80;
+
+	const uint32_t tmem_cols = TRAIN ? ((NH + 2) * 64 <= 256 ? 256u : 512u) : 64u;
+	if (tid == 0) {
+		mbar_init(bar_mma, 1);
+		for (uint32_t g = 0; g < 2; ++g) {
+			mbar_init(bar_enc_full + 8 * g, WS_SUB_THREADS / 32);   // one arrival per memory warp
+			mbar_init(bar_enc_free + 8 * g, 1);                      // tcgen05.commit
+			mbar_init(bar_park_full + 8 * g, WS_MLP_THREADS / 32);  // one arrival per MLP warp
+			mbar_init(bar_park_free + 8 * g, WS_SUB_THREADS / 32);
+		}
+		fence_mbar_init();
+	}
+	if (warp == 0) {
+		__syncwarp();
+		tmem_alloc(s_tmem_slot, tmem_cols);
+		tmem_relinquish();
+	}
+	for (uint32_t i = tid; i < p.grid.n_levels * (uint32_t)(sizeof(LevelInfo) / 4); i += WS_THREADS) {
+		const uint32_t v = reinterpret_cast<const uint32_t*>(p.grid.levels)[i];
+		asm volatile("st.shared.b32 [%0], %1;" ::"r"(s_levels + i * 4), "r"(v) : "memory");
+	}
+	{
+		const __half* __restrict__ w = p.params;  // MLP weights come first in the parameter buffer
+		for (uint32_t i = tid; i < WIDTH * 8; i += WS_THREADS) {
+			const uint32_t r = i >> 3, c = i & 7;
+			uint4 v = make_uint4(0, 0, 0, 0);
+			if (c * 8 < in_w) v = __ldg(reinterpret_cast<const uint4*>(w + r * in_w + c * 8));
+			st_shared_v4(s_w0 + sw128(r, c), v.x, v.y, v.z, v.w);
+		}
+		w += WIDTH * in_w;
+		for (uint32_t l = 1; l < NH; ++l) {
+			for (uint32_t i = tid; i < WIDTH * 8; i += WS_THREADS) {
+				const uint32_t r = i >> 3, c = i & 7;
+				const uint4 v = __ldg(reinterpret_cast<const uint4*>(w + r * WIDTH + c * 8));
+				st_shared_v4(s_w0 + l * (WIDTH * 128) + sw128(r, c), v.x, v.y, v.z, v.w);
+			}
+			w += WIDTH * WIDTH;
+		}
+		for (uint32_t i = tid; i < 16 * 8; i += WS_THREADS) {
+			const uint32_t r = i >> 3, c = i & 7;
+			const uint4 v = __ldg(reinterpret_cast<const uint4*>(w + r * WIDTH + c * 8));
+			st_shared_v4(s_wout + sw128(r, c), v.x, v.y, v.z, v.w);
+		}
+	}
+	fence_proxy_async_smem();
+	tc_fence_before_sync();
+	__syncthreads();
+	tc_fence_after_sync();
+
+	uint32_t tmem_base;
+	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem_slot));
+	const uint32_t n_tiles = p.batch_size / TILE_M;
+
+	if (warp >= WS_MLP_THREADS / 32) {
+		// =========================================================================================== memory group
+		const uint32_t mt = tid - WS_MLP_THREADS;
+		const uint32_t g = mt / WS_SUB_THREADS;     // sub-group == enc / park buffer it owns
+		const uint32_t lt = mt % WS_SUB_THREADS;
+		const uint32_t row = lt & 127u;
+		const uint32_t hsel = lt >> 7;
+		const uint32_t enc_tile = s_enc + g * TILE_BYTES;
+		const uint32_t park_tile = s_park + g * TILE_BYTES;
+
+		constexpr uint32_t LEVELS_PER_CHUNK = 8 / F;
+		const uint32_t n_chunks = in_w / 8;
+		const uint32_t level_begin = hsel * (n_chunks / 2) * LEVELS_PER_CHUNK;
+		const uint32_t level_end = min(p.grid.n_levels, level_begin + (n_chunks / 2) * LEVELS_PER_CHUNK);
+		const __half* __restrict__ table = p.params + p.n_mlp_params;
+		__half* __restrict__ grad_table = p.grads + p.n_mlp_params;
+
+		auto load_level = [&](uint32_t level) {
+			LevelInfo lv;
+			uint32_t* w = reinterpret_cast<uint32_t*>(&lv);
+			const uint32_t base = s_levels + level * (uint32_t)sizeof(LevelInfo);
+			static_assert(sizeof(LevelInfo) == 32, "LevelInfo layout");
+			asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(base));
+			asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(base + 16));
+			return lv;
+		};
+
+		float x_prev[D], x_cur[D];
+		uint32_t os_cur = 0;
+#pragma unroll
+		for (uint32_t d = 0; d < D; ++d) x_prev[d] = x_cur[d] = 0.0f;
+
+		auto scatter_prev = [&]() {
+#pragma unroll 1
+			for (uint32_t level = level_begin; level < level_end; ++level) {
+				const LevelInfo lv = load_level(level);
+				LevelCorners<D> lc;
+				level_corners<D>(lv, x_prev, p.grid.interpolation, lc);
+				uint32_t gbits;
+				const uint32_t feat = level * F;
+				asm volatile("ld.shared.b32 %0, [%1];" : "=r"(gbits) : "r"(park_tile + sw128(row, feat >> 3) + (feat & 7u) * 2u));
+				const __half2 grad = *reinterpret_cast<const __half2*>(&gbits);
+				uint32_t* __restrict__ ltab = reinterpret_cast<uint32_t*>(grad_table + (size_t)lv.offset * F);
+#pragma unroll
+				for (uint32_t pr = 0; pr < (1u << (D - 1)); ++pr) {
+					// (GRAD_T)weight * grad -> __hmul2, then atomic f16x2 add (grid.h:252-255, vec.h:328-336)
+					const __half2 a0 = __hmul2(__float2half2_rn(lc.w[2 * pr]), grad);
+					const __half2 a1 = __hmul2(__float2half2_rn(lc.w[2 * pr + 1]), grad);
+					const bool paired = (lc.paired >> pr) & 1u;
+					if (!(p.ablate & ABLATE_SCATTER)) {
+						scatter_pair_f16x2(ltab, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(p.ablate & ABLATE_PAIRING), *reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
+					}
+				}
+			}
+		};
+
+		uint32_t j = 0;  // this sub-group's tile counter
+		for (uint32_t k = g, tile = blockIdx.x + g * gridDim.x; tile < n_tiles; k += 2, tile += 2 * gridDim.x, ++j) {
+			// ---- position of this thread's sample
+			os_cur = tile * TILE_M + row;
+			if (p.perm) os_cur = __ldg(p.perm + os_cur);
+#pragma unroll
+			for (uint32_t d = 0; d < D; ++d) x_cur[d] = __ldg(p.positions + (size_t)os_cur * D + d);
+
+			// ---- gather tile k into enc[g] once the MMAs of tile k-2 have released it
+			if (j >= 1) mbar_wait(bar_enc_free + 8 * g, (j - 1) & 1u);
+#pragma unroll
+			for (uint32_t c = 0; c < 4; ++c) {  // zero this thread's half of the row (padding features are zero, grid.h:759-766)
+				const uint32_t chunk = c < n_chunks / 2 ? hsel * (n_chunks / 2) + c : n_chunks + hsel * ((8 - n_chunks) / 2) + (c - n_chunks / 2);
+				st_shared_v4(enc_tile + sw128(row, chunk), 0, 0, 0, 0);
+			}
+#pragma unroll 1
+			for (uint32_t level = level_begin; level < level_end; ++level) {
+				const LevelInfo lv = load_level(level);
+				LevelCorners<D> lc;
+				level_corners<D>(lv, x_cur, p.grid.interpolation, lc);
+				const uint32_t* __restrict__ ltab = reinterpret_cast<const uint32_t*>(table + (size_t)lv.offset * F);
+				uint32_t vals[1u << D];
+#pragma unroll
+				for (uint32_t pr = 0; pr < (1u << (D - 1)); ++pr) {
+					const bool paired = (lc.paired >> pr) & 1u;
+					if (p.ablate & ABLATE_GATHER) {
+						vals[2 * pr] = lc.idx[2 * pr];
+						vals[2 * pr + 1] = lc.idx[2 * pr + 1];
+					} else {
+						gather_pair_f16x2(ltab, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(p.ablate & ABLATE_PAIRING), vals[2 * pr], vals[2 * pr + 1]);
+					}
+				}
+				__half2 result = __float2half2_rn(0.0f);
+#pragma unroll
+				for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+					// fma((T)weight, grid_val, result) with T = __half -> __hfma2 (grid.h:162, vec.h:372-378)
+					result = __hfma2(__float2half2_rn(lc.w[idx]), *reinterpret_cast<const __half2*>(&vals[idx]), result);
+				}
+				const uint32_t feat = level * F;
+				asm volatile("st.shared.b32 [%0], %1;" ::"r"(enc_tile + sw128(row, feat >> 3) + (feat & 7u) * 2u), "r"(*reinterpret_cast<uint32_t*>(&result)) : "memory");
+				if (p.dbg_enc) *reinterpret_cast<uint32_t*>(p.dbg_enc + (size_t)os_cur * 64 + feat) = *reinterpret_cast<uint32_t*>(&result);
+			}
+			fence_proxy_async_smem();  // the tile is read by tcgen05.mma (async proxy)
+			__syncwarp();
+			if ((tid & 31u) == 0) mbar_arrive(bar_enc_full + 8 * g);
+
+			// ---- scatter the previous tile of this sub-group (k-2) while the MLP group chews on tile k-1 / k
+			if (TRAIN && j >= 1) {
+				mbar_wait(bar_park_full + 8 * g, (j - 1) & 1u);
+				scatter_prev();
+				__syncwarp();
+				if ((tid & 31u) == 0) mbar_arrive(bar_park_free + 8 * g);
+			}
+#pragma unroll
+			for (uint32_t d = 0; d < D; ++d) x_prev[d] = x_cur[d];
+		}
+		if (TRAIN && j >= 1) {  // drain: the last tile of this sub-group
+			mbar_wait(bar_park_full + 8 * g, (j - 1) & 1u);
+			scatter_prev();
+		}
+	} else {
+		// =========================================================================================== MLP group
+		const uint32_t row = tid;  // 0..127
+		const uint32_t lane_field = (warp * 32u) << 16;
+		const uint32_t tmem_acc = tmem_base;
+		uint32_t phase = 0;
+		float loss_acc = 0.0f;
+		bool dw_started = false;
+
+		constexpr uint32_t IDESC_FWD_N64 = umma_idesc_f16(128, 64, 0, 0);
+		constexpr uint32_t IDESC_FWD_N16 = umma_idesc_f16(128, 16, 0, 0);
+		constexpr uint32_t IDESC_DGRAD = umma_idesc_f16(128, 64, 0, 1);
+		constexpr uint32_t IDESC_WGRAD = umma_idesc_f16(64, 64, 1, 1);
+		auto kmaj = [](uint32_t tile, uint32_t jj) { return umma_desc_sw128(tile + jj * 32u, 16u, 1024u); };
+		auto mnmaj = [](uint32_t tile, uint32_t jj) { return umma_desc_sw128(tile + jj * 2048u, TILE_BYTES, 1024u); };
+		auto stage_sync = [&]() {
+			tmem_ld_wait();
+			tc_fence_before_sync();
+			fence_proxy_async_smem();
+			named_bar_sync(1, WS_MLP_THREADS);
+		};
+		auto wait_mma = [&]() {
+			mbar_wait(bar_mma, phase);
+			phase ^= 1u;
+			tc_fence_after_sync();
+		};
+
+		const uint32_t n_batches = TRAIN ? 2 * NH + 2 : NH + 1;
+		uint32_t k = 0;
+		for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+			const uint32_t g = k & 1u, j = k >> 1;
+			const uint32_t enc_cur = s_enc + g * TILE_BYTES;
+			uint32_t osample = tile * TILE_M + row;
+			if (p.perm) osample = __ldg(p.perm + osample);
+			mbar_wait(bar_enc_full + 8 * g, j & 1u);
+
+#pragma unroll 1
+			for (uint32_t b = 0; b < n_batches; ++b) {
+				stage_sync();
+				if (tid == 0) {
+					tc_fence_after_sync();
+					if (b < NH) {
+						const uint32_t a_tile = b == 0 ? enc_cur : s_h0 + (b - 1) * TILE_BYTES;
+						const uint32_t b_tile = s_w0 + b * (WIDTH * 128);
+						const uint32_t ksteps = b == 0 ? in_w / 16 : WIDTH / 16;
+						for (uint32_t jj = 0; jj < ksteps; ++jj) umma_f16_ss(tmem_acc, kmaj(a_tile, jj), kmaj(b_tile, jj), IDESC_FWD_N64, jj > 0);
+						if (!TRAIN && b == 0) umma_commit(bar_enc_free + 8 * g);  // inference: L0 is the only reader of enc
+					} else if (b == NH) {
+						const uint32_t a_tile = s_h0 + (NH - 1) * TILE_BYTES;
+						for (uint32_t jj = 0; jj < WIDTH / 16; ++jj) umma_f16_ss(tmem_acc, kmaj(a_tile, jj), kmaj(s_wout, jj), IDESC_FWD_N16, jj > 0);
+					} else if (b <= 2 * NH) {
+						const uint32_t l = 2 * NH + 1 - b;
+						const uint32_t h_prev = s_h0 + (l - 1) * TILE_BYTES;
+						if (l == NH) {
+							umma_f16_ss(tmem_acc, kmaj(s_dy, 0), mnmaj(s_wout, 0), IDESC_DGRAD, 0);
+							const uint32_t dw = tmem_base + 64u * (1 + NH);
+							for (uint32_t jj = 0; jj < TILE_M / 16; ++jj) umma_f16_ss(dw, mnmaj(h_prev, jj), mnmaj(s_dy, jj), IDESC_WGRAD, dw_started || jj > 0);
+						} else {
+							const uint32_t g_tile = s_h0 + l * TILE_BYTES;
+							const uint32_t w_tile = s_w0 + l * (WIDTH * 128);
+							for (uint32_t jj = 0; jj < WIDTH / 16; ++jj) umma_f16_ss(tmem_acc, kmaj(g_tile, jj), mnmaj(w_tile, jj), IDESC_DGRAD, jj > 0);
+							const uint32_t dw = tmem_base + 64u * (1 + l);
+							for (uint32_t jj = 0; jj < TILE_M / 16; ++jj) umma_f16_ss(dw, mnmaj(g_tile, jj), mnmaj(h_prev, jj), IDESC_WGRAD, dw_started || jj > 0);
+						}
+					} else {
+						const uint32_t g_tile = s_h0;
+						for (uint32_t jj = 0; jj < WIDTH / 16; ++jj) umma_f16_ss(tmem_acc, kmaj(g_tile, jj), mnmaj(s_w0, jj), IDESC_DGRAD, jj > 0);
+						const uint32_t dw = tmem_base + 64u;
+						for (uint32_t jj = 0; jj < TILE_M / 16; ++jj) umma_f16_ss(dw, mnmaj(g_tile, jj), mnmaj(enc_cur, jj), IDESC_WGRAD, dw_started || jj > 0);
+						umma_commit(bar_enc_free + 8 * g);  // last reader of enc[g]: release it to the memory group
+					}
+					umma_commit(bar_mma);
+				}
+				__syncwarp();
+				wait_mma();
+
+				// ---- epilogue of batch b: this thread owns row `row`, all 64 accumulator columns (two passes of 32)
+				if (b < NH) {
+					const uint32_t h_tile = s_h0 + b * TILE_BYTES;
+#pragma unroll
+					for (uint32_t half = 0; half < 2; ++half) {
+						uint32_t r[32];
+						tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
+						tmem_ld_wait();
+#pragma unroll
+						for (uint32_t c = 0; c < 4; ++c) {
+							const uint32_t v0 = relu_pack(r[c * 8 + 0], r[c * 8 + 1]), v1 = relu_pack(r[c * 8 + 2], r[c * 8 + 3]);
+							const uint32_t v2 = relu_pack(r[c * 8 + 4], r[c * 8 + 5]), v3 = relu_pack(r[c * 8 + 6], r[c * 8 + 7]);
+							st_shared_v4(h_tile + sw128(row, half * 4 + c), v0, v1, v2, v3);
+							if (p.dbg_hidden) *reinterpret_cast<uint4*>(p.dbg_hidden + ((size_t)b * p.batch_size + osample) * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
+						}
+					}
+				} else if (b == NH) {
+					uint32_t r[16];
+					tmem_ld_32x32b_x16(tmem_acc + lane_field, r);
+					tmem_ld_wait();
+					__half y16[16];
+#pragma unroll
+					for (uint32_t q = 0; q < 16; ++q) y16[q] = __float2half_rn(__uint_as_float(r[q]));
+					if (p.out_fp16) {
+						uint4* dst = reinterpret_cast<uint4*>(p.out_fp16 + (size_t)osample * 16);
+						dst[0] = *reinterpret_cast<uint4*>(&y16[0]);
+						dst[1] = *reinterpret_cast<uint4*>(&y16[8]);
+					}
+					if (p.out_fp32) {
+						for (uint32_t q = 0; q < p.n_out; ++q) p.out_fp32[(size_t)osample * p.n_out + q] = __half2float(y16[q]);
+					}
+					if (TRAIN) {
+						// relative_l2_loss / l2_loss (losses/relative_l2.h:56-75, l2.h:56-74); pad lanes give 0.
+						__half dy[16];
+						const float n_total = (float)(p.loss_batch_size * p.n_out);
+#pragma unroll
+						for (uint32_t q = 0; q < 16; ++q) {
+							float gq = 0.0f;
+							if (q < p.n_out) {
+								const float pred = __half2float(y16[q]);
+								const float diff = pred - __ldg(p.targets + (size_t)osample * p.n_out + q);
+								float value, grad;
+								if (p.loss_type == LOSS_RELATIVE_L2) {
+									const float psq = pred * pred + 0.01f;
+									value = diff * diff / psq / n_total;
+									grad = 2.0f * diff / psq;
+								} else {
+									value = diff * diff / n_total;
+									grad = 2.0f * diff;
+								}
+								gq = p.loss_scale * grad / n_total;
+								loss_acc += value;
+								if (p.loss_values) p.loss_values[(size_t)osample * p.n_out + q] = value;
+							}
+							dy[q] = __float2half_rn(gq);
+						}
+						const uint4 lo = *reinterpret_cast<uint4*>(&dy[0]), hi = *reinterpret_cast<uint4*>(&dy[8]);
+						st_shared_v4(s_dy + sw128(row, 0), lo.x, lo.y, lo.z, lo.w);
+						st_shared_v4(s_dy + sw128(row, 1), hi.x, hi.y, hi.z, hi.w);
+						if (p.dbg_dy) {
+							uint4* dst = reinterpret_cast<uint4*>(p.dbg_dy + (size_t)osample * 16);
+							dst[0] = lo;
+							dst[1] = hi;
+						}
+					}
+				} else if (b <= 2 * NH) {
+					// g overwrites h in place (see fused_step.cu)
+					const uint32_t l = 2 * NH + 1 - b;
+					const uint32_t h_tile = s_h0 + (l - 1) * TILE_BYTES;
+#pragma unroll
+					for (uint32_t half = 0; half < 2; ++half) {
+						uint32_t r[32];
+						tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
+						tmem_ld_wait();
+#pragma unroll
+						for (uint32_t c = 0; c < 4; ++c) {
+							uint32_t f0, f1, f2, f3;
+							ld_shared_v4(h_tile + sw128(row, half * 4 + c), f0, f1, f2, f3);
+							const uint32_t v0 = relu_bwd_pack(r[c * 8 + 0], r[c * 8 + 1], f0), v1 = relu_bwd_pack(r[c * 8 + 2], r[c * 8 + 3], f1);
+							const uint32_t v2 = relu_bwd_pack(r[c * 8 + 4], r[c * 8 + 5], f2), v3 = relu_bwd_pack(r[c * 8 + 6], r[c * 8 + 7], f3);
+							st_shared_v4(h_tile + sw128(row, half * 4 + c), v0, v1, v2, v3);
+							if (p.dbg_grad_hidden) *reinterpret_cast<uint4*>(p.dbg_grad_hidden + ((size_t)(l - 1) * p.batch_size + osample) * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
+						}
+					}
+				} else {
+					// dL/d(encoded): round once to fp16 (fully_fused_mlp.cu:835) and park the row for the memory group
+					dw_started = true;
+					const uint32_t park_tile = s_park + g * TILE_BYTES;
+					if (j >= 1) mbar_wait(bar_park_free + 8 * g, (j - 1) & 1u);  // scatter of tile k-2 has consumed park[g]
+#pragma unroll
+					for (uint32_t half = 0; half < 2; ++half) {
+						uint32_t r[32];
+						tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
+						tmem_ld_wait();
+#pragma unroll
+						for (uint32_t c = 0; c < 4; ++c) {
+							const uint32_t v0 = pack_half2(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1]));
+							const uint32_t v1 = pack_half2(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3]));
+							const uint32_t v2 = pack_half2(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5]));
+							const uint32_t v3 = pack_half2(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7]));
+							st_shared_v4(park_tile + sw128(row, half * 4 + c), v0, v1, v2, v3);
+							if (p.dbg_denc) *reinterpret_cast<uint4*>(p.dbg_denc + (size_t)osample * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
+						}
+					}
+					__syncwarp();
+					if ((tid & 31u) == 0) mbar_arrive(bar_park_full + 8 * g);
+				}
+			}
+		}
+
+		// ---- flush the weight-gradient accumulators and the loss
+		if (TRAIN) {
+			tmem_ld_wait();
+			tc_fence_before_sync();
+			named_bar_sync(1, WS_MLP_THREADS);
+			tc_fence_after_sync();
+			if (dw_started) {
+				// M = 64 accumulators: row m lives in TMEM lane (m % 16) + 32 * (m / 16) -> lanes 0..15 of each lane quadrant
+				const uint32_t lane = tid & 31u;
+				const uint32_t m = warp * 16 + lane;
+				for (uint32_t l = 0; l <= NH; ++l) {
+					const uint32_t dw = tmem_base + 64u * (1 + l) + lane_field;
+#pragma unroll
+					for (uint32_t half = 0; half < 2; ++half) {
+						uint32_t r[32];
+						tmem_ld_32x32b_x32(dw + half * 32, r);
+						tmem_ld_wait();
+						if (lane < 16) {
+							if (l == 0) {
+								float* dst = p.dw_accum + m * in_w;
+#pragma unroll
+								for (uint32_t q = 0; q < 32; q += 4) {
+									const uint32_t n = half * 32 + q;
+									if (n < in_w) red_add_v4_f32(dst + n, __uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
+								}
+							} else if (l < NH) {
+								float* dst = p.dw_accum + WIDTH * in_w + (l - 1) * WIDTH * WIDTH + m * WIDTH + half * 32;
+#pragma unroll
+								for (uint32_t q = 0; q < 32; q += 4) red_add_v4_f32(dst + q, __uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
+							} else if (half == 0) {
+								float* dst = p.dw_accum + WIDTH * in_w + (NH - 1) * WIDTH * WIDTH;
+#pragma unroll
+								for (uint32_t n = 0; n < 16; ++n) red_add_f32(dst + n * WIDTH + m, __uint_as_float(r[n]));
+							}
+						}
+					}
+				}
+			}
+#pragma unroll
+			for (uint32_t o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xFFFFFFFFu, loss_acc, o);
+			if ((tid & 31u) == 0 && p.loss_sum) atomicAdd(p.loss_sum, loss_acc);
+		}
+		tmem_ld_wait();
+		tc_fence_before_sync();
+	}
+
+	__syncthreads();
+	if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+size_t fused_ws_smem_bytes(uint32_t n_hidden_layers, bool train) {
+	const size_t tiles = 2 + n_hidden_layers + (train ? 3 : 0);
+	return tiles * TILE_BYTES + n_hidden_layers * (WIDTH * 128) + 16 * 128 + 96 + MAX_LEVELS * sizeof(LevelInfo) + 1024 /* alignment slack */;
+}
+
+template <uint32_t D, bool TRAIN>
+static cudaError_t launch_ws_impl(const FusedStepParams& p, uint32_t n_ctas, cudaStream_t stream) {
+	auto kernel = fused_ws_kernel<D, 2, TRAIN>;
+	const size_t smem = fused_ws_smem_bytes(p.n_hidden_layers, TRAIN);
+	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (err != cudaSuccess) return err;
+	kernel<<<n_ctas, WS_THREADS, smem, stream>>>(p);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_fused_ws(const FusedStepParams& p, uint32_t n_pos_dims, bool train, uint32_t n_ctas, cudaStream_t stream) {
+	if (n_pos_dims == 3) return train ? launch_ws_impl<3, true>(p, n_ctas, stream) : launch_ws_impl<3, false>(p, n_ctas, stream);
+	if (n_pos_dims == 2) return train ? launch_ws_impl<2, true>(p, n_ctas, stream) : launch_ws_impl<2, false>(p, n_ctas, stream);
+	return cudaErrorInvalidValue;
+}
+
+}  // namespace tcnnb

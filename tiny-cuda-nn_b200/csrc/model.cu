@@ -277,6 +277,7 @@ struct Model {
 
 	// spatial binning scratch (binning.cu): sorted copies of the batch + permutation
 	bool binning = true;  // TCNNB_BINNING=0 disables
+	bool warp_specialized = false;  // TCNNB_KERNEL=ws selects fused_ws.cu, =sync fused_step.cu
 	DeviceBuffer<uint32_t> bin_keys, bin_hist, bin_perm;
 
 	// host staging for the *_host entry points
@@ -351,6 +352,7 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 	m.n_sms = prop.multiProcessorCount;
 	if (const char* e = std::getenv("TCNNB_ABLATE")) m.ablate = (uint32_t)std::atoi(e);
 	if (const char* e = std::getenv("TCNNB_BINNING")) m.binning = std::atoi(e) != 0;
+	if (const char* e = std::getenv("TCNNB_KERNEL")) m.warp_specialized = std::string(e) == "ws";
 	m.n_in = n_in;
 	m.n_out = n_out;
 
@@ -563,7 +565,11 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
 		p.perm = m.bin_perm.ptr;
 	}
 	m.prof_mark(stream);
-	TCNNB_CUDA_CHECK(launch_fused_step(p, m.grid.n_pos_dims, true, fused_grid_size(m, batch), stream));
+	if (m.warp_specialized && m.mlp.n_hidden_layers <= 4) {
+		TCNNB_CUDA_CHECK(launch_fused_ws(p, m.grid.n_pos_dims, true, std::min(batch / TILE_M, (uint32_t)m.n_sms), stream));
+	} else {
+		TCNNB_CUDA_CHECK(launch_fused_step(p, m.grid.n_pos_dims, true, fused_grid_size(m, batch), stream));
+	}
 	++g_kernel_launches;
 	m.prof_mark(stream);
 	m.mlp_grads_in_accum = true;
@@ -702,6 +708,7 @@ uint32_t tcnnb_encoded_width(const tcnnb_model* m) { return m->impl.grid.padded_
 float* tcnnb_params_full_precision(tcnnb_model* m) { return m->impl.params_fp32; }
 void* tcnnb_params(tcnnb_model* m) { return m->impl.params_fp16; }
 float* tcnnb_mlp_gradient_accumulator(tcnnb_model* m) { return m->impl.dw_accum.ptr; }
+void* tcnnb_grid_gradients(tcnnb_model* m) { return m->impl.grads_fp16 + m->impl.mlp.n_params; }
 
 void* tcnnb_param_gradients(tcnnb_model* m) {
 	// The MLP part is materialised as fp16 on demand (the fused kernel accumulates it in fp32).

@@ -58,6 +58,7 @@ ABI = [
     ("tcnnb_training_step_shard", _int, [_vp, _vp, _u32, _u32, _vp, _vp, _int]),
     ("tcnnb_optimizer_step", _int, [_vp, _vp]),
     ("tcnnb_mlp_gradient_accumulator", _vp, [_vp]),
+    ("tcnnb_grid_gradients", _vp, [_vp]),
     ("tcnnb_loss", _int, [_vp, _vp, _f32p]),
     ("tcnnb_inference", _int, [_vp, _vp, _u32, _vp, _vp]),
     ("tcnnb_training_step_host", _int, [_vp, _u32, _vp, _vp, _f32p]),
@@ -205,8 +206,9 @@ class _Trainer:
         if not hasattr(self, "_grad_bufs"):
             import torch
 
-            ptr = load().tcnnb_param_gradients(self._m._h)
-            self._grad_bufs = [self._view(ptr + 2 * self._m.n_mlp_params, self._m.n_params - self._m.n_mlp_params, torch.float16), self.mlp_gradient_accumulator()]
+            # NOT tcnnb_param_gradients(): that call materialises the fp16 MLP gradients and re-arms the fp32 accumulator
+            ptr = load().tcnnb_grid_gradients(self._m._h)
+            self._grad_bufs = [self._view(ptr, self._m.n_params - self._m.n_mlp_params, torch.float16), self.mlp_gradient_accumulator()]
         return self._grad_bufs
 
     def device(self):
