@@ -277,7 +277,7 @@ struct Model {
 
 	// spatial binning scratch (binning.cu): sorted copies of the batch + permutation
 	bool binning = true;  // TCNNB_BINNING=0 disables
-	bool warp_specialized = false;  // TCNNB_KERNEL=ws selects fused_ws.cu, =sync fused_step.cu
+	bool warp_specialized = true;   // fused_ws.cu by default; TCNNB_KERNEL=sync selects the bulk-synchronous fused_step.cu
 	DeviceBuffer<uint32_t> bin_keys, bin_hist, bin_perm;
 
 	// host staging for the *_host entry points
