@@ -50,7 +50,10 @@ __global__ void bin_count_kernel(uint32_t n, const float* __restrict__ pos, uint
 // The counters are staged through shared memory with coalesced accesses (all loads of a thread are independent), each
 // thread scans a contiguous run of the staged copy, and the 1024 run totals are combined with shuffles.
 // The counters are re-armed to zero for the next step, so no memset is needed per step.
-constexpr uint32_t SCAN_CHUNK = 16384;  // bins staged per pass (64 KB of shared memory)
+constexpr uint32_t SCAN_CHUNK = 16384;  // bins staged per pass (66 KB of shared memory incl. padding)
+// one padding word every 32: thread t's contiguous run (stride 16 words) then falls into distinct banks across a warp
+__device__ __forceinline__ uint32_t scan_pad(uint32_t i) { return i + (i >> 5); }
+constexpr uint32_t SCAN_SMEM_WORDS = SCAN_CHUNK + SCAN_CHUNK / 32;
 
 __global__ void __launch_bounds__(1024) bin_scan_kernel(uint32_t n_bins, uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor) {
 	extern __shared__ uint32_t staged[];
@@ -71,7 +74,7 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(uint32_t n_bins, uint32_
 			for (uint32_t j = 0; j < SCAN_CHUNK / 1024; ++j) {
 				const uint32_t i = threadIdx.x + j * 1024;
 				if (i < n) {
-					staged[i] = v[j];
+					staged[scan_pad(i)] = v[j];
 					hist[base + i] = 0;
 				}
 			}
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(uint32_t n_bins, uint32_
 		const uint32_t per = (n + 1023u) / 1024u;
 		const uint32_t begin = min(n, threadIdx.x * per), end = min(n, begin + per);
 		uint32_t total = 0;
-		for (uint32_t i = begin; i < end; ++i) total += staged[i];
+		for (uint32_t i = begin; i < end; ++i) total += staged[scan_pad(i)];
 		uint32_t incl = total;
 #pragma unroll
 		for (uint32_t o = 1; o < 32; o <<= 1) {
@@ -102,12 +105,12 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(uint32_t n_bins, uint32_
 		const uint32_t c = carry;
 		uint32_t run = c + ((threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0u) + incl - total;
 		for (uint32_t i = begin; i < end; ++i) {
-			const uint32_t v = staged[i];
-			staged[i] = run;
+			const uint32_t v = staged[scan_pad(i)];
+			staged[scan_pad(i)] = run;
 			run += v;
 		}
 		__syncthreads();
-		for (uint32_t i = threadIdx.x; i < n; i += 1024) cursor[base + i] = staged[i];
+		for (uint32_t i = threadIdx.x; i < n; i += 1024) cursor[base + i] = staged[scan_pad(i)];
 		if (threadIdx.x == 1023) carry = c + warp_sums[31];
 		__syncthreads();
 	}
@@ -142,7 +145,7 @@ cudaError_t launch_binning(cudaStream_t stream, uint32_t n_pos_dims, uint32_t n,
 	const uint32_t blocks = (n + 255) / 256;
 	static bool attr_set = false;
 	if (!attr_set) {
-		cudaError_t err = cudaFuncSetAttribute(bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SCAN_CHUNK * sizeof(uint32_t)));
+		cudaError_t err = cudaFuncSetAttribute(bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SCAN_SMEM_WORDS * sizeof(uint32_t)));
 		if (err != cudaSuccess) return err;
 		attr_set = true;
 	}
@@ -153,7 +156,7 @@ cudaError_t launch_binning(cudaStream_t stream, uint32_t n_pos_dims, uint32_t n,
 	} else {
 		return cudaErrorInvalidValue;
 	}
-	bin_scan_kernel<<<1, 1024, SCAN_CHUNK * sizeof(uint32_t), stream>>>(n_bins, hist, cursor);
+	bin_scan_kernel<<<1, 1024, SCAN_SMEM_WORDS * sizeof(uint32_t), stream>>>(n_bins, hist, cursor);
 	bin_scatter_kernel<<<blocks, 256, 0, stream>>>(n, keys, cursor, perm);
 	return cudaGetLastError();
 }

@@ -181,11 +181,11 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 #pragma unroll
 			for (uint32_t pr = 0; pr < (1u << (D - 1)); ++pr) {
 				const bool paired = (lc.paired >> pr) & 1u;
-				if (p.ablate & ABLATE_GATHER) {
+				if (TCNNB_ABLATE(ABLATE_GATHER)) {
 					f.vals[2 * pr] = lc.idx[2 * pr];
 					f.vals[2 * pr + 1] = lc.idx[2 * pr + 1];
 				} else {
-					gather_pair_f16x2(lt, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(p.ablate & ABLATE_PAIRING), f.vals[2 * pr], f.vals[2 * pr + 1]);
+					gather_pair_f16x2(lt, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(TCNNB_ABLATE(ABLATE_PAIRING)), f.vals[2 * pr], f.vals[2 * pr + 1]);
 				}
 			}
 #pragma unroll
@@ -237,8 +237,8 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 				const __half2 a0 = __hmul2(__float2half2_rn(lc.w[2 * pr]), grad);
 				const __half2 a1 = __hmul2(__float2half2_rn(lc.w[2 * pr + 1]), grad);
 				const bool paired = (lc.paired >> pr) & 1u;
-				if (!(p.ablate & ABLATE_SCATTER)) {
-					scatter_pair_f16x2(lt, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(p.ablate & ABLATE_PAIRING), *reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
+				if (!(TCNNB_ABLATE(ABLATE_SCATTER))) {
+					scatter_pair_f16x2(lt, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(TCNNB_ABLATE(ABLATE_PAIRING)), *reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
 				}
 			}
 		}

@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 					const __half2 a0 = __hmul2(__float2half2_rn(lc.w[2 * pr]), grad);
 					const __half2 a1 = __hmul2(__float2half2_rn(lc.w[2 * pr + 1]), grad);
 					const bool paired = (lc.paired >> pr) & 1u;
-					if (!(p.ablate & ABLATE_SCATTER)) {
-						scatter_pair_f16x2(ltab, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(p.ablate & ABLATE_PAIRING), *reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
+					if (!(TCNNB_ABLATE(ABLATE_SCATTER))) {
+						scatter_pair_f16x2(ltab, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(TCNNB_ABLATE(ABLATE_PAIRING)), *reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
 					}
 				}
 			}
@@ -192,32 +192,54 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 				const uint32_t chunk = c < n_chunks / 2 ? hsel * (n_chunks / 2) + c : n_chunks + hsel * ((8 - n_chunks) / 2) + (c - n_chunks / 2);
 				st_shared_v4(enc_tile + sw128(row, chunk), 0, 0, 0, 0);
 			}
-#pragma unroll 1
-			for (uint32_t level = level_begin; level < level_end; ++level) {
-				const LevelInfo lv = load_level(level);
-				LevelCorners<D> lc;
-				level_corners<D>(lv, x_cur, p.grid.interpolation, lc);
-				const uint32_t* __restrict__ ltab = reinterpret_cast<const uint32_t*>(table + (size_t)lv.offset * F);
-				uint32_t vals[1u << D];
+			{
+				// Two levels in flight: the loads of level l+1 are issued before the values of level l are consumed.
+				struct InFlight {
+					uint32_t vals[1u << D];
+					uint32_t w16[1u << D];  // (half)weight duplicated into both halves
+				};
+				auto issue = [&](uint32_t level, InFlight& f) {
+					const LevelInfo lv = load_level(level);
+					LevelCorners<D> lc;
+					level_corners<D>(lv, x_cur, p.grid.interpolation, lc);
+					const uint32_t* __restrict__ ltab = reinterpret_cast<const uint32_t*>(table + (size_t)lv.offset * F);
 #pragma unroll
-				for (uint32_t pr = 0; pr < (1u << (D - 1)); ++pr) {
-					const bool paired = (lc.paired >> pr) & 1u;
-					if (p.ablate & ABLATE_GATHER) {
-						vals[2 * pr] = lc.idx[2 * pr];
-						vals[2 * pr + 1] = lc.idx[2 * pr + 1];
-					} else {
-						gather_pair_f16x2(ltab, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(p.ablate & ABLATE_PAIRING), vals[2 * pr], vals[2 * pr + 1]);
+					for (uint32_t pr = 0; pr < (1u << (D - 1)); ++pr) {
+						const bool paired = (lc.paired >> pr) & 1u;
+						if (TCNNB_ABLATE(ABLATE_GATHER)) {
+							f.vals[2 * pr] = lc.idx[2 * pr];
+							f.vals[2 * pr + 1] = lc.idx[2 * pr + 1];
+						} else {
+							gather_pair_f16x2(ltab, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(TCNNB_ABLATE(ABLATE_PAIRING)), f.vals[2 * pr], f.vals[2 * pr + 1]);
+						}
+					}
+#pragma unroll
+					for (uint32_t i = 0; i < (1u << D); ++i) {
+						const __half2 h = __float2half2_rn(lc.w[i]);
+						f.w16[i] = *reinterpret_cast<const uint32_t*>(&h);
+					}
+				};
+				auto consume = [&](uint32_t level, const InFlight& f) {
+					__half2 result = __float2half2_rn(0.0f);
+#pragma unroll
+					for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+						// fma((T)weight, grid_val, result) with T = __half -> __hfma2 (grid.h:162, vec.h:372-378)
+						result = __hfma2(*reinterpret_cast<const __half2*>(&f.w16[idx]), *reinterpret_cast<const __half2*>(&f.vals[idx]), result);
+					}
+					const uint32_t feat = level * F;
+					asm volatile("st.shared.b32 [%0], %1;" ::"r"(enc_tile + sw128(row, feat >> 3) + (feat & 7u) * 2u), "r"(*reinterpret_cast<uint32_t*>(&result)) : "memory");
+					if (p.dbg_enc) *reinterpret_cast<uint32_t*>(p.dbg_enc + (size_t)os_cur * 64 + feat) = *reinterpret_cast<uint32_t*>(&result);
+				};
+				if (level_begin < level_end) {
+					InFlight cur, nxt;
+					issue(level_begin, cur);
+#pragma unroll 1
+					for (uint32_t level = level_begin; level < level_end; ++level) {
+						if (level + 1 < level_end) issue(level + 1, nxt);
+						consume(level, cur);
+						cur = nxt;
 					}
 				}
-				__half2 result = __float2half2_rn(0.0f);
-#pragma unroll
-				for (uint32_t idx = 0; idx < (1u << D); ++idx) {
-					// fma((T)weight, grid_val, result) with T = __half -> __hfma2 (grid.h:162, vec.h:372-378)
-					result = __hfma2(__float2half2_rn(lc.w[idx]), *reinterpret_cast<const __half2*>(&vals[idx]), result);
-				}
-				const uint32_t feat = level * F;
-				asm volatile("st.shared.b32 [%0], %1;" ::"r"(enc_tile + sw128(row, feat >> 3) + (feat & 7u) * 2u), "r"(*reinterpret_cast<uint32_t*>(&result)) : "memory");
-				if (p.dbg_enc) *reinterpret_cast<uint32_t*>(p.dbg_enc + (size_t)os_cur * 64 + feat) = *reinterpret_cast<uint32_t*>(&result);
 			}
 			fence_proxy_async_smem();  // the tile is read by tcgen05.mma (async proxy)
 			__syncwarp();

@@ -225,40 +225,29 @@ __device__ __forceinline__ void level_corners(const LevelInfo& lv, const float (
 	}
 }
 
-// Gather the two fp16x2 entries of a corner pair: one 64-bit load when they share an aligned slot, else two 32-bit loads.
+// Gather the two fp16x2 entries of a corner pair. Every lane fetches the aligned 8-byte slot that holds entry idx0 (one
+// LDG.64); lanes whose partner entry does not live in that slot fetch it with a second, predicated 4-byte load.
 __device__ __forceinline__ void gather_pair_f16x2(const uint32_t* __restrict__ table, uint32_t idx0, uint32_t idx1, bool paired, uint32_t& v0, uint32_t& v1) {
-	const uint32_t* a0 = table + (paired ? (idx0 & ~1u) : idx0);
-	const uint32_t* a1 = table + idx1;
-	uint32_t lo, hi;
-	asm("{\n"
-	    ".reg .pred p;\n"
-	    "setp.ne.u32 p, %4, 0;\n"
-	    "@p ld.global.nc.v2.u32 {%0, %1}, [%2];\n"
-	    "@!p ld.global.nc.u32 %0, [%2];\n"
-	    "@!p ld.global.nc.u32 %1, [%3];\n"
-	    "}\n"
-	    : "=r"(lo), "=r"(hi)
-	    : "l"(a0), "l"(a1), "r"((uint32_t)paired));
-	const bool swap = paired && (idx0 & 1u);
-	v0 = swap ? hi : lo;
-	v1 = swap ? lo : hi;
+	const uint2 slot = __ldg(reinterpret_cast<const uint2*>(table + (idx0 & ~1u)));
+	const bool odd = idx0 & 1u;
+	v0 = odd ? slot.y : slot.x;
+	// The partner entry is fetched unconditionally: for paired lanes it lies in the slot just requested (an L1 hit on
+	// the in-flight sector, no extra L2 traffic), and the straight-line form keeps the loop free of predicated loads.
+	const uint32_t far = __ldg(table + idx1);
+	v1 = paired ? (odd ? slot.x : slot.y) : far;
 }
 
-// Scatter-add two fp16x2 addends of a corner pair: one 64-bit vector reduction when paired, else two 32-bit reductions.
+// Scatter-add two fp16x2 addends of a corner pair: one 64-bit vector reduction when paired, else two 32-bit reductions
+// (red.global.add.noftz.f16x2 is what the reference's atomic_add_gmem(__half2) lowers to, vec.h:328-336).
 __device__ __forceinline__ void scatter_pair_f16x2(uint32_t* __restrict__ table, uint32_t idx0, uint32_t idx1, bool paired, uint32_t a0, uint32_t a1) {
-	uint32_t* p0 = table + (paired ? (idx0 & ~1u) : idx0);
-	uint32_t* p1 = table + idx1;
-	const bool swap = paired && (idx0 & 1u);
-	const uint32_t lo = swap ? a1 : a0;
-	const uint32_t hi = swap ? a0 : a1;
-	asm volatile("{\n"
-	             ".reg .pred p;\n"
-	             "setp.ne.u32 p, %4, 0;\n"
-	             "@p red.relaxed.gpu.global.add.noftz.v2.f16x2 [%0], {%2, %3};\n"
-	             "@!p red.relaxed.gpu.global.add.noftz.f16x2 [%0], %2;\n"
-	             "@!p red.relaxed.gpu.global.add.noftz.f16x2 [%1], %3;\n"
-	             "}\n" ::"l"(p0), "l"(p1), "r"(lo), "r"(hi), "r"((uint32_t)paired)
-	             : "memory");
+	if (paired) {
+		const bool odd = idx0 & 1u;
+		const uint32_t lo = odd ? a1 : a0, hi = odd ? a0 : a1;
+		asm volatile("red.relaxed.gpu.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(table + (idx0 & ~1u)), "r"(lo), "r"(hi) : "memory");
+	} else {
+		asm volatile("red.relaxed.gpu.global.add.noftz.f16x2 [%0], %1;" ::"l"(table + idx0), "r"(a0) : "memory");
+		asm volatile("red.relaxed.gpu.global.add.noftz.f16x2 [%0], %1;" ::"l"(table + idx1), "r"(a1) : "memory");
+	}
 }
 
 }  // namespace tcnnb
