@@ -52,27 +52,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 	const uint32_t NH = p.n_hidden_layers;
 	const uint32_t in_w = p.grid.padded_width;
 
-	// ---- shared memory: [ enc_0 | enc_1 | h_0 .. h_{NH-1} | dy | park_0 | park_1 | W_0 .. W_{NH-1} | W_out ] barriers, level table
+	// ---- shared memory: [ enc_0 | enc_1 | h (2 chains x NH) | dy_0 | dy_1 | park_0 | park_1 | W_0 .. W_{NH-1} | W_out ] barriers, level table
 	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 	const uint32_t s_enc = smem_base;
-	const uint32_t s_h0 = s_enc + 2 * TILE_BYTES;
-	const uint32_t s_dy = s_h0 + NH * TILE_BYTES;
-	const uint32_t s_park = s_dy + (TRAIN ? TILE_BYTES : 0);
+	const uint32_t s_h0 = s_enc + 2 * TILE_BYTES;                    // [2 chains][NH]
+	const uint32_t s_dy = s_h0 + 2 * NH * TILE_BYTES;                // [2 chains]
+	const uint32_t s_park = s_dy + (TRAIN ? 2 * TILE_BYTES : 0);
 	const uint32_t s_w0 = s_park + (TRAIN ? 2 * TILE_BYTES : 0);
 	const uint32_t s_wout = s_w0 + NH * (WIDTH * 128);
-	const uint32_t s_bars = s_wout + 16 * 128;  // 9 mbarriers
-	const uint32_t bar_mma = s_bars;
-	const uint32_t bar_enc_full = s_bars + 8;    // [2]
-	const uint32_t bar_enc_free = s_bars + 24;   // [2]
-	const uint32_t bar_park_full = s_bars + 40;  // [2]
-	const uint32_t bar_park_free = s_bars + 56;  // [2]
-	const uint32_t s_tmem_slot = s_bars + 72;
-	const uint32_t s_levels = s_bars + 80;
+	const uint32_t s_bars = s_wout + 16 * 128;  // 10 mbarriers
+	const uint32_t bar_mma = s_bars;             // [2] one per MLP chain
+	const uint32_t bar_enc_full = s_bars + 16;   // [2]
+	const uint32_t bar_enc_free = s_bars + 32;   // [2]
+	const uint32_t bar_park_full = s_bars + 48;  // [2]
+	const uint32_t bar_park_free = s_bars + 64;  // [2]
+	const uint32_t s_tmem_slot = s_bars + 80;
+	const uint32_t s_levels = s_bars + 96;
 
-	const uint32_t tmem_cols = TRAIN ? ((NH + 2) * 64 <= 256 ? 256u : 512u) : 64u;
+	const uint32_t tmem_cols = TRAIN ? ((NH + 3) * 64 <= 256 ? 256u : 512u) : 128u;  // 2 activation accumulators + NH+1 wgrad accumulators
 	if (tid == 0) {
-		mbar_init(bar_mma, 1);
 		for (uint32_t g = 0; g < 2; ++g) {
+			mbar_init(bar_mma + 8 * g, 1);
 			mbar_init(bar_enc_full + 8 * g, WS_SUB_THREADS / 32);   // one arrival per memory warp
 			mbar_init(bar_enc_free + 8 * g, 1);                      // tcgen05.commit
 			mbar_init(bar_park_full + 8 * g, WS_MLP_THREADS / 32);  // one arrival per MLP warp
@@ -261,10 +261,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 		}
 	} else {
 		// =========================================================================================== MLP group
+		// Two tiles ("chains" c = 0, 1 <-> enc[c], park[c], their own activation tiles and TMEM accumulator) are in flight
+		// in these 128 threads: while the tensor core executes batch b of one chain, the threads run the epilogue of the
+		// other chain's batch. The per-batch latencies (barrier, MMA issue + execution, mbarrier wake-up) of one chain hide
+		// behind the epilogue work of the other.
 		const uint32_t row = tid;  // 0..127
 		const uint32_t lane_field = (warp * 32u) << 16;
-		const uint32_t tmem_acc = tmem_base;
-		uint32_t phase = 0;
+		uint32_t phase[2] = {0, 0};
 		float loss_acc = 0.0f;
 		bool dw_started = false;
 
@@ -274,175 +277,201 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 		constexpr uint32_t IDESC_WGRAD = umma_idesc_f16(64, 64, 1, 1);
 		auto kmaj = [](uint32_t tile, uint32_t jj) { return umma_desc_sw128(tile + jj * 32u, 16u, 1024u); };
 		auto mnmaj = [](uint32_t tile, uint32_t jj) { return umma_desc_sw128(tile + jj * 2048u, TILE_BYTES, 1024u); };
-		auto stage_sync = [&]() {
+		const uint32_t tmem_dw = tmem_base + 128u;  // wgrad accumulators follow the two activation accumulators
+		const uint32_t n_batches = TRAIN ? 2 * NH + 2 : NH + 1;
+
+		// All MLP threads: publish this thread's smem tile writes / TMEM reads, rendezvous, then thread 0 issues batch b of chain c.
+		auto sync_and_issue = [&](uint32_t c, uint32_t b, uint32_t j) {
 			tmem_ld_wait();
 			tc_fence_before_sync();
 			fence_proxy_async_smem();
 			named_bar_sync(1, WS_MLP_THREADS);
-		};
-		auto wait_mma = [&]() {
-			mbar_wait(bar_mma, phase);
-			phase ^= 1u;
-			tc_fence_after_sync();
-		};
-
-		const uint32_t n_batches = TRAIN ? 2 * NH + 2 : NH + 1;
-		uint32_t k = 0;
-		for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
-			const uint32_t g = k & 1u, j = k >> 1;
-			const uint32_t enc_cur = s_enc + g * TILE_BYTES;
-			uint32_t osample = tile * TILE_M + row;
-			if (p.perm) osample = __ldg(p.perm + osample);
-			mbar_wait(bar_enc_full + 8 * g, j & 1u);
-
-#pragma unroll 1
-			for (uint32_t b = 0; b < n_batches; ++b) {
-				stage_sync();
-				if (tid == 0) {
-					tc_fence_after_sync();
-					if (b < NH) {
-						const uint32_t a_tile = b == 0 ? enc_cur : s_h0 + (b - 1) * TILE_BYTES;
-						const uint32_t b_tile = s_w0 + b * (WIDTH * 128);
-						const uint32_t ksteps = b == 0 ? in_w / 16 : WIDTH / 16;
-						for (uint32_t jj = 0; jj < ksteps; ++jj) umma_f16_ss(tmem_acc, kmaj(a_tile, jj), kmaj(b_tile, jj), IDESC_FWD_N64, jj > 0);
-						if (!TRAIN && b == 0) umma_commit(bar_enc_free + 8 * g);  // inference: L0 is the only reader of enc
-					} else if (b == NH) {
-						const uint32_t a_tile = s_h0 + (NH - 1) * TILE_BYTES;
-						for (uint32_t jj = 0; jj < WIDTH / 16; ++jj) umma_f16_ss(tmem_acc, kmaj(a_tile, jj), kmaj(s_wout, jj), IDESC_FWD_N16, jj > 0);
-					} else if (b <= 2 * NH) {
-						const uint32_t l = 2 * NH + 1 - b;
-						const uint32_t h_prev = s_h0 + (l - 1) * TILE_BYTES;
-						if (l == NH) {
-							umma_f16_ss(tmem_acc, kmaj(s_dy, 0), mnmaj(s_wout, 0), IDESC_DGRAD, 0);
-							const uint32_t dw = tmem_base + 64u * (1 + NH);
-							for (uint32_t jj = 0; jj < TILE_M / 16; ++jj) umma_f16_ss(dw, mnmaj(h_prev, jj), mnmaj(s_dy, jj), IDESC_WGRAD, dw_started || jj > 0);
-						} else {
-							const uint32_t g_tile = s_h0 + l * TILE_BYTES;
-							const uint32_t w_tile = s_w0 + l * (WIDTH * 128);
-							for (uint32_t jj = 0; jj < WIDTH / 16; ++jj) umma_f16_ss(tmem_acc, kmaj(g_tile, jj), mnmaj(w_tile, jj), IDESC_DGRAD, jj > 0);
-							const uint32_t dw = tmem_base + 64u * (1 + l);
-							for (uint32_t jj = 0; jj < TILE_M / 16; ++jj) umma_f16_ss(dw, mnmaj(g_tile, jj), mnmaj(h_prev, jj), IDESC_WGRAD, dw_started || jj > 0);
-						}
-					} else {
-						const uint32_t g_tile = s_h0;
-						for (uint32_t jj = 0; jj < WIDTH / 16; ++jj) umma_f16_ss(tmem_acc, kmaj(g_tile, jj), mnmaj(s_w0, jj), IDESC_DGRAD, jj > 0);
-						const uint32_t dw = tmem_base + 64u;
-						for (uint32_t jj = 0; jj < TILE_M / 16; ++jj) umma_f16_ss(dw, mnmaj(g_tile, jj), mnmaj(enc_cur, jj), IDESC_WGRAD, dw_started || jj > 0);
-						umma_commit(bar_enc_free + 8 * g);  // last reader of enc[g]: release it to the memory group
-					}
-					umma_commit(bar_mma);
-				}
-				__syncwarp();
-				wait_mma();
-
-				// ---- epilogue of batch b: this thread owns row `row`, all 64 accumulator columns (two passes of 32)
+			if (tid == 0) {
+				tc_fence_after_sync();
+				const uint32_t acc = tmem_base + c * 64u;
+				const uint32_t enc_cur = s_enc + c * TILE_BYTES;
+				const uint32_t h0 = s_h0 + c * NH * TILE_BYTES;
+				const uint32_t dy = s_dy + c * TILE_BYTES;
+				const bool accumulate_dw = dw_started || c == 1;  // chain 0 of the first pair starts the wgrad accumulators
 				if (b < NH) {
-					const uint32_t h_tile = s_h0 + b * TILE_BYTES;
-#pragma unroll
-					for (uint32_t half = 0; half < 2; ++half) {
-						uint32_t r[32];
-						tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
-						tmem_ld_wait();
-#pragma unroll
-						for (uint32_t c = 0; c < 4; ++c) {
-							const uint32_t v0 = relu_pack(r[c * 8 + 0], r[c * 8 + 1]), v1 = relu_pack(r[c * 8 + 2], r[c * 8 + 3]);
-							const uint32_t v2 = relu_pack(r[c * 8 + 4], r[c * 8 + 5]), v3 = relu_pack(r[c * 8 + 6], r[c * 8 + 7]);
-							st_shared_v4(h_tile + sw128(row, half * 4 + c), v0, v1, v2, v3);
-							if (p.dbg_hidden) *reinterpret_cast<uint4*>(p.dbg_hidden + ((size_t)b * p.batch_size + osample) * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
-						}
-					}
+					const uint32_t a_tile = b == 0 ? enc_cur : h0 + (b - 1) * TILE_BYTES;
+					const uint32_t b_tile = s_w0 + b * (WIDTH * 128);
+					const uint32_t ksteps = b == 0 ? in_w / 16 : WIDTH / 16;
+					for (uint32_t jj = 0; jj < ksteps; ++jj) umma_f16_ss(acc, kmaj(a_tile, jj), kmaj(b_tile, jj), IDESC_FWD_N64, jj > 0);
+					if (!TRAIN && b == 0) umma_commit(bar_enc_free + 8 * c);  // inference: L0 is the only reader of enc
 				} else if (b == NH) {
-					uint32_t r[16];
-					tmem_ld_32x32b_x16(tmem_acc + lane_field, r);
-					tmem_ld_wait();
-					__half y16[16];
-#pragma unroll
-					for (uint32_t q = 0; q < 16; ++q) y16[q] = __float2half_rn(__uint_as_float(r[q]));
-					if (p.out_fp16) {
-						uint4* dst = reinterpret_cast<uint4*>(p.out_fp16 + (size_t)osample * 16);
-						dst[0] = *reinterpret_cast<uint4*>(&y16[0]);
-						dst[1] = *reinterpret_cast<uint4*>(&y16[8]);
-					}
-					if (p.out_fp32) {
-						for (uint32_t q = 0; q < p.n_out; ++q) p.out_fp32[(size_t)osample * p.n_out + q] = __half2float(y16[q]);
-					}
-					if (TRAIN) {
-						// relative_l2_loss / l2_loss (losses/relative_l2.h:56-75, l2.h:56-74); pad lanes give 0.
-						__half dy[16];
-						const float n_total = (float)(p.loss_batch_size * p.n_out);
-#pragma unroll
-						for (uint32_t q = 0; q < 16; ++q) {
-							float gq = 0.0f;
-							if (q < p.n_out) {
-								const float pred = __half2float(y16[q]);
-								const float diff = pred - __ldg(p.targets + (size_t)osample * p.n_out + q);
-								float value, grad;
-								if (p.loss_type == LOSS_RELATIVE_L2) {
-									const float psq = pred * pred + 0.01f;
-									value = diff * diff / psq / n_total;
-									grad = 2.0f * diff / psq;
-								} else {
-									value = diff * diff / n_total;
-									grad = 2.0f * diff;
-								}
-								gq = p.loss_scale * grad / n_total;
-								loss_acc += value;
-								if (p.loss_values) p.loss_values[(size_t)osample * p.n_out + q] = value;
-							}
-							dy[q] = __float2half_rn(gq);
-						}
-						const uint4 lo = *reinterpret_cast<uint4*>(&dy[0]), hi = *reinterpret_cast<uint4*>(&dy[8]);
-						st_shared_v4(s_dy + sw128(row, 0), lo.x, lo.y, lo.z, lo.w);
-						st_shared_v4(s_dy + sw128(row, 1), hi.x, hi.y, hi.z, hi.w);
-						if (p.dbg_dy) {
-							uint4* dst = reinterpret_cast<uint4*>(p.dbg_dy + (size_t)osample * 16);
-							dst[0] = lo;
-							dst[1] = hi;
-						}
-					}
+					const uint32_t a_tile = h0 + (NH - 1) * TILE_BYTES;
+					for (uint32_t jj = 0; jj < WIDTH / 16; ++jj) umma_f16_ss(acc, kmaj(a_tile, jj), kmaj(s_wout, jj), IDESC_FWD_N16, jj > 0);
 				} else if (b <= 2 * NH) {
-					// g overwrites h in place (see fused_step.cu)
+					// g_{NH-1} = (dy . W_out) * act'(h_{NH-1});  dW_out^T += h_{NH-1}^T . dy   (fully_fused_mlp.cu:192-240, :784-787)
+					// g_{l-1}  = (g_l . W_l)   * act'(h_{l-1});   dW_l     += g_l^T . h_{l-1}   (fully_fused_mlp.cu:248-250, :815-830)
 					const uint32_t l = 2 * NH + 1 - b;
-					const uint32_t h_tile = s_h0 + (l - 1) * TILE_BYTES;
-#pragma unroll
-					for (uint32_t half = 0; half < 2; ++half) {
-						uint32_t r[32];
-						tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
-						tmem_ld_wait();
-#pragma unroll
-						for (uint32_t c = 0; c < 4; ++c) {
-							uint32_t f0, f1, f2, f3;
-							ld_shared_v4(h_tile + sw128(row, half * 4 + c), f0, f1, f2, f3);
-							const uint32_t v0 = relu_bwd_pack(r[c * 8 + 0], r[c * 8 + 1], f0), v1 = relu_bwd_pack(r[c * 8 + 2], r[c * 8 + 3], f1);
-							const uint32_t v2 = relu_bwd_pack(r[c * 8 + 4], r[c * 8 + 5], f2), v3 = relu_bwd_pack(r[c * 8 + 6], r[c * 8 + 7], f3);
-							st_shared_v4(h_tile + sw128(row, half * 4 + c), v0, v1, v2, v3);
-							if (p.dbg_grad_hidden) *reinterpret_cast<uint4*>(p.dbg_grad_hidden + ((size_t)(l - 1) * p.batch_size + osample) * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
-						}
+					const uint32_t h_prev = h0 + (l - 1) * TILE_BYTES;
+					if (l == NH) {
+						umma_f16_ss(acc, kmaj(dy, 0), mnmaj(s_wout, 0), IDESC_DGRAD, 0);
+						const uint32_t dw = tmem_dw + 64u * NH;
+						for (uint32_t jj = 0; jj < TILE_M / 16; ++jj) umma_f16_ss(dw, mnmaj(h_prev, jj), mnmaj(dy, jj), IDESC_WGRAD, accumulate_dw || jj > 0);
+					} else {
+						const uint32_t g_tile = h0 + l * TILE_BYTES;  // g_l lives in h_l's tile
+						const uint32_t w_tile = s_w0 + l * (WIDTH * 128);
+						for (uint32_t jj = 0; jj < WIDTH / 16; ++jj) umma_f16_ss(acc, kmaj(g_tile, jj), mnmaj(w_tile, jj), IDESC_DGRAD, jj > 0);
+						const uint32_t dw = tmem_dw + 64u * l;
+						for (uint32_t jj = 0; jj < TILE_M / 16; ++jj) umma_f16_ss(dw, mnmaj(g_tile, jj), mnmaj(h_prev, jj), IDESC_WGRAD, accumulate_dw || jj > 0);
 					}
 				} else {
-					// dL/d(encoded): round once to fp16 (fully_fused_mlp.cu:835) and park the row for the memory group
-					dw_started = true;
-					const uint32_t park_tile = s_park + g * TILE_BYTES;
-					if (j >= 1) mbar_wait(bar_park_free + 8 * g, (j - 1) & 1u);  // scatter of tile k-2 has consumed park[g]
+					// d_enc = g_0 . W_0 (fully_fused_mlp.cu:833-836);  dW_0 += g_0^T . enc (:827-830)
+					const uint32_t g_tile = h0;
+					for (uint32_t jj = 0; jj < WIDTH / 16; ++jj) umma_f16_ss(acc, kmaj(g_tile, jj), mnmaj(s_w0, jj), IDESC_DGRAD, jj > 0);
+					for (uint32_t jj = 0; jj < TILE_M / 16; ++jj) umma_f16_ss(tmem_dw, mnmaj(g_tile, jj), mnmaj(enc_cur, jj), IDESC_WGRAD, accumulate_dw || jj > 0);
+					umma_commit(bar_enc_free + 8 * c);  // last reader of enc[c]: release it to the memory group
+				}
+				umma_commit(bar_mma + 8 * c);
+			}
+			__syncwarp();
+		};
+
+		// Wait for batch b of chain c and run its epilogue. Thread = row, all 64 accumulator columns (two passes of 32).
+		auto wait_and_epilogue = [&](uint32_t c, uint32_t b, uint32_t j, uint32_t osample) {
+			mbar_wait(bar_mma + 8 * c, phase[c]);
+			phase[c] ^= 1u;
+			tc_fence_after_sync();
+			const uint32_t acc = tmem_base + c * 64u;
+			const uint32_t h0 = s_h0 + c * NH * TILE_BYTES;
+			const uint32_t dy_tile = s_dy + c * TILE_BYTES;
+			if (b < NH) {
+				const uint32_t h_tile = h0 + b * TILE_BYTES;
 #pragma unroll
-					for (uint32_t half = 0; half < 2; ++half) {
-						uint32_t r[32];
-						tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
-						tmem_ld_wait();
+				for (uint32_t half = 0; half < 2; ++half) {
+					uint32_t r[32];
+					tmem_ld_32x32b_x32(acc + lane_field + half * 32, r);
+					tmem_ld_wait();
 #pragma unroll
-						for (uint32_t c = 0; c < 4; ++c) {
-							const uint32_t v0 = pack_half2(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1]));
-							const uint32_t v1 = pack_half2(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3]));
-							const uint32_t v2 = pack_half2(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5]));
-							const uint32_t v3 = pack_half2(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7]));
-							st_shared_v4(park_tile + sw128(row, half * 4 + c), v0, v1, v2, v3);
-							if (p.dbg_denc) *reinterpret_cast<uint4*>(p.dbg_denc + (size_t)osample * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
-						}
+					for (uint32_t q = 0; q < 4; ++q) {
+						const uint32_t v0 = relu_pack(r[q * 8 + 0], r[q * 8 + 1]), v1 = relu_pack(r[q * 8 + 2], r[q * 8 + 3]);
+						const uint32_t v2 = relu_pack(r[q * 8 + 4], r[q * 8 + 5]), v3 = relu_pack(r[q * 8 + 6], r[q * 8 + 7]);
+						st_shared_v4(h_tile + sw128(row, half * 4 + q), v0, v1, v2, v3);
+						if (p.dbg_hidden) *reinterpret_cast<uint4*>(p.dbg_hidden + ((size_t)b * p.batch_size + osample) * 64 + (half * 4 + q) * 8) = make_uint4(v0, v1, v2, v3);
 					}
-					__syncwarp();
-					if ((tid & 31u) == 0) mbar_arrive(bar_park_full + 8 * g);
+				}
+			} else if (b == NH) {
+				uint32_t r[16];
+				tmem_ld_32x32b_x16(acc + lane_field, r);
+				tmem_ld_wait();
+				// The reference's network output is fp16 (fully_fused_mlp.cu:421-476); everything downstream reads that rounding.
+				__half y16[16];
+#pragma unroll
+				for (uint32_t q = 0; q < 16; ++q) y16[q] = __float2half_rn(__uint_as_float(r[q]));
+				if (p.out_fp16) {
+					uint4* dst = reinterpret_cast<uint4*>(p.out_fp16 + (size_t)osample * 16);
+					dst[0] = *reinterpret_cast<uint4*>(&y16[0]);
+					dst[1] = *reinterpret_cast<uint4*>(&y16[8]);
+				}
+				if (p.out_fp32) {
+					for (uint32_t q = 0; q < p.n_out; ++q) p.out_fp32[(size_t)osample * p.n_out + q] = __half2float(y16[q]);
+				}
+				if (TRAIN) {
+					// relative_l2_loss / l2_loss (losses/relative_l2.h:56-75, l2.h:56-74); pad lanes give 0.
+					__half dyv[16];
+					const float n_total = (float)(p.loss_batch_size * p.n_out);
+#pragma unroll
+					for (uint32_t q = 0; q < 16; ++q) {
+						float gq = 0.0f;
+						if (q < p.n_out) {
+							const float pred = __half2float(y16[q]);
+							const float diff = pred - __ldg(p.targets + (size_t)osample * p.n_out + q);
+							float value, grad;
+							if (p.loss_type == LOSS_RELATIVE_L2) {
+								const float psq = pred * pred + 0.01f;
+								value = diff * diff / psq / n_total;
+								grad = 2.0f * diff / psq;
+							} else {
+								value = diff * diff / n_total;
+								grad = 2.0f * diff;
+							}
+							gq = p.loss_scale * grad / n_total;
+							loss_acc += value;
+							if (p.loss_values) p.loss_values[(size_t)osample * p.n_out + q] = value;
+						}
+						dyv[q] = __float2half_rn(gq);
+					}
+					const uint4 lo = *reinterpret_cast<uint4*>(&dyv[0]), hi = *reinterpret_cast<uint4*>(&dyv[8]);
+					st_shared_v4(dy_tile + sw128(row, 0), lo.x, lo.y, lo.z, lo.w);
+					st_shared_v4(dy_tile + sw128(row, 1), hi.x, hi.y, hi.z, hi.w);
+					if (p.dbg_dy) {
+						uint4* dst = reinterpret_cast<uint4*>(p.dbg_dy + (size_t)osample * 16);
+						dst[0] = lo;
+						dst[1] = hi;
+					}
+				}
+			} else if (b <= 2 * NH) {
+				// g overwrites h in place: every thread rewrites only chunks of its own row that it has just read, and all MMAs
+				// that read this tile (forward A operand, wgrad B operand of the batch just completed) are finished.
+				const uint32_t l = 2 * NH + 1 - b;
+				const uint32_t h_tile = h0 + (l - 1) * TILE_BYTES;
+#pragma unroll
+				for (uint32_t half = 0; half < 2; ++half) {
+					uint32_t r[32];
+					tmem_ld_32x32b_x32(acc + lane_field + half * 32, r);
+					tmem_ld_wait();
+#pragma unroll
+					for (uint32_t q = 0; q < 4; ++q) {
+						uint32_t f0, f1, f2, f3;
+						ld_shared_v4(h_tile + sw128(row, half * 4 + q), f0, f1, f2, f3);
+						const uint32_t v0 = relu_bwd_pack(r[q * 8 + 0], r[q * 8 + 1], f0), v1 = relu_bwd_pack(r[q * 8 + 2], r[q * 8 + 3], f1);
+						const uint32_t v2 = relu_bwd_pack(r[q * 8 + 4], r[q * 8 + 5], f2), v3 = relu_bwd_pack(r[q * 8 + 6], r[q * 8 + 7], f3);
+						st_shared_v4(h_tile + sw128(row, half * 4 + q), v0, v1, v2, v3);
+						if (p.dbg_grad_hidden) *reinterpret_cast<uint4*>(p.dbg_grad_hidden + ((size_t)(l - 1) * p.batch_size + osample) * 64 + (half * 4 + q) * 8) = make_uint4(v0, v1, v2, v3);
+					}
+				}
+			} else {
+				// dL/d(encoded): round once to fp16 (fully_fused_mlp.cu:835) and park the row for the memory group
+				const uint32_t park_tile = s_park + c * TILE_BYTES;
+				if (j >= 1) mbar_wait(bar_park_free + 8 * c, (j - 1) & 1u);  // scatter of this chain's previous tile has consumed park[c]
+#pragma unroll
+				for (uint32_t half = 0; half < 2; ++half) {
+					uint32_t r[32];
+					tmem_ld_32x32b_x32(acc + lane_field + half * 32, r);
+					tmem_ld_wait();
+#pragma unroll
+					for (uint32_t q = 0; q < 4; ++q) {
+						const uint32_t v0 = pack_half2(__uint_as_float(r[q * 8 + 0]), __uint_as_float(r[q * 8 + 1]));
+						const uint32_t v1 = pack_half2(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3]));
+						const uint32_t v2 = pack_half2(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5]));
+						const uint32_t v3 = pack_half2(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7]));
+						st_shared_v4(park_tile + sw128(row, half * 4 + q), v0, v1, v2, v3);
+						if (p.dbg_denc) *reinterpret_cast<uint4*>(p.dbg_denc + (size_t)osample * 64 + (half * 4 + q) * 8) = make_uint4(v0, v1, v2, v3);
+					}
+				}
+				__syncwarp();
+				if ((tid & 31u) == 0) mbar_arrive(bar_park_full + 8 * c);
+			}
+		};
+
+		for (uint32_t j = 0;; ++j) {
+			const uint32_t tile0 = blockIdx.x + (2 * j) * gridDim.x, tile1 = tile0 + gridDim.x;
+			if (tile0 >= n_tiles) break;
+			const bool have1 = tile1 < n_tiles;
+			uint32_t os0 = tile0 * TILE_M + row, os1 = tile1 * TILE_M + row;
+			if (p.perm) {
+				os0 = __ldg(p.perm + os0);
+				if (have1) os1 = __ldg(p.perm + os1);
+			}
+			mbar_wait(bar_enc_full, j & 1u);
+			sync_and_issue(0, 0, j);
+			if (have1) {
+				mbar_wait(bar_enc_full + 8, j & 1u);
+				sync_and_issue(1, 0, j);
+			}
+#pragma unroll 1
+			for (uint32_t b = 0; b < n_batches; ++b) {
+				wait_and_epilogue(0, b, j, os0);
+				if (b + 1 < n_batches) sync_and_issue(0, b + 1, j);
+				if (have1) {
+					wait_and_epilogue(1, b, j, os1);
+					if (b + 1 < n_batches) sync_and_issue(1, b + 1, j);
 				}
 			}
+			dw_started = true;
 		}
 
 		// ---- flush the weight-gradient accumulators and the loss
@@ -456,7 +485,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 				const uint32_t lane = tid & 31u;
 				const uint32_t m = warp * 16 + lane;
 				for (uint32_t l = 0; l <= NH; ++l) {
-					const uint32_t dw = tmem_base + 64u * (1 + l) + lane_field;
+					const uint32_t dw = tmem_base + 128u + 64u * l + lane_field;
 #pragma unroll
 					for (uint32_t half = 0; half < 2; ++half) {
 						uint32_t r[32];
@@ -497,8 +526,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 
 // ------------------------------------------------------------------------------------------------------------------
 size_t fused_ws_smem_bytes(uint32_t n_hidden_layers, bool train) {
-	const size_t tiles = 2 + n_hidden_layers + (train ? 3 : 0);
-	return tiles * TILE_BYTES + n_hidden_layers * (WIDTH * 128) + 16 * 128 + 96 + MAX_LEVELS * sizeof(LevelInfo) + 1024 /* alignment slack */;
+	const size_t tiles = 2 + 2 * n_hidden_layers + (train ? 4 : 0);
+	return tiles * TILE_BYTES + n_hidden_layers * (WIDTH * 128) + 16 * 128 + 128 + MAX_LEVELS * sizeof(LevelInfo) + 1024 /* alignment slack */;
 }
 
 template <uint32_t D, bool TRAIN>

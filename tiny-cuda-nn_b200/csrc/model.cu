@@ -565,7 +565,7 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
 		p.perm = m.bin_perm.ptr;
 	}
 	m.prof_mark(stream);
-	if (m.warp_specialized && m.mlp.n_hidden_layers <= 4) {
+	if (m.warp_specialized && m.mlp.n_hidden_layers <= 3) {  // shared memory: two chains of activation tiles
 		TCNNB_CUDA_CHECK(launch_fused_ws(p, m.grid.n_pos_dims, true, std::min(batch / TILE_M, (uint32_t)m.n_sms), stream));
 	} else {
 		TCNNB_CUDA_CHECK(launch_fused_step(p, m.grid.n_pos_dims, true, fused_grid_size(m, batch), stream));
