@@ -103,7 +103,7 @@ inline half_t activation_bwd(uint32_t act, half_t grad, half_t fwd) {
 		case ORC_ACT_RELU: return hmul(grad, (half_t)(fwd > (half_t)0.0f ? 1.0f : 0.0f));
 		case ORC_ACT_LEAKY_RELU: return hmul(grad, (half_t)(fwd > (half_t)0.0f ? 1.0f : 0.01f));
 		case ORC_ACT_EXPONENTIAL: return hmul(grad, fwd);
-		case ORC_ACT_SIGMOID: return hmul(grad, (half_t)((float)fwd * (1.0f - (float)fwd)));
+		case ORC_ACT_SIGMOID: return hmul(grad, hmul(fwd, (half_t)(1.0f - (float)fwd)));  // frag * (T)(fwd * (T)(1 - fwd)), common_device.h:392-396
 		case ORC_ACT_SQUAREPLUS: { float y = (float)fwd * 10.0f; float y2 = y * y; return hmul(grad, (half_t)(y2 / (y2 + 1))); }
 		case ORC_ACT_SOFTPLUS: return hmul(grad, (half_t)(1.0f - expf(-(float)fwd * 10.0f)));
 		case ORC_ACT_TANH: return hmul(grad, (half_t)(1.0f - (float)fwd * (float)fwd));

@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-for a in 0 1 2 3; do TCNNB_ABLATE=$a timeout 120 python scripts/ablate.py; done 2>&1 | grep ablate | tee gpurun_out/ablate_ws.log
-for a in 1 2; do TCNNB_BINNING=0 TCNNB_ABLATE=$a timeout 120 python scripts/ablate.py; done 2>&1 | grep ablate | tee -a gpurun_out/ablate_ws.log
+timeout 300 python tests/debug_stages.py hash3d_small 3 3 512 > gpurun_out/debug_ws.log 2>&1; echo "debug rc=$?"; grep -E "encoded|hidden\[|output |dW\[|grid grads|params after|loss dev" gpurun_out/debug_ws.log | cut -c1-200
+timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -n 4 gpurun_out/pytest_gpu.log
+timeout 120 python scripts/ablate.py 2>&1 | grep ablate | tee gpurun_out/ablate.log
+timeout 600 python bench.py --steps 200 --warmup 20 > gpurun_out/bench_own.log 2>&1; tail -n 1 gpurun_out/bench_own.log | cut -c1-300

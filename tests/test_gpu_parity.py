@@ -359,3 +359,73 @@ def test_against_reference_golden_vectors(torch_cuda, name):
     assert rae(out, g["inference_final_f32"].reshape(B, n_out), 99.0) < 5e-2
     pf = ob.half_bits_to_float(f16(model.trainer.params()))
     assert np.abs(pf - ob.half_bits_to_float(g["params_final_f16"])).mean() < 0.05 * lr * g["meta"]["n_steps"]
+
+
+@pytest.mark.parametrize("activation,output_activation", [("LeakyReLU", "None"), ("Sigmoid", "None"), ("Tanh", "Sigmoid"), ("Squareplus", "None"), ("Softplus", "Exponential"), ("None", "None")])
+def test_other_activations_match_oracle(torch_cuda, activation, output_activation):
+    """FullyFusedMLP's activation set (fully_fused_mlp.cu:689-699), hidden and output, against the oracle's restatement of
+    warp_activation / warp_activation_backward (common_device.h:110-215, 354-420)."""
+    torch = torch_cuda
+    import tcnn_b200
+
+    cfg = load_cfg("hash3d_small")
+    cfg["network"]["activation"] = activation
+    cfg["network"]["output_activation"] = output_activation
+    cfg["loss"] = {"otype": "L2"}
+    B = 512
+    model = tcnn_b200.create_from_config(3, 3, cfg)
+    orc = ob.OracleModel(3, 3, cfg, scales=model.grid_levels()["scales"])
+    x, y = make_batch(3, 3, B)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    out_tap = torch.zeros(B, 16, dtype=torch.float16, device="cuda")
+    model.set_debug_taps(output=out_tap)
+    model.trainer.training_step(xd, yd, run_optimizer=False)
+    loss = model.trainer.loss()
+    torch.cuda.synchronize()
+    ref_loss = orc.training_step(x, y, run_optimizer=False)
+    enc = orc.encode(x)
+    _, out_ref = orc.mlp_forward(enc)
+    a = ob.half_bits_to_float(f16(out_tap))[:, :3]
+    b = ob.half_bits_to_float(out_ref)[:, :3]
+    assert rae(a, b, 99.0) < 2e-3, (activation, output_activation)  # fast-math exp/tanh vs libm
+    assert abs(loss - ref_loss) <= 2e-3 * abs(ref_loss) + 1e-7
+    g_dev = ob.half_bits_to_float(f16(model.trainer.param_gradients()))
+    g_ref = ob.half_bits_to_float(orc.grads_fp16)
+    assert rae(g_dev[: orc.n_mlp], g_ref[: orc.n_mlp], 99.9) < 1.2e-2
+    assert rae(g_dev[orc.n_mlp :], g_ref[orc.n_mlp :], 99.9) < 1.2e-2
+    with pytest.raises(tcnn_b200.TcnnError, match="Unsupported activation"):
+        bad = json.loads(json.dumps(cfg))
+        bad["network"]["activation"] = "Sine"
+        tcnn_b200.create_from_config(3, 3, bad)
+
+
+@pytest.mark.parametrize("width,n_hidden", [(16, 2), (32, 1), (32, 3), (64, 3)])
+def test_network_shapes_match_oracle(torch_cuda, width, n_hidden):
+    """FullyFusedMLP widths 16 / 32 / 64 (src/network.cu:116-123) and 1-3 hidden layers: 10 training steps track the oracle."""
+    torch = torch_cuda
+    import tcnn_b200
+
+    cfg = load_cfg("hash3d_small")
+    cfg["network"]["n_neurons"] = width
+    cfg["network"]["n_hidden_layers"] = n_hidden
+    B = 512
+    model = tcnn_b200.create_from_config(3, 3, cfg)
+    orc = ob.OracleModel(3, 3, cfg, scales=model.grid_levels()["scales"])
+    assert model.n_params == orc.n_params and model.n_mlp_params == orc.n_mlp == width * 32 + (n_hidden - 1) * width * width + 16 * width
+    assert np.array_equal(model.trainer.params_full_precision().cpu().numpy().view(np.uint32), orc.params_fp32.view(np.uint32))
+    x, y = make_batch(3, 3, B)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    model.trainer.training_step(xd, yd, run_optimizer=False)
+    orc.training_step(x, y, run_optimizer=False)
+    g_dev = ob.half_bits_to_float(f16(model.trainer.param_gradients()))
+    g_ref = ob.half_bits_to_float(orc.grads_fp16)
+    assert rae(g_dev[: orc.n_mlp], g_ref[: orc.n_mlp], 99.9) < 1.2e-2
+    assert rae(g_dev[orc.n_mlp :], g_ref[orc.n_mlp :], 99.9) < 1.2e-2
+    dev_losses, ref_losses = [], []
+    for _ in range(10):
+        model.trainer.training_step(xd, yd)
+        dev_losses.append(model.trainer.loss())
+        ref_losses.append(orc.training_step(x, y))
+    for a, b in zip(dev_losses, ref_losses):
+        assert abs(a - b) <= 3e-2 * abs(b) + 1e-6, (dev_losses, ref_losses)
+    assert rae(model.network.inference(xd).cpu().numpy(), orc.inference(x), 99.0) < 5e-2

@@ -45,6 +45,52 @@ __device__ __forceinline__ uint32_t relu_bwd_pack(uint32_t lo_bits, uint32_t hi_
 	return *reinterpret_cast<uint32_t*>(&g);
 }
 
+// ---- generic activations, evaluated like the reference's warp_activation<__half> / warp_activation_backward<__half>
+// (common_device.h:110-215, 354-420): on the fp16-rounded value, transcendental math in fp32, result rounded to fp16.
+__device__ __forceinline__ __half act_fwd_h(uint32_t act, __half x) {
+	const float xf = __half2float(x);
+	switch (act) {
+		case ACT_RELU: return __hmax(x, __float2half_rn(0.0f));
+		case ACT_LEAKY_RELU: return __hmul(x, __float2half_rn(__hgt(x, __float2half_rn(0.0f)) ? 1.0f : 0.01f));
+		case ACT_EXPONENTIAL: return __float2half_rn(expf(xf));
+		case ACT_SIGMOID: return __float2half_rn(1.0f / (1.0f + expf(-xf)));
+		case ACT_SQUAREPLUS: { const float v = xf * 10.0f; return __float2half_rn(0.5f * (v + sqrtf(v * v + 4)) / 10.0f); }
+		case ACT_SOFTPLUS: return __float2half_rn(logf(expf(xf * 10.0f) + 1.0f) / 10.0f);
+		case ACT_TANH: return __float2half_rn(tanhf(xf));
+		default: return x;  // None
+	}
+}
+
+// grad * f'(.) expressed through the stored FORWARD (post-activation) value, all products in fp16 like the reference.
+__device__ __forceinline__ __half act_bwd_h(uint32_t act, __half grad, __half fwd) {
+	const float f = __half2float(fwd);
+	switch (act) {
+		case ACT_RELU: return __hmul(grad, __float2half_rn(__hgt(fwd, __float2half_rn(0.0f)) ? 1.0f : 0.0f));
+		case ACT_LEAKY_RELU: return __hmul(grad, __float2half_rn(__hgt(fwd, __float2half_rn(0.0f)) ? 1.0f : 0.01f));
+		case ACT_EXPONENTIAL: return __hmul(grad, fwd);
+		case ACT_SIGMOID: return __hmul(grad, __hmul(fwd, __float2half_rn(1.0f - f)));
+		case ACT_SQUAREPLUS: { const float y = f * 10.0f; return __hmul(grad, __float2half_rn(y * y / (y * y + 1))); }
+		case ACT_SOFTPLUS: return __hmul(grad, __float2half_rn(1.0f - expf(-f * 10.0f)));
+		case ACT_TANH: return __hmul(grad, __float2half_rn(1.0f - f * f));
+		default: return grad;  // None
+	}
+}
+
+__device__ __forceinline__ uint32_t act_pack(uint32_t act, uint32_t lo_bits, uint32_t hi_bits) {
+	if (act == ACT_RELU) return relu_pack(lo_bits, hi_bits);  // packed fast path
+	const __half2 x = __floats2half2_rn(__uint_as_float(lo_bits), __uint_as_float(hi_bits));
+	const __half2 y = __halves2half2(act_fwd_h(act, __low2half(x)), act_fwd_h(act, __high2half(x)));
+	return *reinterpret_cast<const uint32_t*>(&y);
+}
+
+__device__ __forceinline__ uint32_t act_bwd_pack(uint32_t act, uint32_t lo_bits, uint32_t hi_bits, uint32_t fwd_bits) {
+	if (act == ACT_RELU) return relu_bwd_pack(lo_bits, hi_bits, fwd_bits);
+	const __half2 g = __floats2half2_rn(__uint_as_float(lo_bits), __uint_as_float(hi_bits));
+	const __half2 f = *reinterpret_cast<const __half2*>(&fwd_bits);
+	const __half2 y = __halves2half2(act_bwd_h(act, __low2half(g), __low2half(f)), act_bwd_h(act, __high2half(g), __high2half(f)));
+	return *reinterpret_cast<const uint32_t*>(&y);
+}
+
 struct SmemSync {
 	// dynamic shared memory, 1024-byte aligned:
 	//   [ enc_0 | enc_1 | h_0 .. h_{NH-1} | dy | (park) | W_0 .. W_{NH-1} | W_out ] then barriers

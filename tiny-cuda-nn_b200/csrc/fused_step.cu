@@ -79,29 +79,26 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 
 	// Stage the fp16 weights: W_l rows are 128-byte tile rows (K-major, SWIZZLE_128B); unused columns are zeroed.
 	{
+		// W_l [out][in] row-major -> 128-byte tile rows (K-major, SWIZZLE_128B). Rows / columns beyond the network's width
+		// and the encoding's width are zero, which makes a 16- or 32-wide network an exact sub-problem of the 64-wide tiles.
 		const __half* __restrict__ w = p.params;  // MLP weights come first in the parameter buffer
-		for (uint32_t i = tid; i < WIDTH * 8; i += 256) {  // first layer: [64][in_w]
-			const uint32_t r = i >> 3, c = i & 7;
-			uint4 v = make_uint4(0, 0, 0, 0);
-			if (c * 8 < in_w) v = __ldg(reinterpret_cast<const uint4*>(w + r * in_w + c * 8));
-			st_shared_v4(s.w0 + sw128(r, c), v.x, v.y, v.z, v.w);
-		}
-		w += WIDTH * in_w;
-		for (uint32_t l = 1; l < NH; ++l) {
-			for (uint32_t i = tid; i < WIDTH * 8; i += 256) {
+		const uint32_t NW = p.width;
+		auto stage = [&](uint32_t tile, const __half* __restrict__ src, uint32_t rows, uint32_t cols, uint32_t tile_rows) {
+			for (uint32_t i = tid; i < tile_rows * 8; i += 256) {
 				const uint32_t r = i >> 3, c = i & 7;
-				const uint4 v = __ldg(reinterpret_cast<const uint4*>(w + r * WIDTH + c * 8));
-				st_shared_v4(s.w0 + l * (WIDTH * 128) + sw128(r, c), v.x, v.y, v.z, v.w);
+				uint4 v = make_uint4(0, 0, 0, 0);
+				if (r < rows && c * 8 < cols) v = __ldg(reinterpret_cast<const uint4*>(src + r * cols + c * 8));
+				st_shared_v4(tile + sw128(r, c), v.x, v.y, v.z, v.w);
 			}
-			w += WIDTH * WIDTH;
+		};
+		stage(s.w0, w, NW, in_w, WIDTH);
+		w += NW * in_w;
+		for (uint32_t l = 1; l < NH; ++l) {
+			stage(s.w0 + l * (WIDTH * 128), w, NW, NW, WIDTH);
+			w += NW * NW;
 		}
-		for (uint32_t i = tid; i < 16 * 8; i += 256) {
-			const uint32_t r = i >> 3, c = i & 7;
-			const uint4 v = __ldg(reinterpret_cast<const uint4*>(w + r * WIDTH + c * 8));
-			st_shared_v4(s.w_out + sw128(r, c), v.x, v.y, v.z, v.w);
-		}
+		stage(s.w_out, w, 16, NW, 16);
 	}
-
 	fence_proxy_async_smem();
 	tc_fence_before_sync();
 	__syncthreads();
@@ -343,8 +340,8 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 				tmem_ld_wait();
 #pragma unroll
 				for (uint32_t c = 0; c < 4; ++c) {
-					const uint32_t v0 = relu_pack(r[c * 8 + 0], r[c * 8 + 1]), v1 = relu_pack(r[c * 8 + 2], r[c * 8 + 3]);
-					const uint32_t v2 = relu_pack(r[c * 8 + 4], r[c * 8 + 5]), v3 = relu_pack(r[c * 8 + 6], r[c * 8 + 7]);
+					const uint32_t v0 = act_pack(p.activation, r[c * 8 + 0], r[c * 8 + 1]), v1 = act_pack(p.activation, r[c * 8 + 2], r[c * 8 + 3]);
+					const uint32_t v2 = act_pack(p.activation, r[c * 8 + 4], r[c * 8 + 5]), v3 = act_pack(p.activation, r[c * 8 + 6], r[c * 8 + 7]);
 					st_shared_v4(h_tile + sw128(row, hsel * 4 + c), v0, v1, v2, v3);
 					if (p.dbg_hidden) *reinterpret_cast<uint4*>(p.dbg_hidden + ((size_t)b * p.batch_size + osample) * 64 + (hsel * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
 				}
@@ -356,7 +353,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 					// The reference's network output is fp16 (fully_fused_mlp.cu:421-476); everything downstream reads that rounding.
 					__half y16[16];
 #pragma unroll
-					for (uint32_t j = 0; j < 16; ++j) y16[j] = __float2half_rn(__uint_as_float(r[j]));
+					for (uint32_t j = 0; j < 16; ++j) y16[j] = act_fwd_h(p.output_activation, __float2half_rn(__uint_as_float(r[j])));
 					if (p.out_fp16) {
 						uint4* dst = reinterpret_cast<uint4*>(p.out_fp16 + (size_t)osample * 16);
 						dst[0] = *reinterpret_cast<uint4*>(&y16[0]);
@@ -388,7 +385,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 								loss_acc += value;
 								if (p.loss_values) p.loss_values[(size_t)osample * p.n_out + j] = value;
 							}
-							dy[j] = __float2half_rn(g);
+							dy[j] = act_bwd_h(p.output_activation, __float2half_rn(g), y16[j]);
 						}
 						const uint4 lo = *reinterpret_cast<uint4*>(&dy[0]), hi = *reinterpret_cast<uint4*>(&dy[8]);
 						st_shared_v4(s.dy + sw128(row, 0), lo.x, lo.y, lo.z, lo.w);
@@ -412,8 +409,8 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 				for (uint32_t c = 0; c < 4; ++c) {
 					uint32_t f0, f1, f2, f3;
 					ld_shared_v4(h_tile + sw128(row, hsel * 4 + c), f0, f1, f2, f3);
-					const uint32_t v0 = relu_bwd_pack(r[c * 8 + 0], r[c * 8 + 1], f0), v1 = relu_bwd_pack(r[c * 8 + 2], r[c * 8 + 3], f1);
-					const uint32_t v2 = relu_bwd_pack(r[c * 8 + 4], r[c * 8 + 5], f2), v3 = relu_bwd_pack(r[c * 8 + 6], r[c * 8 + 7], f3);
+					const uint32_t v0 = act_bwd_pack(p.activation, r[c * 8 + 0], r[c * 8 + 1], f0), v1 = act_bwd_pack(p.activation, r[c * 8 + 2], r[c * 8 + 3], f1);
+					const uint32_t v2 = act_bwd_pack(p.activation, r[c * 8 + 4], r[c * 8 + 5], f2), v3 = act_bwd_pack(p.activation, r[c * 8 + 6], r[c * 8 + 7], f3);
 					st_shared_v4(h_tile + sw128(row, hsel * 4 + c), v0, v1, v2, v3);
 					if (p.dbg_grad_hidden) *reinterpret_cast<uint4*>(p.dbg_grad_hidden + ((size_t)(l - 1) * p.batch_size + osample) * 64 + (hsel * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
 				}
@@ -467,7 +464,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 				uint32_t r[32];
 				tmem_ld_32x32b_x32(dw + half * 32, r);
 				tmem_ld_wait();
-				if (lane < 16) {
+				if (lane < 16 && m < p.width) {
 					if (l == 0) {
 						// dW_0[out = m][in = n], n < in_w
 						float* dst = p.dw_accum + m * in_w;
@@ -477,14 +474,14 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 							if (n < in_w) red_add_v4_f32(dst + n, __uint_as_float(r[k]), __uint_as_float(r[k + 1]), __uint_as_float(r[k + 2]), __uint_as_float(r[k + 3]));
 						}
 					} else if (l < NH) {
-						float* dst = p.dw_accum + WIDTH * in_w + (l - 1) * WIDTH * WIDTH + m * WIDTH + half * 32;
+						float* dst = p.dw_accum + p.width * in_w + (l - 1) * p.width * p.width + m * p.width + half * 32;
 #pragma unroll
-						for (uint32_t k = 0; k < 32; k += 4) red_add_v4_f32(dst + k, __uint_as_float(r[k]), __uint_as_float(r[k + 1]), __uint_as_float(r[k + 2]), __uint_as_float(r[k + 3]));
+						for (uint32_t k = 0; k < 32; k += 4) if (half * 32 + k < p.width) red_add_v4_f32(dst + k, __uint_as_float(r[k]), __uint_as_float(r[k + 1]), __uint_as_float(r[k + 2]), __uint_as_float(r[k + 3]));
 					} else if (half == 0) {
 						// accumulator holds dW_out^T[in = m][out = n], n < 16
-						float* dst = p.dw_accum + WIDTH * in_w + (NH - 1) * WIDTH * WIDTH;
+						float* dst = p.dw_accum + p.width * in_w + (NH - 1) * p.width * p.width;
 #pragma unroll
-						for (uint32_t n = 0; n < 16; ++n) red_add_f32(dst + n * WIDTH + m, __uint_as_float(r[n]));
+						for (uint32_t n = 0; n < 16; ++n) red_add_f32(dst + n * p.width + m, __uint_as_float(r[n]));
 					}
 				}
 			}

@@ -18,7 +18,10 @@ struct FusedStepParams {
 	uint32_t ablate;
 	// model
 	GridMeta grid;
-	uint32_t n_hidden_layers;      // 1..6, hidden width 64, ReLU
+	uint32_t width;                // hidden width 16 / 32 / 64 (narrower layers run as 64-wide tiles with zero-padded weights)
+	uint32_t n_hidden_layers;      // 1..6
+	uint32_t activation;           // hidden activation (Activation enum)
+	uint32_t output_activation;    // applied to the network output before the loss
 	uint32_t n_out;                // logical outputs (<= 16)
 	uint32_t n_mlp_params;         // grid params start here in the parameter / gradient buffers
 	uint32_t loss_type;            // LossType

@@ -416,10 +416,12 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 	mlp.n_params = mlp.width * mlp.in_width + (mlp.n_hidden_layers - 1) * mlp.width * mlp.width + mlp.padded_out_width * mlp.width;
 
 	// ---- what the sm_100a kernels of this round cover; everything else fails loudly (no fallback by design)
-	if (mlp.width != 64) throw std::runtime_error("tcnn_b200: the tcgen05 fused path currently covers n_neurons == 64 (got " + std::to_string(mlp.width) + ")");
+	if (mlp.width > 64) throw std::runtime_error("tcnn_b200: the tcgen05 fused path currently covers n_neurons <= 64 (got " + std::to_string(mlp.width) + "); 128-wide layers are the next row");
 	if (mlp.n_hidden_layers > 6) throw std::runtime_error("tcnn_b200: the fused path keeps all hidden activations on chip and covers n_hidden_layers <= 6");
-	if (mlp.activation != ACT_RELU) throw std::runtime_error(std::string("tcnn_b200: fused path covers activation == ReLU (got ") + activation_name(mlp.activation) + ")");
-	if (mlp.output_activation != ACT_NONE) throw std::runtime_error(std::string("tcnn_b200: fused path covers output_activation == None (got ") + activation_name(mlp.output_activation) + ")");
+	// FullyFusedMLP's activation set (fully_fused_mlp.cu:689-699): Sine and SiLU need stored pre-activations and are rejected there too.
+	for (uint32_t act : {mlp.activation, mlp.output_activation}) {
+		if (act == ACT_SINE || act == ACT_SILU) throw std::runtime_error("Unsupported activation.");
+	}
 	if (mlp.padded_out_width != 16) throw std::runtime_error("tcnn_b200: fused path covers n_output_dims <= 16");
 	if (m.grid.n_features_per_level != 2) throw std::runtime_error("tcnn_b200: fused path covers n_features_per_level == 2");
 	if (m.grid.n_pos_dims != 2 && m.grid.n_pos_dims != 3) throw std::runtime_error("tcnn_b200: fused path covers 2-D and 3-D inputs");
@@ -493,7 +495,10 @@ static FusedStepParams make_params(Model& m, uint32_t batch, uint32_t loss_batch
 	FusedStepParams p{};
 	p.ablate = m.ablate;
 	p.grid = m.grid_meta();
+	p.width = m.mlp.width;
 	p.n_hidden_layers = m.mlp.n_hidden_layers;
+	p.activation = m.mlp.activation;
+	p.output_activation = m.mlp.output_activation;
 	p.n_out = m.n_out;
 	p.n_mlp_params = m.mlp.n_params;
 	p.loss_type = m.loss_type;
@@ -565,7 +570,7 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
 		p.perm = m.bin_perm.ptr;
 	}
 	m.prof_mark(stream);
-	if (m.warp_specialized && m.mlp.n_hidden_layers <= 3) {  // shared memory: two chains of activation tiles
+	if (m.warp_specialized && m.mlp.n_hidden_layers <= 4) {
 		TCNNB_CUDA_CHECK(launch_fused_ws(p, m.grid.n_pos_dims, true, std::min(batch / TILE_M, (uint32_t)m.n_sms), stream));
 	} else {
 		TCNNB_CUDA_CHECK(launch_fused_step(p, m.grid.n_pos_dims, true, fused_grid_size(m, batch), stream));
