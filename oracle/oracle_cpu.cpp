@@ -440,7 +440,7 @@ void orc_mlp_backward(const orc_mlp_t* m, uint32_t B, int accum_mode, const uint
 		double* dWp = dW_part[0].data();
 #endif
 		std::vector<half_t> g(std::max(OUT, W)), gn(std::max(W, IN));
-		// NOTE: output activation transfer is done before the fused kernel (fully_fused_mlp.cu:755-759); only None is restated here.
+		// NOTE: the output activation's transfer is applied by the caller before this function (fully_fused_mlp.cu:758-762).
 		for (uint32_t o = 0; o < OUT; ++o) g[o] = bits_to_half(dL_dout[(size_t)i * OUT + o]);
 
 		// Output layer weight gradient: dW_out = dL_dout . h_last^T (fully_fused_mlp.cu:784-787)
@@ -650,6 +650,12 @@ double orc_training_step_shard(const orc_model_t* model, uint32_t B, uint32_t B_
 	if (loss_values) {
 		for (uint32_t i = 0; i < B; ++i)
 			for (uint32_t j = 0; j < m->out_width; ++j) loss_values[(size_t)i * m->out_width + j] = L[(size_t)i * OUT + j];
+	}
+
+	// Transfer of the output activation happens ahead of the backward kernel, from the forward OUTPUT values
+	// (fully_fused_mlp.cu:758-762, activation_backward_output_gpu -> warp_activation_backward, common_device.h:354-420).
+	if (m->output_activation != ORC_ACT_NONE) {
+		for (size_t i = 0; i < dL_dy.size(); ++i) dL_dy[i] = half_to_bits(activation_bwd(m->output_activation, bits_to_half(dL_dy[i]), bits_to_half(out[i])));
 	}
 
 	std::vector<double> dW(n_mlp), dG(n_grid);

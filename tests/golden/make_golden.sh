@@ -13,6 +13,7 @@ $H dump $C/hash3d_small.json 3 3 512 10 "$OUT/hash3d_small" 0
 $H dump $C/hash3d_small.json 3 3 512 10 "$OUT/hash3d_small_jit" 1
 $H dump $C/dense_mix3d.json 3 2 256 10 "$OUT/dense_mix3d" 0
 $H dump $C/image2d.json 2 3 512 10 "$OUT/image2d" 0
+$H dump $C/tanh_w32.json 3 3 512 10 "$OUT/tanh_w32" 0
 $H probe 1.5 16 16 > "$OUT/probe_s1.5_b16.json"
 $H probe 2.0 16 16 > "$OUT/probe_s2.0_b16.json"
 $H probe 1.5 4 8 > "$OUT/probe_s1.5_b4.json"

@@ -37,8 +37,12 @@ __device__ __forceinline__ uint32_t bin_key(const float* __restrict__ pos, uint3
 }
 
 template <uint32_t D>
-__global__ void bin_count_kernel(uint32_t n, const float* __restrict__ pos, uint32_t log2_r, uint32_t* __restrict__ keys, uint32_t* __restrict__ hist) {
+__global__ void bin_count_kernel(uint32_t n, const float* __restrict__ pos, uint32_t log2_r, uint32_t* __restrict__ keys, uint32_t* __restrict__ hist, uint4* __restrict__ zero_ptr, uint32_t zero_n16, float* __restrict__ zero_scalar) {
 	const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
+	// This kernel waits on atomic round trips and leaves the memory pipes idle: the step's gradient zeroing (GradientMode::Overwrite,
+	// grid.h:865-867) rides along here instead of being a separate 26 MB memset launch in front of the fused kernel.
+	for (uint32_t j = i; j < zero_n16; j += gridDim.x * blockDim.x) zero_ptr[j] = make_uint4(0u, 0u, 0u, 0u);
+	if (i == 0 && zero_scalar) *zero_scalar = 0.0f;
 	if (i >= n) return;
 	const uint32_t k = bin_key<D>(pos, i, log2_r);
 	// the value returned by the counting atomic is this sample's rank inside its bin: the scatter pass needs no atomics
@@ -139,7 +143,9 @@ uint32_t binning_log2_resolution(uint32_t n_samples, uint32_t n_pos_dims) {
 
 uint32_t binning_n_bins(uint32_t log2_r, uint32_t n_pos_dims) { return n_pos_dims == 2 ? (1u << log2_r) : (1u << (2 * log2_r)); }
 
-cudaError_t launch_binning(cudaStream_t stream, uint32_t n_pos_dims, uint32_t n, const float* pos, uint32_t log2_r, uint32_t* keys, uint32_t* hist, uint32_t* perm) {
+cudaError_t launch_binning(cudaStream_t stream, uint32_t n_pos_dims, uint32_t n, const float* pos, uint32_t log2_r, uint32_t* keys, uint32_t* hist, uint32_t* perm, void* zero_ptr, size_t zero_bytes, float* zero_scalar) {
+	if (((uintptr_t)zero_ptr | zero_bytes) & 15u) return cudaErrorMisalignedAddress;
+	const uint32_t zero_n16 = (uint32_t)(zero_bytes / 16);
 	const uint32_t n_bins = binning_n_bins(log2_r, n_pos_dims);
 	uint32_t* cursor = hist + n_bins;  // hist: [n_bins counters (zero between calls) | n_bins cursors]
 	const uint32_t blocks = (n + 255) / 256;
@@ -150,9 +156,9 @@ cudaError_t launch_binning(cudaStream_t stream, uint32_t n_pos_dims, uint32_t n,
 		attr_set = true;
 	}
 	if (n_pos_dims == 2) {
-		bin_count_kernel<2><<<blocks, 256, 0, stream>>>(n, pos, log2_r, keys, hist);
+		bin_count_kernel<2><<<blocks, 256, 0, stream>>>(n, pos, log2_r, keys, hist, (uint4*)zero_ptr, zero_n16, zero_scalar);
 	} else if (n_pos_dims == 3) {
-		bin_count_kernel<3><<<blocks, 256, 0, stream>>>(n, pos, log2_r, keys, hist);
+		bin_count_kernel<3><<<blocks, 256, 0, stream>>>(n, pos, log2_r, keys, hist, (uint4*)zero_ptr, zero_n16, zero_scalar);
 	} else {
 		return cudaErrorInvalidValue;
 	}

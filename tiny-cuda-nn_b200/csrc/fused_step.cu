@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 	static_assert(F == 2, "fused path: F == 2");
 	extern __shared__ __align__(1024) uint8_t smem_raw[];
 	const uint32_t tid = threadIdx.x;
-	const uint32_t warp = tid >> 5;
+	const uint32_t warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);  // broadcast: the compiler can treat it as warp-uniform
 	const uint32_t row = tid & 127u;   // sample within the tile == smem tile row == TMEM lane
 	const uint32_t hsel = tid >> 7;    // which half of the levels / accumulator columns this thread owns (warp-uniform)
 	const uint32_t NH = p.n_hidden_layers;
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 #pragma unroll 1
 		for (uint32_t b = 0; b < n_batches; ++b) {
 			stage_sync();
-			if (tid == 0) {
+			if (warp == 0 && elect_one_sync()) {  // warp-uniform branch + one elected lane: operands stay in uniform registers
 				tc_fence_after_sync();
 				if (b < NH) {
 					const uint32_t a_tile = b == 0 ? enc_cur : s.h0 + (b - 1) * TILE_BYTES;

@@ -46,6 +46,7 @@ struct FusedStepParams {
 	__half* dbg_dy;                // [batch][16]
 	__half* dbg_grad_hidden;       // [n_hidden][batch][64]
 	__half* dbg_denc;              // [batch][64]
+	long long* dbg_clock;          // ablation builds: [cta][role 3][tile 16][slot 16] clock64 stamps of the ws kernel's phases
 };
 
 size_t fused_step_smem_bytes(uint32_t n_hidden_layers, uint32_t in_w, bool train);

@@ -26,6 +26,18 @@
 
 namespace tcnnb {
 
+// Phase timestamps for pipeline analysis (ablation builds only: make ABLATION=1; scripts/ws_timeline.py reads them).
+#ifdef TCNNB_ENABLE_ABLATION
+#define WS_STAMP(role, tile_idx, slot)                                                                                   \
+	do {                                                                                                                \
+		if (p.dbg_clock && (tile_idx) < 16u) p.dbg_clock[((blockIdx.x * 3u + (role)) * 16u + (tile_idx)) * 16u + (slot)] = clock64(); \
+	} while (0)
+#else
+#define WS_STAMP(role, tile_idx, slot) \
+	do {                               \
+	} while (0)
+#endif
+
 using namespace ptx;
 using namespace fused;
 
@@ -45,12 +57,15 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads) 
 
 }  // namespace
 
-template <uint32_t D, uint32_t F, bool TRAIN>
+template <uint32_t D, uint32_t F, bool TRAIN, bool GENERIC_ACT>
 __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStepParams p) {
+	// ReLU hidden / linear output (the reference's default and the benchmark configuration) fold to the packed fast path at compile time
+	const uint32_t hid_act = GENERIC_ACT ? p.activation : (uint32_t)ACT_RELU;
+	const uint32_t out_act = GENERIC_ACT ? p.output_activation : (uint32_t)ACT_NONE;
 	static_assert(F == 2, "fused path: F == 2");
 	extern __shared__ __align__(1024) uint8_t smem_raw[];
 	const uint32_t tid = threadIdx.x;
-	const uint32_t warp = tid >> 5;
+	const uint32_t warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);  // broadcast: the compiler can treat it as warp-uniform
 	const uint32_t NH = p.n_hidden_layers;
 	const uint32_t in_w = p.grid.padded_width;
 
@@ -138,15 +153,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 		const __half* __restrict__ table = p.params + p.n_mlp_params;
 		__half* __restrict__ grad_table = p.grads + p.n_mlp_params;
 
-		auto load_level = [&](uint32_t level) {
-			LevelInfo lv;
-			uint32_t* w = reinterpret_cast<uint32_t*>(&lv);
-			const uint32_t base = s_levels + level * (uint32_t)sizeof(LevelInfo);
-			static_assert(sizeof(LevelInfo) == 32, "LevelInfo layout");
-			asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(base));
-			asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(base + 16));
-			return lv;
-		};
+		// The level descriptor is indexed by a warp-uniform loop counter: it is read straight from the kernel parameters
+		// (constant bank, uniform registers) and costs the load/store unit nothing.
+		auto load_level = [&](uint32_t level) -> const LevelInfo& { return p.grid.levels[level]; };
 
 		float x_prev[D], x_cur[D];
 		uint32_t os_cur = 0;
@@ -156,7 +165,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 		auto scatter_prev = [&]() {
 #pragma unroll 1
 			for (uint32_t level = level_begin; level < level_end; ++level) {
-				const LevelInfo lv = load_level(level);
+				const LevelInfo& lv = load_level(level);
 				LevelCorners<D> lc;
 				level_corners<D>(lv, x_prev, p.grid.interpolation, lc);
 				uint32_t gbits;
@@ -177,16 +186,34 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 			}
 		};
 
+		auto sample_of = [&](uint32_t tile) {
+			const uint32_t s = tile * TILE_M + row;
+			return p.perm ? __ldg(p.perm + s) : s;
+		};
+		const uint32_t tile_first = blockIdx.x + g * gridDim.x, tile_stride = 2 * gridDim.x;
+		uint32_t os_next = tile_first < n_tiles ? sample_of(tile_first) : 0;
+		uint32_t os_next2 = tile_first + tile_stride < n_tiles ? sample_of(tile_first + tile_stride) : 0;
+		float x_next[D];
+#pragma unroll
+		for (uint32_t d = 0; d < D; ++d) x_next[d] = tile_first < n_tiles ? __ldg(p.positions + (size_t)os_next * D + d) : 0.0f;
 		uint32_t j = 0;  // this sub-group's tile counter
 		for (uint32_t k = g, tile = blockIdx.x + g * gridDim.x; tile < n_tiles; k += 2, tile += 2 * gridDim.x, ++j) {
-			// ---- position of this thread's sample
-			os_cur = tile * TILE_M + row;
-			if (p.perm) os_cur = __ldg(p.perm + os_cur);
+			// ---- position of this thread's sample (fetched one tile ahead, its index two tiles ahead: no dependent global
+			//      load latency in front of the gather)
+			os_cur = os_next;
+			os_next = os_next2;
 #pragma unroll
-			for (uint32_t d = 0; d < D; ++d) x_cur[d] = __ldg(p.positions + (size_t)os_cur * D + d);
+			for (uint32_t d = 0; d < D; ++d) x_cur[d] = x_next[d];
+			if (tile + tile_stride < n_tiles) {
+#pragma unroll
+				for (uint32_t d = 0; d < D; ++d) x_next[d] = __ldg(p.positions + (size_t)os_next * D + d);
+			}
+			if (tile + 2 * tile_stride < n_tiles) os_next2 = sample_of(tile + 2 * tile_stride);
 
 			// ---- gather tile k into enc[g] once the MMAs of tile k-2 have released it
+			if (lt == 0) WS_STAMP(1 + g, k, 0);
 			if (j >= 1) mbar_wait(bar_enc_free + 8 * g, (j - 1) & 1u);
+			if (lt == 0) WS_STAMP(1 + g, k, 1);
 #pragma unroll
 			for (uint32_t c = 0; c < 4; ++c) {  // zero this thread's half of the row (padding features are zero, grid.h:759-766)
 				const uint32_t chunk = c < n_chunks / 2 ? hsel * (n_chunks / 2) + c : n_chunks + hsel * ((8 - n_chunks) / 2) + (c - n_chunks / 2);
@@ -199,7 +226,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 					uint32_t w16[1u << D];  // (half)weight duplicated into both halves
 				};
 				auto issue = [&](uint32_t level, InFlight& f) {
-					const LevelInfo lv = load_level(level);
+					const LevelInfo& lv = load_level(level);
 					LevelCorners<D> lc;
 					level_corners<D>(lv, x_cur, p.grid.interpolation, lc);
 					const uint32_t* __restrict__ ltab = reinterpret_cast<const uint32_t*>(table + (size_t)lv.offset * F);
@@ -244,13 +271,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 			fence_proxy_async_smem();  // the tile is read by tcgen05.mma (async proxy)
 			__syncwarp();
 			if ((tid & 31u) == 0) mbar_arrive(bar_enc_full + 8 * g);
+			if (lt == 0) WS_STAMP(1 + g, k, 2);
 
 			// ---- scatter the previous tile of this sub-group (k-2) while the MLP group chews on tile k-1 / k
 			if (TRAIN && j >= 1) {
 				mbar_wait(bar_park_full + 8 * g, (j - 1) & 1u);
+				if (lt == 0) WS_STAMP(1 + g, k, 3);
 				scatter_prev();
 				__syncwarp();
 				if ((tid & 31u) == 0) mbar_arrive(bar_park_free + 8 * g);
+				if (lt == 0) WS_STAMP(1 + g, k, 4);
 			}
 #pragma unroll
 			for (uint32_t d = 0; d < D; ++d) x_prev[d] = x_cur[d];
@@ -287,18 +317,38 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 		};
 
 		const uint32_t n_batches = TRAIN ? 2 * NH + 2 : NH + 1;
+		// The sample index (through the binning permutation) and the targets are global loads whose latency, under the memory
+		// group's traffic, would otherwise sit in the middle of this group's dependent MMA / epilogue chain: the index is
+		// fetched one tile ahead, the targets at the top of the tile (the loss needs them three MMA stages later).
+		constexpr uint32_t N_TGT_PREFETCH = 4;
+		auto sample_of = [&](uint32_t tile) {
+			const uint32_t s = tile * TILE_M + row;
+			return p.perm ? __ldg(p.perm + s) : s;
+		};
+		uint32_t osample_next = blockIdx.x < n_tiles ? sample_of(blockIdx.x) : 0;
 		uint32_t k = 0;
 		for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
 			const uint32_t g = k & 1u, j = k >> 1;
 			const uint32_t enc_cur = s_enc + g * TILE_BYTES;
-			uint32_t osample = tile * TILE_M + row;
-			if (p.perm) osample = __ldg(p.perm + osample);
+			const uint32_t osample = osample_next;
+			float tgt[N_TGT_PREFETCH];
+			if (TRAIN) {
+#pragma unroll
+				for (uint32_t q = 0; q < N_TGT_PREFETCH; ++q) tgt[q] = q < p.n_out ? __ldg(p.targets + (size_t)osample * p.n_out + q) : 0.0f;
+			}
+			if (tile + gridDim.x < n_tiles) osample_next = sample_of(tile + gridDim.x);
+			if (tid == 0) WS_STAMP(0, k, 0);
 			mbar_wait(bar_enc_full + 8 * g, j & 1u);
+			if (tid == 0) WS_STAMP(0, k, 1);
 
 #pragma unroll 1
 			for (uint32_t b = 0; b < n_batches; ++b) {
+				if (tid == 0 && (b == 1 || b == NH + 1)) WS_STAMP(0, k, b == 1 ? 6 : 11);
+				if (tid == 0 && (b == 2 || b == NH + 2)) WS_STAMP(0, k, b == 2 ? 10 : 15);
 				stage_sync();
-				if (tid == 0) {
+				if (tid == 0 && b == NH + 1) WS_STAMP(0, k, 2);
+				if (tid == 0 && (b == 1 || b == NH + 1)) WS_STAMP(0, k, b == 1 ? 7 : 12);
+				if (warp == 0 && elect_one_sync()) {  // warp-uniform branch + one elected lane: operands stay in uniform registers
 					tc_fence_after_sync();
 					if (b < NH) {
 						const uint32_t a_tile = b == 0 ? enc_cur : s_h0 + (b - 1) * TILE_BYTES;
@@ -331,22 +381,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 						umma_commit(bar_enc_free + 8 * g);  // last reader of enc[g]: release it to the memory group
 					}
 					umma_commit(bar_mma);
+					if (b == 1 || b == NH + 1) WS_STAMP(0, k, b == 1 ? 8 : 13);
 				}
 				__syncwarp();
 				wait_mma();
+				if (tid == 0 && (b == 1 || b == NH + 1)) WS_STAMP(0, k, b == 1 ? 9 : 14);
 
 				// ---- epilogue of batch b: this thread owns row `row`, all 64 accumulator columns (two passes of 32)
 				if (b < NH) {
 					const uint32_t h_tile = s_h0 + b * TILE_BYTES;
+					// both halves of the accumulator row are requested before the single wait (one TMEM round trip, not two)
+					uint32_t racc[2][32];
+					tmem_ld_32x32b_x32(tmem_acc + lane_field, racc[0]);
+					tmem_ld_32x32b_x32(tmem_acc + lane_field + 32, racc[1]);
+					tmem_ld_wait();
 #pragma unroll
 					for (uint32_t half = 0; half < 2; ++half) {
-						uint32_t r[32];
-						tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
-						tmem_ld_wait();
+						const uint32_t(&r)[32] = racc[half];
 #pragma unroll
 						for (uint32_t c = 0; c < 4; ++c) {
-							const uint32_t v0 = act_pack(p.activation, r[c * 8 + 0], r[c * 8 + 1]), v1 = act_pack(p.activation, r[c * 8 + 2], r[c * 8 + 3]);
-							const uint32_t v2 = act_pack(p.activation, r[c * 8 + 4], r[c * 8 + 5]), v3 = act_pack(p.activation, r[c * 8 + 6], r[c * 8 + 7]);
+							const uint32_t v0 = act_pack(hid_act, r[c * 8 + 0], r[c * 8 + 1]), v1 = act_pack(hid_act, r[c * 8 + 2], r[c * 8 + 3]);
+							const uint32_t v2 = act_pack(hid_act, r[c * 8 + 4], r[c * 8 + 5]), v3 = act_pack(hid_act, r[c * 8 + 6], r[c * 8 + 7]);
 							st_shared_v4(h_tile + sw128(row, half * 4 + c), v0, v1, v2, v3);
 							if (p.dbg_hidden) *reinterpret_cast<uint4*>(p.dbg_hidden + ((size_t)b * p.batch_size + osample) * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
 						}
@@ -357,7 +412,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 					tmem_ld_wait();
 					__half y16[16];
 #pragma unroll
-					for (uint32_t q = 0; q < 16; ++q) y16[q] = act_fwd_h(p.output_activation, __float2half_rn(__uint_as_float(r[q])));
+					for (uint32_t q = 0; q < 16; ++q) y16[q] = act_fwd_h(out_act, __float2half_rn(__uint_as_float(r[q])));
 					if (p.out_fp16) {
 						uint4* dst = reinterpret_cast<uint4*>(p.out_fp16 + (size_t)osample * 16);
 						dst[0] = *reinterpret_cast<uint4*>(&y16[0]);
@@ -375,7 +430,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 							float gq = 0.0f;
 							if (q < p.n_out) {
 								const float pred = __half2float(y16[q]);
-								const float diff = pred - __ldg(p.targets + (size_t)osample * p.n_out + q);
+								const float diff = pred - (q < N_TGT_PREFETCH ? tgt[q] : __ldg(p.targets + (size_t)osample * p.n_out + q));
 								float value, grad;
 								if (p.loss_type == LOSS_RELATIVE_L2) {
 									const float psq = pred * pred + 0.01f;
@@ -390,7 +445,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 								if (p.loss_values) p.loss_values[(size_t)osample * p.n_out + q] = value;
 							}
 							// activation_backward_output (fully_fused_mlp.cu:755-759): dL/dy through the output activation, in fp16
-						dy[q] = act_bwd_h(p.output_activation, __float2half_rn(gq), y16[q]);
+						dy[q] = act_bwd_h(out_act, __float2half_rn(gq), y16[q]);
 						}
 						const uint4 lo = *reinterpret_cast<uint4*>(&dy[0]), hi = *reinterpret_cast<uint4*>(&dy[8]);
 						st_shared_v4(s_dy + sw128(row, 0), lo.x, lo.y, lo.z, lo.w);
@@ -405,17 +460,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 					// g overwrites h in place (see fused_step.cu)
 					const uint32_t l = 2 * NH + 1 - b;
 					const uint32_t h_tile = s_h0 + (l - 1) * TILE_BYTES;
+					uint32_t racc[2][32];
+					tmem_ld_32x32b_x32(tmem_acc + lane_field, racc[0]);
+					tmem_ld_32x32b_x32(tmem_acc + lane_field + 32, racc[1]);
+					tmem_ld_wait();
 #pragma unroll
 					for (uint32_t half = 0; half < 2; ++half) {
-						uint32_t r[32];
-						tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
-						tmem_ld_wait();
+						const uint32_t(&r)[32] = racc[half];
 #pragma unroll
 						for (uint32_t c = 0; c < 4; ++c) {
 							uint32_t f0, f1, f2, f3;
 							ld_shared_v4(h_tile + sw128(row, half * 4 + c), f0, f1, f2, f3);
-							const uint32_t v0 = act_bwd_pack(p.activation, r[c * 8 + 0], r[c * 8 + 1], f0), v1 = act_bwd_pack(p.activation, r[c * 8 + 2], r[c * 8 + 3], f1);
-							const uint32_t v2 = act_bwd_pack(p.activation, r[c * 8 + 4], r[c * 8 + 5], f2), v3 = act_bwd_pack(p.activation, r[c * 8 + 6], r[c * 8 + 7], f3);
+							const uint32_t v0 = act_bwd_pack(hid_act, r[c * 8 + 0], r[c * 8 + 1], f0), v1 = act_bwd_pack(hid_act, r[c * 8 + 2], r[c * 8 + 3], f1);
+							const uint32_t v2 = act_bwd_pack(hid_act, r[c * 8 + 4], r[c * 8 + 5], f2), v3 = act_bwd_pack(hid_act, r[c * 8 + 6], r[c * 8 + 7], f3);
 							st_shared_v4(h_tile + sw128(row, half * 4 + c), v0, v1, v2, v3);
 							if (p.dbg_grad_hidden) *reinterpret_cast<uint4*>(p.dbg_grad_hidden + ((size_t)(l - 1) * p.batch_size + osample) * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
 						}
@@ -424,12 +481,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 					// dL/d(encoded): round once to fp16 (fully_fused_mlp.cu:835) and park the row for the memory group
 					dw_started = true;
 					const uint32_t park_tile = s_park + g * TILE_BYTES;
+					if (tid == 0) WS_STAMP(0, k, 3);
 					if (j >= 1) mbar_wait(bar_park_free + 8 * g, (j - 1) & 1u);  // scatter of tile k-2 has consumed park[g]
+					if (tid == 0) WS_STAMP(0, k, 4);
+					uint32_t racc[2][32];
+					tmem_ld_32x32b_x32(tmem_acc + lane_field, racc[0]);
+					tmem_ld_32x32b_x32(tmem_acc + lane_field + 32, racc[1]);
+					tmem_ld_wait();
 #pragma unroll
 					for (uint32_t half = 0; half < 2; ++half) {
-						uint32_t r[32];
-						tmem_ld_32x32b_x32(tmem_acc + lane_field + half * 32, r);
-						tmem_ld_wait();
+						const uint32_t(&r)[32] = racc[half];
 #pragma unroll
 						for (uint32_t c = 0; c < 4; ++c) {
 							const uint32_t v0 = pack_half2(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1]));
@@ -442,6 +503,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 					}
 					__syncwarp();
 					if ((tid & 31u) == 0) mbar_arrive(bar_park_full + 8 * g);
+					if (tid == 0) WS_STAMP(0, k, 5);
 				}
 			}
 		}
@@ -502,9 +564,9 @@ size_t fused_ws_smem_bytes(uint32_t n_hidden_layers, bool train) {
 	return tiles * TILE_BYTES + n_hidden_layers * (WIDTH * 128) + 16 * 128 + 96 + MAX_LEVELS * sizeof(LevelInfo) + 1024 /* alignment slack */;
 }
 
-template <uint32_t D, bool TRAIN>
+template <uint32_t D, bool TRAIN, bool GENERIC>
 static cudaError_t launch_ws_impl(const FusedStepParams& p, uint32_t n_ctas, cudaStream_t stream) {
-	auto kernel = fused_ws_kernel<D, 2, TRAIN>;
+	auto kernel = fused_ws_kernel<D, 2, TRAIN, GENERIC>;
 	const size_t smem = fused_ws_smem_bytes(p.n_hidden_layers, TRAIN);
 	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (err != cudaSuccess) return err;
@@ -512,9 +574,15 @@ static cudaError_t launch_ws_impl(const FusedStepParams& p, uint32_t n_ctas, cud
 	return cudaGetLastError();
 }
 
+template <uint32_t D, bool TRAIN>
+static cudaError_t launch_ws_act(const FusedStepParams& p, uint32_t n_ctas, cudaStream_t stream) {
+	const bool generic = p.activation != ACT_RELU || p.output_activation != ACT_NONE;
+	return generic ? launch_ws_impl<D, TRAIN, true>(p, n_ctas, stream) : launch_ws_impl<D, TRAIN, false>(p, n_ctas, stream);
+}
+
 cudaError_t launch_fused_ws(const FusedStepParams& p, uint32_t n_pos_dims, bool train, uint32_t n_ctas, cudaStream_t stream) {
-	if (n_pos_dims == 3) return train ? launch_ws_impl<3, true>(p, n_ctas, stream) : launch_ws_impl<3, false>(p, n_ctas, stream);
-	if (n_pos_dims == 2) return train ? launch_ws_impl<2, true>(p, n_ctas, stream) : launch_ws_impl<2, false>(p, n_ctas, stream);
+	if (n_pos_dims == 3) return train ? launch_ws_act<3, true>(p, n_ctas, stream) : launch_ws_act<3, false>(p, n_ctas, stream);
+	if (n_pos_dims == 2) return train ? launch_ws_act<2, true>(p, n_ctas, stream) : launch_ws_act<2, false>(p, n_ctas, stream);
 	return cudaErrorInvalidValue;
 }
 

@@ -237,13 +237,26 @@ __device__ __forceinline__ void gather_pair_f16x2(const uint32_t* __restrict__ t
 	v1 = paired ? (odd ? slot.x : slot.y) : far;
 }
 
-// Scatter-add two fp16x2 addends of a corner pair: one 64-bit vector reduction when paired, else two 32-bit reductions
-// (red.global.add.noftz.f16x2 is what the reference's atomic_add_gmem(__half2) lowers to, vec.h:328-336).
+// Scatter-add two fp16x2 addends of a corner pair (red.global.add.noftz.f16x2 is what the reference's
+// atomic_add_gmem(__half2) lowers to, vec.h:328-336). The L2 retires a fixed number of reduction OPERATIONS per second
+// whatever their width (4, 8 and 16 bytes measure the same, scripts/experiments/red_bench.cu), so the pair goes out as ONE
+// operation whenever both entries lie in one aligned 16-byte group: a 64-bit reduction if they share an aligned slot
+// (x even), a 128-bit one with zero addends in the two other entries if they straddle the middle of a group (x % 4 == 1,
+// dense or hashed: idx0 ^ idx1 == 3). Adding +0 leaves the other entries unchanged. Otherwise two 32-bit reductions.
 __device__ __forceinline__ void scatter_pair_f16x2(uint32_t* __restrict__ table, uint32_t idx0, uint32_t idx1, bool paired, uint32_t a0, uint32_t a1) {
 	if (paired) {
 		const bool odd = idx0 & 1u;
 		const uint32_t lo = odd ? a1 : a0, hi = odd ? a0 : a1;
 		asm volatile("red.relaxed.gpu.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(table + (idx0 & ~1u)), "r"(lo), "r"(hi) : "memory");
+#ifndef TCNNB_NO_QUAD_RED
+	} else if ((idx0 ^ idx1) == 3u) {
+		const uint32_t p0 = idx0 & 3u;  // idx1 sits at p0 ^ 3
+		const uint32_t v0 = p0 == 0u ? a0 : (p0 == 3u ? a1 : 0u);
+		const uint32_t v1 = p0 == 1u ? a0 : (p0 == 2u ? a1 : 0u);
+		const uint32_t v2 = p0 == 2u ? a0 : (p0 == 1u ? a1 : 0u);
+		const uint32_t v3 = p0 == 3u ? a0 : (p0 == 0u ? a1 : 0u);
+		asm volatile("red.relaxed.gpu.global.add.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(table + (idx0 & ~3u)), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+#endif
 	} else {
 		asm volatile("red.relaxed.gpu.global.add.noftz.f16x2 [%0], %1;" ::"l"(table + idx0), "r"(a0) : "memory");
 		asm volatile("red.relaxed.gpu.global.add.noftz.f16x2 [%0], %1;" ::"l"(table + idx1), "r"(a1) : "memory");

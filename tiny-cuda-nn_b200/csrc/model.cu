@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -272,6 +273,7 @@ struct Model {
 	DeviceBuffer<uint32_t> param_steps;
 	DeviceBuffer<float> dw_accum;   // fp32 MLP weight-gradient accumulator
 	DeviceBuffer<float> scalars;    // [0] = loss sum
+	DeviceBuffer<long long> dbg_clock;  // TCNNB_CLOCKS=<file> in ablation builds: phase stamps of the last ws launch
 	DeviceBuffer<float> level_scales_dev;
 	bool mlp_grads_in_accum = false;
 
@@ -353,6 +355,12 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 	if (const char* e = std::getenv("TCNNB_ABLATE")) m.ablate = (uint32_t)std::atoi(e);
 	if (const char* e = std::getenv("TCNNB_BINNING")) m.binning = std::atoi(e) != 0;
 	if (const char* e = std::getenv("TCNNB_KERNEL")) m.warp_specialized = std::string(e) == "ws";
+#ifdef TCNNB_ENABLE_ABLATION
+	if (std::getenv("TCNNB_CLOCKS")) {
+		m.dbg_clock.resize((size_t)m.n_sms * 3 * 16 * 16);
+		m.dbg_clock.zero();
+	}
+#endif
 	m.n_in = n_in;
 	m.n_out = n_out;
 
@@ -518,6 +526,7 @@ static FusedStepParams make_params(Model& m, uint32_t batch, uint32_t loss_batch
 	p.dbg_dy = (__half*)m.taps.dL_doutput;
 	p.dbg_grad_hidden = (__half*)m.taps.grad_hidden;
 	p.dbg_denc = (__half*)m.taps.dL_dencoded;
+	p.dbg_clock = m.dbg_clock.n ? m.dbg_clock.ptr : nullptr;
 	return p;
 }
 
@@ -544,9 +553,16 @@ static void optimizer_step(Model& m, cudaStream_t stream) {
 
 static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_t loss_batch, const float* x, const float* y, bool run_optimizer) {
 	check_batch(batch);
-	// GradientMode::Overwrite: zero the grid gradient table (grid.h:865-867) and the loss accumulator.
-	TCNNB_CUDA_CHECK(cudaMemsetAsync(m.grads_fp16 + m.mlp.n_params, 0, sizeof(__half) * m.grid.n_params, stream));
-	TCNNB_CUDA_CHECK(cudaMemsetAsync(m.scalars.ptr, 0, sizeof(float), stream));
+	// GradientMode::Overwrite: zero the grid gradient table (grid.h:865-867) and the loss accumulator -- inside the binning pass
+	// when there is one, else as memsets.
+	__half* const grid_grads = m.grads_fp16 + m.mlp.n_params;
+	const size_t grid_grad_bytes = sizeof(__half) * m.grid.n_params;
+	const bool bin = m.binning && batch >= 16384;
+	const bool zero_in_binning = bin && (((uintptr_t)grid_grads | grid_grad_bytes) & 15u) == 0;
+	if (!zero_in_binning) {
+		TCNNB_CUDA_CHECK(cudaMemsetAsync(grid_grads, 0, grid_grad_bytes, stream));
+		TCNNB_CUDA_CHECK(cudaMemsetAsync(m.scalars.ptr, 0, sizeof(float), stream));
+	}
 	if (m.mlp_grads_in_accum) {
 		// a previous step left un-consumed weight gradients (run_optimizer == false twice in a row): Overwrite semantics
 		TCNNB_CUDA_CHECK(cudaMemsetAsync(m.dw_accum.ptr, 0, sizeof(float) * m.mlp.n_params, stream));
@@ -554,7 +570,7 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
 	FusedStepParams p = make_params(m, batch, loss_batch, x, y);
 	m.prof_mark(stream);
 	// Process the batch in (y, z)-column order: same sums, far fewer distinct memory sectors on the coarse levels (binning.cu).
-	if (m.binning && batch >= 16384) {
+	if (bin) {
 		const uint32_t log2_r = binning_log2_resolution(batch, m.grid.n_pos_dims);
 		m.bin_keys.resize(std::max(m.bin_keys.n, 2 * (size_t)batch));
 		m.bin_perm.resize(std::max(m.bin_perm.n, (size_t)batch));
@@ -565,7 +581,8 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
 				m.bin_hist.zero(stream);
 			}
 		}
-		TCNNB_CUDA_CHECK(launch_binning(stream, m.grid.n_pos_dims, batch, x, log2_r, m.bin_keys.ptr, m.bin_hist.ptr, m.bin_perm.ptr));
+		TCNNB_CUDA_CHECK(launch_binning(stream, m.grid.n_pos_dims, batch, x, log2_r, m.bin_keys.ptr, m.bin_hist.ptr, m.bin_perm.ptr, zero_in_binning ? grid_grads : nullptr,
+		                                zero_in_binning ? grid_grad_bytes : 0, zero_in_binning ? (float*)m.scalars.ptr : nullptr));
 		g_kernel_launches += 3;
 		p.perm = m.bin_perm.ptr;
 	}
@@ -702,7 +719,20 @@ int tcnnb_create_from_config(uint32_t n_input_dims, uint32_t n_output_dims, cons
 	TCNNB_API_END
 }
 
-void tcnnb_destroy(tcnnb_model* model) { delete model; }
+void tcnnb_destroy(tcnnb_model* model) {
+#ifdef TCNNB_ENABLE_ABLATION
+	if (model && model->impl.dbg_clock.n) {  // dump the phase stamps of the last ws launch
+		std::vector<long long> host(model->impl.dbg_clock.n);
+		if (cudaMemcpy(host.data(), model->impl.dbg_clock.ptr, host.size() * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+			if (FILE* f = std::fopen(std::getenv("TCNNB_CLOCKS"), "wb")) {
+				std::fwrite(host.data(), sizeof(long long), host.size(), f);
+				std::fclose(f);
+			}
+		}
+	}
+#endif
+	delete model;
+}
 
 uint64_t tcnnb_n_params(const tcnnb_model* m) { return m->impl.n_params; }
 uint64_t tcnnb_n_mlp_params(const tcnnb_model* m) { return m->impl.mlp.n_params; }

@@ -97,6 +97,20 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, ui
 		: "memory");
 }
 
+// One lane of a converged warp (elect.sync). With a warp-UNIFORM enclosing branch this lets the compiler keep the operands of the
+// tcgen05 instructions in uniform registers; under a `tid == 0` branch it wraps every UTCHMMA in an ELECT / R2UR loop instead.
+__device__ __forceinline__ bool elect_one_sync() {
+	uint32_t pred;
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"elect.sync _|p, 0xffffffff;\n"
+		"selp.u32 %0, 1, 0, p;\n"
+		"}\n"
+		: "=r"(pred));
+	return pred != 0;
+}
+
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
 	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -11,7 +11,8 @@ import json
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(os.path.dirname(_HERE), "libtcnn_b200.so")
+# TCNNB_LIB selects another build of the same library (profiling experiments use an ABLATION=1 build next to the product one)
+_LIB_PATH = os.environ.get("TCNNB_LIB") or os.path.join(os.path.dirname(_HERE), "libtcnn_b200.so")
 _lib = None
 
 
