@@ -17,7 +17,13 @@
 //                                enc_free[g]  (tcgen05.commit -> memory: last MMA that reads enc[g] has finished)
 //                                park_full[g] (MLP -> memory: dL/d(enc) of the tile parked)
 //                                park_free[g] (memory -> MLP: parked gradients consumed)
-// One persistent CTA per SM (640 threads), grid = #SMs.
+// Two shapes of the same kernel (template parameter SUBS):
+//   SUBS = 2: one persistent CTA per SM, 640 threads (4 MLP warps + two memory sub-groups), grid = #SMs.
+//   SUBS = 1: TWO persistent CTAs per SM, 384 threads each (4 MLP warps + one memory sub-group that serves every tile of the
+//             CTA, alternating between the two enc buffers). The phase timeline (scripts/ws_timeline.py) shows the single MLP
+//             chain of the SUBS = 2 shape to be the critical path while the memory warps wait ~15 % of the time; two CTAs give
+//             the SM two independent MLP chains. To fit two CTAs in shared memory the parked dL/d(enc) rows live in the unused
+//             upper half of the enc tiles (needs an encoding of at most 32 features) instead of in tiles of their own.
 #include "common.cuh"
 #include "fused_common.cuh"
 #include "fused_step.h"
@@ -45,7 +51,7 @@ namespace {
 
 constexpr uint32_t WS_MLP_THREADS = 128;
 constexpr uint32_t WS_SUB_THREADS = 256;
-constexpr uint32_t WS_THREADS = WS_MLP_THREADS + 2 * WS_SUB_THREADS;  // 640
+__host__ __device__ constexpr uint32_t ws_threads(uint32_t subs) { return WS_MLP_THREADS + subs * WS_SUB_THREADS; }  // 640 / 384
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -57,8 +63,9 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads) 
 
 }  // namespace
 
-template <uint32_t D, uint32_t F, bool TRAIN, bool GENERIC_ACT>
-__global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStepParams p) {
+template <uint32_t D, uint32_t F, bool TRAIN, bool GENERIC_ACT, uint32_t SUBS>
+__global__ void __launch_bounds__(ws_threads(SUBS), SUBS == 1 ? 2 : 1) fused_ws_kernel(const FusedStepParams p) {
+	constexpr uint32_t WS_THREADS = ws_threads(SUBS);
 	// ReLU hidden / linear output (the reference's default and the benchmark configuration) fold to the packed fast path at compile time
 	const uint32_t hid_act = GENERIC_ACT ? p.activation : (uint32_t)ACT_RELU;
 	const uint32_t out_act = GENERIC_ACT ? p.output_activation : (uint32_t)ACT_NONE;
@@ -69,29 +76,38 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 	const uint32_t NH = p.n_hidden_layers;
 	const uint32_t in_w = p.grid.padded_width;
 
-	// ---- shared memory: [ enc_0 | enc_1 | h_0 .. h_{NH-1} | dy | park_0 | park_1 | W_0 .. W_{NH-1} | W_out ] barriers, level table
+	// ---- shared memory: [ enc_0 .. enc_{NE-1} | h_0 .. h_{NH-1} | dy | park_0 | park_1 | W_0 .. W_{NH-1} | W_out ] barriers
 	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 	const uint32_t s_enc = smem_base;
-	const uint32_t s_h0 = s_enc + 2 * TILE_BYTES;
+	// enc buffers: tile k uses buffer k % NE. Four of them in the one-CTA training shape: a sub-group then gathers its next
+	// tile without waiting for the MLP group to finish with its previous one (the enc tile is read until the last
+	// weight-gradient MMA of the tile), which takes the gather off the MLP chain's critical path.
+	constexpr uint32_t NE = (SUBS == 2 && TRAIN) ? 4u : 2u;
+	const uint32_t s_h0 = s_enc + NE * TILE_BYTES;
 	const uint32_t s_dy = s_h0 + NH * TILE_BYTES;
 	const uint32_t s_park = s_dy + (TRAIN ? TILE_BYTES : 0);
-	const uint32_t s_w0 = s_park + (TRAIN ? 2 * TILE_BYTES : 0);
+	const uint32_t s_w0 = s_park + (TRAIN && SUBS == 2 ? 2 * TILE_BYTES : 0);
+	// parked dL/d(enc) row `row`, 16-byte chunk `chunk` of buffer g: own tiles (SUBS == 2) or chunks 4..7 of enc[g] (SUBS == 1)
+	auto park_addr = [&](uint32_t g, uint32_t row, uint32_t chunk) {
+		return SUBS == 2 ? s_park + g * TILE_BYTES + sw128(row, chunk) : s_enc + g * TILE_BYTES + sw128(row, 4u + chunk);
+	};
 	const uint32_t s_wout = s_w0 + NH * (WIDTH * 128);
 	const uint32_t s_bars = s_wout + 16 * 128;  // 9 mbarriers
 	const uint32_t bar_mma = s_bars;
-	const uint32_t bar_enc_full = s_bars + 8;    // [2]
-	const uint32_t bar_enc_free = s_bars + 24;   // [2]
-	const uint32_t bar_park_full = s_bars + 40;  // [2]
-	const uint32_t bar_park_free = s_bars + 56;  // [2]
-	const uint32_t s_tmem_slot = s_bars + 72;
-	const uint32_t s_levels = s_bars + 80;
+	const uint32_t bar_enc_full = s_bars + 8;    // [4]
+	const uint32_t bar_enc_free = s_bars + 40;   // [4]
+	const uint32_t bar_park_full = s_bars + 72;  // [2]
+	const uint32_t bar_park_free = s_bars + 88;  // [2]
+	const uint32_t s_tmem_slot = s_bars + 104;
 
 	const uint32_t tmem_cols = TRAIN ? ((NH + 2) * 64 <= 256 ? 256u : 512u) : 64u;
 	if (tid == 0) {
 		mbar_init(bar_mma, 1);
+		for (uint32_t e = 0; e < NE; ++e) {
+			mbar_init(bar_enc_full + 8 * e, WS_SUB_THREADS / 32);   // one arrival per memory warp
+			mbar_init(bar_enc_free + 8 * e, 1);                      // tcgen05.commit
+		}
 		for (uint32_t g = 0; g < 2; ++g) {
-			mbar_init(bar_enc_full + 8 * g, WS_SUB_THREADS / 32);   // one arrival per memory warp
-			mbar_init(bar_enc_free + 8 * g, 1);                      // tcgen05.commit
 			mbar_init(bar_park_full + 8 * g, WS_MLP_THREADS / 32);  // one arrival per MLP warp
 			mbar_init(bar_park_free + 8 * g, WS_SUB_THREADS / 32);
 		}
@@ -102,10 +118,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 		tmem_alloc(s_tmem_slot, tmem_cols);
 		tmem_relinquish();
 	}
-	for (uint32_t i = tid; i < p.grid.n_levels * (uint32_t)(sizeof(LevelInfo) / 4); i += WS_THREADS) {
-		const uint32_t v = reinterpret_cast<const uint32_t*>(p.grid.levels)[i];
-		asm volatile("st.shared.b32 [%0], %1;" ::"r"(s_levels + i * 4), "r"(v) : "memory");
-	}
+
 	{
 		// W_l [out][in] row-major -> 128-byte tile rows (K-major, SWIZZLE_128B). Rows / columns beyond the network's width
 		// and the encoding's width are zero, which makes a 16- or 32-wide network an exact sub-problem of the 64-wide tiles.
@@ -139,12 +152,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 	if (warp >= WS_MLP_THREADS / 32) {
 		// =========================================================================================== memory group
 		const uint32_t mt = tid - WS_MLP_THREADS;
-		const uint32_t g = mt / WS_SUB_THREADS;     // sub-group == enc / park buffer it owns
+		const uint32_t sub = mt / WS_SUB_THREADS;   // sub-group; with SUBS == 2 it owns the tiles (and buffers) of parity `sub`
 		const uint32_t lt = mt % WS_SUB_THREADS;
 		const uint32_t row = lt & 127u;
 		const uint32_t hsel = lt >> 7;
-		const uint32_t enc_tile = s_enc + g * TILE_BYTES;
-		const uint32_t park_tile = s_park + g * TILE_BYTES;
 
 		constexpr uint32_t LEVELS_PER_CHUNK = 8 / F;
 		const uint32_t n_chunks = in_w / 8;
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 #pragma unroll
 		for (uint32_t d = 0; d < D; ++d) x_prev[d] = x_cur[d] = 0.0f;
 
-		auto scatter_prev = [&]() {
+		auto scatter_prev = [&](uint32_t gp) {
 #pragma unroll 1
 			for (uint32_t level = level_begin; level < level_end; ++level) {
 				const LevelInfo& lv = load_level(level);
@@ -170,7 +181,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 				level_corners<D>(lv, x_prev, p.grid.interpolation, lc);
 				uint32_t gbits;
 				const uint32_t feat = level * F;
-				asm volatile("ld.shared.b32 %0, [%1];" : "=r"(gbits) : "r"(park_tile + sw128(row, feat >> 3) + (feat & 7u) * 2u));
+				asm volatile("ld.shared.b32 %0, [%1];" : "=r"(gbits) : "r"(park_addr(gp, row, feat >> 3) + (feat & 7u) * 2u));
 				const __half2 grad = *reinterpret_cast<const __half2*>(&gbits);
 				uint32_t* __restrict__ ltab = reinterpret_cast<uint32_t*>(grad_table + (size_t)lv.offset * F);
 #pragma unroll
@@ -190,14 +201,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 			const uint32_t s = tile * TILE_M + row;
 			return p.perm ? __ldg(p.perm + s) : s;
 		};
-		const uint32_t tile_first = blockIdx.x + g * gridDim.x, tile_stride = 2 * gridDim.x;
+		// tiles of this sub-group: k = sub, sub + 2, ... (SUBS == 2) or every tile of the CTA (SUBS == 1)
+		const uint32_t k_first = SUBS == 2 ? sub : 0u, k_step = SUBS;
+		const uint32_t tile_first = blockIdx.x + k_first * gridDim.x, tile_stride = k_step * gridDim.x;
 		uint32_t os_next = tile_first < n_tiles ? sample_of(tile_first) : 0;
 		uint32_t os_next2 = tile_first + tile_stride < n_tiles ? sample_of(tile_first + tile_stride) : 0;
 		float x_next[D];
 #pragma unroll
 		for (uint32_t d = 0; d < D; ++d) x_next[d] = tile_first < n_tiles ? __ldg(p.positions + (size_t)os_next * D + d) : 0.0f;
-		uint32_t j = 0;  // this sub-group's tile counter
-		for (uint32_t k = g, tile = blockIdx.x + g * gridDim.x; tile < n_tiles; k += 2, tile += 2 * gridDim.x, ++j) {
+		bool have_prev = false;
+		uint32_t k_prev = 0;
+		for (uint32_t k = k_first, tile = tile_first; tile < n_tiles; k += k_step, tile += tile_stride) {
+			const uint32_t e = k % NE, je = k / NE;  // enc buffer and its use count
+			const uint32_t enc_tile = s_enc + e * TILE_BYTES;
 			// ---- position of this thread's sample (fetched one tile ahead, its index two tiles ahead: no dependent global
 			//      load latency in front of the gather)
 			os_cur = os_next;
@@ -210,12 +226,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 			}
 			if (tile + 2 * tile_stride < n_tiles) os_next2 = sample_of(tile + 2 * tile_stride);
 
-			// ---- gather tile k into enc[g] once the MMAs of tile k-2 have released it
-			if (lt == 0) WS_STAMP(1 + g, k, 0);
-			if (j >= 1) mbar_wait(bar_enc_free + 8 * g, (j - 1) & 1u);
-			if (lt == 0) WS_STAMP(1 + g, k, 1);
+			// ---- gather tile k into enc[k % NE] once the MMAs of tile k - NE have released it
+			if (lt == 0) WS_STAMP(1 + sub, k, 0);
+			if (je >= 1) mbar_wait(bar_enc_free + 8 * e, (je - 1) & 1u);
+			if (lt == 0) WS_STAMP(1 + sub, k, 1);
+			// zero this thread's half of the row (padding features are zero, grid.h:759-766). With SUBS == 1 the upper half of
+			// the tile holds parked gradients instead: the forward MMA reads only the first in_w columns, and what the
+			// weight-gradient MMA makes of the rest lands in accumulator columns that are never flushed.
 #pragma unroll
-			for (uint32_t c = 0; c < 4; ++c) {  // zero this thread's half of the row (padding features are zero, grid.h:759-766)
+			for (uint32_t c = 0; SUBS == 2 && c < 4; ++c) {
 				const uint32_t chunk = c < n_chunks / 2 ? hsel * (n_chunks / 2) + c : n_chunks + hsel * ((8 - n_chunks) / 2) + (c - n_chunks / 2);
 				st_shared_v4(enc_tile + sw128(row, chunk), 0, 0, 0, 0);
 			}
@@ -270,24 +289,28 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 			}
 			fence_proxy_async_smem();  // the tile is read by tcgen05.mma (async proxy)
 			__syncwarp();
-			if ((tid & 31u) == 0) mbar_arrive(bar_enc_full + 8 * g);
-			if (lt == 0) WS_STAMP(1 + g, k, 2);
+			if ((tid & 31u) == 0) mbar_arrive(bar_enc_full + 8 * e);
+			if (lt == 0) WS_STAMP(1 + sub, k, 2);
 
-			// ---- scatter the previous tile of this sub-group (k-2) while the MLP group chews on tile k-1 / k
-			if (TRAIN && j >= 1) {
-				mbar_wait(bar_park_full + 8 * g, (j - 1) & 1u);
-				if (lt == 0) WS_STAMP(1 + g, k, 3);
-				scatter_prev();
+			// ---- scatter the previous tile of this sub-group while the MLP group chews on the tiles in between
+			if (TRAIN && have_prev) {
+				const uint32_t gp = k_prev & 1u, jp = k_prev >> 1;
+				mbar_wait(bar_park_full + 8 * gp, jp & 1u);
+				if (lt == 0) WS_STAMP(1 + sub, k, 3);
+				scatter_prev(gp);
 				__syncwarp();
-				if ((tid & 31u) == 0) mbar_arrive(bar_park_free + 8 * g);
-				if (lt == 0) WS_STAMP(1 + g, k, 4);
+				if ((tid & 31u) == 0) mbar_arrive(bar_park_free + 8 * gp);
+				if (lt == 0) WS_STAMP(1 + sub, k, 4);
 			}
 #pragma unroll
 			for (uint32_t d = 0; d < D; ++d) x_prev[d] = x_cur[d];
+			have_prev = true;
+			k_prev = k;
 		}
-		if (TRAIN && j >= 1) {  // drain: the last tile of this sub-group
-			mbar_wait(bar_park_full + 8 * g, (j - 1) & 1u);
-			scatter_prev();
+		if (TRAIN && have_prev) {  // drain: the last tile of this sub-group
+			const uint32_t gp = k_prev & 1u, jp = k_prev >> 1;
+			mbar_wait(bar_park_full + 8 * gp, jp & 1u);
+			scatter_prev(gp);
 		}
 	} else {
 		// =========================================================================================== MLP group
@@ -329,7 +352,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 		uint32_t k = 0;
 		for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
 			const uint32_t g = k & 1u, j = k >> 1;
-			const uint32_t enc_cur = s_enc + g * TILE_BYTES;
+			const uint32_t e = k % NE, je = k / NE;
+			const uint32_t enc_cur = s_enc + e * TILE_BYTES;
 			const uint32_t osample = osample_next;
 			float tgt[N_TGT_PREFETCH];
 			if (TRAIN) {
@@ -338,7 +362,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 			}
 			if (tile + gridDim.x < n_tiles) osample_next = sample_of(tile + gridDim.x);
 			if (tid == 0) WS_STAMP(0, k, 0);
-			mbar_wait(bar_enc_full + 8 * g, j & 1u);
+			mbar_wait(bar_enc_full + 8 * e, je & 1u);
 			if (tid == 0) WS_STAMP(0, k, 1);
 
 #pragma unroll 1
@@ -355,7 +379,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 						const uint32_t b_tile = s_w0 + b * (WIDTH * 128);
 						const uint32_t ksteps = b == 0 ? in_w / 16 : WIDTH / 16;
 						for (uint32_t jj = 0; jj < ksteps; ++jj) umma_f16_ss(tmem_acc, kmaj(a_tile, jj), kmaj(b_tile, jj), IDESC_FWD_N64, jj > 0);
-						if (!TRAIN && b == 0) umma_commit(bar_enc_free + 8 * g);  // inference: L0 is the only reader of enc
+						if (!TRAIN && b == 0) umma_commit(bar_enc_free + 8 * e);  // inference: L0 is the only reader of enc
 					} else if (b == NH) {
 						const uint32_t a_tile = s_h0 + (NH - 1) * TILE_BYTES;
 						for (uint32_t jj = 0; jj < WIDTH / 16; ++jj) umma_f16_ss(tmem_acc, kmaj(a_tile, jj), kmaj(s_wout, jj), IDESC_FWD_N16, jj > 0);
@@ -378,7 +402,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 						for (uint32_t jj = 0; jj < WIDTH / 16; ++jj) umma_f16_ss(tmem_acc, kmaj(g_tile, jj), mnmaj(s_w0, jj), IDESC_DGRAD, jj > 0);
 						const uint32_t dw = tmem_base + 64u;
 						for (uint32_t jj = 0; jj < TILE_M / 16; ++jj) umma_f16_ss(dw, mnmaj(g_tile, jj), mnmaj(enc_cur, jj), IDESC_WGRAD, dw_started || jj > 0);
-						umma_commit(bar_enc_free + 8 * g);  // last reader of enc[g]: release it to the memory group
+						umma_commit(bar_enc_free + 8 * e);  // last reader of this enc buffer: release it to the memory group
 					}
 					umma_commit(bar_mma);
 					if (b == 1 || b == NH + 1) WS_STAMP(0, k, b == 1 ? 8 : 13);
@@ -480,7 +504,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 				} else {
 					// dL/d(encoded): round once to fp16 (fully_fused_mlp.cu:835) and park the row for the memory group
 					dw_started = true;
-					const uint32_t park_tile = s_park + g * TILE_BYTES;
 					if (tid == 0) WS_STAMP(0, k, 3);
 					if (j >= 1) mbar_wait(bar_park_free + 8 * g, (j - 1) & 1u);  // scatter of tile k-2 has consumed park[g]
 					if (tid == 0) WS_STAMP(0, k, 4);
@@ -497,7 +520,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 							const uint32_t v1 = pack_half2(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3]));
 							const uint32_t v2 = pack_half2(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5]));
 							const uint32_t v3 = pack_half2(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7]));
-							st_shared_v4(park_tile + sw128(row, half * 4 + c), v0, v1, v2, v3);
+							if ((half * 4 + c) * 8 < in_w) st_shared_v4(park_addr(g, row, half * 4 + c), v0, v1, v2, v3);
 							if (p.dbg_denc) *reinterpret_cast<uint4*>(p.dbg_denc + (size_t)osample * 64 + (half * 4 + c) * 8) = make_uint4(v0, v1, v2, v3);
 						}
 					}
@@ -559,30 +582,41 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-size_t fused_ws_smem_bytes(uint32_t n_hidden_layers, bool train) {
-	const size_t tiles = 2 + n_hidden_layers + (train ? 3 : 0);
-	return tiles * TILE_BYTES + n_hidden_layers * (WIDTH * 128) + 16 * 128 + 96 + MAX_LEVELS * sizeof(LevelInfo) + 1024 /* alignment slack */;
+size_t fused_ws_smem_bytes(uint32_t n_hidden_layers, bool train, uint32_t subs) {
+	const size_t enc_tiles = (subs == 2 && train) ? 4 : 2;
+	const size_t tiles = enc_tiles + n_hidden_layers + (train ? (subs == 2 ? 3 : 1) : 0);
+	return tiles * TILE_BYTES + n_hidden_layers * (WIDTH * 128) + 16 * 128 + 128 /* barriers, TMEM slot */ + 1024 /* alignment slack */;
 }
 
-template <uint32_t D, bool TRAIN, bool GENERIC>
+// Two CTAs per SM (SUBS == 1): training only, parked gradients must fit the spare half of the enc tiles, two CTAs must fit
+// the SM's shared memory (227 KB) and tensor memory (2 x 256 columns).
+bool fused_ws_two_ctas_ok(uint32_t n_hidden_layers, uint32_t enc_width, bool train) {
+	return train && enc_width <= 32 && (n_hidden_layers + 2) * 64 <= 256 && 2 * (fused_ws_smem_bytes(n_hidden_layers, true, 1) + 1024) <= 227 * 1024;
+}
+
+template <uint32_t D, bool TRAIN, bool GENERIC, uint32_t SUBS>
 static cudaError_t launch_ws_impl(const FusedStepParams& p, uint32_t n_ctas, cudaStream_t stream) {
-	auto kernel = fused_ws_kernel<D, 2, TRAIN, GENERIC>;
-	const size_t smem = fused_ws_smem_bytes(p.n_hidden_layers, TRAIN);
+	auto kernel = fused_ws_kernel<D, 2, TRAIN, GENERIC, SUBS>;
+	const size_t smem = fused_ws_smem_bytes(p.n_hidden_layers, TRAIN, SUBS);
 	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (err != cudaSuccess) return err;
-	kernel<<<n_ctas, WS_THREADS, smem, stream>>>(p);
+	kernel<<<n_ctas, ws_threads(SUBS), smem, stream>>>(p);
 	return cudaGetLastError();
 }
 
 template <uint32_t D, bool TRAIN>
-static cudaError_t launch_ws_act(const FusedStepParams& p, uint32_t n_ctas, cudaStream_t stream) {
+static cudaError_t launch_ws_act(const FusedStepParams& p, uint32_t n_ctas, uint32_t subs, cudaStream_t stream) {
 	const bool generic = p.activation != ACT_RELU || p.output_activation != ACT_NONE;
-	return generic ? launch_ws_impl<D, TRAIN, true>(p, n_ctas, stream) : launch_ws_impl<D, TRAIN, false>(p, n_ctas, stream);
+	if (TRAIN && subs == 1) {
+		return generic ? launch_ws_impl<D, TRAIN, true, TRAIN ? 1 : 2>(p, n_ctas, stream) : launch_ws_impl<D, TRAIN, false, TRAIN ? 1 : 2>(p, n_ctas, stream);
+	}
+	return generic ? launch_ws_impl<D, TRAIN, true, 2>(p, n_ctas, stream) : launch_ws_impl<D, TRAIN, false, 2>(p, n_ctas, stream);
 }
 
-cudaError_t launch_fused_ws(const FusedStepParams& p, uint32_t n_pos_dims, bool train, uint32_t n_ctas, cudaStream_t stream) {
-	if (n_pos_dims == 3) return train ? launch_ws_act<3, true>(p, n_ctas, stream) : launch_ws_act<3, false>(p, n_ctas, stream);
-	if (n_pos_dims == 2) return train ? launch_ws_act<2, true>(p, n_ctas, stream) : launch_ws_act<2, false>(p, n_ctas, stream);
+cudaError_t launch_fused_ws(const FusedStepParams& p, uint32_t n_pos_dims, bool train, uint32_t n_ctas, uint32_t subs, cudaStream_t stream) {
+	if (subs == 1 && !fused_ws_two_ctas_ok(p.n_hidden_layers, p.grid.padded_width, train)) return cudaErrorInvalidValue;
+	if (n_pos_dims == 3) return train ? launch_ws_act<3, true>(p, n_ctas, subs, stream) : launch_ws_act<3, false>(p, n_ctas, subs, stream);
+	if (n_pos_dims == 2) return train ? launch_ws_act<2, true>(p, n_ctas, subs, stream) : launch_ws_act<2, false>(p, n_ctas, subs, stream);
 	return cudaErrorInvalidValue;
 }
 

@@ -242,13 +242,13 @@ __device__ __forceinline__ void gather_pair_f16x2(const uint32_t* __restrict__ t
 // whatever their width (4, 8 and 16 bytes measure the same, scripts/experiments/red_bench.cu), so the pair goes out as ONE
 // operation whenever both entries lie in one aligned 16-byte group: a 64-bit reduction if they share an aligned slot
 // (x even), a 128-bit one with zero addends in the two other entries if they straddle the middle of a group (x % 4 == 1,
-// dense or hashed: idx0 ^ idx1 == 3). Adding +0 leaves the other entries unchanged. Otherwise two 32-bit reductions.
+// dense or hashed: idx0 ^ idx1 == 3; adding +0 leaves the other entries unchanged). Otherwise two 32-bit reductions.
+// (Sending the x-even case through the 128-bit form as well -- two shapes instead of three -- measured 2 % slower.)
 __device__ __forceinline__ void scatter_pair_f16x2(uint32_t* __restrict__ table, uint32_t idx0, uint32_t idx1, bool paired, uint32_t a0, uint32_t a1) {
 	if (paired) {
 		const bool odd = idx0 & 1u;
 		const uint32_t lo = odd ? a1 : a0, hi = odd ? a0 : a1;
 		asm volatile("red.relaxed.gpu.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(table + (idx0 & ~1u)), "r"(lo), "r"(hi) : "memory");
-#ifndef TCNNB_NO_QUAD_RED
 	} else if ((idx0 ^ idx1) == 3u) {
 		const uint32_t p0 = idx0 & 3u;  // idx1 sits at p0 ^ 3
 		const uint32_t v0 = p0 == 0u ? a0 : (p0 == 3u ? a1 : 0u);
@@ -256,7 +256,6 @@ __device__ __forceinline__ void scatter_pair_f16x2(uint32_t* __restrict__ table,
 		const uint32_t v2 = p0 == 2u ? a0 : (p0 == 1u ? a1 : 0u);
 		const uint32_t v3 = p0 == 3u ? a0 : (p0 == 0u ? a1 : 0u);
 		asm volatile("red.relaxed.gpu.global.add.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(table + (idx0 & ~3u)), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
-#endif
 	} else {
 		asm volatile("red.relaxed.gpu.global.add.noftz.f16x2 [%0], %1;" ::"l"(table + idx0), "r"(a0) : "memory");
 		asm volatile("red.relaxed.gpu.global.add.noftz.f16x2 [%0], %1;" ::"l"(table + idx1), "r"(a1) : "memory");

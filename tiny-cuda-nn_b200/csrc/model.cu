@@ -279,6 +279,7 @@ struct Model {
 
 	// spatial binning scratch (binning.cu): sorted copies of the batch + permutation
 	bool binning = true;  // TCNNB_BINNING=0 disables
+	uint32_t ws_subs_override = 0;  // TCNNB_WS_SUBS
 	bool warp_specialized = true;   // fused_ws.cu by default; TCNNB_KERNEL=sync selects the bulk-synchronous fused_step.cu
 	DeviceBuffer<uint32_t> bin_keys, bin_hist, bin_perm;
 
@@ -355,9 +356,10 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 	if (const char* e = std::getenv("TCNNB_ABLATE")) m.ablate = (uint32_t)std::atoi(e);
 	if (const char* e = std::getenv("TCNNB_BINNING")) m.binning = std::atoi(e) != 0;
 	if (const char* e = std::getenv("TCNNB_KERNEL")) m.warp_specialized = std::string(e) == "ws";
+	if (const char* e = std::getenv("TCNNB_WS_SUBS")) m.ws_subs_override = (uint32_t)std::atoi(e);
 #ifdef TCNNB_ENABLE_ABLATION
 	if (std::getenv("TCNNB_CLOCKS")) {
-		m.dbg_clock.resize((size_t)m.n_sms * 3 * 16 * 16);
+		m.dbg_clock.resize((size_t)2 * m.n_sms * 3 * 16 * 16);
 		m.dbg_clock.zero();
 	}
 #endif
@@ -588,7 +590,10 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
 	}
 	m.prof_mark(stream);
 	if (m.warp_specialized && m.mlp.n_hidden_layers <= 4) {
-		TCNNB_CUDA_CHECK(launch_fused_ws(p, m.grid.n_pos_dims, true, std::min(batch / TILE_M, (uint32_t)m.n_sms), stream));
+		// one 640-thread CTA per SM; TCNNB_WS_SUBS=1 selects the two-CTAs-per-SM shape where it fits (measured slower on the
+		// headline configuration: 0.265 vs 0.213 ms)
+		const uint32_t subs = m.ws_subs_override == 1 && fused_ws_two_ctas_ok(m.mlp.n_hidden_layers, m.grid.padded_width, true) ? 1u : 2u;
+		TCNNB_CUDA_CHECK(launch_fused_ws(p, m.grid.n_pos_dims, true, std::min(batch / TILE_M, (subs == 1 ? 2u : 1u) * (uint32_t)m.n_sms), subs, stream));
 	} else {
 		TCNNB_CUDA_CHECK(launch_fused_step(p, m.grid.n_pos_dims, true, fused_grid_size(m, batch), stream));
 	}
