@@ -52,6 +52,33 @@ class ClockSampler:
         self.thread = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
+        try:
+            self.run_nvml()
+        except Exception:  # noqa: BLE001 -- no NVML binding: poll nvidia-smi (slow, a few samples per run)
+            self.run_smi()
+
+    def run_nvml(self):
+        import pynvml as nv
+
+        nv.nvmlInit()
+        # CUDA_VISIBLE_DEVICES-relative index -> NVML index
+        idx = self.index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis and all(t.strip().isdigit() for t in vis.split(",")):
+            idx = int(vis.split(",")[self.index])
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop.is_set():
+            self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), max_mhz))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for n, b in bits.items():
+                if r & b:
+                    self.reasons.add(n)
+            self.stop.wait(0.002)
+
+    def run_smi(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop.is_set():
@@ -146,6 +173,15 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        return {"kernel": t["kernel"], "bytes": t["dram_bytes_read_per_launch"] + t["dram_bytes_write_per_launch"]}
+    except Exception:  # noqa: BLE001
+        return {}
+
+
 def run_own(args):
     import numpy as np
     import torch
@@ -178,7 +214,9 @@ def run_own(args):
         ys.append(yh[-1].cuda())
     from tcnn_b200.dp import DataParallelTrainer
 
-    dp = DataParallelTrainer(trainer)  # world == 1: plain training_step; else shard step + 2 all-reduces + replicated Adam
+    # world == 1: plain training_step; else shard step + reduce-scatter of the table gradients + Adam on the rank's own table
+    # slice + all-gather of the updated fp16 slices (TCNNB_DP_REPLICATED=1: all-reduce + full Adam on every replica)
+    dp = DataParallelTrainer(trainer, shard_optimizer=os.environ.get("TCNNB_DP_REPLICATED", "0") != "1")
     stream = torch.cuda.current_stream()
 
     def step(i):
@@ -216,11 +254,22 @@ def run_own(args):
     e2e_steps = max(3, min(args.steps, 20))
     xn = [t.numpy() for t in xh]
     yn = [t.numpy() for t in yh]
-    model.training_step_host(xn[0], yn[0])
+    x_dev, y_dev = torch.empty_like(xs[0]), torch.empty_like(ys[0])
+
+    def e2e_step(i):
+        if world == 1:
+            return model.training_step_host(xn[i % pool], yn[i % pool])  # C ABI: H2D of inputs + targets, step, D2H of the loss
+        # data-parallel public API: pinned host shard -> device, sharded step, global loss back on the host
+        x_dev.copy_(xh[i % pool], non_blocking=True)
+        y_dev.copy_(yh[i % pool], non_blocking=True)
+        dp.training_step(x_dev, y_dev)
+        return dp.loss()
+
+    e2e_step(0)
     sync_all()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        model.training_step_host(xn[i % pool], yn[i % pool])
+        e2e_step(i)
     sync_all()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -236,18 +285,19 @@ def run_own(args):
         binning_ms = prof["binning_ms_total"] / n_prof
         achieved = FUSED_BYTES_PER_SAMPLE * BATCH / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else 0.0
         ms_per_step = ms / args.steps
+        traffic = ncu_traffic()
         line = {
             "metric": METRIC, "value": global_batch * args.steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": global_batch, "parallelism": f"dp{world}",
+            "config": {"workload": WORKLOAD, "global_batch": global_batch, "parallelism": f"dp{world}" + ("" if world == 1 else ("-zero1" if dp.shard_optimizer else "-replicated")),
                        "l2": "per-step working set (tables+optimizer state ~770 MB) exceeds the 126 MB L2; 4 rotating input batches; no explicit flush"},
             "clocks": cs.summary(),
             "e2e": {"value": global_batch * e2e_steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": BATCH * (N_IN + N_OUT) * 4, "d2h_bytes_per_step": 4,
-                    "steps": e2e_steps, "api": "tcnnb_training_step_host (C ABI, host buffers)"},
+                    "steps": e2e_steps, "api": "tcnnb_training_step_host (C ABI, host buffers)" if world == 1 else "DataParallelTrainer.training_step on pinned host shards + loss()"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "fused_step_kernel<3,2,true>", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel_ms": fused_ms, "optimizer_kernel_ms": adam_ms, "binning_kernels_ms": binning_ms,
+            "roofline": {"bound": "hbm", "kernel": traffic.get("kernel", "fused_ws_kernel"), "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic.get("bytes"), "traffic_unit": "B/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "kernel_ms": fused_ms, "optimizer_kernel_ms": adam_ms, "binning_kernels_ms": binning_ms,
                          "optimizer_achieved_gbs": ADAM_BYTES_PER_PARAM * model.n_params / (adam_ms * 1e-3) / 1e9 if adam_ms > 0 else None,
                          "step_share": fused_ms / ms_per_step if ms_per_step > 0 else None},
             "final_loss": final_loss,

@@ -73,6 +73,10 @@ int tcnnb_training_step(tcnnb_model* m, tcnnb_stream stream, uint32_t batch_size
 int tcnnb_training_step_shard(tcnnb_model* m, tcnnb_stream stream, uint32_t shard_batch_size, uint32_t global_batch_size, const float* input_dev, const float* target_dev, int run_optimizer);
 /* trainer->optimizer_step(stream, loss_scale) (trainer.h:155-157): Adam on the current gradient buffers. */
 int tcnnb_optimizer_step(tcnnb_model* m, tcnnb_stream stream);
+/* The same optimizer step restricted to the parameter ranges [begins[r], begins[r] + counts[r]) (adam.h:48-129 is element-wise,
+ * so a range is the reference kernel launched on a sub-span). Used by the sharded-optimizer data-parallel trainer: every rank
+ * updates the network weights (a range starting at 0 that covers all of them) and its own slice of the grid table. */
+int tcnnb_optimizer_step_ranges(tcnnb_model* m, tcnnb_stream stream, uint32_t n_ranges, const uint64_t* begins, const uint64_t* counts);
 /* Device pointer + element count of the fp32 accumulator that holds the MLP weight gradients between the backward
  * pass and the optimizer (for the data-parallel all-reduce); the grid gradients are tcnnb_param_gradients(). */
 float* tcnnb_mlp_gradient_accumulator(tcnnb_model* m);

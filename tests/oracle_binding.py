@@ -238,11 +238,30 @@ class OracleShardTrainer:
     def gradient_buffers(self):
         return [self.grad_sums]
 
-    def optimizer_step(self):
+    def shardable_gradients(self):
+        return self.grad_sums[self.m.n_mlp :], self.m.n_mlp
+
+    def replicated_gradients(self):
+        return [self.grad_sums[: self.m.n_mlp]]
+
+    def params(self):
+        import torch
+
+        return torch.from_numpy(self.m.params_fp16.view(np.int16))  # fp16 bit patterns; shares memory with the oracle model
+
+    def params_full_precision(self):
+        import torch
+
+        return torch.from_numpy(self.m.params_fp32)
+
+    def optimizer_step(self, ranges=None):
         m = self.m
         m.grads_fp16[:] = self.grad_sums.numpy().astype(np.float16).view(np.uint16)
-        m.lib.orc_adam_step(ctypes.byref(m.adam), ctypes.c_uint64(m.n_params), ctypes.c_uint64(m.n_mlp), ctypes.c_float(128.0), _p(m.params_fp32), _p(m.params_fp16),
-                            _p(m.grads_fp16), _p(m.m1), _p(m.m2), _p(m.steps))
+        for b, c in ranges if ranges is not None else [(0, m.n_params)]:
+            n_matrix = max(0, min(m.n_mlp - b, c))
+            sl = slice(b, b + c)
+            m.lib.orc_adam_step(ctypes.byref(m.adam), ctypes.c_uint64(c), ctypes.c_uint64(n_matrix), ctypes.c_float(128.0), _p(m.params_fp32[sl]), _p(m.params_fp16[sl]),
+                                _p(m.grads_fp16[sl]), _p(m.m1[sl]), _p(m.m2[sl]), _p(m.steps[sl]))
 
     def loss(self):
         return self._loss

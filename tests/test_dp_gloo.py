@@ -26,7 +26,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, shard_optimizer):
     sys.path.insert(0, os.path.join(ROOT, "tiny-cuda-nn_b200"))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as ob
@@ -40,32 +40,37 @@ def _worker(rank, world, port, out_dir):
         rng = ob.default_rng(1337)
         x = ob.generate_random_uniform(rng, B_GLOBAL * 3).reshape(B_GLOBAL, 3)
         y = ob.make_targets(x, 3)
-        dp = DataParallelTrainer(ob.OracleShardTrainer(3, 3, CFG))
-        assert (dp.world, dp.rank) == (world, rank)
+        dp = DataParallelTrainer(ob.OracleShardTrainer(3, 3, CFG), shard_optimizer=shard_optimizer)
+        assert (dp.world, dp.rank, dp.shard_optimizer) == (world, rank, shard_optimizer)
         lo, hi = dp.shard(B_GLOBAL)
         losses = []
         for _ in range(STEPS):
             dp.training_step(torch.from_numpy(x[lo:hi]), torch.from_numpy(y[lo:hi]))
             losses.append(dp.loss())
-        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), params=dp.trainer.m.params_fp32, steps=dp.trainer.m.steps, losses=np.array(losses), shard=np.array([lo, hi]))
+        stale = dp.trainer.m.params_fp32.copy()  # sharded optimizer: masters of the other ranks' slices are not current yet
+        dp.sync_full_precision()
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), params=dp.trainer.m.params_fp32, params_before_sync=stale, params16=dp.trainer.m.params_fp16,
+                 steps=dp.trainer.m.steps, losses=np.array(losses), shard=np.array([lo, hi]), owned=np.array(dp.owned_ranges()))
         with pytest.raises(ValueError):
             dp.shard(B_GLOBAL + 256)  # not divisible into 256-multiples per rank
     finally:
         dist.destroy_process_group()
 
 
-def test_two_rank_data_parallel_matches_single_process(tmp_path):
+@pytest.mark.parametrize("shard_optimizer", [False, True])
+def test_two_rank_data_parallel_matches_single_process(tmp_path, shard_optimizer):
     import oracle_binding as ob
 
     world = 2
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), shard_optimizer), nprocs=world, join=True)
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
     # shards partition the batch
     assert list(r0["shard"]) == [0, 512] and list(r1["shard"]) == [512, 1024]
-    # replicas stay bit-identical (same reduced gradients -> same Adam step, including the zero-gradient skip)
+    # replicas stay bit-identical (same reduced gradients -> same Adam step, including the zero-gradient skip): the working
+    # (fp16) parameters after every step, the fp32 masters once the slices have been exchanged
+    assert np.array_equal(r0["params16"], r1["params16"])
     assert np.array_equal(r0["params"].view(np.uint32), r1["params"].view(np.uint32))
-    assert np.array_equal(r0["steps"], r1["steps"])
     assert np.allclose(r0["losses"], r1["losses"], rtol=0, atol=0)
 
     # single process, full batch
@@ -76,5 +81,23 @@ def test_two_rank_data_parallel_matches_single_process(tmp_path):
     ref_losses = [ref.training_step(x, y) for _ in range(STEPS)]
     assert np.allclose(r0["losses"], ref_losses, rtol=1e-6)
     # gradients are exact sums in both cases -> parameters agree to fp32 rounding of one Adam step
-    assert np.array_equal(r0["steps"], ref.steps)
     assert np.abs(r0["params"] - ref.params_fp32).max() < 1e-6
+    assert np.array_equal(r0["params16"], ref.params_fp16)
+    n_mlp, n = ref.n_mlp, ref.n_params
+    if not shard_optimizer:
+        assert np.array_equal(r0["steps"], r1["steps"]) and np.array_equal(r0["steps"], ref.steps)
+        assert [list(r) for r in r0["owned"]] == [[0, n]]
+    else:
+        # every parameter has exactly one authoritative owner besides the replicated network weights / left-over entries, and
+        # the owner's per-parameter step counters (adam.h:100) match the single-process run
+        chunk = ((n - n_mlp) // 16) * 8
+        tail = (n - n_mlp) - 2 * chunk
+        expect0 = [[0, n_mlp], [n_mlp, chunk]] + ([[n_mlp + 2 * chunk, tail]] if tail else [])
+        expect1 = [[0, n_mlp], [n_mlp + chunk, chunk]] + ([[n_mlp + 2 * chunk, tail]] if tail else [])
+        assert [list(r) for r in r0["owned"]] == expect0 and [list(r) for r in r1["owned"]] == expect1
+        for r in (r0, r1):
+            for b, c in r["owned"]:
+                assert np.array_equal(r["steps"][b : b + c], ref.steps[b : b + c])
+        # before the exchange a rank's masters of the OTHER rank's slice are stale (still the initial values there)
+        other = slice(n_mlp + chunk, n_mlp + 2 * chunk)
+        assert not np.array_equal(r0["params_before_sync"][other], r0["params"][other])

@@ -239,10 +239,12 @@ __global__ void __launch_bounds__(ws_threads(SUBS), SUBS == 1 ? 2 : 1) fused_ws_
 				st_shared_v4(enc_tile + sw128(row, chunk), 0, 0, 0, 0);
 			}
 			{
-				// Two levels in flight: the loads of level l+1 are issued before the values of level l are consumed.
+				// Three levels in flight: the loads of levels l+1 and l+2 are issued before the values of level l are consumed.
+				// What travels with the loads is the fractional position (D floats), not the 2^D weights: they are rebuilt at
+				// consumption, which is what makes the third level fit the register budget.
 				struct InFlight {
 					uint32_t vals[1u << D];
-					uint32_t w16[1u << D];  // (half)weight duplicated into both halves
+					float frac[D];
 				};
 				auto issue = [&](uint32_t level, InFlight& f) {
 					const LevelInfo& lv = load_level(level);
@@ -260,30 +262,31 @@ __global__ void __launch_bounds__(ws_threads(SUBS), SUBS == 1 ? 2 : 1) fused_ws_
 						}
 					}
 #pragma unroll
-					for (uint32_t i = 0; i < (1u << D); ++i) {
-						const __half2 h = __float2half2_rn(lc.w[i]);
-						f.w16[i] = *reinterpret_cast<const uint32_t*>(&h);
-					}
+					for (uint32_t d = 0; d < D; ++d) f.frac[d] = lc.frac[d];
 				};
 				auto consume = [&](uint32_t level, const InFlight& f) {
+					float w[1u << D];
+					corner_weights<D>(f.frac, w);
 					__half2 result = __float2half2_rn(0.0f);
 #pragma unroll
 					for (uint32_t idx = 0; idx < (1u << D); ++idx) {
 						// fma((T)weight, grid_val, result) with T = __half -> __hfma2 (grid.h:162, vec.h:372-378)
-						result = __hfma2(*reinterpret_cast<const __half2*>(&f.w16[idx]), *reinterpret_cast<const __half2*>(&f.vals[idx]), result);
+						result = __hfma2(__float2half2_rn(w[idx]), *reinterpret_cast<const __half2*>(&f.vals[idx]), result);
 					}
 					const uint32_t feat = level * F;
 					asm volatile("st.shared.b32 [%0], %1;" ::"r"(enc_tile + sw128(row, feat >> 3) + (feat & 7u) * 2u), "r"(*reinterpret_cast<uint32_t*>(&result)) : "memory");
 					if (p.dbg_enc) *reinterpret_cast<uint32_t*>(p.dbg_enc + (size_t)os_cur * 64 + feat) = *reinterpret_cast<uint32_t*>(&result);
 				};
 				if (level_begin < level_end) {
-					InFlight cur, nxt;
-					issue(level_begin, cur);
+					InFlight f0, f1, f2;
+					issue(level_begin, f0);
+					if (level_begin + 1 < level_end) issue(level_begin + 1, f1);
 #pragma unroll 1
 					for (uint32_t level = level_begin; level < level_end; ++level) {
-						if (level + 1 < level_end) issue(level + 1, nxt);
-						consume(level, cur);
-						cur = nxt;
+						if (level + 2 < level_end) issue(level + 2, f2);
+						consume(level, f0);
+						f0 = f1;
+						f1 = f2;
 					}
 				}
 			}

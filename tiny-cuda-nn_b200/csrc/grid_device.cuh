@@ -126,27 +126,35 @@ __device__ __forceinline__ CornerPair<D> corner_pair(const LevelInfo& lv, const 
 // 8-byte slot. Contributions of the non-x dimensions to the hash / dense stride are computed once per value, not per corner.
 template <uint32_t D>
 struct LevelCorners {
+	float frac[D];  // the (interpolation-mapped) fractional position the weights are built from
 	float w[1u << D];
 	uint32_t idx[1u << D];
 	uint32_t paired;  // bit k: pair k is covered by one 64-bit access at (idx[2k] & ~1)
 };
 
+// weights: w[i] for corner bits (b0 = x, b1 = y, ...), built dimension by dimension -> ((t_x * t_y) * t_z)
+template <uint32_t D>
+__device__ __forceinline__ void corner_weights(const float (&frac)[D], float (&w)[1u << D]) {
+	w[0] = 1.0f - frac[0];
+	w[1] = frac[0];
+#pragma unroll
+	for (uint32_t d = 1; d < D; ++d) {
+		const float hi = frac[d], lo = 1.0f - frac[d];
+#pragma unroll
+		for (uint32_t i = 0; i < (1u << d); ++i) {
+			w[i + (1u << d)] = w[i] * hi;
+			w[i] = w[i] * lo;
+		}
+	}
+}
+
 template <uint32_t D>
 __device__ __forceinline__ void level_corners(const LevelInfo& lv, const float (&x)[D], uint32_t interpolation, LevelCorners<D>& out) {
 	CellPos<D> cp;
 	pos_fract<D>(x, lv.scale, interpolation, cp);
-	// weights: w[i] for corner bits (b0 = x, b1 = y, ...), built dimension by dimension -> ((t_x * t_y) * t_z)
-	out.w[0] = 1.0f - cp.frac[0];
-	out.w[1] = cp.frac[0];
 #pragma unroll
-	for (uint32_t d = 1; d < D; ++d) {
-		const float hi = cp.frac[d], lo = 1.0f - cp.frac[d];
-#pragma unroll
-		for (uint32_t i = 0; i < (1u << d); ++i) {
-			out.w[i + (1u << d)] = out.w[i] * hi;
-			out.w[i] = out.w[i] * lo;
-		}
-	}
+	for (uint32_t d = 0; d < D; ++d) out.frac[d] = cp.frac[d];
+	corner_weights<D>(cp.frac, out.w);
 	// indices: two straight-line paths selected by a warp-uniform test (all lanes of a warp work on the same level)
 	uint32_t rest[1u << (D - 1)];
 	rest[0] = 0;

@@ -288,6 +288,8 @@ struct Model {
 	size_t pinned_floats = 0;
 	DeviceBuffer<float> stage_in, stage_target, stage_out;
 	cudaStream_t own_stream = nullptr;
+	cudaStream_t copy_stream = nullptr;  // host-buffer step: the targets travel here while the binning pass runs on own_stream
+	cudaEvent_t ev_inputs = nullptr, ev_targets = nullptr;
 
 	tcnnb_debug_taps taps{};
 	std::string hyperparams_json;
@@ -300,6 +302,9 @@ struct Model {
 	~Model() {
 		if (pinned) cudaFreeHost(pinned);
 		if (own_stream) cudaStreamDestroy(own_stream);
+		if (copy_stream) cudaStreamDestroy(copy_stream);
+		if (ev_inputs) cudaEventDestroy(ev_inputs);
+		if (ev_targets) cudaEventDestroy(ev_targets);
 		for (auto e : prof_events) cudaEventDestroy(e);
 	}
 
@@ -492,6 +497,9 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 	++g_kernel_launches;
 	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
 	TCNNB_CUDA_CHECK(cudaStreamCreateWithFlags(&m.own_stream, cudaStreamNonBlocking));
+	TCNNB_CUDA_CHECK(cudaStreamCreateWithFlags(&m.copy_stream, cudaStreamNonBlocking));
+	TCNNB_CUDA_CHECK(cudaEventCreateWithFlags(&m.ev_inputs, cudaEventDisableTiming));
+	TCNNB_CUDA_CHECK(cudaEventCreateWithFlags(&m.ev_targets, cudaEventDisableTiming));
 }
 
 static void check_batch(uint32_t batch) {
@@ -538,7 +546,9 @@ static uint32_t fused_grid_size(const Model& m, uint32_t batch) {
 	return std::min(tiles, resident);
 }
 
-static void optimizer_step(Model& m, cudaStream_t stream) {
+// Adam over the parameter ranges [begin, begin + count) (all parameters when n_ranges == 0). One optimizer step whatever the
+// number of ranges: the data-parallel trainer updates the MLP weights everywhere and the grid entries of its own shard only.
+static void optimizer_step(Model& m, cudaStream_t stream, uint32_t n_ranges = 0, const uint64_t* begins = nullptr, const uint64_t* counts = nullptr) {
 	++m.adam_step_count;
 	AdamParams a = m.adam;
 	a.lower_lr_bound = 0;
@@ -547,13 +557,32 @@ static void optimizer_step(Model& m, cudaStream_t stream) {
 		a.lower_lr_bound = 0.1f - 0.1f / ((1 - a.beta2) * (float)m.adam_step_count + 1);
 		a.upper_lr_bound = 0.1f + 0.1f / ((1 - a.beta2) * (float)m.adam_step_count);
 	}
-	TCNNB_CUDA_CHECK(launch_adam_step(stream, a, (uint32_t)m.n_params, m.mlp.n_params, m.loss_scale, m.params_fp32, m.params_fp16, m.grads_fp16,
-	                                  m.mlp_grads_in_accum ? m.dw_accum.ptr : nullptr, m.first_moments.ptr, m.second_moments.ptr, m.param_steps.ptr));
-	++g_kernel_launches;
-	m.mlp_grads_in_accum = false;
+	const uint64_t whole_begin = 0, whole_count = m.n_params;
+	if (n_ranges == 0) {
+		n_ranges = 1;
+		begins = &whole_begin;
+		counts = &whole_count;
+	}
+	bool covers_mlp = false;
+	for (uint32_t r = 0; r < n_ranges; ++r) {
+		const uint64_t b = begins[r], c = counts[r];
+		if (b + c > m.n_params) throw std::runtime_error("optimizer_step: parameter range out of bounds.");
+		if (c == 0) continue;
+		if (b < m.mlp.n_params && b + c < m.mlp.n_params) throw std::runtime_error("optimizer_step: a range may not split the network weights.");
+		const uint32_t n_matrix = b < m.mlp.n_params ? (uint32_t)(m.mlp.n_params - b) : 0u;  // matrix weights inside this range
+		covers_mlp |= b == 0 && n_matrix > 0;
+		if (n_matrix > 0 && b != 0) throw std::runtime_error("optimizer_step: the network weights must be covered from parameter 0.");
+		TCNNB_CUDA_CHECK(launch_adam_step(stream, a, (uint32_t)c, n_matrix, m.loss_scale, m.params_fp32 + b, m.params_fp16 + b, m.grads_fp16 + b,
+		                                  (m.mlp_grads_in_accum && n_matrix > 0) ? m.dw_accum.ptr : nullptr, m.first_moments.ptr + b, m.second_moments.ptr + b,
+		                                  m.param_steps.ptr + b));
+		++g_kernel_launches;
+	}
+	if (covers_mlp) m.mlp_grads_in_accum = false;
 }
 
-static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_t loss_batch, const float* x, const float* y, bool run_optimizer) {
+// `targets_ready`: optional event the fused kernel (the first consumer of `y`) waits for; everything before it in the step --
+// gradient zeroing, the binning pass -- only needs `x` and runs while the targets are still in flight.
+static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_t loss_batch, const float* x, const float* y, bool run_optimizer, cudaEvent_t targets_ready = nullptr) {
 	check_batch(batch);
 	// GradientMode::Overwrite: zero the grid gradient table (grid.h:865-867) and the loss accumulator -- inside the binning pass
 	// when there is one, else as memsets.
@@ -589,6 +618,7 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
 		p.perm = m.bin_perm.ptr;
 	}
 	m.prof_mark(stream);
+	if (targets_ready) TCNNB_CUDA_CHECK(cudaStreamWaitEvent(stream, targets_ready, 0));
 	if (m.warp_specialized && m.mlp.n_hidden_layers <= 4) {
 		// one 640-thread CTA per SM; TCNNB_WS_SUBS=1 selects the two-CTAs-per-SM shape where it fits (measured slower on the
 		// headline configuration: 0.265 vs 0.213 ms)
@@ -809,6 +839,13 @@ int tcnnb_optimizer_step(tcnnb_model* m, tcnnb_stream stream) {
 	TCNNB_API_END
 }
 
+int tcnnb_optimizer_step_ranges(tcnnb_model* m, tcnnb_stream stream, uint32_t n_ranges, const uint64_t* begins, const uint64_t* counts) {
+	TCNNB_API_BEGIN
+	if (n_ranges > 0 && (!begins || !counts)) throw std::runtime_error("optimizer_step_ranges: null range arrays.");
+	optimizer_step(m->impl, (cudaStream_t)stream, n_ranges, begins, counts);
+	TCNNB_API_END
+}
+
 int tcnnb_loss(tcnnb_model* m, tcnnb_stream stream, float* loss_out) {
 	TCNNB_API_BEGIN
 	float v = 0;
@@ -839,10 +876,15 @@ int tcnnb_training_step_host(tcnnb_model* m, uint32_t batch_size, const float* i
 	const float* sx = input_host;
 	const float* sy = target_host;
 	if (!x_pinned) { std::memcpy(mm.pinned, input_host, n_x * sizeof(float)); sx = mm.pinned; }
-	if (!y_pinned) { std::memcpy(mm.pinned + n_x, target_host, n_y * sizeof(float)); sy = mm.pinned + n_x; }
+	// inputs on the compute stream; the targets follow on the copy stream (one after the other on the link, so the inputs
+	// land first) and only the fused kernel waits for them: the binning pass overlaps their transfer.
 	TCNNB_CUDA_CHECK(cudaMemcpyAsync(mm.stage_in.ptr, sx, n_x * sizeof(float), cudaMemcpyHostToDevice, s));
-	TCNNB_CUDA_CHECK(cudaMemcpyAsync(mm.stage_target.ptr, sy, n_y * sizeof(float), cudaMemcpyHostToDevice, s));
-	training_step(mm, s, batch_size, batch_size, mm.stage_in.ptr, mm.stage_target.ptr, true);
+	TCNNB_CUDA_CHECK(cudaEventRecord(mm.ev_inputs, s));
+	if (!y_pinned) { std::memcpy(mm.pinned + n_x, target_host, n_y * sizeof(float)); sy = mm.pinned + n_x; }  // while the inputs travel
+	TCNNB_CUDA_CHECK(cudaStreamWaitEvent(mm.copy_stream, mm.ev_inputs, 0));
+	TCNNB_CUDA_CHECK(cudaMemcpyAsync(mm.stage_target.ptr, sy, n_y * sizeof(float), cudaMemcpyHostToDevice, mm.copy_stream));
+	TCNNB_CUDA_CHECK(cudaEventRecord(mm.ev_targets, mm.copy_stream));
+	training_step(mm, s, batch_size, batch_size, mm.stage_in.ptr, mm.stage_target.ptr, true, mm.ev_targets);
 	float* loss_pinned = mm.pinned + mm.pinned_floats - 1;
 	TCNNB_CUDA_CHECK(cudaMemcpyAsync(loss_pinned, mm.scalars.ptr, sizeof(float), cudaMemcpyDeviceToHost, s));
 	TCNNB_CUDA_CHECK(cudaStreamSynchronize(s));

@@ -58,6 +58,7 @@ ABI = [
     ("tcnnb_training_step", _int, [_vp, _vp, _u32, _vp, _vp, _int]),
     ("tcnnb_training_step_shard", _int, [_vp, _vp, _u32, _u32, _vp, _vp, _int]),
     ("tcnnb_optimizer_step", _int, [_vp, _vp]),
+    ("tcnnb_optimizer_step_ranges", _int, [_vp, _vp, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     ("tcnnb_mlp_gradient_accumulator", _vp, [_vp]),
     ("tcnnb_grid_gradients", _vp, [_vp]),
     ("tcnnb_loss", _int, [_vp, _vp, _f32p]),
@@ -156,8 +157,15 @@ class _Trainer:
         _check(load().tcnnb_training_step_shard(m._h, _stream_handle(stream), inputs.shape[0], global_batch_size, inputs.data_ptr(), targets.data_ptr(), int(run_optimizer)))
         return self
 
-    def optimizer_step(self, stream=None):
-        _check(load().tcnnb_optimizer_step(self._m._h, _stream_handle(stream)))
+    def optimizer_step(self, stream=None, ranges=None):
+        """Adam on the current gradients; `ranges` = [(begin, count), ...] restricts it to those parameter spans."""
+        if ranges is None:
+            _check(load().tcnnb_optimizer_step(self._m._h, _stream_handle(stream)))
+            return
+        n = len(ranges)
+        b = (ctypes.c_uint64 * n)(*[int(r[0]) for r in ranges])
+        c = (ctypes.c_uint64 * n)(*[int(r[1]) for r in ranges])
+        _check(load().tcnnb_optimizer_step_ranges(self._m._h, _stream_handle(stream), n, b, c))
 
     def loss(self, ctx=None, stream=None):
         out = ctypes.c_float(0)
@@ -211,6 +219,14 @@ class _Trainer:
             ptr = load().tcnnb_grid_gradients(self._m._h)
             self._grad_bufs = [self._view(ptr, self._m.n_params - self._m.n_mlp_params, torch.float16), self.mlp_gradient_accumulator()]
         return self._grad_bufs
+
+    def shardable_gradients(self):
+        """(fp16 grid-gradient table, index of its first parameter): what the sharded-optimizer trainer reduce-scatters."""
+        return self.gradient_buffers()[0], self._m.n_mlp_params
+
+    def replicated_gradients(self):
+        """Gradient buffers every rank needs in full (the fp32 network weight-gradient accumulator)."""
+        return [self.gradient_buffers()[1]]
 
     def device(self):
         return "cuda"
