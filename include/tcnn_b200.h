@@ -48,6 +48,9 @@ void tcnnb_destroy(tcnnb_model* model);
 
 /* ---- introspection (network_with_input_encoding.h:132-150, trainer.h:385-407,477-482) ---- */
 uint64_t tcnnb_n_params(const tcnnb_model* m);                 /* trainer->n_params() */
+/* Allocated length of each of the three parameter regions (>= n_params, multiple of 512; the padding is zero and never
+ * touched). The sharded-optimizer data-parallel trainer cuts [0, n_params_padded) into equal slices. */
+uint64_t tcnnb_n_params_padded(const tcnnb_model* m);
 uint64_t tcnnb_n_mlp_params(const tcnnb_model* m);             /* network part; grid params follow */
 uint32_t tcnnb_n_input_dims(const tcnnb_model* m);
 uint32_t tcnnb_n_output_dims(const tcnnb_model* m);            /* network->output_width() */
@@ -76,6 +79,10 @@ int tcnnb_optimizer_step(tcnnb_model* m, tcnnb_stream stream);
 /* The same optimizer step restricted to the parameter ranges [begins[r], begins[r] + counts[r]) (adam.h:48-129 is element-wise,
  * so a range is the reference kernel launched on a sub-span). Used by the sharded-optimizer data-parallel trainer: every rank
  * updates the network weights (a range starting at 0 that covers all of them) and its own slice of the grid table. */
+/* Stream-ordering hook for callers that refresh the working parameters on another stream (the data-parallel all-gather):
+ * the next kernel of this model that READS the parameters (fused step, inference, optimizer) waits for `cuda_event`
+ * (a cudaEvent_t the caller keeps alive until that launch); work that does not read them (the binning pass) is not held back. */
+int tcnnb_wait_before_compute(tcnnb_model* m, void* cuda_event);
 int tcnnb_optimizer_step_ranges(tcnnb_model* m, tcnnb_stream stream, uint32_t n_ranges, const uint64_t* begins, const uint64_t* counts);
 /* Device pointer + element count of the fp32 accumulator that holds the MLP weight gradients between the backward
  * pass and the optimizer (for the data-parallel all-reduce); the grid gradients are tcnnb_param_gradients(). */

@@ -222,8 +222,17 @@ class OracleShardTrainer:
     def __init__(self, n_in, n_out, config, seed=1337):
         import torch
 
-        self.m = OracleModel(n_in, n_out, config, seed=seed)
-        self.grad_sums = torch.zeros(self.m.n_params, dtype=torch.float64)
+        self.m = m = OracleModel(n_in, n_out, config, seed=seed)
+        # padded whole-vector buffers like the CUDA trainer's (tcnnb_n_params_padded): the model's arrays become prefixes of them
+        self.n_pad = (m.n_params + 511) // 512 * 512
+        self._p16 = np.zeros(self.n_pad, np.uint16)
+        self._p32 = np.zeros(self.n_pad, np.float32)
+        self._p16[: m.n_params] = m.params_fp16
+        self._p32[: m.n_params] = m.params_fp32
+        m.params_fp16 = self._p16[: m.n_params]
+        m.params_fp32 = self._p32[: m.n_params]
+        self._grads = torch.zeros(self.n_pad, dtype=torch.float64)
+        self.grad_sums = self._grads[: m.n_params]
         self._loss = 0.0
         load().orc_training_step_shard.restype = ctypes.c_double
 
@@ -238,21 +247,14 @@ class OracleShardTrainer:
     def gradient_buffers(self):
         return [self.grad_sums]
 
-    def shardable_gradients(self):
-        return self.grad_sums[self.m.n_mlp :], self.m.n_mlp
-
-    def replicated_gradients(self):
-        return [self.grad_sums[: self.m.n_mlp]]
-
-    def params(self):
+    def sharded_buffers(self):
         import torch
 
-        return torch.from_numpy(self.m.params_fp16.view(np.int16))  # fp16 bit patterns; shares memory with the oracle model
+        return {"grads": self._grads, "params": torch.from_numpy(self._p16.view(np.int16)), "masters": torch.from_numpy(self._p32),
+                "n_params": self.m.n_params, "n_matrix": self.m.n_mlp}
 
-    def params_full_precision(self):
-        import torch
-
-        return torch.from_numpy(self.m.params_fp32)
+    def finalize_gradients(self):
+        pass  # one fp64 gradient vector already
 
     def optimizer_step(self, ranges=None):
         m = self.m

@@ -266,6 +266,7 @@ struct Model {
 	size_t n_params = 0;
 	// trainer.h:489-503: one allocation [fp32 master | fp16 params | fp16 gradients]
 	DeviceBuffer<char> params_buffer;
+	size_t n_params_padded = 0;
 	float* params_fp32 = nullptr;
 	__half* params_fp16 = nullptr;
 	__half* grads_fp16 = nullptr;
@@ -290,6 +291,13 @@ struct Model {
 	cudaStream_t own_stream = nullptr;
 	cudaStream_t copy_stream = nullptr;  // host-buffer step: the targets travel here while the binning pass runs on own_stream
 	cudaEvent_t ev_inputs = nullptr, ev_targets = nullptr;
+	cudaEvent_t pending_params_event = nullptr;  // caller-owned: the next reader of the parameters waits for it (tcnnb_wait_before_compute)
+	void wait_pending(cudaStream_t stream) {
+		if (pending_params_event) {
+			cudaStreamWaitEvent(stream, pending_params_event, 0);
+			pending_params_event = nullptr;
+		}
+	}
 
 	tcnnb_debug_taps taps{};
 	std::string hyperparams_json;
@@ -453,11 +461,15 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 
 	// ---- parameter buffers (trainer.h:69-87,489-503)
 	m.n_params = (size_t)mlp.n_params + m.grid.n_params;
-	m.params_buffer.resize(m.n_params * (sizeof(float) + 2 * sizeof(__half)));
+	// Same order as the reference's single allocation [fp32 master | working fp16 | fp16 gradients]; each region is padded to
+	// a multiple of 512 parameters (never-touched zero entries) so that a data-parallel job can cut it into equal, 16-byte
+	// aligned slices for any world size up to 64 (tcnn_b200/dp.py).
+	m.n_params_padded = (m.n_params + 511) / 512 * 512;
+	m.params_buffer.resize(m.n_params_padded * (sizeof(float) + 2 * sizeof(__half)));
 	m.params_buffer.zero();
 	m.params_fp32 = (float*)m.params_buffer.ptr;
-	m.params_fp16 = (__half*)(m.params_buffer.ptr + sizeof(float) * m.n_params);
-	m.grads_fp16 = (__half*)(m.params_buffer.ptr + sizeof(float) * m.n_params + sizeof(__half) * m.n_params);
+	m.params_fp16 = (__half*)(m.params_buffer.ptr + sizeof(float) * m.n_params_padded);
+	m.grads_fp16 = (__half*)(m.params_buffer.ptr + sizeof(float) * m.n_params_padded + sizeof(__half) * m.n_params_padded);
 	m.first_moments.resize(m.n_params);
 	m.first_moments.zero();
 	m.second_moments.resize(m.n_params);
@@ -549,6 +561,7 @@ static uint32_t fused_grid_size(const Model& m, uint32_t batch) {
 // Adam over the parameter ranges [begin, begin + count) (all parameters when n_ranges == 0). One optimizer step whatever the
 // number of ranges: the data-parallel trainer updates the MLP weights everywhere and the grid entries of its own shard only.
 static void optimizer_step(Model& m, cudaStream_t stream, uint32_t n_ranges = 0, const uint64_t* begins = nullptr, const uint64_t* counts = nullptr) {
+	m.wait_pending(stream);
 	++m.adam_step_count;
 	AdamParams a = m.adam;
 	a.lower_lr_bound = 0;
@@ -619,6 +632,7 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
 	}
 	m.prof_mark(stream);
 	if (targets_ready) TCNNB_CUDA_CHECK(cudaStreamWaitEvent(stream, targets_ready, 0));
+	m.wait_pending(stream);  // e.g. the all-gather of the previous data-parallel step: binning above did not need the parameters
 	if (m.warp_specialized && m.mlp.n_hidden_layers <= 4) {
 		// one 640-thread CTA per SM; TCNNB_WS_SUBS=1 selects the two-CTAs-per-SM shape where it fits (measured slower on the
 		// headline configuration: 0.265 vs 0.213 ms)
@@ -646,6 +660,7 @@ static void finalize_mlp_grads(Model& m, cudaStream_t stream) {
 
 static void inference(Model& m, cudaStream_t stream, uint32_t batch, const float* x, float* out) {
 	check_batch(batch);
+	m.wait_pending(stream);
 	FusedStepParams p = make_params(m, batch, batch, x, nullptr);
 	p.out_fp32 = out;
 	p.loss_sum = nullptr;
@@ -770,6 +785,7 @@ void tcnnb_destroy(tcnnb_model* model) {
 }
 
 uint64_t tcnnb_n_params(const tcnnb_model* m) { return m->impl.n_params; }
+uint64_t tcnnb_n_params_padded(const tcnnb_model* m) { return m->impl.n_params_padded; }
 uint64_t tcnnb_n_mlp_params(const tcnnb_model* m) { return m->impl.mlp.n_params; }
 uint32_t tcnnb_n_input_dims(const tcnnb_model* m) { return m->impl.n_in; }
 uint32_t tcnnb_n_output_dims(const tcnnb_model* m) { return m->impl.n_out; }
@@ -972,6 +988,12 @@ int tcnnb_deserialize(tcnnb_model* m, const void* src_host, uint64_t size) {
 		mm.adam_step_count = st;
 	}
 	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
+	TCNNB_API_END
+}
+
+int tcnnb_wait_before_compute(tcnnb_model* m, void* cuda_event) {
+	TCNNB_API_BEGIN
+	m->impl.pending_params_event = (cudaEvent_t)cuda_event;
 	TCNNB_API_END
 }
 

@@ -43,6 +43,7 @@ ABI = [
     ("tcnnb_abi_version", _u32, []),
     ("tcnnb_create_from_config", _int, [_u32, _u32, ctypes.c_char_p, _u32, ctypes.POINTER(_vp)]),
     ("tcnnb_destroy", None, [_vp]),
+    ("tcnnb_n_params_padded", ctypes.c_uint64, [_vp]),
     ("tcnnb_n_params", _u64, [_vp]),
     ("tcnnb_n_mlp_params", _u64, [_vp]),
     ("tcnnb_n_input_dims", _u32, [_vp]),
@@ -58,6 +59,7 @@ ABI = [
     ("tcnnb_training_step", _int, [_vp, _vp, _u32, _vp, _vp, _int]),
     ("tcnnb_training_step_shard", _int, [_vp, _vp, _u32, _u32, _vp, _vp, _int]),
     ("tcnnb_optimizer_step", _int, [_vp, _vp]),
+    ("tcnnb_wait_before_compute", _int, [_vp, _vp]),
     ("tcnnb_optimizer_step_ranges", _int, [_vp, _vp, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     ("tcnnb_mlp_gradient_accumulator", _vp, [_vp]),
     ("tcnnb_grid_gradients", _vp, [_vp]),
@@ -220,13 +222,32 @@ class _Trainer:
             self._grad_bufs = [self._view(ptr, self._m.n_params - self._m.n_mlp_params, torch.float16), self.mlp_gradient_accumulator()]
         return self._grad_bufs
 
-    def shardable_gradients(self):
-        """(fp16 grid-gradient table, index of its first parameter): what the sharded-optimizer trainer reduce-scatters."""
-        return self.gradient_buffers()[0], self._m.n_mlp_params
+    def sharded_buffers(self):
+        """Whole (padded) parameter vector views for the sharded-optimizer trainer: fp16 gradients, fp16 working parameters,
+        fp32 masters -- each n_params_padded long -- plus the real parameter count and the number of network weights."""
+        if not hasattr(self, "_sharded"):
+            import torch
 
-    def replicated_gradients(self):
-        """Gradient buffers every rank needs in full (the fp32 network weight-gradient accumulator)."""
-        return [self.gradient_buffers()[1]]
+            lib, h = load(), self._m._h
+            n_pad = int(lib.tcnnb_n_params_padded(h))
+            self._sharded = {
+                "grads": self._view(lib.tcnnb_param_gradients(h), n_pad, torch.float16),
+                "params": self._view(lib.tcnnb_params(h), n_pad, torch.float16),
+                "masters": self._view(lib.tcnnb_params_full_precision(h), n_pad, torch.float32),
+                "n_params": self._m.n_params,
+                "n_matrix": self._m.n_mlp_params,
+            }
+        return self._sharded
+
+    def wait_before_compute(self, event):
+        """The next kernel of this model that reads the parameters waits for `event` (a torch.cuda.Event, kept alive here)."""
+        self._pending_event = event
+        _check(load().tcnnb_wait_before_compute(self._m._h, ctypes.c_void_p(event.cuda_event)))
+
+    def finalize_gradients(self):
+        """Round the fp32 network weight-gradient sums into the fp16 gradient buffer (what the reference's buffer holds)."""
+        if not load().tcnnb_param_gradients(self._m._h):
+            raise TcnnError(load().tcnnb_last_error().decode())
 
     def device(self):
         return "cuda"

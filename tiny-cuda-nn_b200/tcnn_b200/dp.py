@@ -7,16 +7,18 @@ replica of the working-precision parameters. A step is:
        (`training_step_shard`), so per-rank gradients are partial sums of the single-GPU gradient;
     2. the gradients are summed over the ranks and Adam is applied -- in one of two ways:
 
-       shard_optimizer=True (default, ZeRO-1 style):
-         reduce-scatter(sum) of the grid-gradient table: rank r receives the reduced gradients of ITS slice of the table;
-         all-reduce of the (tiny) network weight gradients and of the few table entries left over by the equal split;
-         Adam on the network weights (every rank, identical) and on the rank's own table slice only -- the optimizer pass, the
-         largest HBM consumer of the step (36 B/parameter), shrinks by the world size;
-         all-gather of the updated working-precision (fp16) table slices.
-         Same bytes on the wire as an all-reduce. fp32 master parameters and Adam moments of a slice live on its owner only;
-         `sync_full_precision()` all-gathers the masters (before serialising, or to read them anywhere).
+       shard_optimizer=True (default, ZeRO-1 style). The parameter vector [network weights | grid table], padded to a multiple
+       of 512, is cut into `world` equal slices; rank r owns slice r:
+         reduce-scatter(sum) of the fp16 gradient vector -> rank r holds the reduced gradients of its slice;
+         Adam on that slice only -- the optimizer pass, the largest HBM consumer of the step (36 B/parameter), shrinks by the
+         world size;
+         all-gather of the updated working-precision (fp16) slices, launched on a side stream: the next step's binning pass
+         (which reads only positions) overlaps it, only the fused kernel waits for it.
+         Two collectives per step, the same bytes on the wire as one all-reduce. fp32 master parameters and Adam moments of a
+         slice live on its owner only; `sync_full_precision()` all-gathers the masters (before serialising, or to read them).
 
-       shard_optimizer=False: all-reduce of both gradient buffers, then the same full Adam step on every replica.
+       shard_optimizer=False: all-reduce of both gradient buffers (fp16 table, fp32 network accumulator), then the same full
+       Adam step on every replica.
 
     Either way the zero-gradient skip of adam.h:79-82 is evaluated on the REDUCED gradients, which keeps the replicas'
     working parameters bit-identical.
@@ -24,8 +26,8 @@ replica of the working-precision parameters. A step is:
 `trainer` is anything with the methods used below (the CUDA trainer in production; the CPU tests drive the same class with an
 oracle-backed stand-in over gloo):
     training_step_shard(x, y, global_batch, run_optimizer), optimizer_step(ranges=None), loss(), gradient_buffers(),
-    and for the sharded optimizer: shardable_gradients() -> (tensor, first_param), replicated_gradients() -> [tensor],
-    params() -> working-precision tensor of all parameters, params_full_precision() -> fp32 tensor of all parameters.
+    and for the sharded optimizer: sharded_buffers() -> {"grads", "params", "masters": padded whole-vector tensors,
+    "n_params", "n_matrix"}, finalize_gradients(), and optionally wait_before_compute(event) (CUDA only).
 """
 import torch.distributed as dist
 
@@ -39,8 +41,14 @@ class DataParallelTrainer:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.shard_optimizer = bool(shard_optimizer) and self.world > 1 and hasattr(trainer, "shardable_gradients")
+        self.shard_optimizer = bool(shard_optimizer) and self.world > 1 and hasattr(trainer, "sharded_buffers")
+        if self.shard_optimizer:
+            b = trainer.sharded_buffers()
+            n_pad = b["grads"].numel()
+            if n_pad % (SLICE_GRANULARITY * self.world) != 0 or n_pad // self.world < b["n_matrix"]:
+                self.shard_optimizer = False  # slices must be aligned, and the network weights must sit inside slice 0
         self._masters_synced = True
+        self._comm_stream = None
 
     def shard(self, n_global):
         """[begin, end) of this rank's contiguous shard of a global batch; shards must stay multiples of 256."""
@@ -50,21 +58,15 @@ class DataParallelTrainer:
         return self.rank * per, (self.rank + 1) * per
 
     # ------------------------------------------------------------------ parameter slices of the sharded optimizer
-    def slice_layout(self, n_shardable):
-        """Equal split of `n_shardable` table parameters: (slice length, number of left-over parameters at the end)."""
-        chunk = (n_shardable // (SLICE_GRANULARITY * self.world)) * SLICE_GRANULARITY
-        return chunk, n_shardable - chunk * self.world
-
-    def owned_ranges(self):
-        """Parameter ranges [(begin, count)] this rank's optimizer state is authoritative for."""
-        g, first = self.trainer.shardable_gradients()
+    def owned_range(self):
+        """(begin, count) of the parameters this rank's optimizer state is authoritative for."""
         if not self.shard_optimizer:
-            return [(0, first + g.numel())]
-        chunk, tail = self.slice_layout(g.numel())
-        ranges = [(0, first), (first + self.rank * chunk, chunk)]
-        if tail:
-            ranges.append((first + chunk * self.world, tail))
-        return [r for r in ranges if r[1] > 0]
+            g = self.trainer.gradient_buffers()
+            return 0, sum(int(t.numel()) for t in g) if len(g) > 1 else int(g[0].numel())
+        b = self.trainer.sharded_buffers()
+        chunk = b["grads"].numel() // self.world
+        begin = self.rank * chunk
+        return begin, max(0, min(chunk, b["n_params"] - begin))
 
     # ------------------------------------------------------------------ collectives (NCCL; gloo fallbacks for the CPU tests)
     def _reduce_scatter(self, whole, own):
@@ -82,6 +84,21 @@ class DataParallelTrainer:
         else:
             dist.all_gather_into_tensor(whole, own, group=self.group)  # in place: own is whole[rank]
 
+    def _all_gather_overlapped(self, whole, own):
+        """All-gather on a side stream; the trainer's next fused kernel waits for it, the binning pass in front of it does not."""
+        import torch
+
+        if not (whole.is_cuda and hasattr(self.trainer, "wait_before_compute")):
+            self._all_gather(whole, own)
+            return
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream()
+        self._comm_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._comm_stream):
+            self._all_gather(whole, own)
+            done = self._comm_stream.record_event()
+        self.trainer.wait_before_compute(done)
+
     # ------------------------------------------------------------------ the step
     def training_step(self, x_shard, y_shard):
         """x_shard / y_shard: this rank's samples. Returns nothing; the global loss is `loss()`."""
@@ -97,30 +114,24 @@ class DataParallelTrainer:
             t.optimizer_step()
             return
 
-        grads, first = t.shardable_gradients()
-        chunk, tail = self.slice_layout(grads.numel())
+        t.finalize_gradients()
+        b = t.sharded_buffers()
+        chunk = b["grads"].numel() // self.world
         lo = self.rank * chunk
-        if chunk:
-            self._reduce_scatter(grads[: chunk * self.world], grads[lo : lo + chunk])
-        for buf in t.replicated_gradients():
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
-        if tail:
-            dist.all_reduce(grads[chunk * self.world :], op=dist.ReduceOp.SUM, group=self.group)
-        t.optimizer_step(ranges=self.owned_ranges())
-        if chunk:
-            table = t.params()[first : first + chunk * self.world]
-            self._all_gather(table, table[lo : lo + chunk])
+        self._reduce_scatter(b["grads"], b["grads"][lo : lo + chunk])
+        begin, count = self.owned_range()
+        if count:
+            t.optimizer_step(ranges=[(begin, count)])
+        self._all_gather_overlapped(b["params"], b["params"][lo : lo + chunk])
         self._masters_synced = False
 
     def sync_full_precision(self):
-        """All-gather the fp32 master parameters of the table slices (their owners hold the current values)."""
+        """All-gather the fp32 master parameters (the owner of a slice holds its current values)."""
         if not self.shard_optimizer or self._masters_synced:
             return
-        grads, first = self.trainer.shardable_gradients()
-        chunk, _ = self.slice_layout(grads.numel())
-        if chunk:
-            masters = self.trainer.params_full_precision()[first : first + chunk * self.world]
-            self._all_gather(masters, masters[self.rank * chunk : (self.rank + 1) * chunk])
+        m = self.trainer.sharded_buffers()["masters"]
+        chunk = m.numel() // self.world
+        self._all_gather(m, m[self.rank * chunk : (self.rank + 1) * chunk])
         self._masters_synced = True
 
     def loss(self):
