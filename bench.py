@@ -216,7 +216,7 @@ def run_own(args):
 
     # world == 1: plain training_step; else shard step + reduce-scatter of the table gradients + Adam on the rank's own table
     # slice + all-gather of the updated fp16 slices (TCNNB_DP_REPLICATED=1: all-reduce + full Adam on every replica)
-    dp = DataParallelTrainer(trainer, shard_optimizer=os.environ.get("TCNNB_DP_REPLICATED", "0") != "1")
+    dp = DataParallelTrainer(trainer, shard_optimizer=os.environ.get("TCNNB_DP_REPLICATED", "0") != "1", native=os.environ.get("TCNNB_DP_PYTHON", "0") != "1")
     stream = torch.cuda.current_stream()
 
     def step(i):
@@ -290,7 +290,7 @@ def run_own(args):
             "metric": METRIC, "value": global_batch * args.steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": global_batch, "parallelism": f"dp{world}" + ("" if world == 1 else ("-zero1" if dp.shard_optimizer else "-replicated")),
+            "config": {"workload": WORKLOAD, "global_batch": global_batch, "parallelism": f"dp{world}" + ("" if world == 1 else ("-zero1" if dp.shard_optimizer else "-replicated") + ("-native" if dp.native else "-torchdist")),
                        "l2": "per-step working set (tables+optimizer state ~770 MB) exceeds the 126 MB L2; 4 rotating input batches; no explicit flush"},
             "clocks": cs.summary(),
             "e2e": {"value": global_batch * e2e_steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": BATCH * (N_IN + N_OUT) * 4, "d2h_bytes_per_step": 4,
@@ -308,6 +308,7 @@ def run_own(args):
             line["cpu_baseline"] = {"error": repr(e)}
         print(json.dumps(line))
     if world > 1:
+        dp.close()
         dist.destroy_process_group()
 
 

@@ -79,6 +79,22 @@ int tcnnb_optimizer_step(tcnnb_model* m, tcnnb_stream stream);
 /* The same optimizer step restricted to the parameter ranges [begins[r], begins[r] + counts[r]) (adam.h:48-129 is element-wise,
  * so a range is the reference kernel launched on a sub-span). Used by the sharded-optimizer data-parallel trainer: every rank
  * updates the network weights (a range starting at 0 that covers all of them) and its own slice of the grid table. */
+/* ---- data parallelism, natively over NCCL (no counterpart in the single-GPU reference) -------------
+ * One process per GPU. Rendezvous is the host framework's job (torch.distributed in tcnn_b200/dp.py): rank 0 draws two NCCL
+ * ids with tcnnb_dp_unique_id (128 bytes each), broadcasts them, and every rank calls tcnnb_dp_init. libnccl.so.2 is resolved
+ * at run time on the first of these calls. A tcnnb_dp_training_step is: fwd+bwd on this rank's shard with the loss normalised
+ * over the global batch; then, with shard_optimizer, reduce-scatter of the fp16 gradient vector, Adam on this rank's slice of the
+ * (padded) parameter vector, all-gather of the updated fp16 slices on a side stream (the next step's binning pass overlaps it);
+ * without, all-reduce of the gradients and the full Adam step on every replica. The zero-gradient skip of adam.h:79-82 is
+ * evaluated on the reduced gradients either way, so the working parameters stay identical on all ranks. fp32 masters of a slice
+ * are current on its owner only until tcnnb_dp_sync_full_precision gathers them. */
+int tcnnb_dp_unique_id(void* out_id, uint64_t n_bytes);
+int tcnnb_dp_init(tcnnb_model* m, const void* id_grads, const void* id_params, int world_size, int rank, int shard_optimizer);
+int tcnnb_dp_shards_optimizer(const tcnnb_model* m); /* 1 if the sharded optimizer is in effect (aligned slices, world > 1) */
+int tcnnb_dp_training_step(tcnnb_model* m, tcnnb_stream stream, uint32_t shard_batch_size, uint32_t global_batch_size, const float* input_dev, const float* target_dev);
+int tcnnb_dp_sync_full_precision(tcnnb_model* m, tcnnb_stream stream);
+int tcnnb_dp_finish(tcnnb_model* m); /* destroys the communicators (call before the process group goes away) */
+
 /* Stream-ordering hook for callers that refresh the working parameters on another stream (the data-parallel all-gather):
  * the next kernel of this model that READS the parameters (fused step, inference, optimizer) waits for `cuda_event`
  * (a cudaEvent_t the caller keeps alive until that launch); work that does not read them (the binning pass) is not held back. */

@@ -15,7 +15,7 @@ CFG = json.load(open(os.path.join(ROOT, "tests", "golden", "configs", "hash3d_sm
 B = 32768
 
 
-def worker(rank, world, out, shard_optimizer):
+def worker(rank, world, out, shard_optimizer, native):
     import oracle_binding as ob
     import tcnn_b200
     from tcnn_b200.dp import DataParallelTrainer
@@ -27,7 +27,8 @@ def worker(rank, world, out, shard_optimizer):
     x = ob.generate_random_uniform(rng, B * 3).reshape(B, 3)
     y = ob.make_targets(x, 3)
     model = tcnn_b200.create_from_config(3, 3, CFG)
-    dp = DataParallelTrainer(model.trainer, shard_optimizer=shard_optimizer)
+    dp = DataParallelTrainer(model.trainer, shard_optimizer=shard_optimizer, native=native)
+    assert dp.native == native and dp.shard_optimizer == shard_optimizer
     lo, hi = dp.shard(B)
     xd, yd = torch.from_numpy(x[lo:hi]).cuda(), torch.from_numpy(y[lo:hi]).cuda()
     losses = []
@@ -36,15 +37,17 @@ def worker(rank, world, out, shard_optimizer):
         losses.append(dp.loss())
     dp.sync_full_precision()
     torch.cuda.synchronize()
-    np.savez(os.path.join(out, f"dp{rank}_{int(shard_optimizer)}.npz"), p=model.trainer.params_full_precision().cpu().numpy(), p16=model.trainer.params().cpu().view(torch.int16).numpy(), losses=np.array(losses))
+    np.savez(os.path.join(out, f"dp{rank}_{int(shard_optimizer)}{int(native)}.npz"), p=model.trainer.params_full_precision().cpu().numpy(), p16=model.trainer.params().cpu().view(torch.int16).numpy(), losses=np.array(losses))
+    dp.close()
     dist.destroy_process_group()
 
 
 if __name__ == "__main__":
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
-    for so in (False, True):
-        mp.spawn(worker, args=(2, out, so), nprocs=2, join=True)
+    MODES = [(False, False), (True, False), (False, True), (True, True)]  # (sharded optimizer, native NCCL engine)
+    for so, nat in MODES:
+        mp.spawn(worker, args=(2, out, so, nat), nprocs=2, join=True)
     import oracle_binding as ob
     import tcnn_b200
 
@@ -59,9 +62,9 @@ if __name__ == "__main__":
         model.trainer.training_step(xd, yd)
         losses.append(model.trainer.loss())
     p1 = model.trainer.params_full_precision().cpu().numpy()
-    for so in (0, 1):
-        r0, r1 = np.load(os.path.join(out, f"dp0_{so}.npz")), np.load(os.path.join(out, f"dp1_{so}.npz"))
-        print("sharded optimizer:", bool(so))
+    for so, nat in MODES:
+        r0, r1 = np.load(os.path.join(out, f"dp0_{int(so)}{int(nat)}.npz")), np.load(os.path.join(out, f"dp1_{int(so)}{int(nat)}.npz"))
+        print("sharded optimizer:", so, "native engine:", nat)
         print("  replicas identical (fp32 masters / fp16 working):", np.array_equal(r0["p"], r1["p"]), np.array_equal(r0["p16"], r1["p16"]))
         print("  losses dp:", r0["losses"].tolist())
         print("  losses 1gpu:", losses)

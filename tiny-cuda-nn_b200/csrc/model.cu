@@ -17,6 +17,9 @@
 #include "json_mini.h"
 #include "misc_kernels.h"
 
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: libnccl is resolved at run time (dlopen), single-GPU users never need it
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -251,6 +254,66 @@ static GridConfig parse_grid(uint32_t n_dims_to_encode, const json::Value& e) {
 	return g;
 }
 
+// ------------------------------------------------------------------------------------------------ NCCL (data parallel)
+// libnccl.so.2 is looked up when the first data-parallel call is made. In a PyTorch process this resolves to the copy
+// torch has already loaded, so both use one NCCL; tcnn_b200 itself has no link-time dependency on it.
+struct NcclApi {
+	decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+	decltype(&ncclCommInitRank) CommInitRank = nullptr;
+	decltype(&ncclCommDestroy) CommDestroy = nullptr;
+	decltype(&ncclAllReduce) AllReduce = nullptr;
+	decltype(&ncclReduceScatter) ReduceScatter = nullptr;
+	decltype(&ncclAllGather) AllGather = nullptr;
+	decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+
+static NcclApi& nccl_api() {
+	static NcclApi api = [] {
+		NcclApi a;
+		void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+		if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+		if (!lib) throw std::runtime_error(std::string("data-parallel training needs NCCL: ") + dlerror());
+		auto sym = [&](const char* name) {
+			void* f = dlsym(lib, name);
+			if (!f) throw std::runtime_error(std::string("libnccl lacks ") + name);
+			return f;
+		};
+		a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId");
+		a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+		a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+		a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
+		a.ReduceScatter = (decltype(a.ReduceScatter))sym("ncclReduceScatter");
+		a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
+		a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+		return a;
+	}();
+	return api;
+}
+
+#define TCNNB_NCCL_CHECK(x)                                                                                             \
+	do {                                                                                                                \
+		ncclResult_t _r = (x);                                                                                          \
+		if (_r != ncclSuccess) throw std::runtime_error(std::string(#x " failed: ") + nccl_api().GetErrorString(_r));   \
+	} while (0)
+
+// Two communicators: the gradient reduction runs on the caller's stream, the parameter all-gather on a side stream, and two
+// collectives of ONE communicator may not be in flight concurrently.
+struct DpState {
+	ncclComm_t comm_grads = nullptr, comm_params = nullptr;
+	int world = 1, rank = 0;
+	bool shard_optimizer = true;
+	bool masters_synced = true;
+	cudaStream_t gather_stream = nullptr;
+	cudaEvent_t ev_updated = nullptr, ev_gathered = nullptr;
+	~DpState() {
+		if (comm_grads) nccl_api().CommDestroy(comm_grads);
+		if (comm_params) nccl_api().CommDestroy(comm_params);
+		if (gather_stream) cudaStreamDestroy(gather_stream);
+		if (ev_updated) cudaEventDestroy(ev_updated);
+		if (ev_gathered) cudaEventDestroy(ev_gathered);
+	}
+};
+
 struct Model {
 	uint32_t n_in = 0, n_out = 0;
 	GridConfig grid;
@@ -291,6 +354,7 @@ struct Model {
 	cudaStream_t own_stream = nullptr;
 	cudaStream_t copy_stream = nullptr;  // host-buffer step: the targets travel here while the binning pass runs on own_stream
 	cudaEvent_t ev_inputs = nullptr, ev_targets = nullptr;
+	std::unique_ptr<DpState> dp;  // set by tcnnb_dp_init
 	cudaEvent_t pending_params_event = nullptr;  // caller-owned: the next reader of the parameters waits for it (tcnnb_wait_before_compute)
 	void wait_pending(cudaStream_t stream) {
 		if (pending_params_event) {
@@ -658,6 +722,44 @@ static void finalize_mlp_grads(Model& m, cudaStream_t stream) {
 	}
 }
 
+// One data-parallel step, natively over NCCL (tcnn_b200/dp.py has the same logic over torch.distributed).
+//   sharded optimizer: fwd+bwd on the shard -> fp16 gradient vector -> reduce-scatter: this rank's slice of the padded parameter
+//   vector -> Adam on that slice -> all-gather of the updated fp16 slices on a side stream. The next step's binning pass
+//   overlaps the all-gather; its fused kernel waits for it (pending_params_event).
+//   replicated: all-reduce of the table gradients (fp16) and of the network accumulator (fp32), full Adam everywhere.
+static void dp_training_step(Model& m, cudaStream_t stream, uint32_t shard_batch, uint32_t global_batch, const float* x, const float* y) {
+	if (!m.dp) throw std::runtime_error("dp_training_step: call tcnnb_dp_init first.");
+	DpState& d = *m.dp;
+	NcclApi& n = nccl_api();
+	training_step(m, stream, shard_batch, global_batch, x, y, false);
+	if (d.world == 1) {
+		optimizer_step(m, stream);
+		return;
+	}
+	if (!d.shard_optimizer) {
+		TCNNB_NCCL_CHECK(n.AllReduce(m.grads_fp16 + m.mlp.n_params, m.grads_fp16 + m.mlp.n_params, m.grid.n_params, ncclHalf, ncclSum, d.comm_grads, stream));
+		TCNNB_NCCL_CHECK(n.AllReduce(m.dw_accum.ptr, m.dw_accum.ptr, m.mlp.n_params, ncclFloat, ncclSum, d.comm_grads, stream));
+		optimizer_step(m, stream);
+		return;
+	}
+	if (m.mlp_grads_in_accum) {  // fp32 network weight-gradient sums -> the fp16 gradient vector (what the reference's buffer holds)
+		TCNNB_CUDA_CHECK(launch_mlp_grad_finalize(stream, m.mlp.n_params, m.dw_accum.ptr, m.grads_fp16));
+		++g_kernel_launches;
+		m.mlp_grads_in_accum = false;
+	}
+	const size_t chunk = m.n_params_padded / (size_t)d.world, lo = chunk * (size_t)d.rank;
+	TCNNB_NCCL_CHECK(n.ReduceScatter(m.grads_fp16, m.grads_fp16 + lo, chunk, ncclHalf, ncclSum, d.comm_grads, stream));
+	const uint64_t begin = lo, count = lo < m.n_params ? std::min<uint64_t>(chunk, m.n_params - lo) : 0;
+	if (count) optimizer_step(m, stream, 1, &begin, &count);
+	else ++m.adam_step_count;
+	TCNNB_CUDA_CHECK(cudaEventRecord(d.ev_updated, stream));
+	TCNNB_CUDA_CHECK(cudaStreamWaitEvent(d.gather_stream, d.ev_updated, 0));
+	TCNNB_NCCL_CHECK(n.AllGather(m.params_fp16 + lo, m.params_fp16, chunk, ncclHalf, d.comm_params, d.gather_stream));
+	TCNNB_CUDA_CHECK(cudaEventRecord(d.ev_gathered, d.gather_stream));
+	m.pending_params_event = d.ev_gathered;
+	d.masters_synced = false;
+}
+
 static void inference(Model& m, cudaStream_t stream, uint32_t batch, const float* x, float* out) {
 	check_batch(batch);
 	m.wait_pending(stream);
@@ -988,6 +1090,67 @@ int tcnnb_deserialize(tcnnb_model* m, const void* src_host, uint64_t size) {
 		mm.adam_step_count = st;
 	}
 	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
+	TCNNB_API_END
+}
+
+int tcnnb_dp_unique_id(void* out_id, uint64_t n_bytes) {
+	TCNNB_API_BEGIN
+	if (!out_id || n_bytes < sizeof(ncclUniqueId)) throw std::runtime_error("dp_unique_id: need a 128-byte buffer.");
+	ncclUniqueId id;
+	TCNNB_NCCL_CHECK(nccl_api().GetUniqueId(&id));
+	std::memcpy(out_id, &id, sizeof(id));
+	TCNNB_API_END
+}
+
+int tcnnb_dp_init(tcnnb_model* m, const void* id_grads, const void* id_params, int world_size, int rank, int shard_optimizer) {
+	TCNNB_API_BEGIN
+	Model& mm = m->impl;
+	if (world_size < 1 || rank < 0 || rank >= world_size) throw std::runtime_error("dp_init: bad world size / rank.");
+	auto d = std::make_unique<DpState>();
+	d->world = world_size;
+	d->rank = rank;
+	// slices must be 16-byte aligned and the network weights must sit inside slice 0, else fall back to replicated Adam
+	d->shard_optimizer = shard_optimizer != 0 && mm.n_params_padded % (8 * (size_t)world_size) == 0 && mm.n_params_padded / (size_t)world_size >= mm.mlp.n_params;
+	if (world_size > 1) {
+		if (!id_grads || !id_params) throw std::runtime_error("dp_init: null NCCL ids.");
+		ncclUniqueId a, b;
+		std::memcpy(&a, id_grads, sizeof(a));
+		std::memcpy(&b, id_params, sizeof(b));
+		TCNNB_NCCL_CHECK(nccl_api().CommInitRank(&d->comm_grads, world_size, a, rank));
+		TCNNB_NCCL_CHECK(nccl_api().CommInitRank(&d->comm_params, world_size, b, rank));
+	}
+	TCNNB_CUDA_CHECK(cudaStreamCreateWithFlags(&d->gather_stream, cudaStreamNonBlocking));
+	TCNNB_CUDA_CHECK(cudaEventCreateWithFlags(&d->ev_updated, cudaEventDisableTiming));
+	TCNNB_CUDA_CHECK(cudaEventCreateWithFlags(&d->ev_gathered, cudaEventDisableTiming));
+	mm.dp = std::move(d);
+	TCNNB_API_END
+}
+
+int tcnnb_dp_shards_optimizer(const tcnnb_model* m) { return m->impl.dp && m->impl.dp->world > 1 && m->impl.dp->shard_optimizer ? 1 : 0; }
+
+int tcnnb_dp_training_step(tcnnb_model* m, tcnnb_stream stream, uint32_t shard_batch_size, uint32_t global_batch_size, const float* input_dev, const float* target_dev) {
+	TCNNB_API_BEGIN
+	dp_training_step(m->impl, (cudaStream_t)stream, shard_batch_size, global_batch_size, input_dev, target_dev);
+	TCNNB_API_END
+}
+
+int tcnnb_dp_sync_full_precision(tcnnb_model* m, tcnnb_stream stream) {
+	TCNNB_API_BEGIN
+	Model& mm = m->impl;
+	if (mm.dp && mm.dp->world > 1 && mm.dp->shard_optimizer && !mm.dp->masters_synced) {
+		const size_t chunk = mm.n_params_padded / (size_t)mm.dp->world, lo = chunk * (size_t)mm.dp->rank;
+		mm.wait_pending((cudaStream_t)stream);
+		TCNNB_NCCL_CHECK(nccl_api().AllGather(mm.params_fp32 + lo, mm.params_fp32, chunk, ncclFloat, mm.dp->comm_grads, (cudaStream_t)stream));
+		mm.dp->masters_synced = true;
+	}
+	TCNNB_API_END
+}
+
+int tcnnb_dp_finish(tcnnb_model* m) {
+	TCNNB_API_BEGIN
+	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
+	m->impl.pending_params_event = nullptr;
+	m->impl.dp.reset();
 	TCNNB_API_END
 }
 

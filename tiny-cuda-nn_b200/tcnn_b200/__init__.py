@@ -59,6 +59,12 @@ ABI = [
     ("tcnnb_training_step", _int, [_vp, _vp, _u32, _vp, _vp, _int]),
     ("tcnnb_training_step_shard", _int, [_vp, _vp, _u32, _u32, _vp, _vp, _int]),
     ("tcnnb_optimizer_step", _int, [_vp, _vp]),
+    ("tcnnb_dp_unique_id", _int, [_vp, ctypes.c_uint64]),
+    ("tcnnb_dp_init", _int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    ("tcnnb_dp_shards_optimizer", _int, [_vp]),
+    ("tcnnb_dp_training_step", _int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),
+    ("tcnnb_dp_sync_full_precision", _int, [_vp, _vp]),
+    ("tcnnb_dp_finish", _int, [_vp]),
     ("tcnnb_wait_before_compute", _int, [_vp, _vp]),
     ("tcnnb_optimizer_step_ranges", _int, [_vp, _vp, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     ("tcnnb_mlp_gradient_accumulator", _vp, [_vp]),
@@ -238,6 +244,35 @@ class _Trainer:
                 "n_matrix": self._m.n_mlp_params,
             }
         return self._sharded
+
+    # ---- native data parallelism (NCCL inside libtcnn_b200; tcnn_b200/dp.py drives it)
+    def dp_native_init(self, group, shard_optimizer=True):
+        """Create this model's NCCL communicators across `group` (a torch.distributed NCCL group): two ids from rank 0."""
+        import torch
+        import torch.distributed as dist
+
+        lib, h = load(), self._m._h
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        ids = torch.zeros(256, dtype=torch.uint8)
+        if rank == 0:
+            buf = (ctypes.c_char * 128)()
+            for k in range(2):
+                _check(lib.tcnnb_dp_unique_id(buf, 128))
+                ids[128 * k : 128 * (k + 1)] = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8)
+        ids = ids.cuda()
+        dist.broadcast(ids, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(ids.cpu().numpy().tobytes())
+        _check(lib.tcnnb_dp_init(h, ctypes.c_char_p(raw[:128]), ctypes.c_char_p(raw[128:]), world, rank, int(bool(shard_optimizer))))
+        return bool(lib.tcnnb_dp_shards_optimizer(h))
+
+    def dp_training_step(self, inputs, targets, global_batch_size, stream=None):
+        _check(load().tcnnb_dp_training_step(self._m._h, _stream_handle(stream), inputs.shape[0], global_batch_size, inputs.data_ptr(), targets.data_ptr()))
+
+    def dp_sync_full_precision(self, stream=None):
+        _check(load().tcnnb_dp_sync_full_precision(self._m._h, _stream_handle(stream)))
+
+    def dp_finish(self):
+        _check(load().tcnnb_dp_finish(self._m._h))
 
     def wait_before_compute(self, event):
         """The next kernel of this model that reads the parameters waits for `event` (a torch.cuda.Event, kept alive here)."""

@@ -36,7 +36,7 @@ SLICE_GRANULARITY = 8
 
 
 class DataParallelTrainer:
-    def __init__(self, trainer, group=None, shard_optimizer=True):
+    def __init__(self, trainer, group=None, shard_optimizer=True, native=True):
         self.trainer = trainer
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -49,6 +49,13 @@ class DataParallelTrainer:
                 self.shard_optimizer = False  # slices must be aligned, and the network weights must sit inside slice 0
         self._masters_synced = True
         self._comm_stream = None
+        # Production engine: the whole step (collectives included) is one call into libtcnn_b200, which talks to NCCL itself --
+        # a Python-driven step costs ~0.4 ms of host time, more than the step takes on the device. The torch.distributed
+        # version below is the same logic; it serves backends without NCCL (the gloo CPU tests) and as readable reference.
+        self.native = False
+        if self.world > 1 and native and hasattr(trainer, "dp_native_init") and dist.get_backend(group) == "nccl":
+            self.shard_optimizer = trainer.dp_native_init(group, shard_optimizer)
+            self.native = True
 
     def shard(self, n_global):
         """[begin, end) of this rank's contiguous shard of a global batch; shards must stay multiples of 256."""
@@ -107,6 +114,10 @@ class DataParallelTrainer:
         if self.world == 1:
             t.training_step_shard(x_shard, y_shard, global_batch, run_optimizer=True)
             return
+        if self.native:
+            t.dp_training_step(x_shard, y_shard, global_batch)
+            self._masters_synced = not self.shard_optimizer
+            return
         t.training_step_shard(x_shard, y_shard, global_batch, run_optimizer=False)
         if not self.shard_optimizer:
             for buf in t.gradient_buffers():
@@ -129,10 +140,20 @@ class DataParallelTrainer:
         """All-gather the fp32 master parameters (the owner of a slice holds its current values)."""
         if not self.shard_optimizer or self._masters_synced:
             return
+        if self.native:
+            self.trainer.dp_sync_full_precision()
+            self._masters_synced = True
+            return
         m = self.trainer.sharded_buffers()["masters"]
         chunk = m.numel() // self.world
         self._all_gather(m, m[self.rank * chunk : (self.rank + 1) * chunk])
         self._masters_synced = True
+
+    def close(self):
+        """Tear the native communicators down (before torch.distributed's process group is destroyed)."""
+        if self.native:
+            self.trainer.dp_finish()
+            self.native = False
 
     def loss(self):
         """Sum of the ranks' partial losses == the single-GPU loss of the global batch."""
