@@ -39,6 +39,8 @@ __device__ __forceinline__ uint32_t bin_key(const float* __restrict__ pos, uint3
 template <uint32_t D>
 __global__ void bin_count_kernel(uint32_t n, const float* __restrict__ pos, uint32_t log2_r, uint32_t* __restrict__ keys, uint32_t* __restrict__ hist, uint4* __restrict__ zero_ptr, uint32_t zero_n16, float* __restrict__ zero_scalar) {
 	const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
+	pdl_wait();
+	pdl_launch_dependents();
 	// This kernel waits on atomic round trips and leaves the memory pipes idle: the step's gradient zeroing (GradientMode::Overwrite,
 	// grid.h:865-867) rides along here instead of being a separate 26 MB memset launch in front of the fused kernel.
 	for (uint32_t j = i; j < zero_n16; j += gridDim.x * blockDim.x) zero_ptr[j] = make_uint4(0u, 0u, 0u, 0u);
@@ -63,6 +65,8 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(uint32_t n_bins, uint32_
 	extern __shared__ uint32_t staged[];
 	__shared__ uint32_t warp_sums[32];
 	__shared__ uint32_t carry;
+	pdl_wait();
+	pdl_launch_dependents();
 	if (threadIdx.x == 0) carry = 0;
 	for (uint32_t base = 0; base < n_bins; base += SCAN_CHUNK) {
 		const uint32_t n = min(SCAN_CHUNK, n_bins - base);
@@ -124,6 +128,8 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(uint32_t n_bins, uint32_
 // kernel fetches positions / targets through it (one extra 12-byte read per sample, against ~100 table sectors per sample).
 __global__ void bin_scatter_kernel(uint32_t n, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm) {
 	const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
+	pdl_wait();
+	pdl_launch_dependents();
 	if (i >= n) return;
 	const uint2 kr = reinterpret_cast<const uint2*>(keys)[i];
 	perm[__ldg(cursor + kr.x) + kr.y] = i;
@@ -155,16 +161,18 @@ cudaError_t launch_binning(cudaStream_t stream, uint32_t n_pos_dims, uint32_t n,
 		if (err != cudaSuccess) return err;
 		attr_set = true;
 	}
+	cudaError_t err = cudaSuccess;
 	if (n_pos_dims == 2) {
-		bin_count_kernel<2><<<blocks, 256, 0, stream>>>(n, pos, log2_r, keys, hist, (uint4*)zero_ptr, zero_n16, zero_scalar);
+		err = launch_pdl(bin_count_kernel<2>, blocks, 256, 0, stream, n, pos, log2_r, keys, hist, (uint4*)zero_ptr, zero_n16, zero_scalar);
 	} else if (n_pos_dims == 3) {
-		bin_count_kernel<3><<<blocks, 256, 0, stream>>>(n, pos, log2_r, keys, hist, (uint4*)zero_ptr, zero_n16, zero_scalar);
+		err = launch_pdl(bin_count_kernel<3>, blocks, 256, 0, stream, n, pos, log2_r, keys, hist, (uint4*)zero_ptr, zero_n16, zero_scalar);
 	} else {
 		return cudaErrorInvalidValue;
 	}
-	bin_scan_kernel<<<1, 1024, SCAN_SMEM_WORDS * sizeof(uint32_t), stream>>>(n_bins, hist, cursor);
-	bin_scatter_kernel<<<blocks, 256, 0, stream>>>(n, keys, cursor, perm);
-	return cudaGetLastError();
+	if (err != cudaSuccess) return err;
+	err = launch_pdl(bin_scan_kernel, 1, 1024, SCAN_SMEM_WORDS * sizeof(uint32_t), stream, n_bins, hist, cursor);
+	if (err != cudaSuccess) return err;
+	return launch_pdl(bin_scatter_kernel, blocks, 256, 0, stream, n, (const uint32_t*)keys, (const uint32_t*)cursor, perm);
 }
 
 }  // namespace tcnnb

@@ -42,4 +42,29 @@ struct Pcg32 {
 	uint64_t state, inc;
 };
 
+
+// ---- programmatic dependent launch (PDL). Every kernel of the training step is launched with programmatic stream
+// serialization allowed: its CTAs may be scheduled -- and run their prologue -- while the kernel in front of it on the stream
+// is still draining, and block in pdl_wait() until that kernel has completed and its writes are visible. pdl_wait() sits in
+// front of the first global-memory access of each kernel, so the semantics are those of ordinary stream order; what is saved
+// is the launch latency between the six kernels of a step. pdl_launch_dependents() tells the scheduler that the NEXT
+// kernel's CTAs may start arriving (small kernels call it at once; the persistent fused kernel near its end).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid;
+	cfg.blockDim = block;
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace tcnnb

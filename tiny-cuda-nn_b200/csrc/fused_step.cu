@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 		asm volatile("st.shared.b32 [%0], %1;" ::"r"(s.levels + i * 4), "r"(v) : "memory");
 	}
 
+	pdl_wait();  // first access to global memory below: the previous kernel on the stream must have completed (common.cuh)
 	// Stage the fp16 weights: W_l rows are 128-byte tile rows (K-major, SWIZZLE_128B); unused columns are zeroed.
 	{
 		// W_l [out][in] row-major -> 128-byte tile rows (K-major, SWIZZLE_128B). Rows / columns beyond the network's width
@@ -510,8 +511,7 @@ static cudaError_t launch_impl(const FusedStepParams& p, uint32_t n_ctas, cudaSt
 	const size_t smem = fused_step_smem_bytes(p.n_hidden_layers, p.grid.padded_width, TRAIN);
 	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (err != cudaSuccess) return err;
-	kernel<<<n_ctas, 256, smem, stream>>>(p);
-	return cudaGetLastError();
+	return launch_pdl(kernel, n_ctas, 256, smem, stream, p);
 }
 
 cudaError_t launch_fused_step(const FusedStepParams& p, uint32_t n_pos_dims, bool train, uint32_t n_ctas, cudaStream_t stream) {

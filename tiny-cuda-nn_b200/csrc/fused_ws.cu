@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(ws_threads(SUBS), SUBS == 1 ? 2 : 1) fused_ws_
 		tmem_relinquish();
 	}
 
+	pdl_wait();  // everything above touched only shared / tensor memory; from here on the previous kernel's writes are needed
 	{
 		// W_l [out][in] row-major -> 128-byte tile rows (K-major, SWIZZLE_128B). Rows / columns beyond the network's width
 		// and the encoding's width are zero, which makes a 16- or 32-wide network an exact sub-problem of the 64-wide tiles.
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(ws_threads(SUBS), SUBS == 1 ? 2 : 1) fused_ws_
 			have_prev = true;
 			k_prev = k;
 		}
+		pdl_launch_dependents();  // the optimizer's CTAs may start arriving (they block until this grid has completed)
 		if (TRAIN && have_prev) {  // drain: the last tile of this sub-group
 			const uint32_t gp = k_prev & 1u, jp = k_prev >> 1;
 			mbar_wait(bar_park_full + 8 * gp, jp & 1u);
@@ -534,6 +536,7 @@ __global__ void __launch_bounds__(ws_threads(SUBS), SUBS == 1 ? 2 : 1) fused_ws_
 			}
 		}
 
+		pdl_launch_dependents();
 		// ---- flush the weight-gradient accumulators and the loss
 		if (TRAIN) {
 			tmem_ld_wait();
@@ -603,8 +606,7 @@ static cudaError_t launch_ws_impl(const FusedStepParams& p, uint32_t n_ctas, cud
 	const size_t smem = fused_ws_smem_bytes(p.n_hidden_layers, TRAIN, SUBS);
 	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (err != cudaSuccess) return err;
-	kernel<<<n_ctas, ws_threads(SUBS), smem, stream>>>(p);
-	return cudaGetLastError();
+	return launch_pdl(kernel, n_ctas, ws_threads(SUBS), smem, stream, p);
 }
 
 template <uint32_t D, bool TRAIN>

@@ -81,6 +81,7 @@ __global__ void adam_step_kernel(const AdamParams a, const uint32_t n_elements, 
                                  float* __restrict__ weights_full_precision, __half* __restrict__ weights, __half* __restrict__ gradients,
                                  float* __restrict__ dw_accum, float* __restrict__ first_moments, float* __restrict__ second_moments,
                                  uint32_t* __restrict__ param_steps) {
+	pdl_wait();  // no early pdl_launch_dependents(): a long bandwidth-bound kernel should not share its SMs with parked CTAs
 	const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
 	if (i >= n_elements) return;
 
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(256) adam_step_vec4_kernel(const AdamParams a,
                                       float4* __restrict__ weights_full_precision, uint2* __restrict__ weights, uint2* __restrict__ gradients,
                                       float4* __restrict__ dw_accum, float4* __restrict__ first_moments, float4* __restrict__ second_moments,
                                       uint4* __restrict__ param_steps) {
+	pdl_wait();
 	const uint32_t gidx = threadIdx.x + blockIdx.x * blockDim.x;
 	if (gidx >= n_groups) return;
 	const uint32_t i0 = gidx * 4;
@@ -221,6 +223,8 @@ __global__ void __launch_bounds__(256) adam_step_vec4_kernel(const AdamParams a,
 }
 
 __global__ void mlp_grad_finalize_kernel(uint32_t n, float* __restrict__ dw_accum, __half* __restrict__ gradients) {
+	pdl_wait();
+	pdl_launch_dependents();
 	const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
 	if (i < n) {
 		gradients[i] = (__half)dw_accum[i];
@@ -261,20 +265,18 @@ cudaError_t launch_adam_step(cudaStream_t stream, const AdamParams& a, uint32_t 
 	                    aligned(first_moments, 16) && aligned(second_moments, 16) && aligned(param_steps, 16) && (dw_accum == nullptr || aligned(dw_accum, 16));
 	if (vec_ok) {
 		const uint32_t n_groups = n_elements / 4;
-		adam_step_vec4_kernel<<<blocks_for(n_groups, 256), 256, 0, stream>>>(a, n_groups, n_matrix_weights, loss_scale, (float4*)weights_full_precision, (uint2*)weights,
-		                                                                   (uint2*)gradients, (float4*)dw_accum, (float4*)first_moments, (float4*)second_moments,
-		                                                                   (uint4*)param_steps);
+		return launch_pdl(adam_step_vec4_kernel, blocks_for(n_groups, 256), 256, 0, stream, a, n_groups, n_matrix_weights, loss_scale, (float4*)weights_full_precision,
+		                  (uint2*)weights, (uint2*)gradients, (float4*)dw_accum, (float4*)first_moments, (float4*)second_moments, (uint4*)param_steps);
 	} else {
-		adam_step_kernel<<<blocks_for(n_elements, 256), 256, 0, stream>>>(a, n_elements, n_matrix_weights, loss_scale, weights_full_precision, weights, gradients,
-		                                                                dw_accum, first_moments, second_moments, param_steps);
+		return launch_pdl(adam_step_kernel, blocks_for(n_elements, 256), 256, 0, stream, a, n_elements, n_matrix_weights, loss_scale, weights_full_precision, weights,
+		                  gradients, dw_accum, first_moments, second_moments, param_steps);
 	}
 	return cudaGetLastError();
 }
 
 cudaError_t launch_mlp_grad_finalize(cudaStream_t stream, uint32_t n, float* dw_accum, __half* gradients) {
 	if (n == 0) return cudaSuccess;
-	mlp_grad_finalize_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(n, dw_accum, gradients);
-	return cudaGetLastError();
+	return launch_pdl(mlp_grad_finalize_kernel, blocks_for(n, 256), 256, 0, stream, n, dw_accum, gradients);
 }
 
 }  // namespace tcnnb
