@@ -79,6 +79,23 @@ int tcnnb_optimizer_step(tcnnb_model* m, tcnnb_stream stream);
 /* The same optimizer step restricted to the parameter ranges [begins[r], begins[r] + counts[r]) (adam.h:48-129 is element-wise,
  * so a range is the reference kernel launched on a sub-span). Used by the sharded-optimizer data-parallel trainer: every rank
  * updates the network weights (a range starting at 0 that covers all of them) and its own slice of the grid table. */
+/* ---- module tier: tcnn::cpp::Module as returned by create_network_with_input_encoding (cpp_api.h:76-125, src/cpp_api.cu:71-158) --
+ * Parameters, gradients and activations are CALLER-owned device arrays (what the PyTorch extension passes, bindings.cpp:79-171):
+ * params / dL_dparams are fp16 [n_params] (network weights first, then the grid table; 16-byte aligned), output / dL_doutput are
+ * fp16 [n_elements][padded_output_width] rows, input is fp32 [n_elements][n_input_dims]. The handle is a tcnnb_model without
+ * trainer state: destroy with tcnnb_destroy; tcnnb_n_params / tcnnb_padded_output_width / tcnnb_hyperparams apply; the trainer
+ * calls do not. Differences from the reference, by design: forward keeps no context (backward recomputes the forward pass inside
+ * the fused kernel), and gradients w.r.t. the input positions are not implemented yet (dL_dinput must be null,
+ * prepare_input_gradients 0; anything else returns an error). dL_dparams is overwritten (GradientMode::Overwrite, cpp_api.cu:115);
+ * null = compute nothing. */
+int tcnnb_module_create(uint32_t n_input_dims, uint32_t n_output_dims, const char* encoding_json, const char* network_json, tcnnb_model** out);
+/* Module::initialize_params(seed, params_full_precision, scale) (cpp_api.cu:140-143): pcg32{seed}, network then grid; device fp32 [n_params]. */
+int tcnnb_module_initialize_params(tcnnb_model* m, uint64_t seed, float* params_full_precision_dev, float scale);
+int tcnnb_module_inference(tcnnb_model* m, tcnnb_stream stream, uint32_t n_elements, const float* input_dev, void* output_dev, const void* params_dev);
+int tcnnb_module_forward(tcnnb_model* m, tcnnb_stream stream, uint32_t n_elements, const float* input_dev, void* output_dev, const void* params_dev, int prepare_input_gradients);
+int tcnnb_module_backward(tcnnb_model* m, tcnnb_stream stream, uint32_t n_elements, float* dL_dinput_dev, const void* dL_doutput_dev, void* dL_dparams_dev, const float* input_dev,
+                          const void* output_dev, const void* params_dev);
+
 /* ---- data parallelism, natively over NCCL (no counterpart in the single-GPU reference) -------------
  * One process per GPU. Rendezvous is the host framework's job (torch.distributed in tcnn_b200/dp.py): rank 0 draws two NCCL
  * ids with tcnnb_dp_unique_id (128 bytes each), broadcasts them, and every rank calls tcnnb_dp_init. libnccl.so.2 is resolved

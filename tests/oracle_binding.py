@@ -171,6 +171,15 @@ class OracleModel:
         self.lib.orc_grid_backward(ctypes.byref(self.grid), x.shape[0], _p(x), _p(d_enc_soa), _p(g))
         return g
 
+    def backward_from_dy(self, x, dL_dout_bits):
+        """Module-tier backward (cpp_api.cu:105-117) restated from the stage functions: fp16-rounded gradients of all parameters
+        for a caller-supplied dL/d(output) [B][padded_out] (fp16 bit patterns). Output activation None only."""
+        enc = self.encode(x)
+        hidden, _ = self.mlp_forward(enc)
+        dW, d_enc = self.mlp_backward(enc, hidden, np.ascontiguousarray(dL_dout_bits))
+        dG = self.grid_backward(x, d_enc)
+        return np.concatenate([dW, dG]).astype(np.float16).astype(np.float32)
+
     def training_step(self, x, y, run_optimizer=True, want_loss_values=False):
         B = x.shape[0]
         lv = np.zeros((B, self.n_out), np.float32) if want_loss_values else None

@@ -429,3 +429,72 @@ def test_network_shapes_match_oracle(torch_cuda, width, n_hidden):
     for a, b in zip(dev_losses, ref_losses):
         assert abs(a - b) <= 3e-2 * abs(b) + 1e-6, (dev_losses, ref_losses)
     assert rae(model.network.inference(xd).cpu().numpy(), orc.inference(x), 99.0) < 5e-2
+
+
+@pytest.mark.parametrize("batch", [512, 32768])
+def test_module_tier_matches_trainer_tier_and_oracle(torch_cuda, batch):
+    """tcnn::cpp::Module semantics (src/cpp_api.cu:71-158): caller-owned fp16 parameters, padded fp16 outputs, dL_dparams from an
+    external dL_doutput. Checked against (i) the oracle's restatement of initialize_params, (ii) the trainer tier run on the
+    same parameters (which the golden tests tie to the reference), (iii) the oracle's forward / backward on a small batch."""
+    torch = torch_cuda
+    import ctypes
+
+    import tcnn_b200
+
+    cfg = load_cfg("hash3d_small")
+    mod = tcnn_b200.Module(3, 3, cfg["encoding"], cfg["network"])
+    model = tcnn_b200.create_from_config(3, 3, cfg)
+    assert mod.n_params == model.n_params and mod.n_output_dims == 16
+    orc = ob.OracleModel(3, 3, cfg, scales=model.grid_levels()["scales"])
+
+    # (i) initialize_params(seed, params_full_precision, scale): pcg32{seed}, network weights then grid table
+    for seed, scale in ((42, 1.0), (7, 0.5)):
+        rng = ob.default_rng(seed)
+        expect = np.zeros(orc.n_params, np.float32)
+        orc.lib.orc_initialize_params(ctypes.byref(orc.grid), ctypes.byref(orc.mlp), ctypes.byref(rng), expect.ctypes.data_as(ctypes.c_void_p))
+        got = mod.initial_params(seed, scale).cpu().numpy()
+        if scale == 1.0:
+            assert np.array_equal(got.view(np.uint32), expect.view(np.uint32))
+        else:
+            assert np.allclose(got, expect * scale, rtol=1e-6, atol=0)
+
+    # (ii) same parameters as the trainer -> same outputs (bit for bit) and the same gradients
+    x, y = make_batch(3, 3, batch)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    p16 = model.trainer.params().clone()
+    out_tap = torch.zeros(batch, 16, dtype=torch.float16, device="cuda")
+    dy_tap = torch.zeros(batch, 16, dtype=torch.float16, device="cuda")
+    model.set_debug_taps(output=out_tap, dL_doutput=dy_tap)
+    model.trainer.training_step(xd, yd, run_optimizer=False)
+    g_trainer = ob.half_bits_to_float(f16(model.trainer.param_gradients()))
+    out = mod.fwd(xd, p16)
+    out_inf = mod.fwd(xd, p16, inference=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(f16(out), f16(out_tap)) and np.array_equal(f16(out), f16(out_inf))
+    g_mod = ob.half_bits_to_float(f16(mod.bwd(xd, p16, dy_tap, output=out)))
+    n_mlp = model.n_mlp_params
+    assert rae(g_mod[:n_mlp], g_trainer[:n_mlp], 99.9) < 1e-3          # fp32 sums, different accumulation order only
+    assert rae(g_mod[n_mlp:], g_trainer[n_mlp:], 99.9) < 5e-3          # fp16 atomics in a different order
+    assert np.array_equal(g_mod[n_mlp:] != 0, g_trainer[n_mlp:] != 0)  # same set of touched table entries
+    # gradients are OVERWRITTEN, not accumulated: a second call gives the same result
+    g_again = ob.half_bits_to_float(f16(mod.bwd(xd, p16, dy_tap)))
+    assert rae(g_again, g_mod, 99.9) < 5e-3
+
+    # (iii) the oracle, with an arbitrary dL_doutput (small batch only: the oracle is a scalar CPU port)
+    if batch <= 512:
+        rng = np.random.default_rng(5)
+        dy = (rng.standard_normal((batch, 16)) * 1e-2).astype(np.float16)
+        dy[:, 3:] = 0
+        enc = orc.encode(x)
+        hidden, out_ref = orc.mlp_forward(enc)
+        assert np.array_equal(f16(out), out_ref.view(np.uint16).reshape(batch, 16)) or rae(ob.half_bits_to_float(f16(out)), ob.half_bits_to_float(out_ref), 99.0) < 2e-3
+        g_ref = orc.backward_from_dy(x, dy.view(np.uint16))
+        g_dev = ob.half_bits_to_float(f16(mod.bwd(xd, p16, torch.from_numpy(dy).cuda())))
+        assert rae(g_dev[:n_mlp], g_ref[:n_mlp], 99.9) < 1.2e-2
+        assert rae(g_dev[n_mlp:], g_ref[n_mlp:], 99.9) < 1.2e-2
+
+    # the two tiers do not mix, and unsupported requests fail loudly
+    with pytest.raises(tcnn_b200.TcnnError, match="tcnnb_module_"):
+        tcnn_b200._check(tcnn_b200.load().tcnnb_training_step(mod._h, None, batch, xd.data_ptr(), yd.data_ptr(), 0))
+    with pytest.raises(tcnn_b200.TcnnError, match="input positions"):
+        tcnn_b200._check(tcnn_b200.load().tcnnb_module_forward(mod._h, None, batch, xd.data_ptr(), out.data_ptr(), p16.data_ptr(), 1))

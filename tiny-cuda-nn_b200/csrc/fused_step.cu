@@ -367,6 +367,14 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 						// relative_l2_loss / l2_loss (losses/relative_l2.h:56-75, l2.h:56-74); pad lanes give 0.
 						__half dy[16];
 						const float n_total = (float)(p.loss_batch_size * p.n_out);
+						if (p.ext_dy) {
+							// Module::backward (cpp_api.cu:115-124): the caller's dL/d(output), through the output activation's transfer
+							const uint4* src = reinterpret_cast<const uint4*>(p.ext_dy + (size_t)osample * 16);
+							*reinterpret_cast<uint4*>(&dy[0]) = __ldg(src);
+							*reinterpret_cast<uint4*>(&dy[8]) = __ldg(src + 1);
+#pragma unroll
+							for (uint32_t j = 0; j < 16; ++j) dy[j] = act_bwd_h(p.output_activation, dy[j], y16[j]);
+						} else
 #pragma unroll
 						for (uint32_t j = 0; j < 16; ++j) {
 							float g = 0.0f;

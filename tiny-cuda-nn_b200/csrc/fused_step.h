@@ -30,7 +30,8 @@ struct FusedStepParams {
 	uint32_t batch_size;           // samples processed by this launch (multiple of 256)
 	uint32_t loss_batch_size;      // samples the loss is normalised over (== batch_size unless the batch is sharded over GPUs)
 	const float* positions;        // [batch][D] fp32
-	const float* targets;          // [batch][n_out] fp32 (training only)
+	const float* targets;          // [batch][n_out] fp32 (training step only)
+	const __half* ext_dy;          // [batch][16] fp16, module-tier backward: the caller's dL/d(output) replaces the loss (targets unused)
 	const uint32_t* perm;          // optional spatial binning: tile row i processes the caller's sample perm[i] (positions/targets/outputs)
 	// parameters: [MLP weights | grid table] fp16, and the matching fp16 gradient buffer (grid part accumulated with red.f16x2)
 	const __half* params;

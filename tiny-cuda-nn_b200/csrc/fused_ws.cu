@@ -361,9 +361,15 @@ __global__ void __launch_bounds__(ws_threads(SUBS), SUBS == 1 ? 2 : 1) fused_ws_
 			const uint32_t enc_cur = s_enc + e * TILE_BYTES;
 			const uint32_t osample = osample_next;
 			float tgt[N_TGT_PREFETCH];
+			uint4 edy_lo = make_uint4(0, 0, 0, 0), edy_hi = make_uint4(0, 0, 0, 0);
 			if (TRAIN) {
+				if (p.ext_dy) {  // module-tier backward: the caller's dL/d(output) row instead of targets
+					edy_lo = __ldg(reinterpret_cast<const uint4*>(p.ext_dy + (size_t)osample * 16));
+					edy_hi = __ldg(reinterpret_cast<const uint4*>(p.ext_dy + (size_t)osample * 16) + 1);
+				} else {
 #pragma unroll
-				for (uint32_t q = 0; q < N_TGT_PREFETCH; ++q) tgt[q] = q < p.n_out ? __ldg(p.targets + (size_t)osample * p.n_out + q) : 0.0f;
+					for (uint32_t q = 0; q < N_TGT_PREFETCH; ++q) tgt[q] = q < p.n_out ? __ldg(p.targets + (size_t)osample * p.n_out + q) : 0.0f;
+				}
 			}
 			if (tile + gridDim.x < n_tiles) osample_next = sample_of(tile + gridDim.x);
 			if (tid == 0) WS_STAMP(0, k, 0);
@@ -454,6 +460,14 @@ __global__ void __launch_bounds__(ws_threads(SUBS), SUBS == 1 ? 2 : 1) fused_ws_
 						// relative_l2_loss / l2_loss (losses/relative_l2.h:56-75, l2.h:56-74); pad lanes give 0.
 						__half dy[16];
 						const float n_total = (float)(p.loss_batch_size * p.n_out);
+						if (p.ext_dy) {
+							// Module::backward (cpp_api.cu:115-124): dL/d(output) comes from the caller and, like the loss gradient below,
+							// passes through the output activation's transfer (fully_fused_mlp.cu:758-762)
+							*reinterpret_cast<uint4*>(&dy[0]) = edy_lo;
+							*reinterpret_cast<uint4*>(&dy[8]) = edy_hi;
+#pragma unroll
+							for (uint32_t q = 0; q < 16; ++q) dy[q] = act_bwd_h(out_act, dy[q], y16[q]);
+						} else
 #pragma unroll
 						for (uint32_t q = 0; q < 16; ++q) {
 							float gq = 0.0f;

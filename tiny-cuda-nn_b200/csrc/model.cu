@@ -330,6 +330,7 @@ struct Model {
 	// trainer.h:489-503: one allocation [fp32 master | fp16 params | fp16 gradients]
 	DeviceBuffer<char> params_buffer;
 	size_t n_params_padded = 0;
+	bool module_only = false;  // tcnnb_module: no trainer-owned parameters / optimizer state
 	float* params_fp32 = nullptr;
 	__half* params_fp16 = nullptr;
 	__half* grads_fp16 = nullptr;
@@ -422,7 +423,31 @@ struct Model {
 	}
 };
 
-static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Value& cfg, uint32_t seed) {
+// initialize_params(rnd, params_full_precision, scale) of NetworkWithInputEncoding (network_with_input_encoding.h:124-130):
+// network weights first, then the grid table, one pcg32 stream. `dst` is a DEVICE fp32 array of n_params elements.
+static void init_params(Model& m, HostPcg32& rng, float* dst, float scale) {
+	const MlpConfig& mlp = m.mlp;
+	// MLP: xavier uniform on the host, sequential draws (fully_fused_mlp.cu:868-892, gpu_matrix.h:292-306)
+	{
+		std::vector<float> w(mlp.n_params);
+		std::vector<std::pair<uint32_t, uint32_t>> mats;
+		mats.emplace_back(mlp.width, mlp.in_width);
+		for (uint32_t i = 0; i + 1 < mlp.n_hidden_layers; ++i) mats.emplace_back(mlp.width, mlp.width);
+		mats.emplace_back(mlp.padded_out_width, mlp.width);
+		size_t pos = 0;
+		for (auto& rc : mats) {
+			const float bound = scale * std::sqrt(6.0f / (float)(rc.second + rc.first));
+			for (size_t i = 0; i < (size_t)rc.first * rc.second; ++i) w[pos++] = rng.next_float() * 2.0f * bound - bound;
+		}
+		TCNNB_CUDA_CHECK(cudaMemcpy(dst, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+	}
+	// grid: U(-1e-4, 1e-4) * scale generated on the device with the jump-ahead pattern (grid.h:1076-1079, random.h:56-69)
+	TCNNB_CUDA_CHECK(launch_random_uniform(nullptr, rng.device(), m.grid.n_params, dst + mlp.n_params, -1e-4f * scale, 1e-4f * scale));
+	++g_kernel_launches;
+	rng.advance(m.grid.n_params);
+}
+
+static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Value& cfg, uint32_t seed, bool module_only = false) {
 	TCNNB_CUDA_CHECK(cudaGetDevice(&m.device));
 	cudaDeviceProp prop;
 	TCNNB_CUDA_CHECK(cudaGetDeviceProperties(&prop, m.device));
@@ -529,48 +554,36 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 	// a multiple of 512 parameters (never-touched zero entries) so that a data-parallel job can cut it into equal, 16-byte
 	// aligned slices for any world size up to 64 (tcnn_b200/dp.py).
 	m.n_params_padded = (m.n_params + 511) / 512 * 512;
-	m.params_buffer.resize(m.n_params_padded * (sizeof(float) + 2 * sizeof(__half)));
-	m.params_buffer.zero();
-	m.params_fp32 = (float*)m.params_buffer.ptr;
-	m.params_fp16 = (__half*)(m.params_buffer.ptr + sizeof(float) * m.n_params_padded);
-	m.grads_fp16 = (__half*)(m.params_buffer.ptr + sizeof(float) * m.n_params_padded + sizeof(__half) * m.n_params_padded);
-	m.first_moments.resize(m.n_params);
-	m.first_moments.zero();
-	m.second_moments.resize(m.n_params);
-	m.second_moments.zero();
-	m.param_steps.resize(m.n_params);
-	m.param_steps.zero();
+	m.module_only = module_only;
+	if (!module_only) {  // the module tier works on caller-owned parameter / gradient arrays and has no optimizer state
+		m.params_buffer.resize(m.n_params_padded * (sizeof(float) + 2 * sizeof(__half)));
+		m.params_buffer.zero();
+		m.params_fp32 = (float*)m.params_buffer.ptr;
+		m.params_fp16 = (__half*)(m.params_buffer.ptr + sizeof(float) * m.n_params_padded);
+		m.grads_fp16 = (__half*)(m.params_buffer.ptr + sizeof(float) * m.n_params_padded + sizeof(__half) * m.n_params_padded);
+		m.first_moments.resize(m.n_params);
+		m.first_moments.zero();
+		m.second_moments.resize(m.n_params);
+		m.second_moments.zero();
+		m.param_steps.resize(m.n_params);
+		m.param_steps.zero();
+	}
 	m.dw_accum.resize(mlp.n_params);
 	m.dw_accum.zero();
 	m.scalars.resize(4);
 	m.scalars.zero();
 
-	// ---- initialisation: std::seed_seq{seed} -> pcg32{seeds[0]} (trainer.h:51-58)
-	std::seed_seq seq{seed};
-	std::vector<uint32_t> seeds(2);
-	seq.generate(seeds.begin(), seeds.end());
-	HostPcg32 rng{seeds.front()};
-	// MLP: xavier uniform on the host, sequential draws (fully_fused_mlp.cu:868-892, gpu_matrix.h:292-306)
-	{
-		std::vector<float> w(mlp.n_params);
-		std::vector<std::pair<uint32_t, uint32_t>> mats;
-		mats.emplace_back(mlp.width, mlp.in_width);
-		for (uint32_t i = 0; i + 1 < mlp.n_hidden_layers; ++i) mats.emplace_back(mlp.width, mlp.width);
-		mats.emplace_back(mlp.padded_out_width, mlp.width);
-		size_t pos = 0;
-		for (auto& rc : mats) {
-			const float scale = 1.0f * std::sqrt(6.0f / (float)(rc.second + rc.first));
-			for (size_t i = 0; i < (size_t)rc.first * rc.second; ++i) w[pos++] = rng.next_float() * 2.0f * scale - scale;
-		}
-		TCNNB_CUDA_CHECK(cudaMemcpy(m.params_fp32, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+	if (!module_only) {
+		// ---- initialisation: std::seed_seq{seed} -> pcg32{seeds[0]} (trainer.h:51-58)
+		std::seed_seq seq{seed};
+		std::vector<uint32_t> seeds(2);
+		seq.generate(seeds.begin(), seeds.end());
+		HostPcg32 rng{seeds.front()};
+		init_params(m, rng, m.params_fp32, 1.0f);
+		// fp32 -> fp16 (trainer.h:409-421)
+		TCNNB_CUDA_CHECK(launch_cast_params(nullptr, m.n_params, m.params_fp32, m.params_fp16));
+		++g_kernel_launches;
 	}
-	// grid: U(-1e-4, 1e-4) generated on the device with the jump-ahead pattern (grid.h:1076-1079, random.h:56-69)
-	TCNNB_CUDA_CHECK(launch_random_uniform(nullptr, rng.device(), m.grid.n_params, m.params_fp32 + mlp.n_params, -1e-4f, 1e-4f));
-	++g_kernel_launches;
-	rng.advance(m.grid.n_params);
-	// fp32 -> fp16 (trainer.h:409-421)
-	TCNNB_CUDA_CHECK(launch_cast_params(nullptr, m.n_params, m.params_fp32, m.params_fp16));
-	++g_kernel_launches;
 	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
 	TCNNB_CUDA_CHECK(cudaStreamCreateWithFlags(&m.own_stream, cudaStreamNonBlocking));
 	TCNNB_CUDA_CHECK(cudaStreamCreateWithFlags(&m.copy_stream, cudaStreamNonBlocking));
@@ -625,6 +638,7 @@ static uint32_t fused_grid_size(const Model& m, uint32_t batch) {
 // Adam over the parameter ranges [begin, begin + count) (all parameters when n_ranges == 0). One optimizer step whatever the
 // number of ranges: the data-parallel trainer updates the MLP weights everywhere and the grid entries of its own shard only.
 static void optimizer_step(Model& m, cudaStream_t stream, uint32_t n_ranges = 0, const uint64_t* begins = nullptr, const uint64_t* counts = nullptr) {
+	if (m.module_only) throw std::runtime_error("this handle was created with tcnnb_module_create: it has no optimizer.");
 	m.wait_pending(stream);
 	++m.adam_step_count;
 	AdamParams a = m.adam;
@@ -659,11 +673,21 @@ static void optimizer_step(Model& m, cudaStream_t stream, uint32_t n_ranges = 0,
 
 // `targets_ready`: optional event the fused kernel (the first consumer of `y`) waits for; everything before it in the step --
 // gradient zeroing, the binning pass -- only needs `x` and runs while the targets are still in flight.
-static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_t loss_batch, const float* x, const float* y, bool run_optimizer, cudaEvent_t targets_ready = nullptr) {
+// Caller-owned arrays of the module tier (cpp_api.h:76-104): working-precision parameters, gradient array, dL/d(output).
+struct ModuleIO {
+	const __half* params = nullptr;
+	__half* grads = nullptr;
+	const __half* dL_doutput = nullptr;
+};
+
+static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_t loss_batch, const float* x, const float* y, bool run_optimizer, cudaEvent_t targets_ready = nullptr,
+                          const ModuleIO* io = nullptr) {
 	check_batch(batch);
+	if (!io && m.module_only) throw std::runtime_error("this handle was created with tcnnb_module_create: use the tcnnb_module_* calls.");
+	__half* const grads_base = io ? io->grads : m.grads_fp16;
 	// GradientMode::Overwrite: zero the grid gradient table (grid.h:865-867) and the loss accumulator -- inside the binning pass
 	// when there is one, else as memsets.
-	__half* const grid_grads = m.grads_fp16 + m.mlp.n_params;
+	__half* const grid_grads = grads_base + m.mlp.n_params;
 	const size_t grid_grad_bytes = sizeof(__half) * m.grid.n_params;
 	const bool bin = m.binning && batch >= 16384;
 	const bool zero_in_binning = bin && (((uintptr_t)grid_grads | grid_grad_bytes) & 15u) == 0;
@@ -676,6 +700,14 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
 		TCNNB_CUDA_CHECK(cudaMemsetAsync(m.dw_accum.ptr, 0, sizeof(float) * m.mlp.n_params, stream));
 	}
 	FusedStepParams p = make_params(m, batch, loss_batch, x, y);
+	if (io) {
+		p.params = io->params;
+		p.grads = io->grads;
+		p.ext_dy = io->dL_doutput;
+		p.targets = nullptr;
+		p.loss_sum = nullptr;
+		p.loss_values = nullptr;
+	}
 	m.prof_mark(stream);
 	// Process the batch in (y, z)-column order: same sums, far fewer distinct memory sectors on the coarse levels (binning.cu).
 	if (bin) {
@@ -762,12 +794,58 @@ static void dp_training_step(Model& m, cudaStream_t stream, uint32_t shard_batch
 
 static void inference(Model& m, cudaStream_t stream, uint32_t batch, const float* x, float* out) {
 	check_batch(batch);
+	if (m.module_only) throw std::runtime_error("this handle was created with tcnnb_module_create: use the tcnnb_module_* calls.");
 	m.wait_pending(stream);
 	FusedStepParams p = make_params(m, batch, batch, x, nullptr);
 	p.out_fp32 = out;
 	p.loss_sum = nullptr;
 	TCNNB_CUDA_CHECK(launch_fused_step(p, m.grid.n_pos_dims, false, std::min(batch / TILE_M, 4u * (uint32_t)m.n_sms), stream));
 	++g_kernel_launches;
+}
+
+// ---- module tier (tcnn::cpp::Module for NetworkWithInputEncoding, cpp_api.cu:71-158): caller-owned parameters -------------
+static void check_module_ptr(const void* ptr, const char* what) {
+	if (!ptr) throw std::runtime_error(std::string("module: ") + what + " is null.");
+	if ((uintptr_t)ptr % 16 != 0) throw std::runtime_error(std::string("module: ") + what + " must be 16-byte aligned.");
+}
+
+// inference / forward: fp16 [n][padded_output_width] rows (column-major padded x n in the reference's terms, cpp_api.cu:82-83).
+// Nothing is saved for the backward pass -- it recomputes the forward inside the fused kernel (the gather + three MMAs per
+// tile are cheaper than writing and re-reading 2 x 64 x n fp16 activations, which is what the reference's context holds).
+static void module_forward(Model& m, cudaStream_t stream, uint32_t n, const float* x, void* output, const void* params) {
+	check_batch(n);
+	check_module_ptr(params, "params");
+	check_module_ptr(output, "output");
+	FusedStepParams p = make_params(m, n, n, x, nullptr);
+	p.params = (const __half*)params;
+	p.grads = nullptr;
+	p.out_fp16 = (__half*)output;
+	p.out_fp32 = nullptr;
+	p.loss_sum = nullptr;
+	TCNNB_CUDA_CHECK(launch_fused_step(p, m.grid.n_pos_dims, false, std::min(n / TILE_M, 4u * (uint32_t)m.n_sms), stream));
+	++g_kernel_launches;
+}
+
+// backward: dL_dparams (fp16 [n_params], OVERWRITTEN -- GradientMode::Overwrite, cpp_api.cu:115) from dL_doutput (fp16 [n][padded]).
+static void module_backward(Model& m, cudaStream_t stream, uint32_t n, float* dL_dinput, const void* dL_doutput, void* dL_dparams, const float* x, const void* params) {
+	if (dL_dinput) throw std::runtime_error("module: gradients w.r.t. the input positions are not implemented (pass dL_dinput = null).");
+	if (!dL_dparams) return;  // nothing to compute (GradientMode::Ignore)
+	check_module_ptr(params, "params");
+	check_module_ptr(dL_doutput, "dL_doutput");
+	check_module_ptr(dL_dparams, "dL_dparams");
+	ModuleIO io;
+	io.params = (const __half*)params;
+	io.grads = (__half*)dL_dparams;
+	io.dL_doutput = (const __half*)dL_doutput;
+	if (m.mlp_grads_in_accum) {
+		TCNNB_CUDA_CHECK(cudaMemsetAsync(m.dw_accum.ptr, 0, sizeof(float) * m.mlp.n_params, stream));
+		m.mlp_grads_in_accum = false;
+	}
+	training_step(m, stream, n, n, x, nullptr, false, nullptr, &io);
+	// network weight gradients: fp32 sums -> fp16 entries of the caller's array; re-arms the accumulator
+	TCNNB_CUDA_CHECK(launch_mlp_grad_finalize(stream, m.mlp.n_params, m.dw_accum.ptr, (__half*)dL_dparams));
+	++g_kernel_launches;
+	m.mlp_grads_in_accum = false;
 }
 
 static void ensure_staging(Model& m, uint32_t batch) {
@@ -1151,6 +1229,48 @@ int tcnnb_dp_finish(tcnnb_model* m) {
 	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
 	m->impl.pending_params_event = nullptr;
 	m->impl.dp.reset();
+	TCNNB_API_END
+}
+
+// ---- module tier ------------------------------------------------------------------------------------------------------------
+int tcnnb_module_create(uint32_t n_input_dims, uint32_t n_output_dims, const char* encoding_json, const char* network_json, tcnnb_model** out) {
+	TCNNB_API_BEGIN
+	if (!out) throw std::runtime_error("tcnnb_module_create: out is null");
+	*out = nullptr;
+	const std::string cfg = std::string("{\"encoding\": ") + (encoding_json ? encoding_json : "{}") + ", \"network\": " + (network_json ? network_json : "{}") + "}";
+	auto m = std::make_unique<tcnnb_model>();
+	build_model(m->impl, n_input_dims, n_output_dims, json::parse(cfg), 1337, /*module_only=*/true);
+	*out = m.release();
+	TCNNB_API_END
+}
+
+int tcnnb_module_initialize_params(tcnnb_model* m, uint64_t seed, float* params_full_precision_dev, float scale) {
+	TCNNB_API_BEGIN
+	if (!params_full_precision_dev) throw std::runtime_error("module: params_full_precision is null.");
+	HostPcg32 rng{seed};  // cpp_api.cu:140-143: pcg32 rng{seed}
+	init_params(m->impl, rng, params_full_precision_dev, scale);
+	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
+	TCNNB_API_END
+}
+
+int tcnnb_module_inference(tcnnb_model* m, tcnnb_stream stream, uint32_t n_elements, const float* input_dev, void* output_dev, const void* params_dev) {
+	TCNNB_API_BEGIN
+	module_forward(m->impl, (cudaStream_t)stream, n_elements, input_dev, output_dev, params_dev);
+	TCNNB_API_END
+}
+
+int tcnnb_module_forward(tcnnb_model* m, tcnnb_stream stream, uint32_t n_elements, const float* input_dev, void* output_dev, const void* params_dev, int prepare_input_gradients) {
+	TCNNB_API_BEGIN
+	if (prepare_input_gradients) throw std::runtime_error("module: gradients w.r.t. the input positions are not implemented (prepare_input_gradients must be 0).");
+	module_forward(m->impl, (cudaStream_t)stream, n_elements, input_dev, output_dev, params_dev);
+	TCNNB_API_END
+}
+
+int tcnnb_module_backward(tcnnb_model* m, tcnnb_stream stream, uint32_t n_elements, float* dL_dinput_dev, const void* dL_doutput_dev, void* dL_dparams_dev, const float* input_dev,
+                          const void* output_dev, const void* params_dev) {
+	TCNNB_API_BEGIN
+	(void)output_dev;  // the forward pass is recomputed; the saved output is not needed
+	module_backward(m->impl, (cudaStream_t)stream, n_elements, dL_dinput_dev, dL_doutput_dev, dL_dparams_dev, input_dev, params_dev);
 	TCNNB_API_END
 }
 

@@ -59,6 +59,11 @@ ABI = [
     ("tcnnb_training_step", _int, [_vp, _vp, _u32, _vp, _vp, _int]),
     ("tcnnb_training_step_shard", _int, [_vp, _vp, _u32, _u32, _vp, _vp, _int]),
     ("tcnnb_optimizer_step", _int, [_vp, _vp]),
+    ("tcnnb_module_create", _int, [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    ("tcnnb_module_initialize_params", _int, [_vp, ctypes.c_uint64, _vp, ctypes.c_float]),
+    ("tcnnb_module_inference", _int, [_vp, _vp, ctypes.c_uint32, _vp, _vp, _vp]),
+    ("tcnnb_module_forward", _int, [_vp, _vp, ctypes.c_uint32, _vp, _vp, _vp, ctypes.c_int]),
+    ("tcnnb_module_backward", _int, [_vp, _vp, ctypes.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp]),
     ("tcnnb_dp_unique_id", _int, [_vp, ctypes.c_uint64]),
     ("tcnnb_dp_init", _int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     ("tcnnb_dp_shards_optimizer", _int, [_vp]),
@@ -305,6 +310,61 @@ class _Trainer:
     def deserialize(self, blob):
         buf = ctypes.create_string_buffer(blob, len(blob))
         _check(load().tcnnb_deserialize(self._m._h, buf, len(blob)))
+
+
+class Module:
+    """tcnn::cpp::Module for a network with input encoding (cpp_api.h:76-125): caller-owned parameters, fp16 in/out.
+
+    Mirrors what bindings/torch/tinycudann/bindings.cpp hands to autograd: `fwd(input, params)` -> padded fp16 output,
+    `bwd(input, params, dL_doutput)` -> fp16 dL_dparams, `initial_params(seed)` -> fp32 parameter vector."""
+
+    def __init__(self, n_input_dims, n_output_dims, encoding_config, network_config):
+        lib = load()
+        handle = ctypes.c_void_p()
+        enc = encoding_config if isinstance(encoding_config, str) else json.dumps(encoding_config)
+        net = network_config if isinstance(network_config, str) else json.dumps(network_config)
+        _check(lib.tcnnb_module_create(n_input_dims, n_output_dims, enc.encode(), net.encode(), ctypes.byref(handle)))
+        self._h = handle
+        self.n_input_dims = n_input_dims
+        self.n_output_dims = lib.tcnnb_padded_output_width(handle)  # Module::n_output_dims() is the PADDED width (cpp_api.cu:137)
+        self.n_params = lib.tcnnb_n_params(handle)
+
+    def initial_params(self, seed=1337, scale=1.0):
+        import torch
+
+        p = torch.empty(self.n_params, dtype=torch.float32, device="cuda")
+        _check(load().tcnnb_module_initialize_params(self._h, seed, ctypes.c_void_p(p.data_ptr()), ctypes.c_float(scale)))
+        return p
+
+    def fwd(self, inputs, params, stream=None, inference=False):
+        import torch
+
+        out = torch.empty(inputs.shape[0], self.n_output_dims, dtype=torch.float16, device="cuda")
+        lib = load()
+        if inference:
+            _check(lib.tcnnb_module_inference(self._h, _stream_handle(stream), inputs.shape[0], inputs.data_ptr(), out.data_ptr(), params.data_ptr()))
+        else:
+            _check(lib.tcnnb_module_forward(self._h, _stream_handle(stream), inputs.shape[0], inputs.data_ptr(), out.data_ptr(), params.data_ptr(), 0))
+        return out
+
+    def bwd(self, inputs, params, dL_doutput, output=None, stream=None):
+        import torch
+
+        grads = torch.empty(self.n_params, dtype=torch.float16, device="cuda")
+        _check(load().tcnnb_module_backward(self._h, _stream_handle(stream), inputs.shape[0], None, dL_doutput.data_ptr(), grads.data_ptr(), inputs.data_ptr(),
+                                            output.data_ptr() if output is not None else None, params.data_ptr()))
+        return grads
+
+    def close(self):
+        if self._h:
+            load().tcnnb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 class TrainableModel:
