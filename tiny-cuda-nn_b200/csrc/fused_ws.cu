@@ -82,14 +82,21 @@ __global__ void __launch_bounds__(ws_threads(SUBS), SUBS == 1 ? 2 : 1) fused_ws_
 	// enc buffers: tile k uses buffer k % NE. Four of them in the one-CTA training shape: a sub-group then gathers its next
 	// tile without waiting for the MLP group to finish with its previous one (the enc tile is read until the last
 	// weight-gradient MMA of the tile), which takes the gather off the MLP chain's critical path.
-	constexpr uint32_t NE = (SUBS == 2 && TRAIN) ? 4u : 2u;
+#ifndef TCNNB_WS_ENC_BUFFERS
+#define TCNNB_WS_ENC_BUFFERS 2  // four buffers (gather never waits for an earlier tile's backward) measured 1.6 % slower: 32 KB less L1
+#endif
+	constexpr uint32_t NE = (SUBS == 2 && TRAIN) ? TCNNB_WS_ENC_BUFFERS : 2u;
 	const uint32_t s_h0 = s_enc + NE * TILE_BYTES;
 	const uint32_t s_dy = s_h0 + NH * TILE_BYTES;
 	const uint32_t s_park = s_dy + (TRAIN ? TILE_BYTES : 0);
-	const uint32_t s_w0 = s_park + (TRAIN && SUBS == 2 ? 2 * TILE_BYTES : 0);
-	// parked dL/d(enc) row `row`, 16-byte chunk `chunk` of buffer g: own tiles (SUBS == 2) or chunks 4..7 of enc[g] (SUBS == 1)
+	// The parked dL/d(enc) rows need enc_width columns; with an encoding of at most 32 features they fit the unused upper half
+	// of the two enc tiles (tile k parks into enc[k & 1], NE == 2) and the kernel does without park tiles of its own -- 32 KB of
+	// shared memory that the hardware hands to the L1 instead, which the table gathers make good use of.
+	const bool park_in_enc = NE == 2 && in_w <= 32;
+	const uint32_t s_w0 = s_park + (TRAIN && !park_in_enc ? 2 * TILE_BYTES : 0);
+	// parked dL/d(enc) row `row`, 16-byte chunk `chunk` of buffer g: chunks 4..7 of enc[g], or park tiles of their own
 	auto park_addr = [&](uint32_t g, uint32_t row, uint32_t chunk) {
-		return SUBS == 2 ? s_park + g * TILE_BYTES + sw128(row, chunk) : s_enc + g * TILE_BYTES + sw128(row, 4u + chunk);
+		return park_in_enc ? s_enc + g * TILE_BYTES + sw128(row, 4u + chunk) : s_park + g * TILE_BYTES + sw128(row, chunk);
 	};
 	const uint32_t s_wout = s_w0 + NH * (WIDTH * 128);
 	const uint32_t s_bars = s_wout + 16 * 128;  // 9 mbarriers
@@ -231,11 +238,11 @@ __global__ void __launch_bounds__(ws_threads(SUBS), SUBS == 1 ? 2 : 1) fused_ws_
 			if (lt == 0) WS_STAMP(1 + sub, k, 0);
 			if (je >= 1) mbar_wait(bar_enc_free + 8 * e, (je - 1) & 1u);
 			if (lt == 0) WS_STAMP(1 + sub, k, 1);
-			// zero this thread's half of the row (padding features are zero, grid.h:759-766). With SUBS == 1 the upper half of
+			// zero this thread's half of the row (padding features are zero, grid.h:759-766). With park_in_enc the upper half of
 			// the tile holds parked gradients instead: the forward MMA reads only the first in_w columns, and what the
 			// weight-gradient MMA makes of the rest lands in accumulator columns that are never flushed.
 #pragma unroll
-			for (uint32_t c = 0; SUBS == 2 && c < 4; ++c) {
+			for (uint32_t c = 0; !park_in_enc && c < 4; ++c) {
 				const uint32_t chunk = c < n_chunks / 2 ? hsel * (n_chunks / 2) + c : n_chunks + hsel * ((8 - n_chunks) / 2) + (c - n_chunks / 2);
 				st_shared_v4(enc_tile + sw128(row, chunk), 0, 0, 0, 0);
 			}
@@ -602,22 +609,23 @@ __global__ void __launch_bounds__(ws_threads(SUBS), SUBS == 1 ? 2 : 1) fused_ws_
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-size_t fused_ws_smem_bytes(uint32_t n_hidden_layers, bool train, uint32_t subs) {
-	const size_t enc_tiles = (subs == 2 && train) ? 4 : 2;
-	const size_t tiles = enc_tiles + n_hidden_layers + (train ? (subs == 2 ? 3 : 1) : 0);
+size_t fused_ws_smem_bytes(uint32_t n_hidden_layers, uint32_t enc_width, bool train, uint32_t subs) {
+	const size_t enc_tiles = (subs == 2 && train) ? TCNNB_WS_ENC_BUFFERS : 2;
+	const bool park_in_enc = enc_tiles == 2 && enc_width <= 32;
+	const size_t tiles = enc_tiles + n_hidden_layers + (train ? (park_in_enc ? 1 : 3) : 0);
 	return tiles * TILE_BYTES + n_hidden_layers * (WIDTH * 128) + 16 * 128 + 128 /* barriers, TMEM slot */ + 1024 /* alignment slack */;
 }
 
 // Two CTAs per SM (SUBS == 1): training only, parked gradients must fit the spare half of the enc tiles, two CTAs must fit
 // the SM's shared memory (227 KB) and tensor memory (2 x 256 columns).
 bool fused_ws_two_ctas_ok(uint32_t n_hidden_layers, uint32_t enc_width, bool train) {
-	return train && enc_width <= 32 && (n_hidden_layers + 2) * 64 <= 256 && 2 * (fused_ws_smem_bytes(n_hidden_layers, true, 1) + 1024) <= 227 * 1024;
+	return train && enc_width <= 32 && (n_hidden_layers + 2) * 64 <= 256 && 2 * (fused_ws_smem_bytes(n_hidden_layers, enc_width, true, 1) + 1024) <= 227 * 1024;
 }
 
 template <uint32_t D, bool TRAIN, bool GENERIC, uint32_t SUBS>
 static cudaError_t launch_ws_impl(const FusedStepParams& p, uint32_t n_ctas, cudaStream_t stream) {
 	auto kernel = fused_ws_kernel<D, 2, TRAIN, GENERIC, SUBS>;
-	const size_t smem = fused_ws_smem_bytes(p.n_hidden_layers, TRAIN, SUBS);
+	const size_t smem = fused_ws_smem_bytes(p.n_hidden_layers, p.grid.padded_width, TRAIN, SUBS);
 	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (err != cudaSuccess) return err;
 	return launch_pdl(kernel, n_ctas, ws_threads(SUBS), smem, stream, p);

@@ -233,16 +233,14 @@ __device__ __forceinline__ void level_corners(const LevelInfo& lv, const float (
 	}
 }
 
-// Gather the two fp16x2 entries of a corner pair. Every lane fetches the aligned 8-byte slot that holds entry idx0 (one
-// LDG.64); lanes whose partner entry does not live in that slot fetch it with a second, predicated 4-byte load.
-__device__ __forceinline__ void gather_pair_f16x2(const uint32_t* __restrict__ table, uint32_t idx0, uint32_t idx1, bool paired, uint32_t& v0, uint32_t& v1) {
-	const uint2 slot = __ldg(reinterpret_cast<const uint2*>(table + (idx0 & ~1u)));
-	const bool odd = idx0 & 1u;
-	v0 = odd ? slot.y : slot.x;
-	// The partner entry is fetched unconditionally: for paired lanes it lies in the slot just requested (an L1 hit on
-	// the in-flight sector, no extra L2 traffic), and the straight-line form keeps the loop free of predicated loads.
-	const uint32_t far = __ldg(table + idx1);
-	v1 = paired ? (odd ? slot.x : slot.y) : far;
+// Gather the two fp16x2 entries of a corner pair: two independent 4-byte loads (for an aligned pair they fall into the same
+// 32-byte sector, so the second one costs no extra L2 traffic). Deliberately NO arithmetic on the loaded values here: callers
+// keep several levels of loads in flight, and anything that touches a value -- an earlier version fetched the aligned 8-byte slot
+// and SELECTED the two halves -- makes the warp wait for the loads it has just issued (that version ran at a depth of one
+// level whatever the software pipeline said; scripts/ws_timeline.py: gather 10.2 -> see DESIGN.md section 3.1).
+__device__ __forceinline__ void gather_pair_f16x2(const uint32_t* __restrict__ table, uint32_t idx0, uint32_t idx1, bool /*paired*/, uint32_t& v0, uint32_t& v1) {
+	v0 = __ldg(table + idx0);
+	v1 = __ldg(table + idx1);
 }
 
 // Scatter-add two fp16x2 addends of a corner pair (red.global.add.noftz.f16x2 is what the reference's
