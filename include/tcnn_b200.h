@@ -79,6 +79,10 @@ int tcnnb_optimizer_step(tcnnb_model* m, tcnnb_stream stream);
 /* The same optimizer step restricted to the parameter ranges [begins[r], begins[r] + counts[r]) (adam.h:48-129 is element-wise,
  * so a range is the reference kernel launched on a sub-span). Used by the sharded-optimizer data-parallel trainer: every rank
  * updates the network weights (a range starting at 0 that covers all of them) and its own slice of the grid table. */
+/* generate_random_uniform<float>(stream, rng, n, out, lower, upper) (random.h:40-69) for a pcg32 with the given (state, inc):
+ * thread i draws 4 consecutive numbers after advance(4 i), as the reference does. The caller advances its generator by n. */
+int tcnnb_generate_random_uniform(tcnnb_stream stream, uint64_t rng_state, uint64_t rng_inc, uint64_t n_elements, float* out_dev, float lower, float upper);
+
 /* ---- module tier: tcnn::cpp::Module as returned by create_network_with_input_encoding (cpp_api.h:76-125, src/cpp_api.cu:71-158) --
  * Parameters, gradients and activations are CALLER-owned device arrays (what the PyTorch extension passes, bindings.cpp:79-171):
  * params / dL_dparams are fp16 [n_params] (network weights first, then the grid table; 16-byte aligned), output / dL_doutput are

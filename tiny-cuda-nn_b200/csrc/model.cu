@@ -1232,6 +1232,17 @@ int tcnnb_dp_finish(tcnnb_model* m) {
 	TCNNB_API_END
 }
 
+int tcnnb_generate_random_uniform(tcnnb_stream stream, uint64_t rng_state, uint64_t rng_inc, uint64_t n_elements, float* out_dev, float lower, float upper) {
+	TCNNB_API_BEGIN
+	if (n_elements && !out_dev) throw std::runtime_error("generate_random_uniform: out is null.");
+	Pcg32 rng;
+	rng.state = rng_state;
+	rng.inc = rng_inc;
+	TCNNB_CUDA_CHECK(launch_random_uniform((cudaStream_t)stream, rng, n_elements, out_dev, lower, upper));
+	++g_kernel_launches;
+	TCNNB_API_END
+}
+
 // ---- module tier ------------------------------------------------------------------------------------------------------------
 int tcnnb_module_create(uint32_t n_input_dims, uint32_t n_output_dims, const char* encoding_json, const char* network_json, tcnnb_model** out) {
 	TCNNB_API_BEGIN

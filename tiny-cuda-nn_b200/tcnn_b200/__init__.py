@@ -59,6 +59,7 @@ ABI = [
     ("tcnnb_training_step", _int, [_vp, _vp, _u32, _vp, _vp, _int]),
     ("tcnnb_training_step_shard", _int, [_vp, _vp, _u32, _u32, _vp, _vp, _int]),
     ("tcnnb_optimizer_step", _int, [_vp, _vp]),
+    ("tcnnb_generate_random_uniform", _int, [_vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, _vp, ctypes.c_float, ctypes.c_float]),
     ("tcnnb_module_create", _int, [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(_vp)]),
     ("tcnnb_module_initialize_params", _int, [_vp, ctypes.c_uint64, _vp, ctypes.c_float]),
     ("tcnnb_module_inference", _int, [_vp, _vp, ctypes.c_uint32, _vp, _vp, _vp]),
