@@ -169,6 +169,20 @@ def run_reference(args):
         line.update(value=cb["value"], ms_per_step=1e3 * BATCH / cb["value"], reference_mode="cpu_oracle_port", reference_modes=modes)
         line["cpu_baseline"] = cb
     line["e2e"] = {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    if ok:
+        # The reference is a GPU library, so its end-to-end number is measured like the new library's: through its own API with the
+        # inputs and targets in pinned HOST buffers (H2D every step) and the loss read back every step (ref_harness `bench ... e2e`).
+        cfg_file, jit = ("headline.json", 1) if best == "fully_fused_jit" else ("headline.json", 0)
+        e2e_steps = max(3, min(args.steps, 20))
+        cmd = [harness, "bench", os.path.join(ROOT, "tests", "golden", "configs", cfg_file), str(N_IN), str(N_OUT), str(BATCH), str(e2e_steps), "3", str(jit), "0", "1"]
+        try:
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+            js = [l for l in out.stdout.splitlines() if l.startswith("{")]
+            r = json.loads(js[-1])
+            line["e2e"] = {"value": BATCH / (r["wall_ms_per_step"] * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(r["h2d_bytes_per_step"]), "d2h_bytes_per_step": 4,
+                           "steps": e2e_steps, "api": f"Trainer::training_step + Trainer::loss ({best}) on pinned host buffers, wall clock"}
+        except Exception as e:  # noqa: BLE001
+            line["e2e"]["error"] = repr(e)
     line["gpu_launches"] = 0
     print(json.dumps(line))
 

@@ -206,7 +206,9 @@ static int cmd_dump(int argc, char** argv) {
 	return 0;
 }
 
-// bench <config.json> <n_in> <n_out> <B> <steps> <warmup> <jit 0|1> [inference 0|1]
+// bench <config.json> <n_in> <n_out> <B> <steps> <warmup> <jit 0|1> [inference 0|1] [e2e 0|1]
+// e2e = 1: every step copies the inputs and targets from PINNED HOST buffers to the device and reads the loss back -- the
+// same end-to-end region bench.py times for the new library (tcnnb_training_step_host); wall-clock timed.
 static int cmd_bench(int argc, char** argv) {
 	if (argc < 9) {
 		fprintf(stderr, "usage: bench config n_in n_out B steps warmup jit [inference]\n");
@@ -216,14 +218,28 @@ static int cmd_bench(int argc, char** argv) {
 	make_setup(s, argv[2], atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[8]) != 0);
 	const uint32_t steps = atoi(argv[6]), warmup = atoi(argv[7]);
 	const bool inference = argc > 9 && atoi(argv[9]) != 0;
+	const bool e2e = argc > 10 && atoi(argv[10]) != 0;
 	auto& trainer = s.model.trainer;
 	auto& network = s.model.network;
 	cudaStream_t stream;
 	CUDA_CHECK_THROW(cudaStreamCreate(&stream));
 	GPUMatrix<float> pred(s.n_out, s.B);
 
+	float *hx = nullptr, *hy = nullptr;
+	float e2e_loss = 0;
+	if (e2e) {
+		CUDA_CHECK_THROW(cudaMallocHost(&hx, s.x.n_bytes()));
+		CUDA_CHECK_THROW(cudaMallocHost(&hy, s.y.n_bytes()));
+		CUDA_CHECK_THROW(cudaMemcpy(hx, s.x.data(), s.x.n_bytes(), cudaMemcpyDeviceToHost));
+		CUDA_CHECK_THROW(cudaMemcpy(hy, s.y.data(), s.y.n_bytes(), cudaMemcpyDeviceToHost));
+	}
 	auto one = [&]() {
-		if (inference) {
+		if (e2e) {
+			CUDA_CHECK_THROW(cudaMemcpyAsync(s.x.data(), hx, s.x.n_bytes(), cudaMemcpyHostToDevice, stream));
+			CUDA_CHECK_THROW(cudaMemcpyAsync(s.y.data(), hy, s.y.n_bytes(), cudaMemcpyHostToDevice, stream));
+			auto ctx = trainer->training_step(stream, s.x, s.y);
+			e2e_loss = trainer->loss(stream, *ctx);  // device -> host + stream synchronisation (trainer.h:372-378)
+		} else if (inference) {
 			network->inference(stream, s.x, pred);
 		} else {
 			trainer->training_step(stream, s.x, s.y);
@@ -248,8 +264,9 @@ static int cmd_bench(int argc, char** argv) {
 		auto ctx = trainer->training_step(stream, s.x, s.y);
 		final_loss = trainer->loss(stream, *ctx);
 	}
-	printf("{\"impl\": \"reference\", \"mode\": \"%s\", \"jit_fusion\": %s, \"network\": \"%s\", \"batch\": %u, \"steps\": %u, \"warmup\": %u, \"ms_per_step\": %.6f, \"wall_ms_per_step\": %.6f, \"samples_per_s\": %.6e, \"n_params\": %zu, \"final_loss\": %.6g}\n",
-		inference ? "inference" : "training_step", network->jit_fusion() ? "true" : "false",
+	(void)e2e_loss;
+	printf("{\"impl\": \"reference\", \"e2e\": %s, \"h2d_bytes_per_step\": %zu, \"mode\": \"%s\", \"jit_fusion\": %s, \"network\": \"%s\", \"batch\": %u, \"steps\": %u, \"warmup\": %u, \"ms_per_step\": %.6f, \"wall_ms_per_step\": %.6f, \"samples_per_s\": %.6e, \"n_params\": %zu, \"final_loss\": %.6g}\n",
+		e2e ? "true" : "false", e2e ? s.x.n_bytes() + s.y.n_bytes() : (size_t)0, inference ? "inference" : "training_step", network->jit_fusion() ? "true" : "false",
 		s.config.value("network", json::object()).value("otype", "MLP").c_str(),
 		s.B, steps, warmup, ms / steps, wall_ms / steps, (double)s.B * steps / (ms * 1e-3), trainer->n_params(), final_loss);
 	return 0;

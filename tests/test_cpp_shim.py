@@ -38,3 +38,22 @@ def test_shim_sample_trains(torch_cuda):
     # default_rng_t{1337} + generate_random_uniform == the reference's generator (random.h:40-69), via the oracle restatement
     expect = ob.generate_random_uniform(ob.default_rng(1337), 8)
     assert np.array_equal(np.array(r["first_uniform"], np.float32), expect)
+
+
+def test_shim_sample_compiles_without_a_gpu():
+    """nvcc cross-compiles the application against the compatibility headers (compile only, no link, no GPU)."""
+    import shutil
+    import sys
+    import tempfile
+
+    sys.path.insert(0, ROOT)
+    from __graft_entry__ import json_include_dir
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    inc = json_include_dir()
+    if not os.path.exists(nvcc) or inc is None:
+        pytest.skip("nvcc or nlohmann/json.hpp not available")
+    with tempfile.TemporaryDirectory() as tmp:
+        out = subprocess.run([nvcc, "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-I", os.path.join(ROOT, "include"), "-I", inc, "-c",
+                              os.path.join(ROOT, "tests", "cpp", "shim_sample.cu"), "-o", os.path.join(tmp, "shim_sample.o")], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
