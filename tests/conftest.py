@@ -18,3 +18,12 @@ def oracle():
     import oracle_binding
 
     return oracle_binding.load()
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    torch.cuda.set_device(0)
+    return torch

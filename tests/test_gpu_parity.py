@@ -44,13 +44,6 @@ CASES = [
 ]
 
 
-@pytest.fixture(scope="module")
-def torch_cuda():
-    import torch
-
-    assert torch.cuda.is_available(), "GPU tests need a B200"
-    torch.cuda.set_device(0)
-    return torch
 
 
 def make_batch(n_in, n_out, B, seed=1337):
@@ -499,3 +492,47 @@ def test_module_tier_matches_trainer_tier_and_oracle(torch_cuda, batch):
         tcnn_b200._check(tcnn_b200.load().tcnnb_training_step(mod._h, None, batch, xd.data_ptr(), yd.data_ptr(), 0))
     with pytest.raises(tcnn_b200.TcnnError, match="input positions"):
         tcnn_b200._check(tcnn_b200.load().tcnnb_module_forward(mod._h, None, batch, xd.data_ptr(), out.data_ptr(), p16.data_ptr(), 1))
+
+
+def test_torch_autograd_layer_on_the_module_tier(torch_cuda):
+    """tcnn_b200.torch_modules mirrors tinycudann's modules.py: fp32 nn.Parameter, fp16 compute, batch padding to 256,
+    loss-scaled backward. The gradients autograd delivers must be the native module's, and a plain torch optimizer must train."""
+    torch = torch_cuda
+    import tcnn_b200
+    import tcnn_b200.torch_modules as tcnn
+
+    cfg = load_cfg("hash3d_small")
+    torch.manual_seed(0)
+    model = tcnn.NetworkWithInputEncoding(3, 3, cfg["encoding"], cfg["network"], seed=1337)
+    assert model.params.dtype == torch.float32 and model.params.numel() == model.native_tcnn_module.n_params
+    B = 1000  # not a multiple of 256: exercises the padding path (modules.py:222-226)
+    x = torch.rand(B, 3, device="cuda")
+    y = torch.stack([torch.sin(7 * x[:, 0]) * 0.5 + 0.5, x[:, 1] * x[:, 2], torch.cos(5 * x[:, 2]) * 0.5 + 0.5], 1)
+
+    out = model(x)
+    assert out.shape == (B, 3) and out.dtype == torch.float16
+    ((out.float() - y) ** 2).sum().backward()  # O(1) output gradients: the fp16 parameter gradients stay well above the fp16 floor
+    g_autograd = model.params.grad.clone()
+    # the same thing by hand on the native module: pad, dL/dout = 2 (out - y) scaled by 128, native backward, unscale
+    xp = torch.nn.functional.pad(x, [0, 0, 0, 1024 - B]).contiguous()
+    p16 = model.params.detach().to(torch.float16).contiguous()
+    full = model.native_tcnn_module.fwd(xp, p16)
+    dy = torch.zeros_like(full)
+    dy[:B, :3] = (2 * (full[:B, :3].float() - y) * model.loss_scale).to(torch.float16)
+    g_native = model.native_tcnn_module.bwd(xp, p16, dy).float() / model.loss_scale
+    torch.cuda.synchronize()
+    a, b = g_autograd.cpu().numpy(), g_native.cpu().numpy()
+    n_mlp = 7168
+    assert rae(a[:n_mlp], b[:n_mlp], 99.9) < 2e-3 and rae(a[n_mlp:], b[n_mlp:], 99.9) < 5e-3
+
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, eps=1e-15)
+    losses = []
+    for _ in range(60):
+        opt.zero_grad()
+        loss = ((model(x).float() - y) ** 2).mean()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < 0.1 * losses[0], losses[::10]
+    with pytest.raises(NotImplementedError):
+        model(x.clone().requires_grad_(True))
