@@ -43,7 +43,7 @@ struct ModelHandle {
 template <typename T>
 class Loss {
 public:
-	explicit Loss(const json& opts) : m_opts{opts} {}
+	explicit Loss(const json& opts) : m_opts(opts) {}  /* parentheses: brace-initialising a json from a json makes an array */
 	const json& hyperparams() const { return m_opts; }
 private:
 	json m_opts;
@@ -52,7 +52,7 @@ private:
 template <typename T>
 class Optimizer {
 public:
-	explicit Optimizer(const json& opts) : m_opts{opts} {}
+	explicit Optimizer(const json& opts) : m_opts(opts) {}
 	const json& hyperparams() const { return m_opts; }
 private:
 	json m_opts;
@@ -68,7 +68,7 @@ class NetworkWithInputEncoding {
 public:
 	/* network_with_input_encoding.h:49-55 */
 	NetworkWithInputEncoding(uint32_t n_dims_to_encode, uint32_t n_output_dims, const json& encoding, const json& network)
-	: m_n_in{n_dims_to_encode}, m_n_out{n_output_dims}, m_encoding{encoding}, m_network{network} {}
+	: m_n_in{n_dims_to_encode}, m_n_out{n_output_dims}, m_encoding(encoding), m_network(network) {}
 
 	/* object.h:214-282: input n_in x B (column-major = sample-contiguous), output n_out x B fp32 */
 	void inference(cudaStream_t stream, const GPUMatrixDynamic<float>& input, GPUMatrixDynamic<float>& output) {
