@@ -196,12 +196,22 @@ def ncu_traffic():
         return {}
 
 
+def closed_form_targets(torch, x, n_out):
+    """y_c = 0.5 + 0.5 sin(2 pi sum_d x_d (c + 1 + d) / 2^d): the smooth synthetic field both arms train on (oracle/ref_harness.cu make_targets)."""
+    cols = []
+    for c in range(n_out):
+        phase = torch.zeros(x.shape[0], dtype=torch.float32, device=x.device)
+        for d in range(x.shape[1]):
+            phase = phase + x[:, d] * float(c + 1 + d) / float(1 << d)
+        cols.append(0.5 + 0.5 * torch.sin(6.2831853 * phase))
+    return torch.stack(cols, 1).contiguous()
+
+
 def run_own(args):
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    import oracle_binding as ob  # input generator + cpu_baseline only
     import tcnn_b200
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -217,15 +227,16 @@ def run_own(args):
 
     # A pool of distinct batches (each rank draws its own stream) so consecutive steps do not re-read identical inputs.
     pool = 4
-    rng = ob.default_rng(1337 + rank)
+    rng = tcnn_b200.Pcg32(1337 + rank)  # the library's own generator (reference sequence); no oracle code on this arm
     xs, ys, xh, yh = [], [], [], []
     for _ in range(pool):
-        x = ob.generate_random_uniform(rng, BATCH * N_IN).reshape(BATCH, N_IN)
-        y = ob.make_targets(x, N_OUT)
-        xh.append(torch.from_numpy(x).pin_memory())
-        yh.append(torch.from_numpy(y).pin_memory())
-        xs.append(xh[-1].cuda())
-        ys.append(yh[-1].cuda())
+        x = tcnn_b200.generate_random_uniform(rng, BATCH * N_IN).view(BATCH, N_IN)
+        y = closed_form_targets(torch, x, N_OUT)
+        torch.cuda.synchronize()
+        xs.append(x)
+        ys.append(y)
+        xh.append(x.cpu().pin_memory())
+        yh.append(y.cpu().pin_memory())
     from tcnn_b200.dp import DataParallelTrainer
 
     # world == 1: plain training_step; else shard step + reduce-scatter of the table gradients + Adam on the rank's own table

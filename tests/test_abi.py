@@ -53,3 +53,20 @@ def test_json_reader_roundtrip():
 
     cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "configs", "headline.json")))
     assert cfg["encoding"]["log2_hashmap_size"] == 19 and cfg["network"]["n_neurons"] == 64
+
+
+def test_python_pcg32_matches_the_oracle_generator_state():
+    """tcnn_b200.Pcg32 (what bench.py seeds generate_random_uniform with) == pcg32{seed} of the reference (oracle restatement):
+    same (state, inc) after seeding and after jumping ahead by the number of values a fill consumes."""
+    import ctypes
+
+    import oracle_binding as ob
+    import tcnn_b200
+
+    for seed in (1337, 1338, 42):
+        a, b = tcnn_b200.Pcg32(seed), ob.default_rng(seed)
+        assert (a.state, a.inc) == (b.state, b.inc)
+        n = 3 * 1000 + 7
+        ob.generate_random_uniform(b, n)  # advances the oracle generator by n
+        a.advance(n)
+        assert (a.state, a.inc) == (b.state, b.inc)

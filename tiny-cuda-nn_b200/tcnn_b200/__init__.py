@@ -313,6 +313,47 @@ class _Trainer:
         _check(load().tcnnb_deserialize(self._m._h, buf, len(blob)))
 
 
+class Pcg32:
+    """Host-side state of tiny-cuda-nn's default_rng_t (PCG-XSH-RR 64/32, stream constant 1): what generate_random_uniform
+    needs to know -- (state, inc) -- and the O(log n) jump-ahead that advances it past the numbers a fill has consumed."""
+
+    MULT = 0x5851F42D4C957F2D
+    MASK = (1 << 64) - 1
+
+    def __init__(self, seed=1337, seq=1):
+        self.state = 0
+        self.inc = ((seq << 1) | 1) & self.MASK
+        self._step()
+        self.state = (self.state + seed) & self.MASK
+        self._step()
+
+    def _step(self):
+        self.state = (self.state * self.MULT + self.inc) & self.MASK
+
+    def advance(self, delta):
+        cur_mult, cur_plus, acc_mult, acc_plus = self.MULT, self.inc, 1, 0
+        while delta > 0:
+            if delta & 1:
+                acc_mult = (acc_mult * cur_mult) & self.MASK
+                acc_plus = (acc_plus * cur_mult + cur_plus) & self.MASK
+            cur_plus = ((cur_mult + 1) * cur_plus) & self.MASK
+            cur_mult = (cur_mult * cur_mult) & self.MASK
+            delta >>= 1
+        self.state = (acc_mult * self.state + acc_plus) & self.MASK
+
+
+def generate_random_uniform(rng, n, lower=0.0, upper=1.0, stream=None):
+    """generate_random_uniform<float>(stream, rng, n, ptr, lower, upper) (random.h:56-69): n uniform numbers on the current CUDA
+    device, the reference's sequence for this generator state; advances `rng` by n."""
+    import torch
+
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    _check(load().tcnnb_generate_random_uniform(_stream_handle(stream), ctypes.c_uint64(rng.state), ctypes.c_uint64(rng.inc), ctypes.c_uint64(n), ctypes.c_void_p(out.data_ptr()),
+                                                ctypes.c_float(lower), ctypes.c_float(upper)))
+    rng.advance(n)
+    return out
+
+
 class Module:
     """tcnn::cpp::Module for a network with input encoding (cpp_api.h:76-125): caller-owned parameters, fp16 in/out.
 
