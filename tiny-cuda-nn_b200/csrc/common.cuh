@@ -1,5 +1,6 @@
 // common.cuh -- shared device/host declarations for the tcnn_b200 kernels.
 #pragma once
+#include <cstdlib>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -61,7 +62,8 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 	cfg.stream = stream;
 	cudaLaunchAttribute attr[1];
 	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	static const int allowed = std::getenv("TCNNB_NO_PDL") ? 0 : 1;  // TCNNB_NO_PDL=1: plain stream-ordered launches (A/B switch)
+	attr[0].val.programmaticStreamSerializationAllowed = allowed;
 	cfg.attrs = attr;
 	cfg.numAttrs = 1;
 	return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
