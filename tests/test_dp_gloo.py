@@ -1,4 +1,4 @@
-"""Data-parallel host logic on CPU: two gloo ranks, each holding a replica, must reproduce the single-process step.
+"""Data-parallel host logic on CPU: two (and four) gloo ranks, each holding a replica, must reproduce the single-process step.
 (The CUDA trainer is swapped for an oracle-backed stand-in with the same interface; the class under test is
 tcnn_b200.dp.DataParallelTrainer, which bench.py --gpus N uses with the real trainer over NCCL.)"""
 import json
@@ -57,21 +57,23 @@ def _worker(rank, world, port, out_dir, shard_optimizer):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("shard_optimizer", [False, True])
-def test_two_rank_data_parallel_matches_single_process(tmp_path, shard_optimizer):
+@pytest.mark.parametrize("shard_optimizer,world", [(False, 2), (True, 2), (True, 4)])
+def test_data_parallel_matches_single_process(tmp_path, shard_optimizer, world):
     import oracle_binding as ob
 
-    world = 2
     port = _free_port()
     mp.spawn(_worker, args=(world, port, str(tmp_path), shard_optimizer), nprocs=world, join=True)
-    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    ranks = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    r0, r1 = ranks[0], ranks[1]
     # shards partition the batch
-    assert list(r0["shard"]) == [0, 512] and list(r1["shard"]) == [512, 1024]
+    per = B_GLOBAL // world
+    assert [list(r["shard"]) for r in ranks] == [[i * per, (i + 1) * per] for i in range(world)]
     # replicas stay bit-identical (same reduced gradients -> same Adam step, including the zero-gradient skip): the working
     # (fp16) parameters after every step, the fp32 masters once the slices have been exchanged
-    assert np.array_equal(r0["params16"], r1["params16"])
-    assert np.array_equal(r0["params"].view(np.uint32), r1["params"].view(np.uint32))
-    assert np.allclose(r0["losses"], r1["losses"], rtol=0, atol=0)
+    for r in ranks[1:]:
+        assert np.array_equal(r0["params16"], r["params16"])
+        assert np.array_equal(r0["params"].view(np.uint32), r["params"].view(np.uint32))
+        assert np.allclose(r0["losses"], r["losses"], rtol=0, atol=0)
 
     # single process, full batch
     rng = ob.default_rng(1337)
@@ -90,12 +92,12 @@ def test_two_rank_data_parallel_matches_single_process(tmp_path, shard_optimizer
     else:
         # the padded parameter vector is cut into two equal slices; rank 0's holds the network weights. The owner's
         # per-parameter step counters (adam.h:100) match the single-process run.
-        chunk = ((n + 511) // 512 * 512) // 2
+        chunk = ((n + 511) // 512 * 512) // world
         assert chunk >= n_mlp
-        assert list(r0["owned"]) == [0, chunk] and list(r1["owned"]) == [chunk, n - chunk]
-        for r in (r0, r1):
+        assert [list(r["owned"]) for r in ranks] == [[i * chunk, max(0, min(chunk, n - i * chunk))] for i in range(world)]
+        for r in ranks:
             b, c = r["owned"]
             assert np.array_equal(r["steps"][b : b + c], ref.steps[b : b + c])
-        # before the exchange a rank's masters of the OTHER rank's slice are stale (still the initial values there)
-        other = slice(chunk, n)
+        # before the exchange a rank's masters of the OTHER ranks' slices are stale (still the initial values there)
+        other = slice(chunk, 2 * chunk)
         assert not np.array_equal(r0["params_before_sync"][other], r0["params"][other])
