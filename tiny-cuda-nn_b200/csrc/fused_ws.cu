@@ -77,7 +77,10 @@ __global__ void __launch_bounds__(ws_threads(SUBS), SUBS == 1 ? 2 : 1) fused_ws_
 	const uint32_t in_w = p.grid.padded_width;
 
 	// ---- shared memory: [ enc_0 .. enc_{NE-1} | h_0 .. h_{NH-1} | dy | park_0 | park_1 | W_0 .. W_{NH-1} | W_out ] barriers
-	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+	// The dynamic segment starts 1024-byte aligned (declared so above; there is no static shared memory in this kernel), so no
+	// alignment slack is requested: the last kilobyte decides which shared-memory carve-out the SM uses, i.e. how much L1 is left.
+	const uint32_t smem_base = smem_u32(smem_raw);
+	if (smem_base & 1023u) __trap();
 	const uint32_t s_enc = smem_base;
 	// enc buffers: tile k uses buffer k % NE. Four of them in the one-CTA training shape: a sub-group then gathers its next
 	// tile without waiting for the MLP group to finish with its previous one (the enc tile is read until the last
@@ -613,7 +616,7 @@ size_t fused_ws_smem_bytes(uint32_t n_hidden_layers, uint32_t enc_width, bool tr
 	const size_t enc_tiles = (subs == 2 && train) ? TCNNB_WS_ENC_BUFFERS : 2;
 	const bool park_in_enc = enc_tiles == 2 && enc_width <= 32;
 	const size_t tiles = enc_tiles + n_hidden_layers + (train ? (park_in_enc ? 1 : 3) : 0);
-	return tiles * TILE_BYTES + n_hidden_layers * (WIDTH * 128) + 16 * 128 + 128 /* barriers, TMEM slot */ + 1024 /* alignment slack */;
+	return tiles * TILE_BYTES + n_hidden_layers * (WIDTH * 128) + 16 * 128 + 128 /* barriers, TMEM slot */;
 }
 
 // Two CTAs per SM (SUBS == 1): training only, parked gradients must fit the spare half of the enc tiles, two CTAs must fit
@@ -627,6 +630,10 @@ static cudaError_t launch_ws_impl(const FusedStepParams& p, uint32_t n_ctas, cud
 	auto kernel = fused_ws_kernel<D, 2, TRAIN, GENERIC, SUBS>;
 	const size_t smem = fused_ws_smem_bytes(p.n_hidden_layers, p.grid.padded_width, TRAIN, SUBS);
 	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (err != cudaSuccess) return err;
+	// ask for the smallest shared-memory carve-out that holds the resident CTAs (+1 KB per CTA the system reserves): the rest is L1
+	const size_t per_sm = (SUBS == 1 ? 2 : 1) * (smem + 1024);
+	err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((per_sm * 100 + 228 * 1024 - 1) / (228 * 1024)));
 	if (err != cudaSuccess) return err;
 	return launch_pdl(kernel, n_ctas, ws_threads(SUBS), smem, stream, p);
 }
