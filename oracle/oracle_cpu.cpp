@@ -344,6 +344,68 @@ void orc_grid_forward(const orc_grid_t* g, uint32_t B, const float* positions, c
 	}
 }
 
+// Input gradient of the grid encoding, for the module tier's dL_dinput (next row of SURVEY.md section 8f; the CUDA side does
+// not compute it yet): kernel_grid's `dy_dx` branch (grid.h:171-210) followed by kernel_grid_backward_input (grid.h:322-350).
+// Per level and feature, dy/dx_d = sum over the 2^(D-1) corners of the other dimensions of
+//   scale * prod_other(w) * ((float)val(x_d + 1) - (float)val(x_d)) * pos_derivative_d
+// in fp32 in the reference's loop order; then dL/dx_d = sum_k dL/dy_k * dy_k/dx_d over the encoded features k in order.
+// pos_derivative is 1 for Linear and 6 p (1 - p) for Smoothstep (common_device.h:980-982, 1017-1029).
+void orc_grid_input_gradient(const orc_grid_t* g, uint32_t B, const float* positions, const uint16_t* grid, const uint16_t* dL_denc, float* dL_dx) {
+	const uint32_t D = g->n_pos_dims, F = g->n_features_per_level, L = g->n_levels;
+#pragma omp parallel for schedule(static)
+	for (int64_t ii = 0; ii < (int64_t)B; ++ii) {
+		const uint32_t i = (uint32_t)ii;
+		float result[4] = {0, 0, 0, 0};
+		for (uint32_t level = 0; level < L; ++level) {
+			const uint16_t* level_grid = grid + (size_t)g->offsets[level] * F;
+			const uint32_t hashmap_size = g->offsets[level + 1] - g->offsets[level];
+			const float scale = g->scales[level];
+			const uint32_t resolution = grid_resolution(scale);
+			float pos[4], pos_derivative[4];
+			uint32_t pos_grid[4];
+			for (uint32_t d = 0; d < D; ++d) {
+				float p = fmaf(scale, positions[(size_t)i * D + d], 0.5f);
+				const float tmp = floorf(p);
+				pos_grid[d] = (uint32_t)(int)tmp;
+				p -= tmp;
+				pos_derivative[d] = g->interpolation == ORC_INTERP_SMOOTHSTEP ? 6 * p * (1.0f - p) : 1.0f;  // smoothstep_derivative, common_device.h:980-982
+				pos[d] = g->interpolation == ORC_INTERP_SMOOTHSTEP ? smoothstep(p) : p;
+			}
+			float grads[8][4] = {};
+			if (g->interpolation != ORC_INTERP_NEAREST) {  // Nearest: dy_dx stays zero (grid.h:120-133 returns before the gradient branch)
+				for (uint32_t grad_dim = 0; grad_dim < D; ++grad_dim) {
+					for (uint32_t idx = 0; idx < (1u << (D - 1)); ++idx) {
+						float weight = scale;
+						uint32_t local[4];
+						for (uint32_t non_grad_dim = 0; non_grad_dim + 1 < D; ++non_grad_dim) {
+							const uint32_t dim = non_grad_dim >= grad_dim ? non_grad_dim + 1 : non_grad_dim;
+							if ((idx & (1u << non_grad_dim)) == 0) {
+								weight *= 1 - pos[dim];
+								local[dim] = pos_grid[dim];
+							} else {
+								weight *= pos[dim];
+								local[dim] = pos_grid[dim] + 1;
+							}
+						}
+						local[grad_dim] = pos_grid[grad_dim];
+						const uint32_t left = grid_index(D, g->grid_type, hashmap_size, resolution, local);
+						local[grad_dim] = pos_grid[grad_dim] + 1;
+						const uint32_t right = grid_index(D, g->grid_type, hashmap_size, resolution, local);
+						for (uint32_t f = 0; f < F; ++f) {
+							grads[f][grad_dim] += weight * (h2f(level_grid[(size_t)right * F + f]) - h2f(level_grid[(size_t)left * F + f])) * pos_derivative[grad_dim];
+						}
+					}
+				}
+			}
+			for (uint32_t f = 0; f < F; ++f) {
+				const float dL_dy_local = h2f(dL_denc[i + (size_t)(level * F + f) * B]);
+				for (uint32_t d = 0; d < D; ++d) result[d] += dL_dy_local * grads[f][d];
+			}
+		}
+		for (uint32_t d = 0; d < D; ++d) dL_dx[(size_t)i * D + d] = result[d];
+	}
+}
+
 // kernel_grid_backward (grid.h:215-320): addend = (half)w * dL_dy (fp16 multiply), accumulated per entry.
 void orc_grid_backward(const orc_grid_t* g, uint32_t B, const float* positions, const uint16_t* dL_denc, double* grad_sum) {
 	const uint32_t D = g->n_pos_dims, F = g->n_features_per_level, L = g->n_levels;

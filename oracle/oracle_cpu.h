@@ -92,6 +92,8 @@ void orc_grid_forward(const orc_grid_t* g, uint32_t B, const float* positions, c
 /* dL_denc: SoA [padded_width][B] fp16 bits. grad_sum: double[n_params], the exact sum of the fp16-rounded
  * per-corner addends (half)w * dL_denc (grid.h:252-255); the device accumulates the same addends with f16x2 atomics. */
 void orc_grid_backward(const orc_grid_t* g, uint32_t B, const float* positions, const uint16_t* dL_denc_soa, double* grad_sum);
+/* dL/d(position) [B][D] fp32 from dL/d(encoded) SoA fp16: grid.h:171-210 (dy_dx) + grid.h:322-350 (backward_input). */
+void orc_grid_input_gradient(const orc_grid_t* g, uint32_t B, const float* positions, const uint16_t* grid_fp16, const uint16_t* dL_denc_soa, float* dL_dx);
 
 /* ---- MLP (fully_fused_mlp.cu:499-557 forward, :150-259 + :736-837 backward) ----
  * weights fp16 bits, row-major [out][in], matrices in order first/hidden.../last(padded rows).

@@ -169,3 +169,65 @@ def test_loss_gradient_matches_finite_difference():
     assert np.allclose(g[:, :dims], expect, rtol=2e-3, atol=1e-7)
     assert (g[:, dims:] == 0).all() and (values[:, dims:] == 0).all()
     assert np.allclose(values[:, :dims], (p32 - tgt) ** 2 / (p32 * p32 + 0.01) / (B * dims), rtol=1e-5)
+
+
+@pytest.mark.parametrize("interpolation", ["Linear", "Smoothstep"])
+def test_grid_input_gradient_matches_the_derivative_of_the_encoding(interpolation):
+    """orc_grid_input_gradient (grid.h:171-210 + 322-350 restated; the oracle for the module tier's dL_dinput, which the CUDA side
+    does not implement yet) against central finite differences of an fp64 evaluation of the same multilinear interpolation."""
+    import ctypes
+
+    import oracle_binding as ob
+
+    cfg = {"loss": {"otype": "L2"}, "optimizer": {"otype": "Adam"},
+           "encoding": {"otype": "HashGrid", "n_levels": 6, "n_features_per_level": 2, "log2_hashmap_size": 12, "base_resolution": 4, "per_level_scale": 1.7, "interpolation": interpolation},
+           "network": {"otype": "FullyFusedMLP", "n_neurons": 16, "n_hidden_layers": 1}}
+    m = ob.OracleModel(3, 3, cfg)
+    rng = np.random.default_rng(3)
+    B = 64
+    x = (0.05 + 0.9 * rng.random((B, 3))).astype(np.float32)
+    # larger table values than the 1e-4 initialisation, so that the derivative is well above fp16 / fp32 noise
+    table = rng.standard_normal(m.n_params - m.n_mlp).astype(np.float16)
+    m.params_fp16[m.n_mlp:] = table.view(np.uint16)
+    W = m.grid.padded_width
+    dL_denc = np.zeros((W, B), np.float16)
+    dL_denc[: 12] = rng.standard_normal((12, B)).astype(np.float16)
+    dL_dx = np.zeros((B, 3), np.float32)
+    m.lib.orc_grid_input_gradient(ctypes.byref(m.grid), B, x.ctypes.data_as(ctypes.c_void_p), table.view(np.uint16).ctypes.data_as(ctypes.c_void_p),
+                                  dL_denc.view(np.uint16).ctypes.data_as(ctypes.c_void_p), dL_dx.ctypes.data_as(ctypes.c_void_p))
+
+    # fp64 re-evaluation of sum_k dL_denc[k] * enc_k(x) with the oracle's own corner indices (integer part) and exact weights
+    def objective(xx):
+        _, idx = m.encode(xx.astype(np.float32), want_indices=True)  # [B][L][8] entry indices of the cell xx falls into
+        scales = np.array([m.grid.scales[l] for l in range(6)], np.float64)
+        total = np.zeros(B)
+        tab = table.astype(np.float64).reshape(-1, 2)
+        for l in range(6):
+            p = xx.astype(np.float64) * scales[l] + 0.5
+            frac = p - np.floor(p)
+            if interpolation == "Smoothstep":
+                frac = frac * frac * (3 - 2 * frac)
+            off = m.grid.offsets[l]
+            for c in range(8):
+                w = np.ones(B)
+                for d in range(3):
+                    w *= frac[:, d] if (c >> d) & 1 else 1 - frac[:, d]
+                v = tab[off + idx[:, l, c].astype(np.int64)]
+                for f in range(2):
+                    total += dL_denc[l * 2 + f].astype(np.float64) * w * v[:, f]
+        return total
+
+    h = 1e-4
+    for d in range(3):
+        e = np.zeros(3)
+        e[d] = h
+        # keep both evaluation points inside the cell of x at every level (the derivative is piecewise): skip samples that cross
+        lo, hi = x.astype(np.float64) - e, x.astype(np.float64) + e
+        same = np.ones(B, bool)
+        for l in range(6):
+            s = float(m.grid.scales[l])
+            same &= np.floor(lo[:, d] * s + 0.5) == np.floor(hi[:, d] * s + 0.5)
+        fd = (objective(hi) - objective(lo)) / (2 * h)
+        assert same.sum() > B // 2
+        err = np.abs(fd[same] - dL_dx[same, d].astype(np.float64))
+        assert err.max() <= 2e-3 * np.abs(fd[same]).max() + 1e-3, (d, err.max(), np.abs(fd[same]).max())
