@@ -49,6 +49,9 @@ using namespace fused;
 
 namespace {
 
+// enc buffers per CTA (tile k uses buffer k % 2). Four -- so that a gather never waits for an earlier tile's backward pass -- was
+// measured 1.6 % SLOWER: the 32 KB come out of the L1 that the table gathers live on.
+constexpr uint32_t WS_ENC_BUFFERS = 2;
 constexpr uint32_t WS_MLP_THREADS = 128;
 constexpr uint32_t WS_SUB_THREADS = 256;
 __host__ __device__ constexpr uint32_t ws_threads(uint32_t subs) { return WS_MLP_THREADS + subs * WS_SUB_THREADS; }  // 640 / 384
@@ -82,13 +85,7 @@ __global__ void __launch_bounds__(ws_threads(SUBS), SUBS == 1 ? 2 : 1) fused_ws_
 	const uint32_t smem_base = smem_u32(smem_raw);
 	if (smem_base & 1023u) __trap();
 	const uint32_t s_enc = smem_base;
-	// enc buffers: tile k uses buffer k % NE. Four of them in the one-CTA training shape: a sub-group then gathers its next
-	// tile without waiting for the MLP group to finish with its previous one (the enc tile is read until the last
-	// weight-gradient MMA of the tile), which takes the gather off the MLP chain's critical path.
-#ifndef TCNNB_WS_ENC_BUFFERS
-#define TCNNB_WS_ENC_BUFFERS 2  // four buffers (gather never waits for an earlier tile's backward) measured 1.6 % slower: 32 KB less L1
-#endif
-	constexpr uint32_t NE = (SUBS == 2 && TRAIN) ? TCNNB_WS_ENC_BUFFERS : 2u;
+	constexpr uint32_t NE = WS_ENC_BUFFERS;  // tile k uses enc buffer k % NE
 	const uint32_t s_h0 = s_enc + NE * TILE_BYTES;
 	const uint32_t s_dy = s_h0 + NH * TILE_BYTES;
 	const uint32_t s_park = s_dy + (TRAIN ? TILE_BYTES : 0);
@@ -613,7 +610,7 @@ __global__ void __launch_bounds__(ws_threads(SUBS), SUBS == 1 ? 2 : 1) fused_ws_
 
 // ------------------------------------------------------------------------------------------------------------------
 size_t fused_ws_smem_bytes(uint32_t n_hidden_layers, uint32_t enc_width, bool train, uint32_t subs) {
-	const size_t enc_tiles = (subs == 2 && train) ? TCNNB_WS_ENC_BUFFERS : 2;
+	const size_t enc_tiles = WS_ENC_BUFFERS;
 	const bool park_in_enc = enc_tiles == 2 && enc_width <= 32;
 	const size_t tiles = enc_tiles + n_hidden_layers + (train ? (park_in_enc ? 1 : 3) : 0);
 	return tiles * TILE_BYTES + n_hidden_layers * (WIDTH * 128) + 16 * 128 + 128 /* barriers, TMEM slot */;

@@ -631,7 +631,7 @@ static FusedStepParams make_params(Model& m, uint32_t batch, uint32_t loss_batch
 
 static uint32_t fused_grid_size(const Model& m, uint32_t batch) {
 	const uint32_t tiles = batch / TILE_M;
-	const uint32_t resident = 2u * (uint32_t)m.n_sms;  // __launch_bounds__(128, 2): two CTAs per SM, one wave
+	const uint32_t resident = 2u * (uint32_t)m.n_sms;  // fused_step_kernel: 256 threads, two CTAs per SM, one wave
 	return std::min(tiles, resident);
 }
 
