@@ -630,7 +630,7 @@ static cudaError_t launch_ws_impl(const FusedStepParams& p, uint32_t n_ctas, cud
 	if (err != cudaSuccess) return err;
 	// ask for the smallest shared-memory carve-out that holds the resident CTAs (+1 KB per CTA the system reserves): the rest is L1
 	const size_t per_sm = (SUBS == 1 ? 2 : 1) * (smem + 1024);
-	err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((per_sm * 100 + 228 * 1024 - 1) / (228 * 1024)));
+	err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)(per_sm * 100 / (228 * 1024))  /* rounded DOWN: the driver still has to fit the kernel, so it takes the first configuration that does (rounding up skipped the 100 KB one) */);
 	if (err != cudaSuccess) return err;
 	return launch_pdl(kernel, n_ctas, ws_threads(SUBS), smem, stream, p);
 }
