@@ -231,3 +231,61 @@ def test_grid_input_gradient_matches_the_derivative_of_the_encoding(interpolatio
         assert same.sum() > B // 2
         err = np.abs(fd[same] - dL_dx[same, d].astype(np.float64))
         assert err.max() <= 2e-3 * np.abs(fd[same]).max() + 1e-3, (d, err.max(), np.abs(fd[same]).max())
+
+
+@pytest.mark.parametrize("n_dims,n_features", [(2, 4), (3, 1), (3, 8), (4, 2)])
+def test_grid_forward_is_generic_in_features_and_dimensions(n_dims, n_features):
+    """The oracle's grid loops for F in {1, 4, 8} and D in {2, 4} (the next rows of SURVEY.md section 8f; the CUDA side covers
+    F = 2, D in {2, 3} today): encoded features against an fp64 re-evaluation of the multilinear blend over the oracle's own corner
+    indices, and the backward pass against the transpose of that blend. Index arithmetic is pinned by the golden vectors (it does
+    not depend on F); this pins the F- and D-generic accumulation loops around it."""
+    import ctypes
+
+    import oracle_binding as ob
+
+    L = 5
+    cfg = {"loss": {"otype": "L2"}, "optimizer": {"otype": "Adam"},
+           "encoding": {"otype": "HashGrid", "n_levels": L, "n_features_per_level": n_features, "log2_hashmap_size": 10, "base_resolution": 3, "per_level_scale": 1.6},
+           "network": {"otype": "FullyFusedMLP", "n_neurons": 16, "n_hidden_layers": 1}}
+    m = ob.OracleModel(n_dims, 2, cfg)
+    assert m.grid.padded_width == (L * n_features + 15) // 16 * 16
+    rng = np.random.default_rng(11)
+    B = 96
+    x = (0.02 + 0.96 * rng.random((B, n_dims))).astype(np.float32)
+    table = (rng.standard_normal(m.n_params - m.n_mlp) * 0.25).astype(np.float16)
+    m.params_fp16[m.n_mlp:] = table.view(np.uint16)
+    enc, idx = m.encode(x, want_indices=True)          # enc: [padded][B] fp16 bits, idx: [B][L][2^D]
+    enc = ob.half_bits_to_float(enc)
+    tab = table.astype(np.float64).reshape(-1, n_features)
+    C = 1 << n_dims
+    weights = np.zeros((B, L, C))
+    expect = np.zeros((L * n_features, B))
+    for l in range(L):
+        p = x.astype(np.float64) * float(m.grid.scales[l]) + 0.5
+        frac = p - np.floor(p)
+        off = m.grid.offsets[l]
+        for c in range(C):
+            w = np.ones(B)
+            for d in range(n_dims):
+                w *= frac[:, d] if (c >> d) & 1 else 1 - frac[:, d]
+            weights[:, l, c] = w
+            v = tab[off + idx[:, l, c].astype(np.int64)]
+            for f in range(n_features):
+                expect[l * n_features + f] += w * v[:, f]
+    # fp16 fma chain vs exact arithmetic: 2^D roundings of values of magnitude <= ~1
+    assert np.abs(enc[: L * n_features] - expect).max() < C * 2.0 ** -10
+    assert np.all(enc[L * n_features:] == 0)
+
+    # backward: gradient of sum_k dL_denc[k] * enc_k w.r.t. every table entry == scatter of w * dL_denc
+    dL = np.zeros((m.grid.padded_width, B), np.float16)
+    dL[: L * n_features] = rng.standard_normal((L * n_features, B)).astype(np.float16)
+    g = m.grid_backward(x, dL.view(np.uint16)).reshape(-1, n_features)
+    ref = np.zeros_like(g)
+    for l in range(L):
+        off = m.grid.offsets[l]
+        for c in range(C):
+            rows = off + idx[:, l, c].astype(np.int64)
+            for f in range(n_features):
+                np.add.at(ref[:, f], rows, weights[:, l, c].astype(np.float16).astype(np.float64) * dL[l * n_features + f].astype(np.float64))
+    scale = np.abs(ref).max()
+    assert np.abs(g - ref).max() < 2e-3 * scale + 1e-6
