@@ -16,6 +16,8 @@
  *   - all work is stream-ordered on the caller's stream; nothing synchronises except tcnnb_loss and *_host calls
  *   - errors: every call returns 0 on success, non-zero on failure; tcnnb_last_error() returns the message the
  *     reference would have thrown as std::runtime_error (common_host.h:71-110). There is NO CPU fallback.
+ *   - threading: like the reference (unsynchronised arenas / streams) a handle is NOT thread-safe; different
+ *     handles may be used from different threads. tcnnb_last_error() is per calling thread.
  */
 #ifndef TCNN_B200_H
 #define TCNN_B200_H
@@ -58,7 +60,9 @@ uint32_t tcnnb_padded_output_width(const tcnnb_model* m);      /* network->padde
 uint32_t tcnnb_encoded_width(const tcnnb_model* m);            /* encoding->padded_output_width() */
 float* tcnnb_params_full_precision(tcnnb_model* m);            /* trainer->params_full_precision(): device fp32 [n_params] */
 void* tcnnb_params(tcnnb_model* m);                            /* trainer->params(): device fp16 [n_params] */
-void* tcnnb_param_gradients(tcnnb_model* m);                   /* trainer->param_gradients(): device fp16 [n_params] */
+/* trainer->param_gradients(): device fp16 [n_params]. The network part is materialised from the fp32 accumulator on the stream
+ * of the step that produced it, and THAT stream is synchronised (no other stream is touched). */
+void* tcnnb_param_gradients(tcnnb_model* m);
 /* Level table of the grid encoding: offsets in entries (n_levels+1), per-level scale and resolution (grid.h:692-737). */
 int tcnnb_grid_levels(const tcnnb_model* m, uint32_t* n_levels, uint32_t* offsets, float* scales, uint32_t* resolutions);
 /* JSON with the resolved hyper-parameters (object.h hyperparams()); pointer valid until the next call on this model. */
@@ -137,6 +141,18 @@ int tcnnb_inference(tcnnb_model* m, tcnnb_stream stream, uint32_t batch_size, co
  * Copies inputs host->device (pinned staging inside the model), runs the step, copies the loss / outputs back and
  * synchronises. */
 int tcnnb_training_step_host(tcnnb_model* m, uint32_t batch_size, const float* input_host, const float* target_host, float* loss_out);
+/* Pipelined form of the same step. _submit enqueues {H2D of inputs and targets, training step, D2H of the loss} and returns a
+ * ticket at once; _wait blocks until that step has finished and returns its loss. Up to TWO steps may be in flight, so a caller
+ * that submits step i+1 before waiting for step i gets the copies of step i+1 overlapped with the kernels of step i (the copies
+ * run on a copy stream; the binning pass of a step starts when its positions have landed, the fused kernel when its targets
+ * have). Page-locked caller buffers are copied from directly; pageable ones are staged through pinned memory inside the model
+ * and may be reused by the caller as soon as _submit returns. A pinned buffer must stay untouched until its ticket is waited for.
+ * The handle is not thread-safe (as the reference's Trainer is not): calls on one model must come from one thread at a time. */
+int tcnnb_training_step_host_submit(tcnnb_model* m, uint32_t batch_size, const float* input_host, const float* target_host, uint64_t* ticket_out);
+int tcnnb_training_step_host_wait(tcnnb_model* m, uint64_t ticket, float* loss_out);
+/* Data-parallel form (after tcnnb_dp_init): this rank's HOST shard of a global batch; the loss returned by _wait is the GLOBAL
+ * loss (the partial sums are all-reduced on the device behind the step). */
+int tcnnb_dp_training_step_host_submit(tcnnb_model* m, uint32_t shard_batch_size, uint32_t global_batch_size, const float* input_host, const float* target_host, uint64_t* ticket_out);
 int tcnnb_inference_host(tcnnb_model* m, uint32_t batch_size, const float* input_host, float* output_host);
 
 /* ---- trainer->serialize / deserialize (trainer.h:442-482): fp16 params (+ optional Adam state) as raw bytes ---- */
@@ -155,6 +171,9 @@ typedef struct {
 	float* loss_values;   /* fp32 [batch][n_out] */
 } tcnnb_debug_taps;
 int tcnnb_set_debug_taps(tcnnb_model* m, const tcnnb_debug_taps* taps);
+/* Test-only switches (not dispatch knobs of the product path): "binning" 0/1 -- run the step without / with the spatial
+ * binning pass (tests assert both touch the same table entries); "inference_sync_kernel" 0/1 -- A/B timing of the two inference kernels. */
+int tcnnb_debug_set(tcnnb_model* m, const char* key, int value);
 /* Per-kernel device timing for the roofline report: when enabled, CUDA events bracket the binning kernels, the fused fwd+bwd kernel
  * and the optimizer kernel of every training step on the caller's stream; tcnnb_read_profile synchronises and returns the sums. */
 int tcnnb_set_profiling(tcnnb_model* m, int enable);

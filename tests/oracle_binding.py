@@ -269,6 +269,8 @@ class OracleShardTrainer:
         m = self.m
         m.grads_fp16[:] = self.grad_sums.numpy().astype(np.float16).view(np.uint16)
         for b, c in ranges if ranges is not None else [(0, m.n_params)]:
+            if c == 0:
+                continue
             n_matrix = max(0, min(m.n_mlp - b, c))
             sl = slice(b, b + c)
             m.lib.orc_adam_step(ctypes.byref(m.adam), ctypes.c_uint64(c), ctypes.c_uint64(n_matrix), ctypes.c_float(128.0), _p(m.params_fp32[sl]), _p(m.params_fp16[sl]),

@@ -155,13 +155,9 @@ cudaError_t launch_binning(cudaStream_t stream, uint32_t n_pos_dims, uint32_t n,
 	const uint32_t n_bins = binning_n_bins(log2_r, n_pos_dims);
 	uint32_t* cursor = hist + n_bins;  // hist: [n_bins counters (zero between calls) | n_bins cursors]
 	const uint32_t blocks = (n + 255) / 256;
-	static bool attr_set = false;
-	if (!attr_set) {
-		cudaError_t err = cudaFuncSetAttribute(bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SCAN_SMEM_WORDS * sizeof(uint32_t)));
-		if (err != cudaSuccess) return err;
-		attr_set = true;
-	}
-	cudaError_t err = cudaSuccess;
+	// per launch: the attribute is per device / context, and a process may build models on several GPUs
+	cudaError_t err = cudaFuncSetAttribute(bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SCAN_SMEM_WORDS * sizeof(uint32_t)));
+	if (err != cudaSuccess) return err;
 	if (n_pos_dims == 2) {
 		err = launch_pdl(bin_count_kernel<2>, blocks, 256, 0, stream, n, pos, log2_r, keys, hist, (uint4*)zero_ptr, zero_n16, zero_scalar);
 	} else if (n_pos_dims == 3) {

@@ -28,7 +28,8 @@ struct LevelInfo {
 	uint32_t use_hash;    // grid_type == Hash && size < dense stride (common_device.h:880)
 	uint32_t pow2_mask;   // size - 1 if size is a power of two, else 0 (index % size == index & mask)
 	uint32_t small_mod;   // 1 if every index this level can produce is < 2 * size (index % size == conditional subtract)
-	uint32_t pad;         // keeps the struct 32 bytes: two aligned 128-bit shared-memory loads
+	uint32_t wide_ok;     // 1 if `offset` is a multiple of 4 entries: 8-/16-byte merged reductions relative to the level base are aligned
+	                      // (Tiled grids with an odd base_resolution^D and log2_hashmap_size < 2 are not; they take 4-byte reductions)
 };
 
 struct GridMeta {

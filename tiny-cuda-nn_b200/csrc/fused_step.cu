@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256, 2) fused_step_kernel(const FusedStepParam
 				const __half2 a1 = __hmul2(__float2half2_rn(lc.w[2 * pr + 1]), grad);
 				const bool paired = (lc.paired >> pr) & 1u;
 				if (!(TCNNB_ABLATE(ABLATE_SCATTER))) {
-					scatter_pair_f16x2(lt, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(TCNNB_ABLATE(ABLATE_PAIRING)), *reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
+					scatter_pair_f16x2(lt, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(TCNNB_ABLATE(ABLATE_PAIRING)), lv.wide_ok != 0, *reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
 				}
 			}
 		}
@@ -523,8 +523,9 @@ static cudaError_t launch_impl(const FusedStepParams& p, uint32_t n_ctas, cudaSt
 }
 
 cudaError_t launch_fused_step(const FusedStepParams& p, uint32_t n_pos_dims, bool train, uint32_t n_ctas, cudaStream_t stream) {
-	if (n_pos_dims == 3) return train ? launch_impl<3, true>(p, n_ctas, stream) : launch_impl<3, false>(p, n_ctas, stream);
-	if (n_pos_dims == 2) return train ? launch_impl<2, true>(p, n_ctas, stream) : launch_impl<2, false>(p, n_ctas, stream);
+	if (train) return cudaErrorInvalidValue;  // the training step is fused_ws.cu; only the inference instantiation of this kernel is built
+	if (n_pos_dims == 3) return launch_impl<3, false>(p, n_ctas, stream);
+	if (n_pos_dims == 2) return launch_impl<2, false>(p, n_ctas, stream);
 	return cudaErrorInvalidValue;
 }
 

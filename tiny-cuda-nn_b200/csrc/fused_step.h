@@ -53,10 +53,8 @@ struct FusedStepParams {
 size_t fused_step_smem_bytes(uint32_t n_hidden_layers, uint32_t in_w, bool train);
 cudaError_t launch_fused_step(const FusedStepParams& p, uint32_t n_pos_dims, bool train, uint32_t n_ctas, cudaStream_t stream);
 
-// Warp-specialised variant (fused_ws.cu): subs = 2 -> one 640-thread CTA per SM (n_ctas <= #SMs); subs = 1 -> two 384-thread
-// CTAs per SM (n_ctas <= 2 * #SMs; only where fused_ws_two_ctas_ok()).
-size_t fused_ws_smem_bytes(uint32_t n_hidden_layers, uint32_t enc_width, bool train, uint32_t subs);
-bool fused_ws_two_ctas_ok(uint32_t n_hidden_layers, uint32_t enc_width, bool train);
-cudaError_t launch_fused_ws(const FusedStepParams& p, uint32_t n_pos_dims, bool train, uint32_t n_ctas, uint32_t subs, cudaStream_t stream);
+// Warp-specialised kernel (fused_ws.cu): one 640-thread CTA per SM (n_ctas <= #SMs), training step and inference.
+size_t fused_ws_smem_bytes(uint32_t n_hidden_layers, uint32_t enc_width, bool train);
+cudaError_t launch_fused_ws(const FusedStepParams& p, uint32_t n_pos_dims, bool train, uint32_t n_ctas, cudaStream_t stream);
 
 }  // namespace tcnnb

@@ -17,13 +17,9 @@
 //                                enc_free[g]  (tcgen05.commit -> memory: last MMA that reads enc[g] has finished)
 //                                park_full[g] (MLP -> memory: dL/d(enc) of the tile parked)
 //                                park_free[g] (memory -> MLP: parked gradients consumed)
-// Two shapes of the same kernel (template parameter SUBS):
-//   SUBS = 2: one persistent CTA per SM, 640 threads (4 MLP warps + two memory sub-groups), grid = #SMs.
-//   SUBS = 1: TWO persistent CTAs per SM, 384 threads each (4 MLP warps + one memory sub-group that serves every tile of the
-//             CTA, alternating between the two enc buffers). The phase timeline (scripts/ws_timeline.py) shows the single MLP
-//             chain of the SUBS = 2 shape to be the critical path while the memory warps wait ~15 % of the time; two CTAs give
-//             the SM two independent MLP chains. To fit two CTAs in shared memory the parked dL/d(enc) rows live in the unused
-//             upper half of the enc tiles (needs an encoding of at most 32 features) instead of in tiles of their own.
+// One persistent CTA per SM, 640 threads (4 MLP warps + two memory sub-groups), grid = #SMs. (A second shape -- two 384-thread
+// CTAs per SM with one memory sub-group each -- was measured slower, 0.265 vs 0.213 ms on the headline configuration, and
+// was removed; DESIGN.md section 3.1 keeps the number.)
 #include "common.cuh"
 #include "fused_common.cuh"
 #include "fused_step.h"
@@ -54,7 +50,8 @@ namespace {
 constexpr uint32_t WS_ENC_BUFFERS = 2;
 constexpr uint32_t WS_MLP_THREADS = 128;
 constexpr uint32_t WS_SUB_THREADS = 256;
-__host__ __device__ constexpr uint32_t ws_threads(uint32_t subs) { return WS_MLP_THREADS + subs * WS_SUB_THREADS; }  // 640 / 384
+constexpr uint32_t SUBS = 2;  // memory sub-groups per CTA
+constexpr uint32_t WS_THREADS = WS_MLP_THREADS + SUBS * WS_SUB_THREADS;  // 640
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -66,9 +63,8 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads) 
 
 }  // namespace
 
-template <uint32_t D, uint32_t F, bool TRAIN, bool GENERIC_ACT, uint32_t SUBS>
-__global__ void __launch_bounds__(ws_threads(SUBS), SUBS == 1 ? 2 : 1) fused_ws_kernel(const FusedStepParams p) {
-	constexpr uint32_t WS_THREADS = ws_threads(SUBS);
+template <uint32_t D, uint32_t F, bool TRAIN, bool GENERIC_ACT>
+__global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStepParams p) {
 	// ReLU hidden / linear output (the reference's default and the benchmark configuration) fold to the packed fast path at compile time
 	const uint32_t hid_act = GENERIC_ACT ? p.activation : (uint32_t)ACT_RELU;
 	const uint32_t out_act = GENERIC_ACT ? p.output_activation : (uint32_t)ACT_NONE;
@@ -199,7 +195,7 @@ __global__ void __launch_bounds__(ws_threads(SUBS), SUBS == 1 ? 2 : 1) fused_ws_
 					const __half2 a1 = __hmul2(__float2half2_rn(lc.w[2 * pr + 1]), grad);
 					const bool paired = (lc.paired >> pr) & 1u;
 					if (!(TCNNB_ABLATE(ABLATE_SCATTER))) {
-						scatter_pair_f16x2(ltab, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(TCNNB_ABLATE(ABLATE_PAIRING)), *reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
+						scatter_pair_f16x2(ltab, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(TCNNB_ABLATE(ABLATE_PAIRING)), lv.wide_ok != 0, *reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
 					}
 				}
 			}
@@ -241,10 +237,16 @@ __global__ void __launch_bounds__(ws_threads(SUBS), SUBS == 1 ? 2 : 1) fused_ws_
 			// zero this thread's half of the row (padding features are zero, grid.h:759-766). With park_in_enc the upper half of
 			// the tile holds parked gradients instead: the forward MMA reads only the first in_w columns, and what the
 			// weight-gradient MMA makes of the rest lands in accumulator columns that are never flushed.
+			// With park_in_enc only this thread's chunks BELOW in_w are zeroed (the parked upper half must be left alone), and only
+			// when the levels do not fill them (n_levels * F < in_w, e.g. 12 levels -> 24 features padded to 32): the L0 MMA and the
+			// dW0 weight-gradient MMA read all in_w columns.
+			if (!park_in_enc || p.grid.n_features < in_w) {
 #pragma unroll
-			for (uint32_t c = 0; !park_in_enc && c < 4; ++c) {
-				const uint32_t chunk = c < n_chunks / 2 ? hsel * (n_chunks / 2) + c : n_chunks + hsel * ((8 - n_chunks) / 2) + (c - n_chunks / 2);
-				st_shared_v4(enc_tile + sw128(row, chunk), 0, 0, 0, 0);
+				for (uint32_t c = 0; c < 4; ++c) {
+					if (c >= n_chunks / 2 && park_in_enc) break;
+					const uint32_t chunk = c < n_chunks / 2 ? hsel * (n_chunks / 2) + c : n_chunks + hsel * ((8 - n_chunks) / 2) + (c - n_chunks / 2);
+					st_shared_v4(enc_tile + sw128(row, chunk), 0, 0, 0, 0);
+				}
 			}
 			{
 				// Three levels in flight: the loads of levels l+1 and l+2 are issued before the values of level l are consumed.
@@ -609,45 +611,35 @@ __global__ void __launch_bounds__(ws_threads(SUBS), SUBS == 1 ? 2 : 1) fused_ws_
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-size_t fused_ws_smem_bytes(uint32_t n_hidden_layers, uint32_t enc_width, bool train, uint32_t subs) {
+size_t fused_ws_smem_bytes(uint32_t n_hidden_layers, uint32_t enc_width, bool train) {
 	const size_t enc_tiles = WS_ENC_BUFFERS;
 	const bool park_in_enc = enc_tiles == 2 && enc_width <= 32;
 	const size_t tiles = enc_tiles + n_hidden_layers + (train ? (park_in_enc ? 1 : 3) : 0);
 	return tiles * TILE_BYTES + n_hidden_layers * (WIDTH * 128) + 16 * 128 + 128 /* barriers, TMEM slot */;
 }
 
-// Two CTAs per SM (SUBS == 1): training only, parked gradients must fit the spare half of the enc tiles, two CTAs must fit
-// the SM's shared memory (227 KB) and tensor memory (2 x 256 columns).
-bool fused_ws_two_ctas_ok(uint32_t n_hidden_layers, uint32_t enc_width, bool train) {
-	return train && enc_width <= 32 && (n_hidden_layers + 2) * 64 <= 256 && 2 * (fused_ws_smem_bytes(n_hidden_layers, enc_width, true, 1) + 1024) <= 227 * 1024;
-}
-
-template <uint32_t D, bool TRAIN, bool GENERIC, uint32_t SUBS>
+template <uint32_t D, bool TRAIN, bool GENERIC>
 static cudaError_t launch_ws_impl(const FusedStepParams& p, uint32_t n_ctas, cudaStream_t stream) {
-	auto kernel = fused_ws_kernel<D, 2, TRAIN, GENERIC, SUBS>;
-	const size_t smem = fused_ws_smem_bytes(p.n_hidden_layers, p.grid.padded_width, TRAIN, SUBS);
+	auto kernel = fused_ws_kernel<D, 2, TRAIN, GENERIC>;
+	const size_t smem = fused_ws_smem_bytes(p.n_hidden_layers, p.grid.padded_width, TRAIN);
 	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (err != cudaSuccess) return err;
-	// ask for the smallest shared-memory carve-out that holds the resident CTAs (+1 KB per CTA the system reserves): the rest is L1
-	const size_t per_sm = (SUBS == 1 ? 2 : 1) * (smem + 1024);
+	// ask for the smallest shared-memory carve-out that holds the CTA (+1 KB the system reserves): the rest is L1
+	const size_t per_sm = smem + 1024;
 	err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)(per_sm * 100 / (228 * 1024))  /* rounded DOWN: the driver still has to fit the kernel, so it takes the first configuration that does (rounding up skipped the 100 KB one) */);
 	if (err != cudaSuccess) return err;
-	return launch_pdl(kernel, n_ctas, ws_threads(SUBS), smem, stream, p);
+	return launch_pdl(kernel, n_ctas, WS_THREADS, smem, stream, p);
 }
 
 template <uint32_t D, bool TRAIN>
-static cudaError_t launch_ws_act(const FusedStepParams& p, uint32_t n_ctas, uint32_t subs, cudaStream_t stream) {
+static cudaError_t launch_ws_act(const FusedStepParams& p, uint32_t n_ctas, cudaStream_t stream) {
 	const bool generic = p.activation != ACT_RELU || p.output_activation != ACT_NONE;
-	if (TRAIN && subs == 1) {
-		return generic ? launch_ws_impl<D, TRAIN, true, TRAIN ? 1 : 2>(p, n_ctas, stream) : launch_ws_impl<D, TRAIN, false, TRAIN ? 1 : 2>(p, n_ctas, stream);
-	}
-	return generic ? launch_ws_impl<D, TRAIN, true, 2>(p, n_ctas, stream) : launch_ws_impl<D, TRAIN, false, 2>(p, n_ctas, stream);
+	return generic ? launch_ws_impl<D, TRAIN, true>(p, n_ctas, stream) : launch_ws_impl<D, TRAIN, false>(p, n_ctas, stream);
 }
 
-cudaError_t launch_fused_ws(const FusedStepParams& p, uint32_t n_pos_dims, bool train, uint32_t n_ctas, uint32_t subs, cudaStream_t stream) {
-	if (subs == 1 && !fused_ws_two_ctas_ok(p.n_hidden_layers, p.grid.padded_width, train)) return cudaErrorInvalidValue;
-	if (n_pos_dims == 3) return train ? launch_ws_act<3, true>(p, n_ctas, subs, stream) : launch_ws_act<3, false>(p, n_ctas, subs, stream);
-	if (n_pos_dims == 2) return train ? launch_ws_act<2, true>(p, n_ctas, subs, stream) : launch_ws_act<2, false>(p, n_ctas, subs, stream);
+cudaError_t launch_fused_ws(const FusedStepParams& p, uint32_t n_pos_dims, bool train, uint32_t n_ctas, cudaStream_t stream) {
+	if (n_pos_dims == 3) return train ? launch_ws_act<3, true>(p, n_ctas, stream) : launch_ws_act<3, false>(p, n_ctas, stream);
+	if (n_pos_dims == 2) return train ? launch_ws_act<2, true>(p, n_ctas, stream) : launch_ws_act<2, false>(p, n_ctas, stream);
 	return cudaErrorInvalidValue;
 }
 

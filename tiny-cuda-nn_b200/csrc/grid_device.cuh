@@ -250,8 +250,12 @@ __device__ __forceinline__ void gather_pair_f16x2(const uint32_t* __restrict__ t
 // (x even), a 128-bit one with zero addends in the two other entries if they straddle the middle of a group (x % 4 == 1,
 // dense or hashed: idx0 ^ idx1 == 3; adding +0 leaves the other entries unchanged). Otherwise two 32-bit reductions.
 // (Sending the x-even case through the 128-bit form as well -- two shapes instead of three -- measured 2 % slower.)
-__device__ __forceinline__ void scatter_pair_f16x2(uint32_t* __restrict__ table, uint32_t idx0, uint32_t idx1, bool paired, uint32_t a0, uint32_t a1) {
-	if (paired) {
+// `wide_ok`: the level base is 16-byte aligned (LevelInfo::wide_ok), which the merged forms need; warp-uniform.
+__device__ __forceinline__ void scatter_pair_f16x2(uint32_t* __restrict__ table, uint32_t idx0, uint32_t idx1, bool paired, bool wide_ok, uint32_t a0, uint32_t a1) {
+	if (!wide_ok) {
+		asm volatile("red.relaxed.gpu.global.add.noftz.f16x2 [%0], %1;" ::"l"(table + idx0), "r"(a0) : "memory");
+		asm volatile("red.relaxed.gpu.global.add.noftz.f16x2 [%0], %1;" ::"l"(table + idx1), "r"(a1) : "memory");
+	} else if (paired) {
 		const bool odd = idx0 & 1u;
 		const uint32_t lo = odd ? a1 : a0, hi = odd ? a0 : a1;
 		asm volatile("red.relaxed.gpu.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(table + (idx0 & ~1u)), "r"(lo), "r"(hi) : "memory");

@@ -343,18 +343,31 @@ struct Model {
 	bool mlp_grads_in_accum = false;
 
 	// spatial binning scratch (binning.cu): sorted copies of the batch + permutation
-	bool binning = true;  // TCNNB_BINNING=0 disables
-	uint32_t ws_subs_override = 0;  // TCNNB_WS_SUBS
-	bool warp_specialized = true;   // fused_ws.cu by default; TCNNB_KERNEL=sync selects the bulk-synchronous fused_step.cu
+	bool binning = true;  // tcnnb_debug_set("binning", 0) (tests: binned and unbinned steps must touch the same entries)
+	bool inference_sync_kernel = false;  // tcnnb_debug_set("inference_sync_kernel", 1): fused_step.cu instead of fused_ws.cu (A/B timing)
+	cudaStream_t last_stream = nullptr;  // stream of the most recent step (tcnnb_param_gradients orders itself behind it)
 	DeviceBuffer<uint32_t> bin_keys, bin_hist, bin_perm;
 
 	// host staging for the *_host entry points
 	float* pinned = nullptr;
 	size_t pinned_floats = 0;
-	DeviceBuffer<float> stage_in, stage_target, stage_out;
-	cudaStream_t own_stream = nullptr;
-	cudaStream_t copy_stream = nullptr;  // host-buffer step: the targets travel here while the binning pass runs on own_stream
-	cudaEvent_t ev_inputs = nullptr, ev_targets = nullptr;
+	DeviceBuffer<float> stage_in, stage_out;
+	cudaStream_t own_stream = nullptr;   // compute stream of the *_host entry points
+	cudaStream_t copy_stream = nullptr;  // host->device copies of the pipelined host step (overlap the previous step's kernels)
+	// Pipelined host-buffer training step (tcnnb_training_step_host_submit / _wait): two slots, so that the copies of step i+1
+	// travel while the kernels of step i run. Each slot owns device staging, pinned host staging (for pageable callers) and events.
+	struct HostSlot {
+		DeviceBuffer<float> in, target;
+		float* pinned = nullptr;  // [pinned_floats]: inputs, targets; last element = the loss read back
+		size_t pinned_floats = 0;
+		cudaEvent_t ev_in = nullptr, ev_target = nullptr, ev_done = nullptr;
+		uint64_t ticket = 0;
+		bool busy = false;
+	};
+	HostSlot slots[2];
+	uint64_t next_ticket = 1;
+	const void* known_pinned[4] = {nullptr, nullptr, nullptr, nullptr};  // caller buffers already seen to be page-locked (skips the driver query)
+	uint32_t known_pinned_next = 0;
 	std::unique_ptr<DpState> dp;  // set by tcnnb_dp_init
 	cudaEvent_t pending_params_event = nullptr;  // caller-owned: the next reader of the parameters waits for it (tcnnb_wait_before_compute)
 	void wait_pending(cudaStream_t stream) {
@@ -374,10 +387,14 @@ struct Model {
 
 	~Model() {
 		if (pinned) cudaFreeHost(pinned);
+		for (auto& sl : slots) {
+			if (sl.pinned) cudaFreeHost(sl.pinned);
+			if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+			if (sl.ev_target) cudaEventDestroy(sl.ev_target);
+			if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+		}
 		if (own_stream) cudaStreamDestroy(own_stream);
 		if (copy_stream) cudaStreamDestroy(copy_stream);
-		if (ev_inputs) cudaEventDestroy(ev_inputs);
-		if (ev_targets) cudaEventDestroy(ev_targets);
 		for (auto e : prof_events) cudaEventDestroy(e);
 	}
 
@@ -417,6 +434,7 @@ struct Model {
 			else lv.use_hash = dense_ok ? 0 : 2;
 			lv.pow2_mask = (lv.size & (lv.size - 1)) == 0 ? lv.size - 1 : 0;
 			// dense index <= res * (res^D - 1) / (res - 1) < 2 * res^D: a conditional subtract is an exact modulo when size >= res^D
+			lv.wide_ok = (lv.offset % 4u) == 0 ? 1 : 0;
 			lv.small_mod = (lv.use_hash == 0 && stride != 0xFFFFFFFFu && lv.size >= stride && lv.resolution >= 2) ? 1 : 0;
 		}
 		return m;
@@ -455,11 +473,8 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 		throw std::runtime_error("tcnn_b200 requires an sm_100-class GPU (B200); found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor));
 	}
 	m.n_sms = prop.multiProcessorCount;
+#ifdef TCNNB_ENABLE_ABLATION  // profiling builds only (make ABLATION=1); the production library reads no environment switches
 	if (const char* e = std::getenv("TCNNB_ABLATE")) m.ablate = (uint32_t)std::atoi(e);
-	if (const char* e = std::getenv("TCNNB_BINNING")) m.binning = std::atoi(e) != 0;
-	if (const char* e = std::getenv("TCNNB_KERNEL")) m.warp_specialized = std::string(e) == "ws";
-	if (const char* e = std::getenv("TCNNB_WS_SUBS")) m.ws_subs_override = (uint32_t)std::atoi(e);
-#ifdef TCNNB_ENABLE_ABLATION
 	if (std::getenv("TCNNB_CLOCKS")) {
 		m.dbg_clock.resize((size_t)2 * m.n_sms * 3 * 16 * 16);
 		m.dbg_clock.zero();
@@ -538,6 +553,9 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 	if (m.grid.n_features_per_level != 2) throw std::runtime_error("tcnn_b200: fused path covers n_features_per_level == 2");
 	if (m.grid.n_pos_dims != 2 && m.grid.n_pos_dims != 3) throw std::runtime_error("tcnn_b200: fused path covers 2-D and 3-D inputs");
 	if (m.grid.padded_width > 64 || m.grid.n_levels > MAX_LEVELS) throw std::runtime_error("tcnn_b200: fused path covers encodings up to 64 features");
+	if (fused_ws_smem_bytes(mlp.n_hidden_layers, m.grid.padded_width, true) > 227 * 1024) {
+		throw std::runtime_error("tcnn_b200: this network depth / encoding width does not fit the SM's shared memory on the fused path");
+	}
 	if (m.grid.interpolation == INTERP_NEAREST) throw std::runtime_error("tcnn_b200: fused path covers Linear and Smoothstep interpolation");
 	if (m.grid.stochastic_interpolation) throw std::runtime_error("tcnn_b200: stochastic_interpolation is not built");
 
@@ -587,8 +605,11 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
 	TCNNB_CUDA_CHECK(cudaStreamCreateWithFlags(&m.own_stream, cudaStreamNonBlocking));
 	TCNNB_CUDA_CHECK(cudaStreamCreateWithFlags(&m.copy_stream, cudaStreamNonBlocking));
-	TCNNB_CUDA_CHECK(cudaEventCreateWithFlags(&m.ev_inputs, cudaEventDisableTiming));
-	TCNNB_CUDA_CHECK(cudaEventCreateWithFlags(&m.ev_targets, cudaEventDisableTiming));
+	for (auto& sl : m.slots) {
+		TCNNB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+		TCNNB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.ev_target, cudaEventDisableTiming));
+		TCNNB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+	}
 }
 
 static void check_batch(uint32_t batch) {
@@ -627,12 +648,6 @@ static FusedStepParams make_params(Model& m, uint32_t batch, uint32_t loss_batch
 	p.dbg_denc = (__half*)m.taps.dL_dencoded;
 	p.dbg_clock = m.dbg_clock.n ? m.dbg_clock.ptr : nullptr;
 	return p;
-}
-
-static uint32_t fused_grid_size(const Model& m, uint32_t batch) {
-	const uint32_t tiles = batch / TILE_M;
-	const uint32_t resident = 2u * (uint32_t)m.n_sms;  // fused_step_kernel: 256 threads, two CTAs per SM, one wave
-	return std::min(tiles, resident);
 }
 
 // Adam over the parameter ranges [begin, begin + count) (all parameters when n_ranges == 0). One optimizer step whatever the
@@ -729,15 +744,10 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
 	m.prof_mark(stream);
 	if (targets_ready) TCNNB_CUDA_CHECK(cudaStreamWaitEvent(stream, targets_ready, 0));
 	m.wait_pending(stream);  // e.g. the all-gather of the previous data-parallel step: binning above did not need the parameters
-	if (m.warp_specialized && m.mlp.n_hidden_layers <= 4) {
-		// one 640-thread CTA per SM; TCNNB_WS_SUBS=1 selects the two-CTAs-per-SM shape where it fits (measured slower on the
-		// headline configuration: 0.265 vs 0.213 ms)
-		const uint32_t subs = m.ws_subs_override == 1 && fused_ws_two_ctas_ok(m.mlp.n_hidden_layers, m.grid.padded_width, true) ? 1u : 2u;
-		TCNNB_CUDA_CHECK(launch_fused_ws(p, m.grid.n_pos_dims, true, std::min(batch / TILE_M, (subs == 1 ? 2u : 1u) * (uint32_t)m.n_sms), subs, stream));
-	} else {
-		TCNNB_CUDA_CHECK(launch_fused_step(p, m.grid.n_pos_dims, true, fused_grid_size(m, batch), stream));
-	}
+	// one persistent 640-thread CTA per SM (fused_ws.cu)
+	TCNNB_CUDA_CHECK(launch_fused_ws(p, m.grid.n_pos_dims, true, std::min(batch / TILE_M, (uint32_t)m.n_sms), stream));
 	++g_kernel_launches;
+	m.last_stream = stream;
 	m.prof_mark(stream);
 	m.mlp_grads_in_accum = true;
 	if (run_optimizer) {
@@ -792,6 +802,23 @@ static void dp_training_step(Model& m, cudaStream_t stream, uint32_t shard_batch
 	d.masters_synced = false;
 }
 
+// Sum of the ranks' partial losses (each normalised over the global batch) -> the global loss, in place on every rank.
+static void dp_reduce_loss(Model& m, cudaStream_t stream) {
+	if (m.dp && m.dp->world > 1) {
+		TCNNB_NCCL_CHECK(nccl_api().AllReduce(m.scalars.ptr, m.scalars.ptr, 1, ncclFloat, ncclSum, m.dp->comm_grads, stream));
+	}
+}
+
+static void launch_inference(Model& m, const FusedStepParams& p, uint32_t batch, cudaStream_t stream) {
+	if (m.inference_sync_kernel) {
+		TCNNB_CUDA_CHECK(launch_fused_step(p, m.grid.n_pos_dims, false, std::min(batch / TILE_M, 4u * (uint32_t)m.n_sms), stream));
+	} else {
+		TCNNB_CUDA_CHECK(launch_fused_ws(p, m.grid.n_pos_dims, false, std::min(batch / TILE_M, (uint32_t)m.n_sms), stream));
+	}
+	++g_kernel_launches;
+	m.last_stream = stream;
+}
+
 static void inference(Model& m, cudaStream_t stream, uint32_t batch, const float* x, float* out) {
 	check_batch(batch);
 	if (m.module_only) throw std::runtime_error("this handle was created with tcnnb_module_create: use the tcnnb_module_* calls.");
@@ -799,8 +826,7 @@ static void inference(Model& m, cudaStream_t stream, uint32_t batch, const float
 	FusedStepParams p = make_params(m, batch, batch, x, nullptr);
 	p.out_fp32 = out;
 	p.loss_sum = nullptr;
-	TCNNB_CUDA_CHECK(launch_fused_step(p, m.grid.n_pos_dims, false, std::min(batch / TILE_M, 4u * (uint32_t)m.n_sms), stream));
-	++g_kernel_launches;
+	launch_inference(m, p, batch, stream);
 }
 
 // ---- module tier (tcnn::cpp::Module for NetworkWithInputEncoding, cpp_api.cu:71-158): caller-owned parameters -------------
@@ -822,8 +848,7 @@ static void module_forward(Model& m, cudaStream_t stream, uint32_t n, const floa
 	p.out_fp16 = (__half*)output;
 	p.out_fp32 = nullptr;
 	p.loss_sum = nullptr;
-	TCNNB_CUDA_CHECK(launch_fused_step(p, m.grid.n_pos_dims, false, std::min(n / TILE_M, 4u * (uint32_t)m.n_sms), stream));
-	++g_kernel_launches;
+	launch_inference(m, p, n, stream);
 }
 
 // backward: dL_dparams (fp16 [n_params], OVERWRITTEN -- GradientMode::Overwrite, cpp_api.cu:115) from dL_doutput (fp16 [n][padded]).
@@ -857,8 +882,79 @@ static void ensure_staging(Model& m, uint32_t batch) {
 		m.pinned_floats = need;
 	}
 	m.stage_in.resize(std::max(m.stage_in.n, (size_t)batch * m.n_in));
-	m.stage_target.resize(std::max(m.stage_target.n, (size_t)batch * m.n_out));
 	m.stage_out.resize(std::max(m.stage_out.n, (size_t)batch * m.n_out));
+}
+
+static bool host_ptr_is_pinned(Model& m, const void* ptr) {
+	for (const void* k : m.known_pinned) if (k == ptr) return true;
+	cudaPointerAttributes attr{};
+	const bool pinned = cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	if (pinned) m.known_pinned[m.known_pinned_next++ % 4] = ptr;
+	return pinned;
+}
+
+static void dp_training_step(Model& m, cudaStream_t stream, uint32_t shard_batch, uint32_t global_batch, const float* x, const float* y);
+static void dp_reduce_loss(Model& m, cudaStream_t stream);
+
+// Enqueue one training step on HOST buffers and return at once: host->device copies on the copy stream (they overlap the kernels
+// of the step submitted before), the step on the model's compute stream (the binning pass starts when the positions have
+// landed, the fused kernel when the targets have), the loss read-back behind it. At most two steps are in flight.
+static uint64_t host_step_submit(Model& m, uint32_t batch, uint32_t global_batch, const float* x_host, const float* y_host, bool data_parallel) {
+	check_batch(batch);
+	const uint64_t ticket = m.next_ticket;
+	Model::HostSlot& sl = m.slots[ticket & 1u];
+	if (sl.busy) throw std::runtime_error("training_step_host_submit: two steps are already in flight; collect ticket " + std::to_string(sl.ticket) + " with tcnnb_training_step_host_wait first.");
+	const size_t n_x = (size_t)batch * m.n_in, n_y = (size_t)batch * m.n_out;
+	sl.in.resize(std::max(sl.in.n, n_x));
+	sl.target.resize(std::max(sl.target.n, n_y));
+	if (sl.pinned_floats < 16) {
+		TCNNB_CUDA_CHECK(cudaMallocHost(&sl.pinned, 16 * sizeof(float)));
+		sl.pinned_floats = 16;
+	}
+	const float* sx = x_host;
+	const float* sy = y_host;
+	const bool x_pinned = host_ptr_is_pinned(m, x_host), y_pinned = host_ptr_is_pinned(m, y_host);
+	if (!x_pinned || !y_pinned) {  // pageable caller memory: stage through this slot's page-locked buffer
+		const size_t need = n_x + n_y + 16;
+		if (sl.pinned_floats < need) {
+			if (sl.pinned) cudaFreeHost(sl.pinned);
+			sl.pinned = nullptr;
+			sl.pinned_floats = 0;
+			TCNNB_CUDA_CHECK(cudaMallocHost(&sl.pinned, need * sizeof(float)));
+			sl.pinned_floats = need;
+		}
+	}
+	cudaStream_t cs = m.copy_stream, s = m.own_stream;
+	if (!x_pinned) { std::memcpy(sl.pinned, x_host, n_x * sizeof(float)); sx = sl.pinned; }
+	TCNNB_CUDA_CHECK(cudaMemcpyAsync(sl.in.ptr, sx, n_x * sizeof(float), cudaMemcpyHostToDevice, cs));
+	TCNNB_CUDA_CHECK(cudaEventRecord(sl.ev_in, cs));
+	if (!y_pinned) { std::memcpy(sl.pinned + n_x, y_host, n_y * sizeof(float)); sy = sl.pinned + n_x; }  // while the inputs travel
+	TCNNB_CUDA_CHECK(cudaMemcpyAsync(sl.target.ptr, sy, n_y * sizeof(float), cudaMemcpyHostToDevice, cs));
+	TCNNB_CUDA_CHECK(cudaEventRecord(sl.ev_target, cs));
+	TCNNB_CUDA_CHECK(cudaStreamWaitEvent(s, sl.ev_in, 0));
+	float* loss_pinned = sl.pinned + sl.pinned_floats - 1;
+	if (data_parallel) {
+		TCNNB_CUDA_CHECK(cudaStreamWaitEvent(s, sl.ev_target, 0));
+		dp_training_step(m, s, batch, global_batch, sl.in.ptr, sl.target.ptr);
+		dp_reduce_loss(m, s);
+	} else {
+		training_step(m, s, batch, global_batch, sl.in.ptr, sl.target.ptr, true, sl.ev_target);
+	}
+	TCNNB_CUDA_CHECK(cudaMemcpyAsync(loss_pinned, m.scalars.ptr, sizeof(float), cudaMemcpyDeviceToHost, s));
+	TCNNB_CUDA_CHECK(cudaEventRecord(sl.ev_done, s));
+	sl.ticket = ticket;
+	sl.busy = true;
+	++m.next_ticket;
+	return ticket;
+}
+
+static float host_step_wait(Model& m, uint64_t ticket) {
+	Model::HostSlot& sl = m.slots[ticket & 1u];
+	if (!sl.busy || sl.ticket != ticket) throw std::runtime_error("training_step_host_wait: ticket " + std::to_string(ticket) + " is not in flight.");
+	TCNNB_CUDA_CHECK(cudaEventSynchronize(sl.ev_done));
+	sl.busy = false;
+	return sl.pinned[sl.pinned_floats - 1];
 }
 
 static std::string make_hyperparams(const Model& m) {
@@ -979,8 +1075,9 @@ void* tcnnb_grid_gradients(tcnnb_model* m) { return m->impl.grads_fp16 + m->impl
 void* tcnnb_param_gradients(tcnnb_model* m) {
 	// The MLP part is materialised as fp16 on demand (the fused kernel accumulates it in fp32).
 	try {
-		finalize_mlp_grads(m->impl, nullptr);
-		cudaStreamSynchronize(nullptr);
+		// ordered behind the step that produced the gradients: same stream, and the synchronisation is on that stream only
+		finalize_mlp_grads(m->impl, m->impl.last_stream);
+		TCNNB_CUDA_CHECK(cudaStreamSynchronize(m->impl.last_stream));
 	} catch (const std::exception& e) {
 		g_last_error = e.what();
 		return nullptr;
@@ -1059,32 +1156,31 @@ int tcnnb_inference(tcnnb_model* m, tcnnb_stream stream, uint32_t batch_size, co
 
 int tcnnb_training_step_host(tcnnb_model* m, uint32_t batch_size, const float* input_host, const float* target_host, float* loss_out) {
 	TCNNB_API_BEGIN
-	Model& mm = m->impl;
-	check_batch(batch_size);
-	ensure_staging(mm, batch_size);
-	cudaStream_t s = mm.own_stream;
-	const size_t n_x = (size_t)batch_size * mm.n_in, n_y = (size_t)batch_size * mm.n_out;
-	// Stage through pinned memory unless the caller's buffers are already page-locked.
-	cudaPointerAttributes attr{};
-	const bool x_pinned = cudaPointerGetAttributes(&attr, input_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-	const bool y_pinned = cudaPointerGetAttributes(&attr, target_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-	cudaGetLastError();
-	const float* sx = input_host;
-	const float* sy = target_host;
-	if (!x_pinned) { std::memcpy(mm.pinned, input_host, n_x * sizeof(float)); sx = mm.pinned; }
-	// inputs on the compute stream; the targets follow on the copy stream (one after the other on the link, so the inputs
-	// land first) and only the fused kernel waits for them: the binning pass overlaps their transfer.
-	TCNNB_CUDA_CHECK(cudaMemcpyAsync(mm.stage_in.ptr, sx, n_x * sizeof(float), cudaMemcpyHostToDevice, s));
-	TCNNB_CUDA_CHECK(cudaEventRecord(mm.ev_inputs, s));
-	if (!y_pinned) { std::memcpy(mm.pinned + n_x, target_host, n_y * sizeof(float)); sy = mm.pinned + n_x; }  // while the inputs travel
-	TCNNB_CUDA_CHECK(cudaStreamWaitEvent(mm.copy_stream, mm.ev_inputs, 0));
-	TCNNB_CUDA_CHECK(cudaMemcpyAsync(mm.stage_target.ptr, sy, n_y * sizeof(float), cudaMemcpyHostToDevice, mm.copy_stream));
-	TCNNB_CUDA_CHECK(cudaEventRecord(mm.ev_targets, mm.copy_stream));
-	training_step(mm, s, batch_size, batch_size, mm.stage_in.ptr, mm.stage_target.ptr, true, mm.ev_targets);
-	float* loss_pinned = mm.pinned + mm.pinned_floats - 1;
-	TCNNB_CUDA_CHECK(cudaMemcpyAsync(loss_pinned, mm.scalars.ptr, sizeof(float), cudaMemcpyDeviceToHost, s));
-	TCNNB_CUDA_CHECK(cudaStreamSynchronize(s));
-	if (loss_out) *loss_out = *loss_pinned;
+	const uint64_t t = host_step_submit(m->impl, batch_size, batch_size, input_host, target_host, false);
+	const float loss = host_step_wait(m->impl, t);
+	if (loss_out) *loss_out = loss;
+	TCNNB_API_END
+}
+
+int tcnnb_training_step_host_submit(tcnnb_model* m, uint32_t batch_size, const float* input_host, const float* target_host, uint64_t* ticket_out) {
+	TCNNB_API_BEGIN
+	const uint64_t t = host_step_submit(m->impl, batch_size, batch_size, input_host, target_host, false);
+	if (ticket_out) *ticket_out = t;
+	TCNNB_API_END
+}
+
+int tcnnb_dp_training_step_host_submit(tcnnb_model* m, uint32_t shard_batch_size, uint32_t global_batch_size, const float* input_host, const float* target_host, uint64_t* ticket_out) {
+	TCNNB_API_BEGIN
+	if (!m->impl.dp) throw std::runtime_error("dp_training_step_host_submit: call tcnnb_dp_init first.");
+	const uint64_t t = host_step_submit(m->impl, shard_batch_size, global_batch_size, input_host, target_host, true);
+	if (ticket_out) *ticket_out = t;
+	TCNNB_API_END
+}
+
+int tcnnb_training_step_host_wait(tcnnb_model* m, uint64_t ticket, float* loss_out) {
+	TCNNB_API_BEGIN
+	const float loss = host_step_wait(m->impl, ticket);
+	if (loss_out) *loss_out = loss;
 	TCNNB_API_END
 }
 
@@ -1114,6 +1210,10 @@ int tcnnb_serialize(tcnnb_model* m, void* dst_host, uint64_t size, int with_opti
 	TCNNB_API_BEGIN
 	Model& mm = m->impl;
 	if (size < tcnnb_serialize_size(m, with_optimizer)) throw std::runtime_error("tcnnb_serialize: destination too small");
+	if (with_optimizer && mm.dp && mm.dp->world > 1 && mm.dp->shard_optimizer) {
+		// moments / step counters are current on the owner of a slice only (ZeRO-1): a snapshot of one rank would silently hold stale state
+		throw std::runtime_error("tcnnb_serialize: optimizer state is sharded over the data-parallel ranks; serialize with_optimizer = 0 (after tcnnb_dp_sync_full_precision) or from a single-GPU trainer");
+	}
 	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
 	char* p = (char*)dst_host;
 	const uint64_t n = mm.n_params;
@@ -1320,6 +1420,15 @@ int tcnnb_read_profile(tcnnb_model* m, float* fused_ms_total, float* optimizer_m
 	if (fused_ms_total) *fused_ms_total = fused;
 	if (optimizer_ms_total) *optimizer_ms_total = opt;
 	if (n_steps) *n_steps = (uint32_t)n;
+	TCNNB_API_END
+}
+
+int tcnnb_debug_set(tcnnb_model* m, const char* key, int value) {
+	TCNNB_API_BEGIN
+	const std::string k = key ? key : "";
+	if (k == "binning") m->impl.binning = value != 0;
+	else if (k == "inference_sync_kernel") m->impl.inference_sync_kernel = value != 0;
+	else throw std::runtime_error("tcnnb_debug_set: unknown key '" + k + "'");
 	TCNNB_API_END
 }
 

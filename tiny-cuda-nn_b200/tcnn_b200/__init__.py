@@ -78,11 +78,15 @@ ABI = [
     ("tcnnb_loss", _int, [_vp, _vp, _f32p]),
     ("tcnnb_inference", _int, [_vp, _vp, _u32, _vp, _vp]),
     ("tcnnb_training_step_host", _int, [_vp, _u32, _vp, _vp, _f32p]),
+    ("tcnnb_training_step_host_submit", _int, [_vp, _u32, _vp, _vp, ctypes.POINTER(_u64)]),
+    ("tcnnb_training_step_host_wait", _int, [_vp, _u64, _f32p]),
+    ("tcnnb_dp_training_step_host_submit", _int, [_vp, _u32, _u32, _vp, _vp, ctypes.POINTER(_u64)]),
     ("tcnnb_inference_host", _int, [_vp, _u32, _vp, _vp]),
     ("tcnnb_serialize_size", _u64, [_vp, _int]),
     ("tcnnb_serialize", _int, [_vp, _vp, _u64, _int]),
     ("tcnnb_deserialize", _int, [_vp, _vp, _u64]),
     ("tcnnb_set_debug_taps", _int, [_vp, ctypes.POINTER(DebugTaps)]),
+    ("tcnnb_debug_set", _int, [_vp, ctypes.c_char_p, _int]),
     ("tcnnb_set_profiling", _int, [_vp, _int]),
     ("tcnnb_read_profile", _int, [_vp, _f32p, _f32p, _f32p, ctypes.POINTER(_u32)]),
     ("tcnnb_kernel_launch_count", _u64, []),
@@ -459,6 +463,24 @@ class TrainableModel:
         out = ctypes.c_float(0)
         _check(load().tcnnb_training_step_host(self._h, inputs_np.shape[0], inputs_np.ctypes.data, targets_np.ctypes.data, ctypes.byref(out)))
         return out.value
+
+    def training_step_host_submit(self, inputs_np, targets_np, global_batch=None):
+        """Pipelined form: enqueue {H2D, step, D2H of the loss} and return a ticket; up to two steps may be in flight.
+        `global_batch` (data-parallel trainer, after dp_init): this call's arrays are the rank's shard of that global batch."""
+        t = ctypes.c_uint64(0)
+        if global_batch is None:
+            _check(load().tcnnb_training_step_host_submit(self._h, inputs_np.shape[0], inputs_np.ctypes.data, targets_np.ctypes.data, ctypes.byref(t)))
+        else:
+            _check(load().tcnnb_dp_training_step_host_submit(self._h, inputs_np.shape[0], int(global_batch), inputs_np.ctypes.data, targets_np.ctypes.data, ctypes.byref(t)))
+        return t.value
+
+    def training_step_host_wait(self, ticket):
+        out = ctypes.c_float(0)
+        _check(load().tcnnb_training_step_host_wait(self._h, ticket, ctypes.byref(out)))
+        return out.value
+
+    def debug_set(self, key, value):
+        _check(load().tcnnb_debug_set(self._h, key.encode(), int(value)))
 
     def inference_host(self, inputs_np, outputs_np):
         _check(load().tcnnb_inference_host(self._h, inputs_np.shape[0], inputs_np.ctypes.data, outputs_np.ctypes.data))

@@ -131,8 +131,9 @@ class DataParallelTrainer:
         lo = self.rank * chunk
         self._reduce_scatter(b["grads"], b["grads"][lo : lo + chunk])
         begin, count = self.owned_range()
-        if count:
-            t.optimizer_step(ranges=[(begin, count)])
+        # an empty slice (count == 0: this rank owns only padding) still counts as an optimizer step, as in the native
+        # path (model.cu dp_training_step): AdaBound's learning-rate bounds depend on the step counter
+        t.optimizer_step(ranges=[(begin, count) if count else (0, 0)])
         self._all_gather_overlapped(b["params"], b["params"][lo : lo + chunk])
         self._masters_synced = False
 
