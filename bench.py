@@ -33,6 +33,15 @@ FUSED_BYTES_PER_SAMPLE = 1048
 ADAM_BYTES_PER_PARAM = 36
 
 
+L2_NOTE = "per-step working set (tables+optimizer state ~770 MB) exceeds the 126 MB L2; 4 rotating input batches; no explicit flush"
+E2E_WARMUP = 10
+
+
+def config_dict(world, parallelism):
+    """The SAME dict for both arms at N=1 (the driver compares them)."""
+    return {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": parallelism, "l2": L2_NOTE}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -137,7 +146,7 @@ def run_reference(args):
     harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
     line = {"metric": METRIC, "unit": "samples/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "l2": "per-step working set (tables+optimizer state ~770 MB) exceeds the 126 MB L2; no explicit flush"}}
+            "config": config_dict(1, "dp1")}  # the reference is a single-GPU library: one GPU whatever --gpus says
     modes = {}
     if os.path.exists(harness):
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
@@ -159,7 +168,8 @@ def run_reference(args):
     cb = cpu_baseline()
     if ok:
         best = max(ok, key=lambda k: ok[k]["samples_per_s"])
-        line.update(value=ok[best]["samples_per_s"], ms_per_step=ok[best]["ms_per_step"], reference_mode=best, clocks=ok[best].get("clocks"))
+        line.update(value=ok[best]["samples_per_s"], ms_per_step=ok[best]["ms_per_step"], reference_mode=best, clocks=ok[best].get("clocks"),
+                    final_loss=ok[best].get("loss_after_steps"))
         line["reference_modes"] = modes
         line["cpu_baseline"] = {"value": ok[best]["samples_per_s"], "unit": "samples/s", "cores": 0, "kind": "reference",
                                 "sample": f"the reference's own sm_100 build on the GPU ({best}); it has no CPU path. CPU oracle port: {cb['value']:.3e} samples/s on {cb['cores']} threads"}
@@ -173,8 +183,8 @@ def run_reference(args):
         # The reference is a GPU library, so its end-to-end number is measured like the new library's: through its own API with the
         # inputs and targets in pinned HOST buffers (H2D every step) and the loss read back every step (ref_harness `bench ... e2e`).
         cfg_file, jit = ("headline.json", 1) if best == "fully_fused_jit" else ("headline.json", 0)
-        e2e_steps = max(3, min(args.steps, 100))
-        cmd = [harness, "bench", os.path.join(ROOT, "tests", "golden", "configs", cfg_file), str(N_IN), str(N_OUT), str(BATCH), str(e2e_steps), "3", str(jit), "0", "1"]
+        e2e_steps = max(args.steps, 100)
+        cmd = [harness, "bench", os.path.join(ROOT, "tests", "golden", "configs", cfg_file), str(N_IN), str(N_OUT), str(BATCH), str(e2e_steps), str(E2E_WARMUP), str(jit), "0", "1"]
         try:
             out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
             js = [l for l in out.stdout.splitlines() if l.startswith("{")]
@@ -183,17 +193,29 @@ def run_reference(args):
                            "steps": e2e_steps, "api": f"Trainer::training_step + Trainer::loss ({best}) on pinned host buffers, wall clock"}
         except Exception as e:  # noqa: BLE001
             line["e2e"]["error"] = repr(e)
+        # secondary metric: network->inference samples/s, same batch pool
+        try:
+            cmd = [harness, "bench", os.path.join(ROOT, "tests", "golden", "configs", cfg_file), str(N_IN), str(N_OUT), str(BATCH), str(args.steps), str(args.warmup), str(jit), "1"]
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+            r = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+            line["inference"] = {"value": r["samples_per_s"], "unit": "samples/s", "ms_per_batch": r["ms_per_step"], "mode": best}
+        except Exception as e:  # noqa: BLE001
+            line["inference"] = {"error": repr(e)}
     line["gpu_launches"] = 0
     print(json.dumps(line))
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json)."""
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r0N_traffic.json, newest round)."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        return {"kernel": t["kernel"], "bytes": t["dram_bytes_read_per_launch"] + t["dram_bytes_write_per_launch"]}
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            path = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(path):
+                t = json.load(open(path))
+                return {"kernel": t["kernel"], "bytes": t["dram_bytes_read_per_launch"] + t["dram_bytes_write_per_launch"], "source": "profiles/" + name}
     except Exception:  # noqa: BLE001
-        return {}
+        pass
+    return {}
 
 
 def closed_form_targets(torch, x, n_out):
@@ -269,35 +291,53 @@ def run_own(args):
     prof = model.read_profile()
     model.set_profiling(False)
     launches = tcnn_b200.kernel_launch_count() - launches0
-    final_loss = trainer.loss()
+    # loss of training step number warmup + steps (one more step on the next batch of the pool): the reference arm prints the same
+    # quantity after the same number of steps on the same data sequence (rank 0 draws the reference's pcg32{1337} stream)
+    step(args.warmup + args.steps)
+    final_loss = dp.loss()
+
+    # ---- secondary metric: network->inference samples/s over the same batch pool (device-resident, CUDA events)
+    inf_steps = max(args.steps, 20)
+    for i in range(3):
+        model.network.inference(xs[i % pool])
+    sync_all()
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    i0.record(stream)
+    for i in range(inf_steps):
+        model.network.inference(xs[i % pool])
+    i1.record(stream)
+    sync_all()
+    inf_ms = i0.elapsed_time(i1) / inf_steps
     if world > 1:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
 
-    # ---- end-to-end through the C ABI with HOST buffers: H2D of positions+targets and D2H of the loss every step
-    e2e_steps = max(3, min(args.steps, 100))  # synchronous host loop: enough steps to average the host-side jitter out
+    # ---- end-to-end through the C ABI with HOST buffers: every step copies its positions + targets host -> device and its loss
+    # device -> host. Pipelined public API (tcnnb_training_step_host_submit / _wait): step i+1 is submitted before the loss of
+    # step i is collected, so the copies of step i+1 overlap the kernels of step i; every loss is read on the host.
+    e2e_steps = max(args.steps, 100)
     xn = [t.numpy() for t in xh]
     yn = [t.numpy() for t in yh]
-    x_dev, y_dev = torch.empty_like(xs[0]), torch.empty_like(ys[0])
+    gb = None if world == 1 else global_batch
 
-    def e2e_step(i):
-        if world == 1:
-            return model.training_step_host(xn[i % pool], yn[i % pool])  # C ABI: H2D of inputs + targets, step, D2H of the loss
-        # data-parallel public API: pinned host shard -> device, sharded step, global loss back on the host
-        x_dev.copy_(xh[i % pool], non_blocking=True)
-        y_dev.copy_(yh[i % pool], non_blocking=True)
-        dp.training_step(x_dev, y_dev)
-        return dp.loss()
+    def e2e_run(n):
+        losses = []
+        prev = model.training_step_host_submit(xn[0], yn[0], gb)
+        for i in range(1, n):
+            cur = model.training_step_host_submit(xn[i % pool], yn[i % pool], gb)
+            losses.append(model.training_step_host_wait(prev))
+            prev = cur
+        losses.append(model.training_step_host_wait(prev))
+        return losses
 
-    for i in range(3):
-        e2e_step(i)
+    e2e_run(E2E_WARMUP)
     sync_all()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_step(i)
+    e2e_losses = e2e_run(e2e_steps)
     sync_all()
     e2e_s = time.perf_counter() - t0
+    assert len(e2e_losses) == e2e_steps and all(np.isfinite(l) for l in e2e_losses)
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -316,15 +356,18 @@ def run_own(args):
             "metric": METRIC, "value": global_batch * args.steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": global_batch, "parallelism": f"dp{world}" + ("" if world == 1 else ("-zero1" if dp.shard_optimizer else "-replicated") + ("-native" if dp.native else "-torchdist")),
-                       "l2": "per-step working set (tables+optimizer state ~770 MB) exceeds the 126 MB L2; 4 rotating input batches; no explicit flush"},
+            "config": config_dict(world, f"dp{world}" + ("" if world == 1 else ("-zero1" if dp.shard_optimizer else "-replicated") + ("-native" if dp.native else "-torchdist"))),
             "clocks": cs.summary(),
             "e2e": {"value": global_batch * e2e_steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": BATCH * (N_IN + N_OUT) * 4, "d2h_bytes_per_step": 4,
-                    "steps": e2e_steps, "api": "tcnnb_training_step_host (C ABI, host buffers)" if world == 1 else "DataParallelTrainer.training_step on pinned host shards + loss()"},
+                    "steps": e2e_steps, "warmup": E2E_WARMUP, "last_loss": e2e_losses[-1],
+                    "api": ("tcnnb_training_step_host_submit/_wait" if world == 1 else "tcnnb_dp_training_step_host_submit/_wait") + " (C ABI, pinned host buffers, two steps in flight, every loss read back)"},
+            "inference": {"value": global_batch / (inf_ms * 1e-3), "unit": "samples/s", "ms_per_batch": inf_ms, "steps": inf_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": traffic.get("kernel", "fused_ws_kernel"), "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic.get("bytes"), "traffic_unit": "B/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "kernel_ms": fused_ms, "optimizer_kernel_ms": adam_ms, "binning_kernels_ms": binning_ms,
-                         "optimizer_achieved_gbs": ADAM_BYTES_PER_PARAM * model.n_params / (adam_ms * 1e-3) / 1e9 if adam_ms > 0 else None,
+                         # algorithmic 36 B/parameter; the zero-gradient skip moves fewer bytes (ncu: profiles/). Only
+                         # meaningful at N = 1: the sharded data-parallel optimizer runs inside the collective phase
+                         "optimizer_achieved_gbs": ADAM_BYTES_PER_PARAM * model.n_params / (adam_ms * 1e-3) / 1e9 if (adam_ms > 0 and world == 1) else None,
                          "step_share": fused_ms / ms_per_step if ms_per_step > 0 else None},
             "final_loss": final_loss,
         }

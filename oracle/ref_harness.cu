@@ -7,6 +7,7 @@
 //          gradients, post-step params) for tests/golden/ -- see tests/golden/make_golden.sh
 //   bench  time trainer->training_step / network->inference with CUDA events for the
 //          `bench.py --impl reference` arm (jit on / jit off / CutlassMLP via the JSON config)
+//   dumpbig  the same at the benchmarked size, sub-sampled so that the vectors are small enough to commit
 //   probe  print the per-level grid scale / resolution as evaluated on the device with the
 //          reference's build flags next to the host evaluation (SURVEY.md §7 "hard parts")
 //
@@ -207,13 +208,16 @@ static int cmd_dump(int argc, char** argv) {
 }
 
 // bench <config.json> <n_in> <n_out> <B> <steps> <warmup> <jit 0|1> [inference 0|1] [e2e 0|1]
-// e2e = 1: every step copies the inputs and targets from PINNED HOST buffers to the device and reads the loss back -- the
-// same end-to-end region bench.py times for the new library (tcnnb_training_step_host); wall-clock timed.
+// Trains on a pool of 4 batches drawn one after the other from pcg32{1337} (the same data sequence bench.py's own arm uses on
+// rank 0), step i on batch i % 4. e2e = 1: every step copies the inputs and targets from PINNED HOST buffers to the device and
+// reads the loss back -- the same end-to-end region bench.py times for the new library; wall-clock timed.
+// "loss_after_steps" = the loss of training step number warmup + steps (0-based), i.e. of one more step after the timed loop.
 static int cmd_bench(int argc, char** argv) {
 	if (argc < 9) {
-		fprintf(stderr, "usage: bench config n_in n_out B steps warmup jit [inference]\n");
+		fprintf(stderr, "usage: bench config n_in n_out B steps warmup jit [inference] [e2e]\n");
 		return 2;
 	}
+	constexpr uint32_t POOL = 4;
 	Setup s;
 	make_setup(s, argv[2], atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[8]) != 0);
 	const uint32_t steps = atoi(argv[6]), warmup = atoi(argv[7]);
@@ -225,24 +229,41 @@ static int cmd_bench(int argc, char** argv) {
 	CUDA_CHECK_THROW(cudaStreamCreate(&stream));
 	GPUMatrix<float> pred(s.n_out, s.B);
 
-	float *hx = nullptr, *hy = nullptr;
-	float e2e_loss = 0;
-	if (e2e) {
-		CUDA_CHECK_THROW(cudaMallocHost(&hx, s.x.n_bytes()));
-		CUDA_CHECK_THROW(cudaMallocHost(&hy, s.y.n_bytes()));
-		CUDA_CHECK_THROW(cudaMemcpy(hx, s.x.data(), s.x.n_bytes(), cudaMemcpyDeviceToHost));
-		CUDA_CHECK_THROW(cudaMemcpy(hy, s.y.data(), s.y.n_bytes(), cudaMemcpyDeviceToHost));
+	// pool of device batches: one generator, consecutive draws (random.h:56-69 advances the caller's rng by n per call)
+	std::vector<GPUMatrix<float>> xs, ys;
+	std::vector<float*> hxs(POOL, nullptr), hys(POOL, nullptr);
+	{
+		default_rng_t rng{1337};
+		std::vector<float> hx((size_t)s.B * s.n_in), hy;
+		for (uint32_t i = 0; i < POOL; ++i) {
+			xs.emplace_back(s.n_in, s.B);
+			ys.emplace_back(s.n_out, s.B);
+			generate_random_uniform<float>(nullptr, rng, (size_t)s.B * s.n_in, xs[i].data());
+			CUDA_CHECK_THROW(cudaMemcpy(hx.data(), xs[i].data(), hx.size() * sizeof(float), cudaMemcpyDeviceToHost));
+			make_targets(hx, s.n_in, s.n_out, s.B, hy);
+			CUDA_CHECK_THROW(cudaMemcpy(ys[i].data(), hy.data(), hy.size() * sizeof(float), cudaMemcpyHostToDevice));
+			if (e2e) {
+				CUDA_CHECK_THROW(cudaMallocHost(&hxs[i], xs[i].n_bytes()));
+				CUDA_CHECK_THROW(cudaMallocHost(&hys[i], ys[i].n_bytes()));
+				memcpy(hxs[i], hx.data(), xs[i].n_bytes());
+				memcpy(hys[i], hy.data(), ys[i].n_bytes());
+			}
+		}
 	}
+	float e2e_loss = 0;
+	uint32_t it = 0;
 	auto one = [&]() {
+		const uint32_t b = it++ % POOL;
 		if (e2e) {
-			CUDA_CHECK_THROW(cudaMemcpyAsync(s.x.data(), hx, s.x.n_bytes(), cudaMemcpyHostToDevice, stream));
-			CUDA_CHECK_THROW(cudaMemcpyAsync(s.y.data(), hy, s.y.n_bytes(), cudaMemcpyHostToDevice, stream));
+			// staged into one device batch, as an application with host-side data does
+			CUDA_CHECK_THROW(cudaMemcpyAsync(s.x.data(), hxs[b], s.x.n_bytes(), cudaMemcpyHostToDevice, stream));
+			CUDA_CHECK_THROW(cudaMemcpyAsync(s.y.data(), hys[b], s.y.n_bytes(), cudaMemcpyHostToDevice, stream));
 			auto ctx = trainer->training_step(stream, s.x, s.y);
 			e2e_loss = trainer->loss(stream, *ctx);  // device -> host + stream synchronisation (trainer.h:372-378)
 		} else if (inference) {
-			network->inference(stream, s.x, pred);
+			network->inference(stream, xs[b], pred);
 		} else {
-			trainer->training_step(stream, s.x, s.y);
+			trainer->training_step(stream, xs[b], ys[b]);
 		}
 	};
 	for (uint32_t i = 0; i < warmup; ++i) one();
@@ -261,26 +282,146 @@ static int cmd_bench(int argc, char** argv) {
 	const double wall_ms = std::chrono::duration<double, std::milli>(w1 - w0).count();
 	float final_loss = -1.0f;
 	if (!inference) {
-		auto ctx = trainer->training_step(stream, s.x, s.y);
+		const uint32_t b = it % POOL;
+		auto ctx = trainer->training_step(stream, xs[b], ys[b]);
 		final_loss = trainer->loss(stream, *ctx);
 	}
 	(void)e2e_loss;
-	printf("{\"impl\": \"reference\", \"e2e\": %s, \"h2d_bytes_per_step\": %zu, \"mode\": \"%s\", \"jit_fusion\": %s, \"network\": \"%s\", \"batch\": %u, \"steps\": %u, \"warmup\": %u, \"ms_per_step\": %.6f, \"wall_ms_per_step\": %.6f, \"samples_per_s\": %.6e, \"n_params\": %zu, \"final_loss\": %.6g}\n",
+	printf("{\"impl\": \"reference\", \"e2e\": %s, \"h2d_bytes_per_step\": %zu, \"mode\": \"%s\", \"jit_fusion\": %s, \"network\": \"%s\", \"batch\": %u, \"steps\": %u, \"warmup\": %u, \"ms_per_step\": %.6f, \"wall_ms_per_step\": %.6f, \"samples_per_s\": %.6e, \"n_params\": %zu, \"loss_after_steps\": %.6g, \"batch_pool\": %u}\n",
 		e2e ? "true" : "false", e2e ? s.x.n_bytes() + s.y.n_bytes() : (size_t)0, inference ? "inference" : "training_step", network->jit_fusion() ? "true" : "false",
 		s.config.value("network", json::object()).value("otype", "MLP").c_str(),
-		s.B, steps, warmup, ms / steps, wall_ms / steps, (double)s.B * steps / (ms * 1e-3), trainer->n_params(), final_loss);
+		s.B, steps, warmup, ms / steps, wall_ms / steps, (double)s.B * steps / (ms * 1e-3), trainer->n_params(), final_loss, POOL);
+	return 0;
+}
+
+// Gather a strided subset of a device array: element k of the result = src[first + k * stride].
+template <typename T>
+static void write_strided(const std::string& path, const T* dev, size_t first, size_t n, size_t stride) {
+	std::vector<T> h(n);
+	CUDA_CHECK_THROW(cudaMemcpy(h.data(), dev, n * sizeof(T), cudaMemcpyDeviceToHost));
+	std::vector<T> out;
+	for (size_t i = first; i < n; i += stride) out.push_back(h[i]);
+	write_host_bin(path, out);
+}
+
+// dumpbig <config.json> <n_in> <n_out> <B> <n_steps> <outdir> <jit 0|1> <stride> <n_head>
+// Golden vectors at the BENCHMARKED size (T = 2^19, B = 2^16 .. 2^18) in a form small enough to commit: inputs are regenerated by
+// the test from the seed (sums are recorded here to check that), per-sample outputs only for the first n_head samples,
+// parameter-sized arrays as [all network weights | every stride-th grid parameter], counts of non-zero gradients / moved
+// parameters for the touched-set comparison, and the whole loss trajectory.
+static int cmd_dumpbig(int argc, char** argv) {
+	if (argc < 11) {
+		fprintf(stderr, "usage: dumpbig config n_in n_out B n_steps outdir jit stride n_head\n");
+		return 2;
+	}
+	const std::string outdir = argv[7];
+	mkdir(outdir.c_str(), 0755);
+	Setup s;
+	make_setup(s, argv[2], atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[8]) != 0);
+	const uint32_t n_steps = atoi(argv[6]);
+	const size_t stride = atoi(argv[9]);
+	const uint32_t n_head = atoi(argv[10]);
+	auto& trainer = s.model.trainer;
+	auto& network = s.model.network;
+	const size_t n_params = trainer->n_params();
+	const uint32_t B = s.B;
+	auto enc = network->encoding();
+	const size_t n_net = n_params - enc->n_params();  // network weights come first (network_with_input_encoding.h:115-130)
+
+	auto write_param_sample = [&](const std::string& stem, auto* dev) {
+		using T = std::remove_cv_t<std::remove_pointer_t<decltype(dev)>>;
+		std::vector<T> h(n_params);
+		CUDA_CHECK_THROW(cudaMemcpy(h.data(), dev, n_params * sizeof(T), cudaMemcpyDeviceToHost));
+		std::vector<T> out(h.begin(), h.begin() + n_net);
+		for (size_t i = n_net; i < n_params; i += stride) out.push_back(h[i]);
+		write_host_bin(outdir + "/" + stem, out);
+		return h;
+	};
+
+	double sum_x = 0, sum_y = 0;
+	for (float v : s.hx) sum_x += v;
+	for (float v : s.hy) sum_y += v;
+	auto p_init = write_param_sample("params_init.f32", (const float*)trainer->params_full_precision());
+
+	// encoded features of the first n_head samples (SoA [width][B] -> [width][n_head])
+	GPUMatrixDynamic<precision_t> encoded{enc->padded_output_width(), B, nullptr, enc->preferred_output_layout()};
+	enc->inference_mixed_precision(nullptr, s.x, encoded, true);
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	{
+		std::vector<uint16_t> h((size_t)enc->padded_output_width() * B), out;
+		CUDA_CHECK_THROW(cudaMemcpy(h.data(), encoded.data(), h.size() * 2, cudaMemcpyDeviceToHost));
+		const bool soa = enc->preferred_output_layout() == SoA;
+		for (uint32_t f = 0; f < enc->padded_output_width(); ++f)
+			for (uint32_t i = 0; i < n_head; ++i) out.push_back(soa ? h[(size_t)f * B + i] : h[(size_t)i * enc->padded_output_width() + f]);
+		write_host_bin(outdir + "/encoded_head.f16", out);
+	}
+	GPUMatrix<float> pred(s.n_out, B);
+	network->inference(nullptr, s.x, pred);
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	write_bin(outdir + "/inference_head.f32", pred.data(), (size_t)s.n_out * n_head);
+
+	std::vector<float> losses;
+	size_t n_grad_nonzero = 0;
+	{
+		auto ctx = trainer->training_step(nullptr, s.x, s.y, nullptr, /*run_optimizer=*/false);
+		CUDA_CHECK_THROW(cudaDeviceSynchronize());
+		if (ctx->output.data()) write_bin(outdir + "/output_head.f16", (const uint16_t*)ctx->output.data(), (size_t)network->padded_output_width() * n_head);
+		write_bin(outdir + "/loss_values_head.f32", ctx->L.data(), (size_t)network->padded_output_width() * n_head);
+		auto g = write_param_sample("grads_step0.f16", (const uint16_t*)trainer->param_gradients());
+		for (size_t i = n_net; i < n_params; ++i) n_grad_nonzero += (g[i] & 0x7FFFu) != 0;
+		losses.push_back(trainer->loss(nullptr, *ctx));
+	}
+	size_t n_moved = 0;
+	for (uint32_t i = 0; i < n_steps; ++i) {
+		auto ctx = trainer->training_step(nullptr, s.x, s.y);
+		losses.push_back(trainer->loss(nullptr, *ctx));
+		if (i == 0) {
+			CUDA_CHECK_THROW(cudaDeviceSynchronize());
+			auto p1 = write_param_sample("params_step1.f32", (const float*)trainer->params_full_precision());
+			for (size_t k = n_net; k < n_params; ++k) n_moved += p1[k] != p_init[k];
+		}
+	}
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	write_param_sample("params_final.f16", (const uint16_t*)trainer->params());
+	network->inference(nullptr, s.x, pred);
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	write_bin(outdir + "/inference_final_head.f32", pred.data(), (size_t)s.n_out * n_head);
+
+	json meta;
+	meta["config"] = s.config;
+	meta["n_in"] = s.n_in;
+	meta["n_out"] = s.n_out;
+	meta["batch"] = B;
+	meta["n_steps"] = n_steps;
+	meta["n_params"] = n_params;
+	meta["n_network_params"] = n_net;
+	meta["stride"] = stride;
+	meta["n_head"] = n_head;
+	meta["input_seed"] = 1337;
+	meta["sum_x"] = sum_x;
+	meta["sum_y"] = sum_y;
+	meta["n_grid_grad_nonzero"] = n_grad_nonzero;
+	meta["n_grid_params_moved_step1"] = n_moved;
+	meta["encoded_width"] = enc->padded_output_width();
+	meta["padded_output_width"] = network->padded_output_width();
+	meta["jit_fusion"] = network->jit_fusion();
+	meta["losses"] = losses;
+	std::ofstream f{outdir + "/meta.json"};
+	f << meta.dump(1) << std::endl;
+	printf("dumpbig %s: n_params=%zu B=%u losses[0]=%g losses[last]=%g nonzero grid grads=%zu\n", outdir.c_str(), n_params, B, losses.front(), losses.back(), n_grad_nonzero);
 	return 0;
 }
 
 int main(int argc, char** argv) {
 	try {
 		if (argc < 2) {
-			fprintf(stderr, "usage: %s dump|bench|probe ...\n", argv[0]);
+			fprintf(stderr, "usage: %s dump|dumpbig|bench|probe ...\n", argv[0]);
 			return 2;
 		}
 		const std::string cmd = argv[1];
 		if (cmd == "dump") return cmd_dump(argc, argv);
 		if (cmd == "bench") return cmd_bench(argc, argv);
+		if (cmd == "dumpbig") return cmd_dumpbig(argc, argv);
 		if (cmd == "probe") return cmd_probe(argc, argv);
 		fprintf(stderr, "unknown command %s\n", cmd.c_str());
 		return 2;
