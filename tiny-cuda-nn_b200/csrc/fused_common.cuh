@@ -1,4 +1,4 @@
-// fused_common.cuh -- device helpers shared by the fused-step kernels (fused_step.cu, fused_ws.cu).
+// fused_common.cuh -- device helpers shared by the tcgen05 kernels (fused_ws.cu, mlp_fused.cu).
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"

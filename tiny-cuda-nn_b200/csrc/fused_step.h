@@ -1,4 +1,4 @@
-// fused_step.h -- launch interface of the fused HashGrid + FullyFusedMLP kernel (fused_step.cu).
+// fused_step.h -- launch interface of the fused HashGrid + FullyFusedMLP kernel (fused_ws.cu).
 #pragma once
 #include "common.cuh"
 
@@ -49,9 +49,6 @@ struct FusedStepParams {
 	__half* dbg_denc;              // [batch][64]
 	long long* dbg_clock;          // ablation builds: [cta][role 3][tile 16][slot 16] clock64 stamps of the ws kernel's phases
 };
-
-size_t fused_step_smem_bytes(uint32_t n_hidden_layers, uint32_t in_w, bool train);
-cudaError_t launch_fused_step(const FusedStepParams& p, uint32_t n_pos_dims, bool train, uint32_t n_ctas, cudaStream_t stream);
 
 // Warp-specialised kernel (fused_ws.cu): one 640-thread CTA per SM (n_ctas <= #SMs), training step and inference.
 size_t fused_ws_smem_bytes(uint32_t n_hidden_layers, uint32_t enc_width, bool train);

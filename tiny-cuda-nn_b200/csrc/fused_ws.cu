@@ -1,9 +1,24 @@
-// fused_ws.cu -- warp-specialised variant of the fused training / inference step (same math as fused_step.cu).
+// fused_ws.cu -- the hot path in ONE warp-specialised kernel: HashGrid gather + N-linear blend -> FullyFusedMLP forward (tcgen05)
+// -> loss -> MLP backward (tcgen05: dgrad and wgrad) -> hash-grid gradient scatter (f16x2 reductions); without its backward half
+// it is the inference kernel.
 //
-// Why a second structure: in the bulk-synchronous kernel every MMA batch ends in a CTA-wide barrier, so the long and
-// uneven latencies of the table gathers / gradient reductions that fill the wait slots end up on the critical path of the
-// MLP chain (profiles/: 12 % barrier stalls, 45 % long-scoreboard). Here the two kinds of work never wait for each other
-// inside a tile:
+// Replaces, for one training step, the reference's kernel_grid (grid.h:49), kernel_mlp_fused (fully_fused_mlp.cu:500),
+// relative_l2_loss / l2_loss (losses/*.h:40), kernel_mlp_fused_backward (fully_fused_mlp.cu:151), the three CUTLASS split-K
+// weight-gradient GEMMs and the dL/d(encoded) GEMM (fully_fused_mlp.cu:784-836) and kernel_grid_backward (grid.h:215). No
+// activation ever leaves the SM: the only HBM/L2 traffic is positions, targets, the fp16 tables (gather), their fp16 gradient
+// tables (red.f16x2) and 7 K fp32 weight-gradient partial sums per CTA.
+//
+// Data layout on chip: operand tiles are [128 rows][64 fp16] in the canonical SWIZZLE_128B layout; the SAME bytes are consumed as
+// a K-major A operand by the forward / dgrad MMAs (M = samples, K = neurons) and as an MN-major operand by the wgrad MMAs
+// (M/N = neurons, K = samples), so no transposes are ever materialised. Weights are staged once per CTA: W_l [out][in] row-major
+// is the K-major B operand of the forward MMA and, read MN-major, the B operand of the dgrad MMA (W_l^T). Accumulators live in
+// TMEM: ACC (64 columns, reused by every layer) + one 64x64 fp32 wgrad accumulator per weight matrix that persists across all
+// tiles of the CTA and is flushed once with red.global.add.f32. The backward activations g_l overwrite h_l in place.
+//
+// Why warp-specialised: in a bulk-synchronous structure (round 1's fused_step.cu, removed) every MMA batch ends in a CTA-wide
+// barrier, so the long and uneven latencies of the table gathers / gradient reductions that fill the wait slots end up on the
+// critical path of the MLP chain (12 % barrier stalls, 45 % long-scoreboard; 25 % slower for training, 43 % for inference).
+// Here the two kinds of work never wait for each other inside a tile:
 //
 //   warps 0..3   "MLP group" (128 threads, thread t <-> tile row t <-> TMEM lane t): issues the tcgen05 MMAs and runs the
 //                epilogues of one 128-sample tile at a time, tile after tile.
@@ -509,7 +524,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 						}
 					}
 				} else if (b <= 2 * NH) {
-					// g overwrites h in place (see fused_step.cu)
+					// g overwrites h in place: each thread rewrites the chunk of its own row it has just read
 					const uint32_t l = 2 * NH + 1 - b;
 					const uint32_t h_tile = s_h0 + (l - 1) * TILE_BYTES;
 					uint32_t racc[2][32];
