@@ -104,6 +104,35 @@ int tcnnb_module_forward(tcnnb_model* m, tcnnb_stream stream, uint32_t n_element
 int tcnnb_module_backward(tcnnb_model* m, tcnnb_stream stream, uint32_t n_elements, float* dL_dinput_dev, const void* dL_doutput_dev, void* dL_dparams_dev, const float* input_dev,
                           const void* output_dev, const void* params_dev);
 
+/* ---- network tier: a FullyFusedMLP on its own -------------------------------------------------------------------------------
+ * tcnn::create_network<T>(json) (network.h; src/network.cu:51-141; the object benchmarks/mlp/bench_mlp_ours.cu drives) and
+ * tcnn::cpp::create_network (cpp_api.h:122; src/cpp_api.cu:160-162 = the same network behind the Identity encoding).
+ * `network_json` carries the reference's keys ("otype", "n_neurons", "n_hidden_layers", "activation", "output_activation"); both
+ * "FullyFusedMLP" and "CutlassMLP"/"MLP" run on the tcgen05 kernel of csrc/mlp_fused.cu (widths 16/32/64/128, any depth >= 1,
+ * padded outputs up to n_neurons). Parameters are CALLER-owned fp16 device arrays (16-byte aligned) in the reference's layout
+ * (fully_fused_mlp.cu:635-672): W_0 [n_neurons][input_width], (n_hidden_layers - 1) x [n_neurons][n_neurons],
+ * W_out [padded_output_width][n_neurons], row-major; input_width = n_input_dims rounded up to 16.
+ * Batches are multiples of 256. All work is stream-ordered; nothing synchronises. */
+typedef struct tcnnb_network tcnnb_network;
+int tcnnb_network_create(uint32_t n_input_dims, uint32_t n_output_dims, const char* network_json, tcnnb_network** out);
+void tcnnb_network_destroy(tcnnb_network* n);
+uint64_t tcnnb_network_n_params(const tcnnb_network* n);
+uint32_t tcnnb_network_input_width(const tcnnb_network* n);          /* n_input_dims rounded up to 16 */
+uint32_t tcnnb_network_padded_output_width(const tcnnb_network* n);  /* network->padded_output_width() */
+uint32_t tcnnb_network_width(const tcnnb_network* n);
+uint32_t tcnnb_network_n_hidden_layers(const tcnnb_network* n);
+/* Network::initialize_params (fully_fused_mlp.cu:868-892): xavier uniform per matrix from pcg32{seed}; device fp32 [n_params]. */
+int tcnnb_network_initialize_params(tcnnb_network* n, uint64_t seed, float* params_full_precision_dev, float scale);
+/* network->inference_mixed_precision(stream, input, output) (object.h / network.h): input fp16 [n][n_input_dims] (n_input_dims
+ * must be a multiple of 16), output fp16 [n][padded_output_width]. */
+int tcnnb_network_inference_mixed_precision(tcnnb_network* n, tcnnb_stream stream, uint32_t n_elements, const void* input_dev, void* output_dev, const void* params_dev);
+/* network->forward: the same, and the post-activation hidden layers fp16 [n_hidden_layers][n][n_neurons] are written out
+ * (what the reference's ForwardContext holds, fully_fused_mlp.cu:841-854). output_dev may be null. */
+int tcnnb_network_forward(tcnnb_network* n, tcnnb_stream stream, uint32_t n_elements, const void* input_dev, void* output_dev, void* hidden_dev, const void* params_dev);
+/* cpp::create_network semantics: fp32 input [n][n_input_dims] through the Identity encoding (padding features are 1,
+ * encodings/identity.h:62-66) -> fp32 output [n][n_output_dims] (object.h:214-282). */
+int tcnnb_network_inference(tcnnb_network* n, tcnnb_stream stream, uint32_t n_elements, const float* input_dev, float* output_dev, const void* params_dev);
+
 /* ---- data parallelism, natively over NCCL (no counterpart in the single-GPU reference) -------------
  * One process per GPU. Rendezvous is the host framework's job (torch.distributed in tcnn_b200/dp.py): rank 0 draws two NCCL
  * ids with tcnnb_dp_unique_id (128 bytes each), broadcasts them, and every rank calls tcnnb_dp_init. libnccl.so.2 is resolved

@@ -8,6 +8,7 @@
 //   bench  time trainer->training_step / network->inference with CUDA events for the
 //          `bench.py --impl reference` arm (jit on / jit off / CutlassMLP via the JSON config)
 //   dumpbig  the same at the benchmarked size, sub-sampled so that the vectors are small enough to commit
+//   mlpdump / mlpbench  the network on its own (create_network<T>, fp16 in / out): golden vectors and inference throughput
 //   probe  print the per-level grid scale / resolution as evaluated on the device with the
 //          reference's build flags next to the host evaluation (SURVEY.md §7 "hard parts")
 //
@@ -16,6 +17,7 @@
 // generate_random_uniform (random.h:69).
 #include <tiny-cuda-nn/common_device.h>
 #include <tiny-cuda-nn/config.h>
+#include <tiny-cuda-nn/network.h>
 
 #include <chrono>
 #include <cmath>
@@ -412,16 +414,108 @@ static int cmd_dumpbig(int argc, char** argv) {
 	return 0;
 }
 
+// ---- the network on its own (benchmarks/mlp/bench_mlp_ours.cu): tcnn::create_network<T>(json), fp16 inputs and outputs ----------
+struct NetSetup {
+	std::shared_ptr<Network<precision_t>> network;
+	std::shared_ptr<Trainer<precision_t, precision_t, precision_t>> trainer;
+	uint32_t n_in, n_out;
+};
+
+static void make_net(NetSetup& s, const char* otype, uint32_t width, uint32_t hidden, uint32_t n_in, uint32_t n_out, bool jit, const char* act = "ReLU", const char* out_act = "None") {
+	json opts = {{"otype", otype}, {"n_input_dims", n_in}, {"n_output_dims", n_out}, {"n_neurons", width}, {"n_hidden_layers", hidden}, {"activation", act}, {"output_activation", out_act}};
+	std::shared_ptr<Loss<precision_t>> loss{create_loss<precision_t>(json::object())};
+	std::shared_ptr<Optimizer<precision_t>> optimizer{create_optimizer<precision_t>(json::object())};
+	s.network.reset(create_network<precision_t>(opts));
+	s.network->set_jit_fusion(jit && tcnn::supports_jit_fusion());
+	s.trainer = std::make_shared<Trainer<precision_t, precision_t, precision_t>>(s.network, optimizer, loss);  // owns + initialises the parameters
+	s.n_in = n_in;
+	s.n_out = n_out;
+}
+
+// mlpdump <otype> <width> <hidden> <n_in> <n_out> <B> <outdir> <jit> [activation] [output_activation]
+static int cmd_mlpdump(int argc, char** argv) {
+	if (argc < 10) {
+		fprintf(stderr, "usage: mlpdump otype width hidden n_in n_out B outdir jit [activation] [output_activation]\n");
+		return 2;
+	}
+	NetSetup s;
+	const uint32_t B = atoi(argv[7]);
+	make_net(s, argv[2], atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[9]) != 0, argc > 10 ? argv[10] : "ReLU", argc > 11 ? argv[11] : "None");
+	const std::string outdir = argv[8];
+	mkdir(outdir.c_str(), 0755);
+	default_rng_t rng{1337};
+	GPUMatrixDynamic<precision_t> x(s.n_in, B, CM);  // column-major n_in x B == [B][n_in]
+	generate_random_uniform<precision_t>(nullptr, rng, (size_t)B * s.n_in, x.data());
+	const uint32_t out_w = s.network->padded_output_width();
+	GPUMatrixDynamic<precision_t> y(out_w, B, CM);
+	s.network->inference_mixed_precision(nullptr, x, y);
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	write_bin(outdir + "/x.f16", (const uint16_t*)x.data(), (size_t)B * s.n_in);
+	write_bin(outdir + "/output.f16", (const uint16_t*)y.data(), (size_t)B * out_w);
+	write_bin(outdir + "/params.f16", (const uint16_t*)s.trainer->params(), s.trainer->n_params());
+	json meta;
+	meta["otype"] = argv[2];
+	meta["width"] = atoi(argv[3]);
+	meta["n_hidden_layers"] = atoi(argv[4]);
+	meta["n_in"] = s.n_in;
+	meta["n_out"] = s.n_out;
+	meta["padded_output_width"] = out_w;
+	meta["batch"] = B;
+	meta["n_params"] = s.trainer->n_params();
+	meta["jit_fusion"] = s.network->jit_fusion();
+	meta["activation"] = argc > 10 ? argv[10] : "ReLU";
+	meta["output_activation"] = argc > 11 ? argv[11] : "None";
+	std::ofstream f{outdir + "/meta.json"};
+	f << meta.dump(1) << std::endl;
+	printf("mlpdump %s: n_params=%zu out_w=%u\n", outdir.c_str(), s.trainer->n_params(), out_w);
+	return 0;
+}
+
+// mlpbench <otype> <width> <hidden> <n_in> <n_out> <B> <iters> <warmup> <jit>: inference_mixed_precision throughput (CUDA events)
+static int cmd_mlpbench(int argc, char** argv) {
+	if (argc < 11) {
+		fprintf(stderr, "usage: mlpbench otype width hidden n_in n_out B iters warmup jit\n");
+		return 2;
+	}
+	NetSetup s;
+	const uint32_t B = atoi(argv[7]), iters = atoi(argv[8]), warmup = atoi(argv[9]);
+	const bool jit = atoi(argv[10]) != 0;
+	make_net(s, argv[2], atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), jit);
+	cudaStream_t stream;
+	CUDA_CHECK_THROW(cudaStreamCreate(&stream));
+	default_rng_t rng{1337};
+	// "Most efficient in RM layout when used with JIT, CM layout otherwise" (bench_mlp_ours.cu:81)
+	GPUMatrixDynamic<precision_t> x(s.n_in, B, jit ? RM : CM);
+	GPUMatrix<precision_t, RM> y(s.network->padded_output_width(), B);
+	generate_random_uniform<precision_t>(stream, rng, (size_t)B * s.n_in, x.data());
+	for (uint32_t i = 0; i < warmup; ++i) s.network->inference_mixed_precision(stream, x, y);
+	CUDA_CHECK_THROW(cudaStreamSynchronize(stream));
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	cudaEventRecord(e0, stream);
+	for (uint32_t i = 0; i < iters; ++i) s.network->inference_mixed_precision(stream, x, y);
+	cudaEventRecord(e1, stream);
+	CUDA_CHECK_THROW(cudaStreamSynchronize(stream));
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e0, e1);
+	printf("{\"impl\": \"reference\", \"mode\": \"mlp_inference\", \"otype\": \"%s\", \"jit_fusion\": %s, \"width\": %d, \"n_hidden_layers\": %d, \"n_in\": %u, \"n_out\": %u, \"batch\": %u, \"iters\": %u, \"ms_per_batch\": %.6f, \"samples_per_s\": %.6e}\n",
+		argv[2], s.network->jit_fusion() ? "true" : "false", atoi(argv[3]), atoi(argv[4]), s.n_in, s.n_out, B, iters, ms / iters, (double)B * iters / (ms * 1e-3));
+	return 0;
+}
+
 int main(int argc, char** argv) {
 	try {
 		if (argc < 2) {
-			fprintf(stderr, "usage: %s dump|dumpbig|bench|probe ...\n", argv[0]);
+			fprintf(stderr, "usage: %s dump|dumpbig|mlpdump|mlpbench|bench|probe ...\n", argv[0]);
 			return 2;
 		}
 		const std::string cmd = argv[1];
 		if (cmd == "dump") return cmd_dump(argc, argv);
 		if (cmd == "bench") return cmd_bench(argc, argv);
 		if (cmd == "dumpbig") return cmd_dumpbig(argc, argv);
+		if (cmd == "mlpdump") return cmd_mlpdump(argc, argv);
+		if (cmd == "mlpbench") return cmd_mlpbench(argc, argv);
 		if (cmd == "probe") return cmd_probe(argc, argv);
 		fprintf(stderr, "unknown command %s\n", cmd.c_str());
 		return 2;

@@ -1,0 +1,453 @@
+// mlp_fused.cu -- stand-alone FullyFusedMLP forward / inference on tcgen05: the tensor-core-bound kernel of the hot path.
+//
+// Replaces the reference's kernel_mlp_fused<WIDTH, ..., INFERENCE> (fully_fused_mlp.cu:499-557: threadblock_input_layer_forward_dynamic
+// :315-419, threadblock_layer :47-129, threadblock_last_layer_forward :421-476) for Network<T>::inference_mixed_precision
+// (benchmarks/mlp/bench_mlp_ours.cu:107-120) and, with the Identity encoding fused into the input load, for
+// cpp::create_network / NetworkWithInputEncoding(Identity) (src/cpp_api.cu:160-162, encodings/identity.h:46-67).
+//
+// The reference keeps a 128-sample tile's activations in shared memory and re-reads the weights from L2 into registers for every
+// layer of every block (HMMA.F16). Here, per persistent CTA (one per SM):
+//
+//   * weights are loaded ONCE with TMA (cp.async.bulk.tensor, SWIZZLE_128B boxes of 64 K-elements) into shared memory and stay
+//     there as the K-major B operands of every tile; networks with more matrices than fit (128 wide: > 7) stream them through
+//     the same stages as a ring (w_full / w_free mbarriers);
+//   * activations NEVER touch shared memory: layer l accumulates D = A_l . W_l^T in tensor memory (fp32), the epilogue warps read
+//     the accumulator row with tcgen05.ld, apply the activation in fp16 (as warp_activation<__half>, common_device.h:110-215),
+//     and write the packed fp16 row back INTO tensor memory with tcgen05.st, where the next layer's tcgen05.mma reads it as its A
+//     operand (A-from-TMEM). The network input itself enters that way: global -> registers -> tcgen05.st, prefetched a tile ahead;
+//   * SLOTS independent 128-sample tiles are in flight per CTA (2 for 128-wide layers, 4 below; each owns two accumulator regions
+//     that alternate between layers), so that the single MMA-issuing thread always has a tile whose operand is ready while the
+//     epilogue warps of the others convert: the tensor pipe idles only for what the slowest slot's epilogue exceeds the other
+//     slots' MMA time.
+//
+// Warp roles: warps 4s .. 4s+3 = epilogue / load / store warps of slot s (thread t <-> tile row t <-> TMEM lane t);
+//             warp 4*SLOTS     = MMA issuer (one elected lane) + TMEM allocation;  warp 4*SLOTS + 1 = TMA producer (weights).
+// mbarriers:  a_ready[s]  (4 arrivals, one per epilogue warp: the A operand of this slot's next layer is in tensor memory)
+//             acc_ready[s] (tcgen05.commit: the accumulator of this slot's current layer is complete)
+//             w_full[stage] (TMA complete_tx), w_free[stage] (SLOTS arrivals by tcgen05.commit: ring mode only)
+//
+// Numerics: fp16 operands, fp32 accumulation, ONE rounding to fp16 per layer (the reference accumulates in fp16 inside HMMA;
+// tolerance statement in DESIGN.md section 4).
+#include "mlp_fused.h"
+
+#include "fused_common.cuh"
+#include "ptx.cuh"
+
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint, no link to libcuda)
+
+namespace tcnnb {
+
+using namespace ptx;
+using namespace fused;
+
+namespace {
+
+constexpr uint32_t MLPF_MAX_STAGES = 32;
+
+template <uint32_t W>
+struct MlpCfg {
+	static constexpr uint32_t SLOTS = W == 128 ? 2 : 4;
+	static constexpr uint32_t EPI_WARPS = 4 * SLOTS;
+	static constexpr uint32_t THREADS = (EPI_WARPS + 2) * 32;
+	static constexpr uint32_t REGION = W < 32 ? 32 : W;        // TMEM columns of one accumulator region
+	static constexpr uint32_t TMEM_COLS = SLOTS * 2 * REGION;  // 512 / 512 / 256 / 256
+	static constexpr uint32_t KBLOCKS = (W + 63) / 64;         // 64-element K blocks of a weight stage
+	static constexpr uint32_t KBLOCK_BYTES = W * 128;          // [W rows][64 fp16], SWIZZLE_128B
+	static constexpr uint32_t STAGE_BYTES = KBLOCKS * KBLOCK_BYTES < 2048 ? 2048 : KBLOCKS * KBLOCK_BYTES;
+	static constexpr uint32_t CHUNK = W == 128 ? 64 : (W < 32 ? W : 32);  // accumulator columns per tcgen05.ld (register budget: 576 threads below 128 wide)
+	static constexpr uint32_t MAX_IN = 64 * KBLOCKS;           // widest first-layer input a stage holds
+};
+
+struct MlpKernelParams {
+	MlpForwardParams p;
+	uint32_t n_stages;  // == n_layers when all matrices are resident
+	uint32_t resident;
+};
+
+template <uint32_t N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld_n<16>(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x32b_x16(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ld_n<32>(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32b_x32(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ld_n<64>(uint32_t taddr, uint32_t (&r)[64]) { tmem_ld_32x32b_x64(taddr, r); }
+template <uint32_t N>
+__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t (&r)[N]);
+template <>
+__device__ __forceinline__ void tmem_st_n<8>(uint32_t taddr, const uint32_t (&r)[8]) { tmem_st_32x32b_x8(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_st_n<16>(uint32_t taddr, const uint32_t (&r)[16]) { tmem_st_32x32b_x16(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_st_n<32>(uint32_t taddr, const uint32_t (&r)[32]) { tmem_st_32x32b_x32(taddr, r); }
+
+}  // namespace
+
+template <uint32_t W, bool GENERIC_ACT>
+__global__ void __launch_bounds__(MlpCfg<W>::THREADS, 1)
+mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wo) {
+	using C = MlpCfg<W>;
+	const MlpForwardParams& p = kp.p;
+	const uint32_t hid_act = GENERIC_ACT ? p.activation : (uint32_t)ACT_RELU;
+	const uint32_t out_act = GENERIC_ACT ? p.output_activation : (uint32_t)ACT_NONE;
+	extern __shared__ __align__(1024) uint8_t smem_raw[];
+	const uint32_t tid = threadIdx.x;
+	const uint32_t warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
+	const uint32_t lane = tid & 31u;
+	const uint32_t NH = p.n_hidden_layers, n_layers = NH + 1;
+	const uint32_t in_w = p.in_width, out_w = p.out_width;
+	const uint32_t n_stages = kp.n_stages;
+	const bool resident = kp.resident != 0;
+
+	const uint32_t smem_base = smem_u32(smem_raw);
+	if (smem_base & 1023u) __trap();
+	const uint32_t s_stage0 = smem_base;
+	const uint32_t s_bars = s_stage0 + n_stages * C::STAGE_BYTES;
+	const uint32_t bar_w_full = s_bars;                               // [MLPF_MAX_STAGES]
+	const uint32_t bar_w_free = bar_w_full + 8 * MLPF_MAX_STAGES;     // [MLPF_MAX_STAGES]
+	const uint32_t bar_a_ready = bar_w_free + 8 * MLPF_MAX_STAGES;    // [4]
+	const uint32_t bar_acc_ready = bar_a_ready + 8 * 4;               // [4]
+	const uint32_t s_tmem_slot = bar_acc_ready + 8 * 4;
+
+	if (tid == 0) {
+		for (uint32_t i = 0; i < n_stages; ++i) {
+			mbar_init(bar_w_full + 8 * i, 1);
+			mbar_init(bar_w_free + 8 * i, C::SLOTS);
+		}
+		for (uint32_t s = 0; s < C::SLOTS; ++s) {
+			mbar_init(bar_a_ready + 8 * s, 4);
+			mbar_init(bar_acc_ready + 8 * s, 1);
+		}
+		fence_mbar_init();
+	}
+	if (warp == C::EPI_WARPS) {
+		__syncwarp();
+		tmem_alloc(s_tmem_slot, C::TMEM_COLS);
+		tmem_relinquish();
+	}
+	if (warp == C::EPI_WARPS + 1 && lane == 0) {
+		tma_prefetch_desc(&map_w0);
+		tma_prefetch_desc(&map_wh);
+		tma_prefetch_desc(&map_wo);
+	}
+	tc_fence_before_sync();
+	__syncthreads();
+	tc_fence_after_sync();
+	pdl_wait();  // from here on global memory written by the previous kernel on the stream is read
+
+	uint32_t tmem_base;
+	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem_slot));
+	const uint32_t n_tiles = p.batch_size / TILE_M;
+	// tiles of this CTA: blockIdx.x + j * gridDim.x, j = 0 .. n_my - 1; slot s owns j = s, s + SLOTS, ...
+	const uint32_t n_my = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+	const uint32_t n_rounds = (n_my + C::SLOTS - 1) / C::SLOTS;
+
+	if (warp == C::EPI_WARPS + 1) {
+		// =============================================================================== TMA producer: weight matrices -> stages
+		if (lane == 0) {
+			const uint32_t n_loads = resident ? n_layers : n_rounds * n_layers;
+			for (uint32_t g = 0; g < (n_my ? n_loads : 0u); ++g) {
+				const uint32_t l = resident ? g : g % n_layers;
+				const uint32_t stage = resident ? g : g % n_stages;
+				if (!resident && g >= n_stages) mbar_wait(bar_w_free + 8 * stage, ((g / n_stages) - 1u) & 1u);
+				const uint32_t dst = s_stage0 + stage * C::STAGE_BYTES;
+				const uint32_t full = bar_w_full + 8 * stage;
+				if (l == 0) {
+					const uint32_t kb = (in_w + 63) / 64;
+					mbar_arrive_expect_tx(full, kb * W * 128);
+					for (uint32_t b = 0; b < kb; ++b) tma_load_2d(dst + b * C::KBLOCK_BYTES, &map_w0, full, (int32_t)(b * 64), 0);
+				} else if (l < NH) {
+					mbar_arrive_expect_tx(full, C::KBLOCKS * W * 128);
+					for (uint32_t b = 0; b < C::KBLOCKS; ++b) tma_load_2d(dst + b * C::KBLOCK_BYTES, &map_wh, full, (int32_t)(b * 64), (int32_t)((l - 1) * W));
+				} else {
+					mbar_arrive_expect_tx(full, C::KBLOCKS * out_w * 128);
+					for (uint32_t b = 0; b < C::KBLOCKS; ++b) tma_load_2d(dst + b * C::KBLOCK_BYTES, &map_wo, full, (int32_t)(b * 64), 0);
+				}
+			}
+		}
+	} else if (warp == C::EPI_WARPS) {
+		// =============================================================================== MMA issuer
+		// Per slot: which layer comes next. A slot whose tiles have run out keeps walking the layers of the remaining rounds as a
+		// "virtual" consumer in ring mode: it only releases the weight stages (w_free expects SLOTS arrivals per use).
+		uint32_t layer[C::SLOTS], round[C::SLOTS], a_par[C::SLOTS], n_real[C::SLOTS];
+		uint32_t remaining = 0;
+#pragma unroll
+		for (uint32_t s = 0; s < C::SLOTS; ++s) {
+			layer[s] = round[s] = a_par[s] = 0;
+			n_real[s] = n_my > s ? (n_my - s + C::SLOTS - 1) / C::SLOTS : 0;
+			remaining += (resident ? n_real[s] : n_rounds) * n_layers;
+		}
+		const uint32_t idesc_hidden = umma_idesc_f16(128, W, 0, 0);
+		const uint32_t idesc_out = umma_idesc_f16(128, out_w, 0, 0);
+		while (remaining) {
+#pragma unroll
+			for (uint32_t s = 0; s < C::SLOTS; ++s) {
+				const uint32_t n_rounds_s = resident ? n_real[s] : n_rounds;
+				if (round[s] >= n_rounds_s) continue;
+				const bool real = round[s] < n_real[s];
+				const uint32_t l = layer[s];
+				const uint32_t g = round[s] * n_layers + l;
+				const uint32_t stage = resident ? l : g % n_stages;
+				const uint32_t w_par = resident ? 0u : (g / n_stages) & 1u;
+				// warp-uniform decisions (every lane tests; the vote makes the result one value)
+				if (real && !__all_sync(0xFFFFFFFFu, mbar_test(bar_a_ready + 8 * s, a_par[s]))) continue;
+				if (!__all_sync(0xFFFFFFFFu, mbar_test(bar_w_full + 8 * stage, w_par))) continue;
+				if (real) {
+					tc_fence_after_sync();
+					if (elect_one_sync()) {
+						const uint32_t slot_base = tmem_base + s * 2 * C::REGION;
+						const uint32_t d_tmem = slot_base + (l & 1u) * C::REGION;
+						const uint32_t a_tmem = slot_base + ((l + 1u) & 1u) * C::REGION;  // first half of the other region
+						const uint32_t b_smem = s_stage0 + stage * C::STAGE_BYTES;
+						const uint32_t ksteps = (l == 0 ? in_w : W) / 16;
+						const uint32_t idesc = l == NH ? idesc_out : idesc_hidden;
+						for (uint32_t j = 0; j < ksteps; ++j) {
+							const uint64_t b_desc = umma_desc_sw128(b_smem + (j >> 2) * C::KBLOCK_BYTES + (j & 3u) * 32u, 16u, 1024u);
+							umma_f16_ts(d_tmem, a_tmem + j * 8u, b_desc, idesc, j > 0);
+						}
+						umma_commit(bar_acc_ready + 8 * s);
+						if (!resident) umma_commit(bar_w_free + 8 * stage);
+					}
+					__syncwarp();
+					a_par[s] ^= 1u;
+				} else if (lane == 0) {
+					mbar_arrive_plain(bar_w_free + 8 * stage);
+				}
+				if (++layer[s] == n_layers) {
+					layer[s] = 0;
+					++round[s];
+				}
+				--remaining;
+			}
+		}
+	} else {
+		// =============================================================================== epilogue / load / store warps of one slot
+		const uint32_t s = warp >> 2, wq = warp & 3u;
+		const uint32_t row = wq * 32 + lane;
+		const uint32_t lane_field = (wq * 32u) << 16;
+		const uint32_t slot_base = tmem_base + s * 2 * C::REGION + lane_field;
+		uint32_t acc_par = 0;
+
+		// ---- the row of the network input this thread owns, as packed fp16 pairs (prefetched one tile ahead)
+		constexpr uint32_t IN_WORDS = C::MAX_IN / 2;
+		uint32_t pre[IN_WORDS];
+		auto load_input = [&](uint32_t tile) {
+			const size_t sample = (size_t)tile * TILE_M + row;
+			if (p.input_fp16) {
+				const uint4* src = reinterpret_cast<const uint4*>(p.input_fp16 + sample * in_w);
+#pragma unroll
+				for (uint32_t q = 0; q < IN_WORDS / 4; ++q) {
+					if (q * 8 < in_w) {
+						const uint4 v = __ldg(src + q);
+						pre[4 * q] = v.x;
+						pre[4 * q + 1] = v.y;
+						pre[4 * q + 2] = v.z;
+						pre[4 * q + 3] = v.w;
+					}
+				}
+			} else {
+				// Identity encoding (identity.h:46-67): the first n_input_dims features are the inputs, the padding features are ONE
+				const float* src = p.input_fp32 + sample * p.n_input_dims;
+#pragma unroll
+				for (uint32_t q = 0; q < IN_WORDS; ++q) {
+					if (2 * q < in_w) {
+						const float lo = 2 * q < p.n_input_dims ? __ldg(src + 2 * q) : 1.0f;
+						const float hi = 2 * q + 1 < p.n_input_dims ? __ldg(src + 2 * q + 1) : 1.0f;
+						pre[q] = pack_half2(lo, hi);
+					}
+				}
+			}
+		};
+
+		uint32_t j = s;
+		if (j < n_my) load_input(blockIdx.x + j * gridDim.x);
+		for (; j < n_my; j += C::SLOTS) {
+			const uint32_t tile = blockIdx.x + j * gridDim.x;
+			const size_t sample = (size_t)tile * TILE_M + row;
+			// ---- input row -> tensor memory: A operand of layer 0 lives in the first half of region 1
+			{
+				const uint32_t a0 = slot_base + C::REGION;
+#pragma unroll
+				for (uint32_t q = 0; q < IN_WORDS / 8; ++q) {
+					if (q * 16 < in_w) {
+						uint32_t v[8];
+#pragma unroll
+						for (uint32_t i = 0; i < 8; ++i) v[i] = pre[8 * q + i];
+						tmem_st_n<8>(a0 + q * 8, v);
+					}
+				}
+				tmem_st_wait();
+				tc_fence_before_sync();
+				__syncwarp();
+				if (lane == 0) mbar_arrive_plain(bar_a_ready + 8 * s);
+			}
+			for (uint32_t l = 0; l <= NH; ++l) {
+				// the next tile's input travels while the last layer computes
+				if (l == NH && j + C::SLOTS < n_my) load_input(blockIdx.x + (j + C::SLOTS) * gridDim.x);
+				mbar_wait(bar_acc_ready + 8 * s, acc_par);
+				acc_par ^= 1u;
+				tc_fence_after_sync();
+				const uint32_t acc = slot_base + (l & 1u) * C::REGION;
+				if (l < NH) {
+					// hidden layer: fp32 accumulator row -> activation in fp16 -> packed, IN PLACE into the first half of this region
+					// (chunk c reads columns [c*CHUNK, (c+1)*CHUNK) and writes [c*CHUNK/2, (c+1)*CHUNK/2): always columns already read)
+#pragma unroll
+					for (uint32_t c = 0; c < W / C::CHUNK; ++c) {
+						uint32_t r[C::CHUNK];
+						tmem_ld_n<C::CHUNK>(acc + c * C::CHUNK, r);
+						tmem_ld_wait();
+						uint32_t h[C::CHUNK / 2];
+#pragma unroll
+						for (uint32_t i = 0; i < C::CHUNK / 2; ++i) h[i] = act_pack(hid_act, r[2 * i], r[2 * i + 1]);
+						tmem_st_n<C::CHUNK / 2>(acc + c * (C::CHUNK / 2), h);
+						if (p.hidden_out) {
+							uint4* dst = reinterpret_cast<uint4*>(p.hidden_out + ((size_t)l * p.batch_size + sample) * W + c * C::CHUNK);
+#pragma unroll
+							for (uint32_t i = 0; i < C::CHUNK / 8; ++i) dst[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+						}
+					}
+					tmem_st_wait();
+					tc_fence_before_sync();
+					__syncwarp();
+					if (lane == 0) mbar_arrive_plain(bar_a_ready + 8 * s);
+				} else {
+					// output layer: activation, fp16 rows (and / or trimmed fp32 rows) straight to global memory
+					for (uint32_t c = 0; c * 16 < out_w; ++c) {
+						uint32_t r[16];
+						tmem_ld_n<16>(acc + c * 16, r);
+						tmem_ld_wait();
+						__half y[16];
+#pragma unroll
+						for (uint32_t i = 0; i < 16; ++i) y[i] = act_fwd_h(out_act, __float2half_rn(__uint_as_float(r[i])));
+						if (p.output_fp16) {
+							uint4* dst = reinterpret_cast<uint4*>(p.output_fp16 + sample * out_w + c * 16);
+							dst[0] = *reinterpret_cast<uint4*>(&y[0]);
+							dst[1] = *reinterpret_cast<uint4*>(&y[8]);
+						}
+						if (p.output_fp32) {
+#pragma unroll
+							for (uint32_t i = 0; i < 16; ++i) {
+								if (c * 16 + i < p.n_output_dims) p.output_fp32[sample * p.n_output_dims + c * 16 + i] = __half2float(y[i]);
+							}
+						}
+					}
+				}
+			}
+		}
+		tc_fence_before_sync();
+	}
+
+	pdl_launch_dependents();
+	__syncthreads();
+	if (warp == C::EPI_WARPS) {
+		tc_fence_after_sync();
+		tmem_dealloc(tmem_base, C::TMEM_COLS);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------ host side
+namespace {
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+	static EncodeTiledFn fn = [] {
+		void* f = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+		return (EncodeTiledFn)f;
+	}();
+	return fn;
+}
+
+// fp16 matrix [rows][cols] row-major -> 2-D tensor map with a box of 64 columns x box_rows rows, SWIZZLE_128B, zero fill outside.
+bool make_weight_map(CUtensorMap* map, const __half* base, uint32_t rows, uint32_t cols, uint32_t box_rows) {
+	EncodeTiledFn fn = encode_tiled_fn();
+	if (!fn) return false;
+	const cuuint64_t dims[2] = {cols, rows};
+	const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(__half)};
+	const cuuint32_t box[2] = {64, box_rows};
+	const cuuint32_t elem[2] = {1, 1};
+	return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+	          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <uint32_t W>
+uint32_t max_stages() {
+	return (uint32_t)((227u * 1024u - 1024u) / MlpCfg<W>::STAGE_BYTES) < MLPF_MAX_STAGES ? (uint32_t)((227u * 1024u - 1024u) / MlpCfg<W>::STAGE_BYTES) : MLPF_MAX_STAGES;
+}
+
+template <uint32_t W, bool GENERIC>
+cudaError_t launch_impl(const MlpForwardParams& p, uint32_t n_sms, cudaStream_t stream) {
+	using C = MlpCfg<W>;
+	const uint32_t n_layers = p.n_hidden_layers + 1;
+	MlpKernelParams kp{};
+	kp.p = p;
+	kp.resident = n_layers <= max_stages<W>() ? 1 : 0;
+	kp.n_stages = kp.resident ? n_layers : max_stages<W>();
+	CUtensorMap m0, mh, mo;
+	const __half* w = p.weights;
+	if (!make_weight_map(&m0, w, W, p.in_width, W)) return cudaErrorInvalidValue;
+	w += (size_t)W * p.in_width;
+	if (p.n_hidden_layers > 1) {
+		if (!make_weight_map(&mh, w, (p.n_hidden_layers - 1) * W, W, W)) return cudaErrorInvalidValue;
+	} else {
+		mh = m0;  // never used
+	}
+	w += (size_t)(p.n_hidden_layers - 1) * W * W;
+	if (!make_weight_map(&mo, w, p.out_width, W, p.out_width)) return cudaErrorInvalidValue;
+	auto kernel = mlp_forward_kernel<W, GENERIC>;
+	const size_t smem = (size_t)kp.n_stages * C::STAGE_BYTES + 8 * (2 * MLPF_MAX_STAGES + 8) + 16;
+	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (err != cudaSuccess) return err;
+	const uint32_t n_tiles = p.batch_size / TILE_M;
+	return launch_pdl(kernel, n_tiles < n_sms ? n_tiles : n_sms, C::THREADS, smem, stream, kp, m0, mh, mo);
+}
+
+template <uint32_t W>
+cudaError_t launch_width(const MlpForwardParams& p, uint32_t n_sms, cudaStream_t stream) {
+	const bool generic = p.activation != ACT_RELU || p.output_activation != ACT_NONE;
+	return generic ? launch_impl<W, true>(p, n_sms, stream) : launch_impl<W, false>(p, n_sms, stream);
+}
+
+}  // namespace
+
+uint32_t mlp_forward_resident_layers(uint32_t width) {
+	switch (width) {
+		case 128: return max_stages<128>();
+		case 64: return max_stages<64>();
+		case 32: return max_stages<32>();
+		default: return max_stages<16>();
+	}
+}
+
+bool mlp_forward_supported(const MlpForwardParams& p, const char** why) {
+	auto fail = [&](const char* msg) {
+		if (why) *why = msg;
+		return false;
+	};
+	if (!(p.width == 16 || p.width == 32 || p.width == 64 || p.width == 128)) return fail("FullyFusedMLP only supports 16, 32, 64, and 128 neurons");
+	if (p.n_hidden_layers < 1) return fail("FullyFusedMLP requires at least 1 hidden layer (3 layers in total).");
+	if (p.n_hidden_layers + 1 > 64) return fail("tcnn_b200: the stand-alone MLP kernel covers up to 63 hidden layers");
+	const uint32_t max_in = 64 * ((p.width + 63) / 64);
+	if (p.in_width == 0 || p.in_width % 16 != 0 || p.in_width > max_in) return fail("tcnn_b200: network input width must be a multiple of 16 and at most 64 (128 for 128 neurons)");
+	if (p.out_width == 0 || p.out_width % 16 != 0 || p.out_width > p.width) return fail("tcnn_b200: padded network output width must be a multiple of 16 and at most n_neurons");
+	if (p.batch_size == 0 || p.batch_size % TILE_M != 0) return fail("batch size must be a non-zero multiple of 256");
+	if ((p.input_fp16 != nullptr) == (p.input_fp32 != nullptr)) return fail("tcnn_b200: exactly one network input must be given");
+	if (p.input_fp32 && (p.n_input_dims == 0 || p.n_input_dims > p.in_width)) return fail("tcnn_b200: Identity encoding wider than the network input");
+	return true;
+}
+
+cudaError_t launch_mlp_forward(const MlpForwardParams& p, uint32_t n_sms, cudaStream_t stream) {
+	if (!mlp_forward_supported(p, nullptr)) return cudaErrorInvalidValue;
+	switch (p.width) {
+		case 128: return launch_width<128>(p, n_sms, stream);
+		case 64: return launch_width<64>(p, n_sms, stream);
+		case 32: return launch_width<32>(p, n_sms, stream);
+		case 16: return launch_width<16>(p, n_sms, stream);
+	}
+	return cudaErrorInvalidValue;
+}
+
+}  // namespace tcnnb

@@ -65,6 +65,17 @@ ABI = [
     ("tcnnb_module_inference", _int, [_vp, _vp, ctypes.c_uint32, _vp, _vp, _vp]),
     ("tcnnb_module_forward", _int, [_vp, _vp, ctypes.c_uint32, _vp, _vp, _vp, ctypes.c_int]),
     ("tcnnb_module_backward", _int, [_vp, _vp, ctypes.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("tcnnb_network_create", _int, [_u32, _u32, ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    ("tcnnb_network_destroy", None, [_vp]),
+    ("tcnnb_network_n_params", _u64, [_vp]),
+    ("tcnnb_network_input_width", _u32, [_vp]),
+    ("tcnnb_network_padded_output_width", _u32, [_vp]),
+    ("tcnnb_network_width", _u32, [_vp]),
+    ("tcnnb_network_n_hidden_layers", _u32, [_vp]),
+    ("tcnnb_network_initialize_params", _int, [_vp, _u64, _vp, ctypes.c_float]),
+    ("tcnnb_network_inference_mixed_precision", _int, [_vp, _vp, _u32, _vp, _vp, _vp]),
+    ("tcnnb_network_forward", _int, [_vp, _vp, _u32, _vp, _vp, _vp, _vp]),
+    ("tcnnb_network_inference", _int, [_vp, _vp, _u32, _vp, _vp, _vp]),
     ("tcnnb_dp_unique_id", _int, [_vp, ctypes.c_uint64]),
     ("tcnnb_dp_init", _int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     ("tcnnb_dp_shards_optimizer", _int, [_vp]),
@@ -404,6 +415,67 @@ class Module:
     def close(self):
         if self._h:
             load().tcnnb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class Network:
+    """tcnn::create_network (network.h / cpp_api.h:122): a FullyFusedMLP on its own, caller-owned fp16 parameters."""
+
+    def __init__(self, n_input_dims, n_output_dims, network_config):
+        lib = load()
+        h = ctypes.c_void_p()
+        text = network_config if isinstance(network_config, str) else json.dumps(network_config)
+        _check(lib.tcnnb_network_create(n_input_dims, n_output_dims, text.encode(), ctypes.byref(h)))
+        self._h = h
+        self.n_input_dims, self.n_output_dims = n_input_dims, n_output_dims
+        self.n_params = lib.tcnnb_network_n_params(h)
+        self.input_width = lib.tcnnb_network_input_width(h)
+        self.padded_output_width = lib.tcnnb_network_padded_output_width(h)
+        self.width = lib.tcnnb_network_width(h)
+        self.n_hidden_layers = lib.tcnnb_network_n_hidden_layers(h)
+
+    def initial_params(self, seed=1337, scale=1.0):
+        import torch
+
+        p = torch.empty(self.n_params, dtype=torch.float32, device="cuda")
+        _check(load().tcnnb_network_initialize_params(self._h, seed, p.data_ptr(), scale))
+        return p
+
+    def inference_mixed_precision(self, x16, params16, stream=None):
+        """fp16 [n][n_input_dims] -> fp16 [n][padded_output_width]."""
+        import torch
+
+        out = torch.empty(x16.shape[0], self.padded_output_width, dtype=torch.float16, device=x16.device)
+        _check(load().tcnnb_network_inference_mixed_precision(self._h, _stream_handle(stream), x16.shape[0], x16.data_ptr(), out.data_ptr(), params16.data_ptr()))
+        return out
+
+    def forward(self, x16, params16, stream=None):
+        """-> (output fp16 [n][padded_out], hidden fp16 [n_hidden_layers][n][width])"""
+        import torch
+
+        n = x16.shape[0]
+        out = torch.empty(n, self.padded_output_width, dtype=torch.float16, device=x16.device)
+        hidden = torch.empty(self.n_hidden_layers, n, self.width, dtype=torch.float16, device=x16.device)
+        _check(load().tcnnb_network_forward(self._h, _stream_handle(stream), n, x16.data_ptr(), out.data_ptr(), hidden.data_ptr(), params16.data_ptr()))
+        return out, hidden
+
+    def inference(self, x32, params16, stream=None):
+        """fp32 [n][n_input_dims] through the Identity encoding -> fp32 [n][n_output_dims]."""
+        import torch
+
+        out = torch.empty(x32.shape[0], self.n_output_dims, dtype=torch.float32, device=x32.device)
+        _check(load().tcnnb_network_inference(self._h, _stream_handle(stream), x32.shape[0], x32.data_ptr(), out.data_ptr(), params16.data_ptr()))
+        return out
+
+    def close(self):
+        if self._h:
+            load().tcnnb_network_destroy(self._h)
             self._h = None
 
     def __del__(self):
