@@ -92,10 +92,9 @@ int tcnnb_generate_random_uniform(tcnnb_stream stream, uint64_t rng_state, uint6
  * params / dL_dparams are fp16 [n_params] (network weights first, then the grid table; 16-byte aligned), output / dL_doutput are
  * fp16 [n_elements][padded_output_width] rows, input is fp32 [n_elements][n_input_dims]. The handle is a tcnnb_model without
  * trainer state: destroy with tcnnb_destroy; tcnnb_n_params / tcnnb_padded_output_width / tcnnb_hyperparams apply; the trainer
- * calls do not. Differences from the reference, by design: forward keeps no context (backward recomputes the forward pass inside
- * the fused kernel), and gradients w.r.t. the input positions are not implemented yet (dL_dinput must be null,
- * prepare_input_gradients 0; anything else returns an error). dL_dparams is overwritten (GradientMode::Overwrite, cpp_api.cu:115);
- * null = compute nothing. */
+ * calls do not. Difference from the reference, by design: forward keeps no context -- backward recomputes the forward pass inside
+ * the fused kernel, so prepare_input_gradients is accepted and has nothing to prepare. dL_dinput (fp32 [n_elements][n_input_dims],
+ * may be null) and dL_dparams (may be null) are overwritten (GradientMode::Overwrite, cpp_api.cu:104-125). */
 int tcnnb_module_create(uint32_t n_input_dims, uint32_t n_output_dims, const char* encoding_json, const char* network_json, tcnnb_model** out);
 /* Module::initialize_params(seed, params_full_precision, scale) (cpp_api.cu:140-143): pcg32{seed}, network then grid; device fp32 [n_params]. */
 int tcnnb_module_initialize_params(tcnnb_model* m, uint64_t seed, float* params_full_precision_dev, float scale);
@@ -103,6 +102,29 @@ int tcnnb_module_inference(tcnnb_model* m, tcnnb_stream stream, uint32_t n_eleme
 int tcnnb_module_forward(tcnnb_model* m, tcnnb_stream stream, uint32_t n_elements, const float* input_dev, void* output_dev, const void* params_dev, int prepare_input_gradients);
 int tcnnb_module_backward(tcnnb_model* m, tcnnb_stream stream, uint32_t n_elements, float* dL_dinput_dev, const void* dL_doutput_dev, void* dL_dparams_dev, const float* input_dev,
                           const void* output_dev, const void* params_dev);
+
+/* ---- encoding tier: a grid encoding on its own -------------------------------------------------------------------------------
+ * tcnn::cpp::create_encoding(n_input_dims, json, Precision::Fp16) (cpp_api.h:124, src/cpp_api.cu:165-174) for "Grid" / "HashGrid" /
+ * "DenseGrid" / "TiledGrid" with the reference's JSON keys: n_features_per_level 1 / 2 / 4 / 8, 2 to 4 input dimensions, Nearest /
+ * Linear / Smoothstep. Output width = n_levels * n_features_per_level (no padding: alignment 0). Caller-owned fp16 parameters
+ * [n_params]; batches are multiples of 256; stream-ordered. */
+typedef struct tcnnb_encoding tcnnb_encoding;
+int tcnnb_encoding_create(uint32_t n_input_dims, const char* encoding_json, tcnnb_encoding** out);
+void tcnnb_encoding_destroy(tcnnb_encoding* e);
+uint64_t tcnnb_encoding_n_params(const tcnnb_encoding* e);
+uint32_t tcnnb_encoding_n_input_dims(const tcnnb_encoding* e);
+uint32_t tcnnb_encoding_n_output_dims(const tcnnb_encoding* e);
+int tcnnb_encoding_grid_levels(const tcnnb_encoding* e, uint32_t* n_levels, uint32_t* offsets, float* scales, uint32_t* resolutions);
+/* GridEncoding::set_max_level (grid.h:69-92): fraction in [0, 1] of the levels that is active; the others encode to zero. */
+int tcnnb_encoding_set_max_level(tcnnb_encoding* e, float max_level);
+/* initialize_params (grid.h:1076-1079): U(-1e-4, 1e-4) * scale from pcg32{seed}; device fp32 [n_params]. */
+int tcnnb_encoding_initialize_params(tcnnb_encoding* e, uint64_t seed, float* params_full_precision_dev, float scale);
+/* forward == inference: fp32 [n][n_input_dims] -> fp16 [n][n_output_dims]. */
+int tcnnb_encoding_forward(tcnnb_encoding* e, tcnnb_stream stream, uint32_t n_elements, const float* input_dev, void* output_dev, const void* params_dev);
+/* backward: dL_dparams fp16 [n_params] (OVERWRITTEN) and / or dL_dinput fp32 [n][n_input_dims] from dL_doutput fp16 [n][n_output_dims];
+ * either result pointer may be null. params_dev is needed for dL_dinput only. */
+int tcnnb_encoding_backward(tcnnb_encoding* e, tcnnb_stream stream, uint32_t n_elements, float* dL_dinput_dev, const void* dL_doutput_dev, void* dL_dparams_dev, const float* input_dev,
+                            const void* params_dev);
 
 /* ---- network tier: a FullyFusedMLP on its own -------------------------------------------------------------------------------
  * tcnn::create_network<T>(json) (network.h; src/network.cu:51-141; the object benchmarks/mlp/bench_mlp_ours.cu drives) and

@@ -171,6 +171,13 @@ class OracleModel:
         self.lib.orc_grid_backward(ctypes.byref(self.grid), x.shape[0], _p(x), _p(d_enc_soa), _p(g))
         return g
 
+    def grid_input_gradient(self, x, d_enc_soa, grid_params_fp16=None):
+        """dL/d(position) [B][D] fp32 from dL/d(encoded) SoA fp16 bits (grid.h:171-210 + 322-350)."""
+        out = np.zeros((x.shape[0], self.n_in), np.float32)
+        table = np.ascontiguousarray(self.params_fp16[self.n_mlp:] if grid_params_fp16 is None else grid_params_fp16)
+        self.lib.orc_grid_input_gradient(ctypes.byref(self.grid), x.shape[0], _p(x), _p(table), _p(np.ascontiguousarray(d_enc_soa)), _p(out))
+        return out
+
     def backward_from_dy(self, x, dL_dout_bits):
         """Module-tier backward (cpp_api.cu:105-117) restated from the stage functions: fp16-rounded gradients of all parameters
         for a caller-supplied dL/d(output) [B][padded_out] (fp16 bit patterns). Output activation None only."""

@@ -490,8 +490,8 @@ def test_module_tier_matches_trainer_tier_and_oracle(torch_cuda, batch):
     # the two tiers do not mix, and unsupported requests fail loudly
     with pytest.raises(tcnn_b200.TcnnError, match="tcnnb_module_"):
         tcnn_b200._check(tcnn_b200.load().tcnnb_training_step(mod._h, None, batch, xd.data_ptr(), yd.data_ptr(), 0))
-    with pytest.raises(tcnn_b200.TcnnError, match="input positions"):
-        tcnn_b200._check(tcnn_b200.load().tcnnb_module_forward(mod._h, None, batch, xd.data_ptr(), out.data_ptr(), p16.data_ptr(), 1))
+    # prepare_input_gradients is accepted (nothing to prepare: backward recomputes the forward pass)
+    tcnn_b200._check(tcnn_b200.load().tcnnb_module_forward(mod._h, None, batch, xd.data_ptr(), out.data_ptr(), p16.data_ptr(), 1))
 
 
 def test_torch_autograd_layer_on_the_module_tier(torch_cuda):
@@ -534,5 +534,6 @@ def test_torch_autograd_layer_on_the_module_tier(torch_cuda):
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < 0.1 * losses[0], losses[::10]
-    with pytest.raises(NotImplementedError):
-        model(x.clone().requires_grad_(True))
+    xg = x.clone().requires_grad_(True)
+    model(xg).float().sum().backward()  # input gradients are delivered (tests/test_gpu_encoding.py checks their values)
+    assert xg.grad is not None and torch.isfinite(xg.grad).all()

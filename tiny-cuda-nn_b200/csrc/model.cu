@@ -14,6 +14,8 @@
 #include "binning.h"
 #include "common.cuh"
 #include "fused_step.h"
+#include "grid_config.h"
+#include "grid_kernels.h"
 #include "host_common.h"
 #include "json_mini.h"
 #include "misc_kernels.h"
@@ -39,27 +41,6 @@ namespace tcnnb {
 std::atomic<uint64_t> g_kernel_launches{0};
 thread_local std::string g_last_error;
 
-// ------------------------------------------------------------------------------------------------------------------
-struct GridConfig {
-	uint32_t n_pos_dims = 3;
-	uint32_t n_levels = 16;
-	uint32_t n_features_per_level = 2;
-	uint32_t log2_hashmap_size = 19;
-	uint32_t base_resolution = 16;
-	float per_level_scale = 2.0f;
-	uint32_t grid_type = GRID_HASH;
-	uint32_t interpolation = INTERP_LINEAR;
-	bool stochastic_interpolation = false;
-	bool fixed_point_pos = false;
-	std::string otype = "HashGrid";
-	// derived
-	std::vector<uint32_t> offsets;      // n_levels + 1, in entries
-	std::vector<uint32_t> resolutions;  // from the host evaluation (sizing, grid.h:701)
-	std::vector<float> scales;          // device evaluation (lookup)
-	uint32_t n_params = 0;
-	uint32_t padded_width = 0;
-};
-
 struct MlpConfig {
 	std::string otype = "FullyFusedMLP";
 	uint32_t in_width = 0;
@@ -71,84 +52,6 @@ struct MlpConfig {
 	uint32_t output_activation = ACT_NONE;
 	uint32_t n_params = 0;
 };
-
-// grid.h:1726-1851
-static GridConfig parse_grid(uint32_t n_dims_to_encode, const json::Value& e) {
-	GridConfig g;
-	g.otype = e.value("otype", "OneBlob");  // src/encoding.cu:133 default
-	const std::string lower = to_lower(g.otype);
-	if (!(lower == "grid" || lower == "hashgrid" || lower == "tiledgrid" || lower == "densegrid")) {
-		static const char* known[] = {"composite", "empty", "frequency", "identity", "oneblob", "sphericalharmonics", "trianglewave", "oneblobfrequency", "nrc"};
-		for (auto k : known) {
-			if (lower == k) throw std::runtime_error("Encoding '" + g.otype + "' is outside the tcnn_b200 hot path (only Grid/HashGrid/DenseGrid/TiledGrid are built)");
-		}
-		throw std::runtime_error("Encoding '" + g.otype + "' not found");
-	}
-	const std::string hash = e.value("hash", "CoherentPrime");
-	if (!ieq(hash, "CoherentPrime")) {
-		static const char* other[] = {"Prime", "ReversedPrime", "Rng", "BaseConvert"};
-		for (auto k : other) if (ieq(hash, k)) throw std::runtime_error(std::string("GridEncoding: compiled without ") + k + " hash support.");
-		throw std::runtime_error("Invalid hash type: " + hash);
-	}
-	g.n_features_per_level = (uint32_t)e.value("n_features_per_level", 2.0);
-	if (!(g.n_features_per_level == 1 || g.n_features_per_level == 2 || g.n_features_per_level == 4 || g.n_features_per_level == 8)) {
-		throw std::runtime_error("GridEncoding: n_features_per_level must be 1, 2, 4, or 8.");
-	}
-	g.log2_hashmap_size = (uint32_t)e.value("log2_hashmap_size", 19.0);
-	const std::string default_type = lower == "tiledgrid" ? "Tiled" : (lower == "densegrid" ? "Dense" : "Hash");
-	uint32_t n_features;
-	if (e.contains("n_features") || e.contains("n_grid_features")) {
-		n_features = (uint32_t)(e.contains("n_features") ? e.value("n_features", 0.0) : e.value("n_grid_features", 0.0));
-		if (e.contains("n_levels")) {
-			throw std::runtime_error("GridEncoding: may not specify n_features and n_levels simultaneously (one determines the other)");
-		}
-	} else {
-		n_features = g.n_features_per_level * (uint32_t)e.value("n_levels", 16.0);
-	}
-	if (n_features % g.n_features_per_level != 0) {
-		throw std::runtime_error("GridEncoding: n_features=" + std::to_string(n_features) + " must be a multiple of N_FEATURES_PER_LEVEL=" + std::to_string(g.n_features_per_level));
-	}
-	g.n_levels = n_features / g.n_features_per_level;
-	const std::string type = e.value("type", default_type);
-	if (ieq(type, "Hash")) g.grid_type = GRID_HASH;
-	else if (ieq(type, "Dense")) g.grid_type = GRID_DENSE;
-	else if (ieq(type, "Tiled") || ieq(type, "Tile")) g.grid_type = GRID_TILED;
-	else throw std::runtime_error("Invalid grid type: " + type);
-	g.base_resolution = (uint32_t)e.value("base_resolution", 16.0);
-	g.fixed_point_pos = e.value("fixed_point_pos", false);
-	const float default_scale = g.grid_type == GRID_DENSE ? std::exp(std::log(256.0f / (float)g.base_resolution) / (g.n_levels - 1)) : 2.0f;
-	g.per_level_scale = (float)e.value("per_level_scale", (double)default_scale);
-	g.stochastic_interpolation = e.value("stochastic_interpolation", false);
-	const std::string interp = e.value("interpolation", "Linear");
-	if (ieq(interp, "Nearest")) g.interpolation = INTERP_NEAREST;
-	else if (ieq(interp, "Linear")) g.interpolation = INTERP_LINEAR;
-	else if (ieq(interp, "Smoothstep")) g.interpolation = INTERP_SMOOTHSTEP;
-	else throw std::runtime_error("Invalid interpolation type: " + interp);
-	if (n_dims_to_encode < 2 || n_dims_to_encode > 4) throw std::runtime_error("GridEncoding: number of input dims must be 2 or 3.");
-	g.n_pos_dims = n_dims_to_encode;
-	if (g.n_levels > 128) throw std::runtime_error("GridEncoding: m_n_levels=" + std::to_string(g.n_levels) + " must be at most MAX_N_LEVELS=128");
-
-	// Level sizing, grid.h:692-737 (host evaluation of grid_scale / grid_resolution).
-	const float log2_scale = std::log2(g.per_level_scale);
-	uint32_t offset = 0;
-	g.offsets.resize(g.n_levels + 1);
-	g.resolutions.resize(g.n_levels);
-	for (uint32_t i = 0; i < g.n_levels; ++i) {
-		const float scale = exp2f(i * log2_scale) * g.base_resolution - 1.0f;
-		const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
-		g.resolutions[i] = resolution;
-		const uint32_t max_params = std::numeric_limits<uint32_t>::max() / 2;
-		uint32_t params_in_level = std::pow((float)resolution, (float)g.n_pos_dims) > (float)max_params ? max_params : powi(resolution, g.n_pos_dims);
-		params_in_level = next_multiple(params_in_level, 8u);
-		if (g.grid_type == GRID_TILED) params_in_level = std::min(params_in_level, powi(g.base_resolution, g.n_pos_dims));
-		else if (g.grid_type == GRID_HASH) params_in_level = std::min(params_in_level, 1u << g.log2_hashmap_size);
-		g.offsets[i] = offset;
-		offset += params_in_level;
-	}
-	g.offsets[g.n_levels] = offset;
-	g.n_params = offset * g.n_features_per_level;
-	return g;
-}
 
 // ------------------------------------------------------------------------------------------------ NCCL (data parallel)
 // libnccl.so.2 is looked up when the first data-parallel call is made. In a PyTorch process this resolves to the copy
@@ -236,6 +139,9 @@ struct Model {
 	DeviceBuffer<float> scalars;    // [0] = loss sum
 	DeviceBuffer<long long> dbg_clock;  // TCNNB_CLOCKS=<file> in ablation builds: phase stamps of the last ws launch
 	DeviceBuffer<float> level_scales_dev;
+	DeviceBuffer<LevelInfo> levels_dev;     // per-level descriptors for the stand-alone grid kernels (module tier: dL/d(input))
+	DeviceBuffer<__half> denc_scratch;      // module tier: dL/d(encoded) rows [n][64] handed from the fused kernel to the input-gradient kernel
+	DeviceBuffer<__half> grads_scratch;     // module tier: gradient array when the caller wants dL/d(input) only
 	bool mlp_grads_in_accum = false;
 
 	// spatial binning scratch (binning.cu): sorted copies of the batch + permutation
@@ -310,28 +216,7 @@ struct Model {
 		m.n_features = grid.n_levels * grid.n_features_per_level;
 		m.padded_width = grid.padded_width;
 		m.interpolation = grid.interpolation;
-		static const uint32_t MAX_BASES[] = {0x0, 0xFFFFFFFF, 0xFFFF, 0x659, 0xFF, 0x54, 0x28, 0x17, 0xF, 0xB, 0x9};
-		for (uint32_t l = 0; l < grid.n_levels; ++l) {
-			LevelInfo& lv = m.levels[l];
-			lv.offset = grid.offsets[l];
-			lv.size = grid.offsets[l + 1] - grid.offsets[l];
-			lv.scale = grid.scales[l];
-			lv.resolution = (uint32_t)ceilf(lv.scale) + 1;  // grid_resolution(scale) as the kernels evaluate it (grid.h:98)
-			// grid_index (common_device.h:847-884)
-			uint32_t stride = 1;
-			bool dense_ok = lv.resolution <= MAX_BASES[grid.n_pos_dims];
-			if (dense_ok) {
-				for (uint32_t d = 0; d < grid.n_pos_dims; ++d) stride *= lv.resolution;
-			} else {
-				stride = 0xFFFFFFFFu;
-			}
-			if (grid.grid_type == GRID_HASH && lv.size < stride) lv.use_hash = 1;
-			else lv.use_hash = dense_ok ? 0 : 2;
-			lv.pow2_mask = (lv.size & (lv.size - 1)) == 0 ? lv.size - 1 : 0;
-			// dense index <= res * (res^D - 1) / (res - 1) < 2 * res^D: a conditional subtract is an exact modulo when size >= res^D
-			lv.wide_ok = (lv.offset % 4u) == 0 ? 1 : 0;
-			lv.small_mod = (lv.use_hash == 0 && stride != 0xFFFFFFFFu && lv.size >= stride && lv.resolution >= 2) ? 1 : 0;
-		}
+		for (uint32_t l = 0; l < grid.n_levels; ++l) m.levels[l] = make_level_info(grid, l);
 		return m;
 	}
 };
@@ -455,11 +340,8 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 	if (m.grid.stochastic_interpolation) throw std::runtime_error("tcnn_b200: stochastic_interpolation is not built");
 
 	// ---- per-level scales, evaluated on the device like the reference's kernels (common_device.h:886-891)
-	m.grid.scales.resize(m.grid.n_levels);
 	m.level_scales_dev.resize(128);
-	TCNNB_CUDA_CHECK(launch_level_scales(nullptr, m.grid.n_levels, std::log2(m.grid.per_level_scale), m.grid.base_resolution, m.level_scales_dev.ptr));
-	++g_kernel_launches;
-	TCNNB_CUDA_CHECK(cudaMemcpy(m.grid.scales.data(), m.level_scales_dev.ptr, sizeof(float) * m.grid.n_levels, cudaMemcpyDeviceToHost));
+	evaluate_level_scales(m.grid, m.level_scales_dev.ptr);
 
 	// ---- parameter buffers (trainer.h:69-87,489-503)
 	m.n_params = (size_t)mlp.n_params + m.grid.n_params;
@@ -588,6 +470,7 @@ struct ModuleIO {
 	const __half* params = nullptr;
 	__half* grads = nullptr;
 	const __half* dL_doutput = nullptr;
+	__half* dL_dencoded = nullptr;  // optional [n][64] fp16: the network's input gradient rows, for the input-position gradient
 };
 
 static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_t loss_batch, const float* x, const float* y, bool run_optimizer, cudaEvent_t targets_ready = nullptr,
@@ -614,6 +497,7 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
 		p.params = io->params;
 		p.grads = io->grads;
 		p.ext_dy = io->dL_doutput;
+		if (io->dL_dencoded) p.dbg_denc = io->dL_dencoded;
 		p.targets = nullptr;
 		p.loss_sum = nullptr;
 		p.loss_values = nullptr;
@@ -745,24 +629,55 @@ static void module_forward(Model& m, cudaStream_t stream, uint32_t n, const floa
 
 // backward: dL_dparams (fp16 [n_params], OVERWRITTEN -- GradientMode::Overwrite, cpp_api.cu:115) from dL_doutput (fp16 [n][padded]).
 static void module_backward(Model& m, cudaStream_t stream, uint32_t n, float* dL_dinput, const void* dL_doutput, void* dL_dparams, const float* x, const void* params) {
-	if (dL_dinput) throw std::runtime_error("module: gradients w.r.t. the input positions are not implemented (pass dL_dinput = null).");
-	if (!dL_dparams) return;  // nothing to compute (GradientMode::Ignore)
+	if (!dL_dparams && !dL_dinput) return;  // nothing to compute (GradientMode::Ignore)
 	check_module_ptr(params, "params");
 	check_module_ptr(dL_doutput, "dL_doutput");
-	check_module_ptr(dL_dparams, "dL_dparams");
 	ModuleIO io;
 	io.params = (const __half*)params;
-	io.grads = (__half*)dL_dparams;
 	io.dL_doutput = (const __half*)dL_doutput;
+	if (dL_dparams) {
+		check_module_ptr(dL_dparams, "dL_dparams");
+		io.grads = (__half*)dL_dparams;
+	} else {  // input gradients only: the fused kernel still needs somewhere to scatter
+		m.grads_scratch.resize(m.n_params_padded);
+		io.grads = m.grads_scratch.ptr;
+	}
+	if (dL_dinput) {
+		// dL/d(input) (cpp_api.cu:104-125 -> NetworkWithInputEncoding::backward -> GridEncoding::backward_impl, grid.h:896-921): the fused
+		// kernel hands out the network's input gradient rows, the stand-alone kernel contracts them with d(encoded)/d(position).
+		m.denc_scratch.resize(std::max(m.denc_scratch.n, (size_t)n * 64));
+		io.dL_dencoded = m.denc_scratch.ptr;
+	}
 	if (m.mlp_grads_in_accum) {
 		TCNNB_CUDA_CHECK(cudaMemsetAsync(m.dw_accum.ptr, 0, sizeof(float) * m.mlp.n_params, stream));
 		m.mlp_grads_in_accum = false;
 	}
 	training_step(m, stream, n, n, x, nullptr, false, nullptr, &io);
 	// network weight gradients: fp32 sums -> fp16 entries of the caller's array; re-arms the accumulator
-	TCNNB_CUDA_CHECK(launch_mlp_grad_finalize(stream, m.mlp.n_params, m.dw_accum.ptr, (__half*)dL_dparams));
+	TCNNB_CUDA_CHECK(launch_mlp_grad_finalize(stream, m.mlp.n_params, m.dw_accum.ptr, io.grads));
 	++g_kernel_launches;
 	m.mlp_grads_in_accum = false;
+	if (dL_dinput) {
+		if (m.levels_dev.n == 0) {
+			std::vector<LevelInfo> levels(m.grid.n_levels);
+			for (uint32_t l = 0; l < m.grid.n_levels; ++l) levels[l] = make_level_info(m.grid, l);
+			m.levels_dev.resize(levels.size());
+			TCNNB_CUDA_CHECK(cudaMemcpyAsync(m.levels_dev.ptr, levels.data(), sizeof(LevelInfo) * levels.size(), cudaMemcpyHostToDevice, stream));
+			TCNNB_CUDA_CHECK(cudaStreamSynchronize(stream));  // `levels` is a pageable temporary
+		}
+		GridKernelArgs a{};
+		a.n_pos_dims = m.grid.n_pos_dims;
+		a.n_features_per_level = m.grid.n_features_per_level;
+		a.n_levels = m.grid.n_levels;
+		a.interpolation = m.grid.interpolation;
+		a.max_level = 1.0f;
+		a.levels_dev = m.levels_dev.ptr;
+		a.n_elements = n;
+		a.positions = x;
+		a.row_stride = 64;
+		TCNNB_CUDA_CHECK(launch_grid_input_gradient(stream, a, (const __half*)params + m.mlp.n_params, m.denc_scratch.ptr, dL_dinput));
+		++g_kernel_launches;
+	}
 }
 
 static void ensure_staging(Model& m, uint32_t batch) {
@@ -1251,7 +1166,7 @@ int tcnnb_module_inference(tcnnb_model* m, tcnnb_stream stream, uint32_t n_eleme
 
 int tcnnb_module_forward(tcnnb_model* m, tcnnb_stream stream, uint32_t n_elements, const float* input_dev, void* output_dev, const void* params_dev, int prepare_input_gradients) {
 	TCNNB_API_BEGIN
-	if (prepare_input_gradients) throw std::runtime_error("module: gradients w.r.t. the input positions are not implemented (prepare_input_gradients must be 0).");
+	(void)prepare_input_gradients;  // nothing to prepare: backward recomputes the forward pass, including d(encoded)/d(position)
 	module_forward(m->impl, (cudaStream_t)stream, n_elements, input_dev, output_dev, params_dev);
 	TCNNB_API_END
 }

@@ -65,6 +65,16 @@ ABI = [
     ("tcnnb_module_inference", _int, [_vp, _vp, ctypes.c_uint32, _vp, _vp, _vp]),
     ("tcnnb_module_forward", _int, [_vp, _vp, ctypes.c_uint32, _vp, _vp, _vp, ctypes.c_int]),
     ("tcnnb_module_backward", _int, [_vp, _vp, ctypes.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("tcnnb_encoding_create", _int, [_u32, ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    ("tcnnb_encoding_destroy", None, [_vp]),
+    ("tcnnb_encoding_n_params", _u64, [_vp]),
+    ("tcnnb_encoding_n_input_dims", _u32, [_vp]),
+    ("tcnnb_encoding_n_output_dims", _u32, [_vp]),
+    ("tcnnb_encoding_grid_levels", _int, [_vp, ctypes.POINTER(_u32), ctypes.POINTER(_u32), _f32p, ctypes.POINTER(_u32)]),
+    ("tcnnb_encoding_set_max_level", _int, [_vp, ctypes.c_float]),
+    ("tcnnb_encoding_initialize_params", _int, [_vp, _u64, _vp, ctypes.c_float]),
+    ("tcnnb_encoding_forward", _int, [_vp, _vp, _u32, _vp, _vp, _vp]),
+    ("tcnnb_encoding_backward", _int, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
     ("tcnnb_network_create", _int, [_u32, _u32, ctypes.c_char_p, ctypes.POINTER(_vp)]),
     ("tcnnb_network_destroy", None, [_vp]),
     ("tcnnb_network_n_params", _u64, [_vp]),
@@ -404,17 +414,80 @@ class Module:
             _check(lib.tcnnb_module_forward(self._h, _stream_handle(stream), inputs.shape[0], inputs.data_ptr(), out.data_ptr(), params.data_ptr(), 0))
         return out
 
-    def bwd(self, inputs, params, dL_doutput, output=None, stream=None):
+    def bwd(self, inputs, params, dL_doutput, output=None, stream=None, want_input_grad=False, want_param_grad=True):
+        """dL_dparams (fp16 [n_params]); with want_input_grad -> (dL_dparams or None, dL_dinput fp32 [n][n_input_dims])."""
         import torch
 
-        grads = torch.empty(self.n_params, dtype=torch.float16, device="cuda")
-        _check(load().tcnnb_module_backward(self._h, _stream_handle(stream), inputs.shape[0], None, dL_doutput.data_ptr(), grads.data_ptr(), inputs.data_ptr(),
-                                            output.data_ptr() if output is not None else None, params.data_ptr()))
-        return grads
+        grads = torch.empty(self.n_params, dtype=torch.float16, device="cuda") if want_param_grad else None
+        dinput = torch.empty(inputs.shape[0], self.n_input_dims, dtype=torch.float32, device="cuda") if want_input_grad else None
+        _check(load().tcnnb_module_backward(self._h, _stream_handle(stream), inputs.shape[0], dinput.data_ptr() if want_input_grad else None, dL_doutput.data_ptr(),
+                                            grads.data_ptr() if want_param_grad else None, inputs.data_ptr(), output.data_ptr() if output is not None else None, params.data_ptr()))
+        return (grads, dinput) if want_input_grad else grads
 
     def close(self):
         if self._h:
             load().tcnnb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class Encoding:
+    """tcnn::cpp::create_encoding (cpp_api.h:124) for the grid encodings: caller-owned fp16 parameters, fp16 features."""
+
+    def __init__(self, n_input_dims, encoding_config):
+        lib = load()
+        h = ctypes.c_void_p()
+        text = encoding_config if isinstance(encoding_config, str) else json.dumps(encoding_config)
+        _check(lib.tcnnb_encoding_create(n_input_dims, text.encode(), ctypes.byref(h)))
+        self._h = h
+        self.n_input_dims = n_input_dims
+        self.n_params = lib.tcnnb_encoding_n_params(h)
+        self.n_output_dims = lib.tcnnb_encoding_n_output_dims(h)
+
+    def grid_levels(self):
+        n = ctypes.c_uint32(0)
+        offsets = (ctypes.c_uint32 * 129)()
+        scales = (ctypes.c_float * 128)()
+        res = (ctypes.c_uint32 * 128)()
+        _check(load().tcnnb_encoding_grid_levels(self._h, ctypes.byref(n), offsets, scales, res))
+        L = n.value
+        return {"n_levels": L, "offsets": list(offsets[: L + 1]), "scales": list(scales[:L]), "resolutions": list(res[:L])}
+
+    def set_max_level(self, value):
+        _check(load().tcnnb_encoding_set_max_level(self._h, float(value)))
+
+    def initial_params(self, seed=1337, scale=1.0):
+        import torch
+
+        p = torch.empty(self.n_params, dtype=torch.float32, device="cuda")
+        _check(load().tcnnb_encoding_initialize_params(self._h, seed, p.data_ptr(), scale))
+        return p
+
+    def fwd(self, x, params16, stream=None):
+        import torch
+
+        out = torch.empty(x.shape[0], self.n_output_dims, dtype=torch.float16, device=x.device)
+        _check(load().tcnnb_encoding_forward(self._h, _stream_handle(stream), x.shape[0], x.data_ptr(), out.data_ptr(), params16.data_ptr()))
+        return out
+
+    def bwd(self, x, params16, dL_doutput, want_params=True, want_input=False, stream=None):
+        """-> (dL_dparams fp16 [n_params] or None, dL_dinput fp32 [n][n_input_dims] or None)"""
+        import torch
+
+        gp = torch.empty(self.n_params, dtype=torch.float16, device=x.device) if want_params else None
+        gx = torch.empty(x.shape[0], self.n_input_dims, dtype=torch.float32, device=x.device) if want_input else None
+        _check(load().tcnnb_encoding_backward(self._h, _stream_handle(stream), x.shape[0], gx.data_ptr() if want_input else None, dL_doutput.data_ptr(),
+                                              gp.data_ptr() if want_params else None, x.data_ptr(), params16.data_ptr()))
+        return gp, gx
+
+    def close(self):
+        if self._h:
+            load().tcnnb_encoding_destroy(self._h)
             self._h = None
 
     def __del__(self):
