@@ -122,3 +122,45 @@ def test_network_identity_inference_matches_oracle(torch_cuda):
         tcnn_b200.Network(16, 16, {"otype": "FullyFusedMLP", "n_neurons": 48})
     with pytest.raises(tcnn_b200.TcnnError, match="multiple of 256"):
         net.inference(x[:100], p16)
+
+
+import glob  # noqa: E402
+import json  # noqa: E402
+import os  # noqa: E402
+
+from golden_util import GOLDEN  # noqa: E402
+
+MLP_GOLDEN = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "mlp_*.npz")) if not p.endswith("_jit.npz"))
+
+
+@pytest.mark.parametrize("name", MLP_GOLDEN)
+def test_network_against_reference_golden_vectors(torch_cuda, name):
+    """tests/golden/mlp_*.npz: weights, fp16 inputs and fp16 outputs of the UNMODIFIED reference's Network<__half>::inference_mixed_precision
+    (`ref_harness mlpdump`: create_network<T>(json), FullyFusedMLP 128 x 4 / 64 x 2 / 32 x 3 Tanh->Sigmoid, CutlassMLP 64 x 2) on a B200.
+    Same weights, same inputs -> outputs within the reference's own forward bar (tests/test_common.h:177: RAE < 1e-2 @ p99); the
+    difference is the accumulator: fp16 inside HMMA there, fp32 in tensor memory here."""
+    torch = torch_cuda
+    import tcnn_b200
+
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    cfg = {"otype": meta["otype"], "n_neurons": meta["width"], "n_hidden_layers": meta["n_hidden_layers"], "activation": meta["activation"], "output_activation": meta["output_activation"]}
+    net = tcnn_b200.Network(meta["n_in"], meta["n_out"], cfg)
+    assert net.n_params == meta["n_params"] and net.padded_output_width == meta["padded_output_width"]
+    B = meta["batch"]
+    p16 = torch.from_numpy(z["params_f16"].view(np.float16).copy()).cuda()
+    x = torch.from_numpy(z["x_f16"].view(np.float16).reshape(B, meta["n_in"]).copy()).cuda()
+    out = net.inference_mixed_precision(x, p16)
+    torch.cuda.synchronize()
+    a = out.float().cpu().numpy()
+    b = ob.half_bits_to_float(z["output_f16"]).reshape(B, meta["padded_output_width"])
+    assert rae(a, b, 99.0) < 1e-2
+    assert np.abs(a - b).max() <= 2e-2 * max(1.0, np.abs(b).max())
+    jit = os.path.join(GOLDEN, name + "_jit.npz")
+    if os.path.exists(jit):  # the reference's JIT-fused mode on the same weights and inputs
+        bj = ob.half_bits_to_float(np.load(jit)["output_f16"]).reshape(B, meta["padded_output_width"])
+        assert rae(a, bj, 99.0) < 1e-2
+    # and the oracle, which this kernel must match to fp16 rounding
+    _, o_ref = oracle_forward(meta["width"], meta["n_hidden_layers"], meta["n_in"], meta["padded_output_width"], meta["activation"], meta["output_activation"], z["params_f16"],
+                              z["x_f16"].reshape(B, meta["n_in"]))
+    assert rae(a, ob.half_bits_to_float(o_ref), 99.0) < 2e-3

