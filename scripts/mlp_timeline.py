@@ -1,0 +1,76 @@
+"""Phase timeline of the stand-alone MLP kernel (csrc/mlp_fused.cu) from its clock64 stamps: where a slot's layer period goes.
+
+    python scripts/mlp_timeline.py [width] [hidden] > profiles/r02_mlp_timeline.json
+
+Per slot and layer the epilogue warp records: 0 wait start, 1 accumulator ready, 2/4 tcgen05.ld of chunk 0/1 returned, 3/5 tcgen05.st of
+chunk 0/1 issued, 6 tcgen05.wait::st done, 7 arrived on a_ready; the MMA issuer records 0 operand seen ready, 1 MMAs + commit issued."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tiny-cuda-nn_b200"))
+import numpy as np
+import torch
+
+import tcnn_b200
+
+width = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+hidden = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+slots = 2 if width == 128 else 4
+n_ctas = 148
+tiles_per_slot = 6
+B = n_ctas * 128 * slots * tiles_per_slot
+net = tcnn_b200.Network(width, width, {"otype": "FullyFusedMLP", "n_neurons": width, "n_hidden_layers": hidden})
+p16 = net.initial_params(1).half().contiguous()
+x = torch.rand(B, width, device="cuda").half().contiguous()
+for _ in range(3):
+    net.inference_mixed_precision(x, p16)
+clocks = torch.zeros(n_ctas, 5, 64, 8, dtype=torch.int64, device="cuda")
+tcnn_b200._check(tcnn_b200.load().tcnnb_network_debug_clocks(net._h, clocks.data_ptr()))
+net.inference_mixed_precision(x, p16)
+torch.cuda.synchronize()
+tcnn_b200._check(tcnn_b200.load().tcnnb_network_debug_clocks(net._h, None))
+c = clocks.cpu().numpy().astype(np.float64)
+n_layers = hidden + 1
+n_ev = min(64, tiles_per_slot * n_layers)
+res = {"width": width, "n_hidden_layers": hidden, "slots": slots, "batch": B, "unit": "SM cycles (clock64), medians over CTAs / slots / steady-state events"}
+
+
+def med(a):
+    a = np.asarray(a)
+    return float(np.median(a)) if a.size else None
+
+
+ep = c[:, 1 : 1 + slots, :n_ev, :]  # [cta][slot][event][field]
+hid = np.array([e for e in range(n_ev) if e % n_layers != hidden and e >= n_layers])  # hidden-layer events after the first tile
+res["epilogue"] = {
+    "wait_for_accumulator": med(ep[:, :, hid, 1] - ep[:, :, hid, 0]),
+    "ld_chunk0": med(ep[:, :, hid, 2] - ep[:, :, hid, 1]),
+    "convert_st_chunk0": med(ep[:, :, hid, 3] - ep[:, :, hid, 2]),
+    "ld_chunk1": med(ep[:, :, hid, 4] - ep[:, :, hid, 3]),
+    "convert_st_chunk1": med(ep[:, :, hid, 5] - ep[:, :, hid, 4]),
+    "wait_st": med(ep[:, :, hid, 6] - ep[:, :, hid, 5]),
+    "fence_arrive": med(ep[:, :, hid, 7] - ep[:, :, hid, 6]),
+    "busy_total": med(ep[:, :, hid, 7] - ep[:, :, hid, 1]),
+    "layer_period": med(ep[:, :, hid[1:], 1] - ep[:, :, hid[1:] - 1, 1]) if len(hid) > 1 else None,
+}
+iss = c[:, 0, : min(64, n_ev * slots), :]
+ev = np.arange(slots * n_layers, iss.shape[1])
+res["issuer"] = {
+    "issue_8_mma_and_commit": med(iss[:, ev, 1] - iss[:, ev, 0]),
+    "between_issues": med(iss[:, ev[1:], 0] - iss[:, ev[1:] - 1, 1]),
+}
+# hand-offs: a_ready arrive (epilogue field 7 of event e) -> issuer sees it (issuer field 0 of event (e + 1) of the same slot);
+#            issuer commit (field 1) -> epilogue sees the accumulator (field 1)
+lat_a, lat_acc = [], []
+for s in range(slots):
+    for e in hid:
+        nxt = (e + 1) * slots + s
+        if nxt < iss.shape[1]:
+            lat_a.append(iss[:, nxt, 0] - ep[:, s, e, 7])
+        cur = e * slots + s
+        if cur < iss.shape[1]:
+            lat_acc.append(ep[:, s, e, 1] - iss[:, cur, 1])
+res["handoff"] = {"a_ready_to_issue_start": med(np.concatenate(lat_a)) if lat_a else None, "commit_to_accumulator_seen (MMA execution + barrier)": med(np.concatenate(lat_acc)) if lat_acc else None}
+print(json.dumps(res, indent=1))

@@ -83,6 +83,12 @@ __device__ __forceinline__ void tmem_st_n<32>(uint32_t taddr, const uint32_t (&r
 
 }  // namespace
 
+// Phase stamps for scripts/mlp_timeline.py: [cta][role: 0 = MMA issuer, 1 + s = epilogue warp 0 of slot s][event 0..63][field 0..7].
+#define MLPF_STAMP(role, event, field)                                                                                               \
+	do {                                                                                                                             \
+		if (p.dbg_clock && (event) < 64u) p.dbg_clock[(((size_t)blockIdx.x * 5u + (role)) * 64u + (event)) * 8u + (field)] = clock64(); \
+	} while (0)
+
 template <uint32_t W, bool GENERIC_ACT>
 __global__ void __launch_bounds__(MlpCfg<W>::THREADS, 1)
 mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wo) {
@@ -193,6 +199,8 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 				if (real && !__all_sync(0xFFFFFFFFu, mbar_test(bar_a_ready + 8 * s, a_par[s]))) continue;
 				if (!__all_sync(0xFFFFFFFFu, mbar_test(bar_w_full + 8 * stage, w_par))) continue;
 				if (real) {
+					const uint32_t ev = round[s] * n_layers + l;
+					if (lane == 0) MLPF_STAMP(0, ev * C::SLOTS + s, 0);
 					tc_fence_after_sync();
 					if (elect_one_sync()) {
 						const uint32_t slot_base = tmem_base + s * 2 * C::REGION;
@@ -209,6 +217,7 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 						if (!resident) umma_commit(bar_w_free + 8 * stage);
 					}
 					__syncwarp();
+					if (lane == 0) MLPF_STAMP(0, ev * C::SLOTS + s, 1);
 					a_par[s] ^= 1u;
 				} else if (lane == 0) {
 					mbar_arrive_plain(bar_w_free + 8 * stage);
@@ -284,9 +293,13 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 			for (uint32_t l = 0; l <= NH; ++l) {
 				// the next tile's input travels while the last layer computes
 				if (l == NH && j + C::SLOTS < n_my) load_input(blockIdx.x + (j + C::SLOTS) * gridDim.x);
+				const uint32_t ev = (j / C::SLOTS) * n_layers + l;
+				const bool stamp = wq == 0 && lane == 0;
+				if (stamp) MLPF_STAMP(1 + s, ev, 0);
 				mbar_wait(bar_acc_ready + 8 * s, acc_par);
 				acc_par ^= 1u;
 				tc_fence_after_sync();
+				if (stamp) MLPF_STAMP(1 + s, ev, 1);
 				const uint32_t acc = slot_base + (l & 1u) * C::REGION;
 				if (l < NH) {
 					// hidden layer: fp32 accumulator row -> activation in fp16 -> packed, IN PLACE into the first half of this region
@@ -296,10 +309,12 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 						uint32_t r[C::CHUNK];
 						tmem_ld_n<C::CHUNK>(acc + c * C::CHUNK, r);
 						tmem_ld_wait();
+						if (stamp) MLPF_STAMP(1 + s, ev, 2 + 2 * (c & 1u));
 						uint32_t h[C::CHUNK / 2];
 #pragma unroll
 						for (uint32_t i = 0; i < C::CHUNK / 2; ++i) h[i] = act_pack(hid_act, r[2 * i], r[2 * i + 1]);
 						tmem_st_n<C::CHUNK / 2>(acc + c * (C::CHUNK / 2), h);
+						if (stamp) MLPF_STAMP(1 + s, ev, 3 + 2 * (c & 1u));
 						if (p.hidden_out) {
 							uint4* dst = reinterpret_cast<uint4*>(p.hidden_out + ((size_t)l * p.batch_size + sample) * W + c * C::CHUNK);
 #pragma unroll
@@ -307,9 +322,11 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 						}
 					}
 					tmem_st_wait();
+					if (stamp) MLPF_STAMP(1 + s, ev, 6);
 					tc_fence_before_sync();
 					__syncwarp();
 					if (lane == 0) mbar_arrive_plain(bar_a_ready + 8 * s);
+					if (stamp) MLPF_STAMP(1 + s, ev, 7);
 				} else {
 					// output layer: activation, fp16 rows (and / or trimmed fp32 rows) straight to global memory
 					for (uint32_t c = 0; c * 16 < out_w; ++c) {

@@ -26,6 +26,8 @@ struct MlpForwardParams {
 	uint32_t n_output_dims;
 	// optional: post-activation hidden layers [n_hidden_layers][batch][width] fp16 (forward pass kept for a backward pass)
 	__half* hidden_out;
+	// profiling only (scripts/mlp_timeline.py): clock64 stamps [cta][slot + 1 (0 = issuer)][64 events][8], null in production
+	long long* dbg_clock;
 };
 
 // Maximum number of weight matrices that stay resident in shared memory for a width (more layers stream through a ring).

@@ -27,6 +27,7 @@ struct Network {
 	uint32_t activation = ACT_RELU, output_activation = ACT_NONE;
 	uint64_t n_params = 0;
 	int n_sms = 148;
+	long long* dbg_clock = nullptr;  // profiling only (tcnnb_network_debug_clocks)
 	std::string otype, hyperparams_json;
 };
 
@@ -88,6 +89,7 @@ static MlpForwardParams make_params(const Network& n, uint32_t batch, const void
 	p.batch_size = batch;
 	p.n_input_dims = n.n_input_dims;
 	p.n_output_dims = n.n_output_dims;
+	p.dbg_clock = n.dbg_clock;
 	return p;
 }
 
@@ -124,6 +126,12 @@ uint32_t tcnnb_network_input_width(const tcnnb_network* n) { return n->impl.in_w
 uint32_t tcnnb_network_padded_output_width(const tcnnb_network* n) { return n->impl.padded_out_width; }
 uint32_t tcnnb_network_width(const tcnnb_network* n) { return n->impl.width; }
 uint32_t tcnnb_network_n_hidden_layers(const tcnnb_network* n) { return n->impl.n_hidden_layers; }
+
+int tcnnb_network_debug_clocks(tcnnb_network* n, void* clocks_dev) {
+	TCNNB_API_BEGIN
+	n->impl.dbg_clock = (long long*)clocks_dev;
+	TCNNB_API_END
+}
 
 int tcnnb_network_initialize_params(tcnnb_network* n, uint64_t seed, float* params_full_precision_dev, float scale) {
 	TCNNB_API_BEGIN
