@@ -154,6 +154,9 @@ int tcnnb_network_forward(tcnnb_network* n, tcnnb_stream stream, uint32_t n_elem
 /* cpp::create_network semantics: fp32 input [n][n_input_dims] through the Identity encoding (padding features are 1,
  * encodings/identity.h:62-66) -> fp32 output [n][n_output_dims] (object.h:214-282). */
 int tcnnb_network_inference(tcnnb_network* n, tcnnb_stream stream, uint32_t n_elements, const float* input_dev, float* output_dev, const void* params_dev);
+/* The same with the module tier's output convention (cpp_api.cu:82-83): fp16 [n][padded_output_width]. This is what
+ * tcnn::cpp::Module::inference / forward of create_network returns. */
+int tcnnb_network_module_inference(tcnnb_network* n, tcnnb_stream stream, uint32_t n_elements, const float* input_dev, void* output_dev, const void* params_dev);
 /* Profiling only (scripts/mlp_timeline.py): clock64 phase stamps of the following launches are written to
  * int64 [n_ctas][5 roles][64 events][8 fields] at clocks_dev (null = off). Not part of the drop-in surface. */
 int tcnnb_network_debug_clocks(tcnnb_network* n, void* clocks_dev);

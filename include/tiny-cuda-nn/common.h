@@ -14,6 +14,12 @@
 
 #include "../tcnn_b200.h"
 
+/* The reference's common_host.h:33 includes <fmt/format.h>, and its samples call fmt::format without including it themselves
+ * (samples/mlp_learning_an_image.cu:291). fmt is the APPLICATION's dependency here, as nlohmann/json is: forwarded when present. */
+#if __has_include(<fmt/format.h>)
+#include <fmt/format.h>
+#endif
+
 namespace tcnn {
 
 using network_precision_t = __half;                   /* common.h:121-126 (TCNN_HALF_PRECISION builds) */
@@ -42,7 +48,8 @@ constexpr T div_round_up(T val, T divisor) { return (val + divisor - 1) / diviso
 template <typename T>
 constexpr T next_multiple(T val, T divisor) { return div_round_up(val, divisor) * divisor; } /* common.h:255-258 */
 
-static constexpr uint32_t N_THREADS_LINEAR = 128; /* common.h:288 */
+static constexpr uint32_t N_THREADS_LINEAR = 128; /* common.h:247 */
+static constexpr uint32_t n_threads_linear = N_THREADS_LINEAR; /* common.h:252 */
 template <typename T>
 constexpr uint32_t n_blocks_linear(T n_elements, uint32_t n_threads = N_THREADS_LINEAR) { return (uint32_t)div_round_up(n_elements, (T)n_threads); }
 

