@@ -160,6 +160,8 @@ int tcnnb_network_module_inference(tcnnb_network* n, tcnnb_stream stream, uint32
 /* Profiling only (scripts/mlp_timeline.py): clock64 phase stamps of the following launches are written to
  * int64 [n_ctas][5 roles][64 events][8 fields] at clocks_dev (null = off). Not part of the drop-in surface. */
 int tcnnb_network_debug_clocks(tcnnb_network* n, void* clocks_dev);
+/* Profiling only: select a compile-time variant of the kernel for A/B timing (bit 0: operand hand-off in halves, bit 1: I/O path). */
+int tcnnb_network_debug_flags(tcnnb_network* n, uint32_t flags);
 
 /* ---- data parallelism, natively over NCCL (no counterpart in the single-GPU reference) -------------
  * One process per GPU. Rendezvous is the host framework's job (torch.distributed in tcnn_b200/dp.py): rank 0 draws two NCCL
@@ -173,6 +175,18 @@ int tcnnb_network_debug_clocks(tcnnb_network* n, void* clocks_dev);
 int tcnnb_dp_unique_id(void* out_id, uint64_t n_bytes);
 int tcnnb_dp_init(tcnnb_model* m, const void* id_grads, const void* id_params, int world_size, int rank, int shard_optimizer);
 int tcnnb_dp_shards_optimizer(const tcnnb_model* m); /* 1 if the sharded optimizer is in effect (aligned slices, world > 1) */
+/* Peer-memory engine (single NVSwitch domain, <= 8 ranks). The host framework allocates one SYMMETRIC buffer of at least
+ * 4 * tcnnb_n_params_padded + 256 bytes per rank that every rank has mapped (PyTorch: torch.distributed._symmetric_memory.empty +
+ * rendezvous) and passes this rank's view of every rank's buffer (peer_bases[world], device pointers as integers) and the NVLS
+ * multicast view of the same buffer (0 if the fabric has none). The model moves its working fp16 parameters and its gradient
+ * vector into the buffer; from then on tcnnb_dp_training_step replaces reduce-scatter -> Adam -> all-gather by
+ *   barrier -> ONE kernel on the rank's slice {gradient summed over the ranks with multimem.ld_reduce (or peer loads), Adam,
+ *   updated fp16 weights published to all replicas with multimem.st (or peer stores)} -> barrier,
+ * the barriers being flag exchanges over NVLink inside the same buffer. All ranks must call this collectively and synchronise
+ * (host barrier) before the next step. The buffer must outlive the model's data-parallel state (tcnnb_dp_finish). */
+int tcnnb_dp_attach_symmetric(tcnnb_model* m, const uint64_t* peer_bases, uint64_t multicast_base, uint64_t n_bytes);
+/* 0 = not data parallel, 1 = NCCL collectives, 2 = peer-memory engine over peer loads / stores, 3 = over NVLS multicast */
+int tcnnb_dp_engine(const tcnnb_model* m);
 int tcnnb_dp_training_step(tcnnb_model* m, tcnnb_stream stream, uint32_t shard_batch_size, uint32_t global_batch_size, const float* input_dev, const float* target_dev);
 int tcnnb_dp_sync_full_precision(tcnnb_model* m, tcnnb_stream stream);
 int tcnnb_dp_finish(tcnnb_model* m); /* destroys the communicators (call before the process group goes away) */

@@ -15,7 +15,7 @@ CFG = json.load(open(os.path.join(ROOT, "tests", "golden", "configs", "hash3d_sm
 B = 32768
 
 
-def worker(rank, world, out, shard_optimizer, native):
+def worker(rank, world, out, shard_optimizer, native, peer_memory):
     import oracle_binding as ob
     import tcnn_b200
     from tcnn_b200.dp import DataParallelTrainer
@@ -27,8 +27,12 @@ def worker(rank, world, out, shard_optimizer, native):
     x = ob.generate_random_uniform(rng, B * 3).reshape(B, 3)
     y = ob.make_targets(x, 3)
     model = tcnn_b200.create_from_config(3, 3, CFG)
-    dp = DataParallelTrainer(model.trainer, shard_optimizer=shard_optimizer, native=native)
+    dp = DataParallelTrainer(model.trainer, shard_optimizer=shard_optimizer, native=native, peer_memory=peer_memory)
     assert dp.native == native and dp.shard_optimizer == shard_optimizer
+    if rank == 0:
+        print("engine:", dp.engine, flush=True)
+    if peer_memory and os.environ.get("TCNNB_REQUIRE_PEER_MEMORY"):
+        assert dp.engine.startswith("peer-memory"), dp.engine
     lo, hi = dp.shard(B)
     xd, yd = torch.from_numpy(x[lo:hi]).cuda(), torch.from_numpy(y[lo:hi]).cuda()
     losses = []
@@ -37,7 +41,7 @@ def worker(rank, world, out, shard_optimizer, native):
         losses.append(dp.loss())
     dp.sync_full_precision()
     torch.cuda.synchronize()
-    np.savez(os.path.join(out, f"dp{rank}_{int(shard_optimizer)}{int(native)}.npz"), p=model.trainer.params_full_precision().cpu().numpy(), p16=model.trainer.params().cpu().view(torch.int16).numpy(), losses=np.array(losses))
+    np.savez(os.path.join(out, f"dp{rank}_{int(shard_optimizer)}{int(native)}{int(peer_memory)}.npz"), p=model.trainer.params_full_precision().cpu().numpy(), p16=model.trainer.params().cpu().view(torch.int16).numpy(), losses=np.array(losses))
     dp.close()
     dist.destroy_process_group()
 
@@ -45,9 +49,11 @@ def worker(rank, world, out, shard_optimizer, native):
 if __name__ == "__main__":
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
-    MODES = [(False, False), (True, False), (False, True), (True, True)]  # (sharded optimizer, native NCCL engine)
-    for so, nat in MODES:
-        mp.spawn(worker, args=(2, out, so, nat), nprocs=2, join=True)
+    # (sharded optimizer, native engine inside libtcnn_b200, peer-memory kernels instead of NCCL collectives)
+    MODES = [(False, False, False), (True, False, False), (False, True, False), (True, True, False), (True, True, True)]
+    WORLD = int(os.environ.get("TCNNB_DP_WORLD", "2"))
+    for so, nat, pm in MODES:
+        mp.spawn(worker, args=(WORLD, out, so, nat, pm), nprocs=WORLD, join=True)
     import oracle_binding as ob
     import tcnn_b200
 
@@ -62,9 +68,9 @@ if __name__ == "__main__":
         model.trainer.training_step(xd, yd)
         losses.append(model.trainer.loss())
     p1 = model.trainer.params_full_precision().cpu().numpy()
-    for so, nat in MODES:
-        r0, r1 = np.load(os.path.join(out, f"dp0_{int(so)}{int(nat)}.npz")), np.load(os.path.join(out, f"dp1_{int(so)}{int(nat)}.npz"))
-        print("sharded optimizer:", so, "native engine:", nat)
+    for so, nat, pm in MODES:
+        r0, r1 = np.load(os.path.join(out, f"dp0_{int(so)}{int(nat)}{int(pm)}.npz")), np.load(os.path.join(out, f"dp{WORLD - 1}_{int(so)}{int(nat)}{int(pm)}.npz"))
+        print("sharded optimizer:", so, "native engine:", nat, "peer memory:", pm)
         print("  replicas identical (fp32 masters / fp16 working):", np.array_equal(r0["p"], r1["p"]), np.array_equal(r0["p16"], r1["p16"]))
         print("  losses dp:", r0["losses"].tolist())
         print("  losses 1gpu:", losses)

@@ -18,11 +18,13 @@ import tcnn_b200
 
 width = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 hidden = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 slots = 2 if width == 128 else 4
 n_ctas = 148
 tiles_per_slot = 6
 B = n_ctas * 128 * slots * tiles_per_slot
 net = tcnn_b200.Network(width, width, {"otype": "FullyFusedMLP", "n_neurons": width, "n_hidden_layers": hidden})
+tcnn_b200._check(tcnn_b200.load().tcnnb_network_debug_flags(net._h, flags))
 p16 = net.initial_params(1).half().contiguous()
 x = torch.rand(B, width, device="cuda").half().contiguous()
 for _ in range(3):
@@ -35,7 +37,7 @@ tcnn_b200._check(tcnn_b200.load().tcnnb_network_debug_clocks(net._h, None))
 c = clocks.cpu().numpy().astype(np.float64)
 n_layers = hidden + 1
 n_ev = min(64, tiles_per_slot * n_layers)
-res = {"width": width, "n_hidden_layers": hidden, "slots": slots, "batch": B, "unit": "SM cycles (clock64), medians over CTAs / slots / steady-state events"}
+res = {"variant_flags": flags, "width": width, "n_hidden_layers": hidden, "slots": slots, "batch": B, "unit": "SM cycles (clock64), medians over CTAs / slots / steady-state events"}
 
 
 def med(a):
@@ -77,4 +79,11 @@ for s in range(slots):
 res["handoff"] = {"commit_to_accumulator_seen (MMA drain + barrier)": med(np.concatenate(lat_acc)) if lat_acc else None}
 total = c[:, 1 : 1 + slots, :n_ev, 1]
 res["mma_floor_cycles_per_layer"] = 128 * width * width / 8192 / 4 if False else (width * width) / 32
-print(json.dumps(res, indent=1))
+# raw timeline of one CTA (cycles relative to its first stamp): issuer events [slot][layer-event][fields], epilogue events per slot
+cta = c[3]
+t0 = np.nanmin(np.where(cta > 0, cta, np.nan))
+raw = {"issuer": [[int(v - t0) if v > 0 else None for v in cta[0, e, :3]] for e in range(min(40, iss.shape[1]))]}
+for s_ in range(slots):
+    raw[f"slot{s_}"] = [[int(v - t0) if v > 0 else None for v in cta[1 + s_, e, :8]] for e in range(min(20, n_ev))]
+res["raw_cta3"] = raw
+print(json.dumps(res))

@@ -16,6 +16,7 @@ sys.path.insert(0, os.path.join(ROOT, "tiny-cuda-nn_b200"))
 out = os.path.join(ROOT, "gpurun_out", "ws_clocks.bin")
 os.makedirs(os.path.dirname(out), exist_ok=True)
 os.environ["TCNNB_CLOCKS"] = out
+os.environ.setdefault("TCNNB_LIB", os.path.join(ROOT, "tiny-cuda-nn_b200", "ablation", "libtcnn_b200.so"))  # the ABLATION=1 build
 import torch
 
 import tcnn_b200
@@ -32,11 +33,17 @@ mhz = float(subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm", "--format=csv
 model.close()
 
 c = np.fromfile(out, dtype=np.int64).reshape(-1, 3, 16, 16).astype(np.float64)
+# The buffer has room for 2 x #SMs CTAs (the removed two-CTAs-per-SM shape); the kernel runs #SMs of them. Round 1's version kept the
+# all-zero slots, which poisoned every median: drop CTAs that left no stamp, and treat unset stamps as missing.
+c = c[(c != 0).any(axis=(1, 2, 3))]
+c[c == 0] = np.nan
+n_ctas = int(c.shape[0])
 us = 1.0 / mhz  # cycles -> microseconds
 steady = slice(4, 12)
 
 
 def med(a):
+    a = np.asarray(a, np.float64)
     a = a[np.isfinite(a)]
     return float(np.median(a)) * us if a.size else float("nan")
 
@@ -44,6 +51,7 @@ def med(a):
 mlp = c[:, 0]
 res = {
     "sm_mhz": mhz,
+    "n_ctas_with_stamps": n_ctas,
     "mlp": {
         "tile_period": med((mlp[:, 5:13, 0] - mlp[:, 4:12, 0]).ravel()),
         "wait_enc_full": med((mlp[:, steady, 1] - mlp[:, steady, 0]).ravel()),
@@ -75,8 +83,8 @@ for g_ in (0, 1):
 print(json.dumps({"ws_timeline_us": res}))
 # one CTA's raw timeline (relative to its first stamp), for eyeballing
 cta = c[7]
-t0 = cta[cta > 0].min()
+t0 = np.nanmin(cta)
 for role in range(3):
     for k in range(4, 10):
-        if cta[role, k, 0] > 0:
-            print(role, k, [round((v - t0) * us, 2) if v > 0 else None for v in cta[role, k, :16]])
+        if np.isfinite(cta[role, k, 0]):
+            print(role, k, [round((v - t0) * us, 2) if np.isfinite(v) else None for v in cta[role, k, :16]])

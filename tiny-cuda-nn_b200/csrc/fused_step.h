@@ -6,7 +6,7 @@ namespace tcnnb {
 
 // Ablation switches for profiling experiments (scripts/ablate.py); 0 in production. They skip memory operations only,
 // so the results of an ablated launch are meaningless.
-enum : uint32_t { ABLATE_GATHER = 1, ABLATE_SCATTER = 2, ABLATE_PAIRING = 4 };
+enum : uint32_t { ABLATE_GATHER = 1, ABLATE_SCATTER = 2, ABLATE_PAIRING = 4, ABLATE_GATHER_DENSE = 8, ABLATE_SCATTER_DENSE = 16, ABLATE_GATHER_HASH = 32, ABLATE_SCATTER_HASH = 64 };
 // The switches are compiled in only with -DTCNNB_ENABLE_ABLATION (make ABLATION=1): in the production build they cost nothing.
 #ifdef TCNNB_ENABLE_ABLATION
 #define TCNNB_ABLATE(bit) (p.ablate & (bit))

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 					const __half2 a0 = __hmul2(__float2half2_rn(lc.w[2 * pr]), grad);
 					const __half2 a1 = __hmul2(__float2half2_rn(lc.w[2 * pr + 1]), grad);
 					const bool paired = (lc.paired >> pr) & 1u;
-					if (!(TCNNB_ABLATE(ABLATE_SCATTER))) {
+					if (!(TCNNB_ABLATE(ABLATE_SCATTER)) && !(TCNNB_ABLATE(ABLATE_SCATTER_DENSE) && lv.use_hash == 0) && !(TCNNB_ABLATE(ABLATE_SCATTER_HASH) && lv.use_hash != 0)) {
 						scatter_pair_f16x2(ltab, lc.idx[2 * pr], lc.idx[2 * pr + 1], paired && !(TCNNB_ABLATE(ABLATE_PAIRING)), lv.wide_ok != 0, *reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
 					}
 				}
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 #pragma unroll
 					for (uint32_t pr = 0; pr < (1u << (D - 1)); ++pr) {
 						const bool paired = (lc.paired >> pr) & 1u;
-						if (TCNNB_ABLATE(ABLATE_GATHER)) {
+						if (TCNNB_ABLATE(ABLATE_GATHER) || (TCNNB_ABLATE(ABLATE_GATHER_DENSE) && lv.use_hash == 0) || (TCNNB_ABLATE(ABLATE_GATHER_HASH) && lv.use_hash != 0)) {
 							f.vals[2 * pr] = lc.idx[2 * pr];
 							f.vals[2 * pr + 1] = lc.idx[2 * pr + 1];
 						} else {

@@ -77,70 +77,6 @@ __global__ void level_scales_kernel(uint32_t n_levels, float log2_per_level_scal
 //     for API visibility, and the accumulator is re-armed to zero for the next step.
 //   * optimizer state streams use evict-first loads/stores so that the fp16 table + gradient table stay L2 resident.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void adam_step_kernel(const AdamParams a, const uint32_t n_elements, const uint32_t n_matrix_weights, const float loss_scale,
-                                 float* __restrict__ weights_full_precision, __half* __restrict__ weights, __half* __restrict__ gradients,
-                                 float* __restrict__ dw_accum, float* __restrict__ first_moments, float* __restrict__ second_moments,
-                                 uint32_t* __restrict__ param_steps) {
-	pdl_wait();  // no early pdl_launch_dependents(): a long bandwidth-bound kernel should not share its SMs with parked CTAs
-	const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
-	if (i >= n_elements) return;
-
-	__half grad_h;
-	if (i < n_matrix_weights && dw_accum != nullptr) {
-		grad_h = (__half)dw_accum[i];
-		dw_accum[i] = 0.0f;
-		gradients[i] = grad_h;
-	} else {
-		grad_h = gradients[i];
-	}
-
-	float gradient = (float)grad_h / loss_scale;
-	if (i >= n_matrix_weights) {
-		if (!a.optimize_non_matrix_params || (gradient == 0 && a.skip_zero_grad_non_matrix_params)) return;
-	} else {
-		if (!a.optimize_matrix_params) return;
-	}
-
-	const float weight_fp = __ldcs(weights_full_precision + i);
-
-	if (i < n_matrix_weights) {
-		gradient += a.l2_reg * weight_fp;
-	} else {
-		gradient += a.non_matrix_l2_reg * weight_fp;
-	}
-
-	if (a.gradient_clipping_magnitude != 0.0f) {
-		gradient = copysignf(fminf(fabsf(gradient), a.gradient_clipping_magnitude), gradient);
-	}
-
-	const float gradient_sq = gradient * gradient;
-
-	const float first_moment = a.beta1 * __ldcs(first_moments + i) + (1 - a.beta1) * gradient;
-	__stcs(first_moments + i, first_moment);
-	const float second_moment = a.beta2 * __ldcs(second_moments + i) + (1 - a.beta2) * gradient_sq;
-	__stcs(second_moments + i, second_moment);
-
-	float learning_rate = a.learning_rate;
-	if (i >= n_matrix_weights) learning_rate *= a.non_matrix_learning_rate_factor;
-
-	const uint32_t current_step = __ldcs(param_steps + i) + 1;
-	__stcs(param_steps + i, current_step);
-	learning_rate *= sqrtf(1 - powf(a.beta2, (float)current_step)) / (1 - powf(a.beta1, (float)current_step));
-
-	const float effective_learning_rate = fminf(fmaxf(learning_rate / (sqrtf(second_moment) + a.epsilon), a.lower_lr_bound), a.upper_lr_bound);
-
-	// weight_decay (common_device.h:1045-1048)
-	const float decayed_weight = (1 - a.relative_decay * learning_rate) * weight_fp - copysignf(a.absolute_decay * learning_rate, weight_fp);
-	float new_weight = decayed_weight - effective_learning_rate * first_moment;
-
-	if (a.clipping_magnitude != 0.0f) {
-		new_weight = fminf(fmaxf(new_weight, -a.clipping_magnitude), a.clipping_magnitude);
-	}
-
-	__stcs(weights_full_precision + i, new_weight);
-	weights[i] = (__half)new_weight;
-}
-
 // One Adam update, shared by the scalar and the 4-wide kernels. Returns false if the parameter is skipped.
 __device__ __forceinline__ bool adam_update(const AdamParams& a, const bool is_matrix, const float loss_scale, const __half grad_h,
                                             float& weight_fp, float& first_moment, float& second_moment, uint32_t& step) {
@@ -173,6 +109,33 @@ __device__ __forceinline__ bool adam_update(const AdamParams& a, const bool is_m
 	}
 	weight_fp = new_weight;
 	return true;
+}
+
+// One parameter per thread: the tail / unaligned path (caller-provided arrays that are not 16-byte aligned, lengths that are not a
+// multiple of four); same update as the 4-wide kernel.
+__global__ void adam_step_kernel(const AdamParams a, const uint32_t n_elements, const uint32_t n_matrix_weights, const float loss_scale,
+                                 float* __restrict__ weights_full_precision, __half* __restrict__ weights, __half* __restrict__ gradients,
+                                 float* __restrict__ dw_accum, float* __restrict__ first_moments, float* __restrict__ second_moments,
+                                 uint32_t* __restrict__ param_steps) {
+	pdl_wait();  // no early pdl_launch_dependents(): a long bandwidth-bound kernel should not share its SMs with parked CTAs
+	const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
+	if (i >= n_elements) return;
+	__half grad_h;
+	if (i < n_matrix_weights && dw_accum != nullptr) {
+		grad_h = (__half)dw_accum[i];
+		dw_accum[i] = 0.0f;
+		gradients[i] = grad_h;
+	} else {
+		grad_h = gradients[i];
+	}
+	float w = __ldcs(weights_full_precision + i), m = __ldcs(first_moments + i), v = __ldcs(second_moments + i);
+	uint32_t st = __ldcs(param_steps + i);
+	if (!adam_update(a, i < n_matrix_weights, loss_scale, grad_h, w, m, v, st)) return;
+	__stcs(weights_full_precision + i, w);
+	__stcs(first_moments + i, m);
+	__stcs(second_moments + i, v);
+	__stcs(param_steps + i, st);
+	weights[i] = (__half)w;
 }
 
 // 4 parameters per thread: 128-bit streaming accesses to the fp32 state, 64-bit to the fp16 params / gradients.
@@ -232,6 +195,100 @@ __global__ void mlp_grad_finalize_kernel(uint32_t n, float* __restrict__ dw_accu
 	}
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Data parallelism over peer memory. See misc_kernels.h for the protocol.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void dp_barrier_kernel(const DpPeers peers, const uint32_t epoch) {
+	const uint32_t t = threadIdx.x;
+	if (t >= peers.world) return;
+	__threadfence_system();  // this rank's earlier writes (gradients, published weights) before the signal
+	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.flags[t] + peers.rank), "r"(epoch) : "memory");
+	const uint32_t* mine = peers.flags[peers.rank] + t;
+	const long long t0 = clock64();
+	for (;;) {
+		uint32_t seen;
+		asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+		if ((int32_t)(seen - epoch) >= 0) break;
+		if (clock64() - t0 > 40000000000LL) __trap();  // ~20 s: a peer died; fail loudly instead of hanging the GPU
+	}
+}
+
+template <bool MULTICAST>
+__global__ void __launch_bounds__(256) adam_step_dp_kernel(const AdamParams a, const DpPeers peers, const uint64_t first, const uint32_t n_groups, const uint32_t n_matrix_weights,
+                                                            const uint64_t n_params, const float loss_scale, float* __restrict__ weights_full_precision,
+                                                            float* __restrict__ first_moments, float* __restrict__ second_moments, uint32_t* __restrict__ param_steps) {
+	const uint32_t gidx = threadIdx.x + blockIdx.x * blockDim.x;
+	if (gidx >= n_groups) return;
+	const uint64_t i0 = first + (uint64_t)gidx * 8;
+	if (i0 >= n_params) return;  // padding of the parameter vector: never touched
+
+	// ---- the reduced gradient of 8 consecutive parameters: one 16-byte access per rank, or one in-switch reduction
+	uint32_t gw[4];
+	if (MULTICAST) {
+		asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0, %1, %2, %3}, [%4];" : "=r"(gw[0]), "=r"(gw[1]), "=r"(gw[2]), "=r"(gw[3]) : "l"(peers.grads_mc + i0) : "memory");
+	} else {
+		float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+		for (uint32_t r = 0; r < peers.world; ++r) {
+			uint32_t w[4];
+			asm volatile("ld.relaxed.sys.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(peers.grads[r] + i0) : "memory");
+#pragma unroll
+			for (uint32_t k = 0; k < 4; ++k) {
+				const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+				acc[2 * k] += f.x;
+				acc[2 * k + 1] += f.y;
+			}
+		}
+#pragma unroll
+		for (uint32_t k = 0; k < 4; ++k) {
+			const __half2 h = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
+			gw[k] = *reinterpret_cast<const uint32_t*>(&h);
+		}
+	}
+	// the reduced gradient stays in the local gradient buffer (what trainer->param_gradients() shows for the owned slice)
+	*reinterpret_cast<uint4*>(peers.grads[peers.rank] + i0) = make_uint4(gw[0], gw[1], gw[2], gw[3]);
+	if (i0 >= n_matrix_weights && a.skip_zero_grad_non_matrix_params && ((gw[0] | gw[1] | gw[2] | gw[3]) & 0x7FFF7FFFu) == 0) return;  // untouched entries (adam.h:79-82)
+
+	const float4* w4p = reinterpret_cast<const float4*>(weights_full_precision + i0);
+	const float4* m4p = reinterpret_cast<const float4*>(first_moments + i0);
+	const float4* v4p = reinterpret_cast<const float4*>(second_moments + i0);
+	const uint4* s4p = reinterpret_cast<const uint4*>(param_steps + i0);
+	const float4 wa = __ldcs(w4p), wb = __ldcs(w4p + 1), ma = __ldcs(m4p), mb = __ldcs(m4p + 1), va = __ldcs(v4p), vb = __ldcs(v4p + 1);
+	const uint4 sa = __ldcs(s4p), sb = __ldcs(s4p + 1);
+	float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w}, m[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w}, v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+	uint32_t st[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+	const __half* g = reinterpret_cast<const __half*>(gw);
+	bool any = false;
+#pragma unroll
+	for (uint32_t k = 0; k < 8; ++k) any |= adam_update(a, i0 + k < n_matrix_weights, loss_scale, g[k], w[k], m[k], v[k], st[k]);
+	if (!any) return;
+	float4* w4o = reinterpret_cast<float4*>(weights_full_precision + i0);
+	float4* m4o = reinterpret_cast<float4*>(first_moments + i0);
+	float4* v4o = reinterpret_cast<float4*>(second_moments + i0);
+	uint4* s4o = reinterpret_cast<uint4*>(param_steps + i0);
+	__stcs(w4o, make_float4(w[0], w[1], w[2], w[3]));
+	__stcs(w4o + 1, make_float4(w[4], w[5], w[6], w[7]));
+	__stcs(m4o, make_float4(m[0], m[1], m[2], m[3]));
+	__stcs(m4o + 1, make_float4(m[4], m[5], m[6], m[7]));
+	__stcs(v4o, make_float4(v[0], v[1], v[2], v[3]));
+	__stcs(v4o + 1, make_float4(v[4], v[5], v[6], v[7]));
+	__stcs(s4o, make_uint4(st[0], st[1], st[2], st[3]));
+	__stcs(s4o + 1, make_uint4(st[4], st[5], st[6], st[7]));
+	// ---- publish the working-precision weights to every replica
+	uint32_t hw[4];
+#pragma unroll
+	for (uint32_t k = 0; k < 4; ++k) {
+		const __half2 h = __floats2half2_rn(w[2 * k], w[2 * k + 1]);
+		hw[k] = *reinterpret_cast<const uint32_t*>(&h);
+	}
+	if (MULTICAST) {
+		asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(peers.params_mc + i0), "r"(hw[0]), "r"(hw[1]), "r"(hw[2]), "r"(hw[3]) : "memory");
+	} else {
+		for (uint32_t r = 0; r < peers.world; ++r) {
+			asm volatile("st.relaxed.sys.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(peers.params[r] + i0), "r"(hw[0]), "r"(hw[1]), "r"(hw[2]), "r"(hw[3]) : "memory");
+		}
+	}
+}
+
 }  // namespace
 
 static inline uint32_t blocks_for(uint64_t n, uint32_t threads) { return (uint32_t)((n + threads - 1) / threads); }
@@ -277,6 +334,27 @@ cudaError_t launch_adam_step(cudaStream_t stream, const AdamParams& a, uint32_t 
 cudaError_t launch_mlp_grad_finalize(cudaStream_t stream, uint32_t n, float* dw_accum, __half* gradients) {
 	if (n == 0) return cudaSuccess;
 	return launch_pdl(mlp_grad_finalize_kernel, blocks_for(n, 256), 256, 0, stream, n, dw_accum, gradients);
+}
+
+cudaError_t launch_dp_barrier(cudaStream_t stream, const DpPeers& peers, uint32_t epoch) {
+	if (peers.world < 1 || peers.world > DP_MAX_RANKS) return cudaErrorInvalidValue;
+	dp_barrier_kernel<<<1, 32, 0, stream>>>(peers, epoch);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_adam_step_dp(cudaStream_t stream, const AdamParams& a, const DpPeers& peers, uint64_t first, uint64_t count, uint32_t n_matrix_weights, uint64_t n_params,
+                                float loss_scale, float* weights_full_precision, float* first_moments, float* second_moments, uint32_t* param_steps) {
+	if (count == 0) return cudaSuccess;
+	if (first % 8 != 0 || count % 8 != 0 || n_params % 8 != 0 || n_matrix_weights % 8 != 0) return cudaErrorInvalidValue;
+	const uint32_t n_groups = (uint32_t)(count / 8);
+	if (peers.grads_mc && peers.params_mc) {
+		adam_step_dp_kernel<true><<<blocks_for(n_groups, 256), 256, 0, stream>>>(a, peers, first, n_groups, n_matrix_weights, n_params, loss_scale, weights_full_precision, first_moments,
+		                                                                          second_moments, param_steps);
+	} else {
+		adam_step_dp_kernel<false><<<blocks_for(n_groups, 256), 256, 0, stream>>>(a, peers, first, n_groups, n_matrix_weights, n_params, loss_scale, weights_full_precision, first_moments,
+		                                                                           second_moments, param_steps);
+	}
+	return cudaGetLastError();
 }
 
 }  // namespace tcnnb

@@ -33,4 +33,27 @@ cudaError_t launch_adam_step(cudaStream_t stream, const AdamParams& a, uint32_t 
                              float* second_moments, uint32_t* param_steps);
 cudaError_t launch_mlp_grad_finalize(cudaStream_t stream, uint32_t n, float* dw_accum, __half* gradients);
 
+// ---- data parallelism over peer memory (NVLink / NVSwitch): one-pass "reduce + Adam + publish" on this rank's slice ----------------
+// Every rank holds [fp16 params | fp16 gradients | flags] at the SAME offsets of a symmetric allocation that all peers have
+// mapped (rendezvous by the host framework). peers.* are this rank's views of every rank's copy; *_mc are the NVLS multicast
+// views of the same regions (null when the fabric has no multicast: the kernels then loop over the peer pointers).
+constexpr uint32_t DP_MAX_RANKS = 8;
+struct DpPeers {
+	uint32_t world, rank;
+	__half* params[DP_MAX_RANKS];
+	__half* grads[DP_MAX_RANKS];
+	uint32_t* flags[DP_MAX_RANKS];  // [DP_MAX_RANKS] monotonic epoch counters per rank: flags[r][q] = last barrier rank q has reached, as seen by rank r
+	__half* params_mc;
+	__half* grads_mc;
+};
+// Cross-GPU barrier on `stream`: everything enqueued before it on every rank's stream is complete and visible to all ranks before
+// anything enqueued after it starts. `epoch` must increase by one per call, identically on all ranks.
+cudaError_t launch_dp_barrier(cudaStream_t stream, const DpPeers& peers, uint32_t epoch);
+// Adam over the parameters [first, first + count) (multiples of 8) of the padded vector: the gradient of a parameter is the SUM over
+// ranks of grads[r][i] (multimem.ld_reduce in the switch, or peer loads), evaluated once by the slice's owner; the updated fp16
+// weight is published into every rank's params (multimem.st, or peer stores); the reduced gradient is left in the local gradient
+// buffer. State arrays (fp32 master, moments, steps) are local and indexed by the global parameter index.
+cudaError_t launch_adam_step_dp(cudaStream_t stream, const AdamParams& a, const DpPeers& peers, uint64_t first, uint64_t count, uint32_t n_matrix_weights, uint64_t n_params,
+                                float loss_scale, float* weights_full_precision, float* first_moments, float* second_moments, uint32_t* param_steps);
+
 }  // namespace tcnnb

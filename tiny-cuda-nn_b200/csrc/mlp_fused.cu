@@ -43,6 +43,8 @@ using namespace fused;
 namespace {
 
 constexpr uint32_t MLPF_MAX_STAGES = 32;
+constexpr bool MLPF_DEFAULT_SPLIT = false;  // measured: see profiles/r02_mlp_variants.md
+constexpr bool MLPF_DEFAULT_COAL = true;
 
 template <uint32_t W>
 struct MlpCfg {
@@ -116,10 +118,15 @@ __device__ __forceinline__ void transpose8x8_u128(uint4 (&a)[8], uint32_t lane) 
 		if (p.dbg_clock && (event) < 64u) p.dbg_clock[(((size_t)blockIdx.x * 5u + (role)) * 64u + (event)) * 8u + (field)] = clock64(); \
 	} while (0)
 
-template <uint32_t W, bool GENERIC_ACT>
+// SPLIT: hand the next layer's operand over in two halves (first k-steps overlap the second half of the epilogue).
+// COAL:  move network input / output rows through the 8-lane transpose (coalesced 128-byte row pieces) instead of row-per-thread.
+// Both are compile-time variants so that scripts/bench_mlp.py --variants can A/B them on the device (tcnnb_network_debug_flags).
+template <uint32_t W, bool GENERIC_ACT, bool SPLIT, bool COAL>
 __global__ void __launch_bounds__(MlpCfg<W>::THREADS, 1)
 mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wo) {
 	using C = MlpCfg<W>;
+	constexpr uint32_t NCHUNK = W / C::CHUNK;          // accumulator chunks per hidden-layer epilogue
+	constexpr uint32_t NHALF = SPLIT ? NCHUNK : 1;     // operand hand-offs per layer
 	const MlpForwardParams& p = kp.p;
 	const uint32_t hid_act = GENERIC_ACT ? p.activation : (uint32_t)ACT_RELU;
 	const uint32_t out_act = GENERIC_ACT ? p.output_activation : (uint32_t)ACT_NONE;
@@ -209,7 +216,7 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 		for (uint32_t s = 0; s < C::SLOTS; ++s) {
 			layer[s] = half[s] = round[s] = a_par[s] = 0;
 			n_real[s] = n_my > s ? (n_my - s + C::SLOTS - 1) / C::SLOTS : 0;
-			remaining += (resident ? n_real[s] : n_rounds) * n_layers * C::NHALF;
+			remaining += (resident ? n_real[s] : n_rounds) * n_layers * NHALF;
 		}
 		const uint32_t idesc_hidden = umma_idesc_f16(128, W, 0, 0);
 		const uint32_t idesc_out = umma_idesc_f16(128, out_w, 0, 0);
@@ -229,7 +236,7 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 				// warp-uniform decisions (every lane tests; the vote makes the result one value)
 				if (real && !__all_sync(0xFFFFFFFFu, mbar_test(bar_a_ready + 8 * (2 * s + h), (a_par[s] >> h) & 1u))) continue;
 				if (h == 0 && !__all_sync(0xFFFFFFFFu, mbar_test(bar_w_full + 8 * stage, w_par))) continue;
-				const bool last_half = h == C::NHALF - 1;
+				const bool last_half = h == NHALF - 1;
 				if (real) {
 					const uint32_t ev = round[s] * n_layers + l;
 					if (lane == 0 && h == 0) MLPF_STAMP(0, ev * C::SLOTS + s, 0);
@@ -240,7 +247,7 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 						const uint32_t a_tmem = slot_base + ((l + 1u) & 1u) * C::REGION;  // first half of the other region
 						const uint32_t b_smem = s_stage0 + stage * C::STAGE_BYTES;
 						const uint32_t ksteps = (l == 0 ? in_w : W) / 16;
-						const uint32_t j0 = h * C::KSTEPS_PER_HALF;
+						const uint32_t j0 = SPLIT ? h * C::KSTEPS_PER_HALF : 0u;
 						const uint32_t j1 = last_half ? ksteps : (j0 + C::KSTEPS_PER_HALF < ksteps ? j0 + C::KSTEPS_PER_HALF : ksteps);
 						const uint32_t idesc = l == NH ? idesc_out : idesc_hidden;
 						for (uint32_t j = j0; j < j1; ++j) {
@@ -258,7 +265,7 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 				} else if (last_half && lane == 0) {
 					mbar_arrive_plain(bar_w_free + 8 * stage);
 				}
-				if (++half[s] == C::NHALF) {
+				if (++half[s] == NHALF) {
 					half[s] = 0;
 					if (++layer[s] == n_layers) {
 						layer[s] = 0;
@@ -288,10 +295,12 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 #pragma unroll
 				for (uint32_t b = 0; b < IN_BLOCKS; ++b) {
 					if (b * 64 < in_w) {
-						const uint32_t col = b * 64 + l8 * 8;  // this lane's 16-byte piece inside the block
 #pragma unroll
 						for (uint32_t jj = 0; jj < 8; ++jj) {
-							pre[b][jj] = col < in_w ? __ldg(reinterpret_cast<const uint4*>(p.input_fp16 + (tile_row0 + g8 * 8 + jj) * in_w + col)) : make_uint4(0, 0, 0, 0);
+							// COAL: piece l8 of row (g8 * 8 + jj); else piece jj of this thread's own row
+							const uint32_t col = b * 64 + (COAL ? l8 : jj) * 8;
+							const size_t r = tile_row0 + (COAL ? g8 * 8 + jj : lane);
+							pre[b][jj] = col < in_w ? __ldg(reinterpret_cast<const uint4*>(p.input_fp16 + r * in_w + col)) : make_uint4(0, 0, 0, 0);
 						}
 					}
 				}
@@ -332,7 +341,7 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 #pragma unroll
 				for (uint32_t b = 0; b < IN_BLOCKS; ++b) {
 					if (b * 64 < in_w) {
-						if (p.input_fp16) transpose8x8_u128(pre[b], lane);
+						if (COAL && p.input_fp16) transpose8x8_u128(pre[b], lane);
 #pragma unroll
 						for (uint32_t q = 0; q < 4; ++q) {  // 16 columns of fp16 = 8 TMEM columns per store
 							if (b * 64 + q * 16 < in_w) {
@@ -347,7 +356,7 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 				__syncwarp();
 				if (lane == 0) {
 					mbar_arrive_plain(bar_a_ready + 8 * (2 * s));
-					if (C::NHALF == 2) mbar_arrive_plain(bar_a_ready + 8 * (2 * s + 1));
+					if (NHALF == 2) mbar_arrive_plain(bar_a_ready + 8 * (2 * s + 1));
 				}
 			}
 			for (uint32_t l = 0; l <= NH; ++l) {
@@ -366,7 +375,7 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 					// (chunk c reads columns [c*CHUNK, (c+1)*CHUNK) and writes [c*CHUNK/2, (c+1)*CHUNK/2): always columns already read).
 					// Each chunk is handed to the MMA issuer as soon as it is stored: the next layer's first k-steps overlap chunk 1.
 #pragma unroll
-					for (uint32_t c = 0; c < C::NHALF; ++c) {
+					for (uint32_t c = 0; c < NCHUNK; ++c) {
 						uint32_t r[C::CHUNK];
 						tmem_ld_n<C::CHUNK>(acc + c * C::CHUNK, r);
 						tmem_ld_wait();
@@ -381,10 +390,12 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 #pragma unroll
 							for (uint32_t i = 0; i < C::CHUNK / 8; ++i) dst[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
 						}
-						tmem_st_wait();
-						tc_fence_before_sync();
-						__syncwarp();
-						if (lane == 0) mbar_arrive_plain(bar_a_ready + 8 * (2 * s + c));
+						if (SPLIT || c == NCHUNK - 1) {
+							tmem_st_wait();
+							tc_fence_before_sync();
+							__syncwarp();
+							if (lane == 0) mbar_arrive_plain(bar_a_ready + 8 * (2 * s + (SPLIT ? c : 0u)));
+						}
 						if (stamp) MLPF_STAMP(1 + s, ev, 4 + 3 * c);
 					}
 				} else {
@@ -417,10 +428,11 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 								}
 							}
 							if (p.output_fp16) {
-								transpose8x8_u128(o, lane);
+								if (COAL) transpose8x8_u128(o, lane);
 #pragma unroll
 								for (uint32_t jj = 0; jj < 8; ++jj) {
-									*reinterpret_cast<uint4*>(p.output_fp16 + (tile_row0 + g8 * 8 + jj) * out_w + c16 * 16 + l8 * 8) = o[jj];
+									const size_t r = tile_row0 + (COAL ? g8 * 8 + jj : lane);
+									*reinterpret_cast<uint4*>(p.output_fp16 + r * out_w + c16 * 16 + (COAL ? l8 : jj) * 8) = o[jj];
 								}
 							}
 						}
@@ -491,7 +503,7 @@ uint32_t max_stages() {
 	return (uint32_t)((227u * 1024u - 1024u) / MlpCfg<W>::STAGE_BYTES) < MLPF_MAX_STAGES ? (uint32_t)((227u * 1024u - 1024u) / MlpCfg<W>::STAGE_BYTES) : MLPF_MAX_STAGES;
 }
 
-template <uint32_t W, bool GENERIC>
+template <uint32_t W, bool GENERIC, bool SPLIT, bool COAL>
 cudaError_t launch_impl(const MlpForwardParams& p, uint32_t n_sms, cudaStream_t stream) {
 	using C = MlpCfg<W>;
 	const uint32_t n_layers = p.n_hidden_layers + 1;
@@ -510,7 +522,7 @@ cudaError_t launch_impl(const MlpForwardParams& p, uint32_t n_sms, cudaStream_t 
 	}
 	w += (size_t)(p.n_hidden_layers - 1) * W * W;
 	if (!make_weight_map(&mo, w, p.out_width, W, p.out_width)) return cudaErrorInvalidValue;
-	auto kernel = mlp_forward_kernel<W, GENERIC>;
+	auto kernel = mlp_forward_kernel<W, GENERIC, SPLIT, COAL>;
 	const size_t smem = (size_t)kp.n_stages * C::STAGE_BYTES + 8 * (2 * MLPF_MAX_STAGES + 12) + 16;
 	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (err != cudaSuccess) return err;
@@ -521,7 +533,15 @@ cudaError_t launch_impl(const MlpForwardParams& p, uint32_t n_sms, cudaStream_t 
 template <uint32_t W>
 cudaError_t launch_width(const MlpForwardParams& p, uint32_t n_sms, cudaStream_t stream) {
 	const bool generic = p.activation != ACT_RELU || p.output_activation != ACT_NONE;
-	return generic ? launch_impl<W, true>(p, n_sms, stream) : launch_impl<W, false>(p, n_sms, stream);
+	constexpr bool SPLIT = MLPF_DEFAULT_SPLIT, COAL = MLPF_DEFAULT_COAL;
+	if (generic) return launch_impl<W, true, SPLIT, COAL>(p, n_sms, stream);
+	// profiling variants (ReLU networks only): bit 0 flips SPLIT, bit 1 flips COAL
+	switch (p.dbg_flags & 3u) {
+		case 1: return launch_impl<W, false, !SPLIT, COAL>(p, n_sms, stream);
+		case 2: return launch_impl<W, false, SPLIT, !COAL>(p, n_sms, stream);
+		case 3: return launch_impl<W, false, !SPLIT, !COAL>(p, n_sms, stream);
+		default: return launch_impl<W, false, SPLIT, COAL>(p, n_sms, stream);
+	}
 }
 
 }  // namespace

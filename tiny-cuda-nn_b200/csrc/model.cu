@@ -104,6 +104,11 @@ struct DpState {
 	bool masters_synced = true;
 	cudaStream_t gather_stream = nullptr;
 	cudaEvent_t ev_updated = nullptr, ev_gathered = nullptr;
+	// peer-memory engine (tcnnb_dp_attach_symmetric): the working parameters and the gradient vector live in a symmetric allocation
+	// every rank has mapped; reduce-scatter + Adam + all-gather become ONE kernel between two cross-GPU barriers
+	bool fused = false;
+	DpPeers peers{};
+	uint32_t epoch = 0;
 	~DpState() {
 		if (comm_grads) nccl_api().CommDestroy(comm_grads);
 		if (comm_params) nccl_api().CommDestroy(comm_params);
@@ -427,19 +432,25 @@ static FusedStepParams make_params(Model& m, uint32_t batch, uint32_t loss_batch
 	return p;
 }
 
+// Hyper-parameters of the next optimizer step (advances the step counter; AdaBound bounds per adam.h:161-168).
+static AdamParams next_adam_params(Model& m) {
+	++m.adam_step_count;
+	AdamParams a = m.adam;
+	a.lower_lr_bound = 0;
+	a.upper_lr_bound = std::numeric_limits<float>::max();
+	if (a.adabound) {
+		a.lower_lr_bound = 0.1f - 0.1f / ((1 - a.beta2) * (float)m.adam_step_count + 1);
+		a.upper_lr_bound = 0.1f + 0.1f / ((1 - a.beta2) * (float)m.adam_step_count);
+	}
+	return a;
+}
+
 // Adam over the parameter ranges [begin, begin + count) (all parameters when n_ranges == 0). One optimizer step whatever the
 // number of ranges: the data-parallel trainer updates the MLP weights everywhere and the grid entries of its own shard only.
 static void optimizer_step(Model& m, cudaStream_t stream, uint32_t n_ranges = 0, const uint64_t* begins = nullptr, const uint64_t* counts = nullptr) {
 	if (m.module_only) throw std::runtime_error("this handle was created with tcnnb_module_create: it has no optimizer.");
 	m.wait_pending(stream);
-	++m.adam_step_count;
-	AdamParams a = m.adam;
-	a.lower_lr_bound = 0;
-	a.upper_lr_bound = std::numeric_limits<float>::max();
-	if (a.adabound) {  // adam.h:165-168
-		a.lower_lr_bound = 0.1f - 0.1f / ((1 - a.beta2) * (float)m.adam_step_count + 1);
-		a.upper_lr_bound = 0.1f + 0.1f / ((1 - a.beta2) * (float)m.adam_step_count);
-	}
+	const AdamParams a = next_adam_params(m);
 	const uint64_t whole_begin = 0, whole_count = m.n_params;
 	if (n_ranges == 0) {
 		n_ranges = 1;
@@ -569,6 +580,20 @@ static void dp_training_step(Model& m, cudaStream_t stream, uint32_t shard_batch
 		m.mlp_grads_in_accum = false;
 	}
 	const size_t chunk = m.n_params_padded / (size_t)d.world, lo = chunk * (size_t)d.rank;
+	if (d.fused) {
+		// Peer-memory engine: [barrier: every rank's gradient vector is complete] -> ONE kernel on this rank's slice that sums the
+		// gradient over the ranks (in the switch with multimem.ld_reduce, else by peer loads), applies Adam and publishes the fp16
+		// weights into every replica (multimem.st / peer stores) -> [barrier: all slices have landed everywhere; the gradient
+		// vectors may be zeroed again]. No NCCL call on the step.
+		TCNNB_CUDA_CHECK(launch_dp_barrier(stream, d.peers, ++d.epoch));
+		const AdamParams a = next_adam_params(m);
+		TCNNB_CUDA_CHECK(launch_adam_step_dp(stream, a, d.peers, lo, chunk, (uint32_t)m.mlp.n_params, m.n_params, m.loss_scale, m.params_fp32, m.first_moments.ptr, m.second_moments.ptr,
+		                                     m.param_steps.ptr));
+		TCNNB_CUDA_CHECK(launch_dp_barrier(stream, d.peers, ++d.epoch));
+		g_kernel_launches += 3;
+		d.masters_synced = false;
+		return;
+	}
 	TCNNB_NCCL_CHECK(n.ReduceScatter(m.grads_fp16, m.grads_fp16 + lo, chunk, ncclHalf, ncclSum, d.comm_grads, stream));
 	const uint64_t begin = lo, count = lo < m.n_params ? std::min<uint64_t>(chunk, m.n_params - lo) : 0;
 	if (count) optimizer_step(m, stream, 1, &begin, &count);
@@ -1096,6 +1121,50 @@ int tcnnb_dp_init(tcnnb_model* m, const void* id_grads, const void* id_params, i
 	TCNNB_CUDA_CHECK(cudaEventCreateWithFlags(&d->ev_gathered, cudaEventDisableTiming));
 	mm.dp = std::move(d);
 	TCNNB_API_END
+}
+
+int tcnnb_dp_attach_symmetric(tcnnb_model* m, const uint64_t* peer_bases, uint64_t multicast_base, uint64_t n_bytes) {
+	TCNNB_API_BEGIN
+	Model& mm = m->impl;
+	if (!mm.dp || mm.dp->world < 2) throw std::runtime_error("dp_attach_symmetric: call tcnnb_dp_init with world_size > 1 first.");
+	DpState& d = *mm.dp;
+	if (!d.shard_optimizer) throw std::runtime_error("dp_attach_symmetric: needs the sharded optimizer (aligned slices).");
+	if (d.world > (int)DP_MAX_RANKS) throw std::runtime_error("dp_attach_symmetric: at most 8 ranks (one NVSwitch domain).");
+	if (!peer_bases) throw std::runtime_error("dp_attach_symmetric: peer_bases is null.");
+	const size_t np = mm.n_params_padded;
+	const size_t need = np * 2 * sizeof(__half) + 256;
+	if (n_bytes < need) throw std::runtime_error("dp_attach_symmetric: the symmetric buffer must hold " + std::to_string(need) + " bytes.");
+	if (mm.n_params % 8 != 0 || mm.mlp.n_params % 8 != 0 || (np / (size_t)d.world) % 8 != 0) throw std::runtime_error("dp_attach_symmetric: parameter counts must be multiples of 8.");
+	DpPeers& p = d.peers;
+	p.world = (uint32_t)d.world;
+	p.rank = (uint32_t)d.rank;
+	for (int r = 0; r < d.world; ++r) {
+		if (!peer_bases[r] || peer_bases[r] % 16 != 0) throw std::runtime_error("dp_attach_symmetric: bad peer pointer.");
+		char* base = (char*)(uintptr_t)peer_bases[r];
+		p.params[r] = (__half*)base;
+		p.grads[r] = (__half*)base + np;
+		p.flags[r] = (uint32_t*)(base + np * 2 * sizeof(__half));
+	}
+	p.params_mc = multicast_base ? (__half*)(uintptr_t)multicast_base : nullptr;
+	p.grads_mc = multicast_base ? (__half*)(uintptr_t)multicast_base + np : nullptr;
+	// move the working parameters into the symmetric region (local copy), clear gradients and flags; the caller synchronises all
+	// ranks (host barrier) before the first step
+	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
+	TCNNB_CUDA_CHECK(cudaMemcpy(p.params[d.rank], mm.params_fp16, np * sizeof(__half), cudaMemcpyDeviceToDevice));
+	TCNNB_CUDA_CHECK(cudaMemset(p.grads[d.rank], 0, np * sizeof(__half) + 256));
+	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
+	mm.params_fp16 = p.params[d.rank];
+	mm.grads_fp16 = p.grads[d.rank];
+	d.epoch = 0;
+	d.fused = true;
+	TCNNB_API_END
+}
+
+int tcnnb_dp_engine(const tcnnb_model* m) {
+	const DpState* d = m->impl.dp.get();
+	if (!d || d->world < 2) return 0;
+	if (d->fused) return d->peers.params_mc ? 3 : 2;
+	return 1;
 }
 
 int tcnnb_dp_shards_optimizer(const tcnnb_model* m) { return m->impl.dp && m->impl.dp->world > 1 && m->impl.dp->shard_optimizer ? 1 : 0; }

@@ -87,10 +87,13 @@ ABI = [
     ("tcnnb_network_forward", _int, [_vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     ("tcnnb_network_inference", _int, [_vp, _vp, _u32, _vp, _vp, _vp]),
     ("tcnnb_network_debug_clocks", _int, [_vp, _vp]),
+    ("tcnnb_network_debug_flags", _int, [_vp, _u32]),
     ("tcnnb_network_module_inference", _int, [_vp, _vp, _u32, _vp, _vp, _vp]),
     ("tcnnb_dp_unique_id", _int, [_vp, ctypes.c_uint64]),
     ("tcnnb_dp_init", _int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     ("tcnnb_dp_shards_optimizer", _int, [_vp]),
+    ("tcnnb_dp_attach_symmetric", _int, [_vp, ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint64, ctypes.c_uint64]),
+    ("tcnnb_dp_engine", _int, [_vp]),
     ("tcnnb_dp_training_step", _int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),
     ("tcnnb_dp_sync_full_precision", _int, [_vp, _vp]),
     ("tcnnb_dp_finish", _int, [_vp]),
@@ -297,6 +300,20 @@ class _Trainer:
         raw = bytes(ids.cpu().numpy().tobytes())
         _check(lib.tcnnb_dp_init(h, ctypes.c_char_p(raw[:128]), ctypes.c_char_p(raw[128:]), world, rank, int(bool(shard_optimizer))))
         return bool(lib.tcnnb_dp_shards_optimizer(h))
+
+    def dp_symmetric_bytes(self):
+        """Size of the symmetric buffer of the peer-memory engine: fp16 params + fp16 gradients (padded) + flags."""
+        return 4 * int(load().tcnnb_n_params_padded(self._m._h)) + 256
+
+    def dp_attach_symmetric(self, peer_ptrs, multicast_ptr, n_bytes):
+        arr = (ctypes.c_uint64 * len(peer_ptrs))(*peer_ptrs)
+        _check(load().tcnnb_dp_attach_symmetric(self._m._h, arr, ctypes.c_uint64(multicast_ptr), ctypes.c_uint64(n_bytes)))
+        for cached in ("_sharded", "_grad_bufs"):  # views of the old parameter / gradient regions
+            if hasattr(self, cached):
+                delattr(self, cached)
+
+    def dp_engine(self):
+        return {0: "single", 1: "nccl", 2: "peer-memory-p2p", 3: "peer-memory-multicast"}[load().tcnnb_dp_engine(self._m._h)]
 
     def dp_training_step(self, inputs, targets, global_batch_size, stream=None):
         _check(load().tcnnb_dp_training_step(self._m._h, _stream_handle(stream), inputs.shape[0], global_batch_size, inputs.data_ptr(), targets.data_ptr()))

@@ -36,7 +36,7 @@ SLICE_GRANULARITY = 8
 
 
 class DataParallelTrainer:
-    def __init__(self, trainer, group=None, shard_optimizer=True, native=True):
+    def __init__(self, trainer, group=None, shard_optimizer=True, native=True, peer_memory=True):
         self.trainer = trainer
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -53,9 +53,43 @@ class DataParallelTrainer:
         # a Python-driven step costs ~0.4 ms of host time, more than the step takes on the device. The torch.distributed
         # version below is the same logic; it serves backends without NCCL (the gloo CPU tests) and as readable reference.
         self.native = False
+        self.engine = "single" if self.world == 1 else "torch.distributed"
+        self._symm = None
         if self.world > 1 and native and hasattr(trainer, "dp_native_init") and dist.get_backend(group) == "nccl":
             self.shard_optimizer = trainer.dp_native_init(group, shard_optimizer)
             self.native = True
+            self.engine = "nccl"
+            # Peer-memory engine: the working parameters and the gradient vector move into a symmetric allocation every rank has
+            # mapped (torch's symmetric memory does the rendezvous: peer pointers + the NVLS multicast mapping); the library then
+            # replaces reduce-scatter -> Adam -> all-gather by ONE kernel between two NVLink flag barriers (misc_kernels.cu).
+            if peer_memory and self.shard_optimizer and self.world <= 8 and hasattr(trainer, "dp_attach_symmetric"):
+                try:
+                    self.engine = self._attach_symmetric(group)
+                except Exception as e:  # noqa: BLE001 -- no symmetric memory on this system: stay on the NCCL engine, and say so
+                    import warnings
+
+                    warnings.warn(f"tcnn_b200: peer-memory data-parallel engine unavailable ({e!r}); using NCCL collectives")
+                ok = [self.engine]
+                dist.all_gather_object(all_engines := [None] * self.world, ok[0], group=group)
+                if len(set(all_engines)) != 1:
+                    raise RuntimeError(f"data-parallel ranks disagree on the engine: {all_engines}")
+
+    def _attach_symmetric(self, group):
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+
+        n_bytes = self.trainer.dp_symmetric_bytes()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        buf = symm_mem.empty(n_bytes, dtype=torch.uint8, device=dev)
+        hdl = symm_mem.rendezvous(buf, group=group if group is not None else dist.group.WORLD)
+        peers = [int(p) for p in hdl.buffer_ptrs]
+        mc = int(hdl.multicast_ptr) if getattr(hdl, "multicast_ptr", 0) else 0
+        assert peers[self.rank] == buf.data_ptr()
+        self.trainer.dp_attach_symmetric(peers, mc, n_bytes)
+        self._symm = (buf, hdl)  # keeps the mapping alive
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+        return "peer-memory-multicast" if mc else "peer-memory-p2p"
 
     def shard(self, n_global):
         """[begin, end) of this rank's contiguous shard of a global batch; shards must stay multiples of 256."""
@@ -155,6 +189,7 @@ class DataParallelTrainer:
         if self.native:
             self.trainer.dp_finish()
             self.native = False
+            self._symm = None
 
     def loss(self):
         """Sum of the ranks' partial losses == the single-GPU loss of the global batch."""
