@@ -71,6 +71,14 @@ const char* tcnnb_hyperparams(tcnnb_model* m);
 /* ---- trainer->set_params_full_precision / set_params (trainer.h:409-440) ---- */
 int tcnnb_set_params_full_precision(tcnnb_model* m, const float* params, uint64_t n, int device_ptr);
 
+/* trainer->set_params(params, n, device_ptr) (trainer.h:423-440): working-precision (fp16) parameters; the fp32 masters follow. */
+int tcnnb_set_params(tcnnb_model* m, const void* params_half, uint64_t n, int device_ptr);
+/* Optimizer state for trainer->serialize(true) / deserialize (trainer.h:442-482, optimizers/adam.h:303-325): device pointers to
+ * the fp32 first / second moments and the uint32 per-parameter step counters ([n_params] each; valid for the model's lifetime),
+ * the optimizer's step counter and base learning rate. Synchronises the device. */
+int tcnnb_optimizer_state(tcnnb_model* m, float** first_moments_dev, float** second_moments_dev, uint32_t** param_steps_dev, uint32_t* current_step, float* base_learning_rate);
+int tcnnb_set_optimizer_progress(tcnnb_model* m, uint32_t current_step, float base_learning_rate);
+
 /* ---- trainer->training_step(stream, input, target, ..., run_optimizer) (trainer.h:254-357) ----
  * input_dev [batch][n_in] fp32, target_dev [batch][n_out] fp32, both device pointers.
  * Runs fwd + loss + bwd (+ Adam when run_optimizer != 0). The loss of this step is fetched with tcnnb_loss. */

@@ -19,6 +19,7 @@
 #endif
 
 #include <memory>
+#include <string>
 #include <vector>
 
 #include "common.h"
@@ -135,6 +136,80 @@ public:
 		float v = 0;
 		TCNNB_CHECK_THROW(tcnnb_loss(m_handle->m, (tcnnb_stream)stream, &v));
 		return v;
+	}
+
+	/* trainer.h:442-482 + optimizers/adam.h:303-325: the reference's snapshot schema (nlohmann binary values; instant-ngp stores it as
+	 * msgpack): {"n_params", "params_type": "__half", "params_binary", "optimizer": {"current_step", "base_learning_rate",
+	 * "first_moments_binary", "second_moments_binary", "param_steps_binary"}}. Snapshots written by tiny-cuda-nn load here and vice versa. */
+	json serialize(bool serialize_optimizer = false) {
+		const size_t n = n_params();
+		auto blob = [](const void* dev, size_t bytes) {
+			json::binary_t b;
+			b.resize(bytes);
+			CUDA_CHECK_THROW(cudaMemcpy(b.data(), dev, bytes, cudaMemcpyDeviceToHost));
+			return b;
+		};
+		CUDA_CHECK_THROW(cudaDeviceSynchronize());
+		json data;
+		data["n_params"] = n;
+		data["params_type"] = "__half";
+		data["params_binary"] = blob(tcnnb_params(m_handle->m), n * sizeof(__half));
+		if (serialize_optimizer) {
+			float *m1 = nullptr, *m2 = nullptr, lr = 0;
+			uint32_t *steps = nullptr, cur = 0;
+			TCNNB_CHECK_THROW(tcnnb_optimizer_state(m_handle->m, &m1, &m2, &steps, &cur, &lr));
+			json opt;
+			opt["current_step"] = cur;
+			opt["base_learning_rate"] = lr;
+			opt["first_moments_binary"] = blob(m1, n * sizeof(float));
+			opt["second_moments_binary"] = blob(m2, n * sizeof(float));
+			opt["param_steps_binary"] = blob(steps, n * sizeof(uint32_t));
+			data["optimizer"] = opt;
+		}
+		return data;
+	}
+
+	void deserialize(const json& data) {
+		auto bytes_of = [](const json& j) -> std::vector<uint8_t> {
+			if (j.is_binary()) return j.get_binary();
+			if (j.is_object()) {  /* the textual form of a binary value, gpu_memory_json.h:58-67 */
+				std::vector<uint8_t> out;
+				for (const auto& v : j.at("bytes")) out.push_back((uint8_t)v.get<unsigned>());
+				return out;
+			}
+			throw std::runtime_error{"Invalid json type: must be either binary or object"};
+		};
+		const size_t n = n_params();
+		const std::string type = data.value("params_type", std::string{"__half"});
+		const std::vector<uint8_t> p = bytes_of(data.at("params_binary"));
+		if (type == "float") {
+			if (p.size() != n * sizeof(float)) throw std::runtime_error{"Can't set fp params because buffer has the wrong size."};
+			TCNNB_CHECK_THROW(tcnnb_set_params_full_precision(m_handle->m, (const float*)p.data(), n, 0));
+		} else if (type == "__half") {
+			if (p.size() != n * sizeof(__half)) throw std::runtime_error{"Can't set params because buffer has the wrong size."};
+			TCNNB_CHECK_THROW(tcnnb_set_params(m_handle->m, p.data(), n, 0));
+		} else {
+			throw std::runtime_error{"Trainer: snapshot parameters must be of type float of __half"};
+		}
+		if (data.contains("optimizer")) {
+			const json& opt = data["optimizer"];
+			float *m1 = nullptr, *m2 = nullptr;
+			uint32_t* steps = nullptr;
+			TCNNB_CHECK_THROW(tcnnb_optimizer_state(m_handle->m, &m1, &m2, &steps, nullptr, nullptr));
+			const std::vector<uint8_t> a = bytes_of(opt.at("first_moments_binary")), b = bytes_of(opt.at("second_moments_binary"));
+			if (a.size() != n * sizeof(float) || b.size() != n * sizeof(float)) throw std::runtime_error{"Trainer: optimizer snapshot has the wrong size."};
+			CUDA_CHECK_THROW(cudaMemcpy(m1, a.data(), a.size(), cudaMemcpyHostToDevice));
+			CUDA_CHECK_THROW(cudaMemcpy(m2, b.data(), b.size(), cudaMemcpyHostToDevice));
+			if (opt.contains("param_steps_binary")) {
+				const std::vector<uint8_t> c = bytes_of(opt["param_steps_binary"]);
+				if (c.size() != n * sizeof(uint32_t)) throw std::runtime_error{"Trainer: optimizer snapshot has the wrong size."};
+				CUDA_CHECK_THROW(cudaMemcpy(steps, c.data(), c.size(), cudaMemcpyHostToDevice));
+			} else {
+				CUDA_CHECK_THROW(cudaMemset(steps, 0, n * sizeof(uint32_t)));
+			}
+			TCNNB_CHECK_THROW(tcnnb_set_optimizer_progress(m_handle->m, opt.at("current_step").get<uint32_t>(), opt.at("base_learning_rate").get<float>()));
+		}
+		CUDA_CHECK_THROW(cudaDeviceSynchronize());
 	}
 
 	float* params_full_precision() const { return tcnnb_params_full_precision(m_handle->m); }

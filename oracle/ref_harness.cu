@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <iterator>
 #include <string>
 #include <sys/stat.h>
 #include <vector>
@@ -504,6 +505,66 @@ static int cmd_mlpbench(int argc, char** argv) {
 	return 0;
 }
 
+// ---- snapshot interoperability (trainer.h:442-482): the reference's own serialize() / deserialize(), stored as msgpack like instant-ngp does
+// snapshot save <config> <n_in> <n_out> <B> <n_steps> <outdir> <with_optimizer>: train n_steps, write snapshot.msgpack, x.f32, y.f32, inference.f32
+// snapshot load <config> <n_in> <n_out> <B> <dir> <file.msgpack>: deserialize, inference on dir/x.f32 -> dir/inference_loaded.f32, one more
+//                training step on (x, y) -> prints its loss (exercises the restored optimizer state)
+static std::vector<float> read_f32(const std::string& path) {
+	std::ifstream f{path, std::ios::binary | std::ios::ate};
+	if (!f) throw std::runtime_error{"cannot open " + path};
+	std::vector<float> v((size_t)f.tellg() / 4);
+	f.seekg(0);
+	f.read((char*)v.data(), v.size() * 4);
+	return v;
+}
+
+static int cmd_snapshot(int argc, char** argv) {
+	if (argc < 9) {
+		fprintf(stderr, "usage: snapshot save config n_in n_out B n_steps outdir with_optimizer | snapshot load config n_in n_out B dir file\n");
+		return 2;
+	}
+	const std::string mode = argv[2];
+	Setup s;
+	make_setup(s, argv[3], atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), false);
+	auto& trainer = s.model.trainer;
+	auto& network = s.model.network;
+	GPUMatrix<float> pred(s.n_out, s.B);
+	if (mode == "save") {
+		const std::string outdir = argv[8];
+		mkdir(outdir.c_str(), 0755);
+		float loss = 0;
+		for (int i = 0; i < atoi(argv[7]); ++i) {
+			auto ctx = trainer->training_step(nullptr, s.x, s.y);
+			loss = trainer->loss(nullptr, *ctx);
+		}
+		const json snap = trainer->serialize(argc > 9 && atoi(argv[9]) != 0);
+		const std::vector<uint8_t> bytes = json::to_msgpack(snap);
+		std::ofstream f{outdir + "/snapshot.msgpack", std::ios::binary};
+		f.write((const char*)bytes.data(), bytes.size());
+		network->inference(nullptr, s.x, pred);
+		CUDA_CHECK_THROW(cudaDeviceSynchronize());
+		write_host_bin(outdir + "/x.f32", s.hx);
+		write_host_bin(outdir + "/y.f32", s.hy);
+		write_bin(outdir + "/inference.f32", pred.data(), (size_t)s.n_out * s.B);
+		printf("{\"saved\": \"%s/snapshot.msgpack\", \"bytes\": %zu, \"last_loss\": %.6g}\n", outdir.c_str(), bytes.size(), loss);
+		return 0;
+	}
+	const std::string dir = argv[7];
+	std::ifstream f{argv[8], std::ios::binary};
+	if (!f) throw std::runtime_error{std::string{"cannot open "} + argv[8]};
+	const std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+	trainer->deserialize(json::from_msgpack(bytes));
+	const std::vector<float> hx = read_f32(dir + "/x.f32"), hy = read_f32(dir + "/y.f32");
+	CUDA_CHECK_THROW(cudaMemcpy(s.x.data(), hx.data(), hx.size() * 4, cudaMemcpyHostToDevice));
+	CUDA_CHECK_THROW(cudaMemcpy(s.y.data(), hy.data(), hy.size() * 4, cudaMemcpyHostToDevice));
+	network->inference(nullptr, s.x, pred);
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	write_bin(dir + "/inference_loaded.f32", pred.data(), (size_t)s.n_out * s.B);
+	auto ctx = trainer->training_step(nullptr, s.x, s.y);
+	printf("{\"loaded\": \"%s\", \"next_step_loss\": %.6g}\n", argv[8], trainer->loss(nullptr, *ctx));
+	return 0;
+}
+
 int main(int argc, char** argv) {
 	try {
 		if (argc < 2) {
@@ -515,6 +576,7 @@ int main(int argc, char** argv) {
 		if (cmd == "bench") return cmd_bench(argc, argv);
 		if (cmd == "dumpbig") return cmd_dumpbig(argc, argv);
 		if (cmd == "mlpdump") return cmd_mlpdump(argc, argv);
+		if (cmd == "snapshot") return cmd_snapshot(argc, argv);
 		if (cmd == "mlpbench") return cmd_mlpbench(argc, argv);
 		if (cmd == "probe") return cmd_probe(argc, argv);
 		fprintf(stderr, "unknown command %s\n", cmd.c_str());

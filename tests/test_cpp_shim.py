@@ -105,3 +105,43 @@ def test_unmodified_reference_sample_trains(torch_cuda, tmp_path):
     losses = [float(m) for m in re.findall(r"Step#\d+: loss=([0-9.eE+-]+)", out.stdout)]
     assert len(losses) >= 3 and losses[-1] < 0.2 * losses[0], out.stdout[-1500:]
     assert os.path.getsize(tmp_path / "learned.jpg") > 1000 and os.path.exists(tmp_path / "reference.jpg")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_optimizer", [0, 1])
+def test_snapshots_interoperate_with_the_reference(torch_cuda, tmp_path, with_optimizer):
+    """trainer->serialize() / deserialize() (trainer.h:442-482, optimizers/adam.h:303-325) exchange the reference's JSON schema: a
+    snapshot written by the UNMODIFIED reference (oracle/_ref/ref_harness, msgpack as instant-ngp stores it) loads into this library
+    and reproduces the reference's inference; a snapshot written by this library loads into the reference and reproduces ours."""
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    exe = os.path.join(ROOT, "tests", "cpp", "snapshot_interop")
+    if not (os.path.exists(harness) and os.path.exists(exe)):
+        pytest.skip("oracle/_ref/ref_harness or tests/cpp/snapshot_interop has not been built")
+    cfg = os.path.join(ROOT, "tests", "golden", "configs", "hash3d_small.json")
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "tiny-cuda-nn_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    d = str(tmp_path)
+    B = 1024
+
+    def run(cmd):
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+        return json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+
+    # reference -> this library
+    saved = run([harness, "snapshot", "save", cfg, "3", "3", str(B), "20", d, str(with_optimizer)])
+    loaded = run([exe, "load", cfg, "3", "3", str(B), d, os.path.join(d, "snapshot.msgpack")])
+    ref = np.fromfile(os.path.join(d, "inference.f32"), np.float32)
+    ours = np.fromfile(os.path.join(d, "inference_loaded.f32"), np.float32)
+    from golden_util import rae
+
+    assert rae(ours, ref, 99.0) < 1e-2  # same parameters, the two forward kernels (tests/test_common.h:177)
+    assert loaded["has_optimizer"] == bool(with_optimizer)
+    # the step after loading continues the reference's trajectory (with its optimizer state: moments + per-parameter step counters)
+    assert loaded["next_step_loss"] < 1.5 * saved["last_loss"] + 1e-6
+    # this library -> reference
+    run([exe, "save", cfg, "3", "3", str(B), d, "20", str(with_optimizer)])
+    back = run([harness, "snapshot", "load", cfg, "3", "3", str(B), d, os.path.join(d, "snapshot_b200.msgpack")])
+    ours2 = np.fromfile(os.path.join(d, "inference_b200.f32"), np.float32)
+    ref2 = np.fromfile(os.path.join(d, "inference_loaded.f32"), np.float32)
+    assert rae(ours2, ref2, 99.0) < 1e-2
+    assert np.isfinite(back["next_step_loss"])

@@ -824,6 +824,14 @@ static std::string make_hyperparams(const Model& m) {
 
 }  // namespace tcnnb
 
+namespace tcnnb {
+__global__ void half_to_float_kernel(uint64_t n, const __half* __restrict__ in, float* __restrict__ out) {
+	const uint64_t i = threadIdx.x + (uint64_t)blockIdx.x * blockDim.x;
+	if (i < n) out[i] = (float)in[i];
+}
+}  // namespace tcnnb
+
+
 // ==================================================================================================================
 // C ABI
 // ==================================================================================================================
@@ -930,6 +938,43 @@ int tcnnb_set_params_full_precision(tcnnb_model* m, const float* params, uint64_
 	TCNNB_CUDA_CHECK(launch_cast_params(nullptr, mm.n_params, mm.params_fp32, mm.params_fp16));
 	++g_kernel_launches;
 	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
+	TCNNB_API_END
+}
+
+int tcnnb_set_params(tcnnb_model* m, const void* params_half, uint64_t n, int device_ptr) {
+	TCNNB_API_BEGIN
+	Model& mm = m->impl;
+	if (mm.module_only) throw std::runtime_error("this handle was created with tcnnb_module_create: it owns no parameters.");
+	if (n != mm.n_params) throw std::runtime_error("Can't set params because buffer has the wrong size.");  // trainer.h:424-426
+	// set_params (trainer.h:423-440): the working-precision parameters are authoritative, fp32 master = (float)fp16
+	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
+	TCNNB_CUDA_CHECK(cudaMemcpy(mm.params_fp16, params_half, n * sizeof(__half), device_ptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+	half_to_float_kernel<<<(uint32_t)((n + 255) / 256), 256>>>(n, mm.params_fp16, mm.params_fp32);
+	++g_kernel_launches;
+	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
+	TCNNB_API_END
+}
+
+int tcnnb_optimizer_state(tcnnb_model* m, float** first_moments_dev, float** second_moments_dev, uint32_t** param_steps_dev, uint32_t* current_step, float* base_learning_rate) {
+	TCNNB_API_BEGIN
+	Model& mm = m->impl;
+	if (mm.module_only) throw std::runtime_error("this handle was created with tcnnb_module_create: it has no optimizer.");
+	if (mm.dp && mm.dp->world > 1 && mm.dp->shard_optimizer) {
+		throw std::runtime_error("optimizer state is sharded over the data-parallel ranks: each rank holds the moments of its own slice only");
+	}
+	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
+	if (first_moments_dev) *first_moments_dev = mm.first_moments.ptr;
+	if (second_moments_dev) *second_moments_dev = mm.second_moments.ptr;
+	if (param_steps_dev) *param_steps_dev = mm.param_steps.ptr;
+	if (current_step) *current_step = mm.adam_step_count;
+	if (base_learning_rate) *base_learning_rate = mm.adam.learning_rate;
+	TCNNB_API_END
+}
+
+int tcnnb_set_optimizer_progress(tcnnb_model* m, uint32_t current_step, float base_learning_rate) {
+	TCNNB_API_BEGIN
+	m->impl.adam_step_count = current_step;
+	m->impl.adam.learning_rate = base_learning_rate;
 	TCNNB_API_END
 }
 
@@ -1052,13 +1097,6 @@ int tcnnb_serialize(tcnnb_model* m, void* dst_host, uint64_t size, int with_opti
 	}
 	TCNNB_API_END
 }
-
-namespace tcnnb {
-__global__ void half_to_float_kernel(uint64_t n, const __half* __restrict__ in, float* __restrict__ out) {
-	const uint64_t i = threadIdx.x + (uint64_t)blockIdx.x * blockDim.x;
-	if (i < n) out[i] = (float)in[i];
-}
-}  // namespace tcnnb
 
 int tcnnb_deserialize(tcnnb_model* m, const void* src_host, uint64_t size) {
 	TCNNB_API_BEGIN

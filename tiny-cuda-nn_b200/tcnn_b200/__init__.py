@@ -56,6 +56,9 @@ ABI = [
     ("tcnnb_grid_levels", _int, [_vp, ctypes.POINTER(_u32), ctypes.POINTER(_u32), _f32p, ctypes.POINTER(_u32)]),
     ("tcnnb_hyperparams", ctypes.c_char_p, [_vp]),
     ("tcnnb_set_params_full_precision", _int, [_vp, _vp, _u64, _int]),
+    ("tcnnb_set_params", _int, [_vp, _vp, _u64, _int]),
+    ("tcnnb_optimizer_state", _int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_u32), _f32p]),
+    ("tcnnb_set_optimizer_progress", _int, [_vp, _u32, ctypes.c_float]),
     ("tcnnb_training_step", _int, [_vp, _vp, _u32, _vp, _vp, _int]),
     ("tcnnb_training_step_shard", _int, [_vp, _vp, _u32, _u32, _vp, _vp, _int]),
     ("tcnnb_optimizer_step", _int, [_vp, _vp]),
