@@ -168,8 +168,6 @@ int tcnnb_network_module_inference(tcnnb_network* n, tcnnb_stream stream, uint32
 /* Profiling only (scripts/mlp_timeline.py): clock64 phase stamps of the following launches are written to
  * int64 [n_ctas][5 roles][64 events][8 fields] at clocks_dev (null = off). Not part of the drop-in surface. */
 int tcnnb_network_debug_clocks(tcnnb_network* n, void* clocks_dev);
-/* Profiling only: select a compile-time variant of the kernel for A/B timing (bit 0: operand hand-off in halves, bit 1: I/O path). */
-int tcnnb_network_debug_flags(tcnnb_network* n, uint32_t flags);
 
 /* ---- data parallelism, natively over NCCL (no counterpart in the single-GPU reference) -------------
  * One process per GPU. Rendezvous is the host framework's job (torch.distributed in tcnn_b200/dp.py): rank 0 draws two NCCL

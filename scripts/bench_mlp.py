@@ -33,7 +33,6 @@ def main():
     ap.add_argument("--batches", default="16384,262144,4194304")
     ap.add_argument("--iters", type=int, default=0)
     ap.add_argument("--reference", action="store_true")
-    ap.add_argument("--variants", action="store_true", help="A/B the kernel's compile-time variants (tcnnb_network_debug_flags 0..3)")
     args = ap.parse_args()
     import torch
 
@@ -45,8 +44,7 @@ def main():
         for hidden in [int(v) for v in args.hidden.split(",")]:
             net = tcnn_b200.Network(width, width, {"otype": "FullyFusedMLP", "n_neurons": width, "n_hidden_layers": hidden, "activation": "ReLU", "output_activation": "None"})
             p16 = net.initial_params(1337).to(torch.float16).contiguous()
-            for B, flags in [(int(v), f) for v in args.batches.split(",") for f in (range(4) if args.variants else [0])]:
-                tcnn_b200._check(tcnn_b200.load().tcnnb_network_debug_flags(net._h, flags))
+            for B in [int(v) for v in args.batches.split(",")]:
                 x = torch.rand(B, width, device="cuda").to(torch.float16).contiguous()
                 iters = args.iters or max(20, min(2000, (1 << 27) // B))
                 for _ in range(max(3, iters // 10)):
@@ -61,7 +59,7 @@ def main():
                 ms = e0.elapsed_time(e1) / iters
                 flops = 2.0 * (width * width * (hidden + 1)) * B
                 byts = 2.0 * (width + width) * B
-                line = {"impl": "tcnn_b200", "mode": "mlp_inference", "variant_flags": flags, "width": width, "n_hidden_layers": hidden, "batch": B, "iters": iters, "ms_per_batch": ms,
+                line = {"impl": "tcnn_b200", "mode": "mlp_inference", "width": width, "n_hidden_layers": hidden, "batch": B, "iters": iters, "ms_per_batch": ms,
                         "samples_per_s": B / (ms * 1e-3), "tflops": flops / (ms * 1e-3) / 1e12, "gbs": byts / (ms * 1e-3) / 1e9,
                         "tensor_frac": flops / (ms * 1e-3) / 1e12 / tensor, "hbm_frac": byts / (ms * 1e-3) / 1e9 / hbm, "peaks": kind}
                 if args.reference and os.path.exists(harness):

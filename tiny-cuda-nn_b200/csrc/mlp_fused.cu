@@ -43,23 +43,23 @@ using namespace fused;
 namespace {
 
 constexpr uint32_t MLPF_MAX_STAGES = 32;
-constexpr bool MLPF_DEFAULT_SPLIT = false;  // measured: see profiles/r02_mlp_variants.md
-constexpr bool MLPF_DEFAULT_COAL = true;
 
 template <uint32_t W>
 struct MlpCfg {
-	static constexpr uint32_t SLOTS = W == 128 ? 2 : 4;
-	static constexpr uint32_t EPI_WARPS = 4 * SLOTS;
-	static constexpr uint32_t THREADS = (EPI_WARPS + 2) * 32;
+	static constexpr uint32_t SLOTS = W == 128 ? 2 : 4;        // 128-sample tiles in flight per CTA
+	static constexpr uint32_t GROUPS = W == 128 ? 2 : 1;       // epilogue warp groups (4 warps) per slot: each owns W / GROUPS columns of every row
+	static constexpr uint32_t SLOT_WARPS = 4 * GROUPS;
+	static constexpr uint32_t EPI_WARPS = SLOTS * SLOT_WARPS;  // 16
+	static constexpr uint32_t THREADS = (EPI_WARPS + 2) * 32;  // 576
 	static constexpr uint32_t REGION = W < 32 ? 32 : W;        // TMEM columns of one accumulator region
 	static constexpr uint32_t TMEM_COLS = SLOTS * 2 * REGION;  // 512 / 512 / 256 / 256
 	static constexpr uint32_t KBLOCKS = (W + 63) / 64;         // 64-element K blocks of a weight stage
 	static constexpr uint32_t KBLOCK_BYTES = W * 128;          // [W rows][64 fp16], SWIZZLE_128B
 	static constexpr uint32_t STAGE_BYTES = KBLOCKS * KBLOCK_BYTES < 2048 ? 2048 : KBLOCKS * KBLOCK_BYTES;
-	static constexpr uint32_t CHUNK = W == 128 ? 64 : (W < 32 ? W : 32);  // accumulator columns per tcgen05.ld (register budget: 576 threads below 128 wide)
+	static constexpr uint32_t GROUP_COLS = W / GROUPS;         // accumulator columns a thread converts per hidden layer (<= 64)
+	static constexpr uint32_t PIECE = GROUP_COLS < 32 ? GROUP_COLS : 32;  // ... in pieces of one tcgen05.ld
+	static constexpr uint32_t N_PIECES = GROUP_COLS / PIECE;
 	static constexpr uint32_t MAX_IN = 64 * KBLOCKS;           // widest first-layer input a stage holds
-	static constexpr uint32_t NHALF = W / CHUNK;               // hand-off granularity: a layer's operand becomes ready in NHALF pieces (1 or 2)
-	static constexpr uint32_t KSTEPS_PER_HALF = CHUNK / 16;
 };
 
 struct MlpKernelParams {
@@ -118,15 +118,12 @@ __device__ __forceinline__ void transpose8x8_u128(uint4 (&a)[8], uint32_t lane) 
 		if (p.dbg_clock && (event) < 64u) p.dbg_clock[(((size_t)blockIdx.x * 5u + (role)) * 64u + (event)) * 8u + (field)] = clock64(); \
 	} while (0)
 
-// SPLIT: hand the next layer's operand over in two halves (first k-steps overlap the second half of the epilogue).
-// COAL:  move network input / output rows through the 8-lane transpose (coalesced 128-byte row pieces) instead of row-per-thread.
-// Both are compile-time variants so that scripts/bench_mlp.py --variants can A/B them on the device (tcnnb_network_debug_flags).
-template <uint32_t W, bool GENERIC_ACT, bool SPLIT, bool COAL>
-__global__ void __launch_bounds__(MlpCfg<W>::THREADS, 1)
+// 576 threads per CTA: 65536 / 576 = 113 registers per thread; ptxas' own choice under __launch_bounds__ is 96 and spills the
+// accumulator pieces, so the budget is stated explicitly.
+template <uint32_t W, bool GENERIC_ACT>
+__global__ void __maxnreg__(112)
 mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wo) {
 	using C = MlpCfg<W>;
-	constexpr uint32_t NCHUNK = W / C::CHUNK;          // accumulator chunks per hidden-layer epilogue
-	constexpr uint32_t NHALF = SPLIT ? NCHUNK : 1;     // operand hand-offs per layer
 	const MlpForwardParams& p = kp.p;
 	const uint32_t hid_act = GENERIC_ACT ? p.activation : (uint32_t)ACT_RELU;
 	const uint32_t out_act = GENERIC_ACT ? p.output_activation : (uint32_t)ACT_NONE;
@@ -145,8 +142,8 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 	const uint32_t s_bars = s_stage0 + n_stages * C::STAGE_BYTES;
 	const uint32_t bar_w_full = s_bars;                               // [MLPF_MAX_STAGES]
 	const uint32_t bar_w_free = bar_w_full + 8 * MLPF_MAX_STAGES;     // [MLPF_MAX_STAGES]
-	const uint32_t bar_a_ready = bar_w_free + 8 * MLPF_MAX_STAGES;    // [4 slots][2 halves]
-	const uint32_t bar_acc_ready = bar_a_ready + 8 * 8;               // [4]
+	const uint32_t bar_a_ready = bar_w_free + 8 * MLPF_MAX_STAGES;    // [4]
+	const uint32_t bar_acc_ready = bar_a_ready + 8 * 4;               // [4]
 	const uint32_t s_tmem_slot = bar_acc_ready + 8 * 4;
 
 	if (tid == 0) {
@@ -155,8 +152,7 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 			mbar_init(bar_w_free + 8 * i, C::SLOTS);
 		}
 		for (uint32_t s = 0; s < C::SLOTS; ++s) {
-			mbar_init(bar_a_ready + 8 * (2 * s), 4);
-			mbar_init(bar_a_ready + 8 * (2 * s + 1), 4);
+			mbar_init(bar_a_ready + 8 * s, C::SLOT_WARPS);
 			mbar_init(bar_acc_ready + 8 * s, 1);
 		}
 		fence_mbar_init();
@@ -210,36 +206,32 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 		// =============================================================================== MMA issuer
 		// Per slot: which layer comes next. A slot whose tiles have run out keeps walking the layers of the remaining rounds as a
 		// "virtual" consumer in ring mode: it only releases the weight stages (w_free expects SLOTS arrivals per use).
-		uint32_t layer[C::SLOTS], half[C::SLOTS], round[C::SLOTS], a_par[C::SLOTS], n_real[C::SLOTS];
+		uint32_t layer[C::SLOTS], round[C::SLOTS], a_par[C::SLOTS], n_real[C::SLOTS];
 		uint32_t remaining = 0;
 #pragma unroll
 		for (uint32_t s = 0; s < C::SLOTS; ++s) {
-			layer[s] = half[s] = round[s] = a_par[s] = 0;
+			layer[s] = round[s] = a_par[s] = 0;
 			n_real[s] = n_my > s ? (n_my - s + C::SLOTS - 1) / C::SLOTS : 0;
-			remaining += (resident ? n_real[s] : n_rounds) * n_layers * NHALF;
+			remaining += (resident ? n_real[s] : n_rounds) * n_layers;
 		}
 		const uint32_t idesc_hidden = umma_idesc_f16(128, W, 0, 0);
 		const uint32_t idesc_out = umma_idesc_f16(128, out_w, 0, 0);
-		// One unit of work = the k-steps of one HALF of a layer's operand: the epilogue warps hand the next layer's A operand over
-		// in NHALF pieces (a_ready[s][h], a_par bit h), so the first k-steps of layer l+1 run while the second half of layer l's
-		// accumulator is still being converted. The accumulator is committed after the last half.
 		while (remaining) {
 #pragma unroll
 			for (uint32_t s = 0; s < C::SLOTS; ++s) {
 				const uint32_t n_rounds_s = resident ? n_real[s] : n_rounds;
 				if (round[s] >= n_rounds_s) continue;
 				const bool real = round[s] < n_real[s];
-				const uint32_t l = layer[s], h = half[s];
+				const uint32_t l = layer[s];
 				const uint32_t g = round[s] * n_layers + l;
 				const uint32_t stage = resident ? l : g % n_stages;
 				const uint32_t w_par = resident ? 0u : (g / n_stages) & 1u;
 				// warp-uniform decisions (every lane tests; the vote makes the result one value)
-				if (real && !__all_sync(0xFFFFFFFFu, mbar_test(bar_a_ready + 8 * (2 * s + h), (a_par[s] >> h) & 1u))) continue;
-				if (h == 0 && !__all_sync(0xFFFFFFFFu, mbar_test(bar_w_full + 8 * stage, w_par))) continue;
-				const bool last_half = h == NHALF - 1;
+				if (real && !__all_sync(0xFFFFFFFFu, mbar_test(bar_a_ready + 8 * s, a_par[s]))) continue;
+				if (!__all_sync(0xFFFFFFFFu, mbar_test(bar_w_full + 8 * stage, w_par))) continue;
 				if (real) {
 					const uint32_t ev = round[s] * n_layers + l;
-					if (lane == 0 && h == 0) MLPF_STAMP(0, ev * C::SLOTS + s, 0);
+					if (lane == 0) MLPF_STAMP(0, ev * C::SLOTS + s, 0);
 					tc_fence_after_sync();
 					if (elect_one_sync()) {
 						const uint32_t slot_base = tmem_base + s * 2 * C::REGION;
@@ -247,85 +239,73 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 						const uint32_t a_tmem = slot_base + ((l + 1u) & 1u) * C::REGION;  // first half of the other region
 						const uint32_t b_smem = s_stage0 + stage * C::STAGE_BYTES;
 						const uint32_t ksteps = (l == 0 ? in_w : W) / 16;
-						const uint32_t j0 = SPLIT ? h * C::KSTEPS_PER_HALF : 0u;
-						const uint32_t j1 = last_half ? ksteps : (j0 + C::KSTEPS_PER_HALF < ksteps ? j0 + C::KSTEPS_PER_HALF : ksteps);
 						const uint32_t idesc = l == NH ? idesc_out : idesc_hidden;
-						for (uint32_t j = j0; j < j1; ++j) {
+						for (uint32_t j = 0; j < ksteps; ++j) {
 							const uint64_t b_desc = umma_desc_sw128(b_smem + (j >> 2) * C::KBLOCK_BYTES + (j & 3u) * 32u, 16u, 1024u);
 							umma_f16_ts(d_tmem, a_tmem + j * 8u, b_desc, idesc, j > 0);
 						}
-						if (last_half) {
-							umma_commit(bar_acc_ready + 8 * s);
-							if (!resident) umma_commit(bar_w_free + 8 * stage);
-						}
+						umma_commit(bar_acc_ready + 8 * s);
+						if (!resident) umma_commit(bar_w_free + 8 * stage);
 					}
 					__syncwarp();
-					if (lane == 0) MLPF_STAMP(0, ev * C::SLOTS + s, 1 + h);
-					a_par[s] ^= 1u << h;
-				} else if (last_half && lane == 0) {
+					if (lane == 0) MLPF_STAMP(0, ev * C::SLOTS + s, 1);
+					a_par[s] ^= 1u;
+				} else if (lane == 0) {
 					mbar_arrive_plain(bar_w_free + 8 * stage);
 				}
-				if (++half[s] == NHALF) {
-					half[s] = 0;
-					if (++layer[s] == n_layers) {
-						layer[s] = 0;
-						++round[s];
-					}
+				if (++layer[s] == n_layers) {
+					layer[s] = 0;
+					++round[s];
 				}
 				--remaining;
 			}
 		}
 	} else {
 		// =============================================================================== epilogue / load / store warps of one slot
-		const uint32_t s = warp >> 2, wq = warp & 3u;
+		// SLOT_WARPS warps per slot: warp (grp, wq) owns TMEM lanes 32 wq .. 32 wq + 31 (thread <-> tile row) and the columns
+		// [grp * GROUP_COLS, (grp + 1) * GROUP_COLS) of every accumulator / input / output row of the tile.
+		const uint32_t s = warp / C::SLOT_WARPS, grp = (warp / 4) % C::GROUPS, wq = warp & 3u;
 		const uint32_t row = wq * 32 + lane;
 		const uint32_t lane_field = (wq * 32u) << 16;
 		const uint32_t slot_base = tmem_base + s * 2 * C::REGION + lane_field;
+		const uint32_t col0 = grp * C::GROUP_COLS;  // first accumulator column of this thread
+		const uint32_t g8 = lane >> 3, l8 = lane & 7u;
+		const bool stamp = grp == 0 && wq == 0 && lane == 0;
 		uint32_t acc_par = 0;
 
-		// ---- network input. A thread owns one row (sample) of the tile; per 64-column block the 8 lanes of a group fetch 8 consecutive
-		// 16-byte pieces of one row for 8 rows in turn (coalesced), and transpose8x8_u128 hands every lane its own row. `pre` holds
-		// the pieces as fetched; the transpose happens when the row is consumed, one tile later, so that the loads stay in flight.
-		constexpr uint32_t IN_BLOCKS = C::MAX_IN / 64;
-		const uint32_t g8 = lane >> 3, l8 = lane & 7u;
-		uint4 pre[IN_BLOCKS][8];
+		// ---- network input: one 64-column block per warp group. The 8 lanes of a lane group fetch 8 consecutive 16-byte pieces of
+		// ONE row (128 contiguous bytes) for 8 rows in turn; transpose8x8_u128 hands every lane its own row when the tile starts
+		// (one tile later, so that the loads stay in flight across the last layer).
+		const bool has_in_block = col0 < in_w;
+		uint4 pre[8];
 		auto load_input = [&](uint32_t tile) {
+			if (!has_in_block) return;
 			const size_t tile_row0 = (size_t)tile * TILE_M + wq * 32;
 			if (p.input_fp16) {
+				const uint32_t col = col0 + l8 * 8;
 #pragma unroll
-				for (uint32_t b = 0; b < IN_BLOCKS; ++b) {
-					if (b * 64 < in_w) {
-#pragma unroll
-						for (uint32_t jj = 0; jj < 8; ++jj) {
-							// COAL: piece l8 of row (g8 * 8 + jj); else piece jj of this thread's own row
-							const uint32_t col = b * 64 + (COAL ? l8 : jj) * 8;
-							const size_t r = tile_row0 + (COAL ? g8 * 8 + jj : lane);
-							pre[b][jj] = col < in_w ? __ldg(reinterpret_cast<const uint4*>(p.input_fp16 + r * in_w + col)) : make_uint4(0, 0, 0, 0);
-						}
-					}
+				for (uint32_t jj = 0; jj < 8; ++jj) {
+					pre[jj] = col < in_w ? __ldg(reinterpret_cast<const uint4*>(p.input_fp16 + (tile_row0 + g8 * 8 + jj) * in_w + col)) : make_uint4(0, 0, 0, 0);
 				}
 			} else {
 				// Identity encoding (identity.h:46-67): the first n_input_dims features are the inputs, the padding features are ONE.
 				// A handful of floats per sample: fetched by the owning thread directly, already in row order (no transpose below).
 				const float* src = p.input_fp32 + (tile_row0 + lane) * p.n_input_dims;
 #pragma unroll
-				for (uint32_t b = 0; b < IN_BLOCKS; ++b) {
+				for (uint32_t jj = 0; jj < 8; ++jj) {
+					uint32_t w4[4];
 #pragma unroll
-					for (uint32_t jj = 0; jj < 8; ++jj) {
-						uint32_t w4[4];
-#pragma unroll
-						for (uint32_t i = 0; i < 4; ++i) {
-							const uint32_t c = b * 64 + jj * 8 + i * 2;
-							if (c < in_w) {
-								const float lo = c < p.n_input_dims ? __ldg(src + c) : 1.0f;
-								const float hi = c + 1 < p.n_input_dims ? __ldg(src + c + 1) : 1.0f;
-								w4[i] = pack_half2(lo, hi);
-							} else {
-								w4[i] = 0;
-							}
+					for (uint32_t i = 0; i < 4; ++i) {
+						const uint32_t c = col0 + jj * 8 + i * 2;
+						if (c < in_w) {
+							const float lo = c < p.n_input_dims ? __ldg(src + c) : 1.0f;
+							const float hi = c + 1 < p.n_input_dims ? __ldg(src + c + 1) : 1.0f;
+							w4[i] = pack_half2(lo, hi);
+						} else {
+							w4[i] = 0;
 						}
-						pre[b][jj] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
 					}
+					pre[jj] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
 				}
 			}
 		};
@@ -335,35 +315,28 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 		for (; j < n_my; j += C::SLOTS) {
 			const uint32_t tile = blockIdx.x + j * gridDim.x;
 			const size_t sample = (size_t)tile * TILE_M + row;
+			const size_t tile_row0 = (size_t)tile * TILE_M + wq * 32;
 			// ---- input row -> tensor memory: A operand of layer 0 lives in the first half of region 1
-			{
-				const uint32_t a0 = slot_base + C::REGION;
+			if (has_in_block) {
+				const uint32_t a0 = slot_base + C::REGION + col0 / 2;
+				if (p.input_fp16) transpose8x8_u128(pre, lane);
 #pragma unroll
-				for (uint32_t b = 0; b < IN_BLOCKS; ++b) {
-					if (b * 64 < in_w) {
-						if (COAL && p.input_fp16) transpose8x8_u128(pre[b], lane);
-#pragma unroll
-						for (uint32_t q = 0; q < 4; ++q) {  // 16 columns of fp16 = 8 TMEM columns per store
-							if (b * 64 + q * 16 < in_w) {
-								const uint32_t v[8] = {pre[b][2 * q].x, pre[b][2 * q].y, pre[b][2 * q].z, pre[b][2 * q].w, pre[b][2 * q + 1].x, pre[b][2 * q + 1].y, pre[b][2 * q + 1].z, pre[b][2 * q + 1].w};
-								tmem_st_n<8>(a0 + b * 32 + q * 8, v);
-							}
-						}
+				for (uint32_t q = 0; q < 4; ++q) {  // 16 columns of fp16 = 8 TMEM columns per store
+					if (col0 + q * 16 < in_w) {
+						const uint32_t v[8] = {pre[2 * q].x, pre[2 * q].y, pre[2 * q].z, pre[2 * q].w, pre[2 * q + 1].x, pre[2 * q + 1].y, pre[2 * q + 1].z, pre[2 * q + 1].w};
+						tmem_st_n<8>(a0 + q * 8, v);
 					}
 				}
 				tmem_st_wait();
-				tc_fence_before_sync();
-				__syncwarp();
-				if (lane == 0) {
-					mbar_arrive_plain(bar_a_ready + 8 * (2 * s));
-					if (NHALF == 2) mbar_arrive_plain(bar_a_ready + 8 * (2 * s + 1));
-				}
 			}
+			tc_fence_before_sync();
+			__syncwarp();
+			if (lane == 0) mbar_arrive_plain(bar_a_ready + 8 * s);
+
 			for (uint32_t l = 0; l <= NH; ++l) {
 				// the next tile's input travels while the last layer computes
 				if (l == NH && j + C::SLOTS < n_my) load_input(blockIdx.x + (j + C::SLOTS) * gridDim.x);
 				const uint32_t ev = (j / C::SLOTS) * n_layers + l;
-				const bool stamp = wq == 0 && lane == 0;
 				if (stamp) MLPF_STAMP(1 + s, ev, 0);
 				mbar_wait(bar_acc_ready + 8 * s, acc_par);
 				acc_par ^= 1u;
@@ -371,89 +344,77 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 				if (stamp) MLPF_STAMP(1 + s, ev, 1);
 				const uint32_t acc = slot_base + (l & 1u) * C::REGION;
 				if (l < NH) {
-					// hidden layer: fp32 accumulator row -> activation in fp16 -> packed, IN PLACE into the first half of this region
-					// (chunk c reads columns [c*CHUNK, (c+1)*CHUNK) and writes [c*CHUNK/2, (c+1)*CHUNK/2): always columns already read).
-					// Each chunk is handed to the MMA issuer as soon as it is stored: the next layer's first k-steps overlap chunk 1.
+					// hidden layer: fp32 accumulator row -> activation in fp16 -> packed pairs, IN PLACE into the first half of this
+					// region, which the next layer's MMA reads as its A operand. Columns [c, c + n) are written to [c / 2, (c + n) / 2):
+					// a group's writes land in columns it has read itself or -- with two groups -- in columns the OTHER group reads,
+					// hence: every thread loads all of its columns first, then the slot's groups meet at a named barrier, then store.
+					uint32_t r[C::N_PIECES][C::PIECE];
 #pragma unroll
-					for (uint32_t c = 0; c < NCHUNK; ++c) {
-						uint32_t r[C::CHUNK];
-						tmem_ld_n<C::CHUNK>(acc + c * C::CHUNK, r);
-						tmem_ld_wait();
-						if (stamp) MLPF_STAMP(1 + s, ev, 2 + 3 * c);
-						uint32_t h[C::CHUNK / 2];
+					for (uint32_t k = 0; k < C::N_PIECES; ++k) tmem_ld_n<C::PIECE>(acc + col0 + k * C::PIECE, r[k]);
+					tmem_ld_wait();
+					if (stamp) MLPF_STAMP(1 + s, ev, 2);
+					if (C::GROUPS > 1) asm volatile("bar.sync %0, %1;" ::"r"(1u + s), "r"(C::SLOT_WARPS * 32u) : "memory");
 #pragma unroll
-						for (uint32_t i = 0; i < C::CHUNK / 2; ++i) h[i] = act_pack(hid_act, r[2 * i], r[2 * i + 1]);
-						tmem_st_n<C::CHUNK / 2>(acc + c * (C::CHUNK / 2), h);
-						if (stamp) MLPF_STAMP(1 + s, ev, 3 + 3 * c);
+					for (uint32_t k = 0; k < C::N_PIECES; ++k) {
+						uint32_t h[C::PIECE / 2];
+#pragma unroll
+						for (uint32_t i = 0; i < C::PIECE / 2; ++i) h[i] = act_pack(hid_act, r[k][2 * i], r[k][2 * i + 1]);
+						tmem_st_n<C::PIECE / 2>(acc + (col0 + k * C::PIECE) / 2, h);
 						if (p.hidden_out) {
-							uint4* dst = reinterpret_cast<uint4*>(p.hidden_out + ((size_t)l * p.batch_size + sample) * W + c * C::CHUNK);
+							uint4* dst = reinterpret_cast<uint4*>(p.hidden_out + ((size_t)l * p.batch_size + sample) * W + col0 + k * C::PIECE);
 #pragma unroll
-							for (uint32_t i = 0; i < C::CHUNK / 8; ++i) dst[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+							for (uint32_t i = 0; i < C::PIECE / 8; ++i) dst[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
 						}
-						if (SPLIT || c == NCHUNK - 1) {
-							tmem_st_wait();
-							tc_fence_before_sync();
-							__syncwarp();
-							if (lane == 0) mbar_arrive_plain(bar_a_ready + 8 * (2 * s + (SPLIT ? c : 0u)));
-						}
-						if (stamp) MLPF_STAMP(1 + s, ev, 4 + 3 * c);
 					}
+					if (stamp) MLPF_STAMP(1 + s, ev, 3);
+					tmem_st_wait();
+					tc_fence_before_sync();
+					__syncwarp();
+					if (lane == 0) mbar_arrive_plain(bar_a_ready + 8 * s);
+					if (stamp) MLPF_STAMP(1 + s, ev, 4);
 				} else {
-					// output layer: activation, then fp16 rows (and / or trimmed fp32 rows) to global memory. Full 64-column blocks go
-					// out coalesced (transpose, then 8 lanes write 128 contiguous bytes of one row); narrower tails row by row.
-					const size_t tile_row0 = (size_t)tile * TILE_M + wq * 32;
-					uint32_t c16 = 0;  // next 16-column group
-					if (W >= 64) {
-						for (; (c16 + 4) * 16 <= out_w; c16 += 4) {
-							uint4 o[8];
-#pragma unroll
-							for (uint32_t q = 0; q < 4; ++q) {
-								uint32_t r[16];
-								tmem_ld_n<16>(acc + (c16 + q) * 16, r);
-								tmem_ld_wait();
-								uint32_t y[8];
-#pragma unroll
-								for (uint32_t i = 0; i < 8; ++i) {
-									const __half2 v = __halves2half2(act_fwd_h(out_act, __float2half_rn(__uint_as_float(r[2 * i]))), act_fwd_h(out_act, __float2half_rn(__uint_as_float(r[2 * i + 1]))));
-									y[i] = *reinterpret_cast<const uint32_t*>(&v);
-								}
-								o[2 * q] = make_uint4(y[0], y[1], y[2], y[3]);
-								o[2 * q + 1] = make_uint4(y[4], y[5], y[6], y[7]);
-								if (p.output_fp32) {
-#pragma unroll
-									for (uint32_t i = 0; i < 16; ++i) {
-										const uint32_t col = (c16 + q) * 16 + i;
-										if (col < p.n_output_dims) p.output_fp32[sample * p.n_output_dims + col] = __half2float(reinterpret_cast<const __half*>(y)[i]);
-									}
-								}
-							}
-							if (p.output_fp16) {
-								if (COAL) transpose8x8_u128(o, lane);
-#pragma unroll
-								for (uint32_t jj = 0; jj < 8; ++jj) {
-									const size_t r = tile_row0 + (COAL ? g8 * 8 + jj : lane);
-									*reinterpret_cast<uint4*>(p.output_fp16 + r * out_w + c16 * 16 + (COAL ? l8 : jj) * 8) = o[jj];
-								}
-							}
-						}
-					}
-					for (; c16 * 16 < out_w; ++c16) {
+					// output layer: activation, then fp16 rows (and / or trimmed fp32 rows) to global memory. A full 64-column block
+					// goes out coalesced (transpose, then 8 lanes write 128 contiguous bytes of one row); a narrower tail row by row.
+					auto convert16 = [&](uint32_t c16, uint4& lo, uint4& hi) {
 						uint32_t r[16];
 						tmem_ld_n<16>(acc + c16 * 16, r);
 						tmem_ld_wait();
-						__half y[16];
+						uint32_t y[8];
 #pragma unroll
-						for (uint32_t i = 0; i < 16; ++i) y[i] = act_fwd_h(out_act, __float2half_rn(__uint_as_float(r[i])));
-						if (p.output_fp16) {
-							uint4* dst = reinterpret_cast<uint4*>(p.output_fp16 + sample * out_w + c16 * 16);
-							dst[0] = *reinterpret_cast<uint4*>(&y[0]);
-							dst[1] = *reinterpret_cast<uint4*>(&y[8]);
+						for (uint32_t i = 0; i < 8; ++i) {
+							const __half2 v = __halves2half2(act_fwd_h(out_act, __float2half_rn(__uint_as_float(r[2 * i]))), act_fwd_h(out_act, __float2half_rn(__uint_as_float(r[2 * i + 1]))));
+							y[i] = *reinterpret_cast<const uint32_t*>(&v);
 						}
+						lo = make_uint4(y[0], y[1], y[2], y[3]);
+						hi = make_uint4(y[4], y[5], y[6], y[7]);
 						if (p.output_fp32) {
 #pragma unroll
 							for (uint32_t i = 0; i < 16; ++i) {
-								if (c16 * 16 + i < p.n_output_dims) p.output_fp32[sample * p.n_output_dims + c16 * 16 + i] = __half2float(y[i]);
+								const uint32_t col = c16 * 16 + i;
+								if (col < p.n_output_dims) p.output_fp32[sample * p.n_output_dims + col] = __half2float(reinterpret_cast<const __half*>(y)[i]);
 							}
+						}
+					};
+					const uint32_t c16_begin = col0 / 16, c16_end = (col0 + C::GROUP_COLS) / 16;  // this group's 16-column groups
+					uint32_t c16 = c16_begin;
+					if (C::GROUP_COLS == 64 && (c16 + 4) * 16 <= out_w) {
+						uint4 o[8];
+#pragma unroll
+						for (uint32_t q = 0; q < 4; ++q) convert16(c16 + q, o[2 * q], o[2 * q + 1]);
+						if (p.output_fp16) {
+							transpose8x8_u128(o, lane);
+#pragma unroll
+							for (uint32_t jj = 0; jj < 8; ++jj) *reinterpret_cast<uint4*>(p.output_fp16 + (tile_row0 + g8 * 8 + jj) * out_w + c16 * 16 + l8 * 8) = o[jj];
+						}
+						c16 += 4;
+					}
+					for (; c16 < c16_end && c16 * 16 < out_w; ++c16) {
+						uint4 lo, hi;
+						convert16(c16, lo, hi);
+						if (p.output_fp16) {
+							uint4* dst = reinterpret_cast<uint4*>(p.output_fp16 + sample * out_w + c16 * 16);
+							dst[0] = lo;
+							dst[1] = hi;
 						}
 					}
 				}
@@ -503,7 +464,7 @@ uint32_t max_stages() {
 	return (uint32_t)((227u * 1024u - 1024u) / MlpCfg<W>::STAGE_BYTES) < MLPF_MAX_STAGES ? (uint32_t)((227u * 1024u - 1024u) / MlpCfg<W>::STAGE_BYTES) : MLPF_MAX_STAGES;
 }
 
-template <uint32_t W, bool GENERIC, bool SPLIT, bool COAL>
+template <uint32_t W, bool GENERIC>
 cudaError_t launch_impl(const MlpForwardParams& p, uint32_t n_sms, cudaStream_t stream) {
 	using C = MlpCfg<W>;
 	const uint32_t n_layers = p.n_hidden_layers + 1;
@@ -522,8 +483,8 @@ cudaError_t launch_impl(const MlpForwardParams& p, uint32_t n_sms, cudaStream_t 
 	}
 	w += (size_t)(p.n_hidden_layers - 1) * W * W;
 	if (!make_weight_map(&mo, w, p.out_width, W, p.out_width)) return cudaErrorInvalidValue;
-	auto kernel = mlp_forward_kernel<W, GENERIC, SPLIT, COAL>;
-	const size_t smem = (size_t)kp.n_stages * C::STAGE_BYTES + 8 * (2 * MLPF_MAX_STAGES + 12) + 16;
+	auto kernel = mlp_forward_kernel<W, GENERIC>;
+	const size_t smem = (size_t)kp.n_stages * C::STAGE_BYTES + 8 * (2 * MLPF_MAX_STAGES + 8) + 16;
 	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (err != cudaSuccess) return err;
 	const uint32_t n_tiles = p.batch_size / TILE_M;
@@ -533,15 +494,7 @@ cudaError_t launch_impl(const MlpForwardParams& p, uint32_t n_sms, cudaStream_t 
 template <uint32_t W>
 cudaError_t launch_width(const MlpForwardParams& p, uint32_t n_sms, cudaStream_t stream) {
 	const bool generic = p.activation != ACT_RELU || p.output_activation != ACT_NONE;
-	constexpr bool SPLIT = MLPF_DEFAULT_SPLIT, COAL = MLPF_DEFAULT_COAL;
-	if (generic) return launch_impl<W, true, SPLIT, COAL>(p, n_sms, stream);
-	// profiling variants (ReLU networks only): bit 0 flips SPLIT, bit 1 flips COAL
-	switch (p.dbg_flags & 3u) {
-		case 1: return launch_impl<W, false, !SPLIT, COAL>(p, n_sms, stream);
-		case 2: return launch_impl<W, false, SPLIT, !COAL>(p, n_sms, stream);
-		case 3: return launch_impl<W, false, !SPLIT, !COAL>(p, n_sms, stream);
-		default: return launch_impl<W, false, SPLIT, COAL>(p, n_sms, stream);
-	}
+	return generic ? launch_impl<W, true>(p, n_sms, stream) : launch_impl<W, false>(p, n_sms, stream);
 }
 
 }  // namespace

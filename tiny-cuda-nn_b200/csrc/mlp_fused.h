@@ -28,7 +28,6 @@ struct MlpForwardParams {
 	__half* hidden_out;
 	// profiling only (scripts/mlp_timeline.py): clock64 stamps [cta][slot + 1 (0 = issuer)][64 events][8], null in production
 	long long* dbg_clock;
-	uint32_t dbg_flags;  // profiling only: kernel variant selection (mlp_fused.cu launch_width)
 };
 
 // Maximum number of weight matrices that stay resident in shared memory for a width (more layers stream through a ring).

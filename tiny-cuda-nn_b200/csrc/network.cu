@@ -28,7 +28,6 @@ struct Network {
 	uint64_t n_params = 0;
 	int n_sms = 148;
 	long long* dbg_clock = nullptr;  // profiling only (tcnnb_network_debug_clocks)
-	uint32_t dbg_flags = 0;
 	std::string otype, hyperparams_json;
 };
 
@@ -91,7 +90,6 @@ static MlpForwardParams make_params(const Network& n, uint32_t batch, const void
 	p.n_input_dims = n.n_input_dims;
 	p.n_output_dims = n.n_output_dims;
 	p.dbg_clock = n.dbg_clock;
-	p.dbg_flags = n.dbg_flags;
 	return p;
 }
 
@@ -132,12 +130,6 @@ uint32_t tcnnb_network_n_hidden_layers(const tcnnb_network* n) { return n->impl.
 int tcnnb_network_debug_clocks(tcnnb_network* n, void* clocks_dev) {
 	TCNNB_API_BEGIN
 	n->impl.dbg_clock = (long long*)clocks_dev;
-	TCNNB_API_END
-}
-
-int tcnnb_network_debug_flags(tcnnb_network* n, uint32_t flags) {
-	TCNNB_API_BEGIN
-	n->impl.dbg_flags = flags;
 	TCNNB_API_END
 }
 

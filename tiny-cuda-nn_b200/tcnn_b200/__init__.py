@@ -90,7 +90,6 @@ ABI = [
     ("tcnnb_network_forward", _int, [_vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     ("tcnnb_network_inference", _int, [_vp, _vp, _u32, _vp, _vp, _vp]),
     ("tcnnb_network_debug_clocks", _int, [_vp, _vp]),
-    ("tcnnb_network_debug_flags", _int, [_vp, _u32]),
     ("tcnnb_network_module_inference", _int, [_vp, _vp, _u32, _vp, _vp, _vp]),
     ("tcnnb_dp_unique_id", _int, [_vp, ctypes.c_uint64]),
     ("tcnnb_dp_init", _int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
