@@ -21,3 +21,5 @@ $H probe 1.3819 16 16 > "$OUT/probe_s1.3819_b16.json"
 # Benchmarked size (T = 2^19; B = 2^16 and 2^18), sub-sampled: <stride over grid parameters> <n_head samples of per-sample arrays>
 $H dumpbig $C/headline.json 3 3 65536 10 "$OUT/big_headline_b16" 0 509 2048
 $H dumpbig $C/headline.json 3 3 262144 10 "$OUT/big_headline_b18" 0 509 2048
+# BASELINE.json configs[0]: CutlassMLP 64 x 2 behind the Identity encoding
+$H dump $C/identity_cutlass.json 3 3 512 10 "$OUT/identity_cutlass" 0

@@ -24,6 +24,8 @@ struct FusedStepParams {
 	uint32_t output_activation;    // applied to the network output before the loss
 	uint32_t n_out;                // logical outputs (<= 16)
 	uint32_t n_mlp_params;         // grid params start here in the parameter / gradient buffers
+	uint32_t enc_identity;         // 1: Identity encoding instead of the grid (features = x * scale + offset, padding features = 1)
+	float identity_scale, identity_offset;
 	uint32_t loss_type;            // LossType
 	float loss_scale;              // 128 for fp16 params (common.h:243)
 	// batch

@@ -263,6 +263,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 					st_shared_v4(enc_tile + sw128(row, chunk), 0, 0, 0, 0);
 				}
 			}
+			if (p.enc_identity) {
+				// Identity encoding (encodings/identity.h:46-67): feature j = (half)(x_j * scale + offset) for j < D, ONE for the padding
+				// features up to the network's input width; this thread writes its half of the row's 16-byte chunks.
+				for (uint32_t c = 0; c < n_chunks / 2; ++c) {
+					const uint32_t chunk = hsel * (n_chunks / 2) + c;
+					__half f[8];
+#pragma unroll
+					for (uint32_t i = 0; i < 8; ++i) {
+						const uint32_t jf = chunk * 8 + i;
+						float v = 1.0f;
+#pragma unroll
+						for (uint32_t d = 0; d < D; ++d) v = jf == d ? __fmaf_rn(x_cur[d], p.identity_scale, p.identity_offset) : v;
+						f[i] = __float2half_rn(v);
+					}
+					const uint4 q = *reinterpret_cast<const uint4*>(f);
+					st_shared_v4(enc_tile + sw128(row, chunk), q.x, q.y, q.z, q.w);
+					if (p.dbg_enc) *reinterpret_cast<uint4*>(p.dbg_enc + (size_t)os_cur * 64 + chunk * 8) = q;
+				}
+			}
 			{
 				// Three levels in flight: the loads of levels l+1 and l+2 are issued before the values of level l are consumed.
 				// What travels with the loads is the fractional position (D floats), not the 2^D weights: they are rebuilt at

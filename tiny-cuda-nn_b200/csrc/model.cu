@@ -144,6 +144,8 @@ struct Model {
 	DeviceBuffer<float> scalars;    // [0] = loss sum
 	DeviceBuffer<long long> dbg_clock;  // TCNNB_CLOCKS=<file> in ablation builds: phase stamps of the last ws launch
 	DeviceBuffer<float> level_scales_dev;
+	bool enc_identity = false;              // "Identity" encoding instead of a grid (no encoding parameters)
+	float identity_scale = 1.0f, identity_offset = 0.0f;
 	DeviceBuffer<LevelInfo> levels_dev;     // per-level descriptors for the stand-alone grid kernels (module tier: dL/d(input))
 	DeviceBuffer<__half> denc_scratch;      // module tier: dL/d(encoded) rows [n][64] handed from the fused kernel to the input-gradient kernel
 	DeviceBuffer<__half> grads_scratch;     // module tier: gradient array when the caller wants dL/d(input) only
@@ -245,9 +247,11 @@ static void init_params(Model& m, HostPcg32& rng, float* dst, float scale) {
 		TCNNB_CUDA_CHECK(cudaMemcpy(dst, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
 	}
 	// grid: U(-1e-4, 1e-4) * scale generated on the device with the jump-ahead pattern (grid.h:1076-1079, random.h:56-69)
-	TCNNB_CUDA_CHECK(launch_random_uniform(nullptr, rng.device(), m.grid.n_params, dst + mlp.n_params, -1e-4f * scale, 1e-4f * scale));
-	++g_kernel_launches;
-	rng.advance(m.grid.n_params);
+	if (m.grid.n_params) {
+		TCNNB_CUDA_CHECK(launch_random_uniform(nullptr, rng.device(), m.grid.n_params, dst + mlp.n_params, -1e-4f * scale, 1e-4f * scale));
+		++g_kernel_launches;
+		rng.advance(m.grid.n_params);
+	}
 }
 
 static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Value& cfg, uint32_t seed, bool module_only = false) {
@@ -318,9 +322,27 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 	}
 	if (mlp.n_hidden_layers < 1) throw std::runtime_error("FullyFusedMLP requires at least 1 hidden layer (3 layers in total).");
 
-	m.grid = parse_grid(n_in, cfg.sub("encoding"));
 	const uint32_t alignment = 16;  // FullyFusedMLP / CutlassMLP REQUIRED_ALIGNMENT (src/network.cu:79-98)
-	m.grid.padded_width = next_multiple(m.grid.n_levels * m.grid.n_features_per_level, alignment);
+	const json::Value& enc_cfg = cfg.sub("encoding");
+	if (ieq(enc_cfg.value("otype", "OneBlob"), "Identity")) {
+		// Identity encoding (encodings/identity.h:46-67, src/encoding.cu:77-79): feature j = x_j * scale + offset, the features that pad
+		// the width up to the network's alignment are ONE. No parameters: the memory warps of the fused kernel write the tile rows
+		// directly (BASELINE.json configs[0]: CutlassMLP / FullyFusedMLP 64 x 2 behind Identity).
+		m.enc_identity = true;
+		m.identity_scale = (float)enc_cfg.value("scale", 1.0);
+		m.identity_offset = (float)enc_cfg.value("offset", 0.0);
+		m.grid = GridConfig{};
+		m.grid.otype = "Identity";
+		m.grid.n_pos_dims = n_in;
+		m.grid.n_levels = 0;
+		m.grid.n_params = 0;
+		m.grid.offsets.assign(1, 0u);
+		m.grid.padded_width = next_multiple(n_in, alignment);
+		if (n_in != 2 && n_in != 3) throw std::runtime_error("tcnn_b200: the Identity encoding on the fused path covers 2-D and 3-D inputs");
+	} else {
+		m.grid = parse_grid(n_in, enc_cfg);
+		m.grid.padded_width = next_multiple(m.grid.n_levels * m.grid.n_features_per_level, alignment);
+	}
 
 	mlp.in_width = m.grid.padded_width;
 	mlp.out_width = n_out;
@@ -346,7 +368,7 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 
 	// ---- per-level scales, evaluated on the device like the reference's kernels (common_device.h:886-891)
 	m.level_scales_dev.resize(128);
-	evaluate_level_scales(m.grid, m.level_scales_dev.ptr);
+	if (!m.enc_identity) evaluate_level_scales(m.grid, m.level_scales_dev.ptr);
 
 	// ---- parameter buffers (trainer.h:69-87,489-503)
 	m.n_params = (size_t)mlp.n_params + m.grid.n_params;
@@ -405,6 +427,9 @@ static FusedStepParams make_params(Model& m, uint32_t batch, uint32_t loss_batch
 	FusedStepParams p{};
 	p.ablate = m.ablate;
 	p.grid = m.grid_meta();
+	p.enc_identity = m.enc_identity ? 1u : 0u;
+	p.identity_scale = m.identity_scale;
+	p.identity_offset = m.identity_offset;
 	p.width = m.mlp.width;
 	p.n_hidden_layers = m.mlp.n_hidden_layers;
 	p.activation = m.mlp.activation;
@@ -493,7 +518,7 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
 	// when there is one, else as memsets.
 	__half* const grid_grads = grads_base + m.mlp.n_params;
 	const size_t grid_grad_bytes = sizeof(__half) * m.grid.n_params;
-	const bool bin = m.binning && batch >= 16384;
+	const bool bin = m.binning && batch >= 16384 && !m.enc_identity;  // spatial order only matters to the table gathers
 	const bool zero_in_binning = bin && (((uintptr_t)grid_grads | grid_grad_bytes) & 15u) == 0;
 	if (!zero_in_binning) {
 		TCNNB_CUDA_CHECK(cudaMemsetAsync(grid_grads, 0, grid_grad_bytes, stream));
@@ -792,6 +817,11 @@ static float host_step_wait(Model& m, uint64_t ticket) {
 static std::string make_hyperparams(const Model& m) {
 	json::Value root = json::Value::object();
 	json::Value& enc = root["encoding"];
+	if (m.enc_identity) {
+		enc["otype"] = json::Value::string("Identity");
+		enc["scale"] = json::Value::number(m.identity_scale);
+		enc["offset"] = json::Value::number(m.identity_offset);
+	} else {
 	enc["otype"] = json::Value::string("Grid");
 	enc["type"] = json::Value::string(m.grid.grid_type == GRID_HASH ? "Hash" : (m.grid.grid_type == GRID_DENSE ? "Dense" : "Tiled"));
 	enc["n_levels"] = json::Value::number(m.grid.n_levels);
@@ -801,6 +831,7 @@ static std::string make_hyperparams(const Model& m) {
 	enc["per_level_scale"] = json::Value::number(m.grid.per_level_scale);
 	enc["interpolation"] = json::Value::string(m.grid.interpolation == INTERP_LINEAR ? "Linear" : (m.grid.interpolation == INTERP_SMOOTHSTEP ? "Smoothstep" : "Nearest"));
 	enc["hash"] = json::Value::string("CoherentPrime");
+	}
 	json::Value& net = root["network"];
 	net["otype"] = json::Value::string("FullyFusedMLP");
 	net["activation"] = json::Value::string(activation_name(m.mlp.activation));
