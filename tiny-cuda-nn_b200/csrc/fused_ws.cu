@@ -167,6 +167,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 	uint32_t tmem_base;
 	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem_slot));
 	const uint32_t n_tiles = p.batch_size / TILE_M;
+	// Tiles of this CTA: a CONTIGUOUS range [cta_first, cta_end) of the (spatially binned) batch. With the round-robin assignment of
+	// round 1 (tile = blockIdx + k * gridDim) all 148 CTAs worked on 148 neighbouring tiles at any moment, i.e. on the same few
+	// cells of the coarse dense levels, and their reductions queued up on the same L2 addresses (ablation: the 4 dense levels -- a
+	// quarter of the reductions -- cost 0.047 of the kernel's 0.217 ms). Contiguous ranges put concurrent CTAs in different regions.
+	const uint32_t cta_first = (uint32_t)(((uint64_t)blockIdx.x * n_tiles) / gridDim.x);
+	const uint32_t cta_end = (uint32_t)(((uint64_t)(blockIdx.x + 1) * n_tiles) / gridDim.x);
 
 	if (warp >= WS_MLP_THREADS / 32) {
 		// =========================================================================================== memory group
@@ -222,15 +228,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 		};
 		// tiles of this sub-group: k = sub, sub + 2, ... (SUBS == 2) or every tile of the CTA (SUBS == 1)
 		const uint32_t k_first = SUBS == 2 ? sub : 0u, k_step = SUBS;
-		const uint32_t tile_first = blockIdx.x + k_first * gridDim.x, tile_stride = k_step * gridDim.x;
-		uint32_t os_next = tile_first < n_tiles ? sample_of(tile_first) : 0;
-		uint32_t os_next2 = tile_first + tile_stride < n_tiles ? sample_of(tile_first + tile_stride) : 0;
+		const uint32_t tile_first = cta_first + k_first, tile_stride = k_step;
+		uint32_t os_next = tile_first < cta_end ? sample_of(tile_first) : 0;
+		uint32_t os_next2 = tile_first + tile_stride < cta_end ? sample_of(tile_first + tile_stride) : 0;
 		float x_next[D];
 #pragma unroll
-		for (uint32_t d = 0; d < D; ++d) x_next[d] = tile_first < n_tiles ? __ldg(p.positions + (size_t)os_next * D + d) : 0.0f;
+		for (uint32_t d = 0; d < D; ++d) x_next[d] = tile_first < cta_end ? __ldg(p.positions + (size_t)os_next * D + d) : 0.0f;
 		bool have_prev = false;
 		uint32_t k_prev = 0;
-		for (uint32_t k = k_first, tile = tile_first; tile < n_tiles; k += k_step, tile += tile_stride) {
+		for (uint32_t k = k_first, tile = tile_first; tile < cta_end; k += k_step, tile += tile_stride) {
 			const uint32_t e = k % NE, je = k / NE;  // enc buffer and its use count
 			const uint32_t enc_tile = s_enc + e * TILE_BYTES;
 			// ---- position of this thread's sample (fetched one tile ahead, its index two tiles ahead: no dependent global
@@ -239,11 +245,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 			os_next = os_next2;
 #pragma unroll
 			for (uint32_t d = 0; d < D; ++d) x_cur[d] = x_next[d];
-			if (tile + tile_stride < n_tiles) {
+			if (tile + tile_stride < cta_end) {
 #pragma unroll
 				for (uint32_t d = 0; d < D; ++d) x_next[d] = __ldg(p.positions + (size_t)os_next * D + d);
 			}
-			if (tile + 2 * tile_stride < n_tiles) os_next2 = sample_of(tile + 2 * tile_stride);
+			if (tile + 2 * tile_stride < cta_end) os_next2 = sample_of(tile + 2 * tile_stride);
 
 			// ---- gather tile k into enc[k % NE] once the MMAs of tile k - NE have released it
 			if (lt == 0) WS_STAMP(1 + sub, k, 0);
@@ -396,9 +402,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 			const uint32_t s = tile * TILE_M + row;
 			return p.perm ? __ldg(p.perm + s) : s;
 		};
-		uint32_t osample_next = blockIdx.x < n_tiles ? sample_of(blockIdx.x) : 0;
+		uint32_t osample_next = cta_first < cta_end ? sample_of(cta_first) : 0;
 		uint32_t k = 0;
-		for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+		for (uint32_t tile = cta_first; tile < cta_end; ++tile, ++k) {
 			const uint32_t g = k & 1u, j = k >> 1;
 			const uint32_t e = k % NE, je = k / NE;
 			const uint32_t enc_cur = s_enc + e * TILE_BYTES;
@@ -414,7 +420,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 					for (uint32_t q = 0; q < N_TGT_PREFETCH; ++q) tgt[q] = q < p.n_out ? __ldg(p.targets + (size_t)osample * p.n_out + q) : 0.0f;
 				}
 			}
-			if (tile + gridDim.x < n_tiles) osample_next = sample_of(tile + gridDim.x);
+			if (tile + 1 < cta_end) osample_next = sample_of(tile + 1);
 			if (tid == 0) WS_STAMP(0, k, 0);
 			mbar_wait(bar_enc_full + 8 * e, je & 1u);
 			if (tid == 0) WS_STAMP(0, k, 1);

@@ -118,10 +118,10 @@ __device__ __forceinline__ void transpose8x8_u128(uint4 (&a)[8], uint32_t lane) 
 		if (p.dbg_clock && (event) < 64u) p.dbg_clock[(((size_t)blockIdx.x * 5u + (role)) * 64u + (event)) * 8u + (field)] = clock64(); \
 	} while (0)
 
-// 576 threads per CTA: 65536 / 576 = 113 registers per thread; ptxas' own choice under __launch_bounds__ is 96 and spills the
-// accumulator pieces, so the budget is stated explicitly.
+// 576 threads per CTA -> 96 registers per thread (what the register file's allocation granularity leaves; asking for 112 with
+// __maxnreg__ compiles but does not launch). The accumulator pieces of the widest kernels spill a few words to local memory.
 template <uint32_t W, bool GENERIC_ACT>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(MlpCfg<W>::THREADS, 1)
 mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wo) {
 	using C = MlpCfg<W>;
 	const MlpForwardParams& p = kp.p;
@@ -348,23 +348,43 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 					// region, which the next layer's MMA reads as its A operand. Columns [c, c + n) are written to [c / 2, (c + n) / 2):
 					// a group's writes land in columns it has read itself or -- with two groups -- in columns the OTHER group reads,
 					// hence: every thread loads all of its columns first, then the slot's groups meet at a named barrier, then store.
-					uint32_t r[C::N_PIECES][C::PIECE];
-#pragma unroll
-					for (uint32_t k = 0; k < C::N_PIECES; ++k) tmem_ld_n<C::PIECE>(acc + col0 + k * C::PIECE, r[k]);
-					tmem_ld_wait();
-					if (stamp) MLPF_STAMP(1 + s, ev, 2);
-					if (C::GROUPS > 1) asm volatile("bar.sync %0, %1;" ::"r"(1u + s), "r"(C::SLOT_WARPS * 32u) : "memory");
-#pragma unroll
-					for (uint32_t k = 0; k < C::N_PIECES; ++k) {
-						uint32_t h[C::PIECE / 2];
-#pragma unroll
-						for (uint32_t i = 0; i < C::PIECE / 2; ++i) h[i] = act_pack(hid_act, r[k][2 * i], r[k][2 * i + 1]);
+					// Hazard: group 1's stores (A columns 32..63) land in columns that group 0 still has to READ as accumulator columns
+					// 32..63 (its last piece); group 0's own stores only cover columns it has read itself. So group 0 works piece by piece
+					// and signals a named barrier (bar.arrive, non-blocking) once its last piece is in registers; group 1 converts all
+					// its pieces first and stores them after the barrier.
+					auto store_piece = [&](uint32_t k, const uint32_t (&h)[C::PIECE / 2]) {
 						tmem_st_n<C::PIECE / 2>(acc + (col0 + k * C::PIECE) / 2, h);
 						if (p.hidden_out) {
 							uint4* dst = reinterpret_cast<uint4*>(p.hidden_out + ((size_t)l * p.batch_size + sample) * W + col0 + k * C::PIECE);
 #pragma unroll
 							for (uint32_t i = 0; i < C::PIECE / 8; ++i) dst[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
 						}
+					};
+					if (C::GROUPS == 1 || grp == 0) {
+#pragma unroll
+						for (uint32_t k = 0; k < C::N_PIECES; ++k) {
+							uint32_t r[C::PIECE], h[C::PIECE / 2];
+							tmem_ld_n<C::PIECE>(acc + col0 + k * C::PIECE, r);
+							tmem_ld_wait();
+							if (C::GROUPS > 1 && k == C::N_PIECES - 1) asm volatile("bar.arrive %0, %1;" ::"r"(1u + s), "r"(C::SLOT_WARPS * 32u) : "memory");
+#pragma unroll
+							for (uint32_t i = 0; i < C::PIECE / 2; ++i) h[i] = act_pack(hid_act, r[2 * i], r[2 * i + 1]);
+							store_piece(k, h);
+						}
+						if (stamp) MLPF_STAMP(1 + s, ev, 2);
+					} else {
+						uint32_t h[C::N_PIECES][C::PIECE / 2];
+#pragma unroll
+						for (uint32_t k = 0; k < C::N_PIECES; ++k) {
+							uint32_t r[C::PIECE];
+							tmem_ld_n<C::PIECE>(acc + col0 + k * C::PIECE, r);
+							tmem_ld_wait();
+#pragma unroll
+							for (uint32_t i = 0; i < C::PIECE / 2; ++i) h[k][i] = act_pack(hid_act, r[2 * i], r[2 * i + 1]);
+						}
+						asm volatile("bar.sync %0, %1;" ::"r"(1u + s), "r"(C::SLOT_WARPS * 32u) : "memory");
+#pragma unroll
+						for (uint32_t k = 0; k < C::N_PIECES; ++k) store_piece(k, h[k]);
 					}
 					if (stamp) MLPF_STAMP(1 + s, ev, 3);
 					tmem_st_wait();
