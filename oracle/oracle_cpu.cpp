@@ -633,6 +633,17 @@ static void loss_impl(int loss_type, uint32_t B, uint32_t stride, uint32_t dims,
 			const float psq = pred * pred + 0.01f;
 			value = difference * difference / psq / 1.0f / n_total;
 			gradient = 2 * difference / psq / 1.0f;
+		} else if (loss_type == ORC_LOSS_L1) {
+			// losses/l1.h:68-73
+			value = fabsf(difference) / 1.0f / n_total;
+			gradient = copysignf(1.0f / 1.0f, difference);
+		} else if (loss_type == ORC_LOSS_RELATIVE_L1 || loss_type == ORC_LOSS_MAPE || loss_type == ORC_LOSS_SMAPE) {
+			// losses/relative_l1.h:71-76, mape.h:72-77, smape.h:72-77: |d| * scale, the scale relative to prediction / target / their mean
+			const float tgt = target[target_idx];
+			const float denom = loss_type == ORC_LOSS_RELATIVE_L1 ? fabsf(pred) : (loss_type == ORC_LOSS_MAPE ? fabsf(tgt) : 0.5f * (fabsf(tgt) + fabsf(pred)));
+			const float scale = 1.0f / (denom + 1e-2f) / 1.0f;
+			value = fabsf(difference) * scale / n_total;
+			gradient = copysignf(scale, difference);
 		} else {
 			// losses/l2.h:64-74
 			value = difference * difference / 1.0f / n_total;

@@ -537,3 +537,80 @@ def test_torch_autograd_layer_on_the_module_tier(torch_cuda):
     xg = x.clone().requires_grad_(True)
     model(xg).float().sum().backward()  # input gradients are delivered (tests/test_gpu_encoding.py checks their values)
     assert xg.grad is not None and torch.isfinite(xg.grad).all()
+
+
+@pytest.mark.parametrize("loss", ["L1", "RelativeL1", "Mape", "Smape"])
+def test_other_losses_match_oracle(torch_cuda, loss):
+    """src/loss.cu:57-65: the element-wise losses beside L2 / RelativeL2 (losses/l1.h:68-73, relative_l1.h:71-76, mape.h:72-77,
+    smape.h:72-77), fused into the output epilogue like them: loss values, loss gradients and everything downstream against the oracle."""
+    torch = torch_cuda
+    import tcnn_b200
+
+    cfg = load_cfg("hash3d_small")
+    cfg["loss"] = {"otype": loss}
+    B = 1024
+    model = tcnn_b200.create_from_config(3, 3, cfg)
+    assert model.hyperparams()["loss"]["otype"] == loss
+    orc = ob.OracleModel(3, 3, cfg, scales=model.grid_levels()["scales"])
+    x, y = make_batch(3, 3, B)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    out_tap = torch.zeros(B, 16, dtype=torch.float16, device="cuda")
+    dy_tap = torch.zeros(B, 16, dtype=torch.float16, device="cuda")
+    lv_tap = torch.zeros(B, 3, dtype=torch.float32, device="cuda")
+    model.set_debug_taps(output=out_tap, dL_doutput=dy_tap, loss_values=lv_tap)
+    model.trainer.training_step(xd, yd, run_optimizer=False)
+    loss_dev = model.trainer.loss()
+    torch.cuda.synchronize()
+    lv_ref, dy_ref = orc.loss(f16(out_tap), y)  # the oracle's loss on the DEVICE's outputs: isolates the epilogue
+    assert rae(lv_tap.cpu().numpy(), lv_ref[:, :3]) < 1e-3
+    a, b = ob.half_bits_to_float(f16(dy_tap)), ob.half_bits_to_float(dy_ref)
+    # sign(difference) flips where prediction == target to fp16 rounding; everywhere else the gradients agree to fp16 rounding
+    assert (np.abs(a - b) > 1e-3 * np.abs(b).max()).mean() < 1e-3
+    assert abs(loss_dev - float(lv_ref.sum(dtype=np.float64))) <= 1e-4 * abs(loss_dev)
+    model.set_debug_taps()
+    dev_losses, ref_losses = [], []
+    for _ in range(8):
+        model.trainer.training_step(xd, yd)
+        dev_losses.append(model.trainer.loss())
+        ref_losses.append(orc.training_step(x, y))
+    assert dev_losses[-1] < dev_losses[0]
+    for u, v in zip(dev_losses, ref_losses):
+        assert abs(u - v) <= 5e-2 * abs(v) + 1e-6, (dev_losses, ref_losses)
+
+
+def test_exponential_decay_wrapper_follows_the_schedule(torch_cuda):
+    """optimizers/exponential_decay.h:60-70 around Adam: from decay_start on, every decay_interval steps the learning rate is
+    multiplied by decay_base. The trajectory equals the oracle's Adam driven with the same per-step learning rates."""
+    torch = torch_cuda
+    import tcnn_b200
+
+    cfg = load_cfg("hash3d_small")
+    adam = dict(cfg["optimizer"])
+    cfg["optimizer"] = {"otype": "ExponentialDecay", "decay_start": 2, "decay_interval": 2, "decay_base": 0.5, "decay_end": 6, "nested": adam}
+    B = 512
+    model = tcnn_b200.create_from_config(3, 3, cfg)
+    ocfg = load_cfg("hash3d_small")
+    orc = ob.OracleModel(3, 3, ocfg, scales=model.grid_levels()["scales"])
+    x, y = make_batch(3, 3, B)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    factor, base_lr = 1.0, adam["learning_rate"]
+    for step in range(9):
+        if step >= 2 and (step - 2) % 2 == 0 and step <= 6:
+            factor *= 0.5
+        orc.adam.learning_rate = base_lr * factor
+        model.trainer.training_step(xd, yd)
+        a, b = model.trainer.loss(), orc.training_step(x, y)
+        assert abs(a - b) <= 3e-2 * abs(b) + 1e-6, (step, a, b)
+    assert factor == 0.125
+    p = model.trainer.params_full_precision().cpu().numpy()
+    assert np.abs(p - orc.params_fp32).mean() < 0.05 * base_lr * 9
+    # without the schedule the parameters would have moved further: the schedule is really applied
+    plain = tcnn_b200.create_from_config(3, 3, ocfg)
+    for _ in range(9):
+        plain.trainer.training_step(xd, yd)
+    p0 = ob.OracleModel(3, 3, ocfg).params_fp32
+    assert np.abs(plain.trainer.params_full_precision().cpu().numpy() - p0).mean() > 1.3 * np.abs(p - p0).mean()
+    with pytest.raises(tcnn_b200.TcnnError, match="outside the tcnn_b200 hot path"):
+        bad = json.loads(json.dumps(ocfg))
+        bad["optimizer"] = {"otype": "Shampoo"}
+        tcnn_b200.create_from_config(3, 3, bad)

@@ -126,6 +126,11 @@ struct Model {
 	std::string loss_name = "RelativeL2";
 	AdamParams adam;
 	uint32_t adam_step_count = 0;
+	struct {  // ExponentialDecay wrapper (optimizers/exponential_decay.h)
+		bool enabled = false;
+		float base = 0.1f, factor = 1.0f;
+		uint32_t interval = 10000, start = 10000, end = 10000000;
+	} lr_decay;
 	float loss_scale = 128.0f;  // default_loss_scale<__half>() (common.h:243)
 	int device = 0;
 	int n_sms = 148;
@@ -277,17 +282,34 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 	m.loss_name = loss.value("otype", "RelativeL2");
 	if (ieq(m.loss_name, "RelativeL2")) m.loss_type = LOSS_RELATIVE_L2;
 	else if (ieq(m.loss_name, "L2")) m.loss_type = LOSS_L2;
+	else if (ieq(m.loss_name, "L1")) m.loss_type = LOSS_L1;
+	else if (ieq(m.loss_name, "RelativeL1")) m.loss_type = LOSS_RELATIVE_L1;
+	else if (ieq(m.loss_name, "Mape")) m.loss_type = LOSS_MAPE;
+	else if (ieq(m.loss_name, "Smape")) m.loss_type = LOSS_SMAPE;
 	else {
-		static const char* known[] = {"RelativeL2Luminance", "L1", "RelativeL1", "Mape", "Smape", "CrossEntropy", "Variance"};
-		for (auto k : known) if (ieq(m.loss_name, k)) throw std::runtime_error("Loss '" + m.loss_name + "' is outside the tcnn_b200 hot path (L2 and RelativeL2 are built)");
+		static const char* known[] = {"RelativeL2Luminance", "CrossEntropy", "Variance"};
+		for (auto k : known) if (ieq(m.loss_name, k)) throw std::runtime_error("Loss '" + m.loss_name + "' is outside the tcnn_b200 hot path (L2, RelativeL2, L1, RelativeL1, Mape and Smape are built)");
 		throw std::runtime_error("Loss '" + m.loss_name + "' not found");
 	}
 
 	// ---- optimizer (src/optimizer.cu:50-80, adam.h:221-303)
-	const json::Value& opt = cfg.sub("optimizer");
-	const std::string opt_name = opt.value("otype", "Adam");
+	const json::Value* opt_ptr = &cfg.sub("optimizer");
+	std::string opt_name = opt_ptr->value("otype", "Adam");
+	if (ieq(opt_name, "ExponentialDecay")) {
+		// optimizers/exponential_decay.h:46-160: a learning-rate schedule around the nested optimizer -- from step decay_start on, every
+		// decay_interval steps (until decay_end) the learning rate is multiplied by decay_base. Host-side bookkeeping only.
+		m.lr_decay.enabled = true;
+		m.lr_decay.base = (float)opt_ptr->value("decay_base", 0.1);
+		m.lr_decay.interval = (uint32_t)opt_ptr->value("decay_interval", 10000.0);
+		m.lr_decay.start = (uint32_t)opt_ptr->value("decay_start", 10000.0);
+		m.lr_decay.end = (uint32_t)opt_ptr->value("decay_end", 10000000.0);
+		if (m.lr_decay.interval == 0) throw std::runtime_error("ExponentialDecay: decay_interval must be positive.");
+		opt_ptr = &opt_ptr->sub("nested");
+		opt_name = opt_ptr->value("otype", "Adam");
+	}
+	const json::Value& opt = *opt_ptr;
 	if (!ieq(opt_name, "Adam")) {
-		throw std::runtime_error("Optimizer '" + opt_name + "' is outside the tcnn_b200 hot path (Adam is built)");
+		throw std::runtime_error("Optimizer '" + opt_name + "' is outside the tcnn_b200 hot path (Adam, optionally inside ExponentialDecay, is built)");
 	}
 	AdamParams& a = m.adam;
 	a.beta1 = (float)opt.value("beta1", (double)a.beta1);
@@ -459,8 +481,14 @@ static FusedStepParams make_params(Model& m, uint32_t batch, uint32_t loss_batch
 
 // Hyper-parameters of the next optimizer step (advances the step counter; AdaBound bounds per adam.h:161-168).
 static AdamParams next_adam_params(Model& m) {
+	if (m.lr_decay.enabled) {  // exponential_decay.h:60-70, evaluated with the step count BEFORE this step
+		const uint32_t step = m.adam_step_count;
+		if (step == 0) m.lr_decay.factor = 1.0f;
+		if (step >= m.lr_decay.start && (step - m.lr_decay.start) % m.lr_decay.interval == 0 && step <= m.lr_decay.end) m.lr_decay.factor *= m.lr_decay.base;
+	}
 	++m.adam_step_count;
 	AdamParams a = m.adam;
+	a.learning_rate = m.adam.learning_rate * m.lr_decay.factor;
 	a.lower_lr_bound = 0;
 	a.upper_lr_bound = std::numeric_limits<float>::max();
 	if (a.adabound) {
@@ -839,7 +867,8 @@ static std::string make_hyperparams(const Model& m) {
 	net["n_neurons"] = json::Value::number(m.mlp.width);
 	net["n_hidden_layers"] = json::Value::number(m.mlp.n_hidden_layers);
 	json::Value& loss = root["loss"];
-	loss["otype"] = json::Value::string(m.loss_type == LOSS_L2 ? "L2" : "RelativeL2");
+	static const char* loss_names[] = {"L2", "RelativeL2", "L1", "RelativeL1", "Mape", "Smape"};
+	loss["otype"] = json::Value::string(loss_names[m.loss_type]);
 	json::Value& opt = root["optimizer"];
 	opt["otype"] = json::Value::string("Adam");
 	opt["learning_rate"] = json::Value::number(m.adam.learning_rate);
