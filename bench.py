@@ -263,7 +263,8 @@ def run_own(args):
 
     # world == 1: plain training_step; else shard step + reduce-scatter of the table gradients + Adam on the rank's own table
     # slice + all-gather of the updated fp16 slices (TCNNB_DP_REPLICATED=1: all-reduce + full Adam on every replica)
-    dp = DataParallelTrainer(trainer, shard_optimizer=os.environ.get("TCNNB_DP_REPLICATED", "0") != "1", native=os.environ.get("TCNNB_DP_PYTHON", "0") != "1")
+    dp = DataParallelTrainer(trainer, shard_optimizer=os.environ.get("TCNNB_DP_REPLICATED", "0") != "1", native=os.environ.get("TCNNB_DP_PYTHON", "0") != "1",
+                             peer_memory=os.environ.get("TCNNB_DP_NCCL", "0") != "1")  # env switches: A/B of the data-parallel engines (bench only)
     stream = torch.cuda.current_stream()
 
     def step(i):
@@ -295,6 +296,25 @@ def run_own(args):
     # quantity after the same number of steps on the same data sequence (rank 0 draws the reference's pcg32{1337} stream)
     step(args.warmup + args.steps)
     final_loss = dp.loss()
+
+    # ---- strong scaling (N > 1): the SAME global batch 2^18 cut into N shards -- bounded by the fixed cost
+    # of the gradient exchange + optimizer pass; reported beside the weak-scaling headline
+    strong = None
+    if world > 1 and BATCH % (world * 256) == 0:
+        sh = BATCH // world
+        for i in range(max(3, args.warmup // 2)):
+            dp.training_step(xs[i % pool][:sh], ys[i % pool][:sh])
+        sync_all()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for i in range(args.steps):
+            dp.training_step(xs[i % pool][:sh], ys[i % pool][:sh])
+        s1.record(stream)
+        sync_all()
+        t = torch.tensor([s0.elapsed_time(s1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong_ms = float(t.item()) / args.steps
+        strong = {"global_batch": BATCH, "shard_batch": sh, "ms_per_step": strong_ms, "value": BATCH / (strong_ms * 1e-3), "unit": "samples/s", "scaling": "strong"}
 
     # ---- secondary metric: network->inference samples/s over the same batch pool (device-resident, CUDA events)
     inf_steps = max(args.steps, 20)
@@ -356,12 +376,14 @@ def run_own(args):
             "metric": METRIC, "value": global_batch * args.steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16", "data": "synthetic",
-            "config": config_dict(world, f"dp{world}" + ("" if world == 1 else ("-zero1" if dp.shard_optimizer else "-replicated") + ("-native" if dp.native else "-torchdist"))),
+            "config": config_dict(world, f"dp{world}" + ("" if world == 1 else ("-zero1" if dp.shard_optimizer else "-replicated") + ("-" + dp.engine if dp.native else "-torchdist"))),
             "clocks": cs.summary(),
             "e2e": {"value": global_batch * e2e_steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": BATCH * (N_IN + N_OUT) * 4, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps, "warmup": E2E_WARMUP, "last_loss": e2e_losses[-1],
                     "api": ("tcnnb_training_step_host_submit/_wait" if world == 1 else "tcnnb_dp_training_step_host_submit/_wait") + " (C ABI, pinned host buffers, two steps in flight, every loss read back)"},
             "inference": {"value": global_batch / (inf_ms * 1e-3), "unit": "samples/s", "ms_per_batch": inf_ms, "steps": inf_steps},
+            "strong_scaling": strong,
+            "dp_engine": getattr(dp, "engine", "single"),
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": traffic.get("kernel", "fused_ws_kernel"), "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic.get("bytes"), "traffic_unit": "B/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "kernel_ms": fused_ms, "optimizer_kernel_ms": adam_ms, "binning_kernels_ms": binning_ms,
