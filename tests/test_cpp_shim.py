@@ -145,3 +145,23 @@ def test_snapshots_interoperate_with_the_reference(torch_cuda, tmp_path, with_op
     ref2 = np.fromfile(os.path.join(d, "inference_loaded.f32"), np.float32)
     assert rae(ours2, ref2, 99.0) < 1e-2
     assert np.isfinite(back["next_step_loss"])
+
+
+def test_unmodified_reference_torch_bindings_compile_against_cpp_api_h():
+    """bindings/torch/tinycudann/bindings.cpp (the PyTorch extension's C++ half, which includes only <tiny-cuda-nn/cpp_api.h>) compiles
+    UNCHANGED against this repo's include/tiny-cuda-nn/cpp_api.h: same tcnn::cpp::Module interface, factories and free functions."""
+    import sysconfig
+    import tempfile
+
+    src = "/root/reference/bindings/torch/tinycudann/bindings.cpp"
+    if not os.path.exists(src):
+        pytest.skip("/root/reference is not mounted here")
+    from torch.utils.cpp_extension import include_paths
+
+    with tempfile.TemporaryDirectory() as tmp:
+        cmd = ["g++", "-std=c++17", "-O0", "-w", "-c", src, "-o", os.path.join(tmp, "bindings.o"), "-I" + os.path.join(ROOT, "include"), "-I/root/reference/dependencies",
+               "-I/usr/local/cuda/include", "-I" + sysconfig.get_paths()["include"], "-DTCNN_PARAMS_UNALIGNED", "-DTORCH_EXTENSION_NAME=_C"]
+        for inc in include_paths():
+            cmd += ["-I", inc]
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0, out.stderr[-3000:]
