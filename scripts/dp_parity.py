@@ -52,6 +52,8 @@ if __name__ == "__main__":
     # (sharded optimizer, native engine inside libtcnn_b200, peer-memory kernels instead of NCCL collectives)
     MODES = [(False, False, False), (True, False, False), (False, True, False), (True, True, False), (True, True, True)]
     WORLD = int(os.environ.get("TCNNB_DP_WORLD", "2"))
+    if os.environ.get("TCNNB_DP_MODES"):  # e.g. "4" = the peer-memory engine only (8-GPU runs are charged 8x)
+        MODES = [MODES[int(i)] for i in os.environ["TCNNB_DP_MODES"].split(",")]
     for so, nat, pm in MODES:
         mp.spawn(worker, args=(WORLD, out, so, nat, pm), nprocs=WORLD, join=True)
     import oracle_binding as ob
