@@ -91,6 +91,28 @@ __device__ __forceinline__ uint32_t act_bwd_pack(uint32_t act, uint32_t lo_bits,
 	return *reinterpret_cast<const uint32_t*>(&y);
 }
 
+// One element of the loss (src/loss.cu:57-90; losses/l2.h:56-74, relative_l2.h:56-75, l1.h:68-73, relative_l1.h:71-76, mape.h:72-77,
+// smape.h:72-77): `value` is already divided by n_total = loss-batch size x output dims, `grad` is d(value)/d(pred) x n_total.
+__device__ __forceinline__ void loss_element(uint32_t loss_type, float pred, float target, float n_total, float& value, float& grad) {
+	const float diff = pred - target;
+	if (loss_type == LOSS_RELATIVE_L2) {
+		const float psq = pred * pred + 0.01f;
+		value = diff * diff / psq / n_total;
+		grad = 2.0f * diff / psq;
+	} else if (loss_type == LOSS_L2) {
+		value = diff * diff / n_total;
+		grad = 2.0f * diff;
+	} else if (loss_type == LOSS_L1) {
+		value = fabsf(diff) / n_total;
+		grad = copysignf(1.0f, diff);
+	} else {  // RelativeL1 / Mape / Smape
+		const float denom = loss_type == LOSS_RELATIVE_L1 ? fabsf(pred) : (loss_type == LOSS_MAPE ? fabsf(target) : 0.5f * (fabsf(target) + fabsf(pred)));
+		const float scale = 1.0f / (denom + 1e-2f);
+		value = fabsf(diff) * scale / n_total;
+		grad = copysignf(scale, diff);
+	}
+}
+
 struct SmemSync {
 	// dynamic shared memory, 1024-byte aligned:
 	//   [ enc_0 | enc_1 | h_0 .. h_{NH-1} | dy | (park) | W_0 .. W_{NH-1} | W_out ] then barriers

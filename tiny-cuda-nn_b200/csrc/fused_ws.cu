@@ -523,24 +523,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 							if (q < p.n_out) {
 								const float pred = __half2float(y16[q]);
 								const float target = q < N_TGT_PREFETCH ? tgt[q] : __ldg(p.targets + (size_t)osample * p.n_out + q);
-								const float diff = pred - target;
 								float value, grad;
-								if (p.loss_type == LOSS_RELATIVE_L2) {
-									const float psq = pred * pred + 0.01f;
-									value = diff * diff / psq / n_total;
-									grad = 2.0f * diff / psq;
-								} else if (p.loss_type == LOSS_L2) {
-									value = diff * diff / n_total;
-									grad = 2.0f * diff;
-								} else if (p.loss_type == LOSS_L1) {  // losses/l1.h:68-73
-									value = fabsf(diff) / n_total;
-									grad = copysignf(1.0f, diff);
-								} else {  // RelativeL1 / Mape / Smape (losses/relative_l1.h:71-76, mape.h:72-77, smape.h:72-77)
-									const float denom = p.loss_type == LOSS_RELATIVE_L1 ? fabsf(pred) : (p.loss_type == LOSS_MAPE ? fabsf(target) : 0.5f * (fabsf(target) + fabsf(pred)));
-									const float scale = 1.0f / (denom + 1e-2f);
-									value = fabsf(diff) * scale / n_total;
-									grad = copysignf(scale, diff);
-								}
+								loss_element(p.loss_type, pred, target, n_total, value, grad);
 								gq = p.loss_scale * grad / n_total;
 								loss_acc += value;
 								if (p.loss_values) p.loss_values[(size_t)osample * p.n_out + q] = value;

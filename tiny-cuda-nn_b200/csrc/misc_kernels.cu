@@ -6,6 +6,8 @@
 #include "common.cuh"
 #include "misc_kernels.h"
 
+#include "fused_common.cuh"
+
 namespace tcnnb {
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -195,6 +197,62 @@ __global__ void mlp_grad_finalize_kernel(uint32_t n, float* __restrict__ dw_accu
 	}
 }
 
+// ---- loss on its own (general, unfused training path): prediction rows [batch][stride] fp16 + targets [batch][n_out] fp32 ->
+// dL/d(output) rows (x loss_scale, through the output activation's transfer, padding columns zero), per-element values, sum.
+// Same expressions as the fused kernel's output epilogue (fused_common.cuh loss_element).
+__global__ void loss_kernel(uint32_t loss_type, uint32_t out_act, uint32_t batch, uint32_t n_out, uint32_t stride, float loss_scale, float n_total, const __half* __restrict__ prediction,
+                            const float* __restrict__ targets, __half* __restrict__ dL_dy, float* __restrict__ loss_values, float* __restrict__ loss_sum) {
+	pdl_wait();
+	pdl_launch_dependents();
+	const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;  // one thread per (sample, output column)
+	float value = 0.0f;
+	if (i < batch * stride) {
+		const uint32_t sample = i / stride, q = i % stride;
+		const __half y = prediction[i];
+		float gq = 0.0f;
+		if (q < n_out) {
+			float grad;
+			fused::loss_element(loss_type, __half2float(y), targets[(size_t)sample * n_out + q], n_total, value, grad);
+			gq = loss_scale * grad / n_total;
+			if (loss_values) loss_values[(size_t)sample * n_out + q] = value;
+		}
+		dL_dy[i] = fused::act_bwd_h(out_act, __float2half_rn(gq), y);
+	}
+#pragma unroll
+	for (uint32_t o = 16; o > 0; o >>= 1) value += __shfl_xor_sync(0xFFFFFFFFu, value, o);
+	if ((threadIdx.x & 31u) == 0 && loss_sum && value != 0.0f) atomicAdd(loss_sum, value);
+}
+
+// dL/d(output) of a caller (Network::backward, fully_fused_mlp.cu:755-762) through the output activation's transfer.
+__global__ void activation_backward_output_kernel(uint32_t act, uint64_t n, const __half* __restrict__ grad, const __half* __restrict__ fwd, __half* __restrict__ out) {
+	pdl_wait();
+	pdl_launch_dependents();
+	const uint64_t i = threadIdx.x + (uint64_t)blockIdx.x * blockDim.x;
+	if (i < n) out[i] = fused::act_bwd_h(act, grad[i], fwd[i]);
+}
+
+// Identity encoding on its own (encodings/identity.h:46-67,69-91): rows [n][width] fp16, feature j < n_dims = x_j * scale + offset,
+// padding features 1; and its backward, dL/dx_j = dL/d(feature j) * scale (fp32 rows [n][n_dims]).
+__global__ void identity_encode_kernel(uint64_t n_total, uint32_t n_dims, uint32_t width, float scale, float offset, const float* __restrict__ x, __half* __restrict__ out) {
+	pdl_wait();
+	pdl_launch_dependents();
+	const uint64_t i = threadIdx.x + (uint64_t)blockIdx.x * blockDim.x;
+	if (i >= n_total) return;
+	const uint64_t sample = i / width;
+	const uint32_t j = (uint32_t)(i % width);
+	out[i] = j < n_dims ? __float2half_rn(fmaf(x[sample * n_dims + j], scale, offset)) : __float2half_rn(1.0f);
+}
+
+__global__ void identity_backward_kernel(uint64_t n_total, uint32_t n_dims, uint32_t width, float scale, const __half* __restrict__ dL_dy, float* __restrict__ dL_dx) {
+	pdl_wait();
+	pdl_launch_dependents();
+	const uint64_t i = threadIdx.x + (uint64_t)blockIdx.x * blockDim.x;
+	if (i >= n_total) return;
+	const uint64_t sample = i / n_dims;
+	const uint32_t j = (uint32_t)(i % n_dims);
+	dL_dx[i] = __half2float(dL_dy[sample * width + j]) * scale;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Data parallelism over peer memory. See misc_kernels.h for the protocol.
 // ------------------------------------------------------------------------------------------------------------------
@@ -334,6 +392,30 @@ cudaError_t launch_adam_step(cudaStream_t stream, const AdamParams& a, uint32_t 
 cudaError_t launch_mlp_grad_finalize(cudaStream_t stream, uint32_t n, float* dw_accum, __half* gradients) {
 	if (n == 0) return cudaSuccess;
 	return launch_pdl(mlp_grad_finalize_kernel, blocks_for(n, 256), 256, 0, stream, n, dw_accum, gradients);
+}
+
+cudaError_t launch_loss(cudaStream_t stream, uint32_t loss_type, uint32_t output_activation, uint32_t batch, uint32_t n_out, uint32_t stride, float loss_scale, uint32_t n_total,
+                        const __half* prediction, const float* targets, __half* dL_dy, float* loss_values, float* loss_sum) {
+	if ((uint64_t)batch * stride >= (1ull << 32)) return cudaErrorInvalidValue;
+	return launch_pdl(loss_kernel, blocks_for(batch * stride, 256), 256, 0, stream, loss_type, output_activation, batch, n_out, stride, loss_scale, (float)n_total, prediction, targets,
+	                  dL_dy, loss_values, loss_sum);
+}
+
+cudaError_t launch_activation_backward_output(cudaStream_t stream, uint32_t activation, uint64_t n, const __half* grad, const __half* forward_output, __half* out) {
+	if (n == 0) return cudaSuccess;
+	return launch_pdl(activation_backward_output_kernel, (uint32_t)((n + 255) / 256), 256, 0, stream, activation, n, grad, forward_output, out);
+}
+
+cudaError_t launch_identity_encode(cudaStream_t stream, uint32_t n, uint32_t n_dims, uint32_t width, float scale, float offset, const float* x, __half* out) {
+	const uint64_t total = (uint64_t)n * width;
+	if (total == 0) return cudaSuccess;
+	return launch_pdl(identity_encode_kernel, (uint32_t)((total + 255) / 256), 256, 0, stream, total, n_dims, width, scale, offset, x, out);
+}
+
+cudaError_t launch_identity_backward(cudaStream_t stream, uint32_t n, uint32_t n_dims, uint32_t width, float scale, const __half* dL_dy, float* dL_dx) {
+	const uint64_t total = (uint64_t)n * n_dims;
+	if (total == 0) return cudaSuccess;
+	return launch_pdl(identity_backward_kernel, (uint32_t)((total + 255) / 256), 256, 0, stream, total, n_dims, width, scale, dL_dy, dL_dx);
 }
 
 cudaError_t launch_dp_barrier(cudaStream_t stream, const DpPeers& peers, uint32_t epoch) {

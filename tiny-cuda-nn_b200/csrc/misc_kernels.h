@@ -33,6 +33,16 @@ cudaError_t launch_adam_step(cudaStream_t stream, const AdamParams& a, uint32_t 
                              float* second_moments, uint32_t* param_steps);
 cudaError_t launch_mlp_grad_finalize(cudaStream_t stream, uint32_t n, float* dw_accum, __half* gradients);
 
+// General (unfused) training path: loss + dL/d(output) from fp16 prediction rows [batch][stride]; loss_values / loss_sum may be null.
+cudaError_t launch_loss(cudaStream_t stream, uint32_t loss_type, uint32_t output_activation, uint32_t batch, uint32_t n_out, uint32_t stride, float loss_scale, uint32_t n_total,
+                        const __half* prediction, const float* targets, __half* dL_dy, float* loss_values, float* loss_sum);
+// out = grad * f'(.) of the output activation, expressed through the forward output (element-wise, fp16).
+cudaError_t launch_activation_backward_output(cudaStream_t stream, uint32_t activation, uint64_t n, const __half* grad, const __half* forward_output, __half* out);
+
+// Identity encoding (encodings/identity.h:46-91) as stand-alone kernels: rows [n][width] fp16 with ones as padding; dL/dx in fp32.
+cudaError_t launch_identity_encode(cudaStream_t stream, uint32_t n, uint32_t n_dims, uint32_t width, float scale, float offset, const float* x, __half* out);
+cudaError_t launch_identity_backward(cudaStream_t stream, uint32_t n, uint32_t n_dims, uint32_t width, float scale, const __half* dL_dy, float* dL_dx);
+
 // ---- data parallelism over peer memory (NVLink / NVSwitch): one-pass "reduce + Adam + publish" on this rank's slice ----------------
 // Every rank holds [fp16 params | fp16 gradients | flags] at the SAME offsets of a symmetric allocation that all peers have
 // mapped (rendezvous by the host framework). peers.* are this rank's views of every rank's copy; *_mc are the NVLS multicast

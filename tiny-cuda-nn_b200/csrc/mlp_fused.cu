@@ -33,7 +33,7 @@
 #include "fused_common.cuh"
 #include "ptx.cuh"
 
-#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint, no link to libcuda)
+#include "tma_host.h"
 
 namespace tcnnb {
 
@@ -64,8 +64,9 @@ struct MlpCfg {
 
 struct MlpKernelParams {
 	MlpForwardParams p;
-	uint32_t n_stages;  // == n_layers when all matrices are resident
+	uint32_t n_stages;  // == n_steps when all matrices are resident
 	uint32_t resident;
+	uint32_t n_steps;   // MMAs chained per tile: n_hidden_layers + 1 (the backward chain without dL/d(input): n_hidden_layers)
 };
 
 template <uint32_t N>
@@ -120,19 +121,27 @@ __device__ __forceinline__ void transpose8x8_u128(uint4 (&a)[8], uint32_t lane) 
 
 // 576 threads per CTA -> 96 registers per thread (what the register file's allocation granularity leaves; asking for 112 with
 // __maxnreg__ compiles but does not launch). The accumulator pieces of the widest kernels spill a few words to local memory.
-template <uint32_t W, bool GENERIC_ACT>
+//
+// BWD = true is the same machine run backwards (threadblock_layer<..., BACKWARD>, fully_fused_mlp.cu:47-129,151-259): the operand that
+// enters is dL/d(output) (already through the output activation's transfer), step j multiplies by matrix NH - j read MN-major
+// -- the SAME bytes TMA delivered, W^T without a transposed copy --, the hidden epilogue multiplies by the activation's derivative
+// (from the forward pass's post-activation values in `hidden_in`) and writes g_l to `hidden_out` (for the weight-gradient kernel,
+// mlp_wgrad.cu), and what leaves is dL/d(input).
+template <uint32_t W, bool GENERIC_ACT, bool BWD>
 __global__ void __launch_bounds__(MlpCfg<W>::THREADS, 1)
 mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wo) {
 	using C = MlpCfg<W>;
 	const MlpForwardParams& p = kp.p;
 	const uint32_t hid_act = GENERIC_ACT ? p.activation : (uint32_t)ACT_RELU;
-	const uint32_t out_act = GENERIC_ACT ? p.output_activation : (uint32_t)ACT_NONE;
+	const uint32_t out_act = BWD ? (uint32_t)ACT_NONE : (GENERIC_ACT ? p.output_activation : (uint32_t)ACT_NONE);
 	extern __shared__ __align__(1024) uint8_t smem_raw[];
 	const uint32_t tid = threadIdx.x;
 	const uint32_t warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
 	const uint32_t lane = tid & 31u;
-	const uint32_t NH = p.n_hidden_layers, n_layers = NH + 1;
+	const uint32_t NH = p.n_hidden_layers, n_layers = kp.n_steps;
 	const uint32_t in_w = p.in_width, out_w = p.out_width;
+	const uint32_t first_w = BWD ? out_w : in_w;  // width of the rows that enter the chain ...
+	const uint32_t last_w = BWD ? in_w : out_w;   // ... and of the rows that leave it
 	const uint32_t n_stages = kp.n_stages;
 	const bool resident = kp.resident != 0;
 
@@ -184,7 +193,8 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 		if (lane == 0) {
 			const uint32_t n_loads = resident ? n_layers : n_rounds * n_layers;
 			for (uint32_t g = 0; g < (n_my ? n_loads : 0u); ++g) {
-				const uint32_t l = resident ? g : g % n_layers;
+				const uint32_t step = resident ? g : g % n_layers;
+				const uint32_t l = BWD ? NH - step : step;  // matrix of this step
 				const uint32_t stage = resident ? g : g % n_stages;
 				if (!resident && g >= n_stages) mbar_wait(bar_w_free + 8 * stage, ((g / n_stages) - 1u) & 1u);
 				const uint32_t dst = s_stage0 + stage * C::STAGE_BYTES;
@@ -214,8 +224,6 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 			n_real[s] = n_my > s ? (n_my - s + C::SLOTS - 1) / C::SLOTS : 0;
 			remaining += (resident ? n_real[s] : n_rounds) * n_layers;
 		}
-		const uint32_t idesc_hidden = umma_idesc_f16(128, W, 0, 0);
-		const uint32_t idesc_out = umma_idesc_f16(128, out_w, 0, 0);
 		while (remaining) {
 #pragma unroll
 			for (uint32_t s = 0; s < C::SLOTS; ++s) {
@@ -238,10 +246,14 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 						const uint32_t d_tmem = slot_base + (l & 1u) * C::REGION;
 						const uint32_t a_tmem = slot_base + ((l + 1u) & 1u) * C::REGION;  // first half of the other region
 						const uint32_t b_smem = s_stage0 + stage * C::STAGE_BYTES;
-						const uint32_t ksteps = (l == 0 ? in_w : W) / 16;
-						const uint32_t idesc = l == NH ? idesc_out : idesc_hidden;
+						const uint32_t ksteps = (l == 0 ? first_w : W) / 16;
+						const uint32_t n_cols = l == NH ? last_w : W;
+						const uint32_t idesc = umma_idesc_f16(128, n_cols, 0, BWD ? 1 : 0);
 						for (uint32_t j = 0; j < ksteps; ++j) {
-							const uint64_t b_desc = umma_desc_sw128(b_smem + (j >> 2) * C::KBLOCK_BYTES + (j & 3u) * 32u, 16u, 1024u);
+							// forward: stage = [N rows][64 K] boxes, K-major; backward: the same boxes are [K rows][64 N], MN-major
+							// (16 K-rows = 2 048 bytes per step, the next 64 N-columns one box further)
+							const uint64_t b_desc = BWD ? umma_desc_sw128(b_smem + j * 2048u, C::KBLOCK_BYTES, 1024u)
+							                            : umma_desc_sw128(b_smem + (j >> 2) * C::KBLOCK_BYTES + (j & 3u) * 32u, 16u, 1024u);
 							umma_f16_ts(d_tmem, a_tmem + j * 8u, b_desc, idesc, j > 0);
 						}
 						umma_commit(bar_acc_ready + 8 * s);
@@ -276,7 +288,7 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 		// ---- network input: one 64-column block per warp group. The 8 lanes of a lane group fetch 8 consecutive 16-byte pieces of
 		// ONE row (128 contiguous bytes) for 8 rows in turn; transpose8x8_u128 hands every lane its own row when the tile starts
 		// (one tile later, so that the loads stay in flight across the last layer).
-		const bool has_in_block = col0 < in_w;
+		const bool has_in_block = col0 < first_w;
 		uint4 pre[8];
 		auto load_input = [&](uint32_t tile) {
 			if (!has_in_block) return;
@@ -285,7 +297,7 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 				const uint32_t col = col0 + l8 * 8;
 #pragma unroll
 				for (uint32_t jj = 0; jj < 8; ++jj) {
-					pre[jj] = col < in_w ? __ldg(reinterpret_cast<const uint4*>(p.input_fp16 + (tile_row0 + g8 * 8 + jj) * in_w + col)) : make_uint4(0, 0, 0, 0);
+					pre[jj] = col < first_w ? __ldg(reinterpret_cast<const uint4*>(p.input_fp16 + (tile_row0 + g8 * 8 + jj) * first_w + col)) : make_uint4(0, 0, 0, 0);
 				}
 			} else {
 				// Identity encoding (identity.h:46-67): the first n_input_dims features are the inputs, the padding features are ONE.
@@ -322,7 +334,7 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 				if (p.input_fp16) transpose8x8_u128(pre, lane);
 #pragma unroll
 				for (uint32_t q = 0; q < 4; ++q) {  // 16 columns of fp16 = 8 TMEM columns per store
-					if (col0 + q * 16 < in_w) {
+					if (col0 + q * 16 < first_w) {
 						const uint32_t v[8] = {pre[2 * q].x, pre[2 * q].y, pre[2 * q].z, pre[2 * q].w, pre[2 * q + 1].x, pre[2 * q + 1].y, pre[2 * q + 1].z, pre[2 * q + 1].w};
 						tmem_st_n<8>(a0 + q * 8, v);
 					}
@@ -333,9 +345,43 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 			__syncwarp();
 			if (lane == 0) mbar_arrive_plain(bar_a_ready + 8 * s);
 
-			for (uint32_t l = 0; l <= NH; ++l) {
+			for (uint32_t l = 0; l < n_layers; ++l) {
 				// the next tile's input travels while the last layer computes
-				if (l == NH && j + C::SLOTS < n_my) load_input(blockIdx.x + (j + C::SLOTS) * gridDim.x);
+				if (l == n_layers - 1 && j + C::SLOTS < n_my) load_input(blockIdx.x + (j + C::SLOTS) * gridDim.x);
+				// backward: the forward pass's activations of the layer this step lands on (hidden layer NH - 1 - l), fetched BEFORE the
+				// wait so that the load travels while the MMA runs. ReLU only needs the signs: two bits per fp16 pair.
+				constexpr uint32_t FWD_WORDS = BWD ? (GENERIC_ACT ? C::GROUP_COLS / 2 : 2) : 1;
+				uint32_t fwd[FWD_WORDS];
+				if (BWD && l < NH) {
+					const uint4* src = reinterpret_cast<const uint4*>(p.hidden_in + ((size_t)(NH - 1 - l) * p.batch_size + sample) * W + col0);
+					if (!GENERIC_ACT) fwd[0] = fwd[FWD_WORDS - 1] = 0;
+#pragma unroll
+					for (uint32_t i = 0; i < C::GROUP_COLS / 8; ++i) {
+						const uint4 v = __ldg(src + i);
+						const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+						for (uint32_t c = 0; c < 4; ++c) {
+							if (GENERIC_ACT) {
+								fwd[(4 * i + c) % FWD_WORDS] = w4[c];
+							} else {
+								// positive fp16: sign clear and not zero
+								const uint32_t lo_pos = ((w4[c] & 0x8000u) == 0 && (w4[c] & 0x7FFFu) != 0) ? 1u : 0u;
+								const uint32_t hi_pos = ((w4[c] & 0x80000000u) == 0 && (w4[c] & 0x7FFF0000u) != 0) ? 2u : 0u;
+								fwd[((4 * i + c) / 16) % FWD_WORDS] |= (lo_pos | hi_pos) << (2 * ((4 * i + c) % 16));
+							}
+						}
+					}
+				}
+				// fp32 accumulator pair `idx` of this thread's columns -> packed fp16 pair after the (derivative of the) activation
+				auto convert = [&](uint32_t idx, uint32_t lo_bits, uint32_t hi_bits) -> uint32_t {
+					if (!BWD) return act_pack(hid_act, lo_bits, hi_bits);
+					if (GENERIC_ACT) return act_bwd_pack(hid_act, lo_bits, hi_bits, fwd[idx % FWD_WORDS]);
+					const uint32_t b = (fwd[(idx / 16) % FWD_WORDS] >> (2 * (idx % 16))) & 3u;
+					__half2 g = __floats2half2_rn(__uint_as_float(lo_bits), __uint_as_float(hi_bits));
+					const uint32_t m = ((b & 1u) ? 0x3C00u : 0u) | ((b & 2u) ? 0x3C000000u : 0u);  // (forward > 0) as 1.0 / 0.0, common_device.h:363-368
+					g = __hmul2(g, *reinterpret_cast<const __half2*>(&m));
+					return *reinterpret_cast<const uint32_t*>(&g);
+				};
 				const uint32_t ev = (j / C::SLOTS) * n_layers + l;
 				if (stamp) MLPF_STAMP(1 + s, ev, 0);
 				mbar_wait(bar_acc_ready + 8 * s, acc_par);
@@ -355,7 +401,7 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 					auto store_piece = [&](uint32_t k, const uint32_t (&h)[C::PIECE / 2]) {
 						tmem_st_n<C::PIECE / 2>(acc + (col0 + k * C::PIECE) / 2, h);
 						if (p.hidden_out) {
-							uint4* dst = reinterpret_cast<uint4*>(p.hidden_out + ((size_t)l * p.batch_size + sample) * W + col0 + k * C::PIECE);
+							uint4* dst = reinterpret_cast<uint4*>(p.hidden_out + ((size_t)(BWD ? NH - 1 - l : l) * p.batch_size + sample) * W + col0 + k * C::PIECE);
 #pragma unroll
 							for (uint32_t i = 0; i < C::PIECE / 8; ++i) dst[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
 						}
@@ -368,7 +414,7 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 							tmem_ld_wait();
 							if (C::GROUPS > 1 && k == C::N_PIECES - 1) asm volatile("bar.arrive %0, %1;" ::"r"(1u + s), "r"(C::SLOT_WARPS * 32u) : "memory");
 #pragma unroll
-							for (uint32_t i = 0; i < C::PIECE / 2; ++i) h[i] = act_pack(hid_act, r[2 * i], r[2 * i + 1]);
+							for (uint32_t i = 0; i < C::PIECE / 2; ++i) h[i] = convert(k * (C::PIECE / 2) + i, r[2 * i], r[2 * i + 1]);
 							store_piece(k, h);
 						}
 						if (stamp) MLPF_STAMP(1 + s, ev, 2);
@@ -380,7 +426,7 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 							tmem_ld_n<C::PIECE>(acc + col0 + k * C::PIECE, r);
 							tmem_ld_wait();
 #pragma unroll
-							for (uint32_t i = 0; i < C::PIECE / 2; ++i) h[k][i] = act_pack(hid_act, r[2 * i], r[2 * i + 1]);
+							for (uint32_t i = 0; i < C::PIECE / 2; ++i) h[k][i] = convert(k * (C::PIECE / 2) + i, r[2 * i], r[2 * i + 1]);
 						}
 						asm volatile("bar.sync %0, %1;" ::"r"(1u + s), "r"(C::SLOT_WARPS * 32u) : "memory");
 #pragma unroll
@@ -415,24 +461,25 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 							}
 						}
 					};
-					const uint32_t c16_begin = col0 / 16, c16_end = (col0 + C::GROUP_COLS) / 16;  // this group's 16-column groups
+					// this group's 16-column groups (one group per slot: all of the row -- dL/d(input) may be wider than the layers)
+					const uint32_t c16_begin = col0 / 16, c16_end = C::GROUPS == 1 ? (last_w + 15) / 16 : (col0 + C::GROUP_COLS) / 16;
 					uint32_t c16 = c16_begin;
-					if (C::GROUP_COLS == 64 && (c16 + 4) * 16 <= out_w) {
+					if (C::GROUP_COLS == 64 && (c16 + 4) * 16 <= last_w) {
 						uint4 o[8];
 #pragma unroll
 						for (uint32_t q = 0; q < 4; ++q) convert16(c16 + q, o[2 * q], o[2 * q + 1]);
 						if (p.output_fp16) {
 							transpose8x8_u128(o, lane);
 #pragma unroll
-							for (uint32_t jj = 0; jj < 8; ++jj) *reinterpret_cast<uint4*>(p.output_fp16 + (tile_row0 + g8 * 8 + jj) * out_w + c16 * 16 + l8 * 8) = o[jj];
+							for (uint32_t jj = 0; jj < 8; ++jj) *reinterpret_cast<uint4*>(p.output_fp16 + (tile_row0 + g8 * 8 + jj) * last_w + c16 * 16 + l8 * 8) = o[jj];
 						}
 						c16 += 4;
 					}
-					for (; c16 < c16_end && c16 * 16 < out_w; ++c16) {
+					for (; c16 < c16_end && c16 * 16 < last_w; ++c16) {
 						uint4 lo, hi;
 						convert16(c16, lo, hi);
 						if (p.output_fp16) {
-							uint4* dst = reinterpret_cast<uint4*>(p.output_fp16 + sample * out_w + c16 * 16);
+							uint4* dst = reinterpret_cast<uint4*>(p.output_fp16 + sample * last_w + c16 * 16);
 							dst[0] = lo;
 							dst[1] = hi;
 						}
@@ -454,56 +501,32 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 // ------------------------------------------------------------------------------------------------------------------ host side
 namespace {
 
-using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_tiled_fn() {
-	static EncodeTiledFn fn = [] {
-		void* f = nullptr;
-		cudaDriverEntryPointQueryResult q;
-		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
-		return (EncodeTiledFn)f;
-	}();
-	return fn;
-}
-
-// fp16 matrix [rows][cols] row-major -> 2-D tensor map with a box of 64 columns x box_rows rows, SWIZZLE_128B, zero fill outside.
-bool make_weight_map(CUtensorMap* map, const __half* base, uint32_t rows, uint32_t cols, uint32_t box_rows) {
-	EncodeTiledFn fn = encode_tiled_fn();
-	if (!fn) return false;
-	const cuuint64_t dims[2] = {cols, rows};
-	const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(__half)};
-	const cuuint32_t box[2] = {64, box_rows};
-	const cuuint32_t elem[2] = {1, 1};
-	return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-	          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <uint32_t W>
 uint32_t max_stages() {
 	return (uint32_t)((227u * 1024u - 1024u) / MlpCfg<W>::STAGE_BYTES) < MLPF_MAX_STAGES ? (uint32_t)((227u * 1024u - 1024u) / MlpCfg<W>::STAGE_BYTES) : MLPF_MAX_STAGES;
 }
 
-template <uint32_t W, bool GENERIC>
+template <uint32_t W, bool GENERIC, bool BWD>
 cudaError_t launch_impl(const MlpForwardParams& p, uint32_t n_sms, cudaStream_t stream) {
 	using C = MlpCfg<W>;
-	const uint32_t n_layers = p.n_hidden_layers + 1;
+	const uint32_t n_layers = p.n_hidden_layers + ((BWD && !p.output_fp16) ? 0 : 1);  // steps of the chain
 	MlpKernelParams kp{};
 	kp.p = p;
+	kp.n_steps = n_layers;
 	kp.resident = n_layers <= max_stages<W>() ? 1 : 0;
 	kp.n_stages = kp.resident ? n_layers : max_stages<W>();
 	CUtensorMap m0, mh, mo;
 	const __half* w = p.weights;
-	if (!make_weight_map(&m0, w, W, p.in_width, W)) return cudaErrorInvalidValue;
+	if (!make_fp16_matrix_map(&m0, w, W, p.in_width, W)) return cudaErrorInvalidValue;
 	w += (size_t)W * p.in_width;
 	if (p.n_hidden_layers > 1) {
-		if (!make_weight_map(&mh, w, (p.n_hidden_layers - 1) * W, W, W)) return cudaErrorInvalidValue;
+		if (!make_fp16_matrix_map(&mh, w, (p.n_hidden_layers - 1) * W, W, W)) return cudaErrorInvalidValue;
 	} else {
 		mh = m0;  // never used
 	}
 	w += (size_t)(p.n_hidden_layers - 1) * W * W;
-	if (!make_weight_map(&mo, w, p.out_width, W, p.out_width)) return cudaErrorInvalidValue;
-	auto kernel = mlp_forward_kernel<W, GENERIC>;
+	if (!make_fp16_matrix_map(&mo, w, p.out_width, W, p.out_width)) return cudaErrorInvalidValue;
+	auto kernel = mlp_forward_kernel<W, GENERIC, BWD>;
 	const size_t smem = (size_t)kp.n_stages * C::STAGE_BYTES + 8 * (2 * MLPF_MAX_STAGES + 8) + 16;
 	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (err != cudaSuccess) return err;
@@ -513,8 +536,9 @@ cudaError_t launch_impl(const MlpForwardParams& p, uint32_t n_sms, cudaStream_t 
 
 template <uint32_t W>
 cudaError_t launch_width(const MlpForwardParams& p, uint32_t n_sms, cudaStream_t stream) {
+	if (p.backward) return p.activation != ACT_RELU ? launch_impl<W, true, true>(p, n_sms, stream) : launch_impl<W, false, true>(p, n_sms, stream);
 	const bool generic = p.activation != ACT_RELU || p.output_activation != ACT_NONE;
-	return generic ? launch_impl<W, true>(p, n_sms, stream) : launch_impl<W, false>(p, n_sms, stream);
+	return generic ? launch_impl<W, true, false>(p, n_sms, stream) : launch_impl<W, false, false>(p, n_sms, stream);
 }
 
 }  // namespace
@@ -541,6 +565,10 @@ bool mlp_forward_supported(const MlpForwardParams& p, const char** why) {
 	if (p.out_width == 0 || p.out_width % 16 != 0 || p.out_width > p.width) return fail("tcnn_b200: padded network output width must be a multiple of 16 and at most n_neurons");
 	if (p.batch_size == 0 || p.batch_size % TILE_M != 0) return fail("batch size must be a non-zero multiple of 256");
 	if ((p.input_fp16 != nullptr) == (p.input_fp32 != nullptr)) return fail("tcnn_b200: exactly one network input must be given");
+	if (p.backward) {
+		if (!p.input_fp16 || !p.hidden_in || p.output_fp32) return fail("tcnn_b200: the backward chain needs dL/d(output) and the forward activations in fp16");
+		if (p.output_fp16 && p.in_width > (p.width < 32 ? 32u : p.width)) return fail("tcnn_b200: dL/d(input) of the stand-alone network covers inputs up to max(n_neurons, 32) wide");
+	}
 	if (p.input_fp32 && (p.n_input_dims == 0 || p.n_input_dims > p.in_width)) return fail("tcnn_b200: Identity encoding wider than the network input");
 	return true;
 }

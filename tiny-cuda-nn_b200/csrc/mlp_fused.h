@@ -26,6 +26,13 @@ struct MlpForwardParams {
 	uint32_t n_output_dims;
 	// optional: post-activation hidden layers [n_hidden_layers][batch][width] fp16 (forward pass kept for a backward pass)
 	__half* hidden_out;
+	// backward chain (Network<T>::backward's dgrad half, fully_fused_mlp.cu:733-800): with `backward` set,
+	//   input_fp16  = dL/d(output) [batch][out_width], already multiplied by the output activation's derivative,
+	//   hidden_in   = the forward pass's `hidden_out`,
+	//   hidden_out  = g_l = dL/d(pre-activation of hidden layer l) [n_hidden_layers][batch][width] (may be null),
+	//   output_fp16 = dL/d(input) [batch][in_width] (may be null: the last step of the chain is then skipped).
+	uint32_t backward;
+	const __half* hidden_in;
 	// profiling only (scripts/mlp_timeline.py): clock64 stamps [cta][slot + 1 (0 = issuer)][64 events][8], null in production
 	long long* dbg_clock;
 };
@@ -34,5 +41,37 @@ struct MlpForwardParams {
 uint32_t mlp_forward_resident_layers(uint32_t width);
 bool mlp_forward_supported(const MlpForwardParams& p, const char** why);
 cudaError_t launch_mlp_forward(const MlpForwardParams& p, uint32_t n_sms, cudaStream_t stream);
+
+// ---- weight gradients of the stand-alone network (mlp_wgrad.cu) ------------------------------------------------------------
+struct MlpWgradParams {
+	uint32_t width, in_width, out_width, n_hidden_layers;
+	uint32_t batch_size;          // multiple of 128
+	const __half* input;          // [batch][in_width]                   the network input of the forward pass
+	const __half* hidden;         // [n_hidden_layers][batch][width]     forward activations (mlp forward `hidden_out`)
+	const __half* grad_hidden;    // [n_hidden_layers][batch][width]     g_l (backward chain `hidden_out`)
+	const __half* grad_output;    // [batch][out_width]                  dL/d(output) through the output activation's transfer
+	float* dw_accum;              // fp32 sums in parameter order, ADDED into (red.global.add.f32): the caller zeroes them
+};
+// dW_l += g_l^T . h_{l-1} for every weight matrix (the reference's split-k GEMMs, fully_fused_mlp.cu:802-866).
+bool mlp_wgrad_supported(const MlpWgradParams& p, const char** why);
+cudaError_t launch_mlp_wgrad(const MlpWgradParams& p, uint32_t n_sms, cudaStream_t stream);
+
+
+// ---- the whole backward pass of the stand-alone network: [output activation backward] -> dgrad chain -> weight gradients ------
+struct MlpBackwardArgs {
+	uint32_t width, in_width, out_width, n_hidden_layers, activation, output_activation;
+	const __half* weights;
+	uint32_t batch_size;
+	const __half* input;          // [batch][in_width] forward input (weight gradients of the first matrix); may be null if dw_accum is
+	const __half* hidden;         // [n_hidden_layers][batch][width] forward activations
+	const __half* output;         // [batch][out_width] forward output; only read when output_activation != None
+	const __half* dL_doutput;     // [batch][out_width]
+	__half* grad_hidden;          // scratch [n_hidden_layers][batch][width]
+	__half* grad_output;          // scratch [batch][out_width]; only written when output_activation != None
+	__half* dL_dinput;            // [batch][in_width] or null
+	float* dw_accum;              // fp32 sums, added into; null = no weight gradients
+};
+cudaError_t launch_mlp_backward(const MlpBackwardArgs& a, uint32_t n_sms, cudaStream_t stream, uint32_t* n_launches);
+bool mlp_backward_supported(const MlpBackwardArgs& a, const char** why);
 
 }  // namespace tcnnb

@@ -11,6 +11,7 @@
 
 #include "host_common.h"
 #include "json_mini.h"
+#include "misc_kernels.h"
 #include "mlp_fused.h"
 
 #include <cmath>
@@ -29,6 +30,10 @@ struct Network {
 	int n_sms = 148;
 	long long* dbg_clock = nullptr;  // profiling only (tcnnb_network_debug_clocks)
 	std::string otype, hyperparams_json;
+	// scratch of the backward pass (grown on demand, reused): g_l rows, dL/d(output) through the output activation, fp32 weight-gradient
+	// sums, and -- module tier, fp32 inputs -- the Identity-encoded input rows, the recomputed activations and dL/d(encoded input)
+	DeviceBuffer<__half> grad_hidden, grad_output, enc_input, hidden, output, grad_input;
+	DeviceBuffer<float> dw_accum;
 };
 
 static void build_network(Network& n, uint32_t n_in, uint32_t n_out, const json::Value& net) {
@@ -98,6 +103,58 @@ static void launch(const Network& n, const MlpForwardParams& p, cudaStream_t str
 	if (!mlp_forward_supported(p, &why)) throw std::runtime_error(why);
 	TCNNB_CUDA_CHECK(launch_mlp_forward(p, (uint32_t)n.n_sms, stream));
 	++g_kernel_launches;
+}
+
+template <typename T>
+static void grow(DeviceBuffer<T>& b, size_t n) {
+	if (b.n < n) b.resize(n);
+}
+
+// Network<T>::backward (fully_fused_mlp.cu:733-866): dL/d(input) (fp16 rows, optional) and dL/d(params) (fp16, OVERWRITTEN, optional)
+// from the forward pass's input, activations and output.
+static void network_backward(Network& n, cudaStream_t stream, uint32_t batch, const __half* input, const __half* output, const __half* hidden, const __half* dL_doutput,
+                             const void* params, __half* dL_dinput, __half* dL_dparams) {
+	if (!dL_dinput && !dL_dparams) return;
+	MlpForwardParams probe = make_params(n, batch, params);  // validates batch / params
+	(void)probe;
+	if (!input || !hidden || !dL_doutput) throw std::runtime_error("network: backward needs the forward pass's input and hidden activations and dL_doutput.");
+	if (n.output_activation != ACT_NONE && !output) throw std::runtime_error("network: backward through an output activation needs the forward pass's output.");
+	MlpBackwardArgs a{};
+	a.width = n.width;
+	a.in_width = n.in_width;
+	a.out_width = n.padded_out_width;
+	a.n_hidden_layers = n.n_hidden_layers;
+	a.activation = n.activation;
+	a.output_activation = n.output_activation;
+	a.weights = (const __half*)params;
+	a.batch_size = batch;
+	a.input = input;
+	a.hidden = hidden;
+	a.output = output;
+	a.dL_doutput = dL_doutput;
+	a.dL_dinput = dL_dinput;
+	if (dL_dparams) {
+		grow(n.grad_hidden, (size_t)n.n_hidden_layers * batch * n.width);
+		a.grad_hidden = n.grad_hidden.ptr;
+		if (n.dw_accum.n != n.n_params) {
+			n.dw_accum.resize(n.n_params);
+			n.dw_accum.zero(stream);  // launch_mlp_grad_finalize re-zeroes it after every use
+		}
+		a.dw_accum = n.dw_accum.ptr;
+	}
+	if (n.output_activation != ACT_NONE) {
+		grow(n.grad_output, (size_t)batch * n.padded_out_width);
+		a.grad_output = n.grad_output.ptr;
+	}
+	const char* why = nullptr;
+	if (!mlp_backward_supported(a, &why)) throw std::runtime_error(why);
+	uint32_t launches = 0;
+	TCNNB_CUDA_CHECK(launch_mlp_backward(a, (uint32_t)n.n_sms, stream, &launches));
+	if (dL_dparams) {
+		TCNNB_CUDA_CHECK(launch_mlp_grad_finalize(stream, (uint32_t)n.n_params, n.dw_accum.ptr, dL_dparams));
+		++launches;
+	}
+	g_kernel_launches += launches;
 }
 
 }  // namespace tcnnb
@@ -178,6 +235,52 @@ int tcnnb_network_forward(tcnnb_network* n, tcnnb_stream stream, uint32_t n_elem
 	p.output_fp16 = (__half*)output_dev;
 	p.hidden_out = (__half*)hidden_dev;
 	launch(net, p, (cudaStream_t)stream);
+	TCNNB_API_END
+}
+
+int tcnnb_network_backward(tcnnb_network* n, tcnnb_stream stream, uint32_t n_elements, const void* input_dev, const void* output_dev, const void* hidden_dev, const void* dL_doutput_dev,
+                           const void* params_dev, void* dL_dinput_dev, void* dL_dparams_dev) {
+	TCNNB_API_BEGIN
+	Network& net = n->impl;
+	if (net.n_input_dims != net.in_width) throw std::runtime_error("network: fp16 inputs need n_input_dims to be a multiple of 16.");
+	if (((uintptr_t)input_dev | (uintptr_t)output_dev | (uintptr_t)hidden_dev | (uintptr_t)dL_doutput_dev | (uintptr_t)dL_dinput_dev | (uintptr_t)dL_dparams_dev) % 16 != 0) {
+		throw std::runtime_error("network: all arrays must be 16-byte aligned.");
+	}
+	network_backward(net, (cudaStream_t)stream, n_elements, (const __half*)input_dev, (const __half*)output_dev, (const __half*)hidden_dev, (const __half*)dL_doutput_dev, params_dev,
+	                 (__half*)dL_dinput_dev, (__half*)dL_dparams_dev);
+	TCNNB_API_END
+}
+
+// cpp::Module::backward of cpp::create_network (src/cpp_api.cu:104-125 with the Identity encoding in front): fp32 inputs; nothing is
+// kept from the forward call -- the activations are recomputed here (one more forward pass, no context to hold between the calls).
+int tcnnb_network_module_backward(tcnnb_network* n, tcnnb_stream stream_, uint32_t n_elements, float* dL_dinput_dev, const void* dL_doutput_dev, void* dL_dparams_dev, const float* input_dev,
+                                  const void* params_dev) {
+	TCNNB_API_BEGIN
+	Network& net = n->impl;
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (!dL_dinput_dev && !dL_dparams_dev) return 0;
+	if (!input_dev || !dL_doutput_dev) throw std::runtime_error("network: input / dL_doutput is null.");
+	if (((uintptr_t)dL_doutput_dev | (uintptr_t)dL_dparams_dev) % 16 != 0) throw std::runtime_error("network: dL_doutput / dL_dparams must be 16-byte aligned.");
+	MlpForwardParams p = make_params(net, n_elements, params_dev);
+	grow(net.enc_input, (size_t)n_elements * net.in_width);
+	grow(net.hidden, (size_t)net.n_hidden_layers * n_elements * net.width);
+	grow(net.output, (size_t)n_elements * net.padded_out_width);
+	TCNNB_CUDA_CHECK(launch_identity_encode(stream, n_elements, net.n_input_dims, net.in_width, 1.0f, 0.0f, input_dev, net.enc_input.ptr));
+	++g_kernel_launches;
+	p.input_fp16 = net.enc_input.ptr;
+	p.output_fp16 = net.output.ptr;
+	p.hidden_out = net.hidden.ptr;
+	launch(net, p, stream);
+	__half* dL_denc = nullptr;
+	if (dL_dinput_dev) {
+		grow(net.grad_input, (size_t)n_elements * net.in_width);
+		dL_denc = net.grad_input.ptr;
+	}
+	network_backward(net, stream, n_elements, net.enc_input.ptr, net.output.ptr, net.hidden.ptr, (const __half*)dL_doutput_dev, params_dev, dL_denc, (__half*)dL_dparams_dev);
+	if (dL_dinput_dev) {
+		TCNNB_CUDA_CHECK(launch_identity_backward(stream, n_elements, net.n_input_dims, net.in_width, 1.0f, dL_denc, dL_dinput_dev));
+		++g_kernel_launches;
+	}
 	TCNNB_API_END
 }
 
