@@ -159,6 +159,16 @@ int tcnnb_network_inference_mixed_precision(tcnnb_network* n, tcnnb_stream strea
 /* network->forward: the same, and the post-activation hidden layers fp16 [n_hidden_layers][n][n_neurons] are written out
  * (what the reference's ForwardContext holds, fully_fused_mlp.cu:841-854). output_dev may be null. */
 int tcnnb_network_forward(tcnnb_network* n, tcnnb_stream stream, uint32_t n_elements, const void* input_dev, void* output_dev, void* hidden_dev, const void* params_dev);
+/* network->backward (Network<T>::backward, fully_fused_mlp.cu:733-866) from what tcnnb_network_forward was given and wrote:
+ * dL_doutput fp16 [n][padded_output_width] -> dL_dinput fp16 [n][n_input_dims] and dL_dparams fp16 [n_params] (OVERWRITTEN);
+ * either may be null. output_dev is only read when the network has an output activation. Three kernels: the dgrad chain on
+ * tcgen05 with the transposed weights read in place (mlp_fused.cu, BWD), the weight-gradient kernel (mlp_wgrad.cu), fp32 -> fp16. */
+int tcnnb_network_backward(tcnnb_network* n, tcnnb_stream stream, uint32_t n_elements, const void* input_dev, const void* output_dev, const void* hidden_dev,
+                           const void* dL_doutput_dev, const void* params_dev, void* dL_dinput_dev, void* dL_dparams_dev);
+/* tcnn::cpp::Module::backward of cpp::create_network (cpp_api.cu:104-125): fp32 input through the Identity encoding; nothing is kept
+ * from the forward call (the activations are recomputed). dL_dinput fp32 [n][n_input_dims], dL_dparams fp16; either may be null. */
+int tcnnb_network_module_backward(tcnnb_network* n, tcnnb_stream stream, uint32_t n_elements, float* dL_dinput_dev, const void* dL_doutput_dev, void* dL_dparams_dev,
+                                  const float* input_dev, const void* params_dev);
 /* cpp::create_network semantics: fp32 input [n][n_input_dims] through the Identity encoding (padding features are 1,
  * encodings/identity.h:62-66) -> fp32 output [n][n_output_dims] (object.h:214-282). */
 int tcnnb_network_inference(tcnnb_network* n, tcnnb_stream stream, uint32_t n_elements, const float* input_dev, float* output_dev, const void* params_dev);

@@ -19,6 +19,7 @@
 #include "host_common.h"
 #include "json_mini.h"
 #include "misc_kernels.h"
+#include "mlp_fused.h"
 
 #include <dlfcn.h>
 #include <nccl.h>  // types and prototypes only: libnccl is resolved at run time (dlopen), single-GPU users never need it
@@ -155,6 +156,13 @@ struct Model {
 	DeviceBuffer<__half> denc_scratch;      // module tier: dL/d(encoded) rows [n][64] handed from the fused kernel to the input-gradient kernel
 	DeviceBuffer<__half> grads_scratch;     // module tier: gradient array when the caller wants dL/d(input) only
 	bool mlp_grads_in_accum = false;
+	// General (unfused) path: configurations the fused kernel does not cover -- 128 neurons, n_features_per_level in {1, 4, 8}, 4-D
+	// inputs, Nearest interpolation, wider encodings / outputs -- run as encoding kernel -> stand-alone MLP kernels -> encoding backward
+	// kernel, with the activations of one batch in HBM (the reference's own structure, object.h / network_with_input_encoding.h).
+	bool general = false;
+	std::string general_reason;  // which limit of the fused kernel sent this configuration here (hyperparams / diagnostics)
+	DeviceBuffer<__half> g_enc, g_hidden, g_out, g_dy, g_grad_hidden, g_denc, g_dy_act;
+	DeviceBuffer<float> g_grid_tmp;  // n_features_per_level == 1: fp32 scatter target (grid.h:858-894)
 
 	// spatial binning scratch (binning.cu): sorted copies of the batch + permutation
 	bool binning = true;  // tcnnb_debug_set("binning", 0) (tests: binned and unbinned steps must touch the same entries)
@@ -360,7 +368,6 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 		m.grid.n_params = 0;
 		m.grid.offsets.assign(1, 0u);
 		m.grid.padded_width = next_multiple(n_in, alignment);
-		if (n_in != 2 && n_in != 3) throw std::runtime_error("tcnn_b200: the Identity encoding on the fused path covers 2-D and 3-D inputs");
 	} else {
 		m.grid = parse_grid(n_in, enc_cfg);
 		m.grid.padded_width = next_multiple(m.grid.n_levels * m.grid.n_features_per_level, alignment);
@@ -371,22 +378,42 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 	mlp.padded_out_width = next_multiple(n_out, 16u);
 	mlp.n_params = mlp.width * mlp.in_width + (mlp.n_hidden_layers - 1) * mlp.width * mlp.width + mlp.padded_out_width * mlp.width;
 
-	// ---- what the sm_100a kernels of this round cover; everything else fails loudly (no fallback by design)
-	if (mlp.width > 64) throw std::runtime_error("tcnn_b200: the tcgen05 fused path currently covers n_neurons <= 64 (got " + std::to_string(mlp.width) + "); 128-wide layers are the next row");
-	if (mlp.n_hidden_layers > 6) throw std::runtime_error("tcnn_b200: the fused path keeps all hidden activations on chip and covers n_hidden_layers <= 6");
+	// ---- which kernels run this configuration. The fused kernel (fused_ws.cu) covers the benchmarked family; everything else the
+	// stand-alone kernels cover takes the general path; the rest fails loudly (no fallback to anything that is not a kernel of this library).
 	// FullyFusedMLP's activation set (fully_fused_mlp.cu:689-699): Sine and SiLU need stored pre-activations and are rejected there too.
 	for (uint32_t act : {mlp.activation, mlp.output_activation}) {
 		if (act == ACT_SINE || act == ACT_SILU) throw std::runtime_error("Unsupported activation.");
 	}
-	if (mlp.padded_out_width != 16) throw std::runtime_error("tcnn_b200: fused path covers n_output_dims <= 16");
-	if (m.grid.n_features_per_level != 2) throw std::runtime_error("tcnn_b200: fused path covers n_features_per_level == 2");
-	if (m.grid.n_pos_dims != 2 && m.grid.n_pos_dims != 3) throw std::runtime_error("tcnn_b200: fused path covers 2-D and 3-D inputs");
-	if (m.grid.padded_width > 64 || m.grid.n_levels > MAX_LEVELS) throw std::runtime_error("tcnn_b200: fused path covers encodings up to 64 features");
-	if (fused_ws_smem_bytes(mlp.n_hidden_layers, m.grid.padded_width, true) > 227 * 1024) {
-		throw std::runtime_error("tcnn_b200: this network depth / encoding width does not fit the SM's shared memory on the fused path");
-	}
-	if (m.grid.interpolation == INTERP_NEAREST) throw std::runtime_error("tcnn_b200: fused path covers Linear and Smoothstep interpolation");
 	if (m.grid.stochastic_interpolation) throw std::runtime_error("tcnn_b200: stochastic_interpolation is not built");
+	{
+		const char* why = nullptr;
+		if (mlp.width > 64) why = "n_neurons > 64";
+		else if (mlp.n_hidden_layers > 6) why = "n_hidden_layers > 6";
+		else if (mlp.padded_out_width != 16) why = "more than 16 outputs";
+		else if (!m.enc_identity && m.grid.n_features_per_level != 2) why = "n_features_per_level != 2";
+		else if (m.grid.n_pos_dims != 2 && m.grid.n_pos_dims != 3) why = "input dimensions other than 2 / 3";
+		else if (m.grid.padded_width > 64 || m.grid.n_levels > MAX_LEVELS) why = "encoding wider than 64 features";
+		else if (fused_ws_smem_bytes(mlp.n_hidden_layers, m.grid.padded_width, true) > 227 * 1024) why = "shared-memory footprint of this depth / encoding width";
+		else if (!m.enc_identity && m.grid.interpolation == INTERP_NEAREST) why = "Nearest interpolation";
+		if (why) {
+			m.general = true;
+			m.general_reason = why;
+			MlpBackwardArgs probe{};
+			probe.width = mlp.width;
+			probe.in_width = mlp.in_width;
+			probe.out_width = mlp.padded_out_width;
+			probe.n_hidden_layers = mlp.n_hidden_layers;
+			probe.batch_size = 256;
+			probe.dL_dinput = m.enc_identity ? nullptr : (__half*)16;  // the encoding's backward pass needs dL/d(encoded)
+			const char* why_not = nullptr;
+			if (!mlp_backward_supported(probe, &why_not)) throw std::runtime_error(std::string(why_not) + " (general path of tcnn_b200; the fused kernel does not cover this configuration: " + why + ")");
+			if (!m.enc_identity) {
+				const uint32_t F = m.grid.n_features_per_level, D = m.grid.n_pos_dims;
+				if (!(F == 1 || F == 2 || F == 4 || F == 8)) throw std::runtime_error("GridEncoding: n_features_per_level must be 1, 2, 4, or 8.");
+				if (D < 2 || D > 4) throw std::runtime_error("tcnn_b200: grid encodings cover 2, 3 and 4 input dimensions");
+			}
+		}
+	}
 
 	// ---- per-level scales, evaluated on the device like the reference's kernels (common_device.h:886-891)
 	m.level_scales_dev.resize(128);
@@ -527,6 +554,151 @@ static void optimizer_step(Model& m, cudaStream_t stream, uint32_t n_ranges = 0,
 	if (covers_mlp) m.mlp_grads_in_accum = false;
 }
 
+static void ensure_levels_dev(Model& m, cudaStream_t stream) {
+	if (m.levels_dev.n == 0 && m.grid.n_levels) {
+		std::vector<LevelInfo> levels(m.grid.n_levels);
+		for (uint32_t l = 0; l < m.grid.n_levels; ++l) levels[l] = make_level_info(m.grid, l);
+		m.levels_dev.resize(levels.size());
+		TCNNB_CUDA_CHECK(cudaMemcpyAsync(m.levels_dev.ptr, levels.data(), sizeof(LevelInfo) * levels.size(), cudaMemcpyHostToDevice, stream));
+		TCNNB_CUDA_CHECK(cudaStreamSynchronize(stream));  // `levels` is a pageable temporary
+	}
+}
+
+static GridKernelArgs grid_kernel_args(Model& m, uint32_t n, const float* x, uint32_t row_stride) {
+	GridKernelArgs a{};
+	a.n_pos_dims = m.grid.n_pos_dims;
+	a.n_features_per_level = m.grid.n_features_per_level;
+	a.n_levels = m.grid.n_levels;
+	a.interpolation = m.grid.interpolation;
+	a.max_level = 1.0f;
+	a.levels_dev = m.levels_dev.ptr;
+	a.n_elements = n;
+	a.positions = x;
+	a.row_stride = row_stride;
+	return a;
+}
+
+template <typename T>
+static void grow(DeviceBuffer<T>& b, size_t n) {
+	if (b.n < n) b.resize(n);
+}
+
+// ---- general path: encoding kernel -> stand-alone network kernel (mlp_fused.cu), activations optionally kept for the backward pass
+static void general_forward(Model& m, cudaStream_t stream, uint32_t batch, const float* x, const __half* params, __half* out_fp16, float* out_fp32, bool keep_hidden) {
+	const MlpConfig& mlp = m.mlp;
+	grow(m.g_enc, (size_t)batch * mlp.in_width);
+	if (m.enc_identity) {
+		TCNNB_CUDA_CHECK(launch_identity_encode(stream, batch, m.n_in, mlp.in_width, m.identity_scale, m.identity_offset, x, m.g_enc.ptr));
+	} else {
+		ensure_levels_dev(m, stream);
+		TCNNB_CUDA_CHECK(launch_grid_forward(stream, grid_kernel_args(m, batch, x, mlp.in_width), params + mlp.n_params, m.g_enc.ptr));
+	}
+	MlpForwardParams p{};
+	p.width = mlp.width;
+	p.in_width = mlp.in_width;
+	p.out_width = mlp.padded_out_width;
+	p.n_hidden_layers = mlp.n_hidden_layers;
+	p.activation = mlp.activation;
+	p.output_activation = mlp.output_activation;
+	p.weights = params;
+	p.batch_size = batch;
+	p.input_fp16 = m.g_enc.ptr;
+	p.n_output_dims = m.n_out;
+	p.output_fp16 = out_fp16;
+	p.output_fp32 = out_fp32;
+	if (keep_hidden) {
+		grow(m.g_hidden, (size_t)mlp.n_hidden_layers * batch * mlp.width);
+		p.hidden_out = m.g_hidden.ptr;
+	}
+	const char* why = nullptr;
+	if (!mlp_forward_supported(p, &why)) throw std::runtime_error(why);
+	TCNNB_CUDA_CHECK(launch_mlp_forward(p, (uint32_t)m.n_sms, stream));
+	g_kernel_launches += 2;
+	m.last_stream = stream;
+}
+
+// Forward + loss (or the caller's dL/d(output)) + backward on the general path. Gradients land where the fused kernel leaves them:
+// fp32 network weight-gradient sums in dw_accum, fp16 table gradients in grads + n_mlp_params. `dL_dinput` (fp32 [batch][n_in]) optional.
+static void general_backward_pass(Model& m, cudaStream_t stream, uint32_t batch, uint32_t loss_batch, const float* x, const float* y, const __half* params, __half* grads,
+                                  const __half* ext_dL_doutput, float* dL_dinput, bool want_param_grads) {
+	const MlpConfig& mlp = m.mlp;
+	const bool grid_params = !m.enc_identity && want_param_grads;
+	if (grid_params) {
+		TCNNB_CUDA_CHECK(cudaMemsetAsync(grads + mlp.n_params, 0, sizeof(__half) * m.grid.n_params, stream));  // GradientMode::Overwrite (grid.h:865-867)
+	}
+	if (!ext_dL_doutput) TCNNB_CUDA_CHECK(cudaMemsetAsync(m.scalars.ptr, 0, sizeof(float), stream));
+	if (m.mlp_grads_in_accum) {
+		TCNNB_CUDA_CHECK(cudaMemsetAsync(m.dw_accum.ptr, 0, sizeof(float) * mlp.n_params, stream));
+		m.mlp_grads_in_accum = false;
+	}
+	m.prof_mark(stream);
+	m.prof_mark(stream);  // (no binning pass on this path)
+	m.wait_pending(stream);
+	grow(m.g_out, (size_t)batch * mlp.padded_out_width);
+	general_forward(m, stream, batch, x, params, m.taps.output ? (__half*)m.taps.output : m.g_out.ptr, nullptr, true);
+	const __half* out = m.taps.output ? (const __half*)m.taps.output : m.g_out.ptr;
+
+	MlpBackwardArgs a{};
+	a.width = mlp.width;
+	a.in_width = mlp.in_width;
+	a.out_width = mlp.padded_out_width;
+	a.n_hidden_layers = mlp.n_hidden_layers;
+	a.activation = mlp.activation;
+	a.weights = params;
+	a.batch_size = batch;
+	a.input = m.g_enc.ptr;
+	a.hidden = m.g_hidden.ptr;
+	a.output = out;
+	if (ext_dL_doutput) {  // Module::backward: the caller's dL/d(output) still has to pass the output activation (fully_fused_mlp.cu:755-762)
+		a.output_activation = mlp.output_activation;
+		a.dL_doutput = ext_dL_doutput;
+		if (mlp.output_activation != ACT_NONE) {
+			grow(m.g_dy_act, (size_t)batch * mlp.padded_out_width);
+			a.grad_output = m.g_dy_act.ptr;
+		}
+	} else {  // Trainer: loss gradient x loss_scale, through the output activation, in one kernel
+		grow(m.g_dy, (size_t)batch * mlp.padded_out_width);
+		TCNNB_CUDA_CHECK(launch_loss(stream, m.loss_type, mlp.output_activation, batch, m.n_out, mlp.padded_out_width, m.loss_scale, loss_batch * m.n_out, out, y, m.g_dy.ptr,
+		                             m.taps.loss_values, m.scalars.ptr));
+		++g_kernel_launches;
+		a.output_activation = ACT_NONE;
+		a.dL_doutput = m.g_dy.ptr;
+	}
+	const bool need_denc = grid_params || dL_dinput;
+	if (need_denc) {
+		grow(m.g_denc, (size_t)batch * mlp.in_width);
+		a.dL_dinput = m.g_denc.ptr;
+	}
+	if (want_param_grads) {
+		grow(m.g_grad_hidden, (size_t)mlp.n_hidden_layers * batch * mlp.width);
+		a.grad_hidden = m.g_grad_hidden.ptr;
+		a.dw_accum = m.dw_accum.ptr;
+	}
+	const char* why = nullptr;
+	if (!mlp_backward_supported(a, &why)) throw std::runtime_error(why);
+	uint32_t launches = 0;
+	TCNNB_CUDA_CHECK(launch_mlp_backward(a, (uint32_t)m.n_sms, stream, &launches));
+	g_kernel_launches += launches;
+	if (want_param_grads) m.mlp_grads_in_accum = true;
+	if (grid_params) {
+		float* tmp = nullptr;
+		if (m.grid.n_features_per_level == 1) {
+			grow(m.g_grid_tmp, m.grid.n_params);
+			TCNNB_CUDA_CHECK(cudaMemsetAsync(m.g_grid_tmp.ptr, 0, sizeof(float) * m.grid.n_params, stream));
+			tmp = m.g_grid_tmp.ptr;
+		}
+		TCNNB_CUDA_CHECK(launch_grid_backward(stream, grid_kernel_args(m, batch, x, mlp.in_width), m.g_denc.ptr, grads + mlp.n_params, tmp, (uint32_t)m.grid.n_params));
+		++g_kernel_launches;
+	}
+	if (dL_dinput) {
+		if (m.enc_identity) TCNNB_CUDA_CHECK(launch_identity_backward(stream, batch, m.n_in, mlp.in_width, m.identity_scale, m.g_denc.ptr, dL_dinput));
+		else TCNNB_CUDA_CHECK(launch_grid_input_gradient(stream, grid_kernel_args(m, batch, x, mlp.in_width), params + mlp.n_params, m.g_denc.ptr, dL_dinput));
+		++g_kernel_launches;
+	}
+	m.last_stream = stream;
+	m.prof_mark(stream);
+}
+
 // `targets_ready`: optional event the fused kernel (the first consumer of `y`) waits for; everything before it in the step --
 // gradient zeroing, the binning pass -- only needs `x` and runs while the targets are still in flight.
 // Caller-owned arrays of the module tier (cpp_api.h:76-104): working-precision parameters, gradient array, dL/d(output).
@@ -541,6 +713,14 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
                           const ModuleIO* io = nullptr) {
 	check_batch(batch);
 	if (!io && m.module_only) throw std::runtime_error("this handle was created with tcnnb_module_create: use the tcnnb_module_* calls.");
+	if (m.general) {
+		if (io) throw std::runtime_error("internal: the module tier of the general path does not come through here");
+		if (targets_ready) TCNNB_CUDA_CHECK(cudaStreamWaitEvent(stream, targets_ready, 0));
+		general_backward_pass(m, stream, batch, loss_batch, x, y, m.params_fp16, m.grads_fp16, nullptr, nullptr, true);
+		if (run_optimizer) optimizer_step(m, stream);
+		m.prof_mark(stream);
+		return;
+	}
 	__half* const grads_base = io ? io->grads : m.grads_fp16;
 	// GradientMode::Overwrite: zero the grid gradient table (grid.h:865-867) and the loss accumulator -- inside the binning pass
 	// when there is one, else as memsets.
@@ -677,6 +857,10 @@ static void inference(Model& m, cudaStream_t stream, uint32_t batch, const float
 	check_batch(batch);
 	if (m.module_only) throw std::runtime_error("this handle was created with tcnnb_module_create: use the tcnnb_module_* calls.");
 	m.wait_pending(stream);
+	if (m.general) {
+		general_forward(m, stream, batch, x, m.params_fp16, nullptr, out, false);
+		return;
+	}
 	FusedStepParams p = make_params(m, batch, batch, x, nullptr);
 	p.out_fp32 = out;
 	p.loss_sum = nullptr;
@@ -696,6 +880,10 @@ static void module_forward(Model& m, cudaStream_t stream, uint32_t n, const floa
 	check_batch(n);
 	check_module_ptr(params, "params");
 	check_module_ptr(output, "output");
+	if (m.general) {
+		general_forward(m, stream, n, x, (const __half*)params, (__half*)output, nullptr, false);
+		return;
+	}
 	FusedStepParams p = make_params(m, n, n, x, nullptr);
 	p.params = (const __half*)params;
 	p.grads = nullptr;
@@ -710,6 +898,17 @@ static void module_backward(Model& m, cudaStream_t stream, uint32_t n, float* dL
 	if (!dL_dparams && !dL_dinput) return;  // nothing to compute (GradientMode::Ignore)
 	check_module_ptr(params, "params");
 	check_module_ptr(dL_doutput, "dL_doutput");
+	if (m.general) {
+		check_batch(n);
+		if (dL_dparams) check_module_ptr(dL_dparams, "dL_dparams");
+		general_backward_pass(m, stream, n, n, x, nullptr, (const __half*)params, (__half*)dL_dparams, (const __half*)dL_doutput, dL_dinput, dL_dparams != nullptr);
+		if (dL_dparams) {
+			TCNNB_CUDA_CHECK(launch_mlp_grad_finalize(stream, m.mlp.n_params, m.dw_accum.ptr, (__half*)dL_dparams));
+			++g_kernel_launches;
+			m.mlp_grads_in_accum = false;
+		}
+		return;
+	}
 	ModuleIO io;
 	io.params = (const __half*)params;
 	io.dL_doutput = (const __half*)dL_doutput;
@@ -736,13 +935,7 @@ static void module_backward(Model& m, cudaStream_t stream, uint32_t n, float* dL
 	++g_kernel_launches;
 	m.mlp_grads_in_accum = false;
 	if (dL_dinput) {
-		if (m.levels_dev.n == 0) {
-			std::vector<LevelInfo> levels(m.grid.n_levels);
-			for (uint32_t l = 0; l < m.grid.n_levels; ++l) levels[l] = make_level_info(m.grid, l);
-			m.levels_dev.resize(levels.size());
-			TCNNB_CUDA_CHECK(cudaMemcpyAsync(m.levels_dev.ptr, levels.data(), sizeof(LevelInfo) * levels.size(), cudaMemcpyHostToDevice, stream));
-			TCNNB_CUDA_CHECK(cudaStreamSynchronize(stream));  // `levels` is a pageable temporary
-		}
+		ensure_levels_dev(m, stream);
 		GridKernelArgs a{};
 		a.n_pos_dims = m.grid.n_pos_dims;
 		a.n_features_per_level = m.grid.n_features_per_level;

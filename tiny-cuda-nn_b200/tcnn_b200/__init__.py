@@ -88,6 +88,8 @@ ABI = [
     ("tcnnb_network_initialize_params", _int, [_vp, _u64, _vp, ctypes.c_float]),
     ("tcnnb_network_inference_mixed_precision", _int, [_vp, _vp, _u32, _vp, _vp, _vp]),
     ("tcnnb_network_forward", _int, [_vp, _vp, _u32, _vp, _vp, _vp, _vp]),
+    ("tcnnb_network_backward", _int, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("tcnnb_network_module_backward", _int, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
     ("tcnnb_network_inference", _int, [_vp, _vp, _u32, _vp, _vp, _vp]),
     ("tcnnb_network_debug_clocks", _int, [_vp, _vp]),
     ("tcnnb_network_module_inference", _int, [_vp, _vp, _u32, _vp, _vp, _vp]),
@@ -558,6 +560,37 @@ class Network:
         hidden = torch.empty(self.n_hidden_layers, n, self.width, dtype=torch.float16, device=x16.device)
         _check(load().tcnnb_network_forward(self._h, _stream_handle(stream), n, x16.data_ptr(), out.data_ptr(), hidden.data_ptr(), params16.data_ptr()))
         return out, hidden
+
+    def backward(self, x16, out16, hidden, dL_doutput16, params16, want_input_grad=True, want_param_grad=True, stream=None):
+        """Network<T>::backward from the forward pass's input / output / hidden activations:
+        -> (dL_dinput fp16 [n][n_input_dims] or None, dL_dparams fp16 [n_params] or None)."""
+        import torch
+
+        n = x16.shape[0]
+        dx = torch.empty(n, self.input_width, dtype=torch.float16, device=x16.device) if want_input_grad else None
+        dp = torch.empty(self.n_params, dtype=torch.float16, device=x16.device) if want_param_grad else None
+        _check(load().tcnnb_network_backward(self._h, _stream_handle(stream), n, x16.data_ptr(), out16.data_ptr() if out16 is not None else None, hidden.data_ptr(), dL_doutput16.data_ptr(),
+                                             params16.data_ptr(), dx.data_ptr() if dx is not None else None, dp.data_ptr() if dp is not None else None))
+        return dx, dp
+
+    def module_inference(self, x32, params16, stream=None):
+        """cpp::Module::inference of cpp::create_network: fp32 [n][n_input_dims] (Identity encoding) -> fp16 [n][padded_output_width]."""
+        import torch
+
+        out = torch.empty(x32.shape[0], self.padded_output_width, dtype=torch.float16, device=x32.device)
+        _check(load().tcnnb_network_module_inference(self._h, _stream_handle(stream), x32.shape[0], x32.data_ptr(), out.data_ptr(), params16.data_ptr()))
+        return out
+
+    def module_backward(self, x32, dL_doutput16, params16, want_input_grad=True, want_param_grad=True, stream=None):
+        """cpp::Module::backward of cpp::create_network: -> (dL_dinput fp32 [n][n_input_dims] or None, dL_dparams fp16 or None)."""
+        import torch
+
+        n = x32.shape[0]
+        dx = torch.empty(n, self.n_input_dims, dtype=torch.float32, device=x32.device) if want_input_grad else None
+        dp = torch.empty(self.n_params, dtype=torch.float16, device=x32.device) if want_param_grad else None
+        _check(load().tcnnb_network_module_backward(self._h, _stream_handle(stream), n, dx.data_ptr() if dx is not None else None, dL_doutput16.data_ptr(),
+                                                    dp.data_ptr() if dp is not None else None, x32.data_ptr(), params16.data_ptr()))
+        return dx, dp
 
     def inference(self, x32, params16, stream=None):
         """fp32 [n][n_input_dims] through the Identity encoding -> fp32 [n][n_output_dims]."""
