@@ -63,7 +63,11 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 	cfg.stream = stream;
 	cudaLaunchAttribute attr[1];
 	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-	static const int allowed = std::getenv("TCNNB_NO_PDL") ? 0 : 1;  // TCNNB_NO_PDL=1: plain stream-ordered launches (A/B switch)
+#ifdef TCNNB_ENABLE_ABLATION  // profiling builds only: TCNNB_NO_PDL=1 = plain stream-ordered launches (A/B switch)
+	static const int allowed = std::getenv("TCNNB_NO_PDL") ? 0 : 1;
+#else
+	const int allowed = 1;
+#endif
 	attr[0].val.programmaticStreamSerializationAllowed = allowed;
 	cfg.attrs = attr;
 	cfg.numAttrs = 1;
