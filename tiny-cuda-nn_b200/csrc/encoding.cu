@@ -16,6 +16,7 @@
 #include "misc_kernels.h"
 
 #include <memory>
+#include <vector>
 
 namespace tcnnb {
 
@@ -23,6 +24,7 @@ struct Encoding {
 	GridConfig grid;
 	DeviceBuffer<LevelInfo> levels_dev;
 	DeviceBuffer<float> scratch;        // level scales; fp32 gradient accumulator when F == 1
+	DeviceBuffer<__half> replicas;      // private copies of the coarse levels' gradients (grid_kernels.h plan_grid_scatter)
 	float max_level = 1.0f;
 	std::string hyperparams_json;
 
@@ -142,7 +144,21 @@ int tcnnb_encoding_backward(tcnnb_encoding* e, tcnnb_stream stream, uint32_t n_e
 	check_ptr(input_dev, "input", 4);
 	check_ptr(dL_doutput_dev, "dL_doutput", 2 * F);
 	cudaStream_t s = (cudaStream_t)stream;
-	const GridKernelArgs a = enc.args(n_elements, input_dev);
+	GridKernelArgs a = enc.args(n_elements, input_dev);
+	if (dL_dparams_dev && enc.max_level >= 1.0f) {  // contended coarse levels scatter into private copies
+		std::vector<LevelInfo> levels(enc.grid.n_levels);
+		for (uint32_t l = 0; l < enc.grid.n_levels; ++l) levels[l] = make_level_info(enc.grid, l);
+		const GridScatterPlan plan = plan_grid_scatter(levels.data(), enc.grid.n_levels, F, enc.grid.n_pos_dims, n_elements);
+		if (plan.n_replicas > 1) {
+			if (enc.replicas.n < plan.scratch_halfs) {
+				enc.replicas.resize(plan.scratch_halfs);
+				enc.replicas.zero(s);
+			}
+			a.replica_scratch = enc.replicas.ptr;
+			a.n_replicas = plan.n_replicas;
+			a.replica_entries = plan.replica_entries;
+		}
+	}
 	if (dL_dparams_dev) {  // GradientMode::Overwrite (src/cpp_api.cu:115)
 		check_ptr(dL_dparams_dev, "dL_dparams", 2 * F);
 		TCNNB_CUDA_CHECK(cudaMemsetAsync(dL_dparams_dev, 0, sizeof(__half) * enc.grid.n_params, s));

@@ -125,6 +125,8 @@ __global__ void grid_backward_kernel(const GridKernelArgs a, const __half* __res
 	float x[D];
 	load_position<D>(a.positions, i, x);
 	const Entry<F> grad = load_entry<F>(dL_dy + (size_t)i * a.row_stride + level * F);
+	// coarse levels: one of n_replicas private copies of the level (see plan_grid_scatter)
+	__half* const target = (F > 1 && a.n_replicas > 1 && lv.offset + lv.size <= a.replica_entries) ? a.replica_scratch + (size_t)(blockIdx.x % a.n_replicas) * a.replica_entries * F : grad_table;
 	auto add = [&](uint32_t idx, float weight) {
 		const size_t at = ((size_t)lv.offset + idx) * F;
 		if (F == 1) {
@@ -134,7 +136,7 @@ __global__ void grid_backward_kernel(const GridKernelArgs a, const __half* __res
 			const __half w = __float2half_rn(weight);
 #pragma unroll
 			for (uint32_t f = 0; f < F; ++f) e.v[f] = __hmul(w, grad.v[f]);  // (GRAD_T)weight * grad, grid.h:252-255
-			red_entry<F>(grad_table + at, e);
+			red_entry<F>(target + at, e);
 		}
 	};
 	if (a.interpolation == INTERP_NEAREST) {
@@ -147,6 +149,24 @@ __global__ void grid_backward_kernel(const GridKernelArgs a, const __half* __res
 	level_corners<D>(lv, x, a.interpolation, lc);
 #pragma unroll
 	for (uint32_t c = 0; c < (1u << D); ++c) add(lc.idx[c], lc.w[c]);
+}
+
+// grad_table[word] = sum over the replicas (fp32), replicas re-armed to zero. One thread per f16x2 word of the replicated levels.
+__global__ void replica_reduce_kernel(uint32_t n_words, uint32_t n_replicas, uint32_t* __restrict__ scratch, uint32_t* __restrict__ grad_table) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_words) return;
+	float lo = 0.0f, hi = 0.0f;
+	for (uint32_t r = 0; r < n_replicas; ++r) {
+		const uint32_t w = scratch[(size_t)r * n_words + i];
+		if (w) {
+			const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w));
+			lo += v.x;
+			hi += v.y;
+			scratch[(size_t)r * n_words + i] = 0u;
+		}
+	}
+	const __half2 out = __floats2half2_rn(lo, hi);
+	grad_table[i] = *reinterpret_cast<const uint32_t*>(&out);
 }
 
 __global__ void cast_grad_kernel(uint32_t n, const float* __restrict__ in, __half* __restrict__ out) {
@@ -262,11 +282,38 @@ cudaError_t launch_grid_backward(cudaStream_t stream, const GridKernelArgs& a, c
 		return cudaGetLastError();
 	});
 	if (err != cudaSuccess) return err;
+	if (a.n_features_per_level > 1 && a.n_replicas > 1 && a.replica_entries) {
+		if (!a.replica_scratch) return cudaErrorInvalidValue;
+		const uint32_t n_words = a.replica_entries * a.n_features_per_level / 2;
+		replica_reduce_kernel<<<(n_words + 255) / 256, 256, 0, stream>>>(n_words, a.n_replicas, reinterpret_cast<uint32_t*>(a.replica_scratch), reinterpret_cast<uint32_t*>(grad_table));
+		err = cudaGetLastError();
+	}
 	if (a.n_features_per_level == 1) {
 		cast_grad_kernel<<<(n_params + 255) / 256, 256, 0, stream>>>(n_params, tmp_fp32, grad_table);
 		err = cudaGetLastError();
 	}
 	return err;
+}
+
+GridScatterPlan plan_grid_scatter(const LevelInfo* levels, uint32_t n_levels, uint32_t F, uint32_t D, uint32_t n_elements) {
+	GridScatterPlan plan;
+	if (F < 2 || n_levels == 0 || n_elements < 16384) return plan;
+	const double corners = (double)n_elements * (double)(1u << D);
+	// replicate the levels whose entries receive more than ~64 reductions each, with enough copies to bring the coarsest one there
+	uint32_t entries = 0;
+	for (uint32_t l = 0; l < n_levels; ++l) {
+		if (levels[l].offset != entries || corners / (double)levels[l].size <= 64.0) break;
+		entries += levels[l].size;
+	}
+	if (entries == 0) return plan;
+	uint32_t r = 1;
+	while (r < 64 && corners / (double)levels[0].size / (double)r > 128.0) r *= 2;
+	while (r > 1 && (size_t)r * entries * F * sizeof(__half) > ((size_t)64 << 20)) r /= 2;
+	if (r < 2) return plan;
+	plan.n_replicas = r;
+	plan.replica_entries = entries;
+	plan.scratch_halfs = (size_t)r * entries * F;
+	return plan;
 }
 
 cudaError_t launch_grid_input_gradient(cudaStream_t stream, const GridKernelArgs& a, const __half* table, const __half* dL_dy, float* dL_dx) {

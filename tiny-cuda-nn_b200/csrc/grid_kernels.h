@@ -15,7 +15,22 @@ struct GridKernelArgs {
 	uint32_t n_elements;
 	const float* positions;          // [n][D] fp32
 	uint32_t row_stride;             // fp16 elements per row of encoded / dL_dy (>= n_levels * F)
+	// backward only (optional, see plan_grid_scatter): the coarse levels scatter into one of n_replicas private copies
+	__half* replica_scratch;         // [n_replicas][replica_entries * F] fp16, ZERO on entry (left zero on exit)
+	uint32_t n_replicas;             // 0 / 1 = off
+	uint32_t replica_entries;        // levels with offset + size <= replica_entries are replicated
 };
+
+// Coarse levels receive thousands of reductions per table entry (2^18 samples x 4 corners over the 289 vertices of a 16 x 16 level:
+// 3 600 each) and reductions to ONE address complete one after the other in L2, so that level alone sets the kernel's duration.
+// Those levels scatter into n_replicas private copies (chosen by block index) that a small kernel sums into the gradient table.
+// Sums of the same addends in a different order: the reference's own accumulation order is unspecified (atomics).
+struct GridScatterPlan {
+	uint32_t n_replicas = 1;
+	uint32_t replica_entries = 0;
+	size_t scratch_halfs = 0;  // n_replicas * replica_entries * F
+};
+GridScatterPlan plan_grid_scatter(const LevelInfo* levels_host, uint32_t n_levels, uint32_t n_features_per_level, uint32_t n_pos_dims, uint32_t n_elements);
 
 // encoded [n][row_stride] fp16 (row = sample; columns level * F + f; columns beyond n_levels * F are zeroed)        grid.h:49-169
 cudaError_t launch_grid_forward(cudaStream_t stream, const GridKernelArgs& a, const __half* table, __half* encoded);

@@ -204,23 +204,41 @@ __global__ void loss_kernel(uint32_t loss_type, uint32_t out_act, uint32_t batch
                             const float* __restrict__ targets, __half* __restrict__ dL_dy, float* __restrict__ loss_values, float* __restrict__ loss_sum) {
 	pdl_wait();
 	pdl_launch_dependents();
-	const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;  // one thread per (sample, output column)
-	float value = 0.0f;
-	if (i < batch * stride) {
-		const uint32_t sample = i / stride, q = i % stride;
-		const __half y = prediction[i];
-		float gq = 0.0f;
-		if (q < n_out) {
-			float grad;
-			fused::loss_element(loss_type, __half2float(y), targets[(size_t)sample * n_out + q], n_total, value, grad);
-			gq = loss_scale * grad / n_total;
-			if (loss_values) loss_values[(size_t)sample * n_out + q] = value;
-		}
-		dL_dy[i] = fused::act_bwd_h(out_act, __float2half_rn(gq), y);
-	}
+	// one thread per (sample, group of 8 output columns): 16-byte loads / stores of the fp16 rows
+	const uint32_t groups = stride / 8;
+	const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
+	float value_sum = 0.0f;
+	if (i < batch * groups) {
+		const uint32_t sample = i / groups, q0 = (i % groups) * 8;
+		const uint4 raw = *reinterpret_cast<const uint4*>(prediction + (size_t)sample * stride + q0);
+		const __half* y = reinterpret_cast<const __half*>(&raw);
+		__half dy[8];
 #pragma unroll
-	for (uint32_t o = 16; o > 0; o >>= 1) value += __shfl_xor_sync(0xFFFFFFFFu, value, o);
-	if ((threadIdx.x & 31u) == 0 && loss_sum && value != 0.0f) atomicAdd(loss_sum, value);
+		for (uint32_t k = 0; k < 8; ++k) {
+			const uint32_t q = q0 + k;
+			float gq = 0.0f;
+			if (q < n_out) {
+				float value, grad;
+				fused::loss_element(loss_type, __half2float(y[k]), targets[(size_t)sample * n_out + q], n_total, value, grad);
+				gq = loss_scale * grad / n_total;
+				value_sum += value;
+				if (loss_values) loss_values[(size_t)sample * n_out + q] = value;
+			}
+			dy[k] = fused::act_bwd_h(out_act, __float2half_rn(gq), y[k]);
+		}
+		*reinterpret_cast<uint4*>(dL_dy + (size_t)sample * stride + q0) = *reinterpret_cast<const uint4*>(dy);
+	}
+	// block sum -> ONE atomic per block (a per-warp atomic on the single loss word serialises the whole kernel)
+	__shared__ float warp_sums[8];
+#pragma unroll
+	for (uint32_t o = 16; o > 0; o >>= 1) value_sum += __shfl_xor_sync(0xFFFFFFFFu, value_sum, o);
+	if ((threadIdx.x & 31u) == 0) warp_sums[threadIdx.x >> 5] = value_sum;
+	__syncthreads();
+	if (threadIdx.x == 0 && loss_sum) {
+		float total = 0.0f;
+		for (uint32_t w = 0; w < blockDim.x / 32; ++w) total += warp_sums[w];
+		if (total != 0.0f) atomicAdd(loss_sum, total);
+	}
 }
 
 // dL/d(output) of a caller (Network::backward, fully_fused_mlp.cu:755-762) through the output activation's transfer.
@@ -396,8 +414,8 @@ cudaError_t launch_mlp_grad_finalize(cudaStream_t stream, uint32_t n, float* dw_
 
 cudaError_t launch_loss(cudaStream_t stream, uint32_t loss_type, uint32_t output_activation, uint32_t batch, uint32_t n_out, uint32_t stride, float loss_scale, uint32_t n_total,
                         const __half* prediction, const float* targets, __half* dL_dy, float* loss_values, float* loss_sum) {
-	if ((uint64_t)batch * stride >= (1ull << 32)) return cudaErrorInvalidValue;
-	return launch_pdl(loss_kernel, blocks_for(batch * stride, 256), 256, 0, stream, loss_type, output_activation, batch, n_out, stride, loss_scale, (float)n_total, prediction, targets,
+	if ((uint64_t)batch * stride >= (1ull << 32) || stride % 8 != 0) return cudaErrorInvalidValue;
+	return launch_pdl(loss_kernel, blocks_for(batch * (stride / 8), 256), 256, 0, stream, loss_type, output_activation, batch, n_out, stride, loss_scale, (float)n_total, prediction, targets,
 	                  dL_dy, loss_values, loss_sum);
 }
 

@@ -163,6 +163,8 @@ struct Model {
 	std::string general_reason;  // which limit of the fused kernel sent this configuration here (hyperparams / diagnostics)
 	DeviceBuffer<__half> g_enc, g_hidden, g_out, g_dy, g_grad_hidden, g_denc, g_dy_act;
 	DeviceBuffer<float> g_grid_tmp;  // n_features_per_level == 1: fp32 scatter target (grid.h:858-894)
+	DeviceBuffer<__half> g_replicas; // private copies of the coarse levels' gradients (grid_kernels.h plan_grid_scatter)
+	int grid_replicas_override = -1; // tcnnb_debug_set("grid_replicas", n): experiments (0 / 1 = off)
 
 	// spatial binning scratch (binning.cu): sorted copies of the batch + permutation
 	bool binning = true;  // tcnnb_debug_set("binning", 0) (tests: binned and unbinned steps must touch the same entries)
@@ -687,7 +689,26 @@ static void general_backward_pass(Model& m, cudaStream_t stream, uint32_t batch,
 			TCNNB_CUDA_CHECK(cudaMemsetAsync(m.g_grid_tmp.ptr, 0, sizeof(float) * m.grid.n_params, stream));
 			tmp = m.g_grid_tmp.ptr;
 		}
-		TCNNB_CUDA_CHECK(launch_grid_backward(stream, grid_kernel_args(m, batch, x, mlp.in_width), m.g_denc.ptr, grads + mlp.n_params, tmp, (uint32_t)m.grid.n_params));
+		GridKernelArgs ga = grid_kernel_args(m, batch, x, mlp.in_width);
+		{
+			std::vector<LevelInfo> levels(m.grid.n_levels);
+			for (uint32_t l = 0; l < m.grid.n_levels; ++l) levels[l] = make_level_info(m.grid, l);
+			GridScatterPlan plan = plan_grid_scatter(levels.data(), m.grid.n_levels, m.grid.n_features_per_level, m.grid.n_pos_dims, batch);
+			if (m.grid_replicas_override >= 0 && plan.replica_entries) {
+				plan.n_replicas = (uint32_t)m.grid_replicas_override;
+				plan.scratch_halfs = (size_t)plan.n_replicas * plan.replica_entries * m.grid.n_features_per_level;
+			}
+			if (plan.n_replicas > 1) {
+				if (m.g_replicas.n < plan.scratch_halfs) {
+					m.g_replicas.resize(plan.scratch_halfs);
+					m.g_replicas.zero(stream);  // the reduce kernel leaves it zero
+				}
+				ga.replica_scratch = m.g_replicas.ptr;
+				ga.n_replicas = plan.n_replicas;
+				ga.replica_entries = plan.replica_entries;
+			}
+		}
+		TCNNB_CUDA_CHECK(launch_grid_backward(stream, ga, m.g_denc.ptr, grads + mlp.n_params, tmp, (uint32_t)m.grid.n_params));
 		++g_kernel_launches;
 	}
 	if (dL_dinput) {
@@ -1581,6 +1602,7 @@ int tcnnb_debug_set(tcnnb_model* m, const char* key, int value) {
 	TCNNB_API_BEGIN
 	const std::string k = key ? key : "";
 	if (k == "binning") m->impl.binning = value != 0;
+	else if (k == "grid_replicas") m->impl.grid_replicas_override = value;  // general path: copies of the coarse levels' gradient (-1 = automatic)
 	else throw std::runtime_error("tcnnb_debug_set: unknown key '" + k + "'");
 	TCNNB_API_END
 }
