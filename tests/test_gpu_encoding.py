@@ -170,3 +170,38 @@ def test_torch_layers_deliver_input_gradients(torch_cuda):
     net = tcnn.Network(3, 3, {"otype": "CutlassMLP", "n_neurons": 64, "n_hidden_layers": 2})
     out = net(torch.rand(300, 3, device="cuda"))
     assert out.shape == (300, 3) and out.dtype == torch.float32 and torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("n_in,F", [(2, 2), (3, 4), (3, 8)])
+def test_replicated_scatter_of_the_coarse_levels_matches_exact_sums(torch_cuda, n_in, F):
+    """From 16 384 samples on, the coarse levels -- thousands of reductions per table entry -- scatter into private copies that a
+    second kernel sums (grid_kernels.h plan_grid_scatter). Same addends, different order: compared with the oracle's exact sums, and
+    a second call must give the same table (the copies are re-armed to zero)."""
+    torch = torch_cuda
+    import tcnn_b200
+
+    L = 8
+    enc_cfg = {"otype": "HashGrid", "n_levels": L, "n_features_per_level": F, "log2_hashmap_size": 14, "base_resolution": 8, "per_level_scale": 1.5}
+    enc = tcnn_b200.Encoding(n_in, enc_cfg)
+    levels = enc.grid_levels()
+    orc = ob.OracleModel(n_in, 1, {"encoding": enc_cfg, "network": {"n_neurons": 16, "n_hidden_layers": 1}}, scales=levels["scales"])
+    p16 = enc.initial_params(seed=9, scale=50.0).to(torch.float16).contiguous()
+    B = 32768
+    x = make_x(n_in, B)
+    xd = torch.from_numpy(x).cuda()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    dy = (torch.randn(B, L * F, device="cuda", generator=g) * 0.01).to(torch.float16).contiguous()
+    gp, _ = enc.bwd(xd, p16, dy)
+    gp2, _ = enc.bwd(xd, p16, dy)
+    torch.cuda.synchronize()
+    dy_soa = np.zeros((orc.grid.padded_width, B), np.uint16)
+    dy_soa[: L * F] = f16(dy).T
+    g_ref = orc.grid_backward(x, dy_soa)
+    g_dev = ob.half_bits_to_float(f16(gp)).astype(np.float64)
+    # coarse levels: sums of ~1 000 addends each; fp16 partial sums per copy + fp32 across copies are closer to the exact sums than
+    # one fp16 accumulator would be
+    assert rae(g_dev, g_ref, 99.9) < 1.2e-2
+    assert ((g_dev != 0) != (g_ref != 0)).mean() < 2e-3
+    first = levels["offsets"][1] * F  # level 0 alone
+    assert rae(g_dev[:first], g_ref[:first]) < 1.2e-2
+    assert rae(ob.half_bits_to_float(f16(gp2)), g_dev, 99.9) < 5e-3

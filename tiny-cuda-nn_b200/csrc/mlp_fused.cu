@@ -353,11 +353,24 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 				constexpr uint32_t FWD_WORDS = BWD ? (GENERIC_ACT ? C::GROUP_COLS / 2 : 2) : 1;
 				uint32_t fwd[FWD_WORDS];
 				if (BWD && l < NH) {
-					const uint4* src = reinterpret_cast<const uint4*>(p.hidden_in + ((size_t)(NH - 1 - l) * p.batch_size + sample) * W + col0);
+					uint4 hv[C::GROUP_COLS / 8];
+					if (C::GROUP_COLS == 64) {
+						// coalesced: 8 lanes fetch the 8 consecutive 16-byte chunks of ONE row, for 8 rows in turn; the transpose hands every
+						// lane the chunks of its own row
+						const __half* src = p.hidden_in + ((size_t)(NH - 1 - l) * p.batch_size + tile_row0 + g8 * 8) * W + col0 + l8 * 8;
+#pragma unroll
+						for (uint32_t jj = 0; jj < 8; ++jj) hv[jj % (C::GROUP_COLS / 8)] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)jj * W));
+						uint4(&hv8)[8] = reinterpret_cast<uint4(&)[8]>(hv);
+						transpose8x8_u128(hv8, lane);
+					} else {
+						const uint4* src = reinterpret_cast<const uint4*>(p.hidden_in + ((size_t)(NH - 1 - l) * p.batch_size + sample) * W + col0);
+#pragma unroll
+						for (uint32_t i = 0; i < C::GROUP_COLS / 8; ++i) hv[i] = __ldg(src + i);
+					}
 					if (!GENERIC_ACT) fwd[0] = fwd[FWD_WORDS - 1] = 0;
 #pragma unroll
 					for (uint32_t i = 0; i < C::GROUP_COLS / 8; ++i) {
-						const uint4 v = __ldg(src + i);
+						const uint4 v = hv[i];
 						const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
 						for (uint32_t c = 0; c < 4; ++c) {
@@ -398,9 +411,15 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 					// 32..63 (its last piece); group 0's own stores only cover columns it has read itself. So group 0 works piece by piece
 					// and signals a named barrier (bar.arrive, non-blocking) once its last piece is in registers; group 1 converts all
 					// its pieces first and stores them after the barrier.
+					// The rows also go to global memory when the caller keeps them (forward activations / backward g_l): 64-column groups
+					// AFTER the hand-over to the MMA issuer and coalesced through the 8 x 8 lane transpose, narrower ones directly.
+					uint4 keep[C::GROUP_COLS == 64 ? 8 : 1];
 					auto store_piece = [&](uint32_t k, const uint32_t (&h)[C::PIECE / 2]) {
 						tmem_st_n<C::PIECE / 2>(acc + (col0 + k * C::PIECE) / 2, h);
-						if (p.hidden_out) {
+						if (C::GROUP_COLS == 64) {
+#pragma unroll
+							for (uint32_t i = 0; i < C::PIECE / 8; ++i) keep[(k * (C::PIECE / 8) + i) % (C::GROUP_COLS == 64 ? 8 : 1)] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+						} else if (p.hidden_out) {
 							uint4* dst = reinterpret_cast<uint4*>(p.hidden_out + ((size_t)(BWD ? NH - 1 - l : l) * p.batch_size + sample) * W + col0 + k * C::PIECE);
 #pragma unroll
 							for (uint32_t i = 0; i < C::PIECE / 8; ++i) dst[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
@@ -438,6 +457,13 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 					__syncwarp();
 					if (lane == 0) mbar_arrive_plain(bar_a_ready + 8 * s);
 					if (stamp) MLPF_STAMP(1 + s, ev, 4);
+					if (C::GROUP_COLS == 64 && p.hidden_out) {
+						uint4(&keep8)[8] = reinterpret_cast<uint4(&)[8]>(keep);
+						transpose8x8_u128(keep8, lane);
+						__half* dst = p.hidden_out + ((size_t)(BWD ? NH - 1 - l : l) * p.batch_size + tile_row0 + g8 * 8) * W + col0 + l8 * 8;
+#pragma unroll
+						for (uint32_t jj = 0; jj < 8; ++jj) *reinterpret_cast<uint4*>(dst + (size_t)jj * W) = keep8[jj];
+					}
 				} else {
 					// output layer: activation, then fp16 rows (and / or trimmed fp32 rows) to global memory. A full 64-column block
 					// goes out coalesced (transpose, then 8 lanes write 128 contiguous bytes of one row); a narrower tail row by row.

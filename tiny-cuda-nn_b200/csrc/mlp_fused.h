@@ -54,7 +54,7 @@ struct MlpWgradParams {
 };
 // dW_l += g_l^T . h_{l-1} for every weight matrix (the reference's split-k GEMMs, fully_fused_mlp.cu:802-866).
 bool mlp_wgrad_supported(const MlpWgradParams& p, const char** why);
-cudaError_t launch_mlp_wgrad(const MlpWgradParams& p, uint32_t n_sms, cudaStream_t stream);
+cudaError_t launch_mlp_wgrad(const MlpWgradParams& p, uint32_t n_sms, cudaStream_t stream, uint32_t* n_launches = nullptr);
 
 
 // ---- the whole backward pass of the stand-alone network: [output activation backward] -> dgrad chain -> weight gradients ------

@@ -32,7 +32,6 @@ template <uint32_t W>
 struct WgradCfg {
 	static constexpr uint32_t M = W == 128 ? 128 : 64;          // rows of an accumulator (narrower layers are zero-padded by TMA)
 	static constexpr uint32_t ACC_COLS = W == 128 ? 128 : 64;   // TMEM columns per matrix
-	static constexpr uint32_t MAX_MATRICES = 512 / ACC_COLS;
 	static constexpr uint32_t KB = (W + 63) / 64;               // 64-column boxes per operand tile
 	static constexpr uint32_t OPERAND_BYTES = KB * TILE_BYTES;
 	static constexpr uint32_t STAGE_BYTES = 2 * OPERAND_BYTES;  // [A | B]
@@ -40,10 +39,12 @@ struct WgradCfg {
 	static constexpr uint32_t THREADS = 6 * 32;
 };
 
+constexpr uint32_t WGRAD_MAX_MATRICES = 16;
 struct WgradKernelParams {
 	MlpWgradParams p;
 	uint32_t first_matrix, n_matrices;  // this launch: matrices [first, first + n)
 	uint32_t tmem_cols;
+	uint16_t acc_col[WGRAD_MAX_MATRICES];  // first TMEM column of each matrix's accumulator (packed by the matrices' real fan-in)
 };
 
 }  // namespace
@@ -136,7 +137,7 @@ mlp_wgrad_kernel(const WgradKernelParams kp, const __grid_constant__ CUtensorMap
 				const uint32_t a_tile = smem_base + stage * C::STAGE_BYTES, b_tile = a_tile + C::OPERAND_BYTES;
 				const uint32_t n_cols = mi == 0 ? in_w : (mi == NH ? out_w : W);
 				const uint32_t idesc = umma_idesc_f16(C::M, n_cols, 1, 1);
-				const uint32_t d_tmem = tmem_base + (it % kp.n_matrices) * C::ACC_COLS;
+				const uint32_t d_tmem = tmem_base + kp.acc_col[it % kp.n_matrices];
 				const bool first_tile = it < kp.n_matrices;
 				for (uint32_t kk = 0; kk < TILE_M / 16; ++kk) {
 					// [128 K-rows][64 MN] boxes: 16 K-rows per step = 2 048 bytes; the next 64 MN elements are one box (TILE_BYTES) further
@@ -164,7 +165,7 @@ mlp_wgrad_kernel(const WgradKernelParams kp, const __grid_constant__ CUtensorMap
 			float* base = p.dw_accum + (mi == 0 ? 0 : (size_t)W * in_w + (size_t)(mi - 1) * W * W);
 			for (uint32_t c0 = 0; c0 < n_cols; c0 += 16) {
 				uint32_t r[16];
-				tmem_ld_32x32b_x16(tmem_base + lane_field + a * C::ACC_COLS + c0, r);
+				tmem_ld_32x32b_x16(tmem_base + lane_field + kp.acc_col[a] + c0, r);
 				tmem_ld_wait();
 				if (!row_ok) continue;
 				if (mi < NH) {
@@ -191,7 +192,7 @@ mlp_wgrad_kernel(const WgradKernelParams kp, const __grid_constant__ CUtensorMap
 namespace {
 
 template <uint32_t W>
-cudaError_t launch_wgrad_width(const MlpWgradParams& p, uint32_t n_sms, cudaStream_t stream) {
+cudaError_t launch_wgrad_width(const MlpWgradParams& p, uint32_t n_sms, cudaStream_t stream, uint32_t* n_launches) {
 	using C = WgradCfg<W>;
 	const uint32_t NH = p.n_hidden_layers, B = p.batch_size;
 	CUtensorMap mx, mh, mg, mgo;
@@ -205,16 +206,27 @@ cudaError_t launch_wgrad_width(const MlpWgradParams& p, uint32_t n_sms, cudaStre
 	if (err != cudaSuccess) return err;
 	const uint32_t n_tiles = B / TILE_M;
 	const uint32_t n_matrices = NH + 1;
-	for (uint32_t first = 0; first < n_matrices; first += C::MAX_MATRICES) {
+	// accumulators are packed by the matrices' real column counts (fan-in; 16-column granules): 128 x 4 with a 32-wide input and 16
+	// outputs needs 32 + 3 x 128 + 16 = 432 of the 512 columns -- one launch
+	auto cols_of = [&](uint32_t mi) { return ((mi == 0 ? p.in_width : (mi == NH ? p.out_width : W)) + 15u) / 16u * 16u; };
+	for (uint32_t first = 0; first < n_matrices;) {
 		WgradKernelParams kp{};
 		kp.p = p;
 		kp.first_matrix = first;
-		kp.n_matrices = n_matrices - first < C::MAX_MATRICES ? n_matrices - first : C::MAX_MATRICES;
+		uint32_t used = 0, n = 0;
+		while (first + n < n_matrices && n < WGRAD_MAX_MATRICES && used + cols_of(first + n) <= 512) {
+			kp.acc_col[n] = (uint16_t)used;
+			used += cols_of(first + n);
+			++n;
+		}
+		kp.n_matrices = n;
 		uint32_t cols = 32;
-		while (cols < kp.n_matrices * C::ACC_COLS) cols *= 2;
+		while (cols < used) cols *= 2;
 		kp.tmem_cols = cols;
 		err = launch_pdl(kernel, n_tiles < n_sms ? n_tiles : n_sms, C::THREADS, smem, stream, kp, mx, mh, mg, mgo);
 		if (err != cudaSuccess) return err;
+		if (n_launches) ++*n_launches;
+		first += n;
 	}
 	return cudaSuccess;
 }
@@ -236,13 +248,13 @@ bool mlp_wgrad_supported(const MlpWgradParams& p, const char** why) {
 	return true;
 }
 
-cudaError_t launch_mlp_wgrad(const MlpWgradParams& p, uint32_t n_sms, cudaStream_t stream) {
+cudaError_t launch_mlp_wgrad(const MlpWgradParams& p, uint32_t n_sms, cudaStream_t stream, uint32_t* n_launches) {
 	if (!mlp_wgrad_supported(p, nullptr)) return cudaErrorInvalidValue;
 	switch (p.width) {
-		case 128: return launch_wgrad_width<128>(p, n_sms, stream);
-		case 64: return launch_wgrad_width<64>(p, n_sms, stream);
-		case 32: return launch_wgrad_width<32>(p, n_sms, stream);
-		case 16: return launch_wgrad_width<16>(p, n_sms, stream);
+		case 128: return launch_wgrad_width<128>(p, n_sms, stream, n_launches);
+		case 64: return launch_wgrad_width<64>(p, n_sms, stream, n_launches);
+		case 32: return launch_wgrad_width<32>(p, n_sms, stream, n_launches);
+		case 16: return launch_wgrad_width<16>(p, n_sms, stream, n_launches);
 	}
 	return cudaErrorInvalidValue;
 }
@@ -302,9 +314,8 @@ cudaError_t launch_mlp_backward(const MlpBackwardArgs& a, uint32_t n_sms, cudaSt
 	++launches;
 	if (a.dw_accum) {
 		if (!a.input) return cudaErrorInvalidValue;
-		err = launch_mlp_wgrad(w, n_sms, stream);
+		err = launch_mlp_wgrad(w, n_sms, stream, &launches);
 		if (err != cudaSuccess) return err;
-		launches += (a.n_hidden_layers + 1 + (a.width == 128 ? 3 : 7)) / (a.width == 128 ? 4 : 8);
 	}
 	if (n_launches) *n_launches += launches;
 	return cudaSuccess;
