@@ -40,6 +40,9 @@ CONFIGS = {
     "identity_cutlass": (3, 3, 1 << 16, {"encoding": {"otype": "Identity"}, "network": mlp(64, 2, "CutlassMLP")}, "configs[0] (fused kernel)"),
     "hash3d_w128": (3, 3, 1 << 18, {"encoding": hashgrid(), "network": mlp(128, 2)}, "headline encoding + 128 x 2 (general path)"),
     "f4_l8": (3, 3, 1 << 18, {"encoding": hashgrid(n_levels=8, n_features_per_level=4), "network": mlp(64, 2)}, "n_features_per_level = 4 (general path)"),
+    # BASELINE.json configs[4], training half: the bare network behind an Identity encoding (the reference's bench_mlp_ours only times inference)
+    "mlp_w128_h4": (128, 128, 1 << 18, {"encoding": {"otype": "Identity"}, "network": mlp(128, 4)}, "configs[4] training: 128 -> 128 x 4 -> 128 (general path)"),
+    "mlp_w64_h4": (64, 64, 1 << 18, {"encoding": {"otype": "Identity"}, "network": mlp(64, 4)}, "configs[4] training: 64 -> 64 x 4 -> 64 (general path)"),
     "d4": (4, 3, 1 << 18, {"encoding": hashgrid(), "network": mlp(64, 2)}, "4-D inputs (general path)"),
 }
 for _c in CONFIGS.values():
@@ -49,7 +52,7 @@ for _c in CONFIGS.values():
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="headline,image_w128,image_w64,identity_cutlass,hash3d_w128,f4_l8,d4")
+    ap.add_argument("--configs", default="headline,image_w128,image_w64,identity_cutlass,hash3d_w128,f4_l8,d4,mlp_w128_h4,mlp_w64_h4")
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--reference", action="store_true")

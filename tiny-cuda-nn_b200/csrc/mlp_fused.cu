@@ -417,6 +417,7 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 					auto store_piece = [&](uint32_t k, const uint32_t (&h)[C::PIECE / 2]) {
 						tmem_st_n<C::PIECE / 2>(acc + (col0 + k * C::PIECE) / 2, h);
 						if (C::GROUP_COLS == 64) {
+							if (p.hidden_out)
 #pragma unroll
 							for (uint32_t i = 0; i < C::PIECE / 8; ++i) keep[(k * (C::PIECE / 8) + i) % (C::GROUP_COLS == 64 ? 8 : 1)] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
 						} else if (p.hidden_out) {
