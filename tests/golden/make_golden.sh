@@ -23,3 +23,8 @@ $H dumpbig $C/headline.json 3 3 65536 10 "$OUT/big_headline_b16" 0 509 2048
 $H dumpbig $C/headline.json 3 3 262144 10 "$OUT/big_headline_b18" 0 509 2048
 # BASELINE.json configs[0]: CutlassMLP 64 x 2 behind the Identity encoding
 $H dump $C/identity_cutlass.json 3 3 512 10 "$OUT/identity_cutlass" 0
+# Composite / parameter-free encodings: TriangleWave + OneBlob + Identity ("NRC" layout), HashGrid + SphericalHarmonics
+# (the NeRF-style position + direction input), Frequency on its own
+$H dump $C/composite_nrc.json 6 3 512 10 "$OUT/composite_nrc" 0
+$H dump $C/composite_grid_sh.json 6 3 512 10 "$OUT/composite_grid_sh" 0
+$H dump $C/frequency_top.json 3 3 512 10 "$OUT/frequency_top" 0

@@ -65,9 +65,9 @@ __device__ __forceinline__ void red_entry(__half* p, const Entry<F>& e) {
 }
 
 template <uint32_t D>
-__device__ __forceinline__ void load_position(const float* __restrict__ positions, uint32_t i, float (&x)[D]) {
+__device__ __forceinline__ void load_position(const float* __restrict__ positions, uint32_t stride, uint32_t i, float (&x)[D]) {
 #pragma unroll
-	for (uint32_t d = 0; d < D; ++d) x[d] = __ldg(positions + (size_t)i * D + d);
+	for (uint32_t d = 0; d < D; ++d) x[d] = __ldg(positions + (size_t)i * stride + d);
 }
 
 __device__ __forceinline__ float active_levels(const GridKernelArgs& a) {
@@ -82,7 +82,7 @@ __global__ void grid_forward_kernel(const GridKernelArgs a, const __half* __rest
 	const uint32_t level = blockIdx.y;
 	__half* row = encoded + (size_t)i * a.row_stride;
 	if (level == 0) {  // padding columns are zero (grid.h:757-766)
-		for (uint32_t c = a.n_levels * F; c < a.row_stride; ++c) row[c] = __float2half_rn(0.0f);
+		for (uint32_t c = a.n_levels * F; c < a.n_levels * F + a.pad_cols; ++c) row[c] = __float2half_rn(0.0f);
 	}
 	Entry<F> result;
 #pragma unroll
@@ -94,7 +94,7 @@ __global__ void grid_forward_kernel(const GridKernelArgs a, const __half* __rest
 	const LevelInfo lv = a.levels_dev[level];
 	const __half* __restrict__ ltab = table + (size_t)lv.offset * F;
 	float x[D];
-	load_position<D>(a.positions, i, x);
+	load_position<D>(a.positions, a.pos_stride, i, x);
 	if (a.interpolation == INTERP_NEAREST) {
 		CellPos<D> cp;
 		pos_fract<D>(x, lv.scale, INTERP_LINEAR, cp);
@@ -123,7 +123,7 @@ __global__ void grid_backward_kernel(const GridKernelArgs a, const __half* __res
 	if ((float)level > active_levels(a) + 1e-3f) return;  // grid.h:242 (strict, unlike the forward's >=)
 	const LevelInfo lv = a.levels_dev[level];
 	float x[D];
-	load_position<D>(a.positions, i, x);
+	load_position<D>(a.positions, a.pos_stride, i, x);
 	const Entry<F> grad = load_entry<F>(dL_dy + (size_t)i * a.row_stride + level * F);
 	// coarse levels: one of n_replicas private copies of the level (see plan_grid_scatter)
 	__half* const target = (F > 1 && a.n_replicas > 1 && lv.offset + lv.size <= a.replica_entries) ? a.replica_scratch + (size_t)(blockIdx.x % a.n_replicas) * a.replica_entries * F : grad_table;
@@ -179,7 +179,7 @@ __global__ void grid_input_gradient_kernel(const GridKernelArgs a, const __half*
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= a.n_elements) return;
 	float x[D], result[D];
-	load_position<D>(a.positions, i, x);
+	load_position<D>(a.positions, a.pos_stride, i, x);
 #pragma unroll
 	for (uint32_t d = 0; d < D; ++d) result[d] = 0.0f;
 	const float n_active = active_levels(a);
@@ -239,12 +239,12 @@ __global__ void grid_input_gradient_kernel(const GridKernelArgs a, const __half*
 		}
 	}
 #pragma unroll
-	for (uint32_t d = 0; d < D; ++d) dL_dx[(size_t)i * D + d] = result[d];
+	for (uint32_t d = 0; d < D; ++d) dL_dx[(size_t)i * a.pos_stride + d] = result[d];
 }
 
 bool args_ok(const GridKernelArgs& a) {
 	const uint32_t F = a.n_features_per_level;
-	return a.n_pos_dims >= 2 && a.n_pos_dims <= 4 && (F == 1 || F == 2 || F == 4 || F == 8) && a.n_levels > 0 && a.row_stride >= a.n_levels * F && a.row_stride % F == 0 &&
+	return a.pos_stride >= a.n_pos_dims && a.n_levels * F + a.pad_cols <= a.row_stride && a.n_pos_dims >= 2 && a.n_pos_dims <= 4 && (F == 1 || F == 2 || F == 4 || F == 8) && a.n_levels > 0 && a.row_stride >= a.n_levels * F && a.row_stride % F == 0 &&
 	       a.levels_dev && a.positions;
 }
 

@@ -13,8 +13,10 @@ struct GridKernelArgs {
 	float max_level;                 // fraction of the levels that is active, as GridEncoding::set_max_level (grid.h:69-92); 1 = all
 	const LevelInfo* levels_dev;     // [n_levels] in device memory
 	uint32_t n_elements;
-	const float* positions;          // [n][D] fp32
-	uint32_t row_stride;             // fp16 elements per row of encoded / dL_dy (>= n_levels * F)
+	const float* positions;          // rows [n][pos_stride] fp32, the grid's D coordinates first (a Composite passes a column offset)
+	uint32_t pos_stride;             // floats per row of positions AND of dL_dx (>= D)
+	uint32_t row_stride;             // fp16 elements per row of encoded / dL_dy (>= n_levels * F + pad_cols)
+	uint32_t pad_cols;               // forward: columns behind the features that are zeroed (the grid's own alignment padding)
 	// backward only (optional, see plan_grid_scatter): the coarse levels scatter into one of n_replicas private copies
 	__half* replica_scratch;         // [n_replicas][replica_entries * F] fp16, ZERO on entry (left zero on exit)
 	uint32_t n_replicas;             // 0 / 1 = off
@@ -32,12 +34,12 @@ struct GridScatterPlan {
 };
 GridScatterPlan plan_grid_scatter(const LevelInfo* levels_host, uint32_t n_levels, uint32_t n_features_per_level, uint32_t n_pos_dims, uint32_t n_elements);
 
-// encoded [n][row_stride] fp16 (row = sample; columns level * F + f; columns beyond n_levels * F are zeroed)        grid.h:49-169
+// encoded [n][row_stride] fp16 (row = sample; columns level * F + f; the pad_cols columns behind them are zeroed)        grid.h:49-169
 cudaError_t launch_grid_forward(cudaStream_t stream, const GridKernelArgs& a, const __half* table, __half* encoded);
 // grad_table (fp16, n_params, accumulated INTO: the caller zeroes it) += scatter of dL_dy [n][row_stride] fp16       grid.h:215-320
 // F == 1 accumulates in `tmp_fp32` (n_params floats, zeroed by the caller) and casts at the end, as the reference (grid.h:858-894).
 cudaError_t launch_grid_backward(cudaStream_t stream, const GridKernelArgs& a, const __half* dL_dy, __half* grad_table, float* tmp_fp32, uint32_t n_params);
-// dL_dx [n][D] fp32 = sum over features of dL_dy * d(encoded)/d(position)                                           grid.h:170-212,322-350
+// dL_dx [n][pos_stride] fp32 (first D columns) = sum over features of dL_dy * d(encoded)/d(position)                                           grid.h:170-212,322-350
 cudaError_t launch_grid_input_gradient(cudaStream_t stream, const GridKernelArgs& a, const __half* table, const __half* dL_dy, float* dL_dx);
 
 }  // namespace tcnnb

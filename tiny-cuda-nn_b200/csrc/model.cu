@@ -13,6 +13,7 @@
 
 #include "binning.h"
 #include "common.cuh"
+#include "encoding_plan.h"
 #include "fused_step.h"
 #include "grid_config.h"
 #include "grid_kernels.h"
@@ -160,6 +161,8 @@ struct Model {
 	// inputs, Nearest interpolation, wider encodings / outputs -- run as encoding kernel -> stand-alone MLP kernels -> encoding backward
 	// kernel, with the activations of one batch in HBM (the reference's own structure, object.h / network_with_input_encoding.h).
 	bool general = false;
+	bool plan_only = false;      // an encoding other than one grid / Identity (Composite, Frequency, OneBlob, ...): no fused kernel at all
+	EncodingPlan plan;           // segment table of the encoding (general path)
 	std::string general_reason;  // which limit of the fused kernel sent this configuration here (hyperparams / diagnostics)
 	DeviceBuffer<__half> g_enc, g_hidden, g_out, g_dy, g_grad_hidden, g_denc, g_dy_act;
 	DeviceBuffer<float> g_grid_tmp;  // n_features_per_level == 1: fp32 scatter target (grid.h:858-894)
@@ -262,7 +265,13 @@ static void init_params(Model& m, HostPcg32& rng, float* dst, float scale) {
 		TCNNB_CUDA_CHECK(cudaMemcpy(dst, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
 	}
 	// grid: U(-1e-4, 1e-4) * scale generated on the device with the jump-ahead pattern (grid.h:1076-1079, random.h:56-69)
-	if (m.grid.n_params) {
+	if (m.plan_only) {  // nested encodings draw one after the other from the same stream (composite.h initialize_params)
+		for (auto& g : m.plan.grids) {
+			TCNNB_CUDA_CHECK(launch_random_uniform(nullptr, rng.device(), g->cfg.n_params, dst + mlp.n_params + g->param_offset, -1e-4f * scale, 1e-4f * scale));
+			++g_kernel_launches;
+			rng.advance(g->cfg.n_params);
+		}
+	} else if (m.grid.n_params) {
 		TCNNB_CUDA_CHECK(launch_random_uniform(nullptr, rng.device(), m.grid.n_params, dst + mlp.n_params, -1e-4f * scale, 1e-4f * scale));
 		++g_kernel_launches;
 		rng.advance(m.grid.n_params);
@@ -370,9 +379,22 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 		m.grid.n_params = 0;
 		m.grid.offsets.assign(1, 0u);
 		m.grid.padded_width = next_multiple(n_in, alignment);
-	} else {
+	} else if (plan_detail::is_grid_otype(to_lower(enc_cfg.value("otype", "OneBlob")))) {
 		m.grid = parse_grid(n_in, enc_cfg);
 		m.grid.padded_width = next_multiple(m.grid.n_levels * m.grid.n_features_per_level, alignment);
+	} else {
+		// Composite / Frequency / TriangleWave / OneBlob / SphericalHarmonics (src/encoding.cu:60-120): stand-alone encoding kernels in
+		// front of the stand-alone network kernels. `grid` only carries the totals the rest of the model needs.
+		m.plan_only = true;
+		m.level_scales_dev.resize(128);
+		build_encoding_plan(m.plan, n_in, enc_cfg, alignment, m.level_scales_dev.ptr);
+		m.grid = GridConfig{};
+		m.grid.otype = enc_cfg.value("otype", "OneBlob");
+		m.grid.n_pos_dims = n_in;
+		m.grid.n_levels = 0;
+		m.grid.n_params = (uint32_t)m.plan.n_params;
+		m.grid.offsets.assign(1, 0u);
+		m.grid.padded_width = m.plan.width;
 	}
 
 	mlp.in_width = m.grid.padded_width;
@@ -389,7 +411,8 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 	if (m.grid.stochastic_interpolation) throw std::runtime_error("tcnn_b200: stochastic_interpolation is not built");
 	{
 		const char* why = nullptr;
-		if (mlp.width > 64) why = "n_neurons > 64";
+		if (m.plan_only) why = "an encoding other than one grid / Identity";
+		else if (mlp.width > 64) why = "n_neurons > 64";
 		else if (mlp.n_hidden_layers > 6) why = "n_hidden_layers > 6";
 		else if (mlp.padded_out_width != 16) why = "more than 16 outputs";
 		else if (!m.enc_identity && m.grid.n_features_per_level != 2) why = "n_features_per_level != 2";
@@ -406,10 +429,10 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 			probe.out_width = mlp.padded_out_width;
 			probe.n_hidden_layers = mlp.n_hidden_layers;
 			probe.batch_size = 256;
-			probe.dL_dinput = m.enc_identity ? nullptr : (__half*)16;  // the encoding's backward pass needs dL/d(encoded)
+			probe.dL_dinput = m.grid.n_params == 0 ? nullptr : (__half*)16;  // the encoding's backward pass needs dL/d(encoded)
 			const char* why_not = nullptr;
 			if (!mlp_backward_supported(probe, &why_not)) throw std::runtime_error(std::string(why_not) + " (general path of tcnn_b200; the fused kernel does not cover this configuration: " + why + ")");
-			if (!m.enc_identity) {
+			if (!m.enc_identity && !m.plan_only) {
 				const uint32_t F = m.grid.n_features_per_level, D = m.grid.n_pos_dims;
 				if (!(F == 1 || F == 2 || F == 4 || F == 8)) throw std::runtime_error("GridEncoding: n_features_per_level must be 1, 2, 4, or 8.");
 				if (D < 2 || D > 4) throw std::runtime_error("tcnn_b200: grid encodings cover 2, 3 and 4 input dimensions");
@@ -419,7 +442,8 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 
 	// ---- per-level scales, evaluated on the device like the reference's kernels (common_device.h:886-891)
 	m.level_scales_dev.resize(128);
-	if (!m.enc_identity) evaluate_level_scales(m.grid, m.level_scales_dev.ptr);
+	if (!m.enc_identity && !m.plan_only) evaluate_level_scales(m.grid, m.level_scales_dev.ptr);
+	if (m.general && !m.plan_only) build_encoding_plan(m.plan, n_in, enc_cfg, alignment, m.level_scales_dev.ptr);  // one grid / Identity on the general path
 
 	// ---- parameter buffers (trainer.h:69-87,489-503)
 	m.n_params = (size_t)mlp.n_params + m.grid.n_params;
@@ -576,7 +600,9 @@ static GridKernelArgs grid_kernel_args(Model& m, uint32_t n, const float* x, uin
 	a.levels_dev = m.levels_dev.ptr;
 	a.n_elements = n;
 	a.positions = x;
+	a.pos_stride = m.grid.n_pos_dims;
 	a.row_stride = row_stride;
+	a.pad_cols = row_stride - m.grid.n_levels * m.grid.n_features_per_level;
 	return a;
 }
 
@@ -589,11 +615,16 @@ static void grow(DeviceBuffer<T>& b, size_t n) {
 static void general_forward(Model& m, cudaStream_t stream, uint32_t batch, const float* x, const __half* params, __half* out_fp16, float* out_fp32, bool keep_hidden) {
 	const MlpConfig& mlp = m.mlp;
 	grow(m.g_enc, (size_t)batch * mlp.in_width);
-	if (m.enc_identity) {
-		TCNNB_CUDA_CHECK(launch_identity_encode(stream, batch, m.n_in, mlp.in_width, m.identity_scale, m.identity_offset, x, m.g_enc.ptr));
-	} else {
-		ensure_levels_dev(m, stream);
-		TCNNB_CUDA_CHECK(launch_grid_forward(stream, grid_kernel_args(m, batch, x, mlp.in_width), params + mlp.n_params, m.g_enc.ptr));
+	if (m.plan.has_plain_features()) {
+		TCNNB_CUDA_CHECK(launch_feature_forward(stream, m.plan.segs, batch, x, m.n_in, m.g_enc.ptr, mlp.in_width));
+		++g_kernel_launches;
+	}
+	for (auto& g : m.plan.grids) {
+		const FeatureSegment& sg = m.plan.segs.s[g->segment];
+		GridKernelArgs ga = plan_grid_args(*g, batch, x + sg.in_begin, m.n_in, mlp.in_width);
+		ga.pad_cols = sg.n_pad;
+		TCNNB_CUDA_CHECK(launch_grid_forward(stream, ga, params + mlp.n_params + g->param_offset, m.g_enc.ptr + sg.out_begin));
+		++g_kernel_launches;
 	}
 	MlpForwardParams p{};
 	p.width = mlp.width;
@@ -615,7 +646,7 @@ static void general_forward(Model& m, cudaStream_t stream, uint32_t batch, const
 	const char* why = nullptr;
 	if (!mlp_forward_supported(p, &why)) throw std::runtime_error(why);
 	TCNNB_CUDA_CHECK(launch_mlp_forward(p, (uint32_t)m.n_sms, stream));
-	g_kernel_launches += 2;
+	++g_kernel_launches;
 	m.last_stream = stream;
 }
 
@@ -624,7 +655,7 @@ static void general_forward(Model& m, cudaStream_t stream, uint32_t batch, const
 static void general_backward_pass(Model& m, cudaStream_t stream, uint32_t batch, uint32_t loss_batch, const float* x, const float* y, const __half* params, __half* grads,
                                   const __half* ext_dL_doutput, float* dL_dinput, bool want_param_grads) {
 	const MlpConfig& mlp = m.mlp;
-	const bool grid_params = !m.enc_identity && want_param_grads;
+	const bool grid_params = m.grid.n_params != 0 && want_param_grads;
 	if (grid_params) {
 		TCNNB_CUDA_CHECK(cudaMemsetAsync(grads + mlp.n_params, 0, sizeof(__half) * m.grid.n_params, stream));  // GradientMode::Overwrite (grid.h:865-867)
 	}
@@ -683,38 +714,45 @@ static void general_backward_pass(Model& m, cudaStream_t stream, uint32_t batch,
 	g_kernel_launches += launches;
 	if (want_param_grads) m.mlp_grads_in_accum = true;
 	if (grid_params) {
-		float* tmp = nullptr;
-		if (m.grid.n_features_per_level == 1) {
-			grow(m.g_grid_tmp, m.grid.n_params);
-			TCNNB_CUDA_CHECK(cudaMemsetAsync(m.g_grid_tmp.ptr, 0, sizeof(float) * m.grid.n_params, stream));
-			tmp = m.g_grid_tmp.ptr;
-		}
-		GridKernelArgs ga = grid_kernel_args(m, batch, x, mlp.in_width);
-		{
-			std::vector<LevelInfo> levels(m.grid.n_levels);
-			for (uint32_t l = 0; l < m.grid.n_levels; ++l) levels[l] = make_level_info(m.grid, l);
-			GridScatterPlan plan = plan_grid_scatter(levels.data(), m.grid.n_levels, m.grid.n_features_per_level, m.grid.n_pos_dims, batch);
-			if (m.grid_replicas_override >= 0 && plan.replica_entries) {
-				plan.n_replicas = (uint32_t)m.grid_replicas_override;
-				plan.scratch_halfs = (size_t)plan.n_replicas * plan.replica_entries * m.grid.n_features_per_level;
+		for (auto& g : m.plan.grids) {
+			const FeatureSegment& sg = m.plan.segs.s[g->segment];
+			float* tmp = nullptr;
+			if (g->cfg.n_features_per_level == 1) {
+				grow(m.g_grid_tmp, g->cfg.n_params);
+				TCNNB_CUDA_CHECK(cudaMemsetAsync(m.g_grid_tmp.ptr, 0, sizeof(float) * g->cfg.n_params, stream));
+				tmp = m.g_grid_tmp.ptr;
 			}
-			if (plan.n_replicas > 1) {
-				if (m.g_replicas.n < plan.scratch_halfs) {
-					m.g_replicas.resize(plan.scratch_halfs);
+			GridKernelArgs ga = plan_grid_args(*g, batch, x + sg.in_begin, m.n_in, mlp.in_width);
+			GridScatterPlan sp = plan_grid_scatter(g->levels.data(), g->cfg.n_levels, g->cfg.n_features_per_level, g->cfg.n_pos_dims, batch);
+			if (m.grid_replicas_override >= 0 && sp.replica_entries) {
+				sp.n_replicas = (uint32_t)m.grid_replicas_override;
+				sp.scratch_halfs = (size_t)sp.n_replicas * sp.replica_entries * g->cfg.n_features_per_level;
+			}
+			if (sp.n_replicas > 1) {
+				if (m.g_replicas.n < sp.scratch_halfs) {
+					m.g_replicas.resize(sp.scratch_halfs);
 					m.g_replicas.zero(stream);  // the reduce kernel leaves it zero
 				}
 				ga.replica_scratch = m.g_replicas.ptr;
-				ga.n_replicas = plan.n_replicas;
-				ga.replica_entries = plan.replica_entries;
+				ga.n_replicas = sp.n_replicas;
+				ga.replica_entries = sp.replica_entries;
 			}
+			TCNNB_CUDA_CHECK(launch_grid_backward(stream, ga, m.g_denc.ptr + sg.out_begin, grads + mlp.n_params + g->param_offset, tmp, g->cfg.n_params));
+			++g_kernel_launches;
 		}
-		TCNNB_CUDA_CHECK(launch_grid_backward(stream, ga, m.g_denc.ptr, grads + mlp.n_params, tmp, (uint32_t)m.grid.n_params));
-		++g_kernel_launches;
 	}
 	if (dL_dinput) {
-		if (m.enc_identity) TCNNB_CUDA_CHECK(launch_identity_backward(stream, batch, m.n_in, mlp.in_width, m.identity_scale, m.g_denc.ptr, dL_dinput));
-		else TCNNB_CUDA_CHECK(launch_grid_input_gradient(stream, grid_kernel_args(m, batch, x, mlp.in_width), params + mlp.n_params, m.g_denc.ptr, dL_dinput));
-		++g_kernel_launches;
+		if (m.plan.composite) TCNNB_CUDA_CHECK(cudaMemsetAsync(dL_dinput, 0, sizeof(float) * (size_t)batch * m.n_in, stream));  // dimensions no nested encoding reads
+		if (m.plan.has_plain_features()) {
+			TCNNB_CUDA_CHECK(launch_feature_input_gradient(stream, m.plan.segs, batch, x, m.n_in, m.g_denc.ptr, mlp.in_width, dL_dinput));
+			++g_kernel_launches;
+		}
+		for (auto& g : m.plan.grids) {
+			const FeatureSegment& sg = m.plan.segs.s[g->segment];
+			const GridKernelArgs ga = plan_grid_args(*g, batch, x + sg.in_begin, m.n_in, mlp.in_width);
+			TCNNB_CUDA_CHECK(launch_grid_input_gradient(stream, ga, params + mlp.n_params + g->param_offset, m.g_denc.ptr + sg.out_begin, dL_dinput + sg.in_begin));
+			++g_kernel_launches;
+		}
 	}
 	m.last_stream = stream;
 	m.prof_mark(stream);
@@ -966,6 +1004,7 @@ static void module_backward(Model& m, cudaStream_t stream, uint32_t n, float* dL
 		a.levels_dev = m.levels_dev.ptr;
 		a.n_elements = n;
 		a.positions = x;
+		a.pos_stride = m.grid.n_pos_dims;
 		a.row_stride = 64;
 		TCNNB_CUDA_CHECK(launch_grid_input_gradient(stream, a, (const __half*)params + m.mlp.n_params, m.denc_scratch.ptr, dL_dinput));
 		++g_kernel_launches;
