@@ -68,7 +68,8 @@ def test_encoding_tier_matches_the_oracles(torch_cuda, name):
     got = out.float().cpu().numpy()
     plain = ~np.isnan(want)
     # fp32 evaluation rounded to fp16; the reference's fast-math sin differs from libm's in the last bits: a few fp16 ulps of values <= ~3
-    assert np.abs(got[plain] - want[plain]).max() < 4e-3, np.abs(got[plain] - want[plain]).max()
+    # (relative for the high-degree harmonics of non-unit directions, whose values reach ~50)
+    assert (np.abs(got[plain] - want[plain]) <= 4e-3 * np.maximum(1.0, np.abs(want[plain]))).all(), np.abs(got[plain] - want[plain]).max()
     assert (got[plain].astype(np.float16) != want[plain].astype(np.float16)).mean() < 0.05
 
     # input gradients: analytic oracle per nested encoding; grids through the C oracle
