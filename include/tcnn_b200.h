@@ -71,6 +71,9 @@ const char* tcnnb_hyperparams(tcnnb_model* m);
 /* ---- trainer->set_params_full_precision / set_params (trainer.h:409-440) ---- */
 int tcnnb_set_params_full_precision(tcnnb_model* m, const float* params, uint64_t n, int device_ptr);
 
+/* Trainer::params_inference() (trainer.h:401-403): what network->inference() reads -- the Ema optimizer wrapper's averaged fp16 weights
+ * (optimizers/ema.h) when the configuration has one, else the working parameters. */
+void* tcnnb_params_inference(tcnnb_model* m);
 /* trainer->set_params(params, n, device_ptr) (trainer.h:423-440): working-precision (fp16) parameters; the fp32 masters follow. */
 int tcnnb_set_params(tcnnb_model* m, const void* params_half, uint64_t n, int device_ptr);
 /* Optimizer state for trainer->serialize(true) / deserialize (trainer.h:442-482, optimizers/adam.h:303-325): device pointers to

@@ -628,7 +628,30 @@ static void loss_impl(int loss_type, uint32_t B, uint32_t stride, uint32_t dims,
 		const float pred = h2f(prediction[i]);
 		const float difference = pred - target[target_idx];
 		float value, gradient;
-		if (loss_type == ORC_LOSS_RELATIVE_L2) {
+		if (loss_type == ORC_LOSS_RELATIVE_L2_LUMINANCE) {
+			// losses/relative_l2_luminance.h:66-86: the row's luminance (channels 3..5 folded onto 0..2 when there are 6+ outputs)
+			float r = h2f(prediction[i - intra + 0]), g = h2f(prediction[i - intra + 1]), b = h2f(prediction[i - intra + 2]);
+			if (dims >= 6) {
+				r += h2f(prediction[i - intra + 3]);
+				g += h2f(prediction[i - intra + 4]);
+				b += h2f(prediction[i - intra + 5]);
+			}
+			const float luminance = 0.299f * r + 0.587f * g + 0.114f * b;
+			const float psq = luminance * luminance + 0.01f;
+			value = difference * difference / psq / 1.0f / n_total;
+			gradient = 2 * difference / psq / 1.0f;
+		} else if (loss_type == ORC_LOSS_CROSS_ENTROPY) {
+			// losses/cross_entropy.h:66-75 (the factor already carries 1 / n_total: undone for the common scaling below)
+			const float factor = -target[target_idx] / 1.0f / n_total;
+			value = factor * logf(pred);
+			gradient = factor / pred * n_total;
+		} else if (loss_type == ORC_LOSS_VARIANCE_IS) {
+			// losses/variance_is.h:66-76
+			const float tgt = target[target_idx];
+			const float factor = tgt * tgt / 1.0f / n_total;
+			value = factor / pred - factor / 1.0f;
+			gradient = -factor / (pred * pred) * n_total;
+		} else if (loss_type == ORC_LOSS_RELATIVE_L2) {
 			// losses/relative_l2.h:64-75
 			const float psq = pred * pred + 0.01f;
 			value = difference * difference / psq / 1.0f / n_total;

@@ -15,7 +15,7 @@ LIB = os.path.join(ROOT, "oracle", "liboracle_cpu.so")
 GRID_HASH, GRID_DENSE, GRID_TILED = 0, 1, 2
 INTERP_NEAREST, INTERP_LINEAR, INTERP_SMOOTHSTEP = 0, 1, 2
 ACT = {"relu": 0, "leakyrelu": 1, "silu": 2, "exponential": 3, "sine": 4, "sigmoid": 5, "squareplus": 6, "softplus": 7, "tanh": 8, "none": 9}
-LOSS_L2, LOSS_RELATIVE_L2, LOSS_L1, LOSS_RELATIVE_L1, LOSS_MAPE, LOSS_SMAPE = 0, 1, 2, 3, 4, 5
+LOSS_L2, LOSS_RELATIVE_L2, LOSS_L1, LOSS_RELATIVE_L1, LOSS_MAPE, LOSS_SMAPE, LOSS_RELATIVE_L2_LUMINANCE, LOSS_CROSS_ENTROPY, LOSS_VARIANCE_IS = 0, 1, 2, 3, 4, 5, 6, 7, 8
 ACCUM_FP32, ACCUM_FP16_K16 = 0, 1
 
 
@@ -117,7 +117,7 @@ class OracleModel:
                        ACT[net.get("activation", "ReLU").lower()], ACT[net.get("output_activation", "None").lower()], 0)
         assert lib.orc_mlp_setup(ctypes.byref(self.mlp)) == 0
         self.adam = adam_from_config(config.get("optimizer", {}))
-        self.loss_type = {"l2": LOSS_L2, "relativel2": LOSS_RELATIVE_L2, "l1": LOSS_L1, "relativel1": LOSS_RELATIVE_L1, "mape": LOSS_MAPE, "smape": LOSS_SMAPE}[config.get("loss", {}).get("otype", "RelativeL2").lower()]
+        self.loss_type = {"l2": LOSS_L2, "relativel2": LOSS_RELATIVE_L2, "l1": LOSS_L1, "relativel1": LOSS_RELATIVE_L1, "mape": LOSS_MAPE, "smape": LOSS_SMAPE, "relativel2luminance": LOSS_RELATIVE_L2_LUMINANCE, "crossentropy": LOSS_CROSS_ENTROPY, "variance": LOSS_VARIANCE_IS}[config.get("loss", {}).get("otype", "RelativeL2").lower()]
         self.desc = ModelDesc(ctypes.pointer(self.grid), ctypes.pointer(self.mlp), ctypes.pointer(self.adam), self.loss_type, accum_mode, 128.0)
         self.n_in, self.n_out = n_in, n_out
         self.n_mlp = self.mlp.n_params

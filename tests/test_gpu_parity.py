@@ -539,7 +539,7 @@ def test_torch_autograd_layer_on_the_module_tier(torch_cuda):
     assert xg.grad is not None and torch.isfinite(xg.grad).all()
 
 
-@pytest.mark.parametrize("loss", ["L1", "RelativeL1", "Mape", "Smape"])
+@pytest.mark.parametrize("loss", ["L1", "RelativeL1", "Mape", "Smape", "RelativeL2Luminance", "CrossEntropy", "Variance"])
 def test_other_losses_match_oracle(torch_cuda, loss):
     """src/loss.cu:57-65: the element-wise losses beside L2 / RelativeL2 (losses/l1.h:68-73, relative_l1.h:71-76, mape.h:72-77,
     smape.h:72-77), fused into the output epilogue like them: loss values, loss gradients and everything downstream against the oracle."""
@@ -548,6 +548,8 @@ def test_other_losses_match_oracle(torch_cuda, loss):
 
     cfg = load_cfg("hash3d_small")
     cfg["loss"] = {"otype": loss}
+    if loss in ("CrossEntropy", "Variance"):  # log(prediction) / 1 / prediction (cross_entropy.h:66-75, variance_is.h:66-76): predictions in (0, 1)
+        cfg["network"]["output_activation"] = "Sigmoid"
     B = 1024
     model = tcnn_b200.create_from_config(3, 3, cfg)
     assert model.hyperparams()["loss"]["otype"] == loss
@@ -573,7 +575,7 @@ def test_other_losses_match_oracle(torch_cuda, loss):
         model.trainer.training_step(xd, yd)
         dev_losses.append(model.trainer.loss())
         ref_losses.append(orc.training_step(x, y))
-    assert dev_losses[-1] < dev_losses[0]
+    assert dev_losses[-1] < dev_losses[0] or loss in ("CrossEntropy", "Variance")  # (those two are not distances to the target)
     for u, v in zip(dev_losses, ref_losses):
         assert abs(u - v) <= 5e-2 * abs(v) + 1e-6, (dev_losses, ref_losses)
 
@@ -614,3 +616,38 @@ def test_exponential_decay_wrapper_follows_the_schedule(torch_cuda):
         bad = json.loads(json.dumps(ocfg))
         bad["optimizer"] = {"otype": "Shampoo"}
         tcnn_b200.create_from_config(3, 3, bad)
+
+
+def test_ema_wrapper_averages_the_weights_inference_reads(torch_cuda):
+    """optimizers/ema.h:46-132 around (ExponentialDecay around) Adam: after every step the debiased moving average of the fp16 working weights
+    is updated; network->inference() reads the average (Trainer::params_inference, trainer.h:497-502), training keeps the raw weights."""
+    torch = torch_cuda
+    import tcnn_b200
+
+    cfg = load_cfg("hash3d_small")
+    decay = 0.9
+    cfg["optimizer"] = {"otype": "Ema", "decay": decay, "nested": {"otype": "ExponentialDecay", "decay_start": 2, "decay_interval": 2, "decay_base": 0.5, "nested": cfg["optimizer"]}}
+    model = tcnn_b200.create_from_config(3, 3, cfg)
+    plain_cfg = json.loads(json.dumps(cfg))
+    plain_cfg["optimizer"] = cfg["optimizer"]["nested"]
+    plain = tcnn_b200.create_from_config(3, 3, plain_cfg)
+    x, y = make_batch(3, 3, 512)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    assert torch.equal(model.trainer.params_inference(), model.trainer.params())  # starts as the initial parameters (trainer.h:415-419)
+    ema = None
+    for step in range(1, 7):
+        model.trainer.training_step(xd, yd)
+        plain.trainer.training_step(xd, yd)
+        w = model.trainer.params().float().cpu().numpy()
+        # ema.h:46-75 restated: fp16 storage of the average, fp32 arithmetic
+        prev = np.zeros_like(w) if ema is None else ema
+        ema = ((prev * np.float32(decay) * np.float32(1 - decay ** (step - 1)) + w * np.float32(1 - decay)) * np.float32(1.0 / (1 - decay ** step))).astype(np.float16).astype(np.float32)
+        got = model.trainer.params_inference().float().cpu().numpy()
+        assert np.abs(got - ema).max() <= 2.0 ** -10 * max(1e-3, np.abs(ema).max()), step
+    # the wrapper does not touch training: same weights as the plain optimizer
+    assert torch.equal(model.trainer.params(), plain.trainer.params())
+    # inference reads the averaged weights: equal to the plain model's inference once it is given them
+    out = model.network.inference(xd)
+    plain.trainer.set_params(model.trainer.params_inference())
+    assert torch.equal(out, plain.network.inference(xd))
+    assert not torch.equal(model.trainer.params_inference(), model.trainer.params())

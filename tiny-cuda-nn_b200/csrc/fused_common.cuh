@@ -91,12 +91,15 @@ __device__ __forceinline__ uint32_t act_bwd_pack(uint32_t act, uint32_t lo_bits,
 	return *reinterpret_cast<const uint32_t*>(&y);
 }
 
-// One element of the loss (src/loss.cu:57-90; losses/l2.h:56-74, relative_l2.h:56-75, l1.h:68-73, relative_l1.h:71-76, mape.h:72-77,
-// smape.h:72-77): `value` is already divided by n_total = loss-batch size x output dims, `grad` is d(value)/d(pred) x n_total.
-__device__ __forceinline__ void loss_element(uint32_t loss_type, float pred, float target, float n_total, float& value, float& grad) {
+// One element of the loss (src/loss.cu:57-66; losses/l2.h:56-74, relative_l2.h:56-75, relative_l2_luminance.h:40-86, l1.h:68-73,
+// relative_l1.h:71-76, mape.h:72-77, smape.h:72-77, cross_entropy.h:40-76, variance_is.h:40-77; data_pdf == 1): `value` is already
+// divided by n_total = loss-batch size x output dims, `grad` is d(value)/d(pred) x n_total. `luminance`: of the row's predictions
+// (RelativeL2Luminance only, see row_luminance).
+__device__ __forceinline__ void loss_element(uint32_t loss_type, float pred, float target, float n_total, float luminance, float& value, float& grad) {
 	const float diff = pred - target;
-	if (loss_type == LOSS_RELATIVE_L2) {
-		const float psq = pred * pred + 0.01f;
+	if (loss_type == LOSS_RELATIVE_L2 || loss_type == LOSS_RELATIVE_L2_LUMINANCE) {
+		const float base = loss_type == LOSS_RELATIVE_L2 ? pred : luminance;
+		const float psq = base * base + 0.01f;
 		value = diff * diff / psq / n_total;
 		grad = 2.0f * diff / psq;
 	} else if (loss_type == LOSS_L2) {
@@ -105,12 +108,32 @@ __device__ __forceinline__ void loss_element(uint32_t loss_type, float pred, flo
 	} else if (loss_type == LOSS_L1) {
 		value = fabsf(diff) / n_total;
 		grad = copysignf(1.0f, diff);
+	} else if (loss_type == LOSS_CROSS_ENTROPY) {
+		const float factor = -target / n_total;
+		value = factor * logf(pred);
+		grad = factor / pred * n_total;
+	} else if (loss_type == LOSS_VARIANCE_IS) {
+		const float factor = target * target / n_total;
+		value = factor / pred - factor;
+		grad = -factor / (pred * pred) * n_total;
 	} else {  // RelativeL1 / Mape / Smape
 		const float denom = loss_type == LOSS_RELATIVE_L1 ? fabsf(pred) : (loss_type == LOSS_MAPE ? fabsf(target) : 0.5f * (fabsf(target) + fabsf(pred)));
 		const float scale = 1.0f / (denom + 1e-2f);
 		value = fabsf(diff) * scale / n_total;
 		grad = copysignf(scale, diff);
 	}
+}
+
+// 0.299 r + 0.587 g + 0.114 b of a row of predictions; with 6 or more outputs, channels 3..5 are added to 0..2 first
+// (relative_l2_luminance.h:69-77). `row`: the first 6 predictions of the sample.
+__device__ __forceinline__ float row_luminance(const __half* row, uint32_t dims) {
+	float r = __half2float(row[0]), g = __half2float(row[1]), b = __half2float(row[2]);
+	if (dims >= 6) {
+		r += __half2float(row[3]);
+		g += __half2float(row[4]);
+		b += __half2float(row[5]);
+	}
+	return 0.299f * r + 0.587f * g + 0.114f * b;
 }
 
 struct SmemSync {

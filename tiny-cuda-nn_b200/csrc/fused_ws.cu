@@ -509,6 +509,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 						// relative_l2_loss / l2_loss (losses/relative_l2.h:56-75, l2.h:56-74); pad lanes give 0.
 						__half dy[16];
 						const float n_total = (float)(p.loss_batch_size * p.n_out);
+						const float luminance = p.loss_type == LOSS_RELATIVE_L2_LUMINANCE ? row_luminance(y16, p.n_out) : 0.0f;
 						if (p.ext_dy) {
 							// Module::backward (cpp_api.cu:115-124): dL/d(output) comes from the caller and, like the loss gradient below,
 							// passes through the output activation's transfer (fully_fused_mlp.cu:758-762)
@@ -524,7 +525,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 								const float pred = __half2float(y16[q]);
 								const float target = q < N_TGT_PREFETCH ? tgt[q] : __ldg(p.targets + (size_t)osample * p.n_out + q);
 								float value, grad;
-								loss_element(p.loss_type, pred, target, n_total, value, grad);
+								loss_element(p.loss_type, pred, target, n_total, luminance, value, grad);
 								gq = p.loss_scale * grad / n_total;
 								loss_acc += value;
 								if (p.loss_values) p.loss_values[(size_t)osample * p.n_out + q] = value;

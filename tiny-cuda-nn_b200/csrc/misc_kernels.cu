@@ -213,13 +213,14 @@ __global__ void loss_kernel(uint32_t loss_type, uint32_t out_act, uint32_t batch
 		const uint4 raw = *reinterpret_cast<const uint4*>(prediction + (size_t)sample * stride + q0);
 		const __half* y = reinterpret_cast<const __half*>(&raw);
 		__half dy[8];
+		const float luminance = loss_type == LOSS_RELATIVE_L2_LUMINANCE ? fused::row_luminance(prediction + (size_t)sample * stride, n_out) : 0.0f;
 #pragma unroll
 		for (uint32_t k = 0; k < 8; ++k) {
 			const uint32_t q = q0 + k;
 			float gq = 0.0f;
 			if (q < n_out) {
 				float value, grad;
-				fused::loss_element(loss_type, __half2float(y[k]), targets[(size_t)sample * n_out + q], n_total, value, grad);
+				fused::loss_element(loss_type, __half2float(y[k]), targets[(size_t)sample * n_out + q], n_total, luminance, value, grad);
 				gq = loss_scale * grad / n_total;
 				value_sum += value;
 				if (loss_values) loss_values[(size_t)sample * n_out + q] = value;
@@ -247,6 +248,19 @@ __global__ void activation_backward_output_kernel(uint32_t act, uint64_t n, cons
 	pdl_launch_dependents();
 	const uint64_t i = threadIdx.x + (uint64_t)blockIdx.x * blockDim.x;
 	if (i < n) out[i] = fused::act_bwd_h(act, grad[i], fwd[i]);
+}
+
+// optimizers/ema.h:46-75: debiased exponential moving average of the working weights; `tmp` (fp32 copy of the average) when the
+// wrapper runs in full precision.
+__global__ void ema_step_kernel(uint32_t n, float decay, float debias_old, float debias_new, const __half* __restrict__ weights, __half* __restrict__ weights_ema, float* __restrict__ tmp) {
+	pdl_wait();
+	pdl_launch_dependents();
+	const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
+	if (i >= n) return;
+	const float prev = tmp ? tmp[i] : __half2float(weights_ema[i]);
+	const float filtered = (prev * decay * debias_old + __half2float(weights[i]) * (1.0f - decay)) * debias_new;
+	if (tmp) tmp[i] = filtered;
+	weights_ema[i] = __float2half_rn(filtered);
 }
 
 // Identity encoding on its own (encodings/identity.h:46-67,69-91): rows [n][width] fp16, feature j < n_dims = x_j * scale + offset,
@@ -422,6 +436,11 @@ cudaError_t launch_loss(cudaStream_t stream, uint32_t loss_type, uint32_t output
 cudaError_t launch_activation_backward_output(cudaStream_t stream, uint32_t activation, uint64_t n, const __half* grad, const __half* forward_output, __half* out) {
 	if (n == 0) return cudaSuccess;
 	return launch_pdl(activation_backward_output_kernel, (uint32_t)((n + 255) / 256), 256, 0, stream, activation, n, grad, forward_output, out);
+}
+
+cudaError_t launch_ema_step(cudaStream_t stream, uint32_t n, float decay, float debias_old, float debias_new, const __half* weights, __half* weights_ema, float* tmp) {
+	if (n == 0) return cudaSuccess;
+	return launch_pdl(ema_step_kernel, blocks_for(n, 256), 256, 0, stream, n, decay, debias_old, debias_new, weights, weights_ema, tmp);
 }
 
 cudaError_t launch_identity_encode(cudaStream_t stream, uint32_t n, uint32_t n_dims, uint32_t width, float scale, float offset, const float* x, __half* out) {

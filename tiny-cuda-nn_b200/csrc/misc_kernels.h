@@ -39,6 +39,8 @@ cudaError_t launch_loss(cudaStream_t stream, uint32_t loss_type, uint32_t output
 // out = grad * f'(.) of the output activation, expressed through the forward output (element-wise, fp16).
 cudaError_t launch_activation_backward_output(cudaStream_t stream, uint32_t activation, uint64_t n, const __half* grad, const __half* forward_output, __half* out);
 
+// Ema wrapper (optimizers/ema.h:46-75): weights_ema = (weights_ema * decay * debias_old + weights * (1 - decay)) * debias_new; tmp optional (fp32 average)
+cudaError_t launch_ema_step(cudaStream_t stream, uint32_t n, float decay, float debias_old, float debias_new, const __half* weights, __half* weights_ema, float* tmp);
 // Identity encoding (encodings/identity.h:46-91) as stand-alone kernels: rows [n][width] fp16 with ones as padding; dL/dx in fp32.
 cudaError_t launch_identity_encode(cudaStream_t stream, uint32_t n, uint32_t n_dims, uint32_t width, float scale, float offset, const float* x, __half* out);
 cudaError_t launch_identity_backward(cudaStream_t stream, uint32_t n, uint32_t n_dims, uint32_t width, float scale, const __half* dL_dy, float* dL_dx);

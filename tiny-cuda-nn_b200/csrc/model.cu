@@ -133,6 +133,13 @@ struct Model {
 		float base = 0.1f, factor = 1.0f;
 		uint32_t interval = 10000, start = 10000, end = 10000000;
 	} lr_decay;
+	struct {  // Ema wrapper (optimizers/ema.h:46-200): exponential moving average of the working weights, used by inference
+		bool enabled = false, full_precision = false;
+		float decay = 0.99f;
+	} ema;
+	DeviceBuffer<__half> ema_fp16;  // Trainer::params_inference() (trainer.h:401-403, 497-502)
+	DeviceBuffer<float> ema_tmp;
+	const __half* inference_params() const { return ema.enabled ? ema_fp16.ptr : params_fp16; }
 	float loss_scale = 128.0f;  // default_loss_scale<__half>() (common.h:243)
 	int device = 0;
 	int n_sms = 148;
@@ -305,30 +312,42 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 	else if (ieq(m.loss_name, "RelativeL1")) m.loss_type = LOSS_RELATIVE_L1;
 	else if (ieq(m.loss_name, "Mape")) m.loss_type = LOSS_MAPE;
 	else if (ieq(m.loss_name, "Smape")) m.loss_type = LOSS_SMAPE;
-	else {
-		static const char* known[] = {"RelativeL2Luminance", "CrossEntropy", "Variance"};
-		for (auto k : known) if (ieq(m.loss_name, k)) throw std::runtime_error("Loss '" + m.loss_name + "' is outside the tcnn_b200 hot path (L2, RelativeL2, L1, RelativeL1, Mape and Smape are built)");
-		throw std::runtime_error("Loss '" + m.loss_name + "' not found");
-	}
+	else if (ieq(m.loss_name, "RelativeL2Luminance")) {
+		if (n_out < 3) throw std::runtime_error("tcnn_b200: RelativeL2Luminance needs at least 3 outputs (r, g, b)");
+		m.loss_type = LOSS_RELATIVE_L2_LUMINANCE;
+	} else if (ieq(m.loss_name, "CrossEntropy")) m.loss_type = LOSS_CROSS_ENTROPY;
+	else if (ieq(m.loss_name, "Variance")) m.loss_type = LOSS_VARIANCE_IS;
+	else throw std::runtime_error("Loss '" + m.loss_name + "' not found");
 
 	// ---- optimizer (src/optimizer.cu:50-80, adam.h:221-303)
 	const json::Value* opt_ptr = &cfg.sub("optimizer");
 	std::string opt_name = opt_ptr->value("otype", "Adam");
-	if (ieq(opt_name, "ExponentialDecay")) {
-		// optimizers/exponential_decay.h:46-160: a learning-rate schedule around the nested optimizer -- from step decay_start on, every
-		// decay_interval steps (until decay_end) the learning rate is multiplied by decay_base. Host-side bookkeeping only.
-		m.lr_decay.enabled = true;
-		m.lr_decay.base = (float)opt_ptr->value("decay_base", 0.1);
-		m.lr_decay.interval = (uint32_t)opt_ptr->value("decay_interval", 10000.0);
-		m.lr_decay.start = (uint32_t)opt_ptr->value("decay_start", 10000.0);
-		m.lr_decay.end = (uint32_t)opt_ptr->value("decay_end", 10000000.0);
-		if (m.lr_decay.interval == 0) throw std::runtime_error("ExponentialDecay: decay_interval must be positive.");
+	// wrappers around the nested optimizer, in any order: ExponentialDecay (a learning-rate schedule) and Ema (averaged inference weights)
+	while (ieq(opt_name, "ExponentialDecay") || ieq(opt_name, "Ema")) {
+		if (ieq(opt_name, "ExponentialDecay")) {
+			// optimizers/exponential_decay.h:46-160: from step decay_start on, every decay_interval steps (until decay_end) the learning
+			// rate is multiplied by decay_base. Host-side bookkeeping only.
+			if (m.lr_decay.enabled) throw std::runtime_error("tcnn_b200: one ExponentialDecay wrapper per optimizer");
+			m.lr_decay.enabled = true;
+			m.lr_decay.base = (float)opt_ptr->value("decay_base", 0.1);
+			m.lr_decay.interval = (uint32_t)opt_ptr->value("decay_interval", 10000.0);
+			m.lr_decay.start = (uint32_t)opt_ptr->value("decay_start", 10000.0);
+			m.lr_decay.end = (uint32_t)opt_ptr->value("decay_end", 10000000.0);
+			if (m.lr_decay.interval == 0) throw std::runtime_error("ExponentialDecay: decay_interval must be positive.");
+		} else {
+			// optimizers/ema.h:46-200: after every step of the nested optimizer, ema = (ema * decay * (1 - decay^(t-1)) + w * (1 - decay)) /
+			// (1 - decay^t) on the working-precision weights; network->inference() reads the average (Trainer::params_inference).
+			if (m.ema.enabled) throw std::runtime_error("tcnn_b200: one Ema wrapper per optimizer");
+			m.ema.enabled = true;
+			m.ema.decay = (float)opt_ptr->value("decay", 0.99);
+			m.ema.full_precision = opt_ptr->value("full_precision", false);
+		}
 		opt_ptr = &opt_ptr->sub("nested");
 		opt_name = opt_ptr->value("otype", "Adam");
 	}
 	const json::Value& opt = *opt_ptr;
 	if (!ieq(opt_name, "Adam")) {
-		throw std::runtime_error("Optimizer '" + opt_name + "' is outside the tcnn_b200 hot path (Adam, optionally inside ExponentialDecay, is built)");
+		throw std::runtime_error("Optimizer '" + opt_name + "' is outside the tcnn_b200 hot path (Adam, optionally inside ExponentialDecay and / or Ema, is built)");
 	}
 	AdamParams& a = m.adam;
 	a.beta1 = (float)opt.value("beta1", (double)a.beta1);
@@ -480,6 +499,14 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 		// fp32 -> fp16 (trainer.h:409-421)
 		TCNNB_CUDA_CHECK(launch_cast_params(nullptr, m.n_params, m.params_fp32, m.params_fp16));
 		++g_kernel_launches;
+		if (m.ema.enabled) {  // trainer.h:409-421: the inference parameters start as the initial parameters
+			m.ema_fp16.resize(m.n_params_padded);
+			TCNNB_CUDA_CHECK(cudaMemcpy(m.ema_fp16.ptr, m.params_fp16, sizeof(__half) * m.n_params_padded, cudaMemcpyDeviceToDevice));
+			if (m.ema.full_precision) {
+				m.ema_tmp.resize(m.n_params);
+				m.ema_tmp.zero();
+			}
+		}
 	}
 	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
 	TCNNB_CUDA_CHECK(cudaStreamCreateWithFlags(&m.own_stream, cudaStreamNonBlocking));
@@ -578,6 +605,13 @@ static void optimizer_step(Model& m, cudaStream_t stream, uint32_t n_ranges = 0,
 		++g_kernel_launches;
 	}
 	if (covers_mlp) m.mlp_grads_in_accum = false;
+	if (m.ema.enabled) {
+		if (n_ranges != 1 || begins[0] != 0 || counts[0] != m.n_params) throw std::runtime_error("tcnn_b200: the Ema wrapper is built for whole-vector optimizer steps (not for the sharded data-parallel optimizer)");
+		const float t = (float)m.adam_step_count;
+		TCNNB_CUDA_CHECK(launch_ema_step(stream, (uint32_t)m.n_params, m.ema.decay, 1.0f - std::pow(m.ema.decay, t - 1.0f), 1.0f / (1.0f - std::pow(m.ema.decay, t)), m.params_fp16, m.ema_fp16.ptr,
+		                                 m.ema.full_precision ? m.ema_tmp.ptr : nullptr));
+		++g_kernel_launches;
+	}
 }
 
 static void ensure_levels_dev(Model& m, cudaStream_t stream) {
@@ -917,10 +951,11 @@ static void inference(Model& m, cudaStream_t stream, uint32_t batch, const float
 	if (m.module_only) throw std::runtime_error("this handle was created with tcnnb_module_create: use the tcnnb_module_* calls.");
 	m.wait_pending(stream);
 	if (m.general) {
-		general_forward(m, stream, batch, x, m.params_fp16, nullptr, out, false);
+		general_forward(m, stream, batch, x, m.inference_params(), nullptr, out, false);
 		return;
 	}
 	FusedStepParams p = make_params(m, batch, batch, x, nullptr);
+	p.params = m.inference_params();
 	p.out_fp32 = out;
 	p.loss_sum = nullptr;
 	launch_inference(m, p, batch, stream);
@@ -1250,9 +1285,13 @@ int tcnnb_set_params_full_precision(tcnnb_model* m, const float* params, uint64_
 	TCNNB_CUDA_CHECK(cudaMemcpy(mm.params_fp32, params, sizeof(float) * n, device_ptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
 	TCNNB_CUDA_CHECK(launch_cast_params(nullptr, mm.n_params, mm.params_fp32, mm.params_fp16));
 	++g_kernel_launches;
+	if (mm.ema.enabled) TCNNB_CUDA_CHECK(cudaMemcpy(mm.ema_fp16.ptr, mm.params_fp16, sizeof(__half) * n, cudaMemcpyDeviceToDevice));  // trainer.h:415-419
 	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
 	TCNNB_API_END
 }
+
+// Trainer::params_inference() (trainer.h:401-403): the Ema wrapper's averaged weights when there is one, else the working parameters.
+void* tcnnb_params_inference(tcnnb_model* m) { return (void*)m->impl.inference_params(); }
 
 int tcnnb_set_params(tcnnb_model* m, const void* params_half, uint64_t n, int device_ptr) {
 	TCNNB_API_BEGIN
@@ -1264,6 +1303,7 @@ int tcnnb_set_params(tcnnb_model* m, const void* params_half, uint64_t n, int de
 	TCNNB_CUDA_CHECK(cudaMemcpy(mm.params_fp16, params_half, n * sizeof(__half), device_ptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
 	half_to_float_kernel<<<(uint32_t)((n + 255) / 256), 256>>>(n, mm.params_fp16, mm.params_fp32);
 	++g_kernel_launches;
+	if (mm.ema.enabled) TCNNB_CUDA_CHECK(cudaMemcpy(mm.ema_fp16.ptr, mm.params_fp16, sizeof(__half) * n, cudaMemcpyDeviceToDevice));  // trainer.h:428-429
 	TCNNB_CUDA_CHECK(cudaDeviceSynchronize());
 	TCNNB_API_END
 }
@@ -1272,6 +1312,7 @@ int tcnnb_optimizer_state(tcnnb_model* m, float** first_moments_dev, float** sec
 	TCNNB_API_BEGIN
 	Model& mm = m->impl;
 	if (mm.module_only) throw std::runtime_error("this handle was created with tcnnb_module_create: it has no optimizer.");
+	if (mm.ema.enabled) throw std::runtime_error("tcnn_b200: snapshots of the Ema wrapper's state are not built (serialize the parameters only)");
 	if (mm.dp && mm.dp->world > 1 && mm.dp->shard_optimizer) {
 		throw std::runtime_error("optimizer state is sharded over the data-parallel ranks: each rank holds the moments of its own slice only");
 	}
@@ -1387,6 +1428,7 @@ int tcnnb_serialize(tcnnb_model* m, void* dst_host, uint64_t size, int with_opti
 	TCNNB_API_BEGIN
 	Model& mm = m->impl;
 	if (size < tcnnb_serialize_size(m, with_optimizer)) throw std::runtime_error("tcnnb_serialize: destination too small");
+	if (with_optimizer && mm.ema.enabled) throw std::runtime_error("tcnn_b200: snapshots of the Ema wrapper's state are not built (serialize with_optimizer = 0)");
 	if (with_optimizer && mm.dp && mm.dp->world > 1 && mm.dp->shard_optimizer) {
 		// moments / step counters are current on the owner of a slice only (ZeRO-1): a snapshot of one rank would silently hold stale state
 		throw std::runtime_error("tcnnb_serialize: optimizer state is sharded over the data-parallel ranks; serialize with_optimizer = 0 (after tcnnb_dp_sync_full_precision) or from a single-GPU trainer");
@@ -1454,6 +1496,7 @@ int tcnnb_dp_init(tcnnb_model* m, const void* id_grads, const void* id_params, i
 	TCNNB_API_BEGIN
 	Model& mm = m->impl;
 	if (world_size < 1 || rank < 0 || rank >= world_size) throw std::runtime_error("dp_init: bad world size / rank.");
+	if (mm.ema.enabled && world_size > 1) throw std::runtime_error("tcnn_b200: the Ema optimizer wrapper is not built for the data-parallel engines");
 	auto d = std::make_unique<DpState>();
 	d->world = world_size;
 	d->rank = rank;

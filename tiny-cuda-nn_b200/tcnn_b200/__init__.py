@@ -52,6 +52,7 @@ ABI = [
     ("tcnnb_encoded_width", _u32, [_vp]),
     ("tcnnb_params_full_precision", _vp, [_vp]),
     ("tcnnb_params", _vp, [_vp]),
+    ("tcnnb_params_inference", _vp, [_vp]),
     ("tcnnb_param_gradients", _vp, [_vp]),
     ("tcnnb_grid_levels", _int, [_vp, ctypes.POINTER(_u32), ctypes.POINTER(_u32), _f32p, ctypes.POINTER(_u32)]),
     ("tcnnb_hyperparams", ctypes.c_char_p, [_vp]),
@@ -245,6 +246,12 @@ class _Trainer:
 
         return self._view(load().tcnnb_params(self._m._h), self._m.n_params, torch.float16)
 
+    def params_inference(self):
+        """Trainer::params_inference(): the Ema wrapper's averaged weights when the optimizer has one, else params()."""
+        import torch
+
+        return self._view(load().tcnnb_params_inference(self._m._h), self._m.n_params, torch.float16)
+
     def param_gradients(self):
         import torch
 
@@ -349,6 +356,13 @@ class _Trainer:
         else:
             p = params.contiguous().to(torch.float32)
             _check(load().tcnnb_set_params_full_precision(self._m._h, p.data_ptr(), p.numel(), 0))
+
+    def set_params(self, params16):
+        """trainer->set_params (trainer.h:423-440): fp16 working parameters; the fp32 masters follow."""
+        import torch
+
+        p = params16.contiguous().to(torch.float16)
+        _check(load().tcnnb_set_params(self._m._h, p.data_ptr(), p.numel(), 1 if p.is_cuda else 0))
 
     def serialize(self, with_optimizer=False):
         n = load().tcnnb_serialize_size(self._m._h, int(with_optimizer))
