@@ -1137,6 +1137,10 @@ static std::string make_hyperparams(const Model& m) {
 		enc["otype"] = json::Value::string("Identity");
 		enc["scale"] = json::Value::number(m.identity_scale);
 		enc["offset"] = json::Value::number(m.identity_offset);
+	} else if (m.plan_only) {
+		enc["otype"] = json::Value::string(m.grid.otype);
+		enc["n_nested"] = json::Value::number(m.plan.segs.n);
+		enc["n_output_dims"] = json::Value::number(m.plan.width);
 	} else {
 	enc["otype"] = json::Value::string("Grid");
 	enc["type"] = json::Value::string(m.grid.grid_type == GRID_HASH ? "Hash" : (m.grid.grid_type == GRID_DENSE ? "Dense" : "Tiled"));
@@ -1155,8 +1159,8 @@ static std::string make_hyperparams(const Model& m) {
 	net["n_neurons"] = json::Value::number(m.mlp.width);
 	net["n_hidden_layers"] = json::Value::number(m.mlp.n_hidden_layers);
 	json::Value& loss = root["loss"];
-	static const char* loss_names[] = {"L2", "RelativeL2", "L1", "RelativeL1", "Mape", "Smape"};
-	loss["otype"] = json::Value::string(loss_names[m.loss_type]);
+	static const char* loss_names[] = {"L2", "RelativeL2", "L1", "RelativeL1", "Mape", "Smape", "RelativeL2Luminance", "CrossEntropy", "Variance"};
+	loss["otype"] = json::Value::string(m.loss_type < sizeof(loss_names) / sizeof(loss_names[0]) ? loss_names[m.loss_type] : m.loss_name.c_str());
 	json::Value& opt = root["optimizer"];
 	opt["otype"] = json::Value::string("Adam");
 	opt["learning_rate"] = json::Value::number(m.adam.learning_rate);
@@ -1274,7 +1278,12 @@ int tcnnb_grid_levels(const tcnnb_model* m, uint32_t* n_levels, uint32_t* offset
 }
 
 const char* tcnnb_hyperparams(tcnnb_model* m) {
-	m->impl.hyperparams_json = make_hyperparams(m->impl);
+	try {
+		m->impl.hyperparams_json = make_hyperparams(m->impl);
+	} catch (const std::exception& e) {  // nothing may propagate through the C boundary
+		g_last_error = e.what();
+		m->impl.hyperparams_json = "{}";
+	}
 	return m->impl.hyperparams_json.c_str();
 }
 
