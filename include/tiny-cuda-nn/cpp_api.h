@@ -8,7 +8,7 @@
  * param_precision() (fp16); gradients are OVERWRITTEN; a null result pointer means "do not compute"; factories return owning raw
  * pointers. Differences, by design: forward() keeps no activations (backward recomputes the forward pass inside the fused kernel),
  * so the returned Context only marks "a forward pass was made"; jit fusion does not exist (the fused kernel is the product);
- * backward_backward_input and a backward pass through the stand-alone network throw. */
+ * backward_backward_input throws. */
 #pragma once
 #if __has_include(<json/json.hpp>)
 #include <json/json.hpp>
@@ -154,8 +154,8 @@ public:
 		inference(stream, n, input, output, params);
 		return made_forward_pass();
 	}
-	void backward(cudaStream_t, const Context&, uint32_t, float*, const void*, void*, const float*, const void*, const void*) override {
-		throw std::runtime_error{"tcnn_b200: the stand-alone network is built for inference / forward; train through create_network_with_input_encoding"};
+	void backward(cudaStream_t stream, const Context&, uint32_t n, float* dL_dinput, const void* dL_doutput, void* dL_dparams, const float* input, const void*, const void* params) override {
+		TCNNB_CPP_CHECK(tcnnb_network_module_backward(m_h, (tcnnb_stream)stream, n, dL_dinput, dL_doutput, dL_dparams, input, params));
 	}
 	void backward_backward_input(cudaStream_t, const Context&, uint32_t, const float*, const float*, const void*, void*, void*, float*, const void*) override {
 		throw std::runtime_error{"tcnn_b200: second-order derivatives (backward_backward_input) are outside the built path"};

@@ -167,9 +167,22 @@ def test_torch_layers_deliver_input_gradients(torch_cuda):
     x2 = torch.rand(512, 3, device="cuda", requires_grad=True)
     model(x2).float().sum().backward()
     assert x2.grad is not None and torch.isfinite(x2.grad).all()
+    # the stand-alone network (tinycudann.Network): autograd w.r.t. parameters and inputs, against torch fp32 on the same fp16 weights
     net = tcnn.Network(3, 3, {"otype": "CutlassMLP", "n_neurons": 64, "n_hidden_layers": 2})
-    out = net(torch.rand(300, 3, device="cuda"))
-    assert out.shape == (300, 3) and out.dtype == torch.float32 and torch.isfinite(out).all()
+    x3 = torch.rand(300, 3, device="cuda", requires_grad=True)
+    out = net(x3)
+    assert out.shape == (300, 3) and out.dtype == torch.float16 and torch.isfinite(out).all()
+    out.float().square().sum().backward()
+    w = net.params.detach().half().float()
+    W0, W1, Wo = w[: 64 * 16].view(64, 16).clone().requires_grad_(True), w[1024 : 1024 + 4096].view(64, 64).clone().requires_grad_(True), w[5120:].view(16, 64).clone().requires_grad_(True)
+    xr = x3.detach().clone().requires_grad_(True)
+    xin = torch.cat([xr.half().float(), torch.ones(300, 13, device="cuda")], 1)
+    ref = (torch.relu(torch.relu(xin @ W0.T) @ W1.T) @ Wo.T)[:, :3]
+    ref.square().sum().backward()
+    want = torch.cat([W0.grad.flatten(), W1.grad.flatten(), Wo.grad.flatten()])
+    assert torch.allclose(out.float(), ref, rtol=2e-2, atol=2e-3)
+    assert float((net.params.grad - want).abs().mean()) < 2e-2 * float(want.abs().mean())
+    assert float((x3.grad - xr.grad).abs().mean()) < 3e-2 * float(xr.grad.abs().mean())
 
 
 @pytest.mark.parametrize("n_in,F", [(2, 2), (3, 4), (3, 8)])

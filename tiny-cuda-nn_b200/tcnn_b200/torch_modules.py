@@ -5,14 +5,14 @@
     y = model(x)                      # x: [B, n_input_dims] float CUDA tensor -> [B, n_output_dims] fp16
     loss.backward(); torch_optimizer.step()   # model.params is a torch.nn.Parameter (fp32), as in tinycudann
     enc = tcnn.Encoding(3, enc_config)        # the grid encoding on its own (modules.py:312-330), fp16 features
-    net = tcnn.Network(32, 3, net_config)     # the network on its own (modules.py:248-268), inference / forward
+    net = tcnn.Network(32, 3, net_config)     # the network on its own (modules.py:248-268)
 
 Same conventions as the reference binding: parameters are an fp32 `torch.nn.Parameter` initialised by
 `Module::initialize_params(seed)`, cast to fp16 for every call (modules.py:227-231); the batch is padded to the granularity of
 256 (modules.py:222-226); gradients w.r.t. the output are multiplied by the loss scale (128 for fp16) before the native
 backward pass and the parameter / input gradients divided by it afterwards (modules.py:166-171); the padded output columns are
 sliced away (modules.py:233). Gradients w.r.t. the input positions are delivered when the input requires grad (modules.py:153-160).
-Not supported: second-order terms (bwd_bwd_input), and a backward pass through the stand-alone Network.
+Not supported: second-order terms (bwd_bwd_input).
 
 This file is glue: the work happens in libtcnn_b200 (fused sm_100a kernels) behind `tcnnb_module_*`, `tcnnb_encoding_*`, `tcnnb_network_*`.
 """
@@ -92,7 +92,7 @@ class NetworkWithInputEncoding(_TcnnModule):
 
 
 class Encoding(_TcnnModule):
-    """tinycudann.Encoding (modules.py:312-330) for the grid encodings: fp16 features [B, n_levels * n_features_per_level]."""
+    """tinycudann.Encoding (modules.py:312-330): grids, Identity, Frequency, TriangleWave, OneBlob, SphericalHarmonics, Composite; fp16 features."""
 
     def __init__(self, n_input_dims, encoding_config, seed=1337):
         self.encoding_config = encoding_config
@@ -100,21 +100,29 @@ class Encoding(_TcnnModule):
         super().__init__(native, n_input_dims, native.n_output_dims, seed)
 
 
-class Network(torch.nn.Module):
-    """tinycudann.Network (modules.py:248-268), forward only: fp32 inputs through the Identity encoding -> fp32 outputs.
-    The parameters are an fp32 nn.Parameter like the reference's; no autograd through this module (inference / evaluation)."""
+class _NetworkAdapter:
+    """The stand-alone network behind the same fwd / bwd / initial_params surface as the other native modules (fp32 inputs through the
+    Identity encoding, cpp::create_network, src/cpp_api.cu:160-162)."""
+
+    def __init__(self, native):
+        self.native = native
+
+    def initial_params(self, seed):
+        return self.native.initial_params(seed)
+
+    def fwd(self, inputs, params):
+        return self.native.module_inference(inputs, params)
+
+    def bwd(self, inputs, params, dL_doutput, output=None, want_input_grad=False, want_param_grad=True):
+        dinput, grads = self.native.module_backward(inputs, dL_doutput, params, want_input_grad=want_input_grad, want_param_grad=want_param_grad)
+        return (grads, dinput) if want_input_grad else grads
+
+
+class Network(_TcnnModule):
+    """tinycudann.Network (modules.py:248-268): fp32 inputs through the Identity encoding -> fp16 outputs, with autograd w.r.t. the
+    parameters and the inputs (dgrad chain + weight-gradient kernels of the stand-alone network)."""
 
     def __init__(self, n_input_dims, n_output_dims, network_config, seed=1337):
-        super().__init__()
-        self.native_tcnn_module = _NativeNetwork(n_input_dims, n_output_dims, network_config)
-        self.n_input_dims, self.n_output_dims, self.seed = n_input_dims, n_output_dims, seed
-        self.params = torch.nn.Parameter(self.native_tcnn_module.initial_params(seed), requires_grad=False)
-
-    @torch.no_grad()
-    def forward(self, x):
-        batch = x.shape[0]
-        padded = (batch + _BATCH_GRANULARITY - 1) // _BATCH_GRANULARITY * _BATCH_GRANULARITY
-        x = x.to(torch.float32)
-        if padded != batch:
-            x = torch.nn.functional.pad(x, [0, 0, 0, padded - batch])
-        return self.native_tcnn_module.inference(x.contiguous(), self.params.to(torch.float16).contiguous())[:batch]
+        self.network_config = network_config
+        native = _NativeNetwork(n_input_dims, n_output_dims, network_config)
+        super().__init__(_NetworkAdapter(native), n_input_dims, n_output_dims, seed)
