@@ -24,10 +24,6 @@ struct FusedStepParams {
 	uint32_t output_activation;    // applied to the network output before the loss
 	uint32_t n_out;                // logical outputs (<= 16)
 	uint32_t n_mlp_params;         // grid params start here in the parameter / gradient buffers
-	// Dense coarse levels scatter into one of n_replicas private copies of their gradient entries (grid_kernels.h plan_grid_scatter);
-	// levels with offset + size <= replica_entries are replicated. n_replicas <= 1: off.
-	__half* replica_scratch;
-	uint32_t n_replicas, replica_entries;
 	uint32_t enc_identity;         // 1: Identity encoding instead of the grid (features = x * scale + offset, padding features = 1)
 	float identity_scale, identity_offset;
 	uint32_t loss_type;            // LossType

@@ -208,9 +208,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) fused_ws_kernel(const FusedStep
 				const uint32_t feat = level * F;
 				asm volatile("ld.shared.b32 %0, [%1];" : "=r"(gbits) : "r"(park_addr(gp, row, feat >> 3) + (feat & 7u) * 2u));
 				const __half2 grad = *reinterpret_cast<const __half2*>(&gbits);
-				__half* __restrict__ level_base = grad_table;
-				if (p.n_replicas > 1 && lv.offset + lv.size <= p.replica_entries) level_base = p.replica_scratch + (size_t)(blockIdx.x % p.n_replicas) * p.replica_entries * F;
-				uint32_t* __restrict__ ltab = reinterpret_cast<uint32_t*>(level_base + (size_t)lv.offset * F);
+				uint32_t* __restrict__ ltab = reinterpret_cast<uint32_t*>(grad_table + (size_t)lv.offset * F);
 #pragma unroll
 				for (uint32_t pr = 0; pr < (1u << (D - 1)); ++pr) {
 					// (GRAD_T)weight * grad -> __hmul2, then atomic f16x2 add (grid.h:252-255, vec.h:328-336)

@@ -295,13 +295,6 @@ cudaError_t launch_grid_backward(cudaStream_t stream, const GridKernelArgs& a, c
 	return err;
 }
 
-cudaError_t launch_replica_reduce(cudaStream_t stream, uint32_t replica_entries, uint32_t n_features_per_level, uint32_t n_replicas, __half* scratch, __half* grad_table) {
-	const uint32_t n_words = replica_entries * n_features_per_level / 2;
-	if (n_words == 0 || n_replicas < 2) return cudaSuccess;
-	replica_reduce_kernel<<<(n_words + 255) / 256, 256, 0, stream>>>(n_words, n_replicas, reinterpret_cast<uint32_t*>(scratch), reinterpret_cast<uint32_t*>(grad_table));
-	return cudaGetLastError();
-}
-
 GridScatterPlan plan_grid_scatter(const LevelInfo* levels, uint32_t n_levels, uint32_t F, uint32_t D, uint32_t n_elements) {
 	GridScatterPlan plan;
 	if (F < 2 || n_levels == 0 || n_elements < 16384) return plan;

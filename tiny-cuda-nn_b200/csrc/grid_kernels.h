@@ -32,8 +32,6 @@ struct GridScatterPlan {
 	uint32_t replica_entries = 0;
 	size_t scratch_halfs = 0;  // n_replicas * replica_entries * F
 };
-// grad_table[levels below replica_entries] = sum of the copies (fp32), copies re-armed to zero
-cudaError_t launch_replica_reduce(cudaStream_t stream, uint32_t replica_entries, uint32_t n_features_per_level, uint32_t n_replicas, __half* scratch, __half* grad_table);
 GridScatterPlan plan_grid_scatter(const LevelInfo* levels_host, uint32_t n_levels, uint32_t n_features_per_level, uint32_t n_pos_dims, uint32_t n_elements);
 
 // encoded [n][row_stride] fp16 (row = sample; columns level * F + f; the pad_cols columns behind them are zeroed)        grid.h:49-169

@@ -43,11 +43,6 @@ using namespace fused;
 namespace {
 
 constexpr uint32_t MLPF_MAX_STAGES = 32;
-// 128-wide layers: issue every layer as two N = 64 halves with their own commit, so that the epilogue group of columns 0..63 starts
-// while the tensor pipe still works on columns 64..127 (measured A/B: scripts/bench_mlp.py against a -DMLPF_NSPLIT=0/1 build)
-#ifndef MLPF_NSPLIT
-#define MLPF_NSPLIT 0
-#endif
 
 template <uint32_t W>
 struct MlpCfg {
@@ -165,8 +160,10 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 			mbar_init(bar_w_full + 8 * i, 1);
 			mbar_init(bar_w_free + 8 * i, C::SLOTS);
 		}
-		for (uint32_t s = 0; s < C::SLOTS; ++s) mbar_init(bar_a_ready + 8 * s, C::SLOT_WARPS);
-		for (uint32_t i = 0; i < C::SLOTS * C::GROUPS; ++i) mbar_init(bar_acc_ready + 8 * i, 1);  // one per (slot, epilogue group)
+		for (uint32_t s = 0; s < C::SLOTS; ++s) {
+			mbar_init(bar_a_ready + 8 * s, C::SLOT_WARPS);
+			mbar_init(bar_acc_ready + 8 * s, 1);
+		}
 		fence_mbar_init();
 	}
 	if (warp == C::EPI_WARPS) {
@@ -252,29 +249,14 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 						const uint32_t ksteps = (l == 0 ? first_w : W) / 16;
 						const uint32_t n_cols = l == NH ? last_w : W;
 						const uint32_t idesc = umma_idesc_f16(128, n_cols, 0, BWD ? 1 : 0);
-						if (MLPF_NSPLIT && C::GROUPS == 2 && n_cols == 128) {
-							const uint32_t idesc_half = umma_idesc_f16(128, 64, 0, BWD ? 1 : 0);
-#pragma unroll 1
-							for (uint32_t h = 0; h < 2; ++h) {
-								for (uint32_t j = 0; j < ksteps; ++j) {
-									// output columns 64 h .. 64 h + 63: forward = rows 64 h .. of every K box (8 192 bytes further), backward = box h
-									const uint64_t b_desc = BWD ? umma_desc_sw128(b_smem + j * 2048u + h * C::KBLOCK_BYTES, C::KBLOCK_BYTES, 1024u)
-									                            : umma_desc_sw128(b_smem + (j >> 2) * C::KBLOCK_BYTES + (j & 3u) * 32u + h * 8192u, 16u, 1024u);
-									umma_f16_ts(d_tmem + h * 64u, a_tmem + j * 8u, b_desc, idesc_half, j > 0);
-								}
-								umma_commit(bar_acc_ready + 8 * (s * C::GROUPS + h));
-							}
-						} else {
-							for (uint32_t j = 0; j < ksteps; ++j) {
-								// forward: stage = [N rows][64 K] boxes, K-major; backward: the same boxes are [K rows][64 N], MN-major
-								// (16 K-rows = 2 048 bytes per step, the next 64 N-columns one box further)
-								const uint64_t b_desc = BWD ? umma_desc_sw128(b_smem + j * 2048u, C::KBLOCK_BYTES, 1024u)
-								                            : umma_desc_sw128(b_smem + (j >> 2) * C::KBLOCK_BYTES + (j & 3u) * 32u, 16u, 1024u);
-								umma_f16_ts(d_tmem, a_tmem + j * 8u, b_desc, idesc, j > 0);
-							}
-#pragma unroll
-							for (uint32_t g = 0; g < C::GROUPS; ++g) umma_commit(bar_acc_ready + 8 * (s * C::GROUPS + g));
+						for (uint32_t j = 0; j < ksteps; ++j) {
+							// forward: stage = [N rows][64 K] boxes, K-major; backward: the same boxes are [K rows][64 N], MN-major
+							// (16 K-rows = 2 048 bytes per step, the next 64 N-columns one box further)
+							const uint64_t b_desc = BWD ? umma_desc_sw128(b_smem + j * 2048u, C::KBLOCK_BYTES, 1024u)
+							                            : umma_desc_sw128(b_smem + (j >> 2) * C::KBLOCK_BYTES + (j & 3u) * 32u, 16u, 1024u);
+							umma_f16_ts(d_tmem, a_tmem + j * 8u, b_desc, idesc, j > 0);
 						}
+						umma_commit(bar_acc_ready + 8 * s);
 						if (!resident) umma_commit(bar_w_free + 8 * stage);
 					}
 					__syncwarp();
@@ -415,7 +397,7 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 				};
 				const uint32_t ev = (j / C::SLOTS) * n_layers + l;
 				if (stamp) MLPF_STAMP(1 + s, ev, 0);
-				mbar_wait(bar_acc_ready + 8 * (s * C::GROUPS + grp), acc_par);
+				mbar_wait(bar_acc_ready + 8 * s, acc_par);
 				acc_par ^= 1u;
 				tc_fence_after_sync();
 				if (stamp) MLPF_STAMP(1 + s, ev, 1);

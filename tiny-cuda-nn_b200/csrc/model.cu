@@ -175,7 +175,6 @@ struct Model {
 	DeviceBuffer<float> g_grid_tmp;  // n_features_per_level == 1: fp32 scatter target (grid.h:858-894)
 	DeviceBuffer<__half> g_replicas; // private copies of the coarse levels' gradients (grid_kernels.h plan_grid_scatter)
 	int grid_replicas_override = -1; // tcnnb_debug_set("grid_replicas", n): experiments (0 / 1 = off)
-	int fused_replicas = 0;          // tcnnb_debug_set("fused_replicas", n): the same for the dense levels inside the fused kernel (0 = off)
 
 	// spatial binning scratch (binning.cu): sorted copies of the batch + permutation
 	bool binning = true;  // tcnnb_debug_set("binning", 0) (tests: binned and unbinned steps must touch the same entries)
@@ -861,36 +860,9 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
 	m.prof_mark(stream);
 	if (targets_ready) TCNNB_CUDA_CHECK(cudaStreamWaitEvent(stream, targets_ready, 0));
 	m.wait_pending(stream);  // e.g. the all-gather of the previous data-parallel step: binning above did not need the parameters
-	// experiment (tcnnb_debug_set("fused_replicas", n)): the dense coarse levels scatter into private copies, summed by a small kernel
-	uint32_t fused_replicas = 0, fused_replica_entries = 0;
-	if (m.fused_replicas > 1 && !m.enc_identity && m.grid.n_levels) {
-		const double corners = (double)batch * (double)(1u << m.grid.n_pos_dims);
-		uint32_t entries = 0;
-		for (uint32_t l = 0; l < m.grid.n_levels; ++l) {
-			const uint32_t size = m.grid.offsets[l + 1] - m.grid.offsets[l];
-			if (corners / (double)size <= 64.0) break;
-			entries += size;
-		}
-		if (entries) {
-			fused_replicas = (uint32_t)m.fused_replicas;
-			fused_replica_entries = entries;
-			const size_t need = (size_t)fused_replicas * entries * m.grid.n_features_per_level;
-			if (m.g_replicas.n < need) {
-				m.g_replicas.resize(need);
-				m.g_replicas.zero(stream);
-			}
-			p.replica_scratch = m.g_replicas.ptr;
-			p.n_replicas = fused_replicas;
-			p.replica_entries = entries;
-		}
-	}
 	// one persistent 640-thread CTA per SM (fused_ws.cu)
 	TCNNB_CUDA_CHECK(launch_fused_ws(p, m.grid.n_pos_dims, true, std::min(batch / TILE_M, (uint32_t)m.n_sms), stream));
 	++g_kernel_launches;
-	if (fused_replicas > 1) {
-		TCNNB_CUDA_CHECK(launch_replica_reduce(stream, fused_replica_entries, m.grid.n_features_per_level, fused_replicas, m.g_replicas.ptr, grid_grads));
-		++g_kernel_launches;
-	}
 	m.last_stream = stream;
 	m.prof_mark(stream);
 	m.mlp_grads_in_accum = true;
@@ -1721,8 +1693,7 @@ int tcnnb_debug_set(tcnnb_model* m, const char* key, int value) {
 	TCNNB_API_BEGIN
 	const std::string k = key ? key : "";
 	if (k == "binning") m->impl.binning = value != 0;
-	else if (k == "grid_replicas") m->impl.grid_replicas_override = value;
-	else if (k == "fused_replicas") m->impl.fused_replicas = value;  // general path: copies of the coarse levels' gradient (-1 = automatic)
+	else if (k == "grid_replicas") m->impl.grid_replicas_override = value;  // general path: copies of the coarse levels' gradient (-1 = automatic)
 	else throw std::runtime_error("tcnnb_debug_set: unknown key '" + k + "'");
 	TCNNB_API_END
 }
