@@ -9,7 +9,9 @@
 //                                               (fp16 pairs; fp32 scratch + cast when F == 1, grid.h:858-894)
 //   dy_dx + kernel_grid_backward_input  grid.h:170-212,322-350  summed over features in feature order, fp32
 // Index arithmetic is shared with the fused kernel (grid_device.cuh) and bit-exact with the reference.
-// HBM/L2-bound scattered 2..16-byte accesses; one block row per level keeps a level's table hot in L2 like the reference (grid.h:769-771).
+// HBM/L2-bound scattered 2..16-byte accesses. Thread <-> (sample, level) with the level fastest (the reference runs one block row per
+// level to keep a level's table hot in a small L2, grid.h:769-771; the whole table fits B200's L2, and level-fastest makes the
+// feature-row accesses whole sectors).
 #include "grid_kernels.h"
 
 #include "grid_device.cuh"
@@ -77,9 +79,12 @@ __device__ __forceinline__ float active_levels(const GridKernelArgs& a) {
 
 template <uint32_t D, uint32_t F>
 __global__ void grid_forward_kernel(const GridKernelArgs a, const __half* __restrict__ table, __half* __restrict__ encoded) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	// thread <-> (sample, level), LEVEL fastest: the lanes of a warp write (read, in the backward kernel) consecutive columns of a
+	// few rows -- whole 32-byte sectors -- instead of one column of 32 different rows
+	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t i = (uint32_t)(t / a.n_levels);
 	if (i >= a.n_elements) return;
-	const uint32_t level = blockIdx.y;
+	const uint32_t level = (uint32_t)(t - (uint64_t)i * a.n_levels);
 	__half* row = encoded + (size_t)i * a.row_stride;
 	if (level == 0) {  // padding columns are zero (grid.h:757-766)
 		for (uint32_t c = a.n_levels * F; c < a.n_levels * F + a.pad_cols; ++c) row[c] = __float2half_rn(0.0f);
@@ -117,9 +122,10 @@ __global__ void grid_forward_kernel(const GridKernelArgs a, const __half* __rest
 
 template <uint32_t D, uint32_t F>
 __global__ void grid_backward_kernel(const GridKernelArgs a, const __half* __restrict__ dL_dy, __half* __restrict__ grad_table, float* __restrict__ grad_fp32) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t i = (uint32_t)(t / a.n_levels);
 	if (i >= a.n_elements) return;
-	const uint32_t level = blockIdx.y;
+	const uint32_t level = (uint32_t)(t - (uint64_t)i * a.n_levels);
 	if ((float)level > active_levels(a) + 1e-3f) return;  // grid.h:242 (strict, unlike the forward's >=)
 	const LevelInfo lv = a.levels_dev[level];
 	float x[D];
@@ -265,7 +271,9 @@ cudaError_t dispatch(const GridKernelArgs& a, Fn&& fn) {
 cudaError_t launch_grid_forward(cudaStream_t stream, const GridKernelArgs& a, const __half* table, __half* encoded) {
 	if (!args_ok(a) || !table || !encoded) return cudaErrorInvalidValue;
 	if (a.n_elements == 0) return cudaSuccess;
-	const dim3 grid((a.n_elements + 255) / 256, a.n_levels);
+	const uint64_t n_threads = (uint64_t)a.n_elements * a.n_levels;
+	if ((n_threads + 255) / 256 > 0x7FFFFFFFull) return cudaErrorInvalidValue;
+	const dim3 grid((uint32_t)((n_threads + 255) / 256));
 	return dispatch(a, [&](auto d, auto f) {
 		grid_forward_kernel<decltype(d)::value, decltype(f)::value><<<grid, 256, 0, stream>>>(a, table, encoded);
 		return cudaGetLastError();
@@ -276,7 +284,9 @@ cudaError_t launch_grid_backward(cudaStream_t stream, const GridKernelArgs& a, c
 	if (!args_ok(a) || !dL_dy || !grad_table) return cudaErrorInvalidValue;
 	if (a.n_features_per_level == 1 && !tmp_fp32) return cudaErrorInvalidValue;
 	if (a.n_elements == 0) return cudaSuccess;
-	const dim3 grid((a.n_elements + 255) / 256, a.n_levels);
+	const uint64_t n_threads = (uint64_t)a.n_elements * a.n_levels;
+	if ((n_threads + 255) / 256 > 0x7FFFFFFFull) return cudaErrorInvalidValue;
+	const dim3 grid((uint32_t)((n_threads + 255) / 256));
 	cudaError_t err = dispatch(a, [&](auto d, auto f) {
 		grid_backward_kernel<decltype(d)::value, decltype(f)::value><<<grid, 256, 0, stream>>>(a, dL_dy, grad_table, tmp_fp32);
 		return cudaGetLastError();

@@ -347,11 +347,26 @@ mlp_forward_kernel(const MlpKernelParams kp, const __grid_constant__ CUtensorMap
 
 			for (uint32_t l = 0; l < n_layers; ++l) {
 				// the next tile's input travels while the last layer computes
-				if (l == n_layers - 1 && j + C::SLOTS < n_my) load_input(blockIdx.x + (j + C::SLOTS) * gridDim.x);
+				if (l == n_layers - 1 && j + C::SLOTS < n_my) {
+					load_input(blockIdx.x + (j + C::SLOTS) * gridDim.x);
+					if (BWD && l8 == 0) {  // ... and the forward activations its first step will multiply with
+						const size_t next_row0 = (size_t)(blockIdx.x + (j + C::SLOTS) * gridDim.x) * TILE_M + wq * 32;
+						const __half* nxt = p.hidden_in + ((size_t)(NH - 1) * p.batch_size + next_row0 + g8 * 8) * W + col0;
+#pragma unroll
+						for (uint32_t jj = 0; jj < 8; ++jj) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t)jj * W));
+					}
+				}
 				// backward: the forward pass's activations of the layer this step lands on (hidden layer NH - 1 - l), fetched BEFORE the
 				// wait so that the load travels while the MMA runs. ReLU only needs the signs: two bits per fp16 pair.
 				constexpr uint32_t FWD_WORDS = BWD ? (GENERIC_ACT ? C::GROUP_COLS / 2 : 2) : 1;
 				uint32_t fwd[FWD_WORDS];
+				if (BWD && l + 1 < NH && l8 == 0) {
+					// The rows the NEXT step needs are pulled into L2 now (no registers to spare for a deeper register prefetch: the kernel sits at
+					// the 96-register cap): by the time they are loaded they cost an L2 hit instead of a DRAM round trip in front of the epilogue.
+					const __half* nxt = p.hidden_in + ((size_t)(NH - 2 - l) * p.batch_size + tile_row0 + g8 * 8) * W + col0;
+#pragma unroll
+					for (uint32_t jj = 0; jj < 8; ++jj) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t)jj * W));
+				}
 				if (BWD && l < NH) {
 					uint4 hv[C::GROUP_COLS / 8];
 					if (C::GROUP_COLS == 64) {
