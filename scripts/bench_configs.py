@@ -52,7 +52,7 @@ for _c in CONFIGS.values():
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="headline,image_w128,image_w64,identity_cutlass,hash3d_w128,f4_l8,d4,mlp_w128_h4,mlp_w64_h4")
+    ap.add_argument("--configs", default="headline,image_w128,image_w64,identity_cutlass,hash3d_w128,f4_l8,d4")  # mlp_*: the harness builds 128-D targets on one host thread (minutes)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--reference", action="store_true")

@@ -702,8 +702,9 @@ static void general_backward_pass(Model& m, cudaStream_t stream, uint32_t batch,
 	m.prof_mark(stream);  // (no binning pass on this path)
 	m.wait_pending(stream);
 	grow(m.g_out, (size_t)batch * mlp.padded_out_width);
-	general_forward(m, stream, batch, x, params, m.taps.output ? (__half*)m.taps.output : m.g_out.ptr, nullptr, true);
-	const __half* out = m.taps.output ? (const __half*)m.taps.output : m.g_out.ptr;
+	__half* const out_rows = (m.taps.output && mlp.padded_out_width == 16) ? (__half*)m.taps.output : m.g_out.ptr;  // (the test tap is 16 columns wide)
+	general_forward(m, stream, batch, x, params, out_rows, nullptr, true);
+	const __half* out = out_rows;
 
 	MlpBackwardArgs a{};
 	a.width = mlp.width;
