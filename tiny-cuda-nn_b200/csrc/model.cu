@@ -168,6 +168,8 @@ struct Model {
 	// inputs, Nearest interpolation, wider encodings / outputs -- run as encoding kernel -> stand-alone MLP kernels -> encoding backward
 	// kernel, with the activations of one batch in HBM (the reference's own structure, object.h / network_with_input_encoding.h).
 	bool general = false;
+	bool force_general = false;  // tcnnb_debug_set("general", 1): run the general path although the fused kernel covers the configuration
+	bool use_general() const { return general || force_general; }
 	bool plan_only = false;      // an encoding other than one grid / Identity (Composite, Frequency, OneBlob, ...): no fused kernel at all
 	EncodingPlan plan;           // segment table of the encoding (general path)
 	std::string general_reason;  // which limit of the fused kernel sent this configuration here (hyperparams / diagnostics)
@@ -462,7 +464,9 @@ static void build_model(Model& m, uint32_t n_in, uint32_t n_out, const json::Val
 	// ---- per-level scales, evaluated on the device like the reference's kernels (common_device.h:886-891)
 	m.level_scales_dev.resize(128);
 	if (!m.enc_identity && !m.plan_only) evaluate_level_scales(m.grid, m.level_scales_dev.ptr);
-	if (m.general && !m.plan_only) build_encoding_plan(m.plan, n_in, enc_cfg, alignment, m.level_scales_dev.ptr);  // one grid / Identity on the general path
+	// one grid / Identity: the segment table of the general path is built for every configuration, so that the general path can run what
+	// the fused kernel also covers (tests: both paths must agree; tcnnb_debug_set("general", 1))
+	if (!m.plan_only) build_encoding_plan(m.plan, n_in, enc_cfg, alignment, m.level_scales_dev.ptr);
 
 	// ---- parameter buffers (trainer.h:69-87,489-503)
 	m.n_params = (size_t)mlp.n_params + m.grid.n_params;
@@ -807,7 +811,7 @@ static void training_step(Model& m, cudaStream_t stream, uint32_t batch, uint32_
                           const ModuleIO* io = nullptr) {
 	check_batch(batch);
 	if (!io && m.module_only) throw std::runtime_error("this handle was created with tcnnb_module_create: use the tcnnb_module_* calls.");
-	if (m.general) {
+	if (m.use_general()) {
 		if (io) throw std::runtime_error("internal: the module tier of the general path does not come through here");
 		if (targets_ready) TCNNB_CUDA_CHECK(cudaStreamWaitEvent(stream, targets_ready, 0));
 		general_backward_pass(m, stream, batch, loss_batch, x, y, m.params_fp16, m.grads_fp16, nullptr, nullptr, true);
@@ -951,7 +955,7 @@ static void inference(Model& m, cudaStream_t stream, uint32_t batch, const float
 	check_batch(batch);
 	if (m.module_only) throw std::runtime_error("this handle was created with tcnnb_module_create: use the tcnnb_module_* calls.");
 	m.wait_pending(stream);
-	if (m.general) {
+	if (m.use_general()) {
 		general_forward(m, stream, batch, x, m.inference_params(), nullptr, out, false);
 		return;
 	}
@@ -975,7 +979,7 @@ static void module_forward(Model& m, cudaStream_t stream, uint32_t n, const floa
 	check_batch(n);
 	check_module_ptr(params, "params");
 	check_module_ptr(output, "output");
-	if (m.general) {
+	if (m.use_general()) {
 		general_forward(m, stream, n, x, (const __half*)params, (__half*)output, nullptr, false);
 		return;
 	}
@@ -993,7 +997,7 @@ static void module_backward(Model& m, cudaStream_t stream, uint32_t n, float* dL
 	if (!dL_dparams && !dL_dinput) return;  // nothing to compute (GradientMode::Ignore)
 	check_module_ptr(params, "params");
 	check_module_ptr(dL_doutput, "dL_doutput");
-	if (m.general) {
+	if (m.use_general()) {
 		check_batch(n);
 		if (dL_dparams) check_module_ptr(dL_dparams, "dL_dparams");
 		general_backward_pass(m, stream, n, n, x, nullptr, (const __half*)params, (__half*)dL_dparams, (const __half*)dL_doutput, dL_dinput, dL_dparams != nullptr);
@@ -1694,7 +1698,22 @@ int tcnnb_debug_set(tcnnb_model* m, const char* key, int value) {
 	TCNNB_API_BEGIN
 	const std::string k = key ? key : "";
 	if (k == "binning") m->impl.binning = value != 0;
-	else if (k == "grid_replicas") m->impl.grid_replicas_override = value;  // general path: copies of the coarse levels' gradient (-1 = automatic)
+	else if (k == "grid_replicas") m->impl.grid_replicas_override = value;
+	else if (k == "general") {
+		// the stand-alone kernels have their own limits (e.g. dL/d(encoded) wider than the layers): only switch when they cover the configuration
+		if (value && !m->impl.general) {
+			MlpBackwardArgs probe{};
+			probe.width = m->impl.mlp.width;
+			probe.in_width = m->impl.mlp.in_width;
+			probe.out_width = m->impl.mlp.padded_out_width;
+			probe.n_hidden_layers = m->impl.mlp.n_hidden_layers;
+			probe.batch_size = 256;
+			probe.dL_dinput = m->impl.grid.n_params == 0 ? nullptr : (__half*)16;
+			const char* why_not = nullptr;
+			if (!mlp_backward_supported(probe, &why_not)) throw std::runtime_error(std::string("tcnnb_debug_set(general): ") + why_not);
+		}
+		m->impl.force_general = value != 0;
+	}  // general path: copies of the coarse levels' gradient (-1 = automatic)
 	else throw std::runtime_error("tcnnb_debug_set: unknown key '" + k + "'");
 	TCNNB_API_END
 }
