@@ -59,7 +59,6 @@ struct MlpCfg {
 	static constexpr uint32_t GROUP_COLS = W / GROUPS;         // accumulator columns a thread converts per hidden layer (<= 64)
 	static constexpr uint32_t PIECE = GROUP_COLS < 32 ? GROUP_COLS : 32;  // ... in pieces of one tcgen05.ld
 	static constexpr uint32_t N_PIECES = GROUP_COLS / PIECE;
-	static constexpr uint32_t MAX_IN = 64 * KBLOCKS;           // widest first-layer input a stage holds
 };
 
 struct MlpKernelParams {
@@ -75,16 +74,12 @@ template <>
 __device__ __forceinline__ void tmem_ld_n<16>(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x32b_x16(taddr, r); }
 template <>
 __device__ __forceinline__ void tmem_ld_n<32>(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32b_x32(taddr, r); }
-template <>
-__device__ __forceinline__ void tmem_ld_n<64>(uint32_t taddr, uint32_t (&r)[64]) { tmem_ld_32x32b_x64(taddr, r); }
 template <uint32_t N>
 __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t (&r)[N]);
 template <>
 __device__ __forceinline__ void tmem_st_n<8>(uint32_t taddr, const uint32_t (&r)[8]) { tmem_st_32x32b_x8(taddr, r); }
 template <>
 __device__ __forceinline__ void tmem_st_n<16>(uint32_t taddr, const uint32_t (&r)[16]) { tmem_st_32x32b_x16(taddr, r); }
-template <>
-__device__ __forceinline__ void tmem_st_n<32>(uint32_t taddr, const uint32_t (&r)[32]) { tmem_st_32x32b_x32(taddr, r); }
 
 // 8 x 8 transpose of 128-bit elements across every aligned group of 8 lanes (butterfly over lane bits 2, 1, 0): on return a[j] of
 // lane l8 holds what a[l8] of lane j held. The network input and output are rows of up to 256 bytes per sample and a thread owns a

@@ -31,7 +31,6 @@ namespace {
 template <uint32_t W>
 struct WgradCfg {
 	static constexpr uint32_t M = W == 128 ? 128 : 64;          // rows of an accumulator (narrower layers are zero-padded by TMA)
-	static constexpr uint32_t ACC_COLS = W == 128 ? 128 : 64;   // TMEM columns per matrix
 	static constexpr uint32_t KB = (W + 63) / 64;               // 64-column boxes per operand tile
 	static constexpr uint32_t OPERAND_BYTES = KB * TILE_BYTES;
 	static constexpr uint32_t STAGE_BYTES = 2 * OPERAND_BYTES;  // [A | B]
