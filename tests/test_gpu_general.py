@@ -273,3 +273,44 @@ def test_fused_and_general_paths_agree(torch_cuda, name):
         model.trainer.training_step(xd, yd)
         losses.append(model.trainer.loss())
     assert losses[-1] < losses[0]
+
+
+def test_general_path_full_size_properties(torch_cuda):
+    """BASELINE.json configs[2] (2-D HashGrid + 128 x 4, the model of samples/mlp_learning_an_image.cu) at the benchmarked batch 2^18 on the
+    general path -- 13.8 tiles per CTA in the network kernels, replicated scatter of the coarse grid levels, one packed weight-gradient
+    launch: batch linearity (gradients of the batch == sum over its two halves normalised over the whole batch), zero-gradient entries
+    skipped by Adam, the loss decreases, host-buffer step == device step."""
+    torch = torch_cuda
+    import tcnn_b200
+
+    n_in, n_out, _, cfg = GENERAL_CONFIGS["image_w128"]
+    B = 1 << 18
+    model = tcnn_b200.create_from_config(n_in, n_out, cfg)
+    x, y = make_batch(n_in, n_out, B)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    model.trainer.training_step(xd, yd, run_optimizer=False)
+    full_loss = model.trainer.loss()
+    g_full = model.trainer.param_gradients().float().clone()
+    h = B // 2
+    model.trainer.training_step_shard(xd[:h], yd[:h], B)
+    la, ga = model.trainer.loss(), model.trainer.param_gradients().float().clone()
+    model.trainer.training_step_shard(xd[h:], yd[h:], B)
+    lb, gb = model.trainer.loss(), model.trainer.param_gradients().float().clone()
+    assert abs((la + lb) - full_loss) <= 1e-3 * full_loss
+    gsum = ga + gb
+    nz = g_full != 0
+    assert ((gsum != 0) == nz).float().mean() > 0.999
+    assert rae(gsum[nz].cpu().numpy(), g_full[nz].cpu().numpy(), 99.0) < 2e-2
+    n_mlp = model.n_mlp_params
+    p_before = model.trainer.params_full_precision().clone()
+    losses = []
+    for _ in range(6):
+        model.trainer.training_step(xd, yd)
+        losses.append(model.trainer.loss())
+    p_after = model.trainer.params_full_precision()
+    assert losses[-1] < 0.5 * losses[0] and torch.isfinite(p_after).all()
+    assert (p_before[:n_mlp] != p_after[:n_mlp]).float().mean() > 0.99
+    l_host = model.training_step_host(x, y)
+    assert np.isfinite(l_host) and l_host < losses[0]
+    out = model.network.inference(xd)
+    assert torch.isfinite(out).all() and out.shape == (B, n_out)
