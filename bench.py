@@ -51,41 +51,51 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md). NVML is initialised when the sampler is
+    created -- before the timed region -- so that even a region of a few milliseconds gets samples (one is taken synchronously on
+    entry and one on exit, the thread adds one per millisecond in between)."""
 
     def __init__(self, index=0):
         self.samples = []
         self.reasons = set()
         self.stop = threading.Event()
         self.index = index
+        self.nv = None
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            idx = index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")  # CUDA_VISIBLE_DEVICES-relative index -> NVML index
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[index])
+            self.handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            self.bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                         "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            self.nv = nv
+        except Exception:  # noqa: BLE001 -- no NVML binding: poll nvidia-smi (slow, a few samples per run)
+            self.nv = None
         self.thread = threading.Thread(target=self.run, daemon=True)
 
+    def sample_nvml(self):
+        nv = self.nv
+        self.samples.append((float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)), self.max_mhz))
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for n, b in self.bits.items():
+            if r & b:
+                self.reasons.add(n)
+
     def run(self):
-        try:
-            self.run_nvml()
-        except Exception:  # noqa: BLE001 -- no NVML binding: poll nvidia-smi (slow, a few samples per run)
+        if self.nv is None:
             self.run_smi()
-
-    def run_nvml(self):
-        import pynvml as nv
-
-        nv.nvmlInit()
-        # CUDA_VISIBLE_DEVICES-relative index -> NVML index
-        idx = self.index
-        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
-        if vis and all(t.strip().isdigit() for t in vis.split(",")):
-            idx = int(vis.split(",")[self.index])
-        h = nv.nvmlDeviceGetHandleByIndex(idx)
-        max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
-                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            return
         while not self.stop.is_set():
-            self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), max_mhz))
-            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-            for n, b in bits.items():
-                if r & b:
-                    self.reasons.add(n)
-            self.stop.wait(0.002)
+            try:
+                self.sample_nvml()
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop.wait(0.001)
 
     def run_smi(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -109,6 +119,11 @@ class ClockSampler:
         return self
 
     def __exit__(self, *a):
+        if self.nv is not None:
+            try:
+                self.sample_nvml()  # the GPU is still under load here: the caller synchronises after leaving the region
+            except Exception:  # noqa: BLE001
+                pass
         self.stop.set()
         self.thread.join(timeout=5)
 
